@@ -1,0 +1,149 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the LIVE reference modules.
+
+Run in the build container (needs /root/reference):   python -m oracle.gen_golden
+The reference has no golden vectors of its own, so these fixtures --
+outputs of the unmodified reference modules on seeded synthetic inputs/weights from
+``oracle/synth.py`` -- are what pins the CPU restatement (``oracle/restate.py``), which in
+turn is what the CUDA path is compared against on the GPU box.
+
+Full outputs are tens of MB, so each fixture stores a strided subsample of every output
+tensor plus whole-tensor statistics (sum, abs-sum, argmax histogram / checksum).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_loader, synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+STRIDE = 389  # prime, so the subsample walks every channel / anchor / row phase
+
+
+def summarize(name, t, out):
+    t = t.detach().to(torch.float32).contiguous()
+    flat = t.view(-1)
+    out[name + ".shape"] = np.asarray(t.shape, dtype=np.int64)
+    out[name + ".sub"] = flat[::STRIDE].numpy().copy()
+    out[name + ".sum"] = np.float64(flat.double().sum().item())
+    out[name + ".abssum"] = np.float64(flat.double().abs().sum().item())
+
+
+def argmax_checksum(cls):
+    """cls: [N, P, 2] -> per-map count of argmax==1 and a position-weighted checksum (int64)."""
+    am = cls.argmax(-1).to(torch.int64)
+    idx = torch.arange(am.shape[1], dtype=torch.int64) % 65521
+    return am.sum(1).numpy(), (am * idx).sum(1).numpy()
+
+
+def gen_v2vnet(tag, batch, seed, present=None, gnn_iter=3):
+    m = ref_loader.ref_v2vnet_det(gnn_iter_times=gnn_iter)
+    sd = synth.v2vnet_det_state(seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(batch, 5, seed, present=present)
+    with torch.no_grad():
+        r = m(bevs, trans, nat, batch_size=batch)
+    out = {"meta": np.asarray([batch, 5, seed, gnn_iter], dtype=np.int64)}
+    if present is not None:
+        out["present"] = np.asarray(present, dtype=np.int64)
+    summarize("loc", r["loc"], out)
+    summarize("cls", r["cls"], out)
+    out["cls.argmax_count"], out["cls.argmax_checksum"] = argmax_checksum(r["cls"])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+    print(tag, "loc.sum", out["loc.sum"], "cls.sum", out["cls.sum"])
+
+
+def gen_fafnet(tag, n, seed):
+    m = ref_loader.ref_fafnet(kd_flag=0)
+    sd = synth.fafnet_state(seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs = synth.make_bevs(n, seed)
+    with torch.no_grad():
+        r = m(bevs)
+    out = {"meta": np.asarray([n, seed], dtype=np.int64)}
+    summarize("loc", r["loc"], out)
+    summarize("cls", r["cls"], out)
+    out["cls.argmax_count"], out["cls.argmax_checksum"] = argmax_checksum(r["cls"])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+    print(tag, "loc.sum", out["loc.sum"])
+
+
+def gen_stages(tag, seed):
+    """Encoder layers, fused map and decoder output of the live V2VNet via forward hooks."""
+    m = ref_loader.ref_v2vnet_det()
+    sd = synth.v2vnet_det_state(seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(1, 5, seed)
+    cap = {}
+    m.u_encoder.register_forward_hook(lambda mod, i, o: cap.__setitem__("enc", [t.clone() for t in o]))
+    m.decoder.register_forward_hook(lambda mod, i, o: cap.__setitem__("dec", (i[3].clone(), o[0].clone())))
+    with torch.no_grad():
+        m(bevs, trans, nat, batch_size=1)
+    out = {"meta": np.asarray([1, 5, seed], dtype=np.int64)}
+    for i, t in enumerate(cap["enc"]):
+        summarize("enc%d" % i, t, out)
+    summarize("fused", cap["dec"][0], out)
+    summarize("x8", cap["dec"][1], out)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+    print(tag, "fused.sum", out["fused.sum"])
+
+
+def gen_warp(tag, seed):
+    """Full outputs of DetModelBase.feature_transformation on a small-channel map."""
+    ref_loader.install()
+    from coperception.models.det.base.DetModelBase import DetModelBase
+    g = torch.Generator().manual_seed(seed)
+    C = 8
+    local = torch.randn((2, 5, C, 32, 32), generator=g)
+    trans = synth.make_trans_matrices(2, 5, seed)
+    pairs = [(0, 1, 0), (0, 4, 2), (1, 0, 3), (1, 2, 2), (1, 3, 4)]  # (b, j, i)
+    outs = []
+    with torch.no_grad():
+        for b, j, i in pairs:
+            outs.append(DetModelBase.feature_transformation(b, j, i, local, None, None, (1, C, 32, 32), trans))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), local=local.numpy(), trans=trans.numpy(),
+                        pairs=np.asarray(pairs, dtype=np.int64), out=torch.stack(outs).numpy())
+    print(tag, "ok")
+
+
+def gen_convgru(tag, seed):
+    """Full output of the reference Conv2dGRU (zero hidden) on a small map."""
+    ref_loader.install()
+    import coperception.utils.convolutional_rnn as convrnn
+    C = 16
+    gru = convrnn.Conv2dGRU(in_channels=2 * C, out_channels=C, kernel_size=3, num_layers=1,
+                            bidirectional=False, dilation=1, stride=1)
+    g = torch.Generator().manual_seed(seed)
+    sd = {k: (torch.rand(v.shape, generator=g) - 0.5) * 0.5 for k, v in gru.state_dict().items()}
+    gru.load_state_dict(sd)
+    x = torch.randn((1, 1, 2 * C, 8, 8), generator=g)
+    with torch.no_grad():
+        y, _ = gru(x, None)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), x=x.numpy(), y=y.numpy(),
+                        **{"sd." + k: v.numpy() for k, v in sd.items()})
+    print(tag, "ok")
+
+
+def main():
+    if not ref_loader.available():
+        print("reference tree not available; golden fixtures can only be generated in the build container")
+        return 1
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen_warp("warp_small_seed3", 3)
+    gen_convgru("convgru_small_seed4", 4)
+    gen_fafnet("fafnet_n2_seed0", 2, 0)
+    gen_stages("v2vnet_det_stages_seed0", 0)
+    gen_v2vnet("v2vnet_det_A5B1_seed0", 1, 0)
+    gen_v2vnet("v2vnet_det_A5B2_seed1_present53", 2, 1, present=[5, 3])
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

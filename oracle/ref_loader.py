@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE ONLY -- import the LIVE reference modules from /root/reference.
+
+Only usable in the build container (the GPU box has no /root/reference).  Three shims,
+none of which touches reference files:
+  1. ``import coperception`` fails (CP/__init__.py:4 -> datasets -> shapely), so namespace
+     stubs for the packages are pre-seeded in ``sys.modules`` with ``__path__`` pointing into
+     the reference tree; leaf modules (models/det/V2VNet.py ...) then import cleanly.
+  2. ``collections.Iterable`` alias for CP/utils/convolutional_rnn/utils.py:10.
+  3. (seg When2Com_UNet only) ``.cuda()`` neutralised for CPU runs.
+"""
+from __future__ import annotations
+
+import collections
+import collections.abc
+import importlib
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("V2X_REFERENCE_ROOT", "/root/reference/coperception")
+CP = os.path.join(REF_ROOT, "coperception")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(CP, "models", "det"))
+
+
+def _stub(name, path):
+    m = types.ModuleType(name)
+    m.__path__ = [path]
+    m.__package__ = name
+    sys.modules[name] = m
+    return m
+
+
+def install():
+    """Make ``coperception.models.det.X`` importable from the reference tree.  Idempotent."""
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % CP)
+    if not hasattr(collections, "Iterable"):
+        collections.Iterable = collections.abc.Iterable  # shim 2
+    if getattr(sys.modules.get("coperception"), "_v2x_ref_stub", False):
+        return
+    for k in [k for k in sys.modules if k == "coperception" or k.startswith("coperception.")]:
+        del sys.modules[k]
+    root = _stub("coperception", CP)
+    root._v2x_ref_stub = True
+    for sub in ("models", "utils", "configs", "datasets"):
+        _stub("coperception." + sub, os.path.join(CP, sub))
+    _stub("coperception.models.det", os.path.join(CP, "models", "det"))
+    _stub("coperception.models.seg", os.path.join(CP, "models", "seg"))
+    # coperception.models.det.base is a real package whose __init__ only imports leaf modules
+    importlib.import_module("coperception.models.det.base")
+
+
+def uninstall():
+    for k in [k for k in sys.modules if k == "coperception" or k.startswith("coperception.")]:
+        del sys.modules[k]
+
+
+def ref_config():
+    install()
+    Config = importlib.import_module("coperception.configs.Config").Config
+    return Config("train", binary=True, only_det=True)
+
+
+def ref_v2vnet_det(gnn_iter_times=3, layer=3, layer_channel=256, num_agent=5, compress_level=0):
+    install()
+    V2VNet = importlib.import_module("coperception.models.det.V2VNet").V2VNet
+    return V2VNet(ref_config(), gnn_iter_times, layer, layer_channel, num_agent=num_agent,
+                  compress_level=compress_level)
+
+
+def ref_fafnet(num_agent=5, kd_flag=0):
+    install()
+    FaFNet = importlib.import_module("coperception.models.det.FaFNet").FaFNet
+    return FaFNet(ref_config(), layer=3, kd_flag=kd_flag, num_agent=num_agent)

@@ -1,0 +1,174 @@
+"""TEST INFRASTRUCTURE ONLY -- fp32 torch-CPU restatement of the reference hot path.
+
+A literal, functional (no nn.Module) restatement of coperception's detection forward,
+driven by a reference-format ``state_dict``.  It deliberately keeps the reference's
+structure -- the H flip around the fusion stage, the per-agent / per-round python loops,
+the ConvGRU conv over the all-zero hidden state, warps recomputed in every GNN round --
+because it doubles as the "reference CPU implementation" timed by ``bench.py``'s
+``cpu_baseline`` leg (kind = "port").  Pinned against the live reference modules through
+``tests/golden/*.npz`` (see ``oracle/gen_golden.py``); never imported by the product.
+
+Shorthand: CP/ = /root/reference/coperception/coperception/
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-5  # nn.BatchNorm2d default
+
+
+def _bn(x, sd, name):
+    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"],
+                        sd[name + ".weight"], sd[name + ".bias"], False, 0.0, EPS)
+
+
+def cbr(x, sd, p, conv, bn, stride=1):
+    """conv3x3(pad 1) + BN(eval) + ReLU  (CP/models/det/backbone/Backbone.py:102-136)."""
+    y = F.conv2d(x, sd[p + conv + ".weight"], sd[p + conv + ".bias"], stride=stride, padding=1)
+    return F.relu(_bn(y, sd, p + bn))
+
+
+def conv3d_111(x, sd, p, name):
+    """Conv3D 1x1x1 + BN3d + ReLU over a length-1 sequence (Backbone.py:280-300) == 1x1 conv2d."""
+    w = sd[p + name + ".conv3d.weight"]
+    y = F.conv2d(x, w.reshape(w.shape[0], w.shape[1], 1, 1), sd[p + name + ".conv3d.bias"])
+    return F.relu(_bn(y, sd, p + name + ".bn3d"))
+
+
+def encode(bevs, sd, p="u_encoder.", compress_level=0):
+    """Backbone.encode (Backbone.py:89-143).  bevs: [N,1,256,256,13] (the model permutes to
+    [N,1,13,256,256] first, V2VNet.py:51)."""
+    x = bevs.permute(0, 1, 4, 2, 3)
+    x = x.reshape(-1, x.size(-3), x.size(-2), x.size(-1)).to(torch.float)
+    x = cbr(x, sd, p, "conv_pre_1", "bn_pre_1")
+    x = cbr(x, sd, p, "conv_pre_2", "bn_pre_2")
+    x_1 = cbr(x, sd, p, "conv1_1", "bn1_1", stride=2)
+    x_1 = cbr(x_1, sd, p, "conv1_2", "bn1_2")
+    x_1 = conv3d_111(x_1, sd, p, "conv3d_1")
+    x_2 = cbr(x_1, sd, p, "conv2_1", "bn2_1", stride=2)
+    x_2 = cbr(x_2, sd, p, "conv2_2", "bn2_2")
+    x_2 = conv3d_111(x_2, sd, p, "conv3d_2")
+    x_3 = cbr(x_2, sd, p, "conv3_1", "bn3_1", stride=2)
+    x_3 = cbr(x_3, sd, p, "conv3_2", "bn3_2")
+    x_4 = cbr(x_3, sd, p, "conv4_1", "bn4_1", stride=2)
+    x_4 = cbr(x_4, sd, p, "conv4_2", "bn4_2")
+    if compress_level > 0:  # Backbone.py:139-141
+        y = F.conv2d(x_3, sd[p + "com_compresser.weight"], sd[p + "com_compresser.bias"])
+        x_3 = F.relu(_bn(y, sd, p + "bn_compress"))
+        y = F.conv2d(x_3, sd[p + "com_decompresser.weight"], sd[p + "com_decompresser.bias"])
+        x_3 = F.relu(_bn(y, sd, p + "bn_decompress"))
+    return [x, x_1, x_2, x_3, x_4]
+
+
+def decode(x, x_1, x_2, x_3, x_4, sd, p="decoder.", kd_flag=False):
+    """Backbone.decode (Backbone.py:145-242); nearest x2 upsample, cat((up, skip)), two CBRs.
+    The permute / adaptive_max_pool3d blocks are identities for seq=1."""
+    x_5 = cbr(torch.cat((F.interpolate(x_4, scale_factor=(2, 2)), x_3), 1), sd, p, "conv5_1", "bn5_1")
+    x_5 = cbr(x_5, sd, p, "conv5_2", "bn5_2")
+    x_6 = cbr(torch.cat((F.interpolate(x_5, scale_factor=(2, 2)), x_2), 1), sd, p, "conv6_1", "bn6_1")
+    x_6 = cbr(x_6, sd, p, "conv6_2", "bn6_2")
+    x_7 = cbr(torch.cat((F.interpolate(x_6, scale_factor=(2, 2)), x_1), 1), sd, p, "conv7_1", "bn7_1")
+    x_7 = cbr(x_7, sd, p, "conv7_2", "bn7_2")
+    x_8 = cbr(torch.cat((F.interpolate(x_7, scale_factor=(2, 2)), x), 1), sd, p, "conv8_1", "bn8_1")
+    res = cbr(x_8, sd, p, "conv8_2", "bn8_2")
+    return [res, x_7, x_6, x_5] if kd_flag else [res]
+
+
+def heads(x, sd):
+    """ClassificationHead / SingleRegressionHead + get_cls_loc_result (DetModelBase.py:226-351)."""
+    n = x.shape[0]
+    c = F.relu(_bn(F.conv2d(x, sd["classification.conv1.weight"], sd["classification.conv1.bias"], padding=1),
+                   sd, "classification.bn1"))
+    c = F.conv2d(c, sd["classification.conv2.weight"], sd["classification.conv2.bias"])
+    cls = c.permute(0, 2, 3, 1).contiguous().view(n, -1, 2)
+    r = F.relu(_bn(F.conv2d(x, sd["regression.box_prediction.0.weight"], sd["regression.box_prediction.0.bias"],
+                            padding=1), sd, "regression.box_prediction.1"))
+    r = F.conv2d(r, sd["regression.box_prediction.3.weight"], sd["regression.box_prediction.3.bias"])
+    r = r.permute(0, 2, 3, 1).contiguous()
+    loc = r.view(-1, r.size(1), r.size(2), 6, 1, 6)
+    return {"loc": loc, "cls": cls}
+
+
+def feature_transformation(local_com_mat, b, j, agent_idx, trans_matrices, size):
+    """DetModelBase.feature_transformation (DetModelBase.py:139-169): warp agent j's (H-flipped)
+    map into agent_idx's frame; theta = [R | -t * 4/128], affine_grid + grid_sample defaults
+    (bilinear, zeros padding, align_corners=False)."""
+    nb_agent = local_com_mat[b, j].unsqueeze(0)
+    tfm = trans_matrices[b, j, agent_idx]
+    M = torch.hstack((tfm[:2, :2], -tfm[:2, 3:4])).float().unsqueeze(0)
+    mask = torch.tensor([[[1, 1, 4 / 128], [1, 1, 4 / 128]]])
+    M = M * mask
+    grid = F.affine_grid(M, size=torch.Size(size), align_corners=False)
+    return F.grid_sample(nb_agent, grid, mode="bilinear", padding_mode="zeros", align_corners=False).squeeze(0)
+
+
+def convgru_zero_hidden(x, sd, p="convgru."):
+    """Conv2dGRU, one layer, one time step, hx=None -> zeros (module.py:171-211; GRUCell
+    functional.py:84-105; same-padding conv functional.py:261-301).  x: [1,Cin,H,W]."""
+    w_ih, w_hh = sd[p + "weight_ih_l0"], sd[p + "weight_hh_l0"]
+    b_ih, b_hh = sd[p + "bias_ih_l0"], sd[p + "bias_hh_l0"]
+    hidden = x.new_zeros(x.shape[0], w_hh.shape[1], x.shape[2], x.shape[3])
+    gi = F.conv2d(F.pad(x, (1, 1, 1, 1)), w_ih, b_ih)
+    gh = F.conv2d(F.pad(hidden, (1, 1, 1, 1)), w_hh, b_hh)  # executed by the reference although hidden == 0
+    i_r, i_i, i_n = gi.chunk(3, 1)
+    h_r, h_i, h_n = gh.chunk(3, 1)
+    r = torch.sigmoid(i_r + h_r)
+    z = torch.sigmoid(i_i + h_i)
+    n = torch.tanh(i_n + r * h_n)
+    return n + z * (hidden - n)
+
+
+def v2vnet_fuse(x_3, trans_matrices, num_agent_tensor, sd, batch_size, agent_num=5, gnn_iter=3,
+                return_mean=False):
+    """The GNN block of det V2VNet.forward (V2VNet.py:55-112) incl. the flips
+    (DetModelBase.py:71-92, 53-69).  x_3: [A*B,C,32,32] agent-major."""
+    c, h, w = x_3.shape[1:]
+    size = (1, c, h, w)
+    feat = torch.flip(x_3, (2,))
+    local = torch.stack([feat[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)  # [B,A,C,H,W]
+    upd = local.clone()
+    means = torch.zeros_like(local)
+    for b in range(batch_size):
+        na = int(num_agent_tensor[b, 0])
+        agent_feat = [local[b, i] for i in range(agent_num)]
+        for _ in range(gnn_iter):
+            new = []
+            for i in range(na):
+                nb = [feature_transformation(local, b, j, i, trans_matrices, size) for j in range(na) if j != i]
+                mean = torch.mean(torch.stack(nb), dim=0)  # self excluded (V2VNet.py:96-98)
+                means[b, i] = mean
+                cat = torch.cat([agent_feat[i], mean], 0).unsqueeze(0)
+                new.append(convgru_zero_hidden(cat, sd).squeeze(0))
+            agent_feat = new
+        for k in range(na):
+            upd[b, k] = agent_feat[k]
+    out = torch.flip(torch.cat([upd[:, i] for i in range(agent_num)], 0), (2,))
+    if return_mean:
+        m = torch.flip(torch.cat([means[:, i] for i in range(agent_num)], 0), (2,))
+        return out, m
+    return out
+
+
+def v2vnet_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=1, agent_num=5, gnn_iter=3,
+                       compress_level=0, stages=False):
+    """det V2VNet.forward (CP/models/det/V2VNet.py:47-120)."""
+    enc = encode(bevs, sd, "u_encoder.", compress_level)
+    fused = v2vnet_fuse(enc[3], trans_matrices, num_agent_tensor, sd, batch_size, agent_num, gnn_iter)
+    dec_in = list(enc)
+    dec_in[3] = fused
+    x8 = decode(*dec_in, sd, "decoder.")[0]
+    res = heads(x8, sd)
+    if stages:
+        res = dict(res, enc=enc, fused=fused, x8=x8)
+    return res
+
+
+def fafnet_forward(bevs, sd, compress_level=0, stages=False):
+    """FaFNet.forward with kd_flag=0 semantics (FaFNet.py:28-39, Backbone.py:245-257)."""
+    enc = encode(bevs, sd, "stpn.", compress_level)
+    dec = decode(*enc, sd, "stpn.", kd_flag=True)
+    res = heads(dec[0], sd)
+    if stages:
+        res = dict(res, enc=enc, dec=dec)
+    return res
