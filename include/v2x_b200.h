@@ -1,0 +1,148 @@
+/*
+ * v2x_b200.h -- C ABI of the sm_100a collaborative-perception hot path.
+ *
+ * The reference (ai4ce/V2X-Sim -> coperception) has no FFI: its hot path is a chain of ATen
+ * library calls made from python nn.Modules.  Each entry point below replaces one such call
+ * site (file:line under /root/reference/coperception/coperception/, "CP/"); the python modules
+ * in v2x-sim_b200/coperception/ keep the reference's nn.Module surface and call these through
+ * ctypes.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream); no entry point
+ *     synchronises, allocates device memory or touches the default stream;
+ *   - the caller owns every buffer; nothing is retained after the call returns;
+ *   - return 0 on success, <0 on error; v2x_last_error() returns a thread-local message.
+ *
+ * Activation layout ("act"): NHWC bf16 with `planes` planes, plane p at element offset
+ * p * N*H*W*C.  planes == 1 is plain bf16.  planes == 2 stores x as hi + lo with
+ * hi = bf16(x), lo = bf16(x - hi); convolutions then accumulate hi*hi + hi*lo + lo*hi on the
+ * tensor cores (3 bf16 MMAs, fp32 accumulate: ~16 mantissa bits, "bf16x3"), which is what the
+ * 1e-3 parity tests use.  Weights are packed the same way.
+ */
+#ifndef V2X_B200_H_
+#define V2X_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V2X_OK 0
+#define V2X_ERR_ARG -1
+#define V2X_ERR_CUDA -2
+#define V2X_ERR_UNSUPPORTED -3
+
+/* library / build info; v2x_version() == 100 * major + minor */
+int v2x_version(void);
+const char* v2x_last_error(void);
+/* 1 if the current device is compute capability 10.x (tcgen05/TMA kernels can run) */
+int v2x_device_ok(void);
+
+/* ---- epilogue modes of v2x_conv_fwd -------------------------------------------------- */
+#define V2X_EPI_ACT 0      /* y = [relu](acc + bias) -> act (bf16 planes), optional 2x nearest upsample on store */
+#define V2X_EPI_F32_SPLIT 1 /* y = acc + bias -> fp32 NHWC, channels [0,split) to out0, [split,cout) to out1     */
+#define V2X_EPI_GRU 2      /* zero-hidden ConvGRU gate epilogue, see v2x_conv_params                           */
+
+/*
+ * One fused convolution launch: implicit GEMM on tcgen05 tensor cores, A tiles (8x16 output
+ * pixels x kc channels, one filter tap at a time) and weight tiles staged by TMA, fp32
+ * accumulators in TMEM, fused bias(+folded BN)+ReLU / head-split / GRU-gate epilogue.
+ *
+ * Replaces: F.relu(bn(conv(x)))                       CP/models/det/backbone/Backbone.py:102-136
+ *           conv(cat(interpolate(a), b)) (two srcs)   Backbone.py:173-237
+ *           Conv3D 1x1x1 + BN3d + ReLU (taps == 1)    Backbone.py:280-300
+ *           heads conv3x3+BN+ReLU, conv1x1            CP/models/det/base/DetModelBase.py:283-296,319-329
+ *           GRUCell(conv(x,W_ih), conv(0,W_hh))       CP/utils/convolutional_rnn/functional.py:84-105
+ */
+typedef struct v2x_conv_params {
+  /* inputs: up to two sources, concatenated along channels (src0 channels first) */
+  const void* src[2];  /* act, [planes][N][Hin][Win][cin[s]] bf16; src[1] may be NULL          */
+  int32_t cin[2];      /* channels per source (multiple of 16)                                 */
+  int32_t n_maps;      /* N                                                                    */
+  int32_t h_out, w_out;/* output spatial size (multiple of 8 / 16); input is stride * output   */
+  int32_t stride;      /* 1 or 2                                                               */
+  int32_t taps;        /* 9 (3x3, pad 1) or 1 (1x1)                                            */
+  int32_t planes;      /* 1 (bf16) or 2 (bf16x3 split precision) -- inputs, weights and output */
+  /* packed weights from v2x_pack_conv_weights: [planes][cout_pad][k_total] bf16, bias fp32    */
+  const void* weights;
+  const float* bias;   /* [cout_pad]                                                           */
+  int32_t cout;        /* logical output channels                                              */
+  int32_t cout_pad;    /* rows of the packed weights (multiple of block_n)                     */
+  int32_t block_n;     /* N tile: 32, 48, 64, 128, 192 (GRU) or 256                            */
+  int32_t epilogue;    /* V2X_EPI_*                                                            */
+  int32_t relu;        /* EPI_ACT: apply ReLU                                                  */
+  int32_t upsample2x;  /* EPI_ACT: store every output pixel to the 2x2 block of a [2H,2W] map  */
+  void* out0;          /* EPI_ACT/GRU: act [planes][N][H(*2)][W(*2)][out_c_total]; F32_SPLIT: fp32 */
+  void* out1;          /* F32_SPLIT: second fp32 output                                        */
+  int32_t out_c_total; /* channel stride of out0 (EPI_ACT/GRU)                                 */
+  int32_t out_c_off;   /* channel offset inside out0                                           */
+  int32_t split;       /* F32_SPLIT: first `split` channels go to out0 (row stride = split),
+                          the rest to out1 (row stride = cout - split)                         */
+  /* EPI_GRU: packed rows are [r(64) | z(64) | n(64)] per 64-channel block (block_n == 192),
+     bias = [b_ih_r+b_hh_r | b_ih_z+b_hh_z | b_ih_n]; h' = (1 - sigmoid(z)) * tanh(n + sigmoid(r) * bhn[c]).
+     Units (maps) whose agent slot is >= num_agent[b] pass `passthrough` through unchanged.   */
+  const float* gru_bhn;      /* [cout/3] = b_hh_n                                              */
+  const void* passthrough;   /* act, same geometry as the output; may be NULL                  */
+  const int64_t* num_agent;  /* [batch][agents] (reference num_agent_tensor) or NULL           */
+  int32_t batch, agents;     /* agent-major maps: map = batch * agent + b                      */
+  int32_t reserved[4];
+} v2x_conv_params;
+
+int v2x_conv_fwd(const v2x_conv_params* p, void* stream);
+/* same contract on CUDA cores (no TMA / tcgen05); a test aid to bisect operand-packing vs tensor-core-path bugs */
+int v2x_conv_fwd_crosscheck(const v2x_conv_params* p, void* stream);
+
+/*
+ * Weight packing (one-time, on device).  Writes a block of the packed operand:
+ *   dst[(plane)][row_off + perm(co)][k_off + tap' * cin_pad + (ci - ci_lo)] = split_bf16(w[co][ci][tap] * s[co])
+ *   bias[row_off + perm(co)] = (b[co] - mean[co]) * s[co] + beta[co],  s = gamma / sqrt(var + eps)  (s = 1 without BN)
+ * w is OIHW fp32 ([cout][cin_total][taps]); ci in [ci_lo, ci_hi) selects one concat source;
+ * cin_pad >= ci_hi - ci_lo (extra k columns must already be zero: memset dst first);
+ * vflip != 0 mirrors the filter rows (tap' = (2 - kh) * 3 + kw), used to run the ConvGRU in the
+ * un-flipped domain; gru_gates == 3 applies the gate interleave
+ * perm(g * C + cb * 64 + c) = cb * 192 + g * 64 + c.
+ * Replaces the BN arithmetic of nn.BatchNorm2d (eval) at Backbone.py:102-136 by folding.
+ */
+int v2x_pack_conv_weights(const float* w, const float* b, const float* bn_gamma, const float* bn_beta,
+                          const float* bn_mean, const float* bn_var, float eps, int32_t cout, int32_t cin_total,
+                          int32_t taps, int32_t ci_lo, int32_t ci_hi, int32_t cin_pad, int32_t vflip,
+                          int32_t gru_gates, void* dst, float* dst_bias, int32_t planes, int32_t cout_pad,
+                          int32_t k_total, int32_t row_off, int32_t k_off, int32_t write_bias, void* stream);
+
+/* bias / b_hh_n vectors of the zero-hidden GRU epilogue (functional.py:95-105 with hidden == 0):
+   bias[perm(g*C+c)] = b_ih[g*C+c] + (g < 2 ? b_hh[g*C+c] : 0);  bhn[c] = b_hh[2*C+c]              */
+int v2x_pack_gru_bias(const float* b_ih, const float* b_hh, int32_t c, float* bias, float* bhn, void* stream);
+
+/*
+ * fp32 NHWC occupancy/feature input -> act bf16 planes with channels zero-padded to c_pad.
+ * Replaces x.to(torch.float) + the NCHW view at Backbone.py:100-101 (memory is already NHWC,
+ * V2VNet.py:51).
+ */
+int v2x_pack_input(const float* x, void* out, int64_t n_pixels, int32_t c, int32_t c_pad, int32_t planes,
+                   void* stream);
+
+/*
+ * Cross-agent warp-and-mean (V2VNet neighbour aggregation), all (scene, target, source) pairs in
+ * one launch, in the UN-flipped domain:
+ *   out[b,i] = mean_{j != i, j < na[b]} bilinear_sample(x[b,j], theta'(T[b,j,i]))      (include_self == 0)
+ *   theta' = [[T00, -T01, -T03/32], [-T10, T11, +T13/32]]  (flip folded in)
+ * grid_sample semantics: bilinear, zeros padding, align_corners=False.
+ * x, out: act [planes][A*B][H][W][C] agent-major; trans: [B][A][A][4][4] float64 (device);
+ * num_agent: [B][A] int64 (device).  Targets i >= na[b] are written as zeros.
+ * Replaces DetModelBase.feature_transformation / build_neighbors_feature_list + torch.mean(torch.stack)
+ * at CP/models/det/base/DetModelBase.py:139-209 and CP/models/det/V2VNet.py:85-98.
+ */
+int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent, int32_t batch,
+                      int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t include_self,
+                      int32_t only_v2i, void* stream);
+
+/* act (bf16 planes, NHWC) -> fp32 NCHW, for returning intermediate maps to torch callers */
+int v2x_act_to_nchw_f32(const void* act, float* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t planes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V2X_B200_H_ */

@@ -1,0 +1,227 @@
+"""GPU parity of the individual kernels (through the C ABI) against the CPU oracle / torch fp32.
+
+Tolerances: planes=2 ("bf16x3" split precision) must meet the north-star 1e-3 relative bound and
+in practice sits near 1e-5; planes=1 (plain bf16 storage) is checked against the same fp32 oracle
+with a bf16-sized bound (operands and outputs are rounded to 8 mantissa bits)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = {1: 2e-2, 2: 1e-3}  # max-abs error relative to the tensor's max-abs
+
+
+def _dev():
+    from v2x_b200 import ops
+    ops.require_gpu()
+    return torch.device("cuda")
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def to_act(x_nchw, planes, dev):
+    from v2x_b200 import ops
+    x = x_nchw.permute(0, 2, 3, 1).contiguous().to(dev)
+    return ops.pack_input(x, x.shape[-1], planes)
+
+
+def rand_bn(c, g):
+    return (torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1, torch.randn(c, generator=g) * 0.1,
+            torch.rand(c, generator=g) + 0.5)
+
+
+def ref_cbr(xs, w, b, bn, stride, relu=True):
+    x = torch.cat(xs, 1)
+    pad = 1 if w.shape[-1] == 3 else 0
+    y = F.conv2d(x, w, b, stride=stride, padding=pad)
+    if bn is not None:
+        y = F.batch_norm(y, bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5)
+    return F.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_pack_input_roundtrip(planes):
+    from v2x_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 32, 48, 13), generator=g)
+    act = ops.pack_input(x.to(dev), 16, planes)
+    assert act.shape == (planes, 2, 32, 48, 16)
+    back = ops.act_to_float(act).cpu()  # [2,16,32,48]
+    assert back[:, 13:].abs().max().item() == 0.0
+    err = (back[:, :13] - x.permute(0, 3, 1, 2)).abs().max().item()
+    assert err < (2e-2 if planes == 1 else 1e-4), err
+    occ = (torch.rand((1, 16, 16, 13), generator=g) < 0.1).float()
+    back = ops.act_to_float(ops.pack_input(occ.to(dev), 16, planes)).cpu()
+    assert torch.equal(back[:, :13], occ.permute(0, 3, 1, 2))
+
+
+CONV_CASES = [
+    # name, cins, cout, stride, taps, n, h_in, w_in, upsample
+    ("c32_s1", [32], 32, 1, 9, 1, 16, 16, False),
+    ("c16_first", [13], 32, 1, 9, 1, 16, 32, False),
+    ("c64_s1", [64], 64, 1, 9, 2, 16, 16, False),
+    ("c32_s2", [32], 64, 2, 9, 1, 32, 32, False),
+    ("c128_s2", [128], 256, 2, 9, 1, 32, 32, False),
+    ("c64_1x1", [64], 64, 1, 1, 1, 16, 16, False),
+    ("c256_n512_up", [256], 512, 1, 9, 1, 16, 16, True),
+    ("cat_64_32", [64, 32], 32, 1, 9, 1, 16, 16, False),
+    ("cat_512_256", [512, 256], 256, 1, 9, 1, 16, 32, False),
+]
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("impl", ["crosscheck", "tc"])
+def test_conv_bn_relu(impl, case, planes):
+    from v2x_b200 import ops
+    dev = _dev()
+    name, cins, cout, stride, taps, n, h, w, up = case
+    g = torch.Generator().manual_seed(sum(ord(ch) for ch in name))
+    k = 3 if taps == 9 else 1
+    xs = [torch.randn((n, c, h, w), generator=g) for c in cins]
+    cin = sum(cins)
+    wt = (torch.rand((cout, cin, k, k), generator=g) - 0.5) * (2.0 / (cin * taps) ** 0.5) * 1.7
+    b = torch.randn(cout, generator=g) * 0.1
+    bn = rand_bn(cout, g)
+    ref = ref_cbr(xs, wt, b, bn, stride)
+    if up:
+        ref = F.interpolate(ref, scale_factor=(2, 2))
+    pc = ops.pack_conv(wt, b, bn, cins=cins, stride=stride, planes=planes, device=dev)
+    acts = []
+    for x, cp in zip(xs, pc.cins):
+        xp = F.pad(x, (0, 0, 0, 0, 0, cp - x.shape[1]))
+        acts.append(to_act(xp, planes, dev))
+    out = ops.conv(pc, acts, upsample2x=up, crosscheck=(impl == "crosscheck"))
+    torch.cuda.synchronize()
+    got = ops.act_to_float(out)
+    err = rel_err(got, ref)
+    print("conv %s %s planes=%d rel_err=%.3e" % (impl, name, planes, err))
+    assert err < TOL[planes], err
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("block_n", [32, 64, 128, 256])
+def test_conv_block_n(block_n, planes):
+    """Same layer through every N-tile width (exercises the TMEM column / B-tile geometry)."""
+    from v2x_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(block_n)
+    x = torch.randn((1, 64, 32, 32), generator=g)
+    wt = (torch.rand((256, 64, 3, 3), generator=g) - 0.5) * 0.15
+    b = torch.randn(256, generator=g) * 0.1
+    bn = rand_bn(256, g)
+    ref = ref_cbr([x], wt, b, bn, 1)
+    pc = ops.pack_conv(wt, b, bn, cins=[64], planes=planes, device=dev)
+    out = ops.conv(pc, [to_act(x, planes, dev)], block_n=block_n)
+    err = rel_err(ops.act_to_float(out), ref)
+    print("block_n %d planes=%d rel_err=%.3e" % (block_n, planes, err))
+    assert err < TOL[planes], err
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("impl", ["crosscheck", "tc"])
+def test_heads(impl, planes):
+    """cls/reg heads (DetModelBase.py:268-351): merged 3x3 conv + block-diagonal 1x1 -> fp32 NHWC split."""
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    from v2x_b200.ops import EPI_F32_SPLIT, ConvLaunch
+    dev = _dev()
+    sd = {}
+    synth.heads_state(sd, synth._Gen(5))
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((1, 32, 16, 32), generator=g).relu()
+    ref = restate.heads(x, sd)
+    h1, h2, n_cls = ops.pack_heads(
+        sd["classification.conv1.weight"], sd["classification.conv1.bias"],
+        tuple(sd["classification.bn1." + k] for k in ("weight", "bias", "running_mean", "running_var")),
+        sd["regression.box_prediction.0.weight"], sd["regression.box_prediction.0.bias"],
+        tuple(sd["regression.box_prediction.1." + k] for k in ("weight", "bias", "running_mean", "running_var")),
+        sd["classification.conv2.weight"], sd["classification.conv2.bias"],
+        sd["regression.box_prediction.3.weight"], sd["regression.box_prediction.3.bias"], planes=planes, device=dev)
+    cc = impl == "crosscheck"
+    t = ops.conv(h1, [to_act(x, planes, dev)], crosscheck=cc)
+    cls = torch.empty((1, 16, 32, 12), dtype=torch.float32, device=dev)
+    loc = torch.empty((1, 16, 32, 36), dtype=torch.float32, device=dev)
+    ConvLaunch(h2, [t], epilogue=EPI_F32_SPLIT, relu=False, out0=cls, out1=loc, split=n_cls, block_n=48,
+               crosscheck=cc)()
+    e1 = rel_err(cls.view(1, -1, 2), ref["cls"])
+    e2 = rel_err(loc.view(1, 16, 32, 6, 1, 6), ref["loc"])
+    print("heads %s planes=%d cls=%.3e loc=%.3e" % (impl, planes, e1, e2))
+    assert e1 < TOL[planes] and e2 < TOL[planes]
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+def test_warp_mean_golden_and_oracle(planes, golden_dir):
+    """Cross-agent warp + mean against (a) the live-reference fixture and (b) the oracle GNN mean."""
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    dev = _dev()
+    g = np.load(os.path.join(golden_dir, "warp_small_seed3.npz"))
+    local = torch.from_numpy(g["local"])  # [2,5,8,32,32], already in the reference's H-flipped domain
+    trans = torch.from_numpy(g["trans"])
+    B, A, C = local.shape[:3]
+    x = torch.flip(local, (3,))  # un-flipped maps, agent-major rows = B*i + b
+    x = torch.cat([x[:, i] for i in range(A)], 0)
+    nat = torch.full((B, A), A, dtype=torch.long)
+    out = ops.warp_mean(to_act(x, planes, dev), trans.to(dev), nat.to(dev), B, A)
+    got = ops.act_to_float(out).cpu()
+    worst = 0.0
+    for i in range(A):
+        for b in range(B):
+            nb = [restate.feature_transformation(local, b, j, i, trans, (1, C, 32, 32)) for j in range(A) if j != i]
+            ref = torch.flip(torch.stack(nb).mean(0), (1,))
+            worst = max(worst, rel_err(got[B * i + b], ref))
+    print("warp_mean planes=%d rel_err=%.3e" % (planes, worst))
+    assert worst < TOL[planes]
+    # single-pair check against the live-reference outputs: 2 agents present -> mean of one neighbour
+    for k, (b, j, i) in enumerate(g["pairs"]):
+        b, j, i = int(b), int(j), int(i)
+        x2 = torch.cat([torch.flip(local[b:b + 1, i], (2,)), torch.flip(local[b:b + 1, j], (2,))], 0)
+        t2 = torch.zeros((1, 2, 2, 4, 4), dtype=torch.float64)
+        t2[0, 1, 0] = trans[b, j, i]
+        t2[0, 0, 1] = trans[b, i, j]
+        o = ops.warp_mean(to_act(x2, planes, dev), t2.to(dev), torch.full((1, 2), 2, dtype=torch.long, device=dev), 1, 2)
+        ref = torch.flip(torch.from_numpy(g["out"][k]), (1,))
+        assert rel_err(ops.act_to_float(o).cpu()[0], ref) < TOL[planes]
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("impl", ["crosscheck", "tc"])
+def test_convgru_zero_hidden(impl, planes):
+    """Fused W_ih conv + gate epilogue against the oracle GRU (which runs in the flipped domain)."""
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    from v2x_b200.ops import EPI_GRU, ConvLaunch
+    dev = _dev()
+    c = 64
+    gen = synth._Gen(11)
+    sd = {"convgru.weight_ih_l0": gen.uniform((3 * c, 2 * c, 3, 3), -0.05, 0.05),
+          "convgru.weight_hh_l0": gen.uniform((3 * c, c, 3, 3), -0.05, 0.05),
+          "convgru.bias_ih_l0": gen.uniform((3 * c,), -0.5, 0.5),
+          "convgru.bias_hh_l0": gen.uniform((3 * c,), -0.5, 0.5)}
+    n = 3
+    hfeat, mean = gen.normal((n, c, 16, 16), 1.0), gen.normal((n, c, 16, 16), 1.0)
+    # oracle in the flipped domain, as the reference runs it (DetModelBase.py:91, V2VNet.py:99-101)
+    ref = torch.cat([torch.flip(restate.convgru_zero_hidden(
+        torch.flip(torch.cat([hfeat[i], mean[i]], 0).unsqueeze(0), (2,)), sd), (2,)) for i in range(n)], 0)
+    pc = ops.pack_gru(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"], sd["convgru.bias_hh_l0"], planes=planes,
+                      device=dev)
+    a_h, a_m = to_act(hfeat, planes, dev), to_act(mean, planes, dev)
+    out = torch.empty_like(a_h)
+    # agent slot 2 of a 1-scene x 3-agent layout is absent -> passes a_h through
+    nat = torch.tensor([[2, 2, 2]], dtype=torch.long, device=dev)
+    ConvLaunch(pc, [a_h, a_m], epilogue=EPI_GRU, out0=out, passthrough=a_h, num_agent=nat, batch=1, agents=3,
+               crosscheck=(impl == "crosscheck"))()
+    got = ops.act_to_float(out).cpu()
+    err = rel_err(got[:2], ref[:2])
+    print("gru %s planes=%d rel_err=%.3e" % (impl, planes, err))
+    assert err < TOL[planes]
+    assert rel_err(got[2], ops.act_to_float(a_h).cpu()[2]) == 0.0

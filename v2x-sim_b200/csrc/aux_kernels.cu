@@ -1,0 +1,305 @@
+// Memory-bound helpers of the hot path: input packing, weight packing (BN fold + bf16 hi/lo split),
+// the cross-agent bilinear warp-and-mean, and act -> fp32 NCHW export.
+// All are HBM/L2-bound byte movers: coalesced 16-byte accesses, grids sized in multiples of the SM
+// count, no tensor cores.  Reference call sites: see include/v2x_b200.h.
+#include "common.cuh"
+
+namespace v2x {
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 NHWC [n_pixels][c] -> bf16 planes [planes][n_pixels][c_pad]; one thread per (pixel, 8-channel group)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n_pixels,
+                                  int c, int c_pad, int planes) {
+  const int groups = c_pad / 8;
+  const long long total = n_pixels * groups;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const long long pix = gid / groups;
+    const int g = (int)(gid - pix * groups);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = g * 8 + 2 * i;
+      const float v0 = c0 < c ? __ldg(x + pix * c + c0) : 0.f;
+      const float v1 = c0 + 1 < c ? __ldg(x + pix * c + c0 + 1) : 0.f;
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v0, h0, l0);
+      split_bf16(v1, h1, l1);
+      hi[i] = pack_bf16x2(h0, h1);
+      lo[i] = pack_bf16x2(l0, l1);
+    }
+    __nv_bfloat16* dst = out + pix * c_pad + g * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (planes == 2) *reinterpret_cast<uint4*>(dst + n_pixels * c_pad) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: one thread per (co, ci, tap)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int gru_perm(int row, int gates, int cout) {
+  if (gates != 3) return row;
+  const int C = cout / 3;
+  const int g = row / C, c = row % C;
+  return (c / 64) * 192 + g * 64 + (c % 64);
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout,
+                                    int cin_total, int taps, int ci_lo, int ci_hi, int cin_pad, int vflip, int gates,
+                                    __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_bias, int planes,
+                                    int cout_pad, int k_total, int row_off, int k_off, int write_bias) {
+  const int cin = ci_hi - ci_lo;
+  const long long total = (long long)cout * cin * taps;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(gid % taps);
+    const int ci = (int)((gid / taps) % cin);
+    const int co = (int)(gid / ((long long)taps * cin));
+    const float s = gamma ? gamma[co] / sqrtf(var[co] + eps) : 1.f;  // BN(eval) scale, folded into w
+    const float v = w[((long long)co * cin_total + ci_lo + ci) * taps + tap] * s;
+    int tp = tap;
+    if (vflip && taps == 9) tp = (2 - tap / 3) * 3 + tap % 3;
+    const int row = row_off + gru_perm(co, gates, cout);
+    const long long k = (long long)k_off + (long long)tp * cin_pad + ci;
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    dst[(long long)row * k_total + k] = hi;
+    if (planes == 2) dst[((long long)cout_pad + row) * k_total + k] = lo;
+    if (write_bias && ci == 0 && tap == 0) {
+      float bb = b ? b[co] : 0.f;
+      if (gamma) bb = (bb - mean[co]) * s + beta[co];
+      dst_bias[row] = bb;
+    }
+  }
+}
+
+__global__ void pack_gru_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, int c,
+                                     float* __restrict__ bias, float* __restrict__ bhn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * c) return;
+  const int g = i / c, ch = i % c;
+  bias[(ch / 64) * 192 + g * 64 + (ch % 64)] = b_ih[i] + (g < 2 ? b_hh[i] : 0.f);
+  if (g == 2) bhn[ch] = b_hh[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-agent warp + mean.  One warp per output pixel; lanes stride over channels in 8-channel
+// (16-byte) vectors so every tap of the bilinear gather is a run of fully coalesced 512-byte
+// (C = 256) reads; the four taps x (A-1) sources are accumulated in registers and the mean is
+// written once.  The maps are 32x32xC (0.5 MB each in bf16) and stay L2-resident.
+// ---------------------------------------------------------------------------------------------
+template <int VEC_PER_LANE>
+__global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                 const double* __restrict__ trans, const long long* __restrict__ num_agent, int batch,
+                                 int agents, int H, int W, int C, int planes, int include_self, int only_v2i) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total_pix = (long long)batch * agents * H * W;
+  const long long plane_stride = total_pix * C;
+  for (long long wid = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total_pix;
+       wid += (long long)gridDim.x * warps_per_block) {
+    const int ow = (int)(wid % W);
+    const int oh = (int)((wid / W) % H);
+    const int map = (int)(wid / ((long long)W * H));  // agent-major: map = batch * i + b
+    const int i = map / batch, b = map % batch;
+    const int na = (int)num_agent[(long long)b * agents];
+    float acc[VEC_PER_LANE][8];
+#pragma unroll
+    for (int v = 0; v < VEC_PER_LANE; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[v][e] = 0.f;
+    int count = 0;
+    if (i < na) {
+      const float gx = (2.f * ow + 1.f) / W - 1.f, gy = (2.f * oh + 1.f) / H - 1.f;
+      for (int j = 0; j < na; ++j) {
+        if (j == i && !include_self) continue;
+        if (only_v2i && i != 0 && j != 0 && j != i) continue;  // DetModelBase.py:196-198
+        ++count;
+        float t00, t01, t02, t10, t11, t12;
+        if (j == i) {  // FusionBase-style self term: identity
+          t00 = 1.f; t01 = 0.f; t02 = 0.f; t10 = 0.f; t11 = 1.f; t12 = 0.f;
+        } else {
+          const double* T = trans + ((((long long)b * agents + j) * agents + i) << 4);
+          // theta' (un-flipped domain): [[T00, -T01, -T03/32], [-T10, T11, +T13/32]]
+          t00 = (float)T[0]; t01 = -(float)T[1]; t02 = -(float)T[3] * (1.f / 32.f);
+          t10 = -(float)T[4]; t11 = (float)T[5]; t12 = (float)T[7] * (1.f / 32.f);
+        }
+        const float sx = t00 * gx + t01 * gy + t02, sy = t10 * gx + t11 * gy + t12;
+        const float ix = ((sx + 1.f) * W - 1.f) * 0.5f, iy = ((sy + 1.f) * H - 1.f) * 0.5f;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+        const long long src_map = (long long)batch * j + b;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+          const float wgt = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
+          if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;  // zeros padding (warp-uniform branch)
+          const __nv_bfloat16* sp = x + ((src_map * H + yy) * W + xx) * C;
+#pragma unroll
+          for (int v = 0; v < VEC_PER_LANE; ++v) {
+            const int c0 = (v * 32 + lane) * 8;
+            if (c0 < C) {
+              uint4 q = __ldg(reinterpret_cast<const uint4*>(sp + c0));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+              uint4 ql = make_uint4(0, 0, 0, 0);
+              if (planes == 2) ql = __ldg(reinterpret_cast<const uint4*>(sp + plane_stride + c0));
+              const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __bfloat1622float2(h2[e]);
+                if (planes == 2) {
+                  const float2 g = __bfloat1622float2(l2[e]);
+                  f.x += g.x; f.y += g.y;
+                }
+                acc[v][2 * e] += wgt * f.x;
+                acc[v][2 * e + 1] += wgt * f.y;
+              }
+            }
+          }
+        }
+      }
+    }
+    const float inv = count > 0 ? 1.f / (float)count : 0.f;
+    __nv_bfloat16* dp = out + wid * C;
+#pragma unroll
+    for (int v = 0; v < VEC_PER_LANE; ++v) {
+      const int c0 = (v * 32 + lane) * 8;
+      if (c0 < C) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(acc[v][2 * e] * inv, h0, l0);
+          split_bf16(acc[v][2 * e + 1] * inv, h1, l1);
+          hi[e] = pack_bf16x2(h0, h1);
+          lo[e] = pack_bf16x2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(dp + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (planes == 2) *reinterpret_cast<uint4*>(dp + plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+}
+
+// act planes NHWC -> fp32 NCHW (debug / feature export); one thread per output element, w fastest
+__global__ void act_to_nchw_kernel(const __nv_bfloat16* __restrict__ act, float* __restrict__ out, int n, int h, int w,
+                                   int c, int planes) {
+  const long long total = (long long)n * c * h * w;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(gid % w);
+    const int y = (int)((gid / w) % h);
+    const int ch = (int)((gid / ((long long)w * h)) % c);
+    const int im = (int)(gid / ((long long)w * h * c));
+    const long long src = (((long long)im * h + y) * w + x) * c + ch;
+    float v = __bfloat162float(act[src]);
+    if (planes == 2) v += __bfloat162float(act[src + total]);
+    out[gid] = v;
+  }
+}
+
+}  // namespace v2x
+
+using namespace v2x;
+
+static unsigned grid_for(long long work_items, int threads, int per_sm) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+extern "C" int v2x_pack_input(const float* x, void* out, int64_t n_pixels, int32_t c, int32_t c_pad, int32_t planes,
+                              void* stream) {
+  V2X_REQUIRE(x && out && n_pixels > 0, "null/empty input");
+  V2X_REQUIRE(c > 0 && c_pad >= c && c_pad % 8 == 0, "c_pad must be a multiple of 8 and >= c");
+  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  const long long total = (long long)n_pixels * (c_pad / 8);
+  pack_input_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), n_pixels, c, c_pad, planes);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_pack_conv_weights(const float* w, const float* b, const float* bn_gamma, const float* bn_beta,
+                                     const float* bn_mean, const float* bn_var, float eps, int32_t cout,
+                                     int32_t cin_total, int32_t taps, int32_t ci_lo, int32_t ci_hi, int32_t cin_pad,
+                                     int32_t vflip, int32_t gru_gates, void* dst, float* dst_bias, int32_t planes,
+                                     int32_t cout_pad, int32_t k_total, int32_t row_off, int32_t k_off,
+                                     int32_t write_bias, void* stream) {
+  V2X_REQUIRE(w && dst, "null weights/dst");
+  V2X_REQUIRE(cout > 0 && taps > 0 && 0 <= ci_lo && ci_lo < ci_hi && ci_hi <= cin_total, "bad channel range");
+  V2X_REQUIRE(cin_pad >= ci_hi - ci_lo, "cin_pad too small");
+  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  V2X_REQUIRE(row_off >= 0 && row_off + cout <= cout_pad, "rows out of range");
+  V2X_REQUIRE(k_off >= 0 && k_off + taps * cin_pad <= k_total, "k range out of bounds");
+  V2X_REQUIRE(!bn_gamma || (bn_beta && bn_mean && bn_var), "incomplete BN parameters");
+  V2X_REQUIRE(gru_gates == 0 || (gru_gates == 3 && cout % 192 == 0), "gru_gates needs cout %% 192 == 0");
+  V2X_REQUIRE(!write_bias || dst_bias, "write_bias needs dst_bias");
+  const long long total = (long long)cout * (ci_hi - ci_lo) * taps;
+  pack_weights_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      w, b, bn_gamma, bn_beta, bn_mean, bn_var, eps, cout, cin_total, taps, ci_lo, ci_hi, cin_pad, vflip, gru_gates,
+      reinterpret_cast<__nv_bfloat16*>(dst), dst_bias, planes, cout_pad, k_total, row_off, k_off, write_bias);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_pack_gru_bias(const float* b_ih, const float* b_hh, int32_t c, float* bias, float* bhn,
+                                 void* stream) {
+  V2X_REQUIRE(b_ih && b_hh && bias && bhn, "null pointer");
+  V2X_REQUIRE(c > 0 && c % 64 == 0, "GRU channels must be a multiple of 64");
+  pack_gru_bias_kernel<<<(3 * c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b_ih, b_hh, c, bias, bhn);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent,
+                                 int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes,
+                                 int32_t include_self, int32_t only_v2i, void* stream) {
+  V2X_REQUIRE(x && out && trans && num_agent, "null pointer");
+  V2X_REQUIRE(batch > 0 && agents > 0 && h > 0 && w > 0, "empty geometry");
+  V2X_REQUIRE(c > 0 && c % 8 == 0 && c <= 1024, "channels must be a multiple of 8, <= 1024");
+  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  const long long total_pix = (long long)batch * agents * h * w;
+  const int threads = 256;
+  const unsigned grid = grid_for(total_pix * 32, threads, 8);
+  const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
+  const long long* na = reinterpret_cast<const long long*>(num_agent);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c <= 256)
+    warp_mean_kernel<1><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i);
+  else if (c <= 512)
+    warp_mean_kernel<2><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i);
+  else
+    warp_mean_kernel<4><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_act_to_nchw_f32(const void* act, float* out, int32_t n, int32_t h, int32_t w, int32_t c,
+                                   int32_t planes, void* stream) {
+  V2X_REQUIRE(act && out && n > 0 && h > 0 && w > 0 && c > 0, "null/empty");
+  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  const long long total = (long long)n * c * h * w;
+  act_to_nchw_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(act), out, n, h, w, c, planes);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}

@@ -1,0 +1,569 @@
+// Fused convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+//   M = output pixels (one CTA owns an 8x16 pixel patch of one map = 128 GEMM rows = 128 TMEM lanes)
+//   N = output channels (block_n columns of fp32 accumulators in TMEM)
+//   K = (source, filter tap, input channel); one pipeline stage = one tap x kc channels
+//
+// A operand: the activation tensor is NHWC bf16, so the im2col rows of one tap are a shifted
+//   8x16xkc box of the input -- fetched by ONE TMA tiled load per stage (4-D map {C,W,H,N*planes};
+//   negative / out-of-range coordinates are zero-filled by the TMA unit = the conv's zero padding).
+//   Stride-2 convs use a 5-D view {2C, W/2, 2, H/2, N*planes} of the same memory so that the
+//   parity of the tap selects a dense box (no element strides needed).
+// B operand: packed weights [planes][cout_pad][K] (K-major), 2-D TMA loads.
+// Both land in shared memory in the canonical K-major swizzled UMMA layout (swizzle width =
+// kc * 2 bytes), are consumed by tcgen05.mma (issued by one thread), and the accumulator is read
+// back with tcgen05.ld for the fused epilogue (bias+ReLU -> bf16 planes, head split -> fp32, or the
+// zero-hidden ConvGRU gates).
+//
+// Warp roles (128 threads): warp0/lane0 = TMA producer, warp1/lane0 = MMA issuer, warp2 = TMEM
+// allocator; all four warps run the epilogue (warp w owns TMEM lanes 32w..32w+31).
+// Several CTAs are resident per SM (smem permitting) so one CTA's epilogue overlaps another's
+// main loop.
+//
+// Reference call sites replaced: see include/v2x_b200.h (v2x_conv_fwd).
+#include <mutex>
+
+#include "common.cuh"
+
+namespace v2x {
+
+constexpr int kMaxStages = 8;
+constexpr int kTileH = 8;
+constexpr int kTileW = 16;
+
+struct ConvDev {
+  int n_maps, h_out, w_out, stride, taps, planes;
+  int nsrc;
+  int cin[2];
+  int cblocks[2];
+  int kc;
+  int num_k;
+  int num_stages;
+  int tiles_w, tiles_per_img;
+  int cout, cout_pad;
+  int epilogue, relu, upsample2x;
+  void* out0;
+  void* out1;
+  int out_c_total, out_c_off, split;
+  const float* bias;
+  const float* gru_bhn;
+  const void* passthrough;
+  const long long* num_agent;
+  int batch, agents;
+  uint32_t a_tile_bytes, b_tile_bytes, stage_bytes, tx_bytes, sbo, layout_type;
+  long long out_plane_stride;  // elements between output planes
+  // reference (CUDA-core) kernel only
+  const void* src[2];
+  const void* weights;
+  int k_total;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue pieces shared by the tensor-core kernel and the CUDA-core cross-check kernel.
+// Each call handles 16 consecutive output channels of one output pixel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_act16(const ConvDev& p, int n_img, int oh, int ow, int ch0, const float* v) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[2 * i], h0, l0);
+    split_bf16(v[2 * i + 1], h1, l1);
+    hi[i] = pack_bf16x2(h0, h1);
+    lo[i] = pack_bf16x2(l0, l1);
+  }
+  const int up = p.upsample2x ? 2 : 1;
+  const int H = p.h_out * up, W = p.w_out * up;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out0);
+  for (int dy = 0; dy < up; ++dy)
+    for (int dx = 0; dx < up; ++dx) {
+      const long long pix = ((long long)n_img * H + (oh * up + dy)) * W + (ow * up + dx);
+      __nv_bfloat16* dst = out + pix * p.out_c_total + p.out_c_off + ch0;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      d4[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      d4[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      if (p.planes == 2) {
+        uint4* l4 = reinterpret_cast<uint4*>(dst + p.out_plane_stride);
+        l4[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        l4[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+    }
+}
+
+__device__ __forceinline__ void epi_act16(const ConvDev& p, int n_img, int oh, int ow, int ch0, float* v) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float y = v[i] + __ldg(p.bias + ch0 + i);
+    v[i] = p.relu ? fmaxf(y, 0.f) : y;
+  }
+  store_act16(p, n_img, oh, ow, ch0, v);
+}
+
+__device__ __forceinline__ void epi_f32_split16(const ConvDev& p, int n_img, int oh, int ow, int ch0, const float* v) {
+  const long long pix = ((long long)n_img * p.h_out + oh) * p.w_out + ow;
+  float* o0 = reinterpret_cast<float*>(p.out0) + pix * p.split;
+  float* o1 = reinterpret_cast<float*>(p.out1) + pix * (p.cout - p.split) - p.split;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int ch = ch0 + i;
+    if (ch < p.cout) {
+      const float y = v[i] + __ldg(p.bias + ch);
+      if (ch < p.split) o0[ch] = y; else o1[ch] = y;
+    }
+  }
+}
+
+// GRU gates for 16 channels [c0, c0+16) of one pixel; prow = packed row of the r gate of channel c0
+__device__ __forceinline__ void epi_gru16(const ConvDev& p, int n_img, int oh, int ow, int c0, int prow, const float* r,
+                                          const float* z, const float* nn) {
+  float h[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float rr = 1.f / (1.f + __expf(-(r[i] + __ldg(p.bias + prow + i))));
+    const float zz = 1.f / (1.f + __expf(-(z[i] + __ldg(p.bias + prow + 64 + i))));
+    const float nv = tanhf(nn[i] + __ldg(p.bias + prow + 128 + i) + rr * __ldg(p.gru_bhn + c0 + i));
+    h[i] = (1.f - zz) * nv;
+  }
+  store_act16(p, n_img, oh, ow, c0, h);
+}
+
+// copy `nch` channels of one pixel from the passthrough tensor (absent agents keep their own map)
+__device__ __forceinline__ void copy_passthrough(const ConvDev& p, int n_img, int oh, int ow, int c0, int nch) {
+  const long long pix = ((long long)n_img * p.h_out + oh) * p.w_out + ow;
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.passthrough) + pix * p.out_c_total + p.out_c_off + c0;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out0) + pix * p.out_c_total + p.out_c_off + c0;
+  for (int pl = 0; pl < p.planes; ++pl)
+    for (int c = 0; c < nch; c += 8)
+      *reinterpret_cast<uint4*>(dst + pl * p.out_plane_stride + c) =
+          *reinterpret_cast<const uint4*>(src + pl * p.out_plane_stride + c);
+}
+
+__device__ __forceinline__ bool gru_unit_absent(const ConvDev& p, int n_img) {
+  if (p.epilogue != V2X_EPI_GRU || p.num_agent == nullptr) return false;
+  const int agent = n_img / p.batch, b = n_img % p.batch;
+  return agent >= (int)p.num_agent[(long long)b * p.agents];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                      const __grid_constant__ CUtensorMap tmA1,
+                                                      const __grid_constant__ CUtensorMap tmB, const ConvDev p) {
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int n_img = tile / p.tiles_per_img;
+  const int trem = tile - n_img * p.tiles_per_img;
+  const int oh0 = (trem / p.tiles_w) * kTileH;
+  const int ow0 = (trem % p.tiles_w) * kTileW;
+  const int n0 = blockIdx.y * BN;
+  const int row = threadIdx.x;
+  const int oh = oh0 + (row >> 4), ow = ow0 + (row & 15);
+
+  if (gru_unit_absent(p, n_img)) {  // CTA-uniform
+    copy_passthrough(p, n_img, oh, ow, blockIdx.y * 64, 64);
+    return;
+  }
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t bar_tmem = smem_u32(&bars[2 * kMaxStages]);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA0);
+    if (p.nsrc > 1) prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tmem, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0, phase = 0, kidx = 0;
+      for (int s = 0; s < p.nsrc; ++s) {
+        const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap % 3 : 1;
+          for (int cb = 0; cb < p.cblocks[s]; ++cb, ++kidx) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t full = bar_full + 8 * stage;
+            mbar_expect_tx(full, p.tx_bytes);
+            const uint32_t sa = smem_base + stage * p.stage_bytes;
+            for (int pl = 0; pl < p.planes; ++pl) {
+              const uint32_t dst = sa + pl * p.a_tile_bytes;
+              const int img = pl * p.n_maps + n_img;
+              if (p.stride == 1) {
+                tma_load_4d(dst, tmA, full, cb * p.kc, ow0 + kw - 1, oh0 + kh - 1, img);
+              } else {
+                // input row 2*oh + kh - 1 = 2*(oh + hoff) + hp
+                const int hp = kh == 1 ? 0 : 1, hoff = kh == 0 ? -1 : 0;
+                const int wp = kw == 1 ? 0 : 1, woff = kw == 0 ? -1 : 0;
+                tma_load_5d(dst, tmA, full, wp * p.cin[s] + cb * p.kc, ow0 + woff, hp, oh0 + hoff, img);
+              }
+            }
+            const uint32_t sb = sa + p.planes * p.a_tile_bytes;
+            for (int pl = 0; pl < p.planes; ++pl)
+              tma_load_2d(sb + pl * p.b_tile_bytes, &tmB, full, kidx * p.kc, pl * p.cout_pad + n0);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
+      int stage = 0, phase = 0;
+      uint32_t acc = 0;
+      const int ksteps = p.kc / 16;
+      for (int k = 0; k < p.num_k; ++k) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t a0 = smem_base + stage * p.stage_bytes;
+        const uint32_t b0 = a0 + p.planes * p.a_tile_bytes;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t da = make_smem_desc(a0 + kk * 32, p.sbo, p.layout_type);
+          const uint64_t db = make_smem_desc(b0 + kk * 32, p.sbo, p.layout_type);
+          umma_bf16(tmem_base, da, db, idesc, acc);
+          acc = 1;
+          if (p.planes == 2) {
+            const uint64_t da1 = make_smem_desc(a0 + p.a_tile_bytes + kk * 32, p.sbo, p.layout_type);
+            const uint64_t db1 = make_smem_desc(b0 + p.b_tile_bytes + kk * 32, p.sbo, p.layout_type);
+            umma_bf16(tmem_base, da, db1, idesc, 1);
+            umma_bf16(tmem_base, da1, db, idesc, 1);
+          }
+        }
+        umma_commit(bar_empty + 8 * stage);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(bar_tmem);
+    }
+    __syncwarp();
+  }
+
+  // ===== epilogue: all 4 warps, warp w reads TMEM lanes [32w, 32w+32) =====
+  mbar_wait(bar_tmem, 0);
+  tc_fence_after();
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  if (p.epilogue == V2X_EPI_GRU) {
+    if constexpr (BN == 192) {
+#pragma unroll 1
+      for (int c16 = 0; c16 < 4; ++c16) {
+        float r[16], z[16], nn[16];
+        tmem_ld16(taddr + c16 * 16, r);
+        tmem_ld16(taddr + 64 + c16 * 16, z);
+        tmem_ld16(taddr + 128 + c16 * 16, nn);
+        epi_gru16(p, n_img, oh, ow, blockIdx.y * 64 + c16 * 16, n0 + c16 * 16, r, z, nn);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int c16 = 0; c16 < BN / 16; ++c16) {
+      const int ch0 = n0 + c16 * 16;
+      if (ch0 >= p.cout) break;
+      float v[16];
+      tmem_ld16(taddr + c16 * 16, v);
+      if (p.epilogue == V2X_EPI_ACT) epi_act16(p, n_img, oh, ow, ch0, v);
+      else epi_f32_split16(p, n_img, oh, ow, ch0, v);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core cross-check kernel: same operands, same epilogues, no TMA / tensor cores.
+// One thread = one output pixel x 16 output channels (x3 gates for the GRU).  Test aid only.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_act(const ConvDev& p, int s, long long idx, long long plane_stride) {
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(p.src[s]);
+  float v = __bfloat162float(a[idx]);
+  if (p.planes == 2) v += __bfloat162float(a[idx + plane_stride]);
+  return v;
+}
+__device__ __forceinline__ float ld_w(const ConvDev& p, long long row, long long k) {
+  const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(p.weights);
+  float v = __bfloat162float(w[row * p.k_total + k]);
+  if (p.planes == 2) v += __bfloat162float(w[((long long)p.cout_pad + row) * p.k_total + k]);
+  return v;
+}
+
+__global__ void conv_ref_kernel(const ConvDev p) {
+  const bool gru = p.epilogue == V2X_EPI_GRU;
+  const int chunks = gru ? p.cout / 3 / 16 : p.cout_pad / 16;
+  const long long total = (long long)p.n_maps * p.h_out * p.w_out * chunks;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int chunk = (int)(gid % chunks);
+  const long long pix = gid / chunks;
+  const int ow = (int)(pix % p.w_out);
+  const int oh = (int)((pix / p.w_out) % p.h_out);
+  const int n_img = (int)(pix / ((long long)p.w_out * p.h_out));
+  const int h_in = p.h_out * p.stride, w_in = p.w_out * p.stride;
+
+  if (gru_unit_absent(p, n_img)) {
+    copy_passthrough(p, n_img, oh, ow, chunk * 16, 16);
+    return;
+  }
+  const int ngate = gru ? 3 : 1;
+  // packed row of gate g, channel chunk: GRU rows are [r(64)|z(64)|n(64)] per 64-channel block
+  int prow[3];
+  for (int g = 0; g < ngate; ++g) prow[g] = gru ? (chunk / 4) * 192 + g * 64 + (chunk % 4) * 16 : chunk * 16;
+  float acc[3][16];
+  for (int g = 0; g < 3; ++g)
+    for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
+  long long kbase = 0;
+  for (int s = 0; s < p.nsrc; ++s) {
+    const long long plane_stride = (long long)p.n_maps * h_in * w_in * p.cin[s];
+    for (int tap = 0; tap < p.taps; ++tap) {
+      const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap % 3 : 1;
+      const int ih = oh * p.stride + kh - 1, iw = ow * p.stride + kw - 1;
+      if (ih >= 0 && ih < h_in && iw >= 0 && iw < w_in) {
+        const long long abase = (((long long)n_img * h_in + ih) * w_in + iw) * p.cin[s];
+        for (int c = 0; c < p.cin[s]; ++c) {
+          const float a = ld_act(p, s, abase + c, plane_stride);
+          if (a != 0.f) {
+            const long long k = kbase + (long long)tap * p.cin[s] + c;
+            for (int g = 0; g < ngate; ++g)
+              for (int i = 0; i < 16; ++i) acc[g][i] += a * ld_w(p, prow[g] + i, k);
+          }
+        }
+      }
+    }
+    kbase += (long long)p.taps * p.cin[s];
+  }
+  if (gru) {
+    epi_gru16(p, n_img, oh, ow, chunk * 16, prow[0], acc[0], acc[1], acc[2]);
+  } else {
+    const int ch0 = chunk * 16;
+    if (ch0 >= p.cout) return;
+    if (p.epilogue == V2X_EPI_ACT) epi_act16(p, n_img, oh, ow, ch0, acc[0]);
+    else epi_f32_split16(p, n_img, oh, ow, ch0, acc[0]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                      const cuuint32_t* box, int kc) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return V2X_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d, rank %d)", (int)r, rank);
+    return V2X_ERR_CUDA;
+  }
+  return V2X_OK;
+}
+
+static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
+  V2X_REQUIRE(p != nullptr, "null params");
+  V2X_REQUIRE(p->src[0] && p->weights && p->bias && p->out0, "null src/weights/bias/out0");
+  V2X_REQUIRE(p->stride == 1 || p->stride == 2, "stride must be 1 or 2 (got %d)", p->stride);
+  V2X_REQUIRE(p->taps == 9 || (p->taps == 1 && p->stride == 1), "taps must be 9, or 1 with stride 1");
+  V2X_REQUIRE(p->planes == 1 || p->planes == 2, "planes must be 1 or 2");
+  V2X_REQUIRE(p->n_maps > 0 && p->h_out > 0 && p->w_out > 0, "empty geometry");
+  V2X_REQUIRE(p->h_out % kTileH == 0 && p->w_out % kTileW == 0, "h_out %% 8 / w_out %% 16 != 0 (%d x %d)", p->h_out,
+              p->w_out);
+  V2X_REQUIRE(p->cin[0] > 0 && p->cin[0] % 16 == 0, "cin[0] must be a positive multiple of 16");
+  V2X_REQUIRE(p->src[1] == nullptr || (p->cin[1] > 0 && p->cin[1] % 16 == 0), "cin[1] must be a multiple of 16");
+  const int bn = p->block_n;
+  V2X_REQUIRE(bn == 32 || bn == 48 || bn == 64 || bn == 128 || bn == 192 || bn == 256, "unsupported block_n %d", bn);
+  V2X_REQUIRE(p->cout > 0 && p->cout_pad >= p->cout && p->cout_pad % bn == 0, "cout_pad must be a multiple of block_n");
+  V2X_REQUIRE(p->cout % 16 == 0 || p->epilogue == V2X_EPI_F32_SPLIT, "cout must be a multiple of 16");
+  d = ConvDev{};
+  d.n_maps = p->n_maps; d.h_out = p->h_out; d.w_out = p->w_out; d.stride = p->stride; d.taps = p->taps;
+  d.planes = p->planes;
+  d.nsrc = p->src[1] ? 2 : 1;
+  d.cin[0] = p->cin[0]; d.cin[1] = p->src[1] ? p->cin[1] : 0;
+  int kc = 64;
+  for (int s = 0; s < d.nsrc; ++s)
+    while (d.cin[s] % kc) kc >>= 1;
+  d.kc = kc;
+  d.num_k = 0; d.k_total = 0;
+  for (int s = 0; s < d.nsrc; ++s) {
+    d.cblocks[s] = d.cin[s] / kc;
+    d.num_k += p->taps * d.cblocks[s];
+    d.k_total += p->taps * d.cin[s];
+  }
+  d.tiles_w = p->w_out / kTileW;
+  d.tiles_per_img = d.tiles_w * (p->h_out / kTileH);
+  d.cout = p->cout; d.cout_pad = p->cout_pad;
+  d.epilogue = p->epilogue; d.relu = p->relu; d.upsample2x = p->upsample2x;
+  d.out0 = p->out0; d.out1 = p->out1;
+  d.out_c_total = p->out_c_total; d.out_c_off = p->out_c_off; d.split = p->split;
+  d.bias = p->bias; d.gru_bhn = p->gru_bhn; d.passthrough = p->passthrough;
+  d.num_agent = reinterpret_cast<const long long*>(p->num_agent);
+  d.batch = p->batch; d.agents = p->agents;
+  d.a_tile_bytes = 128u * kc * 2u;
+  d.b_tile_bytes = ((uint32_t)bn * kc * 2u + 1023u) & ~1023u;
+  d.stage_bytes = p->planes * (d.a_tile_bytes + d.b_tile_bytes);
+  d.tx_bytes = p->planes * (d.a_tile_bytes + (uint32_t)bn * kc * 2u);
+  d.sbo = 8u * kc * 2u;
+  d.layout_type = kc == 64 ? 2u : kc == 32 ? 4u : 6u;
+  const int up = p->upsample2x ? 2 : 1;
+  d.src[0] = p->src[0]; d.src[1] = p->src[1]; d.weights = p->weights;
+  switch (p->epilogue) {
+    case V2X_EPI_ACT:
+      V2X_REQUIRE(p->out_c_total >= p->out_c_off + p->cout && p->out_c_total % 8 == 0 && p->out_c_off % 8 == 0,
+                  "bad output channel window");
+      d.out_plane_stride = (long long)p->n_maps * p->h_out * up * p->w_out * up * p->out_c_total;
+      break;
+    case V2X_EPI_F32_SPLIT:
+      V2X_REQUIRE(p->out1 != nullptr || p->split >= p->cout, "F32_SPLIT needs out1");
+      V2X_REQUIRE(p->split > 0 && p->split <= p->cout, "bad split");
+      V2X_REQUIRE(!p->upsample2x, "upsample2x only with EPI_ACT");
+      break;
+    case V2X_EPI_GRU:
+      V2X_REQUIRE(bn == 192 && p->cout % 192 == 0 && p->cout_pad == p->cout, "GRU epilogue needs block_n 192");
+      V2X_REQUIRE(p->gru_bhn != nullptr, "GRU epilogue needs gru_bhn");
+      V2X_REQUIRE(!p->upsample2x, "upsample2x only with EPI_ACT");
+      V2X_REQUIRE(p->out_c_total >= p->out_c_off + p->cout / 3 && p->out_c_total % 8 == 0 && p->out_c_off % 8 == 0,
+                  "bad output channel window");
+      V2X_REQUIRE(p->num_agent == nullptr || (p->batch > 0 && p->agents > 0 && p->batch * p->agents == p->n_maps),
+                  "num_agent needs batch * agents == n_maps");
+      d.out_plane_stride = (long long)p->n_maps * p->h_out * p->w_out * p->out_c_total;
+      break;
+    default:
+      V2X_REQUIRE(false, "unknown epilogue %d", p->epilogue);
+  }
+  return V2X_OK;
+}
+
+template <int BN>
+static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                     size_t smem, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  dim3 grid(d.n_maps * d.tiles_per_img, d.cout_pad / BN);
+  conv_tc_kernel<BN><<<grid, 128, smem, stream>>>(a0, a1, b, d);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+}  // namespace v2x
+
+using namespace v2x;
+
+extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
+  ConvDev d;
+  int rc = fill_dev(p, d);
+  if (rc) return rc;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int bn = p->block_n;
+
+  // pipeline depth: prefer >= 3 stages within a 2-CTA/SM budget, else use most of the SM
+  int stages = (int)(100 * 1024 / d.stage_bytes);
+  if (stages < 3) stages = (int)(200 * 1024 / d.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > d.num_k) stages = d.num_k;
+  V2X_REQUIRE(stages >= 1, "stage of %u bytes does not fit in shared memory", d.stage_bytes);
+  d.num_stages = stages;
+  const size_t smem = (size_t)stages * d.stage_bytes + 1024;
+
+  CUtensorMap tmA[2], tmB;
+  const int h_in = p->h_out * p->stride, w_in = p->w_out * p->stride;
+  for (int s = 0; s < d.nsrc; ++s) {
+    const cuuint64_t C = (cuuint64_t)d.cin[s];
+    const cuuint64_t NP = (cuuint64_t)p->n_maps * p->planes;
+    if (p->stride == 1) {
+      cuuint64_t dims[4] = {C, (cuuint64_t)w_in, (cuuint64_t)h_in, NP};
+      cuuint64_t str[3] = {C * 2, (cuuint64_t)w_in * C * 2, (cuuint64_t)h_in * w_in * C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)d.kc, kTileW, kTileH, 1};
+      rc = encode_map(&tmA[s], p->src[s], 4, dims, str, box, d.kc);
+    } else {
+      cuuint64_t dims[5] = {2 * C, (cuuint64_t)w_in / 2, 2, (cuuint64_t)h_in / 2, NP};
+      cuuint64_t str[4] = {2 * C * 2, (cuuint64_t)w_in * C * 2, 2 * (cuuint64_t)w_in * C * 2,
+                           (cuuint64_t)h_in * w_in * C * 2};
+      cuuint32_t box[5] = {(cuuint32_t)d.kc, kTileW, 1, kTileH, 1};
+      rc = encode_map(&tmA[s], p->src[s], 5, dims, str, box, d.kc);
+    }
+    if (rc) return rc;
+  }
+  if (d.nsrc == 1) tmA[1] = tmA[0];
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.k_total, (cuuint64_t)p->planes * p->cout_pad};
+    cuuint64_t str[1] = {(cuuint64_t)d.k_total * 2};
+    cuuint32_t box[2] = {(cuuint32_t)d.kc, (cuuint32_t)bn};
+    rc = encode_map(&tmB, p->weights, 2, dims, str, box, d.kc);
+    if (rc) return rc;
+  }
+  switch (bn) {
+    case 32: return launch_tc<32>(d, tmA[0], tmA[1], tmB, smem, stream);
+    case 48: return launch_tc<48>(d, tmA[0], tmA[1], tmB, smem, stream);
+    case 64: return launch_tc<64>(d, tmA[0], tmA[1], tmB, smem, stream);
+    case 128: return launch_tc<128>(d, tmA[0], tmA[1], tmB, smem, stream);
+    case 192: return launch_tc<192>(d, tmA[0], tmA[1], tmB, smem, stream);
+    case 256: return launch_tc<256>(d, tmA[0], tmA[1], tmB, smem, stream);
+  }
+  return V2X_ERR_ARG;
+}
+
+// Same contract as v2x_conv_fwd, computed on CUDA cores without TMA / tcgen05.  A test aid used by
+// tests/ to separate operand-packing bugs from tensor-core-path bugs; not used by the product path.
+extern "C" int v2x_conv_fwd_crosscheck(const v2x_conv_params* p, void* stream_) {
+  ConvDev d;
+  int rc = fill_dev(p, d);
+  if (rc) return rc;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const bool gru = p->epilogue == V2X_EPI_GRU;
+  const long long chunks = gru ? p->cout / 3 / 16 : p->cout_pad / 16;
+  const long long total = (long long)p->n_maps * p->h_out * p->w_out * chunks;
+  const int threads = 128;
+  conv_ref_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(d);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}

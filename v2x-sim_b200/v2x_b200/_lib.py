@@ -1,0 +1,95 @@
+"""ctypes binding of libv2x_b200.so (the C ABI declared in include/v2x_b200.h).
+
+The library is the product: there is no python / torch / CPU fallback.  Importing this module
+without the built library, or calling an op without a Blackwell GPU, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libv2x_b200.so")
+
+EPI_ACT, EPI_F32_SPLIT, EPI_GRU = 0, 1, 2
+
+
+class ConvParams(C.Structure):
+    """Mirror of ``v2x_conv_params`` (include/v2x_b200.h)."""
+    _fields_ = [
+        ("src", C.c_void_p * 2),
+        ("cin", C.c_int32 * 2),
+        ("n_maps", C.c_int32),
+        ("h_out", C.c_int32),
+        ("w_out", C.c_int32),
+        ("stride", C.c_int32),
+        ("taps", C.c_int32),
+        ("planes", C.c_int32),
+        ("weights", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("cout", C.c_int32),
+        ("cout_pad", C.c_int32),
+        ("block_n", C.c_int32),
+        ("epilogue", C.c_int32),
+        ("relu", C.c_int32),
+        ("upsample2x", C.c_int32),
+        ("out0", C.c_void_p),
+        ("out1", C.c_void_p),
+        ("out_c_total", C.c_int32),
+        ("out_c_off", C.c_int32),
+        ("split", C.c_int32),
+        ("gru_bhn", C.c_void_p),
+        ("passthrough", C.c_void_p),
+        ("num_agent", C.c_void_p),
+        ("batch", C.c_int32),
+        ("agents", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+# every symbol include/v2x_b200.h declares: (name, restype, argtypes)
+_I32, _I64, _F32, _P = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+SYMBOLS = [
+    ("v2x_version", C.c_int, []),
+    ("v2x_last_error", C.c_char_p, []),
+    ("v2x_device_ok", C.c_int, []),
+    ("v2x_conv_fwd", C.c_int, [C.POINTER(ConvParams), _P]),
+    ("v2x_conv_fwd_crosscheck", C.c_int, [C.POINTER(ConvParams), _P]),
+    ("v2x_pack_conv_weights", C.c_int,
+     [_P, _P, _P, _P, _P, _P, _F32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _I32,
+      _I32, _I32, _P]),
+    ("v2x_pack_gru_bias", C.c_int, [_P, _P, _I32, _P, _P, _P]),
+    ("v2x_pack_input", C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
+    ("v2x_warp_mean_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_act_to_nchw_f32", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+]
+
+_lib = None
+
+
+class V2XError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libv2x_b200.so (built in-tree by ``__graft_entry__.build()``); raises if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise V2XError(
+            "libv2x_b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "there is no CPU / torch fallback for this path" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().v2x_last_error().decode("utf-8", "replace")
+        raise V2XError("%s failed (%d): %s" % (what or "v2x call", rc, msg))

@@ -1,0 +1,232 @@
+"""Whole-forward plans of the detection models on the sm_100a kernels.
+
+A plan owns the packed operands (derived from a reference-format ``state_dict``), a static
+workspace of act tensors for a fixed (batch, agents) geometry, and the bound launch list of the
+forward.  ``run()`` replays the launches on the current stream; ``capture()`` records them into
+one CUDA graph (no python, no host syncs, no per-call H2D in the replayed step -- the reference's
+python triple loop / per-warp ``torch.tensor(mask)`` / ``.item()`` syncs, V2VNet.py:66-107 and
+DetModelBase.py:163, disappear).
+
+Layer order and semantics follow CP/models/det/backbone/Backbone.py:89-242,
+CP/models/det/V2VNet.py:47-120 and CP/models/det/base/DetModelBase.py:226-265.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .ops import EPI_ACT, EPI_F32_SPLIT, EPI_GRU, ConvLaunch, PackedConv
+
+H0 = W0 = 256
+IN_C, IN_C_PAD = 13, 16
+
+
+def _bn(sd, name):
+    return (sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"])
+
+
+class BackboneWeights:
+    """Packed operands of the used halves of a reference ``Backbone`` (encoder and/or decoder)."""
+
+    ENC = [("conv_pre_1", "bn_pre_1", 1, [13]), ("conv_pre_2", "bn_pre_2", 1, [32]),
+           ("conv1_1", "bn1_1", 2, [32]), ("conv1_2", "bn1_2", 1, [64]),
+           ("conv2_1", "bn2_1", 2, [64]), ("conv2_2", "bn2_2", 1, [128]),
+           ("conv3_1", "bn3_1", 2, [128]), ("conv3_2", "bn3_2", 1, [256]),
+           ("conv4_1", "bn4_1", 2, [256]), ("conv4_2", "bn4_2", 1, [512])]
+    DEC = [("conv5_1", "bn5_1", 1, [512, 256]), ("conv5_2", "bn5_2", 1, [256]),
+           ("conv6_1", "bn6_1", 1, [256, 128]), ("conv6_2", "bn6_2", 1, [128]),
+           ("conv7_1", "bn7_1", 1, [128, 64]), ("conv7_2", "bn7_2", 1, [64]),
+           ("conv8_1", "bn8_1", 1, [64, 32]), ("conv8_2", "bn8_2", 1, [32])]
+
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, planes: int, device, encoder=True, decoder=True):
+        self.c: Dict[str, PackedConv] = {}
+        layers = (self.ENC if encoder else []) + (self.DEC if decoder else [])
+        for conv, bn, stride, cins in layers:
+            self.c[conv] = ops.pack_conv(sd[prefix + conv + ".weight"], sd[prefix + conv + ".bias"],
+                                         _bn(sd, prefix + bn), cins=cins, stride=stride, planes=planes, device=device)
+        if encoder:
+            for name in ("conv3d_1", "conv3d_2"):
+                self.c[name] = ops.pack_conv(sd[prefix + name + ".conv3d.weight"], sd[prefix + name + ".conv3d.bias"],
+                                             _bn(sd, prefix + name + ".bn3d"), cins=[sd[prefix + name + ".conv3d.weight"].shape[1]],
+                                             planes=planes, device=device)
+
+
+class HeadWeights:
+    def __init__(self, sd, planes, device):
+        self.head1, self.head2, self.n_cls = ops.pack_heads(
+            sd["classification.conv1.weight"], sd["classification.conv1.bias"], _bn(sd, "classification.bn1"),
+            sd["regression.box_prediction.0.weight"], sd["regression.box_prediction.0.bias"],
+            _bn(sd, "regression.box_prediction.1"),
+            sd["classification.conv2.weight"], sd["classification.conv2.bias"],
+            sd["regression.box_prediction.3.weight"], sd["regression.box_prediction.3.bias"],
+            planes=planes, device=device)
+
+
+class DetPlan:
+    """Shared machinery: workspace, launch list, graph capture."""
+
+    def __init__(self, n_maps: int, planes: int, device):
+        self.n, self.planes, self.device = n_maps, planes, torch.device(device)
+        self.launches: List = []
+        self.ws: Dict[str, torch.Tensor] = {}
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.flops = 0.0
+        self.n_kernels = 0
+
+    def act(self, name, h, w, c):
+        t = ops.empty_act(self.planes, self.n, h, w, c, self.device)
+        self.ws[name] = t
+        return t
+
+    def add(self, launch):
+        self.launches.append(launch)
+        self.n_kernels += 1
+        self.flops += getattr(launch, "flops", 0.0)
+
+    def conv(self, pc, srcs, out_name, *, upsample2x=False, **kw):
+        planes, n, h_in, w_in, _ = srcs[0].shape
+        up = 2 if upsample2x else 1
+        out = self.act(out_name, h_in // pc.stride * up, w_in // pc.stride * up, pc.cout)
+        self.add(ConvLaunch(pc, srcs, out0=out, upsample2x=upsample2x, **kw))
+        return out
+
+    # ---- encoder / decoder / heads (Backbone.py:89-242, DetModelBase.py:226-265) ----
+    def build_input(self):
+        self.bev_in = torch.zeros((self.n, 1, H0, W0, IN_C), dtype=torch.float32, device=self.device)
+        x_in = self.act("x_in", H0, W0, IN_C_PAD)
+        bev, planes = self.bev_in, self.planes
+        self.add(lambda: ops.pack_input(bev, IN_C_PAD, planes, out=x_in))
+        return x_in
+
+    def build_encoder(self, w: BackboneWeights, x_in):
+        c = w.c
+        t = self.conv(c["conv_pre_1"], [x_in], "x0a")
+        x0 = self.conv(c["conv_pre_2"], [t], "x0")
+        t = self.conv(c["conv1_1"], [x0], "x1a")
+        t = self.conv(c["conv1_2"], [t], "x1b")
+        x1 = self.conv(c["conv3d_1"], [t], "x1")
+        t = self.conv(c["conv2_1"], [x1], "x2a")
+        t = self.conv(c["conv2_2"], [t], "x2b")
+        x2 = self.conv(c["conv3d_2"], [t], "x2")
+        t = self.conv(c["conv3_1"], [x2], "x3a")
+        x3 = self.conv(c["conv3_2"], [t], "x3")
+        t = self.conv(c["conv4_1"], [x3], "x4a")
+        # x_4 is only ever consumed through F.interpolate(x_4, 2) (Backbone.py:176): store it upsampled
+        x4u = self.conv(c["conv4_2"], [t], "x4u", upsample2x=True)
+        return x0, x1, x2, x3, x4u
+
+    def build_decoder(self, w: BackboneWeights, x0, x1, x2, x3, x4u):
+        c = w.c
+        t = self.conv(c["conv5_1"], [x4u, x3], "x5a")
+        x5u = self.conv(c["conv5_2"], [t], "x5u", upsample2x=True)
+        t = self.conv(c["conv6_1"], [x5u, x2], "x6a")
+        x6u = self.conv(c["conv6_2"], [t], "x6u", upsample2x=True)
+        t = self.conv(c["conv7_1"], [x6u, x1], "x7a")
+        x7u = self.conv(c["conv7_2"], [t], "x7u", upsample2x=True)
+        t = self.conv(c["conv8_1"], [x7u, x0], "x8a")
+        return self.conv(c["conv8_2"], [t], "x8")
+
+    def build_heads(self, hw: HeadWeights, x8):
+        t = self.conv(hw.head1, [x8], "head1")
+        n_cls = hw.n_cls
+        n_loc = hw.head2.cout - n_cls
+        self.cls = torch.empty((self.n, H0, W0, n_cls), dtype=torch.float32, device=self.device)
+        self.loc = torch.empty((self.n, H0, W0, n_loc), dtype=torch.float32, device=self.device)
+        self.add(ConvLaunch(hw.head2, [t], epilogue=EPI_F32_SPLIT, relu=False, out0=self.cls, out1=self.loc,
+                            split=n_cls, block_n=hw.head2.cout))
+
+    # ---- execution ----
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            for l in self.launches:
+                l()
+
+    def capture(self):
+        """Record the whole forward into one CUDA graph (side stream warm-up first, as CUDA requires)."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                for l in self.launches:
+                    l()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for l in self.launches:
+                l()
+        self.graph = g
+
+    def result(self):
+        """Reference output contract (DetModelBase.py:238-252): cls [N, H*W*6, 2], loc [N,H,W,6,1,6]."""
+        n = self.n
+        return {"loc": self.loc.view(n, H0, W0, 6, 1, 6), "cls": self.cls.view(n, -1, 2)}
+
+
+class V2VNetDetPlan(DetPlan):
+    """det V2VNet forward (V2VNet.py:47-120) for ``batch`` scenes x ``agents`` agent slots."""
+
+    def __init__(self, sd, batch: int, agents: int = 5, gnn_iter: int = 3, planes: int = 1, device="cuda",
+                 only_v2i=False):
+        super().__init__(batch * agents, planes, device)
+        ops.require_gpu()
+        self.batch, self.agents, self.gnn_iter = batch, agents, gnn_iter
+        dev = self.device
+        self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
+        self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
+        self.head_w = HeadWeights(sd, planes, dev)
+        self.gru_w = ops.pack_gru(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"], sd["convgru.bias_hh_l0"],
+                                  planes=planes, device=dev)
+        self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
+        self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
+
+        x_in = self.build_input()
+        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
+        c3 = x3.shape[-1]
+        # neighbours are always warped from the ORIGINAL encoder maps (V2VNet.py:85-94), so the mean is
+        # round-invariant: one warp launch per frame instead of 60 grid_sample calls
+        mean = self.act("mean", 32, 32, c3)
+        trans, na = self.trans, self.num_agent
+        self.add(lambda: ops.warp_mean(x3, trans, na, batch, agents, include_self=False, only_v2i=only_v2i, out=mean))
+        h = x3
+        for r in range(gnn_iter):
+            out = self.act("h%d" % (r + 1), 32, 32, c3)
+            self.add(ConvLaunch(self.gru_w, [h, mean], epilogue=EPI_GRU, out0=out, passthrough=x3, num_agent=na,
+                                batch=batch, agents=agents))
+            h = out
+        x8 = self.build_decoder(self.dec_w, x0, x1, x2, h, x4u)
+        self.build_heads(self.head_w, x8)
+
+    def set_inputs(self, bevs, trans_matrices, num_agent_tensor):
+        """Async copies into the plan's static input buffers (host or device sources)."""
+        self.bev_in.copy_(bevs.reshape(self.bev_in.shape), non_blocking=True)
+        self.trans.copy_(trans_matrices.reshape(self.trans.shape), non_blocking=True)
+        self.num_agent.copy_(num_agent_tensor.reshape(self.num_agent.shape), non_blocking=True)
+
+    def forward(self, bevs, trans_matrices, num_agent_tensor):
+        self.set_inputs(bevs, trans_matrices, num_agent_tensor)
+        self.run()
+        return self.result()
+
+
+class FaFNetPlan(DetPlan):
+    """FaFNet / STPN forward: encoder -> decoder -> heads, no fusion (FaFNet.py:28-39)."""
+
+    def __init__(self, sd, n_maps: int, planes: int = 1, device="cuda"):
+        super().__init__(n_maps, planes, device)
+        ops.require_gpu()
+        self.w = BackboneWeights(sd, "stpn.", planes, self.device, encoder=True, decoder=True)
+        self.head_w = HeadWeights(sd, planes, self.device)
+        x_in = self.build_input()
+        x0, x1, x2, x3, x4u = self.build_encoder(self.w, x_in)
+        x8 = self.build_decoder(self.w, x0, x1, x2, x3, x4u)
+        self.build_heads(self.head_w, x8)
+
+    def forward(self, bevs):
+        self.bev_in.copy_(bevs.reshape(self.bev_in.shape), non_blocking=True)
+        self.run()
+        return self.result()

@@ -1,0 +1,242 @@
+"""Torch-facing wrappers of the C ABI: tensors in, tensors out, kernels from libv2x_b200.so.
+
+torch is plumbing here (device memory, streams); every FLOP of the path runs in the
+hand-written sm_100a kernels.  An ``act`` is a bf16 tensor ``[planes, N, H, W, C]``
+(planes = 1: bf16; planes = 2: bf16 hi/lo split, see include/v2x_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import EPI_ACT, EPI_F32_SPLIT, EPI_GRU, ConvParams, V2XError, check
+
+BN_EPS = 1e-5  # nn.BatchNorm2d default (reference never overrides it)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def require_gpu():
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise V2XError("no CUDA device: the v2x_b200 path has no CPU fallback")
+    if not lib.v2x_device_ok():
+        raise V2XError("current device is not compute capability 10.x (sm_100a kernels only)")
+    return lib
+
+
+def empty_act(planes, n, h, w, c, device):
+    return torch.empty((planes, n, h, w, c), dtype=torch.bfloat16, device=device)
+
+
+def act_to_float(act: torch.Tensor) -> torch.Tensor:
+    """act [P,N,H,W,C] -> fp32 NCHW through the CUDA export kernel."""
+    lib = require_gpu()
+    p, n, h, w, c = act.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=act.device)
+    check(lib.v2x_act_to_nchw_f32(_ptr(act), _ptr(out), n, h, w, c, p, _stream()), "v2x_act_to_nchw_f32")
+    return out
+
+
+def pack_input(x: torch.Tensor, c_pad: int, planes: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 NHWC ``[..., H, W, C]`` (any leading dims) -> act ``[planes, N, H, W, c_pad]``."""
+    lib = require_gpu()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
+    h, w, c = x.shape[-3:]
+    n = x.numel() // (h * w * c)
+    if out is None:
+        out = empty_act(planes, n, h, w, c_pad, x.device)
+    check(lib.v2x_pack_input(_ptr(x), _ptr(out), n * h * w, c, c_pad, planes, _stream()), "v2x_pack_input")
+    return out
+
+
+@dataclass
+class PackedConv:
+    """Packed operand of one fused conv launch (weights bf16 [P, cout_pad, k_total], bias fp32)."""
+    weights: torch.Tensor
+    bias: torch.Tensor
+    cins: List[int]          # padded channels per source
+    taps: int
+    stride: int
+    cout: int
+    cout_pad: int
+    planes: int
+    gru_bhn: Optional[torch.Tensor] = None
+    keep: list = field(default_factory=list)
+
+    @property
+    def k_total(self):
+        return self.taps * sum(self.cins)
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def pack_conv(weight, bias, bn=None, *, cins: Sequence[int], cin_pads: Optional[Sequence[int]] = None, stride=1,
+              planes=1, device=None, vflip=False, gru=False) -> PackedConv:
+    """BN-fold + reorder + bf16 split of one conv's weights, on device.
+
+    weight: OIHW (or OI111 for the 1x1x1 Conv3D) fp32; ``cins`` = logical channels of each concat
+    source (sum == weight.shape[1]); bn = (gamma, beta, running_mean, running_var) or None.
+    """
+    lib = require_gpu()
+    device = device or weight.device
+    cout, cin_total = weight.shape[0], weight.shape[1]
+    taps = int(weight.numel() // (cout * cin_total))
+    assert taps in (1, 9) and sum(cins) == cin_total
+    cin_pads = list(cin_pads) if cin_pads is not None else [((c + 15) // 16) * 16 for c in cins]
+    cout_pad = cout
+    k_total = taps * sum(cin_pads)
+    w = _f32(weight, device).reshape(cout, cin_total, taps)
+    b = _f32(bias, device) if bias is not None else None
+    bnp = [_f32(t, device) for t in bn] if bn is not None else [None] * 4
+    dst = torch.zeros((planes, cout_pad, k_total), dtype=torch.bfloat16, device=device)
+    dst_bias = torch.zeros((cout_pad,), dtype=torch.float32, device=device)
+    ci_lo, k_off = 0, 0
+    for s, (c, cp) in enumerate(zip(cins, cin_pads)):
+        check(lib.v2x_pack_conv_weights(_ptr(w), _ptr(b), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]), _ptr(bnp[3]),
+                                        BN_EPS, cout, cin_total, taps, ci_lo, ci_lo + c, cp, int(vflip),
+                                        3 if gru else 0, _ptr(dst), _ptr(dst_bias), planes, cout_pad, k_total, 0, k_off,
+                                        int(s == 0 and not gru), _stream()), "v2x_pack_conv_weights")
+        ci_lo += c
+        k_off += taps * cp
+    return PackedConv(dst, dst_bias, cin_pads, taps, stride, cout, cout_pad, planes)
+
+
+def pack_gru(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True) -> PackedConv:
+    """Zero-hidden ConvGRU operand: W_ih rows gate-interleaved per 64 channels, filter rows mirrored so
+    the GRU runs in the un-flipped domain.  W_hh is never needed (hidden == 0)."""
+    lib = require_gpu()
+    device = device or w_ih.device
+    c = w_ih.shape[0] // 3
+    pc = pack_conv(w_ih, None, None, cins=[c, w_ih.shape[1] - c], planes=planes, device=device, vflip=vflip, gru=True)
+    bhn = torch.empty((c,), dtype=torch.float32, device=device)
+    bi, bh = _f32(b_ih, device), _f32(b_hh, device)
+    check(lib.v2x_pack_gru_bias(_ptr(bi), _ptr(bh), c, _ptr(pc.bias), _ptr(bhn), _stream()), "v2x_pack_gru_bias")
+    pc.gru_bhn = bhn
+    return pc
+
+
+def pack_heads(cls1_w, cls1_b, cls_bn, reg1_w, reg1_b, reg_bn, cls2_w, cls2_b, reg2_w, reg2_b, *, planes=1,
+               device=None):
+    """Detection heads (DetModelBase.py:268-351) as two launches: one 32->64 3x3 conv (cls.conv1|reg.0 rows
+    stacked, BN folded, ReLU) and one block-diagonal 64->48 1x1 conv (cls.conv2 on channels 0..31, reg.3 on 32..63)."""
+    lib = require_gpu()
+    device = device or cls1_w.device
+    c = cls1_w.shape[1]
+    n1 = cls1_w.shape[0] + reg1_w.shape[0]
+    w1 = torch.zeros((planes, n1, 9 * c), dtype=torch.bfloat16, device=device)
+    b1 = torch.zeros((n1,), dtype=torch.float32, device=device)
+    row = 0
+    for w, b, bn in ((cls1_w, cls1_b, cls_bn), (reg1_w, reg1_b, reg_bn)):
+        wf = _f32(w, device).reshape(w.shape[0], c, 9)
+        bnp = [_f32(t, device) for t in bn]
+        check(lib.v2x_pack_conv_weights(_ptr(wf), _ptr(_f32(b, device)), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]),
+                                        _ptr(bnp[3]), BN_EPS, w.shape[0], c, 9, 0, c, c, 0, 0, _ptr(w1), _ptr(b1),
+                                        planes, n1, 9 * c, row, 0, 1, _stream()), "v2x_pack_conv_weights(head1)")
+        row += w.shape[0]
+    head1 = PackedConv(w1, b1, [c], 9, 1, n1, n1, planes)
+    n2 = cls2_w.shape[0] + reg2_w.shape[0]
+    w2 = torch.zeros((planes, n2, n1), dtype=torch.bfloat16, device=device)
+    b2 = torch.zeros((n2,), dtype=torch.float32, device=device)
+    row, koff = 0, 0
+    for w, b in ((cls2_w, cls2_b), (reg2_w, reg2_b)):
+        ci = w.shape[1]
+        wf = _f32(w, device).reshape(w.shape[0], ci, 1)
+        check(lib.v2x_pack_conv_weights(_ptr(wf), _ptr(_f32(b, device)), None, None, None, None, BN_EPS, w.shape[0],
+                                        ci, 1, 0, ci, ci, 0, 0, _ptr(w2), _ptr(b2), planes, n2, n1, row, koff, 1,
+                                        _stream()), "v2x_pack_conv_weights(head2)")
+        row += w.shape[0]
+        koff += ci
+    head2 = PackedConv(w2, b2, [n1], 1, 1, n2, n2, planes)
+    return head1, head2, cls2_w.shape[0]
+
+
+def pick_block_n(cout: int, m_tiles: int, sms: int = 148) -> int:
+    """Largest N tile that still gives at least one CTA per SM (small deep layers split N instead of M)."""
+    cands = [bn for bn in (256, 128, 64, 32) if cout % bn == 0]
+    if not cands:
+        return 48 if cout % 48 == 0 else 32
+    for bn in cands:
+        if m_tiles * (cout // bn) >= sms:
+            return bn
+    return cands[-1]
+
+
+class ConvLaunch:
+    """A fully-bound v2x_conv_fwd call (parameters resolved once, replayed every step)."""
+
+    def __init__(self, pc: PackedConv, srcs: Sequence[torch.Tensor], *, epilogue=EPI_ACT, relu=True, upsample2x=False,
+                 out0: torch.Tensor = None, out1: torch.Tensor = None, out_c_off=0, split=0, block_n=None,
+                 passthrough=None, num_agent=None, batch=0, agents=0, crosscheck=False):
+        self.lib = require_gpu()
+        planes, n, h_in, w_in, _ = srcs[0].shape
+        assert planes == pc.planes
+        for s, cp in zip(srcs, pc.cins):
+            assert s.shape[-1] == cp and s.is_contiguous() and s.dtype == torch.bfloat16, (s.shape, cp)
+        h_out, w_out = h_in // pc.stride, w_in // pc.stride
+        p = ConvParams()
+        p.src[0] = srcs[0].data_ptr()
+        p.src[1] = srcs[1].data_ptr() if len(srcs) > 1 else None
+        p.cin[0] = pc.cins[0]
+        p.cin[1] = pc.cins[1] if len(srcs) > 1 else 0
+        p.n_maps, p.h_out, p.w_out, p.stride, p.taps, p.planes = n, h_out, w_out, pc.stride, pc.taps, planes
+        p.weights, p.bias = pc.weights.data_ptr(), pc.bias.data_ptr()
+        p.cout, p.cout_pad = pc.cout, pc.cout_pad
+        m_tiles = n * (h_out // 8) * (w_out // 16)
+        if epilogue == EPI_GRU:
+            p.block_n = 192
+        else:
+            p.block_n = block_n or pick_block_n(pc.cout, m_tiles)
+        p.epilogue, p.relu, p.upsample2x = epilogue, int(relu), int(upsample2x)
+        p.out0 = out0.data_ptr()
+        p.out1 = out1.data_ptr() if out1 is not None else None
+        p.out_c_total = out0.shape[-1] if epilogue != EPI_F32_SPLIT else 0
+        p.out_c_off, p.split = out_c_off, split
+        p.gru_bhn = pc.gru_bhn.data_ptr() if pc.gru_bhn is not None else None
+        p.passthrough = passthrough.data_ptr() if passthrough is not None else None
+        p.num_agent = num_agent.data_ptr() if num_agent is not None else None
+        p.batch, p.agents = batch, agents
+        self.p = p
+        self.keep = (pc, list(srcs), out0, out1, passthrough, num_agent)
+        self.fn = self.lib.v2x_conv_fwd_crosscheck if crosscheck else self.lib.v2x_conv_fwd
+        self.flops = 2.0 * n * h_out * w_out * pc.cout * pc.taps * sum(pc.cins)
+
+    def __call__(self):
+        check(self.fn(C.byref(self.p), _stream()), "v2x_conv_fwd")
+
+
+def conv(pc: PackedConv, srcs, *, relu=True, upsample2x=False, out=None, block_n=None, crosscheck=False):
+    """One-off fused conv + (folded BN) + ReLU -> act."""
+    planes, n, h_in, w_in, _ = srcs[0].shape
+    up = 2 if upsample2x else 1
+    if out is None:
+        out = empty_act(planes, n, h_in // pc.stride * up, w_in // pc.stride * up, pc.cout, srcs[0].device)
+    ConvLaunch(pc, srcs, relu=relu, upsample2x=upsample2x, out0=out, block_n=block_n, crosscheck=crosscheck)()
+    return out
+
+
+def warp_mean(x: torch.Tensor, trans: torch.Tensor, num_agent: torch.Tensor, batch: int, agents: int, *,
+              include_self=False, only_v2i=False, out=None) -> torch.Tensor:
+    """Cross-agent bilinear warp + neighbour mean of agent-major maps ``x`` [P, A*B, H, W, C]."""
+    lib = require_gpu()
+    planes, n, h, w, c = x.shape
+    assert n == batch * agents
+    assert trans.dtype == torch.float64 and trans.is_cuda and trans.is_contiguous()
+    assert num_agent.dtype == torch.int64 and num_agent.is_cuda and num_agent.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.v2x_warp_mean_fwd(_ptr(x), _ptr(out), _ptr(trans), _ptr(num_agent), batch, agents, h, w, c, planes,
+                                int(include_self), int(only_v2i), _stream()), "v2x_warp_mean_fwd")
+    return out
