@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the 5-agent V2VNet detection forward on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our sm_100a path (one rank per GPU)
+  python bench.py --impl reference ...                      the reference CPU path (oracle port) on host cores
+
+A *frame* is one scene: all 5 agents' 256x256x13 BEVs -> all agents' loc/cls (BASELINE.json,
+SURVEY.md section 8(d)).  A *step* is one forward over ``--scenes`` scenes per GPU (default 8, so the
+step's inputs, 8 x 17 MB fp32, exceed the 126 MB L2 and nothing survives between timed steps).
+
+  value  frames/s with inputs resident in HBM, CUDA-graph replay, CUDA events on the launch stream
+  e2e    frames/s through the drop-in ``coperception.models.det.V2VNet.forward`` with pinned HOST
+         inputs: H2D of bevs/trans/num_agent and D2H of loc+cls (fp32, as the reference's predict_all
+         moves them, CoDetModule.py:484-511 -> detection_util.py:256) inside the timed region
+  roofline   the conv implicit-GEMM kernel family: algorithmic conv FLOPs / summed live per-launch time
+  cpu_baseline  the oracle port (the reference's CPU algorithm) on this host, bounded sample
+
+Multi-GPU (N > 1): scenes are sharded across ranks (weak scaling, no data-path collective: a scene's
+agents stay on one rank); timing = max over ranks of the device time between barriers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "v2x-sim_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+AGENTS = 5
+GNN_ITER = 3
+# algorithmic conv/linear FLOPs per frame (A=5), SURVEY.md section 8(d) / BASELINE.md section 2
+GFLOP_PER_FRAME = 264.51
+METRIC = "frames/sec 5-agent V2VNet fwd"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1450.0))),
+                "tflops_burst": float(d.get("bf16_tflops", 0.0)), "hbm_gbs": float(d.get("hbm_gbs", 0.0)),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md: 1.59 PF burst / ~1.4 PF sustained)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference(steps, warmup, scenes=1):
+    """The reference's CPU algorithm (oracle port, literal restatement incl. the W_hh conv over the zero
+    hidden state and per-round warps) on this host's cores.  Returns (frames/s, seconds per frame, threads)."""
+    from oracle import restate, synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.v2vnet_det_state(0)
+    bevs, trans, nat = synth.make_scene(scenes, AGENTS, seed=0)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=scenes, agent_num=AGENTS, gnn_iter=GNN_ITER)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return scenes / med, med / scenes, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    fps, spf, threads = cpu_reference(steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": spf * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "V2VNet 5-agent detection fwd, 256x256x13 BEV, 1 scene/step, reference CPU path"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": "%d timed forwards of 1 scene (5 agents), median; torch CPU fp32, %d threads"
+                                       % (steps, threads)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def time_per_launch(plan, iters=3):
+    """Live per-launch device time of every bound launch (CUDA events on the launch stream)."""
+    n = len(plan.launches)
+    tot = [0.0] * n
+    for _ in range(iters):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record()
+        for i, l in enumerate(plan.launches):
+            l()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        for i in range(n):
+            tot[i] += evs[i].elapsed_time(evs[i + 1])
+    return [t / iters for t in tot]
+
+
+def run_ours(args, rank, world, local_rank):
+    from oracle import synth  # synthetic weights / inputs only (not on the measured path)
+    from v2x_b200 import default_det_config, nets
+    from coperception.models.det import V2VNet
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    planes = {"bf16": 1, "bf16x3": 2}[args.precision]
+    B = args.scenes
+    sd = synth.v2vnet_det_state(0)
+    bevs, trans, nat = synth.make_scene(B, AGENTS, seed=rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---------------- value: device-resident inputs, graph replay ----------------
+    plan = nets.V2VNetDetPlan(sd, B, AGENTS, gnn_iter=GNN_ITER, planes=planes, device=dev)
+    plan.set_inputs(bevs.to(dev), trans.to(dev), nat.to(dev))
+    torch.cuda.synchronize()
+    per_launch = time_per_launch(plan) if rank == 0 else None
+    plan.capture()
+    for _ in range(args.warmup):
+        plan.run()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        plan.run()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    frames = B * world * args.steps
+    value = frames / (ms_total * 1e-3)
+
+    # ---------------- e2e: drop-in module, pinned host buffers, H2D + D2H in the timed region ----------------
+    model = V2VNet(default_det_config(), GNN_ITER, 3, 256, num_agent=AGENTS)
+    model.load_state_dict(sd, strict=True)
+    model.precision = args.precision
+    model = model.to(dev).eval()
+    NBUF = 2
+    h_bev = [bevs.clone().pin_memory() for _ in range(NBUF)]
+    h_trans = [trans.clone().pin_memory() for _ in range(NBUF)]
+    h_nat = [nat.clone().pin_memory() for _ in range(NBUF)]
+    d_bev = [torch.empty_like(bevs, device=dev) for _ in range(NBUF)]
+    d_trans = [torch.empty_like(trans, device=dev) for _ in range(NBUF)]
+    d_nat = [torch.empty_like(nat, device=dev) for _ in range(NBUF)]
+    n_maps = B * AGENTS
+    h_loc = [torch.empty((n_maps, 256, 256, 6, 1, 6), dtype=torch.float32).pin_memory() for _ in range(NBUF)]
+    h_cls = [torch.empty((n_maps, 256 * 256 * 6, 2), dtype=torch.float32).pin_memory() for _ in range(NBUF)]
+    d_loc = [torch.empty((n_maps, 256, 256, 6, 1, 6), dtype=torch.float32, device=dev) for _ in range(NBUF)]
+    d_cls = [torch.empty((n_maps, 256 * 256 * 6, 2), dtype=torch.float32, device=dev) for _ in range(NBUF)]
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream()
+    in_ready = [torch.cuda.Event() for _ in range(NBUF)]
+    in_free = [torch.cuda.Event() for _ in range(NBUF)]
+    out_ready = [torch.cuda.Event() for _ in range(NBUF)]
+    out_free = [torch.cuda.Event() for _ in range(NBUF)]
+
+    def e2e_steps(k):
+        """Software-pipelined: H2D of step i+1 and D2H of step i-1 overlap the forward of step i
+        (three streams); every step's inputs come from host memory and its outputs land in host memory."""
+        for i in range(k):
+            b = i % NBUF
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(in_free[b])
+                d_bev[b].copy_(h_bev[b], non_blocking=True)
+                d_trans[b].copy_(h_trans[b], non_blocking=True)
+                d_nat[b].copy_(h_nat[b], non_blocking=True)
+                in_ready[b].record(s_in)
+            main.wait_event(in_ready[b])
+            with torch.no_grad():
+                out = model(d_bev[b], d_trans[b], d_nat[b], batch_size=B)
+            in_free[b].record(main)
+            main.wait_event(out_free[b])
+            d_loc[b].copy_(out["loc"], non_blocking=True)  # plan outputs are reused next step: snapshot them
+            d_cls[b].copy_(out["cls"], non_blocking=True)
+            out_ready[b].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(out_ready[b])
+                h_loc[b].copy_(d_loc[b], non_blocking=True)
+                h_cls[b].copy_(d_cls[b], non_blocking=True)
+                out_free[b].record(s_out)
+        main.wait_stream(s_out)
+        main.wait_stream(s_in)
+
+    e2e_steps(max(2, args.warmup))
+    torch.cuda.synchronize()
+    barrier()
+    e0.record()
+    e2e_steps(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = frames / (e2e_ms * 1e-3)
+    h2d = bevs.numel() * 4 + trans.numel() * 8 + nat.numel() * 8
+    d2h = (h_loc[0].numel() + h_cls[0].numel()) * 4
+
+    if rank != 0:
+        return
+    # ---------------- roofline of the conv kernel family (live per-launch events) ----------------
+    peaks = measured_peaks()
+    conv_ms, layers = 0.0, []
+    for l, ms_l in zip(plan.launches, per_launch):
+        fl = getattr(l, "flops", 0.0)
+        if fl > 0:
+            conv_ms += ms_l
+            layers.append((ms_l, fl))
+    step_ms_eager = sum(per_launch)
+    alg_flops = GFLOP_PER_FRAME * 1e9 * B
+    achieved = alg_flops / (conv_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "v2x::conv_tc_kernel<BN> (all %d conv launches of a step)" % len(layers),
+                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                "traffic": None, "peak_source": peaks["source"],
+                "conv_ms_per_step": conv_ms, "all_kernels_ms_per_step_eager": step_ms_eager,
+                "conv_share_of_step": conv_ms / step_ms_eager,
+                "whole_step_tflops": alg_flops / (ms_total / args.steps * 1e-3) / 1e12,
+                "algorithmic_gflop_per_frame": GFLOP_PER_FRAME}
+
+    # ---------------- CPU baseline (oracle port) on this host, bounded sample ----------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        fps, spf, threads = cpu_reference(3, 1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "3 timed forwards of 1 scene (5 agents), median %.3f s/frame; torch CPU fp32" % spf}
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if planes == 1 else "bf16x3", "data": "synthetic",
+            "config": {"workload": "V2VNet 5-agent detection fwd, 256x256x13 BEV, gnn_iter=3, layer=3 (BASELINE configs[1])",
+                       "scenes_per_gpu_per_step": B, "agents": AGENTS, "precision": args.precision,
+                       "l2": "no flush: per-step inputs %.0f MB and activations ~%.1f GB exceed the 126 MB L2"
+                             % (B * 17.04, 0.4 * B),
+                       "parallelism": "scene-sharded x%d, no data-path collective" % world},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": "coperception.models.det.V2VNet.forward (pinned host in/out, 3-stream pipeline)"},
+            "gpu_launches": plan.n_kernels * args.steps,
+            "kernels_per_step": plan.n_kernels,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes", type=int, default=8, help="scenes (frames) per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,44 @@
+"""coperception.models.det.V2VNet on the sm_100a path (reference: CP/models/det/V2VNet.py:8-120)."""
+import torch
+
+from ._base import B200DetModel
+from ._schema import BackboneParams, Conv2dGRUParams
+
+
+class V2VNet(B200DetModel):
+    """V2VNet (https://arxiv.org/abs/2008.07519): per-agent BEV encoder, ``gnn_iter_times`` rounds of
+    warp -> neighbour mean -> ConvGRU at layer 3, decoder, detection heads.
+
+    Constructor and forward signatures, parameter names and the returned dict match the reference
+    (V2VNet.py:14-24, :47, :120); u_encoder / decoder each carry a full Backbone parameter set
+    (IntermediateModelBase.py:24-25)."""
+
+    def __init__(self, config, gnn_iter_times, layer, layer_channel, in_channels=13, num_agent=5, compress_level=0,
+                 only_v2i=False):
+        super().__init__(config, layer, in_channels, num_agent=num_agent, only_v2i=only_v2i)
+        if layer != 3 or layer_channel != 256:
+            raise NotImplementedError("v2x_b200 V2VNet fuses at layer 3 (256 channels) as the reference scripts do "
+                                      "(train_codet.py:106-114)")
+        if compress_level != 0:
+            raise NotImplementedError("compress_level > 0 is not built on the sm_100a path yet")
+        self.u_encoder = BackboneParams(in_channels, compress_level)
+        self.decoder = BackboneParams(in_channels)
+        self.layer_channel = layer_channel
+        self.gnn_iter_num = gnn_iter_times
+        self.convgru = Conv2dGRUParams(layer_channel * 2, layer_channel, 3)
+        self.compress_level = compress_level
+
+    def forward(self, bevs, trans_matrices, num_agent_tensor, batch_size=1):
+        """bevs [A*B,1,256,256,13] (agent-major), trans_matrices [B,A,A,4,4], num_agent_tensor [B,A]
+        -> {"loc": [A*B,256,256,6,1,6], "cls": [A*B,393216,2]} (fp32, on bevs.device)."""
+        from v2x_b200 import nets
+        self._check_eval()
+        dev = bevs.device
+        if dev.type != "cuda":
+            raise RuntimeError("v2x_b200 V2VNet needs CUDA tensors (no CPU fallback); got %s" % dev)
+        assert bevs.shape[0] == batch_size * self.agent_num, "bevs must hold batch_size * num_agent maps"
+        key = ("v2v", int(batch_size), dev.index, self.precision)
+        plan = self._get_plan(key, lambda: nets.V2VNetDetPlan(
+            self._state(), int(batch_size), self.agent_num, gnn_iter=self.gnn_iter_num, planes=self._planes(),
+            device=dev, only_v2i=self.only_v2i))
+        return plan.forward(bevs.to(torch.float32), trans_matrices.to(torch.float64), num_agent_tensor.to(torch.int64))
