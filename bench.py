@@ -101,22 +101,35 @@ class ClockSampler:
 
 def cpu_reference(steps, warmup, scenes=1):
     """The reference's CPU algorithm (oracle port, literal restatement incl. the W_hh conv over the zero
-    hidden state and per-round warps) on this host's cores.  Returns (frames/s, seconds per frame, threads)."""
+    hidden state and per-round warps) on this host's cores.  torch's CPU backend gets slower, not faster,
+    when handed every core of a big host for these small convolutions, so the thread count is chosen
+    from {8, 16, 32, 64, all} by one probe forward each and the best one is used and reported.
+    Returns (frames/s, seconds per frame, threads)."""
     from oracle import restate, synth
-    torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.v2vnet_det_state(0)
     bevs, trans, nat = synth.make_scene(scenes, AGENTS, seed=0)
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
+
+    def fwd():
+        t0 = time.perf_counter()
+        with torch.no_grad():
             restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=scenes, agent_num=AGENTS, gnn_iter=GNN_ITER)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
+        return time.perf_counter() - t0
+
+    ncpu = os.cpu_count() or 1
+    best_t, best_n = None, None
+    for n in sorted({min(c, ncpu) for c in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(n)
+        fwd()
+        dt = fwd()
+        if best_t is None or dt < best_t:
+            best_t, best_n = dt, n
+        if dt > 20.0:
+            break
+    torch.set_num_threads(best_n)
+    times = [fwd() for _ in range(warmup + steps)][warmup:]
     times.sort()
     med = times[len(times) // 2]
-    return scenes / med, med / scenes, torch.get_num_threads()
+    return scenes / med, med / scenes, best_n
 
 
 def run_reference(args, rank, world):
@@ -129,8 +142,8 @@ def run_reference(args, rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "V2VNet 5-agent detection fwd, 256x256x13 BEV, 1 scene/step, reference CPU path"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": "%d timed forwards of 1 scene (5 agents), median; torch CPU fp32, %d threads"
-                                       % (steps, threads)},
+                             "sample": "%d timed forwards of 1 scene (5 agents), median; torch CPU fp32, best of "
+                                       "{8,16,32,64,all} threads = %d" % (steps, threads)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -291,7 +304,8 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_cpu_baseline:
         fps, spf, threads = cpu_reference(3, 1)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "3 timed forwards of 1 scene (5 agents), median %.3f s/frame; torch CPU fp32" % spf}
+               "sample": "3 timed forwards of 1 scene (5 agents), median %.3f s/frame; torch CPU fp32, best of "
+                         "{8,16,32,64,all} threads" % spf}
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -313,7 +327,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=8, help="scenes (frames) per GPU per step")

@@ -27,7 +27,9 @@
 
 namespace v2x {
 
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
+constexpr int kNumThreads = 192;
+constexpr int kSmemLimit = 227 * 1024 - 2048;  // dynamic smem we may opt into (static barriers live beside it)
 constexpr int kTileH = 8;
 constexpr int kTileW = 16;
 
@@ -40,6 +42,12 @@ struct ConvDev {
   int num_k;
   int num_stages;
   int tiles_w, tiles_per_img;
+  int m_tiles, n_tiles;
+  int b_resident;            // whole [BN x K] weight operand kept in smem for the CTA's lifetime
+  uint32_t b_region_bytes;   // bytes reserved for it in front of the stage ring
+  int kb_per_stage;          // k-blocks (tap x kc channels) per pipeline stage: one mbarrier round trip feeds them all
+  int stages_per_tile;       // ceil(num_k / kb_per_stage)
+  uint32_t kb_bytes, kb_tx_bytes;  // smem footprint / TMA bytes of one k-block
   int cout, cout_pad;
   int epilogue, relu, upsample2x;
   void* out0;
@@ -103,12 +111,18 @@ __device__ __forceinline__ void epi_f32_split16(const ConvDev& p, int n_img, int
   const long long pix = ((long long)n_img * p.h_out + oh) * p.w_out + ow;
   float* o0 = reinterpret_cast<float*>(p.out0) + pix * p.split;
   float* o1 = reinterpret_cast<float*>(p.out1) + pix * (p.cout - p.split) - p.split;
+  // split, cout and both row strides are multiples of 4 (checked on the host): 16-byte stores
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int ch = ch0 + i;
+  for (int g = 0; g < 4; ++g) {
+    const int ch = ch0 + 4 * g;
     if (ch < p.cout) {
-      const float y = v[i] + __ldg(p.bias + ch);
-      if (ch < p.split) o0[ch] = y; else o1[ch] = y;
+      float4 y;
+      y.x = v[4 * g + 0] + __ldg(p.bias + ch + 0);
+      y.y = v[4 * g + 1] + __ldg(p.bias + ch + 1);
+      y.z = v[4 * g + 2] + __ldg(p.bias + ch + 2);
+      y.w = v[4 * g + 3] + __ldg(p.bias + ch + 3);
+      float* dst = ch < p.split ? o0 + ch : o1 + ch;
+      *reinterpret_cast<float4*>(dst) = y;
     }
   }
 }
@@ -145,36 +159,48 @@ __device__ __forceinline__ bool gru_unit_absent(const ConvDev& p, int n_img) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tensor-core kernel
+// Tensor-core kernel: persistent, warp-specialised (192 threads)
+//   warp 0 / lane 0 : TMA producer (A boxes every stage; weights either streamed with A or loaded
+//                     once per CTA when the whole [BN x K] operand fits in shared memory)
+//   warp 1 / lane 0 : tcgen05.mma issuer; alternates between two TMEM accumulator buffers
+//   warps 2..5      : epilogue (tcgen05.ld -> bias/ReLU/gates -> global); warp w owns TMEM lane
+//                     quadrant w % 4, so tile row = (w % 4) * 32 + lane
+// grid = (ctas_x, n_tiles): a CTA keeps its N tile (blockIdx.y) and walks M tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...  The epilogue of tile i overlaps the main loop of tile
+// i+1 through the two accumulator buffers (tmem_full / tmem_empty mbarriers).
 // ---------------------------------------------------------------------------------------------
-template <int BN>
-__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
-                                                      const __grid_constant__ CUtensorMap tmA1,
-                                                      const __grid_constant__ CUtensorMap tmB, const ConvDev p) {
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+struct TileCoord {
+  int n_img, oh0, ow0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvDev& p, int tile) {
+  TileCoord t;
+  t.n_img = tile / p.tiles_per_img;
+  const int trem = tile - t.n_img * p.tiles_per_img;
+  t.oh0 = (trem / p.tiles_w) * kTileH;
+  t.ow0 = (trem % p.tiles_w) * kTileW;
+  return t;
+}
+
+template <int BN, int PLANES>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                                 const __grid_constant__ CUtensorMap tmA1,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const ConvDev p) {
+  constexpr uint32_t ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int n_img = tile / p.tiles_per_img;
-  const int trem = tile - n_img * p.tiles_per_img;
-  const int oh0 = (trem / p.tiles_w) * kTileH;
-  const int ow0 = (trem % p.tiles_w) * kTileW;
   const int n0 = blockIdx.y * BN;
-  const int row = threadIdx.x;
-  const int oh = oh0 + (row >> 4), ow = ow0 + (row & 15);
-
-  if (gru_unit_absent(p, n_img)) {  // CTA-uniform
-    copy_passthrough(p, n_img, oh, ow, blockIdx.y * 64, 64);
-    return;
-  }
-
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // resident weights first, then the stage ring
+  const uint32_t ring_base = smem_base + p.b_region_bytes;
   const uint32_t bar_full = smem_u32(&bars[0]);
   const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
-  const uint32_t bar_tmem = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bar_bres = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages + 1]);   // [2]
+  const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 3]);  // [2]
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA0);
@@ -184,7 +210,11 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_tmem, 1);
+    mbar_init(bar_bres, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);  // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -196,96 +226,157 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  // NOTE: the producer and MMA loops are executed by ALL 32 lanes of their warp with warp-uniform
+  // control flow and values; only the issuing instructions sit under elect_one().  Running the loops
+  // under `if (lane == 0)` instead makes the compiler wrap every tcgen05.mma / TMA in a divergence
+  // "waterfall" (ELECT/BRA.U.ANY), ~200 cycles per instruction -- measured, see DESIGN.md.
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int stage = 0, phase = 0, kidx = 0;
-      for (int s = 0; s < p.nsrc; ++s) {
-        const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap % 3 : 1;
-          for (int cb = 0; cb < p.cblocks[s]; ++cb, ++kidx) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            const uint32_t full = bar_full + 8 * stage;
-            mbar_expect_tx(full, p.tx_bytes);
-            const uint32_t sa = smem_base + stage * p.stage_bytes;
-            for (int pl = 0; pl < p.planes; ++pl) {
+    // ===== TMA producer =====
+    if (p.b_resident && elect_one()) {
+      mbar_expect_tx(bar_bres, (uint32_t)p.num_k * PLANES * (uint32_t)(BN * p.kc * 2));
+      for (int k = 0; k < p.num_k; ++k)
+        for (int pl = 0; pl < PLANES; ++pl)
+          tma_load_2d(smem_base + (k * PLANES + pl) * p.b_tile_bytes, &tmB, bar_bres, k * p.kc, pl * p.cout_pad + n0);
+    }
+    __syncwarp();
+    int stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      if (gru_unit_absent(p, tc.n_img)) continue;
+      int kidx = 0, s = 0, tap = 0, cb = 0;  // k-block cursor: source, filter tap, channel block
+      for (int ks = 0; ks < p.stages_per_tile; ++ks) {
+        const int nblk = min(p.kb_per_stage, p.num_k - kidx);
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        const uint32_t full = bar_full + 8 * stage;
+        const bool leader = elect_one();
+        if (leader) mbar_expect_tx(full, nblk * p.kb_tx_bytes);
+        uint32_t sa = ring_base + stage * p.stage_bytes;
+        for (int j = 0; j < nblk; ++j, ++kidx, sa += p.kb_bytes) {
+          const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
+          const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap - 3 * (tap / 3) : 1;
+          if (leader) {
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl) {
               const uint32_t dst = sa + pl * p.a_tile_bytes;
-              const int img = pl * p.n_maps + n_img;
+              const int img = pl * p.n_maps + tc.n_img;
               if (p.stride == 1) {
-                tma_load_4d(dst, tmA, full, cb * p.kc, ow0 + kw - 1, oh0 + kh - 1, img);
+                tma_load_4d(dst, tmA, full, cb * p.kc, tc.ow0 + kw - 1, tc.oh0 + kh - 1, img);
               } else {
                 // input row 2*oh + kh - 1 = 2*(oh + hoff) + hp
                 const int hp = kh == 1 ? 0 : 1, hoff = kh == 0 ? -1 : 0;
                 const int wp = kw == 1 ? 0 : 1, woff = kw == 0 ? -1 : 0;
-                tma_load_5d(dst, tmA, full, wp * p.cin[s] + cb * p.kc, ow0 + woff, hp, oh0 + hoff, img);
+                tma_load_5d(dst, tmA, full, wp * p.cin[s] + cb * p.kc, tc.ow0 + woff, hp, tc.oh0 + hoff, img);
               }
             }
-            const uint32_t sb = sa + p.planes * p.a_tile_bytes;
-            for (int pl = 0; pl < p.planes; ++pl)
-              tma_load_2d(sb + pl * p.b_tile_bytes, &tmB, full, kidx * p.kc, pl * p.cout_pad + n0);
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+            if (!p.b_resident) {
+              const uint32_t sb = sa + PLANES * p.a_tile_bytes;
+#pragma unroll
+              for (int pl = 0; pl < PLANES; ++pl)
+                tma_load_2d(sb + pl * p.b_tile_bytes, &tmB, full, kidx * p.kc, pl * p.cout_pad + n0);
+            }
+          }
+          if (++cb == p.cblocks[s]) {
+            cb = 0;
+            if (++tap == p.taps) { tap = 0; ++s; }
           }
         }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
-      int stage = 0, phase = 0;
-      uint32_t acc = 0;
-      const int ksteps = p.kc / 16;
-      for (int k = 0; k < p.num_k; ++k) {
-        mbar_wait(bar_full + 8 * stage, phase);
-        tc_fence_after();
-        const uint32_t a0 = smem_base + stage * p.stage_bytes;
-        const uint32_t b0 = a0 + p.planes * p.a_tile_bytes;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t da = make_smem_desc(a0 + kk * 32, p.sbo, p.layout_type);
-          const uint64_t db = make_smem_desc(b0 + kk * 32, p.sbo, p.layout_type);
-          umma_bf16(tmem_base, da, db, idesc, acc);
-          acc = 1;
-          if (p.planes == 2) {
-            const uint64_t da1 = make_smem_desc(a0 + p.a_tile_bytes + kk * 32, p.sbo, p.layout_type);
-            const uint64_t db1 = make_smem_desc(b0 + p.b_tile_bytes + kk * 32, p.sbo, p.layout_type);
-            umma_bf16(tmem_base, da, db1, idesc, 1);
-            umma_bf16(tmem_base, da1, db, idesc, 1);
-          }
-        }
-        umma_commit(bar_empty + 8 * stage);
+        __syncwarp();
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(bar_tmem);
     }
-    __syncwarp();
-  }
-
-  // ===== epilogue: all 4 warps, warp w reads TMEM lanes [32w, 32w+32) =====
-  mbar_wait(bar_tmem, 0);
-  tc_fence_after();
-  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-  if (p.epilogue == V2X_EPI_GRU) {
-    if constexpr (BN == 192) {
-#pragma unroll 1
-      for (int c16 = 0; c16 < 4; ++c16) {
-        float r[16], z[16], nn[16];
-        tmem_ld16(taddr + c16 * 16, r);
-        tmem_ld16(taddr + 64 + c16 * 16, z);
-        tmem_ld16(taddr + 128 + c16 * 16, nn);
-        epi_gru16(p, n_img, oh, ow, blockIdx.y * 64 + c16 * 16, n0 + c16 * 16, r, z, nn);
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
+    if (p.b_resident) mbar_wait(bar_bres, 0);
+    int stage = 0, phase = 0, it = 0;
+    const int ksteps = p.kc / 16;
+    const uint32_t a_plane = p.a_tile_bytes >> 4, b_plane = p.b_tile_bytes >> 4;  // descriptor address units
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      if (gru_unit_absent(p, decode_tile(p, tile).n_img)) continue;
+      const int acc_buf = it & 1;
+      mbar_wait(bar_tempty + 8 * acc_buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc_buf * ACC_STRIDE;
+      uint32_t acc = 0;
+      int kidx = 0;
+      for (int ks = 0; ks < p.stages_per_tile; ++ks) {
+        const int nblk = min(p.kb_per_stage, p.num_k - kidx);
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t a_stage = ring_base + stage * p.stage_bytes;
+        const uint32_t b_stage = p.b_resident ? smem_base + kidx * PLANES * p.b_tile_bytes : a_stage + PLANES * p.a_tile_bytes;
+        const uint32_t b_step = p.b_resident ? PLANES * p.b_tile_bytes : p.kb_bytes;
+        // descriptors differ only in the 14-bit start-address field: add (bytes >> 4) to the low word
+        uint64_t da0 = make_smem_desc(a_stage, p.sbo, p.layout_type);
+        uint64_t db0 = make_smem_desc(b_stage, p.sbo, p.layout_type);
+        if (elect_one()) {
+          for (int j = 0; j < nblk; ++j) {
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint64_t da = da0 + (uint64_t)(kk * 2), db = db0 + (uint64_t)(kk * 2);
+              umma_bf16(tmem_d, da, db, idesc, acc);
+              acc = 1;
+              if (PLANES == 2) {
+                umma_bf16(tmem_d, da, db + b_plane, idesc, 1);
+                umma_bf16(tmem_d, da + a_plane, db, idesc, 1);
+              }
+            }
+            da0 += p.kb_bytes >> 4;
+            db0 += b_step >> 4;
+          }
+          umma_commit(bar_empty + 8 * stage);
+        }
+        __syncwarp();
+        acc = 1;
+        kidx += nblk;
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(bar_tfull + 8 * acc_buf);
+      __syncwarp();
+      ++it;
     }
   } else {
+    // ===== epilogue warps =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int oh = tc.oh0 + (row >> 4), ow = tc.ow0 + (row & 15);
+      if (gru_unit_absent(p, tc.n_img)) {
+        copy_passthrough(p, tc.n_img, oh, ow, blockIdx.y * 64, 64);
+        continue;
+      }
+      const int acc_buf = it & 1;
+      mbar_wait(bar_tfull + 8 * acc_buf, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc_buf * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+      if (p.epilogue == V2X_EPI_GRU) {
+        if constexpr (BN == 192) {
 #pragma unroll 1
-    for (int c16 = 0; c16 < BN / 16; ++c16) {
-      const int ch0 = n0 + c16 * 16;
-      if (ch0 >= p.cout) break;
-      float v[16];
-      tmem_ld16(taddr + c16 * 16, v);
-      if (p.epilogue == V2X_EPI_ACT) epi_act16(p, n_img, oh, ow, ch0, v);
-      else epi_f32_split16(p, n_img, oh, ow, ch0, v);
+          for (int c16 = 0; c16 < 4; ++c16) {
+            float r[16], z[16], nn[16];
+            tmem_ld16(taddr + c16 * 16, r);
+            tmem_ld16(taddr + 64 + c16 * 16, z);
+            tmem_ld16(taddr + 128 + c16 * 16, nn);
+            epi_gru16(p, tc.n_img, oh, ow, blockIdx.y * 64 + c16 * 16, n0 + c16 * 16, r, z, nn);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c16 = 0; c16 < BN / 16; ++c16) {
+          const int ch0 = n0 + c16 * 16;
+          if (ch0 >= p.cout) break;
+          float v[16];
+          tmem_ld16(taddr + c16 * 16, v);
+          if (p.epilogue == V2X_EPI_ACT) epi_act16(p, tc.n_img, oh, ow, ch0, v);
+          else epi_f32_split16(p, tc.n_img, oh, ow, ch0, v);
+        }
+      }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16): release the buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc_buf);
+      ++it;
     }
   }
 
@@ -437,6 +528,8 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
   }
   d.tiles_w = p->w_out / kTileW;
   d.tiles_per_img = d.tiles_w * (p->h_out / kTileH);
+  d.m_tiles = p->n_maps * d.tiles_per_img;
+  d.n_tiles = p->cout_pad / p->block_n;
   d.cout = p->cout; d.cout_pad = p->cout_pad;
   d.epilogue = p->epilogue; d.relu = p->relu; d.upsample2x = p->upsample2x;
   d.out0 = p->out0; d.out1 = p->out1;
@@ -461,6 +554,7 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
     case V2X_EPI_F32_SPLIT:
       V2X_REQUIRE(p->out1 != nullptr || p->split >= p->cout, "F32_SPLIT needs out1");
       V2X_REQUIRE(p->split > 0 && p->split <= p->cout, "bad split");
+      V2X_REQUIRE(p->split % 4 == 0 && p->cout % 4 == 0, "F32_SPLIT needs split %% 4 == 0 and cout %% 4 == 0");
       V2X_REQUIRE(!p->upsample2x, "upsample2x only with EPI_ACT");
       break;
     case V2X_EPI_GRU:
@@ -479,17 +573,36 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
   return V2X_OK;
 }
 
-template <int BN>
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int PLANES>
 static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                      size_t smem, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-  dim3 grid(d.n_maps * d.tiles_per_img, d.cout_pad / BN);
-  conv_tc_kernel<BN><<<grid, 128, smem, stream>>>(a0, a1, b, d);
+  // persistent grid: one CTA per SM, split between the N tiles (every CTA keeps one N tile)
+  int ctas_x = sm_count() / d.n_tiles;
+  if (ctas_x < 1) ctas_x = 1;
+  if (ctas_x > d.m_tiles) ctas_x = d.m_tiles;
+  // balance: no CTA should walk more M tiles than ceil(m_tiles / ctas_x); shrink the grid to the
+  // smallest one with the same number of rounds (fewer CTAs -> fewer resident-weight loads)
+  const int rounds = (d.m_tiles + ctas_x - 1) / ctas_x;
+  ctas_x = (d.m_tiles + rounds - 1) / rounds;
+  dim3 grid(ctas_x, d.n_tiles);
+  conv_tc_kernel<BN, PLANES><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, d);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }
@@ -505,14 +618,39 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int bn = p->block_n;
 
-  // pipeline depth: prefer >= 3 stages within a 2-CTA/SM budget, else use most of the SM
-  int stages = (int)(100 * 1024 / d.stage_bytes);
-  if (stages < 3) stages = (int)(200 * 1024 / d.stage_bytes);
+  // Shared-memory plan.  Small weight operands (all of [block_n x K], e.g. the C=32 layers at 256x256)
+  // stay resident for the CTA's lifetime so only activations stream; otherwise weights ride in the
+  // stage ring next to their A tile.  The ring takes whatever is left, up to kMaxStages deep.
+  const uint32_t b_all = (uint32_t)d.num_k * p->planes * d.b_tile_bytes;
+  const uint32_t a_stage = p->planes * d.a_tile_bytes;
+  const uint32_t budget = (uint32_t)kSmemLimit - 1024u;
+  d.b_resident = (b_all <= 96u * 1024u && b_all + 4u * a_stage <= budget) ? 1 : 0;
+  if (d.b_resident) {
+    d.b_region_bytes = b_all;
+    d.stage_bytes = a_stage;
+    d.tx_bytes = a_stage;
+  } else {
+    d.b_region_bytes = 0;
+  }
+  // One k-block = one filter tap x kc channels (one A box [+ its weight tile]).  A pipeline stage carries
+  // several k-blocks so that each mbarrier round trip (a few hundred cycles of single-thread latency on
+  // both the producer and the MMA side) feeds >= ~24 KB of operands; tiny stages starve the tensor core.
+  d.kb_bytes = d.stage_bytes;
+  d.kb_tx_bytes = d.tx_bytes;
+  const uint32_t ring = budget - d.b_region_bytes;
+  int g = (int)((28u * 1024u + d.kb_bytes - 1) / d.kb_bytes);
+  if (g > d.num_k) g = d.num_k;
+  while (g > 1 && ring / ((uint32_t)g * d.kb_bytes) < 4) --g;      // keep the ring >= 4 deep
+  for (int t = g; t >= 1 && t * 2 > g; --t)                         // prefer an even split of the k loop
+    if (d.num_k % t == 0) { g = t; break; }
+  d.kb_per_stage = g;
+  d.stages_per_tile = (d.num_k + g - 1) / g;
+  d.stage_bytes = (uint32_t)g * d.kb_bytes;
+  int stages = (int)(ring / d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > d.num_k) stages = d.num_k;
-  V2X_REQUIRE(stages >= 1, "stage of %u bytes does not fit in shared memory", d.stage_bytes);
+  V2X_REQUIRE(stages >= 2, "stage of %u bytes does not fit in shared memory", d.stage_bytes);
   d.num_stages = stages;
-  const size_t smem = (size_t)stages * d.stage_bytes + 1024;
+  const size_t smem = (size_t)d.b_region_bytes + (size_t)stages * d.stage_bytes + 1024;
 
   CUtensorMap tmA[2], tmB;
   const int h_in = p->h_out * p->stride, w_in = p->w_out * p->stride;
@@ -541,14 +679,19 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
     rc = encode_map(&tmB, p->weights, 2, dims, str, box, d.kc);
     if (rc) return rc;
   }
+#define V2X_LAUNCH(BN_)                                                                      \
+  case BN_:                                                                                 \
+    return p->planes == 1 ? launch_tc<BN_, 1>(d, tmA[0], tmA[1], tmB, smem, stream)         \
+                          : launch_tc<BN_, 2>(d, tmA[0], tmA[1], tmB, smem, stream);
   switch (bn) {
-    case 32: return launch_tc<32>(d, tmA[0], tmA[1], tmB, smem, stream);
-    case 48: return launch_tc<48>(d, tmA[0], tmA[1], tmB, smem, stream);
-    case 64: return launch_tc<64>(d, tmA[0], tmA[1], tmB, smem, stream);
-    case 128: return launch_tc<128>(d, tmA[0], tmA[1], tmB, smem, stream);
-    case 192: return launch_tc<192>(d, tmA[0], tmA[1], tmB, smem, stream);
-    case 256: return launch_tc<256>(d, tmA[0], tmA[1], tmB, smem, stream);
+    V2X_LAUNCH(32)
+    V2X_LAUNCH(48)
+    V2X_LAUNCH(64)
+    V2X_LAUNCH(128)
+    V2X_LAUNCH(192)
+    V2X_LAUNCH(256)
   }
+#undef V2X_LAUNCH
   return V2X_ERR_ARG;
 }
 

@@ -164,14 +164,21 @@ def pack_heads(cls1_w, cls1_b, cls_bn, reg1_w, reg1_b, reg_bn, cls2_w, cls2_b, r
 
 
 def pick_block_n(cout: int, m_tiles: int, sms: int = 148) -> int:
-    """Largest N tile that still gives at least one CTA per SM (small deep layers split N instead of M)."""
+    """N tile of the persistent conv kernel: grid = (sms // n_tiles, n_tiles) CTAs, each walking
+    ceil(m_tiles / ctas_x) M tiles.  Cost per 16-deep k-step of a 128 x BN tile ~ max(tensor math BN/2,
+    shared-memory operand reads (128 + BN) / 4) cycles; pick the BN minimising rounds * cost."""
     cands = [bn for bn in (256, 128, 64, 32) if cout % bn == 0]
     if not cands:
         return 48 if cout % 48 == 0 else 32
+    best, best_cost = None, None
     for bn in cands:
-        if m_tiles * (cout // bn) >= sms:
-            return bn
-    return cands[-1]
+        n_tiles = cout // bn
+        ctas_x = max(1, min(m_tiles, sms // n_tiles))
+        rounds = -(-m_tiles // ctas_x)
+        cost = rounds * max(bn / 2.0, (128 + bn) / 4.0)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
 
 
 class ConvLaunch:
