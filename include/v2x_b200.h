@@ -91,6 +91,8 @@ typedef struct v2x_conv_params {
 } v2x_conv_params;
 
 int v2x_conv_fwd(const v2x_conv_params* p, void* stream);
+/* profiling aid: ablate one role of v2x_conv_fwd (0 normal, 1 no MMA, 2 no TMA loads, 3 no global stores); outputs are garbage when != 0 */
+int v2x_set_debug_mode(int mode);
 /* same contract on CUDA cores (no TMA / tcgen05); a test aid to bisect operand-packing vs tensor-core-path bugs */
 int v2x_conv_fwd_crosscheck(const v2x_conv_params* p, void* stream);
 

@@ -29,7 +29,7 @@ namespace v2x {
 
 constexpr int kMaxStages = 12;
 constexpr int kNumThreads = 192;
-constexpr int kSmemLimit = 227 * 1024 - 2048;  // dynamic smem we may opt into (static barriers live beside it)
+constexpr int kSmemLimit = 220 * 1024;  // dynamic smem we opt into; ~5 KB of static smem (k-table, bias, barriers) lives beside it (227 KB per CTA)
 constexpr int kTileH = 8;
 constexpr int kTileW = 16;
 
@@ -48,6 +48,7 @@ struct ConvDev {
   int kb_per_stage;          // k-blocks (tap x kc channels) per pipeline stage: one mbarrier round trip feeds them all
   int stages_per_tile;       // ceil(num_k / kb_per_stage)
   uint32_t kb_bytes, kb_tx_bytes;  // smem footprint / TMA bytes of one k-block
+  int debug_mode;            // profiling ablations (v2x_set_debug_mode): 1 = no MMA, 2 = no TMA, 3 = no stores
   int cout, cout_pad;
   int epilogue, relu, upsample2x;
   void* out0;
@@ -83,6 +84,7 @@ __device__ __forceinline__ void store_act16(const ConvDev& p, int n_img, int oh,
   const int up = p.upsample2x ? 2 : 1;
   const int H = p.h_out * up, W = p.w_out * up;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out0);
+  if (p.debug_mode == 3 && hi[0] != 0x7fc17fc1u) return;  // profiling ablation: keep the math, drop the stores
   for (int dy = 0; dy < up; ++dy)
     for (int dx = 0; dx < up; ++dx) {
       const long long pix = ((long long)n_img * H + (oh * up + dy)) * W + (ow * up + dx);
@@ -98,16 +100,18 @@ __device__ __forceinline__ void store_act16(const ConvDev& p, int n_img, int oh,
     }
 }
 
-__device__ __forceinline__ void epi_act16(const ConvDev& p, int n_img, int oh, int ow, int ch0, float* v) {
+__device__ __forceinline__ void epi_act16(const ConvDev& p, int n_img, int oh, int ow, int ch0, float* v,
+                                          const float* bias16) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    float y = v[i] + __ldg(p.bias + ch0 + i);
+    float y = v[i] + bias16[i];
     v[i] = p.relu ? fmaxf(y, 0.f) : y;
   }
   store_act16(p, n_img, oh, ow, ch0, v);
 }
 
-__device__ __forceinline__ void epi_f32_split16(const ConvDev& p, int n_img, int oh, int ow, int ch0, const float* v) {
+__device__ __forceinline__ void epi_f32_split16(const ConvDev& p, int n_img, int oh, int ow, int ch0, const float* v,
+                                                const float* bias16) {
   const long long pix = ((long long)n_img * p.h_out + oh) * p.w_out + ow;
   float* o0 = reinterpret_cast<float*>(p.out0) + pix * p.split;
   float* o1 = reinterpret_cast<float*>(p.out1) + pix * (p.cout - p.split) - p.split;
@@ -117,25 +121,27 @@ __device__ __forceinline__ void epi_f32_split16(const ConvDev& p, int n_img, int
     const int ch = ch0 + 4 * g;
     if (ch < p.cout) {
       float4 y;
-      y.x = v[4 * g + 0] + __ldg(p.bias + ch + 0);
-      y.y = v[4 * g + 1] + __ldg(p.bias + ch + 1);
-      y.z = v[4 * g + 2] + __ldg(p.bias + ch + 2);
-      y.w = v[4 * g + 3] + __ldg(p.bias + ch + 3);
+      y.x = v[4 * g + 0] + bias16[4 * g + 0];
+      y.y = v[4 * g + 1] + bias16[4 * g + 1];
+      y.z = v[4 * g + 2] + bias16[4 * g + 2];
+      y.w = v[4 * g + 3] + bias16[4 * g + 3];
       float* dst = ch < p.split ? o0 + ch : o1 + ch;
+      if (p.debug_mode == 3 && y.x != 12345.678f) continue;  // profiling ablation: no stores
       *reinterpret_cast<float4*>(dst) = y;
     }
   }
 }
 
-// GRU gates for 16 channels [c0, c0+16) of one pixel; prow = packed row of the r gate of channel c0
-__device__ __forceinline__ void epi_gru16(const ConvDev& p, int n_img, int oh, int ow, int c0, int prow, const float* r,
-                                          const float* z, const float* nn) {
+// GRU gates for 16 channels [c0, c0+16) of one pixel.  bias_r16 points at the bias of the r gate of channel
+// c0 inside the [r(64) | z(64) | n(64)] block (z at +64, n at +128); bhn16 at b_hh_n of channel c0.
+__device__ __forceinline__ void epi_gru16(const ConvDev& p, int n_img, int oh, int ow, int c0, const float* r,
+                                          const float* z, const float* nn, const float* bias_r16, const float* bhn16) {
   float h[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float rr = 1.f / (1.f + __expf(-(r[i] + __ldg(p.bias + prow + i))));
-    const float zz = 1.f / (1.f + __expf(-(z[i] + __ldg(p.bias + prow + 64 + i))));
-    const float nv = tanhf(nn[i] + __ldg(p.bias + prow + 128 + i) + rr * __ldg(p.gru_bhn + c0 + i));
+    const float rr = 1.f / (1.f + __expf(-(r[i] + bias_r16[i])));
+    const float zz = 1.f / (1.f + __expf(-(z[i] + bias_r16[64 + i])));
+    const float nv = tanhf(nn[i] + bias_r16[128 + i] + rr * bhn16[i]);
     h[i] = (1.f - zz) * nv;
   }
   store_act16(p, n_img, oh, ow, c0, h);
@@ -160,37 +166,70 @@ __device__ __forceinline__ bool gru_unit_absent(const ConvDev& p, int n_img) {
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-core kernel: persistent, warp-specialised (192 threads)
-//   warp 0 / lane 0 : TMA producer (A boxes every stage; weights either streamed with A or loaded
-//                     once per CTA when the whole [BN x K] operand fits in shared memory)
-//   warp 1 / lane 0 : tcgen05.mma issuer; alternates between two TMEM accumulator buffers
-//   warps 2..5      : epilogue (tcgen05.ld -> bias/ReLU/gates -> global); warp w owns TMEM lane
-//                     quadrant w % 4, so tile row = (w % 4) * 32 + lane
+//   warp 0 : TMA producer (A boxes every stage; weights either streamed with A or loaded once per CTA
+//            when the whole [BN x K] operand fits in shared memory)
+//   warp 1 : tcgen05.mma issuer; alternates between two TMEM accumulator buffers
+//   warps 2..5 : epilogue (tcgen05.ld -> bias/ReLU/gates -> global); warp w owns TMEM lane quadrant
+//            w % 4, so tile row = (w % 4) * 32 + lane
 // grid = (ctas_x, n_tiles): a CTA keeps its N tile (blockIdx.y) and walks M tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ...  The epilogue of tile i overlaps the main loop of tile
 // i+1 through the two accumulator buffers (tmem_full / tmem_empty mbarriers).
+//
+// The role loops are deliberately lean: a tile of a C=32 layer is only ~700 cycles of tensor work,
+// so every role must spend well under that per tile.  Hence: the k-block -> (source, channel offset,
+// tap shift) decode is tabulated in shared memory once per CTA; tiles are walked incrementally (no
+// divisions); KSTEPS (= kc/16) is a template parameter so the MMA burst is straight-line code; bias
+// vectors live in shared memory; and all loops run warp-uniformly with elect_one() only around the
+// issuing instructions (running them under `if (lane == 0)` makes the compiler wrap every
+// tcgen05.mma / TMA in a divergence waterfall, ~200 cycles per instruction -- measured).
 // ---------------------------------------------------------------------------------------------
-struct TileCoord {
-  int n_img, oh0, ow0;
-};
-__device__ __forceinline__ TileCoord decode_tile(const ConvDev& p, int tile) {
-  TileCoord t;
-  t.n_img = tile / p.tiles_per_img;
-  const int trem = tile - t.n_img * p.tiles_per_img;
-  t.oh0 = (trem / p.tiles_w) * kTileH;
-  t.ow0 = (trem % p.tiles_w) * kTileW;
-  return t;
-}
+constexpr int kMaxKBlocks = 160;
 
-template <int BN, int PLANES>
+struct TileIter {
+  int tile, n_img, th, tw;   // current M tile and its decode
+  int d_n, d_th, d_tw;       // decode of the grid stride
+  int tiles_w, tiles_h;
+  __device__ __forceinline__ void init(const ConvDev& p, int first, int stride) {
+    tiles_w = p.tiles_w;
+    tiles_h = p.tiles_per_img / p.tiles_w;
+    tile = first;
+    n_img = first / p.tiles_per_img;
+    int r = first - n_img * p.tiles_per_img;
+    th = r / tiles_w;
+    tw = r - th * tiles_w;
+    d_n = stride / p.tiles_per_img;
+    r = stride - d_n * p.tiles_per_img;
+    d_th = r / tiles_w;
+    d_tw = r - d_th * tiles_w;
+  }
+  __device__ __forceinline__ void next(int stride) {
+    tile += stride;
+    tw += d_tw;
+    if (tw >= tiles_w) { tw -= tiles_w; ++th; }
+    th += d_th;
+    if (th >= tiles_h) { th -= tiles_h; ++n_img; }
+    n_img += d_n;
+  }
+};
+
+template <int BN, int PLANES, int KSTEPS>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                  const __grid_constant__ CUtensorMap tmA1,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const ConvDev p) {
+  constexpr int KC = 16 * KSTEPS;
   constexpr uint32_t ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+  constexpr uint32_t A_TILE = 128u * KC * 2u;                             // bytes
+  constexpr uint32_t B_TILE = ((uint32_t)BN * KC * 2u + 1023u) & ~1023u;  // bytes (1 KB aligned)
+  constexpr uint32_t SBO = 8u * KC * 2u;
+  constexpr uint32_t LAYOUT = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
   __shared__ uint32_t tmem_slot;
+  __shared__ int4 ktab[kMaxKBlocks];  // per k-block: {channel coord, dw, dh, src | hp << 1}
+  __shared__ float s_bias[BN];
+  __shared__ float s_bhn[64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
@@ -202,6 +241,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages + 1]);   // [2]
   const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 3]);  // [2]
 
+  // ---- one-time setup ----
+  for (int k = threadIdx.x; k < p.num_k; k += kNumThreads) {
+    const int k0 = p.taps * p.cblocks[0];
+    const int s = k < k0 ? 0 : 1;
+    const int kr = k - s * k0;
+    const int tap = kr / p.cblocks[s], cb = kr - tap * p.cblocks[s];
+    const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap - 3 * (tap / 3) : 1;
+    int4 e;
+    if (p.stride == 1) {
+      e = make_int4(cb * KC, kw - 1, kh - 1, s);
+    } else {  // input row 2*oh + kh - 1 = 2*(oh + hoff) + hp, same along w
+      const int hp = kh == 1 ? 0 : 1, hoff = kh == 0 ? -1 : 0;
+      const int wp = kw == 1 ? 0 : 1, woff = kw == 0 ? -1 : 0;
+      e = make_int4(wp * p.cin[s] + cb * KC, woff, hoff, s | (hp << 1));
+    }
+    ktab[k] = e;
+  }
+  for (int i = threadIdx.x; i < BN; i += kNumThreads) s_bias[i] = p.bias[n0 + i];
+  if (p.epilogue == V2X_EPI_GRU && threadIdx.x < 64) s_bhn[threadIdx.x] = p.gru_bhn[blockIdx.y * 64 + threadIdx.x];
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA0);
     if (p.nsrc > 1) prefetch_tmap(&tmA1);
@@ -225,62 +283,56 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  const bool is_gru = p.epilogue == V2X_EPI_GRU;
+  const int grid_stride = gridDim.x;
 
-  // NOTE: the producer and MMA loops are executed by ALL 32 lanes of their warp with warp-uniform
-  // control flow and values; only the issuing instructions sit under elect_one().  Running the loops
-  // under `if (lane == 0)` instead makes the compiler wrap every tcgen05.mma / TMA in a divergence
-  // "waterfall" (ELECT/BRA.U.ANY), ~200 cycles per instruction -- measured, see DESIGN.md.
   if (warp == 0) {
     // ===== TMA producer =====
     if (p.b_resident && elect_one()) {
-      mbar_expect_tx(bar_bres, (uint32_t)p.num_k * PLANES * (uint32_t)(BN * p.kc * 2));
+      mbar_expect_tx(bar_bres, (uint32_t)p.num_k * PLANES * (uint32_t)(BN * KC * 2));
       for (int k = 0; k < p.num_k; ++k)
+#pragma unroll
         for (int pl = 0; pl < PLANES; ++pl)
-          tma_load_2d(smem_base + (k * PLANES + pl) * p.b_tile_bytes, &tmB, bar_bres, k * p.kc, pl * p.cout_pad + n0);
+          tma_load_2d(smem_base + (k * PLANES + pl) * B_TILE, &tmB, bar_bres, k * KC, pl * p.cout_pad + n0);
     }
     __syncwarp();
+    const bool no_tma = p.debug_mode == 2;
     int stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      if (gru_unit_absent(p, tc.n_img)) continue;
-      int kidx = 0, s = 0, tap = 0, cb = 0;  // k-block cursor: source, filter tap, channel block
+    TileIter ti;
+    ti.init(p, blockIdx.x, grid_stride);
+    for (; ti.tile < p.m_tiles; ti.next(grid_stride)) {
+      if (is_gru && gru_unit_absent(p, ti.n_img)) continue;
+      const int oh0 = ti.th * kTileH, ow0 = ti.tw * kTileW;
+      int kidx = 0;
       for (int ks = 0; ks < p.stages_per_tile; ++ks) {
         const int nblk = min(p.kb_per_stage, p.num_k - kidx);
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         const uint32_t full = bar_full + 8 * stage;
-        const bool leader = elect_one();
-        if (leader) mbar_expect_tx(full, nblk * p.kb_tx_bytes);
-        uint32_t sa = ring_base + stage * p.stage_bytes;
-        for (int j = 0; j < nblk; ++j, ++kidx, sa += p.kb_bytes) {
-          const CUtensorMap* tmA = s == 0 ? &tmA0 : &tmA1;
-          const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap - 3 * (tap / 3) : 1;
-          if (leader) {
+        if (elect_one()) {
+          if (no_tma) {
+            mbar_arrive(full);
+          } else {
+            mbar_expect_tx(full, nblk * p.kb_tx_bytes);
+            uint32_t sa = ring_base + stage * p.stage_bytes;
+            for (int j = 0; j < nblk; ++j, sa += p.kb_bytes) {
+              const int4 e = ktab[kidx + j];
+              const CUtensorMap* tmA = (e.w & 1) ? &tmA1 : &tmA0;
 #pragma unroll
-            for (int pl = 0; pl < PLANES; ++pl) {
-              const uint32_t dst = sa + pl * p.a_tile_bytes;
-              const int img = pl * p.n_maps + tc.n_img;
-              if (p.stride == 1) {
-                tma_load_4d(dst, tmA, full, cb * p.kc, tc.ow0 + kw - 1, tc.oh0 + kh - 1, img);
-              } else {
-                // input row 2*oh + kh - 1 = 2*(oh + hoff) + hp
-                const int hp = kh == 1 ? 0 : 1, hoff = kh == 0 ? -1 : 0;
-                const int wp = kw == 1 ? 0 : 1, woff = kw == 0 ? -1 : 0;
-                tma_load_5d(dst, tmA, full, wp * p.cin[s] + cb * p.kc, tc.ow0 + woff, hp, tc.oh0 + hoff, img);
+              for (int pl = 0; pl < PLANES; ++pl) {
+                const int img = pl * p.n_maps + ti.n_img;
+                if (p.stride == 1) tma_load_4d(sa + pl * A_TILE, tmA, full, e.x, ow0 + e.y, oh0 + e.z, img);
+                else tma_load_5d(sa + pl * A_TILE, tmA, full, e.x, ow0 + e.y, e.w >> 1, oh0 + e.z, img);
+              }
+              if (!p.b_resident) {
+#pragma unroll
+                for (int pl = 0; pl < PLANES; ++pl)
+                  tma_load_2d(sa + PLANES * A_TILE + pl * B_TILE, &tmB, full, (kidx + j) * KC, pl * p.cout_pad + n0);
               }
             }
-            if (!p.b_resident) {
-              const uint32_t sb = sa + PLANES * p.a_tile_bytes;
-#pragma unroll
-              for (int pl = 0; pl < PLANES; ++pl)
-                tma_load_2d(sb + pl * p.b_tile_bytes, &tmB, full, kidx * p.kc, pl * p.cout_pad + n0);
-            }
-          }
-          if (++cb == p.cblocks[s]) {
-            cb = 0;
-            if (++tap == p.taps) { tap = 0; ++s; }
           }
         }
         __syncwarp();
+        kidx += nblk;
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -288,11 +340,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
     if (p.b_resident) mbar_wait(bar_bres, 0);
+    const bool no_mma = p.debug_mode == 1;
     int stage = 0, phase = 0, it = 0;
-    const int ksteps = p.kc / 16;
-    const uint32_t a_plane = p.a_tile_bytes >> 4, b_plane = p.b_tile_bytes >> 4;  // descriptor address units
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      if (gru_unit_absent(p, decode_tile(p, tile).n_img)) continue;
+    // descriptors differ only in the 14-bit start-address field (units of 16 bytes)
+    const uint64_t desc_ring = make_smem_desc(ring_base, SBO, LAYOUT);
+    const uint64_t desc_bres = make_smem_desc(smem_base, SBO, LAYOUT);
+    const uint32_t stage16 = p.stage_bytes >> 4, kb16 = p.kb_bytes >> 4;
+    TileIter ti;
+    ti.init(p, blockIdx.x, grid_stride);
+    for (; ti.tile < p.m_tiles; ti.next(grid_stride)) {
+      if (is_gru && gru_unit_absent(p, ti.n_img)) continue;
       const int acc_buf = it & 1;
       mbar_wait(bar_tempty + 8 * acc_buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
@@ -303,34 +360,37 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         const int nblk = min(p.kb_per_stage, p.num_k - kidx);
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t a_stage = ring_base + stage * p.stage_bytes;
-        const uint32_t b_stage = p.b_resident ? smem_base + kidx * PLANES * p.b_tile_bytes : a_stage + PLANES * p.a_tile_bytes;
-        const uint32_t b_step = p.b_resident ? PLANES * p.b_tile_bytes : p.kb_bytes;
-        // descriptors differ only in the 14-bit start-address field: add (bytes >> 4) to the low word
-        uint64_t da0 = make_smem_desc(a_stage, p.sbo, p.layout_type);
-        uint64_t db0 = make_smem_desc(b_stage, p.sbo, p.layout_type);
         if (elect_one()) {
-          for (int j = 0; j < nblk; ++j) {
-            for (int kk = 0; kk < ksteps; ++kk) {
-              const uint64_t da = da0 + (uint64_t)(kk * 2), db = db0 + (uint64_t)(kk * 2);
-              umma_bf16(tmem_d, da, db, idesc, acc);
-              acc = 1;
-              if (PLANES == 2) {
-                umma_bf16(tmem_d, da, db + b_plane, idesc, 1);
-                umma_bf16(tmem_d, da + a_plane, db, idesc, 1);
+          if (no_mma) {
+            mbar_arrive(bar_empty + 8 * stage);
+          } else {
+            uint64_t da = desc_ring + (uint64_t)(stage * stage16);
+            uint64_t db = p.b_resident ? desc_bres + (uint64_t)(kidx * PLANES * (B_TILE >> 4))
+                                       : da + (uint64_t)(PLANES * (A_TILE >> 4));
+            const uint32_t db_step = p.b_resident ? PLANES * (B_TILE >> 4) : kb16;
+            for (int j = 0; j < nblk; ++j, da += kb16, db += db_step) {
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                umma_bf16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, acc);
+                acc = 1;
+                if (PLANES == 2) {
+                  umma_bf16(tmem_d, da + 2 * kk, db + 2 * kk + (B_TILE >> 4), idesc, 1);
+                  umma_bf16(tmem_d, da + 2 * kk + (A_TILE >> 4), db + 2 * kk, idesc, 1);
+                }
               }
             }
-            da0 += p.kb_bytes >> 4;
-            db0 += b_step >> 4;
+            umma_commit(bar_empty + 8 * stage);
           }
-          umma_commit(bar_empty + 8 * stage);
         }
         __syncwarp();
         acc = 1;
         kidx += nblk;
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(bar_tfull + 8 * acc_buf);
+      if (elect_one()) {
+        if (no_mma) mbar_arrive(bar_tfull + 8 * acc_buf);
+        else umma_commit(bar_tfull + 8 * acc_buf);
+      }
       __syncwarp();
       ++it;
     }
@@ -339,40 +399,53 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      const int oh = tc.oh0 + (row >> 4), ow = tc.ow0 + (row & 15);
-      if (gru_unit_absent(p, tc.n_img)) {
-        copy_passthrough(p, tc.n_img, oh, ow, blockIdx.y * 64, 64);
+    TileIter ti;
+    ti.init(p, blockIdx.x, grid_stride);
+    for (; ti.tile < p.m_tiles; ti.next(grid_stride)) {
+      const int oh = ti.th * kTileH + (row >> 4), ow = ti.tw * kTileW + (row & 15);
+      if (is_gru && gru_unit_absent(p, ti.n_img)) {
+        copy_passthrough(p, ti.n_img, oh, ow, blockIdx.y * 64, 64);
         continue;
       }
       const int acc_buf = it & 1;
       mbar_wait(bar_tfull + 8 * acc_buf, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_buf * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
-      if (p.epilogue == V2X_EPI_GRU) {
+      if (is_gru) {
         if constexpr (BN == 192) {
 #pragma unroll 1
           for (int c16 = 0; c16 < 4; ++c16) {
             float r[16], z[16], nn[16];
-            tmem_ld16(taddr + c16 * 16, r);
-            tmem_ld16(taddr + 64 + c16 * 16, z);
-            tmem_ld16(taddr + 128 + c16 * 16, nn);
-            epi_gru16(p, tc.n_img, oh, ow, blockIdx.y * 64 + c16 * 16, n0 + c16 * 16, r, z, nn);
+            tmem_ld16_async(taddr + c16 * 16, r);
+            tmem_ld16_async(taddr + 64 + c16 * 16, z);
+            tmem_ld16_async(taddr + 128 + c16 * 16, nn);
+            tmem_ld_wait16(r);
+            tmem_ld_wait16(z);
+            tmem_ld_wait16(nn);
+            epi_gru16(p, ti.n_img, oh, ow, blockIdx.y * 64 + c16 * 16, r, z, nn, s_bias + c16 * 16, s_bhn + c16 * 16);
           }
         }
       } else {
 #pragma unroll 1
-        for (int c16 = 0; c16 < BN / 16; ++c16) {
-          const int ch0 = n0 + c16 * 16;
+        for (int c32 = 0; c32 < (BN + 31) / 32; ++c32) {
+          const int ch0 = n0 + c32 * 32;
           if (ch0 >= p.cout) break;
-          float v[16];
-          tmem_ld16(taddr + c16 * 16, v);
-          if (p.epilogue == V2X_EPI_ACT) epi_act16(p, tc.n_img, oh, ow, ch0, v);
-          else epi_f32_split16(p, tc.n_img, oh, ow, ch0, v);
+          const bool two = (c32 * 32 + 16 < BN) && (ch0 + 16 < p.cout);
+          float v0[16], v1[16];
+          tmem_ld16_async(taddr + c32 * 32, v0);
+          if (two) tmem_ld16_async(taddr + c32 * 32 + 16, v1);
+          tmem_ld_wait16(v0);
+          if (two) tmem_ld_wait16(v1);
+          if (p.epilogue == V2X_EPI_ACT) {
+            epi_act16(p, ti.n_img, oh, ow, ch0, v0, s_bias + c32 * 32);
+            if (two) epi_act16(p, ti.n_img, oh, ow, ch0 + 16, v1, s_bias + c32 * 32 + 16);
+          } else {
+            epi_f32_split16(p, ti.n_img, oh, ow, ch0, v0, s_bias + c32 * 32);
+            if (two) epi_f32_split16(p, ti.n_img, oh, ow, ch0 + 16, v1, s_bias + c32 * 32 + 16);
+          }
         }
       }
-      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16): release the buffer
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld above): release the buffer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc_buf);
@@ -447,12 +520,12 @@ __global__ void conv_ref_kernel(const ConvDev p) {
     kbase += (long long)p.taps * p.cin[s];
   }
   if (gru) {
-    epi_gru16(p, n_img, oh, ow, chunk * 16, prow[0], acc[0], acc[1], acc[2]);
+    epi_gru16(p, n_img, oh, ow, chunk * 16, acc[0], acc[1], acc[2], p.bias + prow[0], p.gru_bhn + chunk * 16);
   } else {
     const int ch0 = chunk * 16;
     if (ch0 >= p.cout) return;
-    if (p.epilogue == V2X_EPI_ACT) epi_act16(p, n_img, oh, ow, ch0, acc[0]);
-    else epi_f32_split16(p, n_img, oh, ow, ch0, acc[0]);
+    if (p.epilogue == V2X_EPI_ACT) epi_act16(p, n_img, oh, ow, ch0, acc[0], p.bias + ch0);
+    else epi_f32_split16(p, n_img, oh, ow, ch0, acc[0], p.bias + ch0);
   }
 }
 
@@ -496,6 +569,8 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
   return V2X_OK;
 }
 
+static int g_debug_mode = 0;
+
 static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
   V2X_REQUIRE(p != nullptr, "null params");
   V2X_REQUIRE(p->src[0] && p->weights && p->bias && p->out0, "null src/weights/bias/out0");
@@ -537,6 +612,7 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
   d.bias = p->bias; d.gru_bhn = p->gru_bhn; d.passthrough = p->passthrough;
   d.num_agent = reinterpret_cast<const long long*>(p->num_agent);
   d.batch = p->batch; d.agents = p->agents;
+  d.debug_mode = g_debug_mode;
   d.a_tile_bytes = 128u * kc * 2u;
   d.b_tile_bytes = ((uint32_t)bn * kc * 2u + 1023u) & ~1023u;
   d.stage_bytes = p->planes * (d.a_tile_bytes + d.b_tile_bytes);
@@ -584,13 +660,13 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int PLANES>
+template <int BN, int PLANES, int KSTEPS>
 static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                      size_t smem, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN, PLANES, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
   // persistent grid: one CTA per SM, split between the N tiles (every CTA keeps one N tile)
@@ -602,7 +678,7 @@ static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap&
   const int rounds = (d.m_tiles + ctas_x - 1) / ctas_x;
   ctas_x = (d.m_tiles + rounds - 1) / rounds;
   dim3 grid(ctas_x, d.n_tiles);
-  conv_tc_kernel<BN, PLANES><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, d);
+  conv_tc_kernel<BN, PLANES, KSTEPS><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, d);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }
@@ -679,20 +755,29 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
     rc = encode_map(&tmB, p->weights, 2, dims, str, box, d.kc);
     if (rc) return rc;
   }
-#define V2X_LAUNCH(BN_)                                                                      \
-  case BN_:                                                                                 \
-    return p->planes == 1 ? launch_tc<BN_, 1>(d, tmA[0], tmA[1], tmB, smem, stream)         \
-                          : launch_tc<BN_, 2>(d, tmA[0], tmA[1], tmB, smem, stream);
-  switch (bn) {
-    V2X_LAUNCH(32)
-    V2X_LAUNCH(48)
-    V2X_LAUNCH(64)
-    V2X_LAUNCH(128)
-    V2X_LAUNCH(192)
-    V2X_LAUNCH(256)
-  }
+  V2X_REQUIRE(d.num_k <= kMaxKBlocks, "too many k-blocks (%d > %d)", d.num_k, kMaxKBlocks);
+#define V2X_LAUNCH(BN_, KS_)                                                                     \
+  if (bn == BN_ && d.kc == 16 * KS_)                                                             \
+    return p->planes == 1 ? launch_tc<BN_, 1, KS_>(d, tmA[0], tmA[1], tmB, smem, stream)         \
+                          : launch_tc<BN_, 2, KS_>(d, tmA[0], tmA[1], tmB, smem, stream);
+  // kc = 16 only occurs for the 13(16)-channel input layer, kc = 32 for the 32/96-channel layers
+  V2X_LAUNCH(32, 1) V2X_LAUNCH(32, 2) V2X_LAUNCH(32, 4)
+  V2X_LAUNCH(48, 4)
+  V2X_LAUNCH(64, 1) V2X_LAUNCH(64, 2) V2X_LAUNCH(64, 4)
+  V2X_LAUNCH(128, 2) V2X_LAUNCH(128, 4)
+  V2X_LAUNCH(192, 4)
+  V2X_LAUNCH(256, 2) V2X_LAUNCH(256, 4)
 #undef V2X_LAUNCH
-  return V2X_ERR_ARG;
+  set_error("no kernel instantiation for block_n %d with kc %d", bn, d.kc);
+  return V2X_ERR_UNSUPPORTED;
+}
+
+// Profiling aid: ablate one pipeline role of v2x_conv_fwd (results are then garbage).
+// 0 = normal, 1 = no tcgen05.mma (TMA + epilogue only), 2 = no TMA loads (MMA on stale smem), 3 = no global stores.
+extern "C" int v2x_set_debug_mode(int mode) {
+  V2X_REQUIRE(mode >= 0 && mode <= 3, "debug mode must be 0..3");
+  g_debug_mode = mode;
+  return V2X_OK;
 }
 
 // Same contract as v2x_conv_fwd, computed on CUDA cores without TMA / tcgen05.  A test aid used by

@@ -55,6 +55,7 @@ SYMBOLS = [
     ("v2x_device_ok", C.c_int, []),
     ("v2x_conv_fwd", C.c_int, [C.POINTER(ConvParams), _P]),
     ("v2x_conv_fwd_crosscheck", C.c_int, [C.POINTER(ConvParams), _P]),
+    ("v2x_set_debug_mode", C.c_int, [C.c_int]),
     ("v2x_pack_conv_weights", C.c_int,
      [_P, _P, _P, _P, _P, _P, _F32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _I32,
       _I32, _I32, _P]),
