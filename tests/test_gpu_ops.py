@@ -79,10 +79,14 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("planes", [2, 1])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-@pytest.mark.parametrize("impl", ["crosscheck", "tc"])
-def test_conv_bn_relu(impl, case, planes):
+@pytest.mark.parametrize("impl", ["crosscheck", "tc", "tc_nohalo"])
+def test_conv_bn_relu(impl, case, planes, monkeypatch):
+    """impl: crosscheck = CUDA-core kernel; tc = tensor-core kernel (halo-tile mode where eligible);
+    tc_nohalo = tensor-core kernel with the per-tap box path forced for every layer."""
     from v2x_b200 import ops
     dev = _dev()
+    if impl == "tc_nohalo":
+        monkeypatch.setenv("V2X_NO_HALO", "1")
     name, cins, cout, stride, taps, n, h, w, up = case
     g = torch.Generator().manual_seed(sum(ord(ch) for ch in name))
     k = 3 if taps == 9 else 1

@@ -21,6 +21,7 @@
 // main loop.
 //
 // Reference call sites replaced: see include/v2x_b200.h (v2x_conv_fwd).
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -48,6 +49,8 @@ struct ConvDev {
   int kb_per_stage;          // k-blocks (tap x kc channels) per pipeline stage: one mbarrier round trip feeds them all
   int stages_per_tile;       // ceil(num_k / kb_per_stage)
   uint32_t kb_bytes, kb_tx_bytes;  // smem footprint / TMA bytes of one k-block
+  int halo;                  // 1: 16x8 output tile, one 18x10 halo box per channel block feeds all 9 taps
+  int num_b_tiles;           // weight tiles of the resident operand (= taps * sum(cblocks))
   int debug_mode;            // profiling ablations (v2x_set_debug_mode): 1 = no MMA, 2 = no TMA, 3 = no stores
   int cout, cout_pad;
   int epilogue, relu, upsample2x;
@@ -84,7 +87,6 @@ __device__ __forceinline__ void store_act16(const ConvDev& p, int n_img, int oh,
   const int up = p.upsample2x ? 2 : 1;
   const int H = p.h_out * up, W = p.w_out * up;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out0);
-  if (p.debug_mode == 3 && hi[0] != 0x7fc17fc1u) return;  // profiling ablation: keep the math, drop the stores
   for (int dy = 0; dy < up; ++dy)
     for (int dx = 0; dx < up; ++dx) {
       const long long pix = ((long long)n_img * H + (oh * up + dy)) * W + (ow * up + dx);
@@ -165,6 +167,55 @@ __device__ __forceinline__ bool gru_unit_absent(const ConvDev& p, int n_img) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lean epilogue pieces of the tensor-core kernel (PLANES compile-time, addresses hoisted per tile)
+// ---------------------------------------------------------------------------------------------
+// 16 fp32 -> bf16 hi (and lo) packed; PLANES == 1 needs a single cvt.rn.bf16x2.f32 per pair
+template <int PLANES>
+__device__ __forceinline__ void pack16(const float* v, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    if (PLANES == 2) {
+      const float2 hf = __bfloat1622float2(h);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+      lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+  }
+}
+
+// output addressing of one pixel, computed once per tile
+struct OutPix {
+  __nv_bfloat16* p00;        // first store position (channel 0 of this CTA's N tile)
+  long long row_stride;      // elements between vertically adjacent output pixels (upsample only)
+  long long plane_stride;
+  int c_total;
+  int up;
+};
+
+template <int PLANES>
+__device__ __forceinline__ void store16(const OutPix& o, int c, const uint32_t* hi, const uint32_t* lo) {
+  const uint4 h0 = make_uint4(hi[0], hi[1], hi[2], hi[3]), h1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  uint4 l0, l1;
+  if (PLANES == 2) { l0 = make_uint4(lo[0], lo[1], lo[2], lo[3]); l1 = make_uint4(lo[4], lo[5], lo[6], lo[7]); }
+  if (o.up == 1) {
+    uint4* d = reinterpret_cast<uint4*>(o.p00 + c);
+    d[0] = h0; d[1] = h1;
+    if (PLANES == 2) { uint4* l = reinterpret_cast<uint4*>(o.p00 + o.plane_stride + c); l[0] = l0; l[1] = l1; }
+  } else {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        __nv_bfloat16* q = o.p00 + dy * o.row_stride + dx * o.c_total + c;
+        uint4* d = reinterpret_cast<uint4*>(q);
+        d[0] = h0; d[1] = h1;
+        if (PLANES == 2) { uint4* l = reinterpret_cast<uint4*>(q + o.plane_stride); l[0] = l0; l[1] = l1; }
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tensor-core kernel: persistent, warp-specialised (192 threads)
 //   warp 0 : TMA producer (A boxes every stage; weights either streamed with A or loaded once per CTA
 //            when the whole [BN x K] operand fits in shared memory)
@@ -212,7 +263,15 @@ struct TileIter {
   }
 };
 
-template <int BN, int PLANES, int KSTEPS>
+// HALO = true (3x3, stride 1, resident weights): the output tile is 16 rows x 8 px and the A operand of ALL nine
+// taps comes from ONE TMA box per channel block -- the 18 x 10 px halo of the tile.  Tap (kh, kw) is read by
+// shifting the UMMA descriptor's start address by (kh*10 + kw) pixel rows; the 8-row groups of the operand are
+// one halo row (10 px) apart, hence SBO = 10 * kc*2 bytes.  This relies on the tensor core applying the swizzle
+// to absolute shared-memory address bits (so unaligned starts are fine) -- verified bit-exactly on B200 for the
+// 32/64/128-byte swizzles with tools/halo_probe.cu.  9x fewer TMA boxes, 6.4x fewer L2->smem bytes.
+constexpr int kHaloH = 18, kHaloW = 10;
+
+template <int BN, int PLANES, int KSTEPS, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                  const __grid_constant__ CUtensorMap tmA1,
                                                                  const __grid_constant__ CUtensorMap tmB,
@@ -222,13 +281,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
   constexpr uint32_t A_TILE = 128u * KC * 2u;                             // bytes
   constexpr uint32_t B_TILE = ((uint32_t)BN * KC * 2u + 1023u) & ~1023u;  // bytes (1 KB aligned)
-  constexpr uint32_t SBO = 8u * KC * 2u;
+  constexpr uint32_t ROW = KC * 2u;                                      // bytes of one pixel's channel block
+  constexpr uint32_t SBO = 8u * ROW;
+  constexpr uint32_t A_HALO = ((uint32_t)(kHaloH * kHaloW) * ROW + 1023u) & ~1023u;
+  constexpr uint32_t A_BLOCK = HALO ? A_HALO : A_TILE;                   // smem bytes of one k-block's A operand (per plane)
   constexpr uint32_t LAYOUT = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
+  constexpr int TILE_H = HALO ? 16 : kTileH, TILE_W = HALO ? 8 : kTileW;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
   __shared__ uint32_t tmem_slot;
   __shared__ int4 ktab[kMaxKBlocks];  // per k-block: {channel coord, dw, dh, src | hp << 1}
-  __shared__ float s_bias[BN];
+  __shared__ __align__(16) float s_bias[BN];
   __shared__ float s_bhn[64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -243,18 +306,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
 
   // ---- one-time setup ----
   for (int k = threadIdx.x; k < p.num_k; k += kNumThreads) {
-    const int k0 = p.taps * p.cblocks[0];
-    const int s = k < k0 ? 0 : 1;
-    const int kr = k - s * k0;
-    const int tap = kr / p.cblocks[s], cb = kr - tap * p.cblocks[s];
-    const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap - 3 * (tap / 3) : 1;
     int4 e;
-    if (p.stride == 1) {
-      e = make_int4(cb * KC, kw - 1, kh - 1, s);
-    } else {  // input row 2*oh + kh - 1 = 2*(oh + hoff) + hp, same along w
-      const int hp = kh == 1 ? 0 : 1, hoff = kh == 0 ? -1 : 0;
-      const int wp = kw == 1 ? 0 : 1, woff = kw == 0 ? -1 : 0;
-      e = make_int4(wp * p.cin[s] + cb * KC, woff, hoff, s | (hp << 1));
+    if (HALO) {  // k-block = (source, channel block); e = {channel coord, first weight tile, weight tile step per tap, source}
+      const int s = k < p.cblocks[0] ? 0 : 1;
+      const int cb = k - s * p.cblocks[0];
+      e = make_int4(cb * KC, s * 9 * p.cblocks[0] + cb, p.cblocks[s], s);
+    } else {
+      const int k0 = p.taps * p.cblocks[0];
+      const int s = k < k0 ? 0 : 1;
+      const int kr = k - s * k0;
+      const int tap = kr / p.cblocks[s], cb = kr - tap * p.cblocks[s];
+      const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap - 3 * (tap / 3) : 1;
+      if (p.stride == 1) {
+        e = make_int4(cb * KC, kw - 1, kh - 1, s);
+      } else {  // input row 2*oh + kh - 1 = 2*(oh + hoff) + hp, same along w
+        const int hp = kh == 1 ? 0 : 1, hoff = kh == 0 ? -1 : 0;
+        const int wp = kw == 1 ? 0 : 1, woff = kw == 0 ? -1 : 0;
+        e = make_int4(wp * p.cin[s] + cb * KC, woff, hoff, s | (hp << 1));
+      }
     }
     ktab[k] = e;
   }
@@ -289,8 +358,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   if (warp == 0) {
     // ===== TMA producer =====
     if (p.b_resident && elect_one()) {
-      mbar_expect_tx(bar_bres, (uint32_t)p.num_k * PLANES * (uint32_t)(BN * KC * 2));
-      for (int k = 0; k < p.num_k; ++k)
+      mbar_expect_tx(bar_bres, (uint32_t)p.num_b_tiles * PLANES * (uint32_t)(BN * KC * 2));
+      for (int k = 0; k < p.num_b_tiles; ++k)
 #pragma unroll
         for (int pl = 0; pl < PLANES; ++pl)
           tma_load_2d(smem_base + (k * PLANES + pl) * B_TILE, &tmB, bar_bres, k * KC, pl * p.cout_pad + n0);
@@ -302,7 +371,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     ti.init(p, blockIdx.x, grid_stride);
     for (; ti.tile < p.m_tiles; ti.next(grid_stride)) {
       if (is_gru && gru_unit_absent(p, ti.n_img)) continue;
-      const int oh0 = ti.th * kTileH, ow0 = ti.tw * kTileW;
+      const int oh0 = ti.th * TILE_H, ow0 = ti.tw * TILE_W;
       int kidx = 0;
       for (int ks = 0; ks < p.stages_per_tile; ++ks) {
         const int nblk = min(p.kb_per_stage, p.num_k - kidx);
@@ -320,10 +389,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
               for (int pl = 0; pl < PLANES; ++pl) {
                 const int img = pl * p.n_maps + ti.n_img;
-                if (p.stride == 1) tma_load_4d(sa + pl * A_TILE, tmA, full, e.x, ow0 + e.y, oh0 + e.z, img);
-                else tma_load_5d(sa + pl * A_TILE, tmA, full, e.x, ow0 + e.y, e.w >> 1, oh0 + e.z, img);
+                if (HALO) tma_load_4d(sa + pl * A_BLOCK, (e.w & 1) ? &tmA1 : &tmA0, full, e.x, ow0 - 1, oh0 - 1, img);
+                else if (p.stride == 1) tma_load_4d(sa + pl * A_BLOCK, tmA, full, e.x, ow0 + e.y, oh0 + e.z, img);
+                else tma_load_5d(sa + pl * A_BLOCK, tmA, full, e.x, ow0 + e.y, e.w >> 1, oh0 + e.z, img);
               }
-              if (!p.b_resident) {
+              if (!HALO && !p.b_resident) {
 #pragma unroll
                 for (int pl = 0; pl < PLANES; ++pl)
                   tma_load_2d(sa + PLANES * A_TILE + pl * B_TILE, &tmB, full, (kidx + j) * KC, pl * p.cout_pad + n0);
@@ -343,7 +413,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     const bool no_mma = p.debug_mode == 1;
     int stage = 0, phase = 0, it = 0;
     // descriptors differ only in the 14-bit start-address field (units of 16 bytes)
-    const uint64_t desc_ring = make_smem_desc(ring_base, SBO, LAYOUT);
+    const uint64_t desc_ring = make_smem_desc(ring_base, HALO ? kHaloW * ROW : SBO, LAYOUT);
     const uint64_t desc_bres = make_smem_desc(smem_base, SBO, LAYOUT);
     const uint32_t stage16 = p.stage_bytes >> 4, kb16 = p.kb_bytes >> 4;
     TileIter ti;
@@ -365,17 +435,38 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             mbar_arrive(bar_empty + 8 * stage);
           } else {
             uint64_t da = desc_ring + (uint64_t)(stage * stage16);
-            uint64_t db = p.b_resident ? desc_bres + (uint64_t)(kidx * PLANES * (B_TILE >> 4))
-                                       : da + (uint64_t)(PLANES * (A_TILE >> 4));
-            const uint32_t db_step = p.b_resident ? PLANES * (B_TILE >> 4) : kb16;
-            for (int j = 0; j < nblk; ++j, da += kb16, db += db_step) {
+            if (HALO) {
+              for (int j = 0; j < nblk; ++j, da += kb16) {
+                const int4 e = ktab[kidx + j];
+                uint64_t db = desc_bres + (uint64_t)(e.y * PLANES * (B_TILE >> 4));
+                const uint32_t db_step = e.z * PLANES * (B_TILE >> 4);
 #pragma unroll
-              for (int kk = 0; kk < KSTEPS; ++kk) {
-                umma_bf16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, acc);
-                acc = 1;
-                if (PLANES == 2) {
-                  umma_bf16(tmem_d, da + 2 * kk, db + 2 * kk + (B_TILE >> 4), idesc, 1);
-                  umma_bf16(tmem_d, da + 2 * kk + (A_TILE >> 4), db + 2 * kk, idesc, 1);
+                for (int tap = 0; tap < 9; ++tap, db += db_step) {
+                  const uint64_t dat = da + (uint64_t)((((tap / 3) * kHaloW + (tap % 3)) * ROW) >> 4);
+#pragma unroll
+                  for (int kk = 0; kk < KSTEPS; ++kk) {
+                    umma_bf16(tmem_d, dat + 2 * kk, db + 2 * kk, idesc, acc);
+                    acc = 1;
+                    if (PLANES == 2) {
+                      umma_bf16(tmem_d, dat + 2 * kk, db + 2 * kk + (B_TILE >> 4), idesc, 1);
+                      umma_bf16(tmem_d, dat + 2 * kk + (A_BLOCK >> 4), db + 2 * kk, idesc, 1);
+                    }
+                  }
+                }
+              }
+            } else {
+              uint64_t db = p.b_resident ? desc_bres + (uint64_t)(kidx * PLANES * (B_TILE >> 4))
+                                         : da + (uint64_t)(PLANES * (A_TILE >> 4));
+              const uint32_t db_step = p.b_resident ? PLANES * (B_TILE >> 4) : kb16;
+              for (int j = 0; j < nblk; ++j, da += kb16, db += db_step) {
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) {
+                  umma_bf16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, acc);
+                  acc = 1;
+                  if (PLANES == 2) {
+                    umma_bf16(tmem_d, da + 2 * kk, db + 2 * kk + (B_TILE >> 4), idesc, 1);
+                    umma_bf16(tmem_d, da + 2 * kk + (A_TILE >> 4), db + 2 * kk, idesc, 1);
+                  }
                 }
               }
             }
@@ -398,11 +489,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     // ===== epilogue warps =====
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    const int r_h = HALO ? (row >> 3) : (row >> 4), r_w = HALO ? (row & 7) : (row & 15);
+    const bool no_store = p.debug_mode == 3;
+    const int up = p.upsample2x ? 2 : 1;
+    const int Hs = p.h_out * up, Ws = p.w_out * up;
     int it = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, grid_stride);
     for (; ti.tile < p.m_tiles; ti.next(grid_stride)) {
-      const int oh = ti.th * kTileH + (row >> 4), ow = ti.tw * kTileW + (row & 15);
+      const int oh = ti.th * TILE_H + r_h, ow = ti.tw * TILE_W + r_w;
       if (is_gru && gru_unit_absent(p, ti.n_img)) {
         copy_passthrough(p, ti.n_img, oh, ow, blockIdx.y * 64, 64);
         continue;
@@ -411,21 +506,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       mbar_wait(bar_tfull + 8 * acc_buf, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_buf * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
-      if (is_gru) {
-        if constexpr (BN == 192) {
-#pragma unroll 1
-          for (int c16 = 0; c16 < 4; ++c16) {
-            float r[16], z[16], nn[16];
-            tmem_ld16_async(taddr + c16 * 16, r);
-            tmem_ld16_async(taddr + 64 + c16 * 16, z);
-            tmem_ld16_async(taddr + 128 + c16 * 16, nn);
-            tmem_ld_wait16(r);
-            tmem_ld_wait16(z);
-            tmem_ld_wait16(nn);
-            epi_gru16(p, ti.n_img, oh, ow, blockIdx.y * 64 + c16 * 16, r, z, nn, s_bias + c16 * 16, s_bhn + c16 * 16);
-          }
-        }
-      } else {
+      if (p.epilogue == V2X_EPI_F32_SPLIT) {
 #pragma unroll 1
         for (int c32 = 0; c32 < (BN + 31) / 32; ++c32) {
           const int ch0 = n0 + c32 * 32;
@@ -436,12 +517,79 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           if (two) tmem_ld16_async(taddr + c32 * 32 + 16, v1);
           tmem_ld_wait16(v0);
           if (two) tmem_ld_wait16(v1);
-          if (p.epilogue == V2X_EPI_ACT) {
-            epi_act16(p, ti.n_img, oh, ow, ch0, v0, s_bias + c32 * 32);
-            if (two) epi_act16(p, ti.n_img, oh, ow, ch0 + 16, v1, s_bias + c32 * 32 + 16);
-          } else {
-            epi_f32_split16(p, ti.n_img, oh, ow, ch0, v0, s_bias + c32 * 32);
-            if (two) epi_f32_split16(p, ti.n_img, oh, ow, ch0 + 16, v1, s_bias + c32 * 32 + 16);
+          epi_f32_split16(p, ti.n_img, oh, ow, ch0, v0, s_bias + c32 * 32);
+          if (two) epi_f32_split16(p, ti.n_img, oh, ow, ch0 + 16, v1, s_bias + c32 * 32 + 16);
+        }
+      } else {
+        OutPix o;
+        o.up = up;
+        o.c_total = p.out_c_total;
+        o.row_stride = (long long)Ws * p.out_c_total;
+        o.plane_stride = p.out_plane_stride;
+        o.p00 = reinterpret_cast<__nv_bfloat16*>(p.out0) +
+                (((long long)ti.n_img * Hs + oh * up) * Ws + ow * up) * p.out_c_total + p.out_c_off +
+                (is_gru ? blockIdx.y * 64 : n0);
+        if (is_gru) {
+          if constexpr (BN == 192) {
+#pragma unroll 1
+            for (int c16 = 0; c16 < 4; ++c16) {
+              float r[16], z[16], nn[16];
+              tmem_ld16_async(taddr + c16 * 16, r);
+              tmem_ld16_async(taddr + 64 + c16 * 16, z);
+              tmem_ld16_async(taddr + 128 + c16 * 16, nn);
+              tmem_ld_wait16(r);
+              tmem_ld_wait16(z);
+              tmem_ld_wait16(nn);
+              const float* br = s_bias + c16 * 16;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float rr = 1.f / (1.f + __expf(-(r[i] + br[i])));
+                const float zz = 1.f / (1.f + __expf(-(z[i] + br[64 + i])));
+                const float nv = tanhf(nn[i] + br[128 + i] + rr * s_bhn[c16 * 16 + i]);
+                r[i] = (1.f - zz) * nv;
+              }
+              uint32_t hi[8], lo[8];
+              pack16<PLANES>(r, hi, lo);
+              if (!no_store) store16<PLANES>(o, c16 * 16, hi, lo);
+            }
+          }
+        } else {
+          const bool relu = p.relu != 0;
+#pragma unroll 1
+          for (int c32 = 0; c32 < (BN + 31) / 32; ++c32) {
+            if (n0 + c32 * 32 >= p.cout) break;
+            const bool two = (c32 * 32 + 16 < BN) && (n0 + c32 * 32 + 16 < p.cout);
+            float v0[16], v1[16];
+            tmem_ld16_async(taddr + c32 * 32, v0);
+            if (two) tmem_ld16_async(taddr + c32 * 32 + 16, v1);
+            tmem_ld_wait16(v0);
+            if (two) tmem_ld_wait16(v1);
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + c32 * 32);
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = b4[q];
+              v0[4 * q + 0] += b.x; v0[4 * q + 1] += b.y; v0[4 * q + 2] += b.z; v0[4 * q + 3] += b.w;
+            }
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v0[i] = fmaxf(v0[i], 0.f);
+            }
+            pack16<PLANES>(v0, hi, lo);
+            if (!no_store) store16<PLANES>(o, c32 * 32, hi, lo);
+            if (two) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 b = b4[4 + q];
+                v1[4 * q + 0] += b.x; v1[4 * q + 1] += b.y; v1[4 * q + 2] += b.z; v1[4 * q + 3] += b.w;
+              }
+              if (relu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v1[i] = fmaxf(v1[i], 0.f);
+              }
+              pack16<PLANES>(v1, hi, lo);
+              if (!no_store) store16<PLANES>(o, c32 * 32 + 16, hi, lo);
+            }
           }
         }
       }
@@ -660,13 +808,13 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int PLANES, int KSTEPS>
+template <int BN, int PLANES, int KSTEPS, bool HALO>
 static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                      size_t smem, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN, PLANES, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN, PLANES, KSTEPS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
   // persistent grid: one CTA per SM, split between the N tiles (every CTA keeps one N tile)
@@ -678,7 +826,7 @@ static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap&
   const int rounds = (d.m_tiles + ctas_x - 1) / ctas_x;
   ctas_x = (d.m_tiles + rounds - 1) / rounds;
   dim3 grid(ctas_x, d.n_tiles);
-  conv_tc_kernel<BN, PLANES, KSTEPS><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, d);
+  conv_tc_kernel<BN, PLANES, KSTEPS, HALO><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, d);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }
@@ -697,11 +845,25 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
   // Shared-memory plan.  Small weight operands (all of [block_n x K], e.g. the C=32 layers at 256x256)
   // stay resident for the CTA's lifetime so only activations stream; otherwise weights ride in the
   // stage ring next to their A tile.  The ring takes whatever is left, up to kMaxStages deep.
-  const uint32_t b_all = (uint32_t)d.num_k * p->planes * d.b_tile_bytes;
+  d.num_b_tiles = d.num_k;
+  const uint32_t b_all = (uint32_t)d.num_b_tiles * p->planes * d.b_tile_bytes;
   const uint32_t a_stage = p->planes * d.a_tile_bytes;
   const uint32_t budget = (uint32_t)kSmemLimit - 1024u;
   d.b_resident = (b_all <= 96u * 1024u && b_all + 4u * a_stage <= budget) ? 1 : 0;
-  if (d.b_resident) {
+  // Halo mode: 3x3 stride-1 convs with resident weights read all nine taps out of one 18x10-pixel box.
+  const uint32_t a_halo = ((uint32_t)(kHaloH * kHaloW) * d.kc * 2u + 1023u) & ~1023u;
+  d.halo = (d.b_resident && p->taps == 9 && p->stride == 1 && (bn == 32 || bn == 64) && p->h_out % 16 == 0 &&
+            p->w_out % 8 == 0 && b_all + 3u * p->planes * a_halo <= budget && !getenv("V2X_NO_HALO"))
+               ? 1 : 0;
+  if (d.halo) {
+    d.tiles_w = p->w_out / 8;
+    d.tiles_per_img = d.tiles_w * (p->h_out / 16);
+    d.m_tiles = p->n_maps * d.tiles_per_img;
+    d.num_k = d.cblocks[0] + (d.nsrc > 1 ? d.cblocks[1] : 0);   // k-blocks = channel blocks; 9 taps each
+    d.b_region_bytes = b_all;
+    d.stage_bytes = p->planes * a_halo;
+    d.tx_bytes = p->planes * (uint32_t)(kHaloH * kHaloW) * d.kc * 2u;
+  } else if (d.b_resident) {
     d.b_region_bytes = b_all;
     d.stage_bytes = a_stage;
     d.tx_bytes = a_stage;
@@ -714,7 +876,7 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
   d.kb_bytes = d.stage_bytes;
   d.kb_tx_bytes = d.tx_bytes;
   const uint32_t ring = budget - d.b_region_bytes;
-  int g = (int)((28u * 1024u + d.kb_bytes - 1) / d.kb_bytes);
+  int g = d.halo ? (int)((20u * 1024u + d.kb_bytes - 1) / d.kb_bytes) : (int)((28u * 1024u + d.kb_bytes - 1) / d.kb_bytes);
   if (g > d.num_k) g = d.num_k;
   while (g > 1 && ring / ((uint32_t)g * d.kb_bytes) < 4) --g;      // keep the ring >= 4 deep
   for (int t = g; t >= 1 && t * 2 > g; --t)                         // prefer an even split of the k loop
@@ -736,7 +898,7 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
     if (p->stride == 1) {
       cuuint64_t dims[4] = {C, (cuuint64_t)w_in, (cuuint64_t)h_in, NP};
       cuuint64_t str[3] = {C * 2, (cuuint64_t)w_in * C * 2, (cuuint64_t)h_in * w_in * C * 2};
-      cuuint32_t box[4] = {(cuuint32_t)d.kc, kTileW, kTileH, 1};
+      cuuint32_t box[4] = {(cuuint32_t)d.kc, (cuuint32_t)(d.halo ? kHaloW : kTileW), (cuuint32_t)(d.halo ? kHaloH : kTileH), 1};
       rc = encode_map(&tmA[s], p->src[s], 4, dims, str, box, d.kc);
     } else {
       cuuint64_t dims[5] = {2 * C, (cuuint64_t)w_in / 2, 2, (cuuint64_t)h_in / 2, NP};
@@ -756,17 +918,20 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
     if (rc) return rc;
   }
   V2X_REQUIRE(d.num_k <= kMaxKBlocks, "too many k-blocks (%d > %d)", d.num_k, kMaxKBlocks);
-#define V2X_LAUNCH(BN_, KS_)                                                                     \
-  if (bn == BN_ && d.kc == 16 * KS_)                                                             \
-    return p->planes == 1 ? launch_tc<BN_, 1, KS_>(d, tmA[0], tmA[1], tmB, smem, stream)         \
-                          : launch_tc<BN_, 2, KS_>(d, tmA[0], tmA[1], tmB, smem, stream);
-  // kc = 16 only occurs for the 13(16)-channel input layer, kc = 32 for the 32/96-channel layers
-  V2X_LAUNCH(32, 1) V2X_LAUNCH(32, 2) V2X_LAUNCH(32, 4)
-  V2X_LAUNCH(48, 4)
-  V2X_LAUNCH(64, 1) V2X_LAUNCH(64, 2) V2X_LAUNCH(64, 4)
-  V2X_LAUNCH(128, 2) V2X_LAUNCH(128, 4)
-  V2X_LAUNCH(192, 4)
-  V2X_LAUNCH(256, 2) V2X_LAUNCH(256, 4)
+#define V2X_LAUNCH(BN_, KS_, HALO_)                                                                      \
+  if (bn == BN_ && d.kc == 16 * KS_ && (d.halo != 0) == HALO_)                                           \
+    return p->planes == 1 ? launch_tc<BN_, 1, KS_, HALO_>(d, tmA[0], tmA[1], tmB, smem, stream)          \
+                          : launch_tc<BN_, 2, KS_, HALO_>(d, tmA[0], tmA[1], tmB, smem, stream);
+  // kc = 16 only occurs for the 13(16)-channel input layer, kc = 32 for the 32/96-channel layers;
+  // halo mode needs resident weights, i.e. the small-N layers
+  V2X_LAUNCH(32, 1, true) V2X_LAUNCH(32, 2, true) V2X_LAUNCH(32, 4, true)
+  V2X_LAUNCH(64, 1, true) V2X_LAUNCH(64, 2, true) V2X_LAUNCH(64, 4, true)
+  V2X_LAUNCH(32, 1, false) V2X_LAUNCH(32, 2, false) V2X_LAUNCH(32, 4, false)
+  V2X_LAUNCH(48, 4, false)
+  V2X_LAUNCH(64, 1, false) V2X_LAUNCH(64, 2, false) V2X_LAUNCH(64, 4, false)
+  V2X_LAUNCH(128, 2, false) V2X_LAUNCH(128, 4, false)
+  V2X_LAUNCH(192, 4, false)
+  V2X_LAUNCH(256, 2, false) V2X_LAUNCH(256, 4, false)
 #undef V2X_LAUNCH
   set_error("no kernel instantiation for block_n %d with kc %d", bn, d.kc);
   return V2X_ERR_UNSUPPORTED;
