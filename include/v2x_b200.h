@@ -140,6 +140,38 @@ int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, const int64
                       int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t include_self,
                       int32_t only_v2i, void* stream);
 
+/* ---- when2com / who2com (CP/models/det/When2com.py) --------------------------------------- */
+
+/*
+ * Small fp32 linear layer y = [relu](x W^T + b), rows x in_f -> rows x out_f (KmGenerator MLP, When2com.py:415-430).
+ * in_mode 0: x is fp32 [rows][in_f].  in_mode 1: x is an act [planes][rows][hw][c] read in NCHW-flatten order
+ * (i = ch * hw + px), the order `features_map.view(-1, n_feat)` produces (When2com.py:429).
+ */
+int v2x_linear_fwd(const void* x, const float* w, const float* b, float* y, int32_t rows, int32_t in_f, int32_t out_f,
+                   int32_t relu, int32_t in_mode, int32_t hw, int32_t c, int32_t planes, void* stream);
+
+/*
+ * Attention scores of MIMOGeneralDotProductAttention.forward (When2com.py:374-412) and the eval-time gate:
+ *   q' = W q + bw (Linear query_size -> key_size); attn[b][k][j] = softmax_k(key[b,k] . q'[b,j])
+ *   coef[b][k][j]: gate_mode 0 = attn; 1 "activated" = p * (p > 0.2) with p = attn + 0.001 * I (When2com.py:125-148,273-276);
+ *                  2 "argmax_test" = one-hot over k of argmax p (When2com.py:94-123)
+ * keys [A*B][key_size], querys [A*B][query_size] fp32, agent-major rows (B*i + b); outputs fp32 [B][A][A].
+ */
+int v2x_attn_scores_fwd(const float* keys, const float* querys, const float* w, const float* bw, float* attn,
+                        float* coef, int32_t batch, int32_t agents, int32_t key_size, int32_t query_size,
+                        int32_t gate_mode, void* stream);
+
+/*
+ * Gated cross-agent fuse (un-flipped domain, same theta' as v2x_warp_mean_fwd):
+ *   warp_flag 1: out[b,q] = sum_{k<na[b]} coef[b,k,q] * (k == q ? x[b,q] : warp(x[b,q], T[b,q,k]))  -- the reference's
+ *                val_mat[b,k,q] pairing (When2com.py:206-225,397-412); agents q >= na[b] give zeros
+ *   warp_flag 0: out[b,q] = sum_{k<A} coef[b,k,q] * x[b,k]
+ * Replaces the [B,A,A,C,H,W] val_mat + broadcast multiply + sum (never materialised here).
+ */
+int v2x_warp_gated_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent, const float* coef,
+                       int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes,
+                       int32_t warp_flag, int32_t only_v2i, void* stream);
+
 /* act (bf16 planes, NHWC) -> fp32 NCHW, for returning intermediate maps to torch callers */
 int v2x_act_to_nchw_f32(const void* act, float* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t planes,
                         void* stream);

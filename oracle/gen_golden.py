@@ -57,6 +57,27 @@ def gen_v2vnet(tag, batch, seed, present=None, gnn_iter=3):
     print(tag, "loc.sum", out["loc.sum"], "cls.sum", out["cls.sum"])
 
 
+def gen_when2com(tag, batch, seed, warp_flag, inference, present=None):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ref_loader.ref_when2com_det(warp_flag=warp_flag)
+    sd = synth.when2com_det_state(seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(batch, 5, seed, present=present)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        r = m(bevs, trans, nat, training=False, MO_flag=True, inference=inference, batch_size=batch)
+    out = {"meta": np.asarray([batch, 5, seed, warp_flag], dtype=np.int64), "inference": np.asarray(inference)}
+    if present is not None:
+        out["present"] = np.asarray(present, dtype=np.int64)
+    summarize("loc", r["loc"], out)
+    summarize("cls", r["cls"], out)
+    out["cls.argmax_count"], out["cls.argmax_checksum"] = argmax_checksum(r["cls"])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+    print(tag, "loc.sum", out["loc.sum"], "cls.sum", out["cls.sum"])
+
+
 def gen_fafnet(tag, n, seed):
     m = ref_loader.ref_fafnet(kd_flag=0)
     sd = synth.fafnet_state(seed)
@@ -142,6 +163,9 @@ def main():
     gen_stages("v2vnet_det_stages_seed0", 0)
     gen_v2vnet("v2vnet_det_A5B1_seed0", 1, 0)
     gen_v2vnet("v2vnet_det_A5B2_seed1_present53", 2, 1, present=[5, 3])
+    gen_when2com("when2com_det_warp_activated_seed2", 1, 2, 1, "activated")
+    gen_when2com("when2com_det_nowarp_argmax_seed3_present4", 1, 3, 0, "argmax_test", present=[4])
+    gen_when2com("when2com_det_warp_softmax_B2_seed4", 2, 4, 1, "softmax", present=[3, 5])
     return 0
 
 

@@ -75,3 +75,9 @@ def ref_fafnet(num_agent=5, kd_flag=0):
     install()
     FaFNet = importlib.import_module("coperception.models.det.FaFNet").FaFNet
     return FaFNet(ref_config(), layer=3, kd_flag=kd_flag, num_agent=num_agent)
+
+
+def ref_when2com_det(warp_flag=1, num_agent=5):
+    install()
+    When2com = importlib.import_module("coperception.models.det.When2com").When2com
+    return When2com(ref_config(), layer=3, warp_flag=warp_flag, num_agent=num_agent)

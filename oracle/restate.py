@@ -172,3 +172,86 @@ def fafnet_forward(bevs, sd, compress_level=0, stages=False):
     if stages:
         res = dict(res, enc=enc, dec=dec)
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# When2com / who2com detection (CP/models/det/When2com.py)
+# ---------------------------------------------------------------------------------------------
+def policy_net4(bevs, sd, p="query_key_net."):
+    """PolicyNet4.forward (When2com.py:353-359): a second LidarEncoder (its x_4) + five conv+BN+ReLU."""
+    x = encode(bevs, sd, p + "lidar_encoder.")[4]
+    for name, stride in (("conv1", 1), ("conv2", 1), ("conv3", 2), ("conv4", 1), ("conv5", 2)):
+        x = cbr(x, sd, p + name + ".", "cbr_unit.0", "cbr_unit.1", stride=stride)
+    return x
+
+
+def km_generator(maps, sd, p):
+    """KmGenerator.forward (When2com.py:428-430): view(-1, 256*4*4) -> Linear/ReLU/Linear/ReLU/Linear."""
+    x = maps.reshape(-1, 256 * 4 * 4)
+    x = F.relu(F.linear(x, sd[p + "fc.0.weight"], sd[p + "fc.0.bias"]))
+    x = F.relu(F.linear(x, sd[p + "fc.2.weight"], sd[p + "fc.2.bias"]))
+    return F.linear(x, sd[p + "fc.4.weight"], sd[p + "fc.4.bias"])
+
+
+def when2com_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=1, agent_num=5, warp_flag=1,
+                         inference="activated", training=False, only_v2i=False, stages=False):
+    """det When2com.forward (When2com.py:150-332), layer = 3, has_query, MO_flag.  Eval-mode semantics:
+    ``inference`` in {"softmax", "activated", "argmax_test"}; training=True stops after the first decoder pass."""
+    enc = encode(bevs, sd, "u_encoder.")
+    x, x_1, x_2, x_3, x_4 = enc
+    c, h, w = x_3.shape[1:]
+    size = (1, c, h, w)
+    feat = torch.flip(x_3, (2,))
+    local = torch.stack([feat[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)  # [B,A,C,H,W]
+    if warp_flag == 1:
+        val_mat = torch.zeros(batch_size, agent_num, agent_num, c, h, w)
+        for b in range(batch_size):
+            na = int(num_agent_tensor[b, 0])
+            for i in range(na):
+                for j in range(na):
+                    if j == i:
+                        val_mat[b, i, j] = local[b, i]
+                    else:
+                        if only_v2i and i != 0 and j != 0:
+                            continue
+                        val_mat[b, i, j] = feature_transformation(local, b, j, i, trans_matrices, size)
+    else:
+        val_mat = local
+    qk = policy_net4(bevs, sd)
+    keys = km_generator(qk, sd, "key_net.")
+    querys = km_generator(qk, sd, "query_net.")
+    key_mat = torch.stack([keys[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)      # [B,A,1024]
+    query_mat = torch.stack([querys[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)  # [B,A,32]
+    # MIMOGeneralDotProductAttention.forward (When2com.py:374-412)
+    query = F.linear(query_mat, sd["attention_net.linear.weight"], sd["attention_net.linear.bias"])
+    attn = torch.softmax(torch.bmm(key_mat, query.transpose(2, 1)), dim=1)  # [B, key, query]
+
+    def weighted(coef):
+        ce = coef.view(batch_size, agent_num, agent_num, 1, 1, 1)
+        v = val_mat if warp_flag == 1 else val_mat.unsqueeze(2).expand(-1, -1, agent_num, -1, -1, -1)
+        return (ce * v).sum(1)  # [B, query, C, H, W]
+
+    def to_batch(f):  # agents_to_batch (DetModelBase.py:53-69): agent-major + flip back
+        return torch.flip(torch.cat([f[:, i] for i in range(agent_num)], 0), (2,))
+
+    fuse1 = to_batch(weighted(attn))
+    x_dec = decode(x, x_1, x_2, fuse1, x_4, sd, "decoder.")[0]
+    prob = attn + torch.eye(agent_num).view(1, agent_num, agent_num) * 0.001
+    fuse2 = None
+    if not training:
+        if inference == "softmax":
+            pass
+        elif inference in ("activated", "argmax_test"):
+            if inference == "activated":
+                coef = prob * (prob > 0.2).float()                       # activated_select (:125-148)
+            else:
+                coef = F.one_hot(prob.max(dim=1)[1], num_classes=agent_num).float().transpose(1, 2)  # argmax_select (:94-123)
+            fuse2 = to_batch(weighted(coef))
+            # NOTE: the layer-0 skip input of the second pass is the OUTPUT of the first pass (`x` was overwritten, :266-270)
+            x_dec = decode(x_dec, x_1, x_2, fuse2, x_4, sd, "decoder.")[0]
+        else:
+            raise ValueError("Incorrect inference mode")
+    res = heads(x_dec, sd)
+    if stages:
+        res = dict(res, enc=enc, qk=qk, keys=keys, querys=querys, attn=attn, fuse1=fuse1, fuse2=fuse2, x8=x_dec)
+    return res

@@ -108,3 +108,43 @@ def test_v2vnet_graph_replay_matches_eager():
     torch.cuda.synchronize()
     for k in eager:
         assert torch.equal(eager[k], out[k])
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("tag", ["when2com_det_warp_activated_seed2", "when2com_det_nowarp_argmax_seed3_present4",
+                                 "when2com_det_warp_softmax_B2_seed4"])
+def test_when2com_det_forward(tag, planes, golden_dir):
+    """det When2com / who2com through the drop-in module, vs oracle + live-reference fixture."""
+    from coperception.models.det import When2com
+    from oracle import restate, synth
+    from v2x_b200 import default_det_config
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    batch, a, seed, warp = [int(v) for v in g["meta"]]
+    inference = str(g["inference"])
+    present = [int(v) for v in g["present"]] if "present" in g.files else None
+    sd = synth.when2com_det_state(seed)
+    bevs, trans, nat = synth.make_scene(batch, a, seed, present=present)
+    with torch.no_grad():
+        ref = restate.when2com_det_forward(bevs, trans, nat, sd, batch_size=batch, agent_num=a, warp_flag=warp,
+                                           inference=inference, stages=True)
+    model = When2com(default_det_config(), layer=3, warp_flag=warp, num_agent=a)
+    model.load_state_dict(sd, strict=True)
+    model.precision = "bf16x3" if planes == 2 else "bf16"
+    model = model.cuda().eval()
+    with torch.no_grad():
+        out = model(bevs.cuda(), trans.cuda(), nat.cuda(), training=False, MO_flag=True, inference=inference,
+                    batch_size=batch)
+    torch.cuda.synchronize()
+    plan = next(iter(model._plans.values()))
+    print("when2com %s planes=%d attn err %.3e" % (tag, planes, (plan.attn.cpu() - ref["attn"]).abs().max().item()))
+    for k in ("loc", "cls"):
+        e, eg = rel_err(out[k], ref[k]), _golden_sub(out[k], g, k)
+        print("when2com %s planes=%d %s rel_err=%.3e golden=%.3e" % (tag, planes, k, e, eg))
+        assert out[k].shape == ref[k].shape
+        if planes == 2 or inference == "softmax":
+            assert e < REL_TOL[planes] and eg < REL_TOL[planes]
+    if planes == 2:
+        err = (out["cls"].cpu() - ref["cls"]).abs().max().item()
+        flips, bad = argmax_flips(out["cls"], ref["cls"], err)
+        print("when2com %s argmax flips %d (outside margin %d)" % (tag, flips, bad))
+        assert bad == 0

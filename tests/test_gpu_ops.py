@@ -229,3 +229,80 @@ def test_convgru_zero_hidden(impl, planes):
     print("gru %s planes=%d rel_err=%.3e" % (impl, planes, err))
     assert err < TOL[planes]
     assert rel_err(got[2], ops.act_to_float(a_h).cpu()[2]) == 0.0
+
+
+def test_conv_partial_tiles():
+    """Maps smaller than one 8x16 tile (PolicyNet4's 8x8 / 4x4 stages, When2com.py:345-351): TMA zero-fills the
+    reads beyond the map and the epilogue masks the stores."""
+    from v2x_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    for stride, h in ((2, 16), (1, 8), (2, 8)):
+        x = torch.randn((3, 64, h, h), generator=g)
+        wt = (torch.rand((256, 64, 3, 3), generator=g) - 0.5) * 0.15
+        b = torch.randn(256, generator=g) * 0.1
+        bn = rand_bn(256, g)
+        ref = ref_cbr([x], wt, b, bn, stride)
+        pc = ops.pack_conv(wt, b, bn, cins=[64], stride=stride, planes=2, device=dev)
+        out = ops.conv(pc, [to_act(x, 2, dev)])
+        assert out.shape[2:4] == (h // stride, h // stride)
+        err = rel_err(ops.act_to_float(out), ref)
+        print("partial tile stride %d %dx%d rel_err=%.3e" % (stride, h, h, err))
+        assert err < TOL[2]
+
+
+def test_linear_and_attention_scores():
+    """KmGenerator MLP (NCHW-flatten of an NHWC act) and the attention score / gate kernel vs torch."""
+    from v2x_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    B, A = 2, 5
+    maps = torch.randn((A * B, 256, 4, 4), generator=g)
+    w0, b0 = torch.randn((256, 4096), generator=g) * 0.02, torch.randn(256, generator=g) * 0.1
+    ref = F.relu(F.linear(maps.reshape(A * B, -1), w0, b0))
+    got = ops.linear(to_act(maps, 2, dev), w0.to(dev), b0.to(dev), relu=True, act_input=True)
+    assert rel_err(got, ref) < 1e-4
+    keys, querys = torch.randn((A * B, 1024), generator=g) * 0.3, torch.randn((A * B, 32), generator=g)
+    aw, ab = (torch.rand((1024, 32), generator=g) - 0.5) * 0.06, (torch.rand(1024, generator=g) - 0.5) * 0.04
+    km = torch.stack([keys[B * i: B * (i + 1)] for i in range(A)], 1)
+    qm = torch.stack([querys[B * i: B * (i + 1)] for i in range(A)], 1)
+    attn_ref = torch.softmax(torch.bmm(km, F.linear(qm, aw, ab).transpose(2, 1)), dim=1)
+    prob = attn_ref + torch.eye(A).view(1, A, A) * 0.001
+    for mode, coef_ref in (("softmax", attn_ref), ("activated", prob * (prob > 0.2).float()),
+                           ("argmax_test", F.one_hot(prob.max(dim=1)[1], num_classes=A).float().transpose(1, 2))):
+        attn, coef = ops.attn_scores(keys.to(dev), querys.to(dev), aw.to(dev), ab.to(dev), B, A, ops.GATE_MODES[mode])
+        assert (attn.cpu() - attn_ref).abs().max().item() < 1e-5
+        assert (coef.cpu() - coef_ref).abs().max().item() < 1e-5, mode
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("warp_flag", [1, 0])
+def test_warp_gated(warp_flag, planes):
+    """when2com gated fuse vs the val_mat formulation of the oracle (flipped domain, When2com.py:199-225,397-412)."""
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(21)
+    B, A, C = 2, 5, 16
+    present = [5, 3]
+    x = torch.randn((A * B, C, 32, 32), generator=g)  # un-flipped, agent-major
+    trans = synth.make_trans_matrices(B, A, 21, present=present)
+    nat = torch.tensor([[p] * A for p in present], dtype=torch.long)
+    coef = torch.rand((B, A, A), generator=g)
+    coef[0, 1, 2] = 0.0
+    feat = torch.flip(x, (2,))
+    local = torch.stack([feat[B * i: B * (i + 1)] for i in range(A)], 1)
+    if warp_flag:
+        val = torch.zeros(B, A, A, C, 32, 32)
+        for b in range(B):
+            for i in range(present[b]):
+                for j in range(present[b]):
+                    val[b, i, j] = local[b, i] if i == j else restate.feature_transformation(local, b, j, i, trans, (1, C, 32, 32))
+    else:
+        val = local.unsqueeze(2).expand(-1, -1, A, -1, -1, -1)
+    fused = (coef.view(B, A, A, 1, 1, 1) * val).sum(1)
+    ref = torch.flip(torch.cat([fused[:, i] for i in range(A)], 0), (2,))
+    out = ops.warp_gated(to_act(x, planes, dev), trans.to(dev), nat.to(dev), coef.to(dev), B, A, warp_flag=warp_flag)
+    err = rel_err(ops.act_to_float(out), ref)
+    print("warp_gated warp=%d planes=%d rel_err=%.3e" % (warp_flag, planes, err))
+    assert err < TOL[planes]

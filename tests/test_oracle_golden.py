@@ -78,3 +78,19 @@ def test_v2vnet_det(golden_dir, tag):
     cnt, chk = argmax_checksum(r["cls"])
     # argmax can legitimately flip where the two logits agree to ~1e-5; allow a handful
     assert np.abs(cnt - g["cls.argmax_count"]).max() <= 4
+
+
+@pytest.mark.parametrize("tag", ["when2com_det_warp_activated_seed2", "when2com_det_nowarp_argmax_seed3_present4",
+                                 "when2com_det_warp_softmax_B2_seed4"])
+def test_when2com_det(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    batch, a, seed, warp = [int(v) for v in g["meta"]]
+    inference = str(g["inference"])
+    present = [int(v) for v in g["present"]] if "present" in g.files else None
+    sd = synth.when2com_det_state(seed)
+    bevs, trans, nat = synth.make_scene(batch, a, seed, present=present)
+    with torch.no_grad():
+        r = restate.when2com_det_forward(bevs, trans, nat, sd, batch_size=batch, agent_num=a, warp_flag=warp,
+                                         inference=inference)
+    _check("loc", r["loc"], g)
+    _check("cls", r["cls"], g)

@@ -303,3 +303,246 @@ extern "C" int v2x_act_to_nchw_f32(const void* act, float* out, int32_t n, int32
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }
+
+// =============================================================================================
+// when2com / who2com helpers (CP/models/det/When2com.py): KmGenerator MLP, attention scores, gated fuse
+// =============================================================================================
+namespace v2x {
+
+// y[r][o] = [relu](b[o] + sum_i w[o][i] * x[r][i]); one warp per output element, lanes stride the reduction.
+// in_mode 1 reads x from an act tensor [planes][rows][hw][c] in NCHW-flatten order (i = ch * hw + px), which is
+// how `features_map.view(-1, n_feat)` flattens the policy maps (When2com.py:429).
+__global__ void linear_kernel(const void* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                              float* __restrict__ y, int rows, int in_f, int out_f, int relu, int in_mode, int hw,
+                              int c, int planes) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= (long long)rows * out_f) return;
+  const int r = (int)(gw / out_f), o = (int)(gw % out_f);
+  const float* wr = w + (long long)o * in_f;
+  float acc = 0.f;
+  if (in_mode == 0) {
+    const float* xr = reinterpret_cast<const float*>(x) + (long long)r * in_f;
+    for (int i = lane; i < in_f; i += 32) acc = fmaf(__ldg(wr + i), __ldg(xr + i), acc);
+  } else {
+    const __nv_bfloat16* xa = reinterpret_cast<const __nv_bfloat16*>(x);
+    const long long plane_stride = (long long)rows * hw * c;
+    for (int i = lane; i < in_f; i += 32) {
+      const int ch = i / hw, px = i - ch * hw;
+      const long long idx = ((long long)r * hw + px) * c + ch;
+      float v = __bfloat162float(xa[idx]);
+      if (planes == 2) v += __bfloat162float(xa[idx + plane_stride]);
+      acc = fmaf(__ldg(wr + i), v, acc);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    acc += b ? b[o] : 0.f;
+    y[(long long)r * out_f + o] = relu ? fmaxf(acc, 0.f) : acc;
+  }
+}
+
+// MIMOGeneralDotProductAttention scores (When2com.py:374-412) + the eval-time gating (:259-327, :94-148).
+// One block per scene.  keys [A*B][ks], querys [A*B][qs] are agent-major (row = B*i + b).
+//   q' = W q + bw;  s[k][j] = key_k . q'_j;  attn[b][k][j] = softmax over k
+//   coef (gate_mode): 0 = attn; 1 ("activated") = p * (p > 0.2), p = attn + 0.001 I; 2 ("argmax_test") = one-hot over k of argmax p
+__global__ void attn_scores_kernel(const float* __restrict__ keys, const float* __restrict__ querys,
+                                   const float* __restrict__ w, const float* __restrict__ bw, float* __restrict__ attn,
+                                   float* __restrict__ coef, int batch, int agents, int ks, int qs, int gate_mode) {
+  extern __shared__ float sm[];
+  float* qp = sm;                    // [agents][ks]
+  float* sc = sm + agents * ks;      // [agents][agents]
+  const int b = blockIdx.x;
+  for (int idx = threadIdx.x; idx < agents * ks; idx += blockDim.x) {
+    const int j = idx / ks, d = idx - j * ks;
+    const float* q = querys + ((long long)batch * j + b) * qs;
+    float a = bw[d];
+    for (int t = 0; t < qs; ++t) a = fmaf(w[(long long)d * qs + t], q[t], a);
+    qp[idx] = a;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int pair = warp; pair < agents * agents; pair += nw) {
+    const int k = pair / agents, j = pair - k * agents;
+    const float* key = keys + ((long long)batch * k + b) * ks;
+    float a = 0.f;
+    for (int d = lane; d < ks; d += 32) a = fmaf(key[d], qp[j * ks + d], a);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if (lane == 0) sc[pair] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < agents) {
+    const int j = threadIdx.x;
+    float m = -INFINITY;
+    for (int k = 0; k < agents; ++k) m = fmaxf(m, sc[k * agents + j]);
+    float sum = 0.f;
+    for (int k = 0; k < agents; ++k) sum += expf(sc[k * agents + j] - m);
+    int best = 0;
+    float bestp = -1.f;
+    for (int k = 0; k < agents; ++k) {
+      const float pa = expf(sc[k * agents + j] - m) / sum;
+      attn[((long long)b * agents + k) * agents + j] = pa;
+      const float pp = pa + (k == j ? 0.001f : 0.f);
+      if (pp > bestp) { bestp = pp; best = k; }
+      if (gate_mode == 0) coef[((long long)b * agents + k) * agents + j] = pa;
+      else if (gate_mode == 1) coef[((long long)b * agents + k) * agents + j] = pp > 0.2f ? pp : 0.f;
+    }
+    if (gate_mode == 2)
+      for (int k = 0; k < agents; ++k) coef[((long long)b * agents + k) * agents + j] = k == best ? 1.f : 0.f;
+  }
+}
+
+// Gated cross-agent fuse of when2com, un-flipped domain (same theta' as warp_mean_kernel):
+//   warp_flag 1: out[b,q] = sum_{k<na} coef[b,k,q] * (k == q ? x[b,q] : warp(x[b,q], T[b,q,k]))   (val_mat[b,k,q], Q8)
+//                 agents q >= na produce zeros (their val_mat rows/cols are never filled, When2com.py:199-225)
+//   warp_flag 0: out[b,q] = sum_{k<A}  coef[b,k,q] * x[b,k]                                        (all agent slots)
+template <int VEC_PER_LANE>
+__global__ void warp_gated_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                  const double* __restrict__ trans, const long long* __restrict__ num_agent,
+                                  const float* __restrict__ coef, int batch, int agents, int H, int W, int C,
+                                  int planes, int warp_flag, int only_v2i) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total_pix = (long long)batch * agents * H * W;
+  const long long plane_stride = total_pix * C;
+  for (long long wid = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total_pix;
+       wid += (long long)gridDim.x * warps_per_block) {
+    const int ow = (int)(wid % W);
+    const int oh = (int)((wid / W) % H);
+    const int map = (int)(wid / ((long long)W * H));
+    const int q = map / batch, b = map % batch;
+    const int na = (int)num_agent[(long long)b * agents];
+    float acc[VEC_PER_LANE][8];
+#pragma unroll
+    for (int v = 0; v < VEC_PER_LANE; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[v][e] = 0.f;
+    const int nterms = warp_flag ? (q < na ? na : 0) : agents;
+    const float gx = (2.f * ow + 1.f) / W - 1.f, gy = (2.f * oh + 1.f) / H - 1.f;
+    for (int k = 0; k < nterms; ++k) {
+      const float cf = coef[((long long)b * agents + k) * agents + q];
+      if (cf == 0.f) continue;
+      if (warp_flag && only_v2i && k != q && k != 0 && q != 0) continue;
+      const long long src_map = warp_flag ? (long long)batch * q + b : (long long)batch * k + b;
+      float wts[4];
+      int xs[4], ys[4];
+      int ntap = 4;
+      if (!warp_flag || k == q) {
+        ntap = 1; wts[0] = 1.f; xs[0] = ow; ys[0] = oh;
+      } else {
+        const double* T = trans + ((((long long)b * agents + q) * agents + k) << 4);  // q's map into k's frame
+        const float t00 = (float)T[0], t01 = -(float)T[1], t02 = -(float)T[3] * (1.f / 32.f);
+        const float t10 = -(float)T[4], t11 = (float)T[5], t12 = (float)T[7] * (1.f / 32.f);
+        const float sx = t00 * gx + t01 * gy + t02, sy = t10 * gx + t11 * gy + t12;
+        const float ix = ((sx + 1.f) * W - 1.f) * 0.5f, iy = ((sy + 1.f) * H - 1.f) * 0.5f;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          xs[t] = x0 + (t & 1); ys[t] = y0 + (t >> 1);
+          wts[t] = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
+        }
+      }
+      for (int t = 0; t < ntap; ++t) {
+        if (xs[t] < 0 || xs[t] >= W || ys[t] < 0 || ys[t] >= H) continue;
+        const float wgt = wts[t] * cf;
+        const __nv_bfloat16* sp = x + ((src_map * H + ys[t]) * W + xs[t]) * C;
+#pragma unroll
+        for (int v = 0; v < VEC_PER_LANE; ++v) {
+          const int c0 = (v * 32 + lane) * 8;
+          if (c0 < C) {
+            uint4 qv = __ldg(reinterpret_cast<const uint4*>(sp + c0));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+            uint4 ql = make_uint4(0, 0, 0, 0);
+            if (planes == 2) ql = __ldg(reinterpret_cast<const uint4*>(sp + plane_stride + c0));
+            const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(h2[e]);
+              if (planes == 2) {
+                const float2 g = __bfloat1622float2(l2[e]);
+                f.x += g.x; f.y += g.y;
+              }
+              acc[v][2 * e] += wgt * f.x;
+              acc[v][2 * e + 1] += wgt * f.y;
+            }
+          }
+        }
+      }
+    }
+    __nv_bfloat16* dp = out + wid * C;
+#pragma unroll
+    for (int v = 0; v < VEC_PER_LANE; ++v) {
+      const int c0 = (v * 32 + lane) * 8;
+      if (c0 < C) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(acc[v][2 * e], h0, l0);
+          split_bf16(acc[v][2 * e + 1], h1, l1);
+          hi[e] = pack_bf16x2(h0, h1);
+          lo[e] = pack_bf16x2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(dp + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (planes == 2) *reinterpret_cast<uint4*>(dp + plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+}
+
+}  // namespace v2x
+
+extern "C" int v2x_linear_fwd(const void* x, const float* w, const float* b, float* y, int32_t rows, int32_t in_f,
+                              int32_t out_f, int32_t relu, int32_t in_mode, int32_t hw, int32_t c, int32_t planes,
+                              void* stream) {
+  V2X_REQUIRE(x && w && y && rows > 0 && in_f > 0 && out_f > 0, "null/empty");
+  V2X_REQUIRE(in_mode == 0 || (in_mode == 1 && hw > 0 && c > 0 && hw * c == in_f && (planes == 1 || planes == 2)),
+              "bad act input geometry");
+  const long long threads = (long long)rows * out_f * 32;
+  linear_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, b, y, rows, in_f, out_f, relu,
+                                                                                    in_mode, hw, c, planes);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_attn_scores_fwd(const float* keys, const float* querys, const float* w, const float* bw,
+                                   float* attn, float* coef, int32_t batch, int32_t agents, int32_t key_size,
+                                   int32_t query_size, int32_t gate_mode, void* stream) {
+  V2X_REQUIRE(keys && querys && w && bw && attn && coef, "null pointer");
+  V2X_REQUIRE(batch > 0 && agents > 0 && agents <= 8 && key_size > 0 && query_size > 0, "bad sizes");
+  V2X_REQUIRE(gate_mode >= 0 && gate_mode <= 2, "gate_mode must be 0 (softmax), 1 (activated) or 2 (argmax)");
+  const size_t smem = ((size_t)agents * key_size + agents * agents) * sizeof(float);
+  V2X_REQUIRE(smem <= 48 * 1024, "key_size too large for the score kernel");
+  attn_scores_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(keys, querys, w, bw, attn, coef, batch, agents, key_size,
+                                                              query_size, gate_mode);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_warp_gated_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent,
+                                  const float* coef, int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c,
+                                  int32_t planes, int32_t warp_flag, int32_t only_v2i, void* stream) {
+  V2X_REQUIRE(x && out && trans && num_agent && coef, "null pointer");
+  V2X_REQUIRE(batch > 0 && agents > 0 && h > 0 && w > 0, "empty geometry");
+  V2X_REQUIRE(c > 0 && c % 8 == 0 && c <= 1024, "channels must be a multiple of 8, <= 1024");
+  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  const long long total_pix = (long long)batch * agents * h * w;
+  const int threads = 256;
+  const unsigned grid = grid_for(total_pix * 32, threads, 8);
+  const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
+  const long long* na = reinterpret_cast<const long long*>(num_agent);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c <= 256)
+    warp_gated_kernel<1><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i);
+  else if (c <= 512)
+    warp_gated_kernel<2><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i);
+  else
+    warp_gated_kernel<4><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}

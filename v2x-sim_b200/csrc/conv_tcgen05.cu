@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int r_h = HALO ? (row >> 3) : (row >> 4), r_w = HALO ? (row & 7) : (row & 15);
-    const bool no_store = p.debug_mode == 3;
+    const bool dbg_no_store = p.debug_mode == 3;
     const int up = p.upsample2x ? 2 : 1;
     const int Hs = p.h_out * up, Ws = p.w_out * up;
     int it = 0;
@@ -498,14 +498,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     ti.init(p, blockIdx.x, grid_stride);
     for (; ti.tile < p.m_tiles; ti.next(grid_stride)) {
       const int oh = ti.th * TILE_H + r_h, ow = ti.tw * TILE_W + r_w;
+      const bool valid = oh < p.h_out && ow < p.w_out;   // partial tiles at the map border
       if (is_gru && gru_unit_absent(p, ti.n_img)) {
-        copy_passthrough(p, ti.n_img, oh, ow, blockIdx.y * 64, 64);
+        if (valid) copy_passthrough(p, ti.n_img, oh, ow, blockIdx.y * 64, 64);
         continue;
       }
       const int acc_buf = it & 1;
       mbar_wait(bar_tfull + 8 * acc_buf, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_buf * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
+      const bool no_store = dbg_no_store || !valid;
       if (p.epilogue == V2X_EPI_F32_SPLIT) {
 #pragma unroll 1
         for (int c32 = 0; c32 < (BN + 31) / 32; ++c32) {
@@ -517,8 +519,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           if (two) tmem_ld16_async(taddr + c32 * 32 + 16, v1);
           tmem_ld_wait16(v0);
           if (two) tmem_ld_wait16(v1);
-          epi_f32_split16(p, ti.n_img, oh, ow, ch0, v0, s_bias + c32 * 32);
-          if (two) epi_f32_split16(p, ti.n_img, oh, ow, ch0 + 16, v1, s_bias + c32 * 32 + 16);
+          if (valid) epi_f32_split16(p, ti.n_img, oh, ow, ch0, v0, s_bias + c32 * 32);
+          if (two && valid) epi_f32_split16(p, ti.n_img, oh, ow, ch0 + 16, v1, s_bias + c32 * 32 + 16);
         }
       } else {
         OutPix o;
@@ -726,8 +728,7 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
   V2X_REQUIRE(p->taps == 9 || (p->taps == 1 && p->stride == 1), "taps must be 9, or 1 with stride 1");
   V2X_REQUIRE(p->planes == 1 || p->planes == 2, "planes must be 1 or 2");
   V2X_REQUIRE(p->n_maps > 0 && p->h_out > 0 && p->w_out > 0, "empty geometry");
-  V2X_REQUIRE(p->h_out % kTileH == 0 && p->w_out % kTileW == 0, "h_out %% 8 / w_out %% 16 != 0 (%d x %d)", p->h_out,
-              p->w_out);
+  V2X_REQUIRE(p->stride == 1 || (p->h_out * 2) % 2 == 0, "bad geometry");
   V2X_REQUIRE(p->cin[0] > 0 && p->cin[0] % 16 == 0, "cin[0] must be a positive multiple of 16");
   V2X_REQUIRE(p->src[1] == nullptr || (p->cin[1] > 0 && p->cin[1] % 16 == 0), "cin[1] must be a multiple of 16");
   const int bn = p->block_n;
@@ -749,8 +750,9 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
     d.num_k += p->taps * d.cblocks[s];
     d.k_total += p->taps * d.cin[s];
   }
-  d.tiles_w = p->w_out / kTileW;
-  d.tiles_per_img = d.tiles_w * (p->h_out / kTileH);
+  // partial tiles are allowed: TMA zero-fills reads beyond the map, the epilogue masks stores beyond it
+  d.tiles_w = (p->w_out + kTileW - 1) / kTileW;
+  d.tiles_per_img = d.tiles_w * ((p->h_out + kTileH - 1) / kTileH);
   d.m_tiles = p->n_maps * d.tiles_per_img;
   d.n_tiles = p->cout_pad / p->block_n;
   d.cout = p->cout; d.cout_pad = p->cout_pad;

@@ -63,6 +63,9 @@ SYMBOLS = [
     ("v2x_pack_input", C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
     ("v2x_warp_mean_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_act_to_nchw_f32", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_linear_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_attn_scores_fwd", C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_warp_gated_fwd", C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
 ]
 
 _lib = None

@@ -100,33 +100,34 @@ class DetPlan:
         self.add(lambda: ops.pack_input(bev, IN_C_PAD, planes, out=x_in))
         return x_in
 
-    def build_encoder(self, w: BackboneWeights, x_in):
+    def build_encoder(self, w: BackboneWeights, x_in, tag="", upsample_x4=True):
         c = w.c
-        t = self.conv(c["conv_pre_1"], [x_in], "x0a")
-        x0 = self.conv(c["conv_pre_2"], [t], "x0")
-        t = self.conv(c["conv1_1"], [x0], "x1a")
-        t = self.conv(c["conv1_2"], [t], "x1b")
-        x1 = self.conv(c["conv3d_1"], [t], "x1")
-        t = self.conv(c["conv2_1"], [x1], "x2a")
-        t = self.conv(c["conv2_2"], [t], "x2b")
-        x2 = self.conv(c["conv3d_2"], [t], "x2")
-        t = self.conv(c["conv3_1"], [x2], "x3a")
-        x3 = self.conv(c["conv3_2"], [t], "x3")
-        t = self.conv(c["conv4_1"], [x3], "x4a")
-        # x_4 is only ever consumed through F.interpolate(x_4, 2) (Backbone.py:176): store it upsampled
-        x4u = self.conv(c["conv4_2"], [t], "x4u", upsample2x=True)
-        return x0, x1, x2, x3, x4u
+        t = self.conv(c["conv_pre_1"], [x_in], tag + "x0a")
+        x0 = self.conv(c["conv_pre_2"], [t], tag + "x0")
+        t = self.conv(c["conv1_1"], [x0], tag + "x1a")
+        t = self.conv(c["conv1_2"], [t], tag + "x1b")
+        x1 = self.conv(c["conv3d_1"], [t], tag + "x1")
+        t = self.conv(c["conv2_1"], [x1], tag + "x2a")
+        t = self.conv(c["conv2_2"], [t], tag + "x2b")
+        x2 = self.conv(c["conv3d_2"], [t], tag + "x2")
+        t = self.conv(c["conv3_1"], [x2], tag + "x3a")
+        x3 = self.conv(c["conv3_2"], [t], tag + "x3")
+        t = self.conv(c["conv4_1"], [x3], tag + "x4a")
+        # in the detection decoder x_4 is only ever consumed through F.interpolate(x_4, 2) (Backbone.py:176):
+        # store it upsampled.  (PolicyNet4 consumes the plain x_4, When2com.py:354.)
+        x4 = self.conv(c["conv4_2"], [t], tag + ("x4u" if upsample_x4 else "x4"), upsample2x=upsample_x4)
+        return x0, x1, x2, x3, x4
 
-    def build_decoder(self, w: BackboneWeights, x0, x1, x2, x3, x4u):
+    def build_decoder(self, w: BackboneWeights, x0, x1, x2, x3, x4u, tag=""):
         c = w.c
-        t = self.conv(c["conv5_1"], [x4u, x3], "x5a")
-        x5u = self.conv(c["conv5_2"], [t], "x5u", upsample2x=True)
-        t = self.conv(c["conv6_1"], [x5u, x2], "x6a")
-        x6u = self.conv(c["conv6_2"], [t], "x6u", upsample2x=True)
-        t = self.conv(c["conv7_1"], [x6u, x1], "x7a")
-        x7u = self.conv(c["conv7_2"], [t], "x7u", upsample2x=True)
-        t = self.conv(c["conv8_1"], [x7u, x0], "x8a")
-        return self.conv(c["conv8_2"], [t], "x8")
+        t = self.conv(c["conv5_1"], [x4u, x3], tag + "x5a")
+        x5u = self.conv(c["conv5_2"], [t], tag + "x5u", upsample2x=True)
+        t = self.conv(c["conv6_1"], [x5u, x2], tag + "x6a")
+        x6u = self.conv(c["conv6_2"], [t], tag + "x6u", upsample2x=True)
+        t = self.conv(c["conv7_1"], [x6u, x1], tag + "x7a")
+        x7u = self.conv(c["conv7_2"], [t], tag + "x7u", upsample2x=True)
+        t = self.conv(c["conv8_1"], [x7u, x0], tag + "x8a")
+        return self.conv(c["conv8_2"], [t], tag + "x8")
 
     def build_heads(self, hw: HeadWeights, x8):
         t = self.conv(hw.head1, [x8], "head1")
@@ -228,5 +229,79 @@ class FaFNetPlan(DetPlan):
 
     def forward(self, bevs):
         self.bev_in.copy_(bevs.reshape(self.bev_in.shape), non_blocking=True)
+        self.run()
+        return self.result()
+
+
+class When2comDetPlan(DetPlan):
+    """det When2com / who2com forward in eval mode (CP/models/det/When2com.py:150-332, layer 3, has_query, MO_flag).
+
+    encoder -> [policy encoder + 5 convs -> key/query MLPs -> attention scores] -> gated fuse -> decoder -> (eval:
+    re-gated fuse -> second decoder pass whose layer-0 skip is the first pass's output) -> heads."""
+
+    def __init__(self, sd, batch: int, agents: int = 5, planes: int = 1, device="cuda", warp_flag=1,
+                 inference="activated", training_pass_only=False, only_v2i=False):
+        super().__init__(batch * agents, planes, device)
+        ops.require_gpu()
+        dev = self.device
+        self.batch, self.agents = batch, agents
+        f32 = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
+        self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
+        self.pol_w = BackboneWeights(sd, "query_key_net.lidar_encoder.", planes, dev, encoder=True, decoder=False)
+        self.head_w = HeadWeights(sd, planes, dev)
+        self.pol_convs = []
+        for name, stride, cin in (("conv1", 1, 512), ("conv2", 1, 512), ("conv3", 2, 256), ("conv4", 1, 256),
+                                  ("conv5", 2, 256)):
+            pre = "query_key_net.%s.cbr_unit." % name
+            self.pol_convs.append(ops.pack_conv(sd[pre + "0.weight"], sd[pre + "0.bias"], _bn(sd, pre + "1"), cins=[cin],
+                                                stride=stride, planes=planes, device=dev))
+        self.mlp = {net: [(f32("%s.fc.%d.weight" % (net, i)), f32("%s.fc.%d.bias" % (net, i))) for i in (0, 2, 4)]
+                    for net in ("key_net", "query_net")}
+        self.att_w, self.att_b = f32("attention_net.linear.weight"), f32("attention_net.linear.bias")
+        self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
+        self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
+        trans, na, n = self.trans, self.num_agent, self.n
+
+        x_in = self.build_input()
+        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
+        # ---- policy branch: second encoder's x_4 -> 5 convs -> [N,4,4,256] -> key / query MLPs ----
+        t = self.build_encoder(self.pol_w, x_in, tag="pol_", upsample_x4=False)[4]
+        for i, pc in enumerate(self.pol_convs):
+            t = self.conv(pc, [t], "pol_c%d" % (i + 1))
+        qk = t
+        feats = {}
+        for net in ("key_net", "query_net"):
+            (w0, b0), (w1, b1), (w2, b2) = self.mlp[net]
+            h0 = torch.empty((n, w0.shape[0]), dtype=torch.float32, device=dev)
+            h1 = torch.empty((n, w1.shape[0]), dtype=torch.float32, device=dev)
+            h2 = torch.empty((n, w2.shape[0]), dtype=torch.float32, device=dev)
+            self.add(lambda w0=w0, b0=b0, h0=h0: ops.linear(qk, w0, b0, relu=True, out=h0, act_input=True))
+            self.add(lambda w1=w1, b1=b1, h0=h0, h1=h1: ops.linear(h0, w1, b1, relu=True, out=h1))
+            self.add(lambda w2=w2, b2=b2, h1=h1, h2=h2: ops.linear(h1, w2, b2, relu=False, out=h2))
+            feats[net] = h2
+        self.keys, self.querys = feats["key_net"], feats["query_net"]
+        self.attn = torch.empty((batch, agents, agents), dtype=torch.float32, device=dev)
+        self.coef = torch.empty((batch, agents, agents), dtype=torch.float32, device=dev)
+        gate = ops.GATE_MODES[inference]
+        keys, querys, attn, coef, aw, ab = self.keys, self.querys, self.attn, self.coef, self.att_w, self.att_b
+        self.add(lambda: ops.attn_scores(keys, querys, aw, ab, batch, agents, gate, attn=attn, coef=coef))
+        # ---- pass 1: softmax-weighted fuse -> decoder ----
+        c3 = x3.shape[-1]
+        fuse1 = self.act("fuse1", 32, 32, c3)
+        self.add(lambda: ops.warp_gated(x3, trans, na, attn, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i,
+                                        out=fuse1))
+        x8 = self.build_decoder(self.dec_w, x0, x1, x2, fuse1, x4u)
+        if not training_pass_only and inference != "softmax":
+            fuse2 = self.act("fuse2", 32, 32, c3)
+            self.add(lambda: ops.warp_gated(x3, trans, na, coef, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i,
+                                            out=fuse2))
+            x8 = self.build_decoder(self.dec_w, x8, x1, x2, fuse2, x4u, tag="p2_")
+        self.build_heads(self.head_w, x8)
+
+    def forward(self, bevs, trans_matrices, num_agent_tensor):
+        self.bev_in.copy_(bevs.reshape(self.bev_in.shape), non_blocking=True)
+        self.trans.copy_(trans_matrices.reshape(self.trans.shape), non_blocking=True)
+        self.num_agent.copy_(num_agent_tensor.reshape(self.num_agent.shape), non_blocking=True)
         self.run()
         return self.result()

@@ -201,7 +201,7 @@ class ConvLaunch:
         p.n_maps, p.h_out, p.w_out, p.stride, p.taps, p.planes = n, h_out, w_out, pc.stride, pc.taps, planes
         p.weights, p.bias = pc.weights.data_ptr(), pc.bias.data_ptr()
         p.cout, p.cout_pad = pc.cout, pc.cout_pad
-        m_tiles = n * (h_out // 8) * (w_out // 16)
+        m_tiles = n * (-(-h_out // 8)) * (-(-w_out // 16))
         if epilogue == EPI_GRU:
             p.block_n = 192
         else:
@@ -246,4 +246,51 @@ def warp_mean(x: torch.Tensor, trans: torch.Tensor, num_agent: torch.Tensor, bat
         out = torch.empty_like(x)
     check(lib.v2x_warp_mean_fwd(_ptr(x), _ptr(out), _ptr(trans), _ptr(num_agent), batch, agents, h, w, c, planes,
                                 int(include_self), int(only_v2i), _stream()), "v2x_warp_mean_fwd")
+    return out
+
+
+# ---- when2com / who2com ----------------------------------------------------------------------
+def linear(x, w, b, *, relu=False, out=None, act_input=False):
+    """fp32 linear layer through v2x_linear_fwd.  ``act_input``: x is an act [P, rows, H, W, C] flattened in
+    NCHW order (KmGenerator's ``view(-1, n_feat)``); otherwise x is fp32 [rows, in_f]."""
+    lib = require_gpu()
+    out_f, in_f = w.shape
+    if act_input:
+        planes, rows, h, wd, c = x.shape
+        assert h * wd * c == in_f
+        mode, hw = 1, h * wd
+    else:
+        rows, planes, hw, c, mode = x.shape[0], 1, 0, 0, 0
+        assert x.dtype == torch.float32 and x.shape[1] == in_f and x.is_contiguous()
+    if out is None:
+        out = torch.empty((rows, out_f), dtype=torch.float32, device=w.device)
+    check(lib.v2x_linear_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(out), rows, in_f, out_f, int(relu), mode, hw, c, planes,
+                             _stream()), "v2x_linear_fwd")
+    return out
+
+
+GATE_MODES = {"softmax": 0, "activated": 1, "argmax_test": 2}
+
+
+def attn_scores(keys, querys, w, bw, batch, agents, gate_mode, attn=None, coef=None):
+    lib = require_gpu()
+    dev = keys.device
+    if attn is None:
+        attn = torch.empty((batch, agents, agents), dtype=torch.float32, device=dev)
+    if coef is None:
+        coef = torch.empty((batch, agents, agents), dtype=torch.float32, device=dev)
+    check(lib.v2x_attn_scores_fwd(_ptr(keys), _ptr(querys), _ptr(w), _ptr(bw), _ptr(attn), _ptr(coef), batch, agents,
+                                  keys.shape[1], querys.shape[1], gate_mode, _stream()), "v2x_attn_scores_fwd")
+    return attn, coef
+
+
+def warp_gated(x, trans, num_agent, coef, batch, agents, *, warp_flag=1, only_v2i=False, out=None):
+    """when2com fuse: out[b,q] = sum_k coef[b,k,q] * val[b,k,q] without materialising val_mat."""
+    lib = require_gpu()
+    planes, n, h, w, c = x.shape
+    assert n == batch * agents and coef.dtype == torch.float32 and coef.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.v2x_warp_gated_fwd(_ptr(x), _ptr(out), _ptr(trans), _ptr(num_agent), _ptr(coef), batch, agents, h, w, c,
+                                 planes, int(warp_flag), int(only_v2i), _stream()), "v2x_warp_gated_fwd")
     return out
