@@ -15,8 +15,12 @@ step's inputs, 8 x 17 MB fp32, exceed the 126 MB L2 and nothing survives between
   roofline   the conv implicit-GEMM kernel family: algorithmic conv FLOPs / summed live per-launch time
   cpu_baseline  the oracle port (the reference's CPU algorithm) on this host, bounded sample
 
-Multi-GPU (N > 1): scenes are sharded across ranks (weak scaling, no data-path collective: a scene's
-agents stay on one rank); timing = max over ranks of the device time between barriers.
+Multi-GPU (N > 1), weak scaling, 8 scenes x 5 agents = 40 units per GPU, timing = max over ranks of the device
+time between barriers:
+  --shard unit  (default)  the 40*N agent-major units are split contiguously over the ranks, so a scene's agents live
+                on different GPUs; the only data-path collective is one NCCL all-gather of the layer-3 maps per
+                step, overlapped with the x_4 encoder branch (BASELINE configs[3])
+  --shard scene            every rank keeps whole scenes; no data-path collective at all
 """
 from __future__ import annotations
 
@@ -182,8 +186,17 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
 
     # ---------------- value: device-resident inputs, graph replay ----------------
-    plan = nets.V2VNetDetPlan(sd, B, AGENTS, gnn_iter=GNN_ITER, planes=planes, device=dev)
-    plan.set_inputs(bevs.to(dev), trans.to(dev), nat.to(dev))
+    unit_sharded = world > 1 and args.shard == "unit"
+    if unit_sharded:
+        from v2x_b200 import sharding
+        gb, gt, gn = synth.make_scene(B * world, AGENTS, seed=0)      # the global batch: B * world scenes
+        off, n_loc = sharding.unit_range(B * world * AGENTS, rank, world)
+        plan = nets.V2VNetDetShardedPlan(sd, B * world, AGENTS, rank, world, gnn_iter=GNN_ITER, planes=planes, device=dev)
+        plan.set_inputs(gb[off:off + n_loc].to(dev), gt.to(dev), gn.to(dev))
+        del gb
+    else:
+        plan = nets.V2VNetDetPlan(sd, B, AGENTS, gnn_iter=GNN_ITER, planes=planes, device=dev)
+        plan.set_inputs(bevs.to(dev), trans.to(dev), nat.to(dev))
     torch.cuda.synchronize()
     plan.capture()
     for _ in range(args.warmup):
@@ -316,7 +329,9 @@ def run_ours(args, rank, world, local_rank):
                        "scenes_per_gpu_per_step": B, "agents": AGENTS, "precision": args.precision,
                        "l2": "no flush: per-step inputs %.0f MB and activations ~%.1f GB exceed the 126 MB L2"
                              % (B * 17.04, 0.4 * B),
-                       "parallelism": "scene-sharded x%d, no data-path collective" % world},
+                       "parallelism": ("unit-sharded x%d (40 agent-major units per GPU), one NCCL all-gather of layer-3 "
+                                       "maps per step overlapped with the x_4 branch" % world) if unit_sharded
+                       else "scene-sharded x%d, no data-path collective" % world},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "api": "coperception.models.det.V2VNet.forward (pinned host in/out, 3-stream pipeline)"},
@@ -335,6 +350,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=8, help="scenes (frames) per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="unit", choices=["unit", "scene"], help="multi-GPU partition (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -86,8 +86,9 @@ typedef struct v2x_conv_params {
   const float* gru_bhn;      /* [cout/3] = b_hh_n                                              */
   const void* passthrough;   /* act, same geometry as the output; may be NULL                  */
   const int64_t* num_agent;  /* [batch][agents] (reference num_agent_tensor) or NULL           */
-  int32_t batch, agents;     /* agent-major maps: map = batch * agent + b                      */
-  int32_t reserved[4];
+  int32_t batch, agents;     /* agent-major maps: global unit = batch * agent + b              */
+  int32_t map_offset;        /* global unit index of this launch's map 0 (sharded plans), else 0 */
+  int32_t reserved[3];
 } v2x_conv_params;
 
 int v2x_conv_fwd(const v2x_conv_params* p, void* stream);
@@ -133,12 +134,14 @@ int v2x_pack_input(const float* x, void* out, int64_t n_pixels, int32_t c, int32
  * grid_sample semantics: bilinear, zeros padding, align_corners=False.
  * x, out: act [planes][A*B][H][W][C] agent-major; trans: [B][A][A][4][4] float64 (device);
  * num_agent: [B][A] int64 (device).  Targets i >= na[b] are written as zeros.
+ * unit_offset / unit_count select a slice of target units (agent-major index B*i + b) for unit-sharded multi-GPU
+ * plans: x is the complete (all-gathered) tensor, out holds unit_count maps; unit_count <= 0 means all.
  * Replaces DetModelBase.feature_transformation / build_neighbors_feature_list + torch.mean(torch.stack)
  * at CP/models/det/base/DetModelBase.py:139-209 and CP/models/det/V2VNet.py:85-98.
  */
 int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent, int32_t batch,
                       int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t include_self,
-                      int32_t only_v2i, void* stream);
+                      int32_t only_v2i, int32_t unit_offset, int32_t unit_count, void* stream);
 
 /* ---- when2com / who2com (CP/models/det/When2com.py) --------------------------------------- */
 

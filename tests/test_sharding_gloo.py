@@ -1,0 +1,70 @@
+"""CPU, world_size = 2 over gloo: the unit-sharding host logic of the multi-GPU path (v2x_b200/sharding.py).
+
+Each rank encodes only its slice of the agent-major units (oracle encoder as the compute stand-in), the ranks
+all-gather x_3 through the same ``all_gather_units`` the GPU plan uses, fuse + decode their own units, and the
+concatenation must equal the unsharded oracle forward: one exchange per forward is sufficient."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    for p in (ROOT, os.path.join(ROOT, "v2x-sim_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import restate, synth
+        from v2x_b200 import sharding
+        torch.set_num_threads(2)
+        B, A = 2, 2                      # 4 units, 2 per rank: rank 0 = agent 0 of both scenes, rank 1 = agent 1
+        sd = synth.v2vnet_det_state(5)
+        bevs, trans, nat = synth.make_scene(B, A, seed=5)
+        off, n = sharding.unit_range(B * A, rank, world)
+        with torch.no_grad():
+            enc = restate.encode(bevs[off:off + n], sd, "u_encoder.")
+            x3_all, _ = sharding.all_gather_units(enc[3])
+            fused_all = restate.v2vnet_fuse(x3_all, trans, nat, sd, B, agent_num=A, gnn_iter=2)
+            dec_in = list(enc)
+            dec_in[3] = fused_all[off:off + n]
+            out = restate.heads(restate.decode(*dec_in, sd, "decoder.")[0], sd)
+            full = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=B, agent_num=A, gnn_iter=2)
+        err = max((out[k] - full[k][off:off + n]).abs().max().item() for k in ("loc", "cls"))
+        # act-plane tensors take the per-plane path of all_gather_units
+        planes = torch.full((2, n, 2, 2, 8), float(rank), dtype=torch.bfloat16)
+        g, _ = sharding.all_gather_units(planes)
+        ok_planes = g.shape == (2, n * world, 2, 2, 8) and bool((g[:, :n] == 0).all()) and bool((g[:, n:] == 1).all())
+        ret[rank] = (err, ok_planes)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unit_range():
+    from v2x_b200 import sharding
+    assert sharding.unit_range(40, 3, 4) == (30, 10)
+    with pytest.raises(ValueError):
+        sharding.unit_range(5, 0, 4)     # one 5-agent scene cannot be split over 4 ranks
+
+
+def test_two_rank_sharded_forward_matches_unsharded():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    for r in range(2):
+        err, ok_planes = ret[r]
+        assert err < 1e-4, (r, err)
+        assert ok_planes

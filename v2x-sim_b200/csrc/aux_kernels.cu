@@ -105,16 +105,18 @@ __global__ void pack_gru_bias_kernel(const float* __restrict__ b_ih, const float
 template <int VEC_PER_LANE>
 __global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                  const double* __restrict__ trans, const long long* __restrict__ num_agent, int batch,
-                                 int agents, int H, int W, int C, int planes, int include_self, int only_v2i) {
+                                 int agents, int H, int W, int C, int planes, int include_self, int only_v2i,
+                                 int unit_offset, int unit_count) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long total_pix = (long long)batch * agents * H * W;
-  const long long plane_stride = total_pix * C;
+  const long long total_pix = (long long)unit_count * H * W;                 // targets computed by this launch
+  const long long plane_stride = (long long)batch * agents * H * W * C;      // of the (complete) source tensor
+  const long long out_plane_stride = total_pix * C;
   for (long long wid = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total_pix;
        wid += (long long)gridDim.x * warps_per_block) {
     const int ow = (int)(wid % W);
     const int oh = (int)((wid / W) % H);
-    const int map = (int)(wid / ((long long)W * H));  // agent-major: map = batch * i + b
+    const int map = (int)(wid / ((long long)W * H)) + unit_offset;  // agent-major: map = batch * i + b
     const int i = map / batch, b = map % batch;
     const int na = (int)num_agent[(long long)b * agents];
     float acc[VEC_PER_LANE][8];
@@ -190,7 +192,7 @@ __global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
           lo[e] = pack_bf16x2(l0, l1);
         }
         *reinterpret_cast<uint4*>(dp + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (planes == 2) *reinterpret_cast<uint4*>(dp + plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (planes == 2) *reinterpret_cast<uint4*>(dp + out_plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
   }
@@ -271,12 +273,15 @@ extern "C" int v2x_pack_gru_bias(const float* b_ih, const float* b_hh, int32_t c
 
 extern "C" int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent,
                                  int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes,
-                                 int32_t include_self, int32_t only_v2i, void* stream) {
+                                 int32_t include_self, int32_t only_v2i, int32_t unit_offset, int32_t unit_count,
+                                 void* stream) {
   V2X_REQUIRE(x && out && trans && num_agent, "null pointer");
   V2X_REQUIRE(batch > 0 && agents > 0 && h > 0 && w > 0, "empty geometry");
   V2X_REQUIRE(c > 0 && c % 8 == 0 && c <= 1024, "channels must be a multiple of 8, <= 1024");
   V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
-  const long long total_pix = (long long)batch * agents * h * w;
+  if (unit_count <= 0) { unit_offset = 0; unit_count = batch * agents; }
+  V2X_REQUIRE(unit_offset >= 0 && unit_offset + unit_count <= batch * agents, "unit range out of bounds");
+  const long long total_pix = (long long)unit_count * h * w;
   const int threads = 256;
   const unsigned grid = grid_for(total_pix * 32, threads, 8);
   const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -284,11 +289,11 @@ extern "C" int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, 
   const long long* na = reinterpret_cast<const long long*>(num_agent);
   cudaStream_t s = (cudaStream_t)stream;
   if (c <= 256)
-    warp_mean_kernel<1><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i);
+    warp_mean_kernel<1><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i, unit_offset, unit_count);
   else if (c <= 512)
-    warp_mean_kernel<2><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i);
+    warp_mean_kernel<2><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i, unit_offset, unit_count);
   else
-    warp_mean_kernel<4><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i);
+    warp_mean_kernel<4><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i, unit_offset, unit_count);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }

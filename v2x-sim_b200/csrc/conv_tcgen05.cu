@@ -61,7 +61,7 @@ struct ConvDev {
   const float* gru_bhn;
   const void* passthrough;
   const long long* num_agent;
-  int batch, agents;
+  int batch, agents, map_offset;
   uint32_t a_tile_bytes, b_tile_bytes, stage_bytes, tx_bytes, sbo, layout_type;
   long long out_plane_stride;  // elements between output planes
   // reference (CUDA-core) kernel only
@@ -162,7 +162,8 @@ __device__ __forceinline__ void copy_passthrough(const ConvDev& p, int n_img, in
 
 __device__ __forceinline__ bool gru_unit_absent(const ConvDev& p, int n_img) {
   if (p.epilogue != V2X_EPI_GRU || p.num_agent == nullptr) return false;
-  const int agent = n_img / p.batch, b = n_img % p.batch;
+  const int unit = n_img + p.map_offset;  // global agent-major unit (sharded plans hold a slice of the maps)
+  const int agent = unit / p.batch, b = unit % p.batch;
   return agent >= (int)p.num_agent[(long long)b * p.agents];
 }
 
@@ -761,7 +762,7 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
   d.out_c_total = p->out_c_total; d.out_c_off = p->out_c_off; d.split = p->split;
   d.bias = p->bias; d.gru_bhn = p->gru_bhn; d.passthrough = p->passthrough;
   d.num_agent = reinterpret_cast<const long long*>(p->num_agent);
-  d.batch = p->batch; d.agents = p->agents;
+  d.batch = p->batch; d.agents = p->agents; d.map_offset = p->map_offset;
   d.debug_mode = g_debug_mode;
   d.a_tile_bytes = 128u * kc * 2u;
   d.b_tile_bytes = ((uint32_t)bn * kc * 2u + 1023u) & ~1023u;
@@ -789,8 +790,9 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
       V2X_REQUIRE(!p->upsample2x, "upsample2x only with EPI_ACT");
       V2X_REQUIRE(p->out_c_total >= p->out_c_off + p->cout / 3 && p->out_c_total % 8 == 0 && p->out_c_off % 8 == 0,
                   "bad output channel window");
-      V2X_REQUIRE(p->num_agent == nullptr || (p->batch > 0 && p->agents > 0 && p->batch * p->agents == p->n_maps),
-                  "num_agent needs batch * agents == n_maps");
+      V2X_REQUIRE(p->num_agent == nullptr ||
+                      (p->batch > 0 && p->agents > 0 && p->map_offset >= 0 && p->map_offset + p->n_maps <= p->batch * p->agents),
+                  "num_agent needs map_offset + n_maps <= batch * agents");
       d.out_plane_stride = (long long)p->n_maps * p->h_out * p->w_out * p->out_c_total;
       break;
     default:

@@ -43,7 +43,8 @@ class ConvParams(C.Structure):
         ("num_agent", C.c_void_p),
         ("batch", C.c_int32),
         ("agents", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("map_offset", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -61,7 +62,7 @@ SYMBOLS = [
       _I32, _I32, _P]),
     ("v2x_pack_gru_bias", C.c_int, [_P, _P, _I32, _P, _P, _P]),
     ("v2x_pack_input", C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
-    ("v2x_warp_mean_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_warp_mean_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_act_to_nchw_f32", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_linear_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_attn_scores_fwd", C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),

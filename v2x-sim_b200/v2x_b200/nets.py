@@ -305,3 +305,108 @@ class When2comDetPlan(DetPlan):
         self.num_agent.copy_(num_agent_tensor.reshape(self.num_agent.shape), non_blocking=True)
         self.run()
         return self.result()
+
+
+class V2VNetDetShardedPlan(DetPlan):
+    """det V2VNet forward, unit-sharded across ``world`` ranks (one process per GPU).
+
+    This rank runs encoder / GRU / decoder / heads for its slice of the agent-major units and exchanges only the
+    layer-3 maps: one NCCL all-gather of x_3, issued asynchronously right after conv3_2 so that conv4_1 / conv4_2
+    overlap it.  The forward is three CUDA graphs (-> x_3 | x_4 branch | fuse + decoder + heads) around the collective."""
+
+    def __init__(self, sd, batch_total: int, agents: int, rank: int, world: int, gnn_iter: int = 3, planes: int = 1,
+                 device="cuda", group=None, only_v2i=False):
+        from . import sharding
+        self.offset, n_loc = sharding.unit_range(batch_total * agents, rank, world)
+        super().__init__(n_loc, planes, device)
+        ops.require_gpu()
+        self.sharding, self.group, self.world = sharding, group, world
+        self.batch, self.agents, self.gnn_iter = batch_total, agents, gnn_iter
+        dev = self.device
+        self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
+        self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
+        self.head_w = HeadWeights(sd, planes, dev)
+        self.gru_w = ops.pack_gru(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"], sd["convgru.bias_hh_l0"],
+                                  planes=planes, device=dev)
+        self.trans = torch.zeros((batch_total, agents, agents, 4, 4), dtype=torch.float64, device=dev)
+        self.num_agent = torch.full((batch_total, agents), agents, dtype=torch.int64, device=dev)
+        trans, na, off = self.trans, self.num_agent, self.offset
+
+        x_in = self.build_input()
+        c = self.enc_w.c
+        t = self.conv(c["conv_pre_1"], [x_in], "x0a")
+        x0 = self.conv(c["conv_pre_2"], [t], "x0")
+        t = self.conv(c["conv1_1"], [x0], "x1a")
+        t = self.conv(c["conv1_2"], [t], "x1b")
+        x1 = self.conv(c["conv3d_1"], [t], "x1")
+        t = self.conv(c["conv2_1"], [x1], "x2a")
+        t = self.conv(c["conv2_2"], [t], "x2b")
+        x2 = self.conv(c["conv3d_2"], [t], "x2")
+        t = self.conv(c["conv3_1"], [x2], "x3a")
+        x3 = self.conv(c["conv3_2"], [t], "x3")
+        self.stage_a = len(self.launches)            # ---- x_3 ready: the all-gather starts here
+        t = self.conv(c["conv4_1"], [x3], "x4a")
+        x4u = self.conv(c["conv4_2"], [t], "x4u", upsample2x=True)
+        self.stage_b = len(self.launches)            # ---- x_4 branch done: wait for the gather
+        c3 = x3.shape[-1]
+        self.x3_local = x3
+        self.x3_all = ops.empty_act(planes, n_loc * world, 32, 32, c3, dev)
+        x3_all = self.x3_all
+        mean = self.act("mean", 32, 32, c3)
+        self.add(lambda: ops.warp_mean(x3_all, trans, na, batch_total, agents, include_self=False, only_v2i=only_v2i,
+                                       out=mean, unit_offset=off, unit_count=n_loc))
+        h = x3
+        for r in range(gnn_iter):
+            out = self.act("h%d" % (r + 1), 32, 32, c3)
+            self.add(ConvLaunch(self.gru_w, [h, mean], epilogue=EPI_GRU, out0=out, passthrough=x3, num_agent=na,
+                                batch=batch_total, agents=agents, map_offset=off))
+            h = out
+        x8 = self.build_decoder(self.dec_w, x0, x1, x2, h, x4u)
+        self.build_heads(self.head_w, x8)
+        self.graphs = None
+
+    def _segments(self):
+        return (self.launches[:self.stage_a], self.launches[self.stage_a:self.stage_b], self.launches[self.stage_b:])
+
+    def run(self):
+        seg = self._segments()
+        for i in range(3):
+            if i == 1:   # x_3 is final: exchange it while the x_4 branch runs
+                _, works = self.sharding.all_gather_units(self.x3_local, out=self.x3_all, group=self.group, async_op=True)
+            if i == 2:
+                for w in works:
+                    w.wait()   # stream-level wait: the fuse kernels queue behind the collective
+            if self.graphs is not None:
+                self.graphs[i].replay()
+            else:
+                for l in seg[i]:
+                    l()
+
+    def capture(self):
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                for l in self.launches:
+                    l()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graphs = []
+        for seg in self._segments():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for l in seg:
+                    l()
+            graphs.append(g)
+        self.graphs = graphs
+
+    def set_inputs(self, bevs_local, trans_matrices, num_agent_tensor):
+        """bevs_local: this rank's unit slice [n_loc,1,256,256,13]; poses / agent counts of ALL scenes."""
+        self.bev_in.copy_(bevs_local.reshape(self.bev_in.shape), non_blocking=True)
+        self.trans.copy_(trans_matrices.reshape(self.trans.shape), non_blocking=True)
+        self.num_agent.copy_(num_agent_tensor.reshape(self.num_agent.shape), non_blocking=True)
+
+    def forward(self, bevs_local, trans_matrices, num_agent_tensor):
+        self.set_inputs(bevs_local, trans_matrices, num_agent_tensor)
+        self.run()
+        return self.result()

@@ -186,7 +186,7 @@ class ConvLaunch:
 
     def __init__(self, pc: PackedConv, srcs: Sequence[torch.Tensor], *, epilogue=EPI_ACT, relu=True, upsample2x=False,
                  out0: torch.Tensor = None, out1: torch.Tensor = None, out_c_off=0, split=0, block_n=None,
-                 passthrough=None, num_agent=None, batch=0, agents=0, crosscheck=False):
+                 passthrough=None, num_agent=None, batch=0, agents=0, map_offset=0, crosscheck=False):
         self.lib = require_gpu()
         planes, n, h_in, w_in, _ = srcs[0].shape
         assert planes == pc.planes
@@ -214,7 +214,7 @@ class ConvLaunch:
         p.gru_bhn = pc.gru_bhn.data_ptr() if pc.gru_bhn is not None else None
         p.passthrough = passthrough.data_ptr() if passthrough is not None else None
         p.num_agent = num_agent.data_ptr() if num_agent is not None else None
-        p.batch, p.agents = batch, agents
+        p.batch, p.agents, p.map_offset = batch, agents, map_offset
         self.p = p
         self.keep = (pc, list(srcs), out0, out1, passthrough, num_agent)
         self.fn = self.lib.v2x_conv_fwd_crosscheck if crosscheck else self.lib.v2x_conv_fwd
@@ -235,17 +235,18 @@ def conv(pc: PackedConv, srcs, *, relu=True, upsample2x=False, out=None, block_n
 
 
 def warp_mean(x: torch.Tensor, trans: torch.Tensor, num_agent: torch.Tensor, batch: int, agents: int, *,
-              include_self=False, only_v2i=False, out=None) -> torch.Tensor:
-    """Cross-agent bilinear warp + neighbour mean of agent-major maps ``x`` [P, A*B, H, W, C]."""
+              include_self=False, only_v2i=False, out=None, unit_offset=0, unit_count=0) -> torch.Tensor:
+    """Cross-agent bilinear warp + neighbour mean of agent-major maps ``x`` [P, A*B, H, W, C].
+    ``unit_offset/unit_count`` restrict the computed targets to a slice of units (unit-sharded plans)."""
     lib = require_gpu()
     planes, n, h, w, c = x.shape
     assert n == batch * agents
     assert trans.dtype == torch.float64 and trans.is_cuda and trans.is_contiguous()
     assert num_agent.dtype == torch.int64 and num_agent.is_cuda and num_agent.is_contiguous()
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty_like(x) if unit_count <= 0 else empty_act(planes, unit_count, h, w, c, x.device)
     check(lib.v2x_warp_mean_fwd(_ptr(x), _ptr(out), _ptr(trans), _ptr(num_agent), batch, agents, h, w, c, planes,
-                                int(include_self), int(only_v2i), _stream()), "v2x_warp_mean_fwd")
+                                int(include_self), int(only_v2i), unit_offset, unit_count, _stream()), "v2x_warp_mean_fwd")
     return out
 
 
