@@ -149,7 +149,7 @@ def run_reference(args, rank, world):
                              "sample": "%d timed forwards of 1 scene (5 agents), median; torch CPU fp32, best of "
                                        "{8,16,32,64,all} threads = %d" % (steps, threads)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def time_launch_list(launches, reps=20):
@@ -338,10 +338,24 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": plan.n_kernels * args.steps,
             "kernels_per_step": plan.n_kernels,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The driver reads ONE JSON line from stdout; libraries (NCCL banners, the reference's prints) are kept off it
+    by pointing fd 1 at stderr for the life of the process and writing the result to the saved descriptor."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

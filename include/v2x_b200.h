@@ -43,6 +43,7 @@ int v2x_device_ok(void);
 /* ---- epilogue modes of v2x_conv_fwd -------------------------------------------------- */
 #define V2X_EPI_ACT 0      /* y = [relu](acc + bias) -> act (bf16 planes), optional 2x nearest upsample on store */
 #define V2X_EPI_F32_SPLIT 1 /* y = acc + bias -> fp32 NHWC, channels [0,split) to out0, [split,cout) to out1     */
+#define V2X_EPI_F32_NCHW 3  /* y = acc + bias -> fp32 NCHW [N][cout][H][W] in out0 (segmentation logits)                       */
 #define V2X_EPI_GRU 2      /* zero-hidden ConvGRU gate epilogue, see v2x_conv_params                           */
 
 /*
@@ -149,9 +150,12 @@ int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, const int64
  * Small fp32 linear layer y = [relu](x W^T + b), rows x in_f -> rows x out_f (KmGenerator MLP, When2com.py:415-430).
  * in_mode 0: x is fp32 [rows][in_f].  in_mode 1: x is an act [planes][rows][hw][c] read in NCHW-flatten order
  * (i = ch * hw + px), the order `features_map.view(-1, n_feat)` produces (When2com.py:429).
+ * split > 1: the maps are viewed as `maps * split` rows of in_f = hw * c / split values (the seg model's
+ * `.view(-1, 4096)` over 16384-wide features, When2Com_UNet.py:207-226 -- SURVEY Q9); `rows` of them are computed.
  */
 int v2x_linear_fwd(const void* x, const float* w, const float* b, float* y, int32_t rows, int32_t in_f, int32_t out_f,
-                   int32_t relu, int32_t in_mode, int32_t hw, int32_t c, int32_t planes, void* stream);
+                   int32_t relu, int32_t in_mode, int32_t hw, int32_t c, int32_t planes, int32_t split, int32_t maps,
+                   void* stream);
 
 /*
  * Attention scores of MIMOGeneralDotProductAttention.forward (When2com.py:374-412) and the eval-time gate:
@@ -174,6 +178,17 @@ int v2x_attn_scores_fwd(const float* keys, const float* querys, const float* w, 
 int v2x_warp_gated_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent, const float* coef,
                        int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes,
                        int32_t warp_flag, int32_t only_v2i, void* stream);
+
+/* ---- segmentation UNet pieces (CP/models/seg/SegModelBase.py) ------------------------------ */
+/* fp32 NCHW [n][c][h][w] (what SegModule.py:49 hands the model) -> act bf16 planes NHWC, channels zero-padded to c_pad */
+int v2x_pack_input_nchw(const float* x, void* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pad,
+                        int32_t planes, void* stream);
+/* nn.MaxPool2d(2) (SegModelBase.py:113): act [n][2*h_out][2*w_out][c] -> [n][h_out][w_out][c] */
+int v2x_maxpool2_fwd(const void* x, void* out, int32_t n, int32_t h_out, int32_t w_out, int32_t c, int32_t planes,
+                     void* stream);
+/* nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) (SegModelBase.py:125): act [n][h][w][c] -> [n][2h][2w][c] */
+int v2x_upsample_bilinear2_fwd(const void* x, void* out, int32_t n, int32_t h_in, int32_t w_in, int32_t c,
+                               int32_t planes, void* stream);
 
 /* act (bf16 planes, NHWC) -> fp32 NCHW, for returning intermediate maps to torch callers */
 int v2x_act_to_nchw_f32(const void* act, float* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t planes,

@@ -78,6 +78,39 @@ def gen_when2com(tag, batch, seed, warp_flag, inference, present=None):
     print(tag, "loc.sum", out["loc.sum"], "cls.sum", out["cls.sum"])
 
 
+def gen_seg(tag, kind, batch, seed, present=None, inference="activated", warp_flag=1):
+    """kind in {"unet", "v2vnet", "when2com"}; logits [N,8,256,256] of the live seg models."""
+    import contextlib
+    import io
+    a = 5
+    x, trans, nat = synth.make_seg_scene(batch, a, seed, present=present)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if kind == "unet":
+            m, sd = ref_loader.ref_seg_unet(), synth.seg_unet_state(seed)
+        elif kind == "v2vnet":
+            m, sd = ref_loader.ref_seg_v2vnet(num_agent=a), synth.seg_v2vnet_state(seed)
+        else:
+            m, sd = ref_loader.ref_seg_when2com(num_agent=a, warp_flag=warp_flag), synth.seg_when2com_state(seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    with torch.no_grad(), ref_loader.cpu_cuda_shim(), contextlib.redirect_stdout(io.StringIO()):
+        if kind == "unet":
+            r = m(x)
+        elif kind == "v2vnet":
+            r = m(x, trans, nat)
+        else:
+            r = m(x, trans, nat, inference=inference, training=False)
+    out = {"meta": np.asarray([batch, a, seed, warp_flag], dtype=np.int64), "inference": np.asarray(inference),
+           "kind": np.asarray(kind)}
+    if present is not None:
+        out["present"] = np.asarray(present, dtype=np.int64)
+    summarize("logits", r, out)
+    am = r.argmax(1).to(torch.int64)
+    out["logits.argmax_hist"] = np.stack([(am == c).sum((1, 2)).numpy() for c in range(r.shape[1])], 1)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+    print(tag, "logits.sum", out["logits.sum"])
+
+
 def gen_fafnet(tag, n, seed):
     m = ref_loader.ref_fafnet(kd_flag=0)
     sd = synth.fafnet_state(seed)
@@ -166,6 +199,10 @@ def main():
     gen_when2com("when2com_det_warp_activated_seed2", 1, 2, 1, "activated")
     gen_when2com("when2com_det_nowarp_argmax_seed3_present4", 1, 3, 0, "argmax_test", present=[4])
     gen_when2com("when2com_det_warp_softmax_B2_seed4", 2, 4, 1, "softmax", present=[3, 5])
+    gen_seg("seg_unet_seed0", "unet", 1, 0)
+    gen_seg("seg_v2vnet_seed1_present4", "v2vnet", 1, 1, present=[4])
+    gen_seg("seg_when2com_warp_activated_seed2", "when2com", 1, 2, inference="activated", warp_flag=1)
+    gen_seg("seg_when2com_nowarp_activated_seed3", "when2com", 1, 3, inference="activated", warp_flag=0, present=[3])  # argmax_test needs torch.cuda.FloatTensor (When2Com_UNet.py:93): not runnable on the CPU reference
     return 0
 
 

@@ -81,3 +81,41 @@ def ref_when2com_det(warp_flag=1, num_agent=5):
     install()
     When2com = importlib.import_module("coperception.models.det.When2com").When2com
     return When2com(ref_config(), layer=3, warp_flag=warp_flag, num_agent=num_agent)
+
+
+def _seg_config():
+    cfg = ref_config()
+    return cfg
+
+
+def ref_seg_unet(n_classes=8):
+    install()
+    UNet = importlib.import_module("coperception.models.seg.UNet").UNet
+    return UNet(13, n_classes)
+
+
+def ref_seg_v2vnet(n_classes=8, num_agent=5):
+    install()
+    V2VNet = importlib.import_module("coperception.models.seg.V2VNet").V2VNet
+    return V2VNet(13, n_classes, num_agent=num_agent)
+
+
+def ref_seg_when2com(n_classes=8, num_agent=5, warp_flag=1):
+    install()
+    W = importlib.import_module("coperception.models.seg.When2Com_UNet").When2Com_UNet
+    return W(_seg_config(), in_channels=13, n_classes=n_classes, warp_flag=warp_flag, num_agent=num_agent)
+
+
+class cpu_cuda_shim:
+    """Shim 3: neutralise the hard-coded ``.cuda()`` of seg When2Com_UNet (When2Com_UNet.py:245) for CPU runs."""
+
+    def __enter__(self):
+        import torch
+        self._t = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.cuda = self._t
+        return False

@@ -255,3 +255,133 @@ def when2com_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=
     if stages:
         res = dict(res, enc=enc, qk=qk, keys=keys, querys=querys, attn=attn, fuse1=fuse1, fuse2=fuse2, x8=x_dec)
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# Segmentation models (CP/models/seg/)
+# ---------------------------------------------------------------------------------------------
+def double_conv(x, sd, p):
+    """DoubleConv (SegModelBase.py:91-106): (conv3x3 + BN + ReLU) x 2; keys p+{0,1,3,4}."""
+    x = F.relu(_bn(F.conv2d(x, sd[p + "0.weight"], sd[p + "0.bias"], padding=1), sd, p + "1"))
+    return F.relu(_bn(F.conv2d(x, sd[p + "3.weight"], sd[p + "3.bias"], padding=1), sd, p + "4"))
+
+
+def seg_down(x, sd, p):
+    """Down (SegModelBase.py:109-118): MaxPool2d(2) + DoubleConv."""
+    return double_conv(F.max_pool2d(x, 2), sd, p + "maxpool_conv.1.double_conv.")
+
+
+def seg_up(x1, x2, sd, p):
+    """Up (SegModelBase.py:121-142): bilinear x2 (align_corners=True), cat([skip, up]), DoubleConv."""
+    x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
+    return double_conv(torch.cat([x2, x1], dim=1), sd, p + "conv.double_conv.")
+
+
+def seg_encode(x, sd, p=""):
+    x1 = double_conv(x, sd, p + "inc.double_conv.")
+    x2 = seg_down(x1, sd, p + "down1.")
+    x3 = seg_down(x2, sd, p + "down2.")
+    x4 = seg_down(x3, sd, p + "down3.")
+    return x1, x2, x3, x4
+
+
+def seg_decode(feat, x1, x2, x3, sd):
+    """down4 / up1..4 / outc on the (fused) layer-4 map (UNet.py:34-40, seg/V2VNet.py:85-91)."""
+    x5 = seg_down(feat, sd, "down4.")
+    x = seg_up(x5, feat, sd, "up1.")
+    x = seg_up(x, x3, sd, "up2.")
+    x = seg_up(x, x2, sd, "up3.")
+    x = seg_up(x, x1, sd, "up4.")
+    return F.conv2d(x, sd["outc.conv.weight"], sd["outc.conv.bias"])
+
+
+def seg_unet_forward(x, sd):
+    """seg UNet.forward (CP/models/seg/UNet.py:24-44), kd_flag=False."""
+    x1, x2, x3, x4 = seg_encode(x, sd)
+    return seg_decode(x4, x1, x2, x3, sd)
+
+
+def seg_v2vnet_forward(x, trans_matrices, num_agent_tensor, sd, agent_num=5, only_v2i=False, stages=False):
+    """seg V2VNet.forward (CP/models/seg/V2VNet.py:25-92): one GNN round, neighbour mean INCLUDES self (:55-56,74)."""
+    x1, x2, x3, x4 = seg_encode(x, sd)
+    c, h, w = x4.shape[1:]
+    size = (1, c, h, w)
+    batch_size = x.size(0) // agent_num
+    feat = torch.flip(x4, (2,))
+    local = torch.stack([feat[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)
+    upd = local.clone()
+    for b in range(batch_size):
+        na = int(num_agent_tensor[b, 0])
+        new = []
+        for i in range(na):
+            nb = [local[b, i]]
+            for j in range(na):
+                if j != i:
+                    if only_v2i and i != 0 and j != 0:
+                        continue
+                    nb.append(feature_transformation(local, b, j, i, trans_matrices, size))
+            mean = torch.mean(torch.stack(nb), dim=0)
+            cat = torch.cat([local[b, i], mean], 0).unsqueeze(0)
+            new.append(convgru_zero_hidden(cat, sd).squeeze(0))
+        for k in range(na):
+            upd[b, k] = new[k]
+    fused = torch.flip(torch.cat([upd[:, i] for i in range(agent_num)], 0), (2,))
+    logits = seg_decode(fused, x1, x2, x3, sd)
+    return dict(logits=logits, x4=x4, fused=fused) if stages else logits
+
+
+def seg_policy_net4(x, sd, p="query_key_net."):
+    """seg PolicyNet4.forward (When2Com_UNet.py:331-339): own inc/down1..3, then five conv+BN+ReLU -> [N,256,8,8]."""
+    t = seg_encode(x, sd, p)[3]
+    for name, stride in (("conv1", 1), ("conv2", 1), ("conv3", 2), ("conv4", 1), ("conv5", 2)):
+        t = cbr(t, sd, p + name + ".", "cbr_unit.0", "cbr_unit.1", stride=stride)
+    return t
+
+
+def seg_when2com_forward(x, trans_matrices, num_agent_tensor, sd, agent_num=5, warp_flag=1, inference="activated",
+                         training=False, only_v2i=False, stages=False):
+    """seg When2Com_UNet.forward (When2Com_UNet.py:144-307).  Reproduces the key/query row quirk: PolicyNet4 emits
+    256*8*8 = 16384 features per map but KmGenerator views them as rows of 4096 (:381-392), and rows 0..A*B-1 of the
+    resulting [4*A*B, .] matrices are taken as the agents' keys / queries (:207-226)."""
+    x1, x2, x3, x4 = seg_encode(x, sd)
+    c, h, w = x4.shape[1:]
+    size = (1, c, h, w)
+    batch_size = x.size(0) // agent_num
+    feat = torch.flip(x4, (2,))
+    local = torch.stack([feat[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)
+    if warp_flag == 1:
+        val_mat = torch.zeros(batch_size, agent_num, agent_num, c, h, w)
+        for b in range(batch_size):
+            na = int(num_agent_tensor[b, 0])
+            for i in range(na):
+                for j in range(na):
+                    if j == i:
+                        val_mat[b, i, j] = local[b, i]
+                    else:
+                        if only_v2i and i != 0 and j != 0:
+                            continue
+                        val_mat[b, i, j] = feature_transformation(local, b, j, i, trans_matrices, size)
+    else:
+        val_mat = local
+    qk = seg_policy_net4(x, sd)
+    keys = km_generator(qk, sd, "key_net.")      # [4*A*B, 1024]
+    querys = km_generator(qk, sd, "query_net.")  # [4*A*B, 32]
+    key_mat = torch.stack([keys[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)
+    query_mat = torch.stack([querys[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)
+    query = F.linear(query_mat, sd["attention_net.linear.weight"], sd["attention_net.linear.bias"])
+    attn = torch.softmax(torch.bmm(key_mat, query.transpose(2, 1)), dim=1)
+    prob = attn + torch.eye(agent_num).view(1, agent_num, agent_num) * 0.001
+    if training or inference == "softmax":
+        coef = attn
+    elif inference == "activated":
+        coef = prob * (prob > 0.2).float()
+    elif inference == "argmax_test":
+        coef = F.one_hot(prob.max(dim=1)[1], num_classes=agent_num).float().transpose(1, 2)
+    else:
+        raise ValueError("Incorrect inference mode")
+    ce = coef.view(batch_size, agent_num, agent_num, 1, 1, 1)
+    v = val_mat if warp_flag == 1 else val_mat.unsqueeze(2).expand(-1, -1, agent_num, -1, -1, -1)
+    fuse = (ce * v).sum(1)
+    fused = torch.flip(torch.cat([fuse[:, i] for i in range(agent_num)], 0), (2,))
+    logits = seg_decode(fused, x1, x2, x3, sd)
+    return dict(logits=logits, attn=attn, fused=fused, x4=x4) if stages else logits

@@ -94,3 +94,22 @@ def test_when2com_det(golden_dir, tag):
                                          inference=inference)
     _check("loc", r["loc"], g)
     _check("cls", r["cls"], g)
+
+
+@pytest.mark.parametrize("tag,kind", [("seg_unet_seed0", "unet"), ("seg_v2vnet_seed1_present4", "v2vnet"),
+                                      ("seg_when2com_warp_activated_seed2", "when2com"),
+                                      ("seg_when2com_nowarp_activated_seed3", "when2com")])
+def test_seg_models(golden_dir, tag, kind):
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    batch, a, seed, warp = [int(v) for v in g["meta"]]
+    present = [int(v) for v in g["present"]] if "present" in g.files else None
+    x, trans, nat = synth.make_seg_scene(batch, a, seed, present=present)
+    with torch.no_grad():
+        if kind == "unet":
+            r = restate.seg_unet_forward(x, synth.seg_unet_state(seed))
+        elif kind == "v2vnet":
+            r = restate.seg_v2vnet_forward(x, trans, nat, synth.seg_v2vnet_state(seed), agent_num=a)
+        else:
+            r = restate.seg_when2com_forward(x, trans, nat, synth.seg_when2com_state(seed), agent_num=a, warp_flag=warp,
+                                             inference=str(g["inference"]))
+    _check("logits", r, g)

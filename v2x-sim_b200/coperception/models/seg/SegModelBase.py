@@ -1,0 +1,87 @@
+"""Parameter schema + host logic of the segmentation models (reference: CP/models/seg/SegModelBase.py:6-151).
+
+The nn.Modules below only hold parameters / BN buffers under the reference's names (inc.double_conv.{0,1,3,4},
+down*.maxpool_conv.1.double_conv.*, up*.conv.double_conv.*, outc.conv) so reference checkpoints load strictly; the
+arithmetic runs in libv2x_b200.so."""
+import os
+
+import torch
+import torch.nn as nn
+
+_PLANES = {"bf16": 1, "bf16x3": 2}
+
+
+class DoubleConv(nn.Module):
+    def __init__(self, in_channels, out_channels, mid_channels=None):
+        super().__init__()
+        mid_channels = mid_channels or out_channels
+        self.double_conv = nn.Sequential(
+            nn.Conv2d(in_channels, mid_channels, kernel_size=3, padding=1), nn.BatchNorm2d(mid_channels), nn.ReLU(inplace=True),
+            nn.Conv2d(mid_channels, out_channels, kernel_size=3, padding=1), nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True))
+
+
+class Down(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConv(in_channels, out_channels))
+
+
+class Up(nn.Module):
+    def __init__(self, in_channels, out_channels, bilinear=True):
+        super().__init__()
+        self.conv = DoubleConv(in_channels, out_channels, in_channels // 2)
+
+
+class OutConv(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+
+
+class SegModelBase(nn.Module):
+    def __init__(self, n_channels, n_classes, bilinear=True, num_agent=5, compress_level=0, only_v2i=False):
+        super().__init__()
+        if not bilinear or compress_level != 0:
+            raise NotImplementedError("v2x_b200 seg models implement the reference defaults (bilinear up, no compression)")
+        self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bilinear
+        self.num_agent, self.only_v2i, self.compress_level = num_agent, only_v2i, compress_level
+        self.inc = DoubleConv(n_channels, 64)
+        self.down1, self.down2, self.down3, self.down4 = Down(64, 128), Down(128, 256), Down(256, 512), Down(512, 512)
+        self.up1, self.up2, self.up3, self.up4 = Up(1024, 256), Up(512, 128), Up(256, 64), Up(128, 64)
+        self.outc = OutConv(64, n_classes)
+        self.precision = os.environ.get("V2X_PRECISION", "bf16")
+        self.use_cuda_graph = os.environ.get("V2X_CUDA_GRAPH", "1") != "0"
+        self._plans = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self):
+        self._plans = {}
+
+    def train(self, mode=True):
+        self.invalidate()
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def _planes(self):
+        return _PLANES[self.precision]
+
+    def _check(self, x):
+        if self.training:
+            raise NotImplementedError("the sm_100a path implements inference (model.eval()); training is not built yet")
+        if x.device.type != "cuda":
+            raise RuntimeError("v2x_b200 seg models need CUDA tensors (no CPU fallback); got %s" % x.device)
+
+    def _state(self):
+        return {k: v.detach() for k, v in self.state_dict().items()}
+
+    def _get_plan(self, key, factory):
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = factory()
+            if self.use_cuda_graph:
+                plan.capture()
+            self._plans[key] = plan
+        return plan

@@ -319,7 +319,7 @@ namespace v2x {
 // how `features_map.view(-1, n_feat)` flattens the policy maps (When2com.py:429).
 __global__ void linear_kernel(const void* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                               float* __restrict__ y, int rows, int in_f, int out_f, int relu, int in_mode, int hw,
-                              int c, int planes) {
+                              int c, int planes, int split, int maps) {
   const int lane = threadIdx.x & 31;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gw >= (long long)rows * out_f) return;
@@ -330,11 +330,14 @@ __global__ void linear_kernel(const void* __restrict__ x, const float* __restric
     const float* xr = reinterpret_cast<const float*>(x) + (long long)r * in_f;
     for (int i = lane; i < in_f; i += 32) acc = fmaf(__ldg(wr + i), __ldg(xr + i), acc);
   } else {
+    // virtual row r of `.view(-1, in_f)` over maps flattened in NCHW order: map r / split, channels
+    // [(r % split) * c / split, ...) -- split > 1 reproduces the seg when2com quirk (When2Com_UNet.py:207-226, Q9)
     const __nv_bfloat16* xa = reinterpret_cast<const __nv_bfloat16*>(x);
-    const long long plane_stride = (long long)rows * hw * c;
+    const long long plane_stride = (long long)maps * hw * c;
+    const int map = r / split, ch_base = (r % split) * (c / split);
     for (int i = lane; i < in_f; i += 32) {
-      const int ch = i / hw, px = i - ch * hw;
-      const long long idx = ((long long)r * hw + px) * c + ch;
+      const int ch = ch_base + i / hw, px = i % hw;
+      const long long idx = ((long long)map * hw + px) * c + ch;
       float v = __bfloat162float(xa[idx]);
       if (planes == 2) v += __bfloat162float(xa[idx + plane_stride]);
       acc = fmaf(__ldg(wr + i), v, acc);
@@ -503,13 +506,15 @@ __global__ void warp_gated_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 
 extern "C" int v2x_linear_fwd(const void* x, const float* w, const float* b, float* y, int32_t rows, int32_t in_f,
                               int32_t out_f, int32_t relu, int32_t in_mode, int32_t hw, int32_t c, int32_t planes,
-                              void* stream) {
+                              int32_t split, int32_t maps, void* stream) {
   V2X_REQUIRE(x && w && y && rows > 0 && in_f > 0 && out_f > 0, "null/empty");
-  V2X_REQUIRE(in_mode == 0 || (in_mode == 1 && hw > 0 && c > 0 && hw * c == in_f && (planes == 1 || planes == 2)),
+  if (in_mode == 1 && split <= 0) split = 1;
+  V2X_REQUIRE(in_mode == 0 || (in_mode == 1 && hw > 0 && c > 0 && c % split == 0 && hw * (c / split) == in_f &&
+                               maps > 0 && rows <= maps * split && (planes == 1 || planes == 2)),
               "bad act input geometry");
   const long long threads = (long long)rows * out_f * 32;
   linear_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, b, y, rows, in_f, out_f, relu,
-                                                                                    in_mode, hw, c, planes);
+                                                                                    in_mode, hw, c, planes, split, maps);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }
@@ -548,6 +553,166 @@ extern "C" int v2x_warp_gated_fwd(const void* x, void* out, const double* trans,
     warp_gated_kernel<2><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i);
   else
     warp_gated_kernel<4><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+// =============================================================================================
+// segmentation UNet helpers (CP/models/seg/SegModelBase.py): NCHW input pack, MaxPool2d(2), bilinear x2 upsample
+// All byte movers: one thread per (pixel, 8-channel group), 16-byte accesses.
+// =============================================================================================
+namespace v2x {
+
+// fp32 NCHW [n][c][h][w] -> act bf16 planes NHWC [planes][n][h][w][c_pad]   (SegModule.py:49 hands the model NCHW)
+__global__ void pack_input_nchw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int n, int c,
+                                       int h, int w, int c_pad, int planes) {
+  const int groups = c_pad / 8;
+  const long long hw = (long long)h * w;
+  const long long total = (long long)n * hw * groups;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    // pixel fastest so that the strided channel reads of a warp are coalesced along w
+    const long long pix = gid % hw;
+    const int g = (int)((gid / hw) % groups);
+    const int im = (int)(gid / (hw * groups));
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = g * 8 + 2 * i;
+      const float v0 = c0 < c ? __ldg(x + ((long long)im * c + c0) * hw + pix) : 0.f;
+      const float v1 = c0 + 1 < c ? __ldg(x + ((long long)im * c + c0 + 1) * hw + pix) : 0.f;
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v0, h0, l0);
+      split_bf16(v1, h1, l1);
+      hi[i] = pack_bf16x2(h0, h1);
+      lo[i] = pack_bf16x2(l0, l1);
+    }
+    __nv_bfloat16* dst = out + ((long long)im * hw + pix) * c_pad + g * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (planes == 2) *reinterpret_cast<uint4*>(dst + (long long)n * hw * c_pad) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, long long plane_stride, int planes, float* v) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+  uint4 ql = make_uint4(0, 0, 0, 0);
+  if (planes == 2) ql = __ldg(reinterpret_cast<const uint4*>(p + plane_stride));
+  const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 f = __bfloat1622float2(h2[e]);
+    if (planes == 2) {
+      const float2 g = __bfloat1622float2(l2[e]);
+      f.x += g.x; f.y += g.y;
+    }
+    v[2 * e] = f.x; v[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, long long plane_stride, int planes, const float* v) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[2 * e], h0, l0);
+    split_bf16(v[2 * e + 1], h1, l1);
+    hi[e] = pack_bf16x2(h0, h1);
+    lo[e] = pack_bf16x2(l0, l1);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (planes == 2) *reinterpret_cast<uint4*>(p + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// nn.MaxPool2d(2) (SegModelBase.py:113): act [n][2h][2w][c] -> [n][h][w][c]
+__global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int n, int h,
+                                int w, int c, int planes) {
+  const int groups = c / 8;
+  const long long total = (long long)n * h * w * groups;
+  const long long in_plane = (long long)n * 4 * h * w * c, out_plane = (long long)n * h * w * c;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(gid % groups);
+    const long long pix = gid / groups;
+    const int ox = (int)(pix % w), oy = (int)((pix / w) % h), im = (int)(pix / ((long long)w * h));
+    float m[8], v[8];
+    const __nv_bfloat16* base = x + (((long long)im * 2 * h + 2 * oy) * 2 * w + 2 * ox) * c + g * 8;
+    load8(base, in_plane, planes, m);
+    load8(base + c, in_plane, planes, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+    load8(base + (long long)2 * w * c, in_plane, planes, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+    load8(base + (long long)2 * w * c + c, in_plane, planes, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+    store8(out + pix * c + g * 8, out_plane, planes, m);
+  }
+}
+
+// nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) (SegModelBase.py:125):
+// src = dst * (in - 1) / (out - 1); act [n][h][w][c] -> [n][2h][2w][c]
+__global__ void upsample_bilinear2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int n,
+                                          int h, int w, int c, int planes) {
+  const int groups = c / 8;
+  const int oh_n = 2 * h, ow_n = 2 * w;
+  const long long total = (long long)n * oh_n * ow_n * groups;
+  const long long in_plane = (long long)n * h * w * c, out_plane = (long long)n * oh_n * ow_n * c;
+  const float sy = oh_n > 1 ? (float)(h - 1) / (float)(oh_n - 1) : 0.f;
+  const float sx = ow_n > 1 ? (float)(w - 1) / (float)(ow_n - 1) : 0.f;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(gid % groups);
+    const long long pix = gid / groups;
+    const int ox = (int)(pix % ow_n), oy = (int)((pix / ow_n) % oh_n), im = (int)(pix / ((long long)ow_n * oh_n));
+    const float fy = oy * sy, fx = ox * sx;
+    const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float wy1 = fy - (float)y0, wx1 = fx - (float)x0, wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+    const __nv_bfloat16* b = x + (long long)im * h * w * c + g * 8;
+    float a00[8], a01[8], a10[8], a11[8], r[8];
+    load8(b + ((long long)y0 * w + x0) * c, in_plane, planes, a00);
+    load8(b + ((long long)y0 * w + x1) * c, in_plane, planes, a01);
+    load8(b + ((long long)y1 * w + x0) * c, in_plane, planes, a10);
+    load8(b + ((long long)y1 * w + x1) * c, in_plane, planes, a11);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)  // same association as ATen's upsample_bilinear2d: rows first, then columns
+      r[e] = wy0 * (wx0 * a00[e] + wx1 * a01[e]) + wy1 * (wx0 * a10[e] + wx1 * a11[e]);
+    store8(out + pix * c + g * 8, out_plane, planes, r);
+  }
+}
+
+}  // namespace v2x
+
+extern "C" int v2x_pack_input_nchw(const float* x, void* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pad,
+                                   int32_t planes, void* stream) {
+  V2X_REQUIRE(x && out && n > 0 && c > 0 && h > 0 && w > 0, "null/empty input");
+  V2X_REQUIRE(c_pad >= c && c_pad % 8 == 0 && (planes == 1 || planes == 2), "bad c_pad / planes");
+  const long long total = (long long)n * h * w * (c_pad / 8);
+  pack_input_nchw_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), n, c, h, w, c_pad, planes);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_maxpool2_fwd(const void* x, void* out, int32_t n, int32_t h_out, int32_t w_out, int32_t c,
+                                int32_t planes, void* stream) {
+  V2X_REQUIRE(x && out && n > 0 && h_out > 0 && w_out > 0 && c > 0 && c % 8 == 0, "bad geometry");
+  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  const long long total = (long long)n * h_out * w_out * (c / 8);
+  maxpool2_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n, h_out, w_out, c, planes);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_upsample_bilinear2_fwd(const void* x, void* out, int32_t n, int32_t h_in, int32_t w_in, int32_t c,
+                                          int32_t planes, void* stream) {
+  V2X_REQUIRE(x && out && n > 0 && h_in > 0 && w_in > 0 && c > 0 && c % 8 == 0, "bad geometry");
+  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  const long long total = (long long)n * 4 * h_in * w_in * (c / 8);
+  upsample_bilinear2_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n, h_in, w_in, c, planes);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }

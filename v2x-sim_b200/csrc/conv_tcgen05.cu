@@ -134,6 +134,16 @@ __device__ __forceinline__ void epi_f32_split16(const ConvDev& p, int n_img, int
   }
 }
 
+// fp32 NCHW output (segmentation logits, SegModelBase.py:145-151): out0[((n * cout + ch) * H + oh) * W + ow]
+__device__ __forceinline__ void epi_f32_nchw16(const ConvDev& p, int n_img, int oh, int ow, int ch0, const float* v,
+                                               const float* bias16) {
+  float* o = reinterpret_cast<float*>(p.out0) + (((long long)n_img * p.cout + ch0) * p.h_out + oh) * p.w_out + ow;
+  const long long cs = (long long)p.h_out * p.w_out;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (ch0 + i < p.cout) o[i * cs] = v[i] + bias16[i];
+}
+
 // GRU gates for 16 channels [c0, c0+16) of one pixel.  bias_r16 points at the bias of the r gate of channel
 // c0 inside the [r(64) | z(64) | n(64)] block (z at +64, n at +128); bhn16 at b_hh_n of channel c0.
 __device__ __forceinline__ void epi_gru16(const ConvDev& p, int n_img, int oh, int ow, int c0, const float* r,
@@ -509,7 +519,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_buf * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
       const bool no_store = dbg_no_store || !valid;
-      if (p.epilogue == V2X_EPI_F32_SPLIT) {
+      if (p.epilogue == V2X_EPI_F32_NCHW) {
+#pragma unroll 1
+        for (int c16 = 0; c16 < BN / 16; ++c16) {
+          if (n0 + c16 * 16 >= p.cout) break;
+          float v0[16];
+          tmem_ld16_async(taddr + c16 * 16, v0);
+          tmem_ld_wait16(v0);
+          if (valid && !dbg_no_store) epi_f32_nchw16(p, ti.n_img, oh, ow, n0 + c16 * 16, v0, s_bias + c16 * 16);
+        }
+      } else if (p.epilogue == V2X_EPI_F32_SPLIT) {
 #pragma unroll 1
         for (int c32 = 0; c32 < (BN + 31) / 32; ++c32) {
           const int ch0 = n0 + c32 * 32;
@@ -676,6 +695,7 @@ __global__ void conv_ref_kernel(const ConvDev p) {
     const int ch0 = chunk * 16;
     if (ch0 >= p.cout) return;
     if (p.epilogue == V2X_EPI_ACT) epi_act16(p, n_img, oh, ow, ch0, acc[0], p.bias + ch0);
+    else if (p.epilogue == V2X_EPI_F32_NCHW) epi_f32_nchw16(p, n_img, oh, ow, ch0, acc[0], p.bias + ch0);
     else epi_f32_split16(p, n_img, oh, ow, ch0, acc[0], p.bias + ch0);
   }
 }
@@ -735,7 +755,8 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
   const int bn = p->block_n;
   V2X_REQUIRE(bn == 32 || bn == 48 || bn == 64 || bn == 128 || bn == 192 || bn == 256, "unsupported block_n %d", bn);
   V2X_REQUIRE(p->cout > 0 && p->cout_pad >= p->cout && p->cout_pad % bn == 0, "cout_pad must be a multiple of block_n");
-  V2X_REQUIRE(p->cout % 16 == 0 || p->epilogue == V2X_EPI_F32_SPLIT, "cout must be a multiple of 16");
+  V2X_REQUIRE(p->cout % 16 == 0 || p->epilogue == V2X_EPI_F32_SPLIT || p->epilogue == V2X_EPI_F32_NCHW,
+              "cout must be a multiple of 16");
   d = ConvDev{};
   d.n_maps = p->n_maps; d.h_out = p->h_out; d.w_out = p->w_out; d.stride = p->stride; d.taps = p->taps;
   d.planes = p->planes;
@@ -782,6 +803,9 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
       V2X_REQUIRE(p->out1 != nullptr || p->split >= p->cout, "F32_SPLIT needs out1");
       V2X_REQUIRE(p->split > 0 && p->split <= p->cout, "bad split");
       V2X_REQUIRE(p->split % 4 == 0 && p->cout % 4 == 0, "F32_SPLIT needs split %% 4 == 0 and cout %% 4 == 0");
+      V2X_REQUIRE(!p->upsample2x, "upsample2x only with EPI_ACT");
+      break;
+    case V2X_EPI_F32_NCHW:
       V2X_REQUIRE(!p->upsample2x, "upsample2x only with EPI_ACT");
       break;
     case V2X_EPI_GRU:

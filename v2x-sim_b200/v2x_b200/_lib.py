@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libv2x_b200.so")
 
-EPI_ACT, EPI_F32_SPLIT, EPI_GRU = 0, 1, 2
+EPI_ACT, EPI_F32_SPLIT, EPI_GRU, EPI_F32_NCHW = 0, 1, 2, 3
 
 
 class ConvParams(C.Structure):
@@ -64,7 +64,10 @@ SYMBOLS = [
     ("v2x_pack_input", C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
     ("v2x_warp_mean_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_act_to_nchw_f32", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
-    ("v2x_linear_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_linear_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_pack_input_nchw", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_maxpool2_fwd", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_upsample_bilinear2_fwd", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_attn_scores_fwd", C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_warp_gated_fwd", C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
 ]

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import EPI_ACT, EPI_F32_SPLIT, EPI_GRU, ConvParams, V2XError, check
+from ._lib import EPI_ACT, EPI_F32_NCHW, EPI_F32_SPLIT, EPI_GRU, ConvParams, V2XError, check
 
 BN_EPS = 1e-5  # nn.BatchNorm2d default (reference never overrides it)
 
@@ -84,7 +84,7 @@ def _f32(t, device):
 
 
 def pack_conv(weight, bias, bn=None, *, cins: Sequence[int], cin_pads: Optional[Sequence[int]] = None, stride=1,
-              planes=1, device=None, vflip=False, gru=False) -> PackedConv:
+              planes=1, device=None, vflip=False, gru=False, cout_pad: Optional[int] = None) -> PackedConv:
     """BN-fold + reorder + bf16 split of one conv's weights, on device.
 
     weight: OIHW (or OI111 for the 1x1x1 Conv3D) fp32; ``cins`` = logical channels of each concat
@@ -96,7 +96,7 @@ def pack_conv(weight, bias, bn=None, *, cins: Sequence[int], cin_pads: Optional[
     taps = int(weight.numel() // (cout * cin_total))
     assert taps in (1, 9) and sum(cins) == cin_total
     cin_pads = list(cin_pads) if cin_pads is not None else [((c + 15) // 16) * 16 for c in cins]
-    cout_pad = cout
+    cout_pad = cout_pad or cout   # zero rows up to a multiple of the N tile (e.g. the 8-class seg logits)
     k_total = taps * sum(cin_pads)
     w = _f32(weight, device).reshape(cout, cin_total, taps)
     b = _f32(bias, device) if bias is not None else None
@@ -209,7 +209,7 @@ class ConvLaunch:
         p.epilogue, p.relu, p.upsample2x = epilogue, int(relu), int(upsample2x)
         p.out0 = out0.data_ptr()
         p.out1 = out1.data_ptr() if out1 is not None else None
-        p.out_c_total = out0.shape[-1] if epilogue != EPI_F32_SPLIT else 0
+        p.out_c_total = out0.shape[-1] if epilogue in (EPI_ACT, EPI_GRU) else 0
         p.out_c_off, p.split = out_c_off, split
         p.gru_bhn = pc.gru_bhn.data_ptr() if pc.gru_bhn is not None else None
         p.passthrough = passthrough.data_ptr() if passthrough is not None else None
@@ -251,22 +251,27 @@ def warp_mean(x: torch.Tensor, trans: torch.Tensor, num_agent: torch.Tensor, bat
 
 
 # ---- when2com / who2com ----------------------------------------------------------------------
-def linear(x, w, b, *, relu=False, out=None, act_input=False):
-    """fp32 linear layer through v2x_linear_fwd.  ``act_input``: x is an act [P, rows, H, W, C] flattened in
-    NCHW order (KmGenerator's ``view(-1, n_feat)``); otherwise x is fp32 [rows, in_f]."""
+def linear(x, w, b, *, relu=False, out=None, act_input=False, rows=None):
+    """fp32 linear layer through v2x_linear_fwd.  ``act_input``: x is an act [P, maps, H, W, C] flattened in NCHW
+    order and viewed as rows of ``in_f`` values (KmGenerator's ``view(-1, n_feat)``; when H*W*C is a multiple of in_f
+    each map spans several rows -- the seg quirk); ``rows`` = how many leading rows to compute.
+    Otherwise x is fp32 [rows, in_f]."""
     lib = require_gpu()
     out_f, in_f = w.shape
+    maps, split = 0, 1
     if act_input:
-        planes, rows, h, wd, c = x.shape
-        assert h * wd * c == in_f
+        planes, maps, h, wd, c = x.shape
+        assert (h * wd * c) % in_f == 0
+        split = h * wd * c // in_f
         mode, hw = 1, h * wd
+        rows = maps if rows is None else rows
     else:
         rows, planes, hw, c, mode = x.shape[0], 1, 0, 0, 0
         assert x.dtype == torch.float32 and x.shape[1] == in_f and x.is_contiguous()
     if out is None:
         out = torch.empty((rows, out_f), dtype=torch.float32, device=w.device)
     check(lib.v2x_linear_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(out), rows, in_f, out_f, int(relu), mode, hw, c, planes,
-                             _stream()), "v2x_linear_fwd")
+                             split, maps, _stream()), "v2x_linear_fwd")
     return out
 
 
@@ -294,4 +299,34 @@ def warp_gated(x, trans, num_agent, coef, batch, agents, *, warp_flag=1, only_v2
         out = torch.empty_like(x)
     check(lib.v2x_warp_gated_fwd(_ptr(x), _ptr(out), _ptr(trans), _ptr(num_agent), _ptr(coef), batch, agents, h, w, c,
                                  planes, int(warp_flag), int(only_v2i), _stream()), "v2x_warp_gated_fwd")
+    return out
+
+
+# ---- segmentation UNet pieces ----------------------------------------------------------------
+def pack_input_nchw(x: torch.Tensor, c_pad: int, planes: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 NCHW [N, C, H, W] -> act [planes, N, H, W, c_pad]."""
+    lib = require_gpu()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda and x.dim() == 4
+    n, c, h, w = x.shape
+    if out is None:
+        out = empty_act(planes, n, h, w, c_pad, x.device)
+    check(lib.v2x_pack_input_nchw(_ptr(x), _ptr(out), n, c, h, w, c_pad, planes, _stream()), "v2x_pack_input_nchw")
+    return out
+
+
+def maxpool2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = require_gpu()
+    planes, n, h, w, c = x.shape
+    if out is None:
+        out = empty_act(planes, n, h // 2, w // 2, c, x.device)
+    check(lib.v2x_maxpool2_fwd(_ptr(x), _ptr(out), n, h // 2, w // 2, c, planes, _stream()), "v2x_maxpool2_fwd")
+    return out
+
+
+def upsample_bilinear2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = require_gpu()
+    planes, n, h, w, c = x.shape
+    if out is None:
+        out = empty_act(planes, n, 2 * h, 2 * w, c, x.device)
+    check(lib.v2x_upsample_bilinear2_fwd(_ptr(x), _ptr(out), n, h, w, c, planes, _stream()), "v2x_upsample_bilinear2_fwd")
     return out
