@@ -58,6 +58,18 @@ def measured_peaks():
             "source": "fallback (B200_PROFILING.md: 1.59 PF burst / ~1.4 PF sustained)"}
 
 
+def conv_traffic(scenes):
+    """dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of one step, from the committed
+    ncu --set full capture (profiles/conv_traffic.json); None when the capture was taken at another batch size."""
+    path = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["conv_dram_bytes_per_step"]) if int(d["scenes_per_step"]) == scenes else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -306,7 +318,8 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "tensor",
                 "kernel": "v2x::conv_tc_kernel<BN,PLANES,KSTEPS,HALO> (the %d conv launches of a step)" % len(conv_launches),
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "peak_source": peaks["source"],
+                "traffic": conv_traffic(B), "traffic_unit": "bytes of DRAM read+write per step over the conv launches (ncu --set full, profiles/conv_traffic.json)",
+                "peak_source": peaks["source"],
                 "conv_ms_per_step": conv_ms, "other_kernels_ms_per_step": other_ms,
                 "conv_share_of_step": conv_ms / step_ms,
                 "launches_per_step": {"conv": len(conv_launches), "other": len(other_launches)},

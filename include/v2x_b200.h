@@ -90,6 +90,10 @@ typedef struct v2x_conv_params {
   int32_t batch, agents;     /* agent-major maps: global unit = batch * agent + b              */
   int32_t map_offset;        /* global unit index of this launch's map 0 (sharded plans), else 0 */
   int32_t reserved[3];
+  /* EPI_GRU, optional: fp32 [N*H*W][cout] (packed gate order) added to the gate pre-activations -- the round-invariant
+     half conv(mean, W_ih[:, C:]) + bias, computed once per frame by an EPI_F32_SPLIT launch (split == cout) so the three
+     GNN rounds only convolve the changing half (V2VNet.py:99: cat([h_i, mean]); the mean never changes). */
+  const float* gru_add;
 } v2x_conv_params;
 
 int v2x_conv_fwd(const v2x_conv_params* p, void* stream);

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     from v2x_b200 import _lib
     # 2 ptr + 2 i32 + 6 i32 + 2 ptr + 6 i32 + 2 ptr + 3 i32 (+pad) + 3 ptr + 2 i32 + 4 i32
-    assert ctypes.sizeof(_lib.ConvParams) == 168
+    assert ctypes.sizeof(_lib.ConvParams) == 176
 
 
 def test_argument_validation_is_loud():

@@ -306,3 +306,35 @@ def test_warp_gated(warp_flag, planes):
     err = rel_err(ops.act_to_float(out), ref)
     print("warp_gated warp=%d planes=%d rel_err=%.3e" % (warp_flag, planes, err))
     assert err < TOL[planes]
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("impl", ["crosscheck", "tc"])
+def test_convgru_split_operands(impl, planes):
+    """Round-invariant split of the zero-hidden ConvGRU: conv(mean, W_ih[:, C:]) + bias once (fp32 pre-activations),
+    conv(h, W_ih[:, :C]) + gate epilogue per round -- must equal the oracle GRU on cat([h, mean])."""
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    from v2x_b200.ops import EPI_F32_SPLIT, EPI_GRU, ConvLaunch
+    dev = _dev()
+    c = 64
+    gen = synth._Gen(13)
+    sd = {"convgru.weight_ih_l0": gen.uniform((3 * c, 2 * c, 3, 3), -0.05, 0.05),
+          "convgru.weight_hh_l0": gen.uniform((3 * c, c, 3, 3), -0.05, 0.05),
+          "convgru.bias_ih_l0": gen.uniform((3 * c,), -0.5, 0.5),
+          "convgru.bias_hh_l0": gen.uniform((3 * c,), -0.5, 0.5)}
+    n = 2
+    hfeat, mean = gen.normal((n, c, 16, 16), 1.0), gen.normal((n, c, 16, 16), 1.0)
+    ref = torch.cat([torch.flip(restate.convgru_zero_hidden(
+        torch.flip(torch.cat([hfeat[i], mean[i]], 0).unsqueeze(0), (2,)), sd), (2,)) for i in range(n)], 0)
+    gru_h, gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"], sd["convgru.bias_hh_l0"],
+                                      planes=planes, device=dev)
+    a_h, a_m = to_act(hfeat, planes, dev), to_act(mean, planes, dev)
+    cc = impl == "crosscheck"
+    pre = torch.empty((n, 16, 16, 3 * c), dtype=torch.float32, device=dev)
+    ConvLaunch(gru_m, [a_m], epilogue=EPI_F32_SPLIT, relu=False, out0=pre, split=3 * c, crosscheck=cc)()
+    out = torch.empty_like(a_h)
+    ConvLaunch(gru_h, [a_h], epilogue=EPI_GRU, out0=out, gru_add=pre, crosscheck=cc)()
+    err = rel_err(ops.act_to_float(out), ref)
+    print("gru split %s planes=%d rel_err=%.3e" % (impl, planes, err))
+    assert err < TOL[planes]

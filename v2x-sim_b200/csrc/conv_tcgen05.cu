@@ -59,6 +59,7 @@ struct ConvDev {
   int out_c_total, out_c_off, split;
   const float* bias;
   const float* gru_bhn;
+  const float* gru_add;      // optional fp32 [pixel][cout] pre-activation term added to the gate accumulators
   const void* passthrough;
   const long long* num_agent;
   int batch, agents, map_offset;
@@ -147,13 +148,15 @@ __device__ __forceinline__ void epi_f32_nchw16(const ConvDev& p, int n_img, int 
 // GRU gates for 16 channels [c0, c0+16) of one pixel.  bias_r16 points at the bias of the r gate of channel
 // c0 inside the [r(64) | z(64) | n(64)] block (z at +64, n at +128); bhn16 at b_hh_n of channel c0.
 __device__ __forceinline__ void epi_gru16(const ConvDev& p, int n_img, int oh, int ow, int c0, const float* r,
-                                          const float* z, const float* nn, const float* bias_r16, const float* bhn16) {
+                                          const float* z, const float* nn, const float* bias_r16, const float* bhn16,
+                                          const float* add_r16 = nullptr) {
   float h[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float rr = 1.f / (1.f + __expf(-(r[i] + bias_r16[i])));
-    const float zz = 1.f / (1.f + __expf(-(z[i] + bias_r16[64 + i])));
-    const float nv = tanhf(nn[i] + bias_r16[128 + i] + rr * bhn16[i]);
+    const float ar = add_r16 ? add_r16[i] : 0.f, az = add_r16 ? add_r16[64 + i] : 0.f, an = add_r16 ? add_r16[128 + i] : 0.f;
+    const float rr = 1.f / (1.f + __expf(-(r[i] + bias_r16[i] + ar)));
+    const float zz = 1.f / (1.f + __expf(-(z[i] + bias_r16[64 + i] + az)));
+    const float nv = tanhf(nn[i] + bias_r16[128 + i] + an + rr * bhn16[i]);
     h[i] = (1.f - zz) * nv;
   }
   store_act16(p, n_img, oh, ow, c0, h);
@@ -563,6 +566,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
               tmem_ld_wait16(z);
               tmem_ld_wait16(nn);
               const float* br = s_bias + c16 * 16;
+              if (p.gru_add != nullptr && valid) {  // round-invariant half of the pre-activations (W_ih[:, mean] * mean + b)
+                const float4* g = reinterpret_cast<const float4*>(
+                    p.gru_add + (((long long)ti.n_img * p.h_out + oh) * p.w_out + ow) * p.cout + n0 + c16 * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 gr = __ldg(g + q), gz = __ldg(g + 16 + q), gn = __ldg(g + 32 + q);
+                  r[4 * q] += gr.x; r[4 * q + 1] += gr.y; r[4 * q + 2] += gr.z; r[4 * q + 3] += gr.w;
+                  z[4 * q] += gz.x; z[4 * q + 1] += gz.y; z[4 * q + 2] += gz.z; z[4 * q + 3] += gz.w;
+                  nn[4 * q] += gn.x; nn[4 * q + 1] += gn.y; nn[4 * q + 2] += gn.z; nn[4 * q + 3] += gn.w;
+                }
+              }
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float rr = 1.f / (1.f + __expf(-(r[i] + br[i])));
@@ -690,7 +704,8 @@ __global__ void conv_ref_kernel(const ConvDev p) {
     kbase += (long long)p.taps * p.cin[s];
   }
   if (gru) {
-    epi_gru16(p, n_img, oh, ow, chunk * 16, acc[0], acc[1], acc[2], p.bias + prow[0], p.gru_bhn + chunk * 16);
+    epi_gru16(p, n_img, oh, ow, chunk * 16, acc[0], acc[1], acc[2], p.bias + prow[0], p.gru_bhn + chunk * 16,
+              p.gru_add ? p.gru_add + (((long long)n_img * p.h_out + oh) * p.w_out + ow) * p.cout + prow[0] : nullptr);
   } else {
     const int ch0 = chunk * 16;
     if (ch0 >= p.cout) return;
@@ -781,7 +796,7 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
   d.epilogue = p->epilogue; d.relu = p->relu; d.upsample2x = p->upsample2x;
   d.out0 = p->out0; d.out1 = p->out1;
   d.out_c_total = p->out_c_total; d.out_c_off = p->out_c_off; d.split = p->split;
-  d.bias = p->bias; d.gru_bhn = p->gru_bhn; d.passthrough = p->passthrough;
+  d.bias = p->bias; d.gru_bhn = p->gru_bhn; d.gru_add = p->gru_add; d.passthrough = p->passthrough;
   d.num_agent = reinterpret_cast<const long long*>(p->num_agent);
   d.batch = p->batch; d.agents = p->agents; d.map_offset = p->map_offset;
   d.debug_mode = g_debug_mode;

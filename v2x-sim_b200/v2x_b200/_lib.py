@@ -45,6 +45,7 @@ class ConvParams(C.Structure):
         ("agents", C.c_int32),
         ("map_offset", C.c_int32),
         ("reserved", C.c_int32 * 3),
+        ("gru_add", C.c_void_p),
     ]
 
 

@@ -129,6 +129,21 @@ class DetPlan:
         t = self.conv(c["conv8_1"], [x7u, x0], tag + "x8a")
         return self.conv(c["conv8_2"], [t], tag + "x8")
 
+    def build_gru_rounds(self, x3, mean, gnn_iter, batch, agents, map_offset):
+        """``gnn_iter`` zero-hidden ConvGRU rounds on cat([h, mean]) (V2VNet.py:99-101).  The mean half of the input never
+        changes between rounds (neighbours are always warped from the original maps), so its contribution
+        conv(mean, W_ih[:, C:]) + bias is computed once into fp32 pre-activations and added in each round's epilogue."""
+        c3, hh, ww = x3.shape[-1], x3.shape[2], x3.shape[3]
+        self.gru_pre = torch.empty((self.n, hh, ww, 3 * c3), dtype=torch.float32, device=self.device)
+        self.add(ConvLaunch(self.gru_m, [mean], epilogue=EPI_F32_SPLIT, relu=False, out0=self.gru_pre, split=3 * c3))
+        h = x3
+        for r in range(gnn_iter):
+            out = self.act("h%d" % (r + 1), hh, ww, c3)
+            self.add(ConvLaunch(self.gru_h, [h], epilogue=EPI_GRU, out0=out, passthrough=x3, num_agent=self.num_agent,
+                                batch=batch, agents=agents, map_offset=map_offset, gru_add=self.gru_pre))
+            h = out
+        return h
+
     def build_heads(self, hw: HeadWeights, x8):
         t = self.conv(hw.head1, [x8], "head1")
         n_cls = hw.n_cls
@@ -180,8 +195,8 @@ class V2VNetDetPlan(DetPlan):
         self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
         self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
         self.head_w = HeadWeights(sd, planes, dev)
-        self.gru_w = ops.pack_gru(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"], sd["convgru.bias_hh_l0"],
-                                  planes=planes, device=dev)
+        self.gru_h, self.gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"],
+                                                    sd["convgru.bias_hh_l0"], planes=planes, device=dev)
         self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
 
@@ -193,12 +208,7 @@ class V2VNetDetPlan(DetPlan):
         mean = self.act("mean", 32, 32, c3)
         trans, na = self.trans, self.num_agent
         self.add(lambda: ops.warp_mean(x3, trans, na, batch, agents, include_self=False, only_v2i=only_v2i, out=mean))
-        h = x3
-        for r in range(gnn_iter):
-            out = self.act("h%d" % (r + 1), 32, 32, c3)
-            self.add(ConvLaunch(self.gru_w, [h, mean], epilogue=EPI_GRU, out0=out, passthrough=x3, num_agent=na,
-                                batch=batch, agents=agents))
-            h = out
+        h = self.build_gru_rounds(x3, mean, gnn_iter, batch, agents, 0)
         x8 = self.build_decoder(self.dec_w, x0, x1, x2, h, x4u)
         self.build_heads(self.head_w, x8)
 
@@ -326,8 +336,8 @@ class V2VNetDetShardedPlan(DetPlan):
         self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
         self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
         self.head_w = HeadWeights(sd, planes, dev)
-        self.gru_w = ops.pack_gru(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"], sd["convgru.bias_hh_l0"],
-                                  planes=planes, device=dev)
+        self.gru_h, self.gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"],
+                                                    sd["convgru.bias_hh_l0"], planes=planes, device=dev)
         self.trans = torch.zeros((batch_total, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch_total, agents), agents, dtype=torch.int64, device=dev)
         trans, na, off = self.trans, self.num_agent, self.offset
@@ -355,12 +365,7 @@ class V2VNetDetShardedPlan(DetPlan):
         mean = self.act("mean", 32, 32, c3)
         self.add(lambda: ops.warp_mean(x3_all, trans, na, batch_total, agents, include_self=False, only_v2i=only_v2i,
                                        out=mean, unit_offset=off, unit_count=n_loc))
-        h = x3
-        for r in range(gnn_iter):
-            out = self.act("h%d" % (r + 1), 32, 32, c3)
-            self.add(ConvLaunch(self.gru_w, [h, mean], epilogue=EPI_GRU, out0=out, passthrough=x3, num_agent=na,
-                                batch=batch_total, agents=agents, map_offset=off))
-            h = out
+        h = self.build_gru_rounds(x3, mean, gnn_iter, batch_total, agents, off)
         x8 = self.build_decoder(self.dec_w, x0, x1, x2, h, x4u)
         self.build_heads(self.head_w, x8)
         self.graphs = None

@@ -135,17 +135,15 @@ class SegV2VNetPlan(_FusedSegPlan):
         ops.require_gpu()
         self._common(batch, agents)
         self.w = SegUNetWeights(sd, planes, self.device)
-        self.gru_w = ops.pack_gru(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"], sd["convgru.bias_hh_l0"],
-                                  planes=planes, device=self.device)
+        self.gru_h, self.gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"],
+                                                    sd["convgru.bias_hh_l0"], planes=planes, device=self.device)
         x_in = self.build_input()
         x1, x2, x3, x4 = self.build_encoder(self.w, x_in)
         c4 = x4.shape[-1]
         mean = self.act("mean", 32, 32, c4)
         trans, na = self.trans, self.num_agent
         self.add(lambda: ops.warp_mean(x4, trans, na, batch, agents, include_self=True, only_v2i=only_v2i, out=mean))
-        fused = self.act("fused", 32, 32, c4)
-        self.add(ConvLaunch(self.gru_w, [x4, mean], epilogue=EPI_GRU, out0=fused, passthrough=x4, num_agent=na,
-                            batch=batch, agents=agents))
+        fused = self.build_gru_rounds(x4, mean, 1, batch, agents, 0)
         self.build_decoder(self.w, fused, x1, x2, x3)
 
 

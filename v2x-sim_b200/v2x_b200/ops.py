@@ -128,6 +128,24 @@ def pack_gru(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True) -> PackedCo
     return pc
 
 
+def pack_gru_split(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True):
+    """The zero-hidden ConvGRU split in two operands: ``gru_m`` convolves the round-invariant neighbour mean
+    (W_ih[:, C:], carries the combined bias) once per frame into fp32 pre-activations; ``gru_h`` convolves the agent's
+    own state (W_ih[:, :C]) in every GNN round and adds them in its gate epilogue (``gru_add``).  Same arithmetic as
+    conv(cat([h, mean])) up to fp32 summation order; one third fewer FLOPs over three rounds."""
+    lib = require_gpu()
+    device = device or w_ih.device
+    c = w_ih.shape[0] // 3
+    gru_h = pack_conv(w_ih[:, :c], None, None, cins=[c], planes=planes, device=device, vflip=vflip, gru=True)
+    gru_m = pack_conv(w_ih[:, c:], None, None, cins=[w_ih.shape[1] - c], planes=planes, device=device, vflip=vflip,
+                      gru=True)
+    bhn = torch.empty((c,), dtype=torch.float32, device=device)
+    bi, bh = _f32(b_ih, device), _f32(b_hh, device)
+    check(lib.v2x_pack_gru_bias(_ptr(bi), _ptr(bh), c, _ptr(gru_m.bias), _ptr(bhn), _stream()), "v2x_pack_gru_bias")
+    gru_h.gru_bhn = bhn     # gru_h.bias stays zero: the bias rides in gru_m's output
+    return gru_h, gru_m
+
+
 def pack_heads(cls1_w, cls1_b, cls_bn, reg1_w, reg1_b, reg_bn, cls2_w, cls2_b, reg2_w, reg2_b, *, planes=1,
                device=None):
     """Detection heads (DetModelBase.py:268-351) as two launches: one 32->64 3x3 conv (cls.conv1|reg.0 rows
@@ -186,7 +204,7 @@ class ConvLaunch:
 
     def __init__(self, pc: PackedConv, srcs: Sequence[torch.Tensor], *, epilogue=EPI_ACT, relu=True, upsample2x=False,
                  out0: torch.Tensor = None, out1: torch.Tensor = None, out_c_off=0, split=0, block_n=None,
-                 passthrough=None, num_agent=None, batch=0, agents=0, map_offset=0, crosscheck=False):
+                 passthrough=None, num_agent=None, batch=0, agents=0, map_offset=0, gru_add=None, crosscheck=False):
         self.lib = require_gpu()
         planes, n, h_in, w_in, _ = srcs[0].shape
         assert planes == pc.planes
@@ -215,8 +233,9 @@ class ConvLaunch:
         p.passthrough = passthrough.data_ptr() if passthrough is not None else None
         p.num_agent = num_agent.data_ptr() if num_agent is not None else None
         p.batch, p.agents, p.map_offset = batch, agents, map_offset
+        p.gru_add = gru_add.data_ptr() if gru_add is not None else None
         self.p = p
-        self.keep = (pc, list(srcs), out0, out1, passthrough, num_agent)
+        self.keep = (pc, list(srcs), out0, out1, passthrough, num_agent, gru_add)
         self.fn = self.lib.v2x_conv_fwd_crosscheck if crosscheck else self.lib.v2x_conv_fwd
         self.flops = 2.0 * n * h_out * w_out * pc.cout * pc.taps * sum(pc.cins)
 
