@@ -7,7 +7,7 @@ import torch
 from oracle import synth
 from v2x_b200 import _lib, nets
 
-NAMES = ["pack_in","pre_1","pre_2","c1_1","c1_2","c3d_1","c2_1","c2_2","c3d_2","c3_1","c3_2","c4_1","c4_2","warp","gru1","gru2","gru3","c5_1","c5_2","c6_1","c6_2","c7_1","c7_2","c8_1","c8_2","head1","head2"]
+NAMES = ["pack_in","pre_1","pre_2","c1_1","c1_2","c3d_1","c2_1","c2_2","c3d_2","c3_1","c3_2","c4_1","c4_2","warp","gru_m","gru1","gru2","gru3","c5_1","c5_2","c6_1","c6_2","c7_1","c7_2","c8_1","c8_2","head1","head2"]
 
 def time_launches(plan, iters=5):
     n = len(plan.launches); tot = [0.0] * n

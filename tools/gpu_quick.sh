@@ -1,5 +1,6 @@
 #!/bin/bash
-# Quick GPU iteration: op + net tests, bench.
+# Quick GPU iteration: op + net tests, bench, per-launch ablation table.
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; grep -E "when2com|passed|failed|Error|partial|warp_gated" gpurun_out/pytest_gpu.log | tail -40
+timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 4 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -n 5 gpurun_out/bench.err
+timeout 600 python tools/ablate.py 8 1 > gpurun_out/ablate.log 2>&1; cat gpurun_out/ablate.log | tail -34

@@ -49,6 +49,8 @@ struct ConvDev {
   int kb_per_stage;          // k-blocks (tap x kc channels) per pipeline stage: one mbarrier round trip feeds them all
   int stages_per_tile;       // ceil(num_k / kb_per_stage)
   uint32_t kb_bytes, kb_tx_bytes;  // smem footprint / TMA bytes of one k-block
+  int b_stages, b_taps;      // halo mode with streamed weights: B ring depth, taps per B stage (1 or 3)
+  uint32_t b_stage_bytes, b_ring_off;
   int halo;                  // 1: 16x8 output tile, one 18x10 halo box per channel block feeds all 9 taps
   int num_b_tiles;           // weight tiles of the resident operand (= taps * sum(cblocks))
   int debug_mode;            // profiling ablations (v2x_set_debug_mode): 1 = no MMA, 2 = no TMA, 3 = no stores
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   constexpr uint32_t LAYOUT = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
   constexpr int TILE_H = HALO ? 16 : kTileH, TILE_W = HALO ? 8 : kTileW;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
+  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 5];
   __shared__ uint32_t tmem_slot;
   __shared__ int4 ktab[kMaxKBlocks];  // per k-block: {channel coord, dw, dh, src | hp << 1}
   __shared__ __align__(16) float s_bias[BN];
@@ -317,6 +319,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   const uint32_t bar_bres = smem_u32(&bars[2 * kMaxStages]);
   const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages + 1]);   // [2]
   const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 3]);  // [2]
+  const uint32_t bar_bfull = smem_u32(&bars[2 * kMaxStages + 5]);   // weight ring of the halo + streamed-B mode
+  const uint32_t bar_bempty = smem_u32(&bars[3 * kMaxStages + 5]);
+  const uint32_t bring_base = smem_base + p.b_ring_off;
+  const bool halo_stream = HALO && !p.b_resident;
 
   // ---- one-time setup ----
   for (int k = threadIdx.x; k < p.num_k; k += kNumThreads) {
@@ -352,6 +358,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_bres, 1);
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(bar_bfull + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, 1);
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 4);  // one arrive per epilogue warp
@@ -380,13 +390,53 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
     __syncwarp();
     const bool no_tma = p.debug_mode == 2;
-    int stage = 0, phase = 0;
+    int stage = 0, phase = 0, bstage = 0, bphase = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, grid_stride);
     for (; ti.tile < p.m_tiles; ti.next(grid_stride)) {
       if (is_gru && gru_unit_absent(p, ti.n_img)) continue;
       const int oh0 = ti.th * TILE_H, ow0 = ti.tw * TILE_W;
       int kidx = 0;
+      if (halo_stream) {
+        // two rings: an A ring of halo tiles (one per channel block) and a weight ring fed tap by tap
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          const int4 e = ktab[kb];
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (elect_one()) {
+            const uint32_t full = bar_full + 8 * stage;
+            if (no_tma) {
+              mbar_arrive(full);
+            } else {
+              mbar_expect_tx(full, p.kb_tx_bytes);
+              const uint32_t sa = ring_base + stage * p.stage_bytes;
+#pragma unroll
+              for (int pl = 0; pl < PLANES; ++pl)
+                tma_load_4d(sa + pl * A_BLOCK, (e.w & 1) ? &tmA1 : &tmA0, full, e.x, ow0 - 1, oh0 - 1, pl * p.n_maps + ti.n_img);
+            }
+          }
+          __syncwarp();
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          for (int t0 = 0; t0 < 9; t0 += p.b_taps) {
+            mbar_wait(bar_bempty + 8 * bstage, bphase ^ 1);
+            if (elect_one()) {
+              const uint32_t bfull = bar_bfull + 8 * bstage;
+              if (no_tma) {
+                mbar_arrive(bfull);
+              } else {
+                mbar_expect_tx(bfull, (uint32_t)p.b_taps * PLANES * (uint32_t)(BN * KC * 2));
+                uint32_t sb = bring_base + bstage * p.b_stage_bytes;
+                for (int t = t0; t < t0 + p.b_taps; ++t)
+#pragma unroll
+                  for (int pl = 0; pl < PLANES; ++pl, sb += B_TILE)
+                    tma_load_2d(sb, &tmB, bfull, (e.y + t * e.z) * KC, pl * p.cout_pad + n0);
+              }
+            }
+            __syncwarp();
+            if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+          }
+        }
+        continue;
+      }
       for (int ks = 0; ks < p.stages_per_tile; ++ks) {
         const int nblk = min(p.kb_per_stage, p.num_k - kidx);
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -425,10 +475,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
     if (p.b_resident) mbar_wait(bar_bres, 0);
     const bool no_mma = p.debug_mode == 1;
-    int stage = 0, phase = 0, it = 0;
+    int stage = 0, phase = 0, it = 0, bstage = 0, bphase = 0;
     // descriptors differ only in the 14-bit start-address field (units of 16 bytes)
     const uint64_t desc_ring = make_smem_desc(ring_base, HALO ? kHaloW * ROW : SBO, LAYOUT);
     const uint64_t desc_bres = make_smem_desc(smem_base, SBO, LAYOUT);
+    const uint64_t desc_bring = make_smem_desc(bring_base, SBO, LAYOUT);
     const uint32_t stage16 = p.stage_bytes >> 4, kb16 = p.kb_bytes >> 4;
     TileIter ti;
     ti.init(p, blockIdx.x, grid_stride);
@@ -440,6 +491,46 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       const uint32_t tmem_d = tmem_base + acc_buf * ACC_STRIDE;
       uint32_t acc = 0;
       int kidx = 0;
+      if (halo_stream) {
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);           // halo tile of this channel block has landed
+          const uint64_t da = desc_ring + (uint64_t)(stage * stage16);
+          for (int t0 = 0; t0 < 9; t0 += p.b_taps) {
+            mbar_wait(bar_bfull + 8 * bstage, bphase);      // weight tiles of the next b_taps taps
+            tc_fence_after();
+            if (elect_one()) {
+              if (no_mma) {
+                mbar_arrive(bar_bempty + 8 * bstage);
+              } else {
+                uint64_t db = desc_bring + (uint64_t)(bstage * (p.b_stage_bytes >> 4));
+                for (int t = t0; t < t0 + p.b_taps; ++t, db += PLANES * (B_TILE >> 4)) {
+                  const int kh = t / 3, kw = t - 3 * kh;
+                  const uint64_t dat = da + (uint64_t)(((kh * kHaloW + kw) * ROW) >> 4);
+#pragma unroll
+                  for (int kk = 0; kk < KSTEPS; ++kk) {
+                    umma_bf16(tmem_d, dat + 2 * kk, db + 2 * kk, idesc, acc);
+                    acc = 1;
+                    if (PLANES == 2) {
+                      umma_bf16(tmem_d, dat + 2 * kk, db + 2 * kk + (B_TILE >> 4), idesc, 1);
+                      umma_bf16(tmem_d, dat + 2 * kk + (A_BLOCK >> 4), db + 2 * kk, idesc, 1);
+                    }
+                  }
+                }
+                umma_commit(bar_bempty + 8 * bstage);
+              }
+            }
+            __syncwarp();
+            acc = 1;
+            if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+          }
+          if (elect_one()) {
+            if (no_mma) mbar_arrive(bar_empty + 8 * stage);
+            else umma_commit(bar_empty + 8 * stage);         // all nine taps of this halo tile are issued
+          }
+          __syncwarp();
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      } else
       for (int ks = 0; ks < p.stages_per_tile; ++ks) {
         const int nblk = min(p.kb_per_stage, p.num_k - kidx);
         mbar_wait(bar_full + 8 * stage, phase);
@@ -898,7 +989,38 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
   d.halo = (d.b_resident && p->taps == 9 && p->stride == 1 && (bn == 32 || bn == 64) && p->h_out % 16 == 0 &&
             p->w_out % 8 == 0 && b_all + 3u * p->planes * a_halo <= budget && !getenv("V2X_NO_HALO"))
                ? 1 : 0;
-  if (d.halo) {
+  d.b_stages = 0; d.b_taps = 1; d.b_stage_bytes = 0; d.b_ring_off = 0;
+  // Halo mode with STREAMED weights (the big layers): the halo tile of a channel block stays in an A ring while its nine
+  // weight tiles flow through a second ring -- activations cross L2->smem once instead of nine times.
+  bool halo_stream = false;
+  if (!d.b_resident && p->taps == 9 && p->stride == 1 && d.kc == 64 && bn >= 64 && p->h_out % 16 == 0 &&
+      p->w_out % 8 == 0 && !getenv("V2X_NO_HALO") && !getenv("V2X_NO_HALO_STREAM")) {
+    const uint32_t a_slot = p->planes * a_halo;
+    const uint32_t b_tap = p->planes * d.b_tile_bytes;
+    for (int taps = 3; taps >= 1 && !halo_stream; taps -= 2) {
+      const int a_slots = 2;
+      const uint32_t left = budget > a_slots * a_slot ? budget - a_slots * a_slot : 0;
+      const int bst = (int)(left / (taps * b_tap));
+      if (bst >= (taps == 3 ? 2 : 3)) {
+        halo_stream = true;
+        d.b_taps = taps;
+        d.b_stages = bst > kMaxStages ? kMaxStages : bst;
+        d.b_stage_bytes = taps * b_tap;
+        d.num_stages = a_slots;
+        d.b_ring_off = a_slots * a_slot;
+      }
+    }
+  }
+  if (halo_stream) {
+    d.halo = 1;
+    d.tiles_w = p->w_out / 8;
+    d.tiles_per_img = d.tiles_w * (p->h_out / 16);
+    d.m_tiles = p->n_maps * d.tiles_per_img;
+    d.num_k = d.cblocks[0] + (d.nsrc > 1 ? d.cblocks[1] : 0);
+    d.b_region_bytes = 0;
+    d.stage_bytes = p->planes * a_halo;
+    d.tx_bytes = p->planes * (uint32_t)(kHaloH * kHaloW) * d.kc * 2u;
+  } else if (d.halo) {
     d.tiles_w = p->w_out / 8;
     d.tiles_per_img = d.tiles_w * (p->h_out / 16);
     d.m_tiles = p->n_maps * d.tiles_per_img;
@@ -918,7 +1040,14 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
   // both the producer and the MMA side) feeds >= ~24 KB of operands; tiny stages starve the tensor core.
   d.kb_bytes = d.stage_bytes;
   d.kb_tx_bytes = d.tx_bytes;
+  size_t smem_total = 0;
+  if (halo_stream) {
+    d.kb_per_stage = 1;
+    d.stages_per_tile = d.num_k;
+    smem_total = (size_t)d.b_ring_off + (size_t)d.b_stages * d.b_stage_bytes + 1024;
+  }
   const uint32_t ring = budget - d.b_region_bytes;
+  if (!halo_stream) {
   int g = d.halo ? (int)((20u * 1024u + d.kb_bytes - 1) / d.kb_bytes) : (int)((28u * 1024u + d.kb_bytes - 1) / d.kb_bytes);
   if (g > d.num_k) g = d.num_k;
   while (g > 1 && ring / ((uint32_t)g * d.kb_bytes) < 4) --g;      // keep the ring >= 4 deep
@@ -931,7 +1060,9 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
   if (stages > kMaxStages) stages = kMaxStages;
   V2X_REQUIRE(stages >= 2, "stage of %u bytes does not fit in shared memory", d.stage_bytes);
   d.num_stages = stages;
-  const size_t smem = (size_t)d.b_region_bytes + (size_t)stages * d.stage_bytes + 1024;
+  smem_total = (size_t)d.b_region_bytes + (size_t)stages * d.stage_bytes + 1024;
+  }
+  const size_t smem = smem_total;
 
   CUtensorMap tmA[2], tmB;
   const int h_in = p->h_out * p->stride, w_in = p->w_out * p->stride;
@@ -969,6 +1100,7 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
   // halo mode needs resident weights, i.e. the small-N layers
   V2X_LAUNCH(32, 1, true) V2X_LAUNCH(32, 2, true) V2X_LAUNCH(32, 4, true)
   V2X_LAUNCH(64, 1, true) V2X_LAUNCH(64, 2, true) V2X_LAUNCH(64, 4, true)
+  V2X_LAUNCH(128, 4, true) V2X_LAUNCH(192, 4, true) V2X_LAUNCH(256, 4, true)
   V2X_LAUNCH(32, 1, false) V2X_LAUNCH(32, 2, false) V2X_LAUNCH(32, 4, false)
   V2X_LAUNCH(48, 4, false)
   V2X_LAUNCH(64, 1, false) V2X_LAUNCH(64, 2, false) V2X_LAUNCH(64, 4, false)
