@@ -295,3 +295,44 @@ def make_seg_scene(batch=1, num_agent=5, seed=0, p=0.03, present=None):
     """(x [A*B,13,256,256] fp32 NCHW as SegModule.py:49 builds it, trans, num_agent_tensor)."""
     bevs, trans, nat = make_scene(batch, num_agent, seed, p=p, present=present)
     return bevs[:, 0].permute(0, 3, 1, 2).contiguous(), trans, nat
+
+
+def plant_detections(sd, cls_ref, per_agent=150, loc_scale=0.05, score=0.7):
+    """Planted-weight variant of a detection state_dict for the NMS / mAP parity runs.
+
+    With seeded random weights no foreground score passes the reference's hard-coded 0.7 filter
+    (postprocess.py:84), so NMS / AP would compare empty sets.  Given the oracle's ``cls`` logits
+    ``[N, H*W*A, 2]`` for the un-planted state, this returns a copy of ``sd`` whose
+      * foreground bias ``classification.conv2.bias[1::2]`` is shifted so that about ``per_agent`` anchors
+        per map score above ``score`` (channel = anchor*2 + class, DetModelBase.py:238-245), and
+      * last regression layer is scaled by ``loc_scale`` and the bias of every cos-residual channel (code 5 of
+        each anchor, channel = anchor*6 + code) is set to 1, so decoded boxes stay near their anchors
+        (w = wa / exp(wp), sin/cos = anchor angle rotated by the residual, detection_util.py:385-398) instead
+        of spanning the whole map or collapsing to a point.
+    Only tensors of the two heads change; backbone / fusion weights are untouched."""
+    sd = OrderedDict((k, v.clone()) for k, v in sd.items())
+    d = (cls_ref[..., 1] - cls_ref[..., 0]).reshape(-1).double()
+    k = min(d.numel() - 1, per_agent * cls_ref.shape[0])
+    q = torch.topk(d, k + 1).values[-1].item()
+    shift = math.log(score / (1.0 - score)) - q
+    sd["classification.conv2.bias"][1::2] += shift
+    sd["regression.box_prediction.3.weight"] *= loc_scale
+    sd["regression.box_prediction.3.bias"] *= loc_scale
+    sd["regression.box_prediction.3.bias"][5::6] = 1.0
+    return sd
+
+
+def make_gt_from_detections(dets, seed=0, keep=0.7, jitter=0.25, extra=3):
+    """Synthetic ground truth for the AP computation: a random ~70% of the oracle's detections, each shifted by a
+    small random offset, plus a few boxes nobody predicts.  dets: list of [m,9]; returns a list of [n,8]."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for d in dets:
+        d = np.asarray(d).reshape(-1, 9)
+        take = rng.rand(d.shape[0]) < keep
+        g = d[take, :8].reshape(-1, 4, 2) + rng.uniform(-jitter, jitter, size=(int(take.sum()), 1, 2))
+        cx, cy = rng.uniform(-28, 28, size=(2, extra))
+        base = np.array([[-1.0, 2.0], [1.0, 2.0], [1.0, -2.0], [-1.0, -2.0]])
+        ex = base[None] + np.stack([cx, cy], axis=-1)[:, None, :]
+        out.append(np.concatenate([g, ex], axis=0).reshape(-1, 8))
+    return out

@@ -30,15 +30,15 @@ def main():
     plan = nets.V2VNetDetPlan(sd, B, 5, planes=planes)
     plan.set_inputs(bevs.cuda(), trans.cuda(), nat.cuda())
     res = {}
-    for mode, tag in ((0, "full"), (1, "noMMA"), (2, "noTMA"), (3, "noST")):
+    for mode, tag in ((0, "full"), (1, "noMMA"), (2, "noTMA"), (3, "noST"), (4, "noEPI"), (0, "full2")):
         lib.v2x_set_debug_mode(mode)
         # launches bake the mode at call time (fill_dev), so just re-run
         res[tag] = time_launches(plan)
     lib.v2x_set_debug_mode(0)
-    print("%-8s %9s %9s %9s %9s   GF      TF/s" % ("layer", "full", "noMMA", "noTMA", "noST"))
+    print("%-8s %9s %9s %9s %9s %9s %9s   GF      TF/s" % ("layer", "full", "noMMA", "noTMA", "noST", "noEPI", "full2"))
     for i, name in enumerate(NAMES[:len(plan.launches)]):
         fl = getattr(plan.launches[i], "flops", 0.0)
-        print("%-8s %9.0f %9.0f %9.0f %9.0f   %6.1f %7.0f" % (name, res["full"][i], res["noMMA"][i], res["noTMA"][i], res["noST"][i], fl / 1e9, fl / (res["full"][i] * 1e-6) / 1e12 if fl else 0))
+        print("%-8s %9.0f %9.0f %9.0f %9.0f %9.0f %9.0f   %6.1f %7.0f" % (name, res["full"][i], res["noMMA"][i], res["noTMA"][i], res["noST"][i], res["noEPI"][i], res["full2"][i], fl / 1e9, fl / (res["full"][i] * 1e-6) / 1e12 if fl else 0))
     print("total", {k: round(sum(v)) for k, v in res.items()})
     json.dump({"names": NAMES, "us": res}, open(os.path.join(ROOT, "gpurun_out", "ablate_B%d_P%d.json" % (B, planes)), "w"))
 

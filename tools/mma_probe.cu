@@ -96,6 +96,16 @@ int main() {
   run<32>("sw64", 1, 4, 512, 32, 32, dres);
   run<32>("sw32", 1, 6, 256, 0, 0, dres);
   run<64>("sw64", 1, 4, 512, 32, 32, dres);
+  // halo-mode addressing of the conv kernel: 8-row groups one halo row (10 px) apart, tap shifts of whole pixel rows
+  for (int n_acc : {1, 2}) {
+    run<32>("halo-sw64", n_acc, 4, 640, 64, 32, dres);
+    run<32>("halo-sw64k", n_acc, 4, 640, 32, 32, dres);
+    run<64>("halo-sw64", n_acc, 4, 640, 64, 32, dres);
+    run<32>("halo-sw32", n_acc, 6, 320, 32, 0, dres);
+    run<64>("halo-sw128", n_acc, 2, 1280, 128, 32, dres);
+    run<128>("halo-sw128", n_acc, 2, 1280, 128, 32, dres);
+    run<192>("halo-sw128", n_acc, 2, 1280, 128, 32, dres);
+  }
   run<32>("sw128-fix", 1, 2, 1024, 0, 0, dres);
   run<192>("sw128-fix", 1, 2, 1024, 0, 0, dres);
   run<256>("sw128-fix", 1, 2, 1024, 0, 0, dres);

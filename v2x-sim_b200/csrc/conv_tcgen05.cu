@@ -53,7 +53,7 @@ struct ConvDev {
   uint32_t b_stage_bytes, b_ring_off;
   int halo;                  // 1: 16x8 output tile, one 18x10 halo box per channel block feeds all 9 taps
   int num_b_tiles;           // weight tiles of the resident operand (= taps * sum(cblocks))
-  int debug_mode;            // profiling ablations (v2x_set_debug_mode): 1 = no MMA, 2 = no TMA, 3 = no stores
+  int debug_mode;            // profiling ablations (v2x_set_debug_mode): 1 = no MMA, 2 = no TMA, 3 = no stores, 4 = no epilogue work
   int cout, cout_pad;
   int epilogue, relu, upsample2x;
   void* out0;
@@ -613,7 +613,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_buf * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
       const bool no_store = dbg_no_store || !valid;
-      if (p.epilogue == V2X_EPI_F32_NCHW) {
+      if (p.debug_mode == 4) {
+        // profiling ablation: barrier handshake only (no tcgen05.ld, no math, no stores)
+      } else if (p.epilogue == V2X_EPI_F32_NCHW) {
 #pragma unroll 1
         for (int c16 = 0; c16 < BN / 16; ++c16) {
           if (n0 + c16 * 16 >= p.cout) break;
@@ -1113,9 +1115,10 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
 }
 
 // Profiling aid: ablate one pipeline role of v2x_conv_fwd (results are then garbage).
-// 0 = normal, 1 = no tcgen05.mma (TMA + epilogue only), 2 = no TMA loads (MMA on stale smem), 3 = no global stores.
+// 0 = normal, 1 = no tcgen05.mma (TMA + epilogue only), 2 = no TMA loads (MMA on stale smem), 3 = no global stores,
+// 4 = epilogue warps only do the accumulator-buffer handshake.
 extern "C" int v2x_set_debug_mode(int mode) {
-  V2X_REQUIRE(mode >= 0 && mode <= 3, "debug mode must be 0..3");
+  V2X_REQUIRE(mode >= 0 && mode <= 4, "debug mode must be 0..4");
   g_debug_mode = mode;
   return V2X_OK;
 }
