@@ -53,6 +53,8 @@ struct ConvDev {
   uint32_t b_stage_bytes, b_ring_off;
   int halo;                  // 1: 16x8 output tile, one 18x10 halo box per channel block feeds all 9 taps
   int num_b_tiles;           // weight tiles of the resident operand (= taps * sum(cblocks))
+  uint32_t epi_off, epi_warp_bytes;  // per-warp output staging buffers (after the operand rings)
+  int ctas_per_sm;           // 2: small-N layers run two co-resident CTAs per SM (two MMA issue streams, eight epilogue warps)
   int debug_mode;            // profiling ablations (v2x_set_debug_mode): 1 = no MMA, 2 = no TMA, 3 = no stores, 4 = no epilogue work
   int cout, cout_pad;
   int epilogue, relu, upsample2x;
@@ -147,6 +149,13 @@ __device__ __forceinline__ void epi_f32_nchw16(const ConvDev& p, int n_img, int 
     if (ch0 + i < p.cout) o[i * cs] = v[i] + bias16[i];
 }
 
+// GRU gate activations on the SFU: sigmoid(x) = 1 / (1 + 2^(-x log2 e)), tanh(x) = 2 sigmoid(2x) - 1; ex2.approx and
+// rcp.approx are accurate to ~2 ulp, i.e. ~1e-6 absolute on gates in (-1, 1) -- far inside the 1e-3 contract -- and an
+// order of magnitude fewer instructions than the IEEE division + tanhf they replace (the GRU epilogue was the
+// bottleneck of the three ConvGRU launches).
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, __fdividef(1.f, 1.f + __expf(-2.f * x)), -1.f); }
+
 // GRU gates for 16 channels [c0, c0+16) of one pixel.  bias_r16 points at the bias of the r gate of channel
 // c0 inside the [r(64) | z(64) | n(64)] block (z at +64, n at +128); bhn16 at b_hh_n of channel c0.
 __device__ __forceinline__ void epi_gru16(const ConvDev& p, int n_img, int oh, int ow, int c0, const float* r,
@@ -156,9 +165,9 @@ __device__ __forceinline__ void epi_gru16(const ConvDev& p, int n_img, int oh, i
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float ar = add_r16 ? add_r16[i] : 0.f, az = add_r16 ? add_r16[64 + i] : 0.f, an = add_r16 ? add_r16[128 + i] : 0.f;
-    const float rr = 1.f / (1.f + __expf(-(r[i] + bias_r16[i] + ar)));
-    const float zz = 1.f / (1.f + __expf(-(z[i] + bias_r16[64 + i] + az)));
-    const float nv = tanhf(nn[i] + bias_r16[128 + i] + an + rr * bhn16[i]);
+    const float rr = fast_sigmoid(r[i] + bias_r16[i] + ar);
+    const float zz = fast_sigmoid(z[i] + bias_r16[64 + i] + az);
+    const float nv = fast_tanh(nn[i] + bias_r16[128 + i] + an + rr * bhn16[i]);
     h[i] = (1.f - zz) * nv;
   }
   store_act16(p, n_img, oh, ow, c0, h);
@@ -200,34 +209,75 @@ __device__ __forceinline__ void pack16(const float* v, uint32_t* hi, uint32_t* l
   }
 }
 
-// output addressing of one pixel, computed once per tile
-struct OutPix {
-  __nv_bfloat16* p00;        // first store position (channel 0 of this CTA's N tile)
-  long long row_stride;      // elements between vertically adjacent output pixels (upsample only)
+// ---------------------------------------------------------------------------------------------
+// Coalesced output through a per-warp shared-memory staging buffer.
+//
+// TMEM hands every epilogue thread one output PIXEL (a row of the accumulator), so a direct store has the 32 lanes
+// of a warp writing 16 bytes each at a stride of one pixel (64..192 bytes): 32 separate L2 requests per instruction,
+// which caps the store rate near 16 B/clk/SM and made every write-heavy layer (upsampling decoder layers, heads)
+// store-bound (measured with the no-store ablation).  Instead each thread parks a 32-column chunk of its pixel in
+// shared memory (XOR-swizzled / padded rows: conflict-free both ways), and the warp writes the chunk back out with
+// consecutive lanes on consecutive 16-byte units, i.e. whole 64..128-byte runs per pixel and 512-byte runs where
+// pixels are adjacent in memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+constexpr uint32_t kStageActPlane = 32u * 64u;    // bf16 chunk: 32 pixels x 32 channels
+constexpr uint32_t kStageF32Row = 128u + 16u;     // fp32 chunk row: 32 channels + 16 bytes of padding (bank spread)
+constexpr uint32_t kStageF32 = 32u * kStageF32Row;
+
+// park 16 bf16 channels (two 16-byte units: 2*half, 2*half+1) of this lane's pixel
+template <int PLANES>
+__device__ __forceinline__ void stage_act16(uint32_t stage, int lane, int half, const uint32_t* hi, const uint32_t* lo) {
+  const uint32_t row = stage + (uint32_t)lane * 64u;
+  const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+  const uint32_t u0 = (((uint32_t)(2 * half)) ^ sw) << 4, u1 = (((uint32_t)(2 * half + 1)) ^ sw) << 4;
+  st_shared_v4(row + u0, hi[0], hi[1], hi[2], hi[3]);
+  st_shared_v4(row + u1, hi[4], hi[5], hi[6], hi[7]);
+  if (PLANES == 2) {
+    st_shared_v4(row + kStageActPlane + u0, lo[0], lo[1], lo[2], lo[3]);
+    st_shared_v4(row + kStageActPlane + u1, lo[4], lo[5], lo[6], lo[7]);
+  }
+}
+
+// per-tile output addressing of the staged bf16 path
+struct ActOut {
+  __nv_bfloat16* tile_p;     // tile origin + channel window of this CTA's N tile
+  long long row_stride;      // elements between vertically adjacent output pixels
   long long plane_stride;
-  int c_total;
-  int up;
+  int c_total, up;
+  int eo[4];                 // element offsets (from the tile origin) of the four pixels this lane writes back
+  uint32_t vmask;            // bit j: pixel j lies inside the map
 };
 
+// write the staged chunk back: lane -> unit (lane & 3) of pixels (lane >> 2) + 8j; nunits = valid 16-byte units per pixel
 template <int PLANES>
-__device__ __forceinline__ void store16(const OutPix& o, int c, const uint32_t* hi, const uint32_t* lo) {
-  const uint4 h0 = make_uint4(hi[0], hi[1], hi[2], hi[3]), h1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-  uint4 l0, l1;
-  if (PLANES == 2) { l0 = make_uint4(lo[0], lo[1], lo[2], lo[3]); l1 = make_uint4(lo[4], lo[5], lo[6], lo[7]); }
-  if (o.up == 1) {
-    uint4* d = reinterpret_cast<uint4*>(o.p00 + c);
-    d[0] = h0; d[1] = h1;
-    if (PLANES == 2) { uint4* l = reinterpret_cast<uint4*>(o.p00 + o.plane_stride + c); l[0] = l0; l[1] = l1; }
-  } else {
+__device__ __forceinline__ void flush_act(uint32_t stage, int lane, int nunits, int ch_off, const ActOut& o) {
+  const int c = lane & 3;
+  if (c >= nunits) return;
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
+  for (int j = 0; j < 4; ++j) {
+    if (!((o.vmask >> j) & 1u)) continue;
+    const int pix = (lane >> 2) + 8 * j;
+    const uint32_t a = stage + (uint32_t)pix * 64u + ((((uint32_t)c) ^ ((uint32_t)(pix >> 1) & 3u)) << 4);
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        __nv_bfloat16* q = o.p00 + dy * o.row_stride + dx * o.c_total + c;
-        uint4* d = reinterpret_cast<uint4*>(q);
-        d[0] = h0; d[1] = h1;
-        if (PLANES == 2) { uint4* l = reinterpret_cast<uint4*>(q + o.plane_stride); l[0] = l0; l[1] = l1; }
+    for (int pl = 0; pl < PLANES; ++pl) {
+      const uint4 v = ld_shared_v4(a + pl * kStageActPlane);
+      __nv_bfloat16* dst = o.tile_p + pl * o.plane_stride + o.eo[j] + ch_off + c * 8;
+      *reinterpret_cast<uint4*>(dst) = v;
+      if (o.up == 2) {
+        *reinterpret_cast<uint4*>(dst + o.c_total) = v;
+        *reinterpret_cast<uint4*>(dst + o.row_stride) = v;
+        *reinterpret_cast<uint4*>(dst + o.row_stride + o.c_total) = v;
       }
+    }
   }
 }
 
@@ -288,7 +338,7 @@ struct TileIter {
 constexpr int kHaloH = 18, kHaloW = 10;
 
 template <int BN, int PLANES, int KSTEPS, bool HALO>
-__global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                  const __grid_constant__ CUtensorMap tmA1,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const ConvDev p) {
@@ -598,11 +648,27 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     const bool dbg_no_store = p.debug_mode == 3;
     const int up = p.upsample2x ? 2 : 1;
     const int Hs = p.h_out * up, Ws = p.w_out * up;
+    const uint32_t stage = smem_base + p.epi_off + (uint32_t)(warp - 2) * p.epi_warp_bytes;  // this warp's staging buffer
+    // write-back roles (kernel constants): bf16 chunks -> pixels (lane >> 2) + 8j; fp32 chunks -> pixels (lane >> 3) + 4j
+    ActOut o;
+    o.up = up;
+    o.c_total = p.out_c_total;
+    o.row_stride = (long long)Ws * p.out_c_total;
+    o.plane_stride = p.out_plane_stride;
+    int wb_h[4], wb_w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int prow = quad * 32 + (lane >> 2) + 8 * j;
+      wb_h[j] = HALO ? (prow >> 3) : (prow >> 4);
+      wb_w[j] = HALO ? (prow & 7) : (prow & 15);
+      o.eo[j] = (wb_h[j] * up * Ws + wb_w[j] * up) * p.out_c_total;
+    }
     int it = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, grid_stride);
     for (; ti.tile < p.m_tiles; ti.next(grid_stride)) {
-      const int oh = ti.th * TILE_H + r_h, ow = ti.tw * TILE_W + r_w;
+      const int oh0 = ti.th * TILE_H, ow0 = ti.tw * TILE_W;
+      const int oh = oh0 + r_h, ow = ow0 + r_w;
       const bool valid = oh < p.h_out && ow < p.w_out;   // partial tiles at the map border
       if (is_gru && gru_unit_absent(p, ti.n_img)) {
         if (valid) copy_passthrough(p, ti.n_img, oh, ow, blockIdx.y * 64, 64);
@@ -612,7 +678,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       mbar_wait(bar_tfull + 8 * acc_buf, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_buf * ACC_STRIDE + ((uint32_t)(quad * 32) << 16);
-      const bool no_store = dbg_no_store || !valid;
       if (p.debug_mode == 4) {
         // profiling ablation: barrier handshake only (no tcgen05.ld, no math, no stores)
       } else if (p.epilogue == V2X_EPI_F32_NCHW) {
@@ -625,6 +690,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           if (valid && !dbg_no_store) epi_f32_nchw16(p, ti.n_img, oh, ow, n0 + c16 * 16, v0, s_bias + c16 * 16);
         }
       } else if (p.epilogue == V2X_EPI_F32_SPLIT) {
+        // fp32 NHWC heads / gate pre-activations: 32-column chunks staged as [pixel][32 floats (+pad)]
+        const long long tile_pix = ((long long)ti.n_img * p.h_out + oh0) * p.w_out + ow0;
+        float* const o0 = reinterpret_cast<float*>(p.out0);
+        float* const o1 = reinterpret_cast<float*>(p.out1);
+        const int c1 = p.cout - p.split;
 #pragma unroll 1
         for (int c32 = 0; c32 < (BN + 31) / 32; ++c32) {
           const int ch0 = n0 + c32 * 32;
@@ -635,23 +705,64 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           if (two) tmem_ld16_async(taddr + c32 * 32 + 16, v1);
           tmem_ld_wait16(v0);
           if (two) tmem_ld_wait16(v1);
-          if (valid) epi_f32_split16(p, ti.n_img, oh, ow, ch0, v0, s_bias + c32 * 32);
-          if (two && valid) epi_f32_split16(p, ti.n_img, oh, ow, ch0 + 16, v1, s_bias + c32 * 32 + 16);
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c32 * 32);
+          const uint32_t srow = stage + (uint32_t)lane * kStageF32Row;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = b4[q];
+            st_shared_v4(srow + 16 * q, __float_as_uint(v0[4 * q] + b.x), __float_as_uint(v0[4 * q + 1] + b.y),
+                         __float_as_uint(v0[4 * q + 2] + b.z), __float_as_uint(v0[4 * q + 3] + b.w));
+          }
+          if (two) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = b4[4 + q];
+              st_shared_v4(srow + 64 + 16 * q, __float_as_uint(v1[4 * q] + b.x), __float_as_uint(v1[4 * q + 1] + b.y),
+                           __float_as_uint(v1[4 * q + 2] + b.z), __float_as_uint(v1[4 * q + 3] + b.w));
+            }
+          }
+          __syncwarp();
+          const int u = lane & 7;
+          const int ch = ch0 + 4 * u;
+          if (u < (two ? 8 : 4) && ch < p.cout && !dbg_no_store) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int pix = (lane >> 3) + 4 * j;
+              const int prow = quad * 32 + pix;
+              const int ph = HALO ? (prow >> 3) : (prow >> 4), pw = HALO ? (prow & 7) : (prow & 15);
+              if (oh0 + ph < p.h_out && ow0 + pw < p.w_out) {
+                const uint4 v = ld_shared_v4(stage + (uint32_t)pix * kStageF32Row + 16u * u);
+                const long long pi = tile_pix + (long long)ph * p.w_out + pw;
+                float* dst = ch < p.split ? o0 + pi * p.split + ch : o1 + pi * c1 + (ch - p.split);
+                *reinterpret_cast<uint4*>(dst) = v;
+              }
+            }
+          }
+          __syncwarp();
         }
       } else {
-        OutPix o;
-        o.up = up;
-        o.c_total = p.out_c_total;
-        o.row_stride = (long long)Ws * p.out_c_total;
-        o.plane_stride = p.out_plane_stride;
-        o.p00 = reinterpret_cast<__nv_bfloat16*>(p.out0) +
-                (((long long)ti.n_img * Hs + oh * up) * Ws + ow * up) * p.out_c_total + p.out_c_off +
-                (is_gru ? blockIdx.y * 64 : n0);
+        o.tile_p = reinterpret_cast<__nv_bfloat16*>(p.out0) +
+                   (((long long)ti.n_img * Hs + oh0 * up) * Ws + ow0 * up) * p.out_c_total + p.out_c_off +
+                   (is_gru ? blockIdx.y * 64 : n0);
+        o.vmask = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (oh0 + wb_h[j] < p.h_out && ow0 + wb_w[j] < p.w_out && !dbg_no_store) o.vmask |= 1u << j;
         if (is_gru) {
           if constexpr (BN == 192) {
 #pragma unroll 1
             for (int c16 = 0; c16 < 4; ++c16) {
               float r[16], z[16], nn[16];
+              // round-invariant half of the pre-activations (W_ih[:, mean] * mean + b): issue the global loads first so
+              // their latency overlaps the TMEM reads
+              float4 gr[4], gz[4], gn[4];
+              const bool has_add = p.gru_add != nullptr && valid;
+              if (has_add) {
+                const float4* g = reinterpret_cast<const float4*>(
+                    p.gru_add + (((long long)ti.n_img * p.h_out + oh) * p.w_out + ow) * p.cout + n0 + c16 * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { gr[q] = __ldg(g + q); gz[q] = __ldg(g + 16 + q); gn[q] = __ldg(g + 32 + q); }
+              }
               tmem_ld16_async(taddr + c16 * 16, r);
               tmem_ld16_async(taddr + 64 + c16 * 16, z);
               tmem_ld16_async(taddr + 128 + c16 * 16, nn);
@@ -659,27 +770,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
               tmem_ld_wait16(z);
               tmem_ld_wait16(nn);
               const float* br = s_bias + c16 * 16;
-              if (p.gru_add != nullptr && valid) {  // round-invariant half of the pre-activations (W_ih[:, mean] * mean + b)
-                const float4* g = reinterpret_cast<const float4*>(
-                    p.gru_add + (((long long)ti.n_img * p.h_out + oh) * p.w_out + ow) * p.cout + n0 + c16 * 16);
+              if (has_add) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  const float4 gr = __ldg(g + q), gz = __ldg(g + 16 + q), gn = __ldg(g + 32 + q);
-                  r[4 * q] += gr.x; r[4 * q + 1] += gr.y; r[4 * q + 2] += gr.z; r[4 * q + 3] += gr.w;
-                  z[4 * q] += gz.x; z[4 * q + 1] += gz.y; z[4 * q + 2] += gz.z; z[4 * q + 3] += gz.w;
-                  nn[4 * q] += gn.x; nn[4 * q + 1] += gn.y; nn[4 * q + 2] += gn.z; nn[4 * q + 3] += gn.w;
+                  r[4 * q] += gr[q].x; r[4 * q + 1] += gr[q].y; r[4 * q + 2] += gr[q].z; r[4 * q + 3] += gr[q].w;
+                  z[4 * q] += gz[q].x; z[4 * q + 1] += gz[q].y; z[4 * q + 2] += gz[q].z; z[4 * q + 3] += gz[q].w;
+                  nn[4 * q] += gn[q].x; nn[4 * q + 1] += gn[q].y; nn[4 * q + 2] += gn[q].z; nn[4 * q + 3] += gn[q].w;
                 }
               }
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float rr = 1.f / (1.f + __expf(-(r[i] + br[i])));
-                const float zz = 1.f / (1.f + __expf(-(z[i] + br[64 + i])));
-                const float nv = tanhf(nn[i] + br[128 + i] + rr * s_bhn[c16 * 16 + i]);
+                const float rr = fast_sigmoid(r[i] + br[i]);
+                const float zz = fast_sigmoid(z[i] + br[64 + i]);
+                const float nv = fast_tanh(nn[i] + br[128 + i] + rr * s_bhn[c16 * 16 + i]);
                 r[i] = (1.f - zz) * nv;
               }
               uint32_t hi[8], lo[8];
               pack16<PLANES>(r, hi, lo);
-              if (!no_store) store16<PLANES>(o, c16 * 16, hi, lo);
+              stage_act16<PLANES>(stage, lane, c16 & 1, hi, lo);
+              if (c16 & 1) {
+                __syncwarp();
+                flush_act<PLANES>(stage, lane, 4, (c16 - 1) * 16, o);
+                __syncwarp();
+              }
             }
           }
         } else {
@@ -705,7 +818,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
               for (int i = 0; i < 16; ++i) v0[i] = fmaxf(v0[i], 0.f);
             }
             pack16<PLANES>(v0, hi, lo);
-            if (!no_store) store16<PLANES>(o, c32 * 32, hi, lo);
+            stage_act16<PLANES>(stage, lane, 0, hi, lo);
             if (two) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -717,8 +830,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
                 for (int i = 0; i < 16; ++i) v1[i] = fmaxf(v1[i], 0.f);
               }
               pack16<PLANES>(v1, hi, lo);
-              if (!no_store) store16<PLANES>(o, c32 * 32 + 16, hi, lo);
+              stage_act16<PLANES>(stage, lane, 1, hi, lo);
             }
+            __syncwarp();
+            flush_act<PLANES>(stage, lane, two ? 4 : 2, c32 * 32, o);
+            __syncwarp();
           }
         }
       }
@@ -951,10 +1067,12 @@ static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap&
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN, PLANES, KSTEPS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (attr_err == cudaSuccess && BN <= 64)
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN, PLANES, KSTEPS, HALO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
   // persistent grid: one CTA per SM, split between the N tiles (every CTA keeps one N tile)
-  int ctas_x = sm_count() / d.n_tiles;
+  int ctas_x = sm_count() * d.ctas_per_sm / d.n_tiles;
   if (ctas_x < 1) ctas_x = 1;
   if (ctas_x > d.m_tiles) ctas_x = d.m_tiles;
   // balance: no CTA should walk more M tiles than ceil(m_tiles / ctas_x); shrink the grid to the
@@ -971,20 +1089,21 @@ static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap&
 
 using namespace v2x;
 
-extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
-  ConvDev d;
-  int rc = fill_dev(p, d);
-  if (rc) return rc;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+// Shared-memory plan of one launch for a dynamic-smem budget (bytes): resident vs streamed weights, halo mode,
+// k-blocks per stage and ring depth.  Fails (V2X_ERR_UNSUPPORTED via V2X_REQUIRE) if not even two stages fit.
+static int plan_smem(const v2x_conv_params* p, ConvDev& d, uint32_t budget, size_t* smem_out) {
   const int bn = p->block_n;
-
+  // output staging of the four epilogue warps comes off the top of the budget
+  d.epi_warp_bytes = p->epilogue == V2X_EPI_F32_SPLIT ? kStageF32
+                     : p->epilogue == V2X_EPI_F32_NCHW ? 0u : (uint32_t)p->planes * kStageActPlane;
+  const uint32_t epi_bytes = 4u * d.epi_warp_bytes;
+  budget -= epi_bytes;
   // Shared-memory plan.  Small weight operands (all of [block_n x K], e.g. the C=32 layers at 256x256)
   // stay resident for the CTA's lifetime so only activations stream; otherwise weights ride in the
   // stage ring next to their A tile.  The ring takes whatever is left, up to kMaxStages deep.
   d.num_b_tiles = d.num_k;
   const uint32_t b_all = (uint32_t)d.num_b_tiles * p->planes * d.b_tile_bytes;
   const uint32_t a_stage = p->planes * d.a_tile_bytes;
-  const uint32_t budget = (uint32_t)kSmemLimit - 1024u;
   d.b_resident = (b_all <= 96u * 1024u && b_all + 4u * a_stage <= budget) ? 1 : 0;
   // Halo mode: 3x3 stride-1 convs with resident weights read all nine taps out of one 18x10-pixel box.
   const uint32_t a_halo = ((uint32_t)(kHaloH * kHaloW) * d.kc * 2u + 1023u) & ~1023u;
@@ -1064,7 +1183,39 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
   d.num_stages = stages;
   smem_total = (size_t)d.b_region_bytes + (size_t)stages * d.stage_bytes + 1024;
   }
-  const size_t smem = smem_total;
+  d.epi_off = (uint32_t)(smem_total - 1024);
+  *smem_out = smem_total + epi_bytes;
+  return V2X_OK;
+}
+
+extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
+  ConvDev d;
+  int rc = fill_dev(p, d);
+  if (rc) return rc;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int bn = p->block_n;
+
+  // Small-N layers (a tile is only a few hundred cycles of tensor work, so the single MMA-issuing thread and the four
+  // epilogue warps of one CTA are the bottleneck -- measured: the MMA warp retires ~210 dependent instructions per tile)
+  // run TWO co-resident CTAs per SM when the operands fit in half the shared memory.
+  size_t smem = 0;
+  d.ctas_per_sm = 1;
+  bool planned = false;
+  if (bn <= 64 && !getenv("V2X_ONE_CTA")) {
+    ConvDev d2 = d;
+    d2.ctas_per_sm = 2;
+    size_t smem2 = 0;
+    const uint32_t budget2 = 106u * 1024u;  // 2 x (106 KB dynamic + ~5 KB static + 1 KB reserved) <= 228 KB per SM
+    if (plan_smem(p, d2, budget2, &smem2) == V2X_OK && d2.b_resident && d2.num_stages >= (d2.halo ? 3 : 4)) {
+      d = d2;
+      smem = smem2;
+      planned = true;
+    }
+  }
+  if (!planned) {
+    rc = plan_smem(p, d, (uint32_t)kSmemLimit - 1024u, &smem);
+    if (rc) return rc;
+  }
 
   CUtensorMap tmA[2], tmB;
   const int h_in = p->h_out * p->stride, w_in = p->w_out * p->stride;
