@@ -23,6 +23,7 @@
 // Reference call sites replaced: see include/v2x_b200.h (v2x_conv_fwd).
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
     const uint64_t desc_ring = make_smem_desc(ring_base, HALO ? kHaloW * ROW : SBO, LAYOUT);
     const uint64_t desc_bres = make_smem_desc(smem_base, SBO, LAYOUT);
     const uint64_t desc_bring = make_smem_desc(bring_base, SBO, LAYOUT);
-    const uint32_t stage16 = p.stage_bytes >> 4, kb16 = p.kb_bytes >> 4;
+    const uint32_t stage16 = p.stage_bytes >> 4, kb16 = p.kb_bytes >> 4, bstage16 = p.b_stage_bytes >> 4;
     TileIter ti;
     ti.init(p, blockIdx.x, grid_stride);
     for (; ti.tile < p.m_tiles; ti.next(grid_stride)) {
@@ -542,37 +543,47 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
       uint32_t acc = 0;
       int kidx = 0;
       if (halo_stream) {
+        // Straight-line issue code: the tap loop is unrolled for both weight-ring groupings so every descriptor offset is
+        // an immediate (with runtime tap bounds the warp spent ~12 instructions per MMA on t/3, t%3 and 64-bit address
+        // arithmetic and was issue-bound on the N<=128 layers -- profiles/r01_v8).
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);           // halo tile of this channel block has landed
           const uint64_t da = desc_ring + (uint64_t)(stage * stage16);
-          for (int t0 = 0; t0 < 9; t0 += p.b_taps) {
-            mbar_wait(bar_bfull + 8 * bstage, bphase);      // weight tiles of the next b_taps taps
-            tc_fence_after();
-            if (elect_one()) {
-              if (no_mma) {
-                mbar_arrive(bar_bempty + 8 * bstage);
-              } else {
-                uint64_t db = desc_bring + (uint64_t)(bstage * (p.b_stage_bytes >> 4));
-                for (int t = t0; t < t0 + p.b_taps; ++t, db += PLANES * (B_TILE >> 4)) {
-                  const int kh = t / 3, kw = t - 3 * kh;
-                  const uint64_t dat = da + (uint64_t)(((kh * kHaloW + kw) * ROW) >> 4);
+          auto issue_taps = [&](auto B_TAPS_C) {
+            constexpr int B_TAPS = decltype(B_TAPS_C)::value;
 #pragma unroll
-                  for (int kk = 0; kk < KSTEPS; ++kk) {
-                    umma_bf16(tmem_d, dat + 2 * kk, db + 2 * kk, idesc, acc);
-                    acc = 1;
-                    if (PLANES == 2) {
-                      umma_bf16(tmem_d, dat + 2 * kk, db + 2 * kk + (B_TILE >> 4), idesc, 1);
-                      umma_bf16(tmem_d, dat + 2 * kk + (A_BLOCK >> 4), db + 2 * kk, idesc, 1);
+            for (int t0 = 0; t0 < 9; t0 += B_TAPS) {
+              mbar_wait(bar_bfull + 8 * bstage, bphase);    // weight tiles of the next B_TAPS taps
+              tc_fence_after();
+              if (elect_one()) {
+                if (no_mma) {
+                  mbar_arrive(bar_bempty + 8 * bstage);
+                } else {
+                  const uint64_t db = desc_bring + (uint64_t)(bstage * bstage16);
+#pragma unroll
+                  for (int tt = 0; tt < B_TAPS; ++tt) {
+                    const int t = t0 + tt;
+                    const uint32_t a_off = (uint32_t)((((t / 3) * kHaloW + (t % 3)) * ROW) >> 4);
+                    const uint32_t b_off = (uint32_t)(tt * PLANES * (B_TILE >> 4));
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk) {
+                      umma_bf16(tmem_d, da + (a_off + 2 * kk), db + (b_off + 2 * kk), idesc, (t | kk) == 0 ? acc : 1u);
+                      if (PLANES == 2) {
+                        umma_bf16(tmem_d, da + (a_off + 2 * kk), db + (b_off + 2 * kk + (B_TILE >> 4)), idesc, 1);
+                        umma_bf16(tmem_d, da + (a_off + 2 * kk + (A_BLOCK >> 4)), db + (b_off + 2 * kk), idesc, 1);
+                      }
                     }
                   }
+                  umma_commit(bar_bempty + 8 * bstage);
                 }
-                umma_commit(bar_bempty + 8 * bstage);
               }
+              __syncwarp();
+              if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
             }
-            __syncwarp();
-            acc = 1;
-            if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
-          }
+          };
+          if (p.b_taps == 3) issue_taps(std::integral_constant<int, 3>{});
+          else issue_taps(std::integral_constant<int, 1>{});
+          acc = 1;
           if (elect_one()) {
             if (no_mma) mbar_arrive(bar_empty + 8 * stage);
             else umma_commit(bar_empty + 8 * stage);         // all nine taps of this halo tile are issued
