@@ -45,6 +45,10 @@ int v2x_device_ok(void);
 #define V2X_EPI_F32_SPLIT 1 /* y = acc + bias -> fp32 NHWC, channels [0,split) to out0, [split,cout) to out1     */
 #define V2X_EPI_F32_NCHW 3  /* y = acc + bias -> fp32 NCHW [N][cout][H][W] in out0 (segmentation logits)                       */
 #define V2X_EPI_GRU 2      /* zero-hidden ConvGRU gate epilogue, see v2x_conv_params                           */
+#define V2X_EPI_TAIL_F32_SPLIT 4 /* t = relu(acc + bias) (bf16 planes, kept in shared memory, never stored);
+                                    y = tail_weights * t + tail_bias -> fp32 NHWC split like V2X_EPI_F32_SPLIT:
+                                    the detection heads' conv3x3+BN+ReLU -> conv1x1 pair in ONE launch
+                                    (DetModelBase.py:283-296, 319-329); needs cout == block_n == 64              */
 
 /*
  * One fused convolution launch: implicit GEMM on tcgen05 tensor cores, A tiles (8x16 output
@@ -94,6 +98,12 @@ typedef struct v2x_conv_params {
      half conv(mean, W_ih[:, C:]) + bias, computed once per frame by an EPI_F32_SPLIT launch (split == cout) so the three
      GNN rounds only convolve the changing half (V2VNet.py:99: cat([h_i, mean]); the mean never changes). */
   const float* gru_add;
+  /* V2X_EPI_TAIL_F32_SPLIT: the fused 1x1 conv. tail_weights = packed [planes][tail_cout_pad][cout] bf16 (K-major, as
+     v2x_pack_conv_weights writes a taps == 1 operand), tail_bias fp32 [tail_cout_pad]; channels [0,split) of the tail
+     output go to out0 (row stride split), [split,tail_cout) to out1 (row stride tail_cout - split). */
+  const void* tail_weights;
+  const float* tail_bias;
+  int32_t tail_cout, tail_cout_pad;
 } v2x_conv_params;
 
 int v2x_conv_fwd(const v2x_conv_params* p, void* stream);

@@ -27,10 +27,20 @@ def test_library_exports_every_declared_symbol():
     assert lib.v2x_version() >= 1
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / field offsets of the ctypes mirror equal what a C compiler makes of include/v2x_b200.h."""
+    import subprocess
     from v2x_b200 import _lib
-    # 2 ptr + 2 i32 + 6 i32 + 2 ptr + 6 i32 + 2 ptr + 3 i32 (+pad) + 3 ptr + 2 i32 + 4 i32
-    assert ctypes.sizeof(_lib.ConvParams) == 176
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "v2x_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu\\n", sizeof(v2x_conv_params), offsetof(v2x_conv_params, weights),'
+                   ' offsetof(v2x_conv_params, gru_add), offsetof(v2x_conv_params, tail_cout));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)])
+    size, o_w, o_g, o_t = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    P = _lib.ConvParams
+    assert (ctypes.sizeof(P), P.weights.offset, P.gru_add.offset, P.tail_cout.offset) == (size, o_w, o_g, o_t)
 
 
 def test_argument_validation_is_loud():

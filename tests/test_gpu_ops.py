@@ -163,6 +163,45 @@ def test_heads(impl, planes):
 
 
 @pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("shape", [(2, 32, 64), (1, 16, 32), (1, 24, 40)], ids=["halo", "small", "partial"])
+def test_heads_fused_tail(shape, planes):
+    """EPI_TAIL_F32_SPLIT: conv3x3+BN+ReLU -> 1x1 in one launch (the 64-channel intermediate stays in shared memory)
+    must reproduce the two-launch form bit for bit (same bf16 rounding of the intermediate, same K order) and the
+    oracle within tolerance; covers the halo tile, the plain tile and partial tiles."""
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    from v2x_b200.ops import EPI_F32_SPLIT, EPI_TAIL_F32_SPLIT, ConvLaunch
+    dev = _dev()
+    n, h, w = shape
+    sd = {}
+    synth.heads_state(sd, synth._Gen(5))
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((n, 32, h, w), generator=g).relu()
+    ref = restate.heads(x, sd)
+    h1, h2, n_cls = ops.pack_heads(
+        sd["classification.conv1.weight"], sd["classification.conv1.bias"],
+        tuple(sd["classification.bn1." + k] for k in ("weight", "bias", "running_mean", "running_var")),
+        sd["regression.box_prediction.0.weight"], sd["regression.box_prediction.0.bias"],
+        tuple(sd["regression.box_prediction.1." + k] for k in ("weight", "bias", "running_mean", "running_var")),
+        sd["classification.conv2.weight"], sd["classification.conv2.bias"],
+        sd["regression.box_prediction.3.weight"], sd["regression.box_prediction.3.bias"], planes=planes, device=dev)
+    xa = to_act(x, planes, dev)
+    t = ops.conv(h1, [xa])
+    cls2 = torch.empty((n, h, w, 12), dtype=torch.float32, device=dev)
+    loc2 = torch.empty((n, h, w, 36), dtype=torch.float32, device=dev)
+    ConvLaunch(h2, [t], epilogue=EPI_F32_SPLIT, relu=False, out0=cls2, out1=loc2, split=n_cls, block_n=48)()
+    cls = torch.full((n, h, w, 12), float("nan"), dtype=torch.float32, device=dev)
+    loc = torch.full((n, h, w, 36), float("nan"), dtype=torch.float32, device=dev)
+    ConvLaunch(h1, [xa], epilogue=EPI_TAIL_F32_SPLIT, relu=True, out0=cls, out1=loc, split=n_cls, block_n=64, tail=h2)()
+    torch.cuda.synchronize()
+    e1 = rel_err(cls.view(n, -1, 2), ref["cls"])
+    e2 = rel_err(loc.view(n, h, w, 6, 1, 6), ref["loc"])
+    print("fused heads planes=%d cls=%.3e loc=%.3e" % (planes, e1, e2))
+    assert e1 < TOL[planes] and e2 < TOL[planes]
+    assert torch.equal(cls, cls2) and torch.equal(loc, loc2)
+
+
+@pytest.mark.parametrize("planes", [2, 1])
 def test_warp_mean_golden_and_oracle(planes, golden_dir):
     """Cross-agent warp + mean against (a) the live-reference fixture and (b) the oracle GNN mean."""
     from oracle import restate, synth

@@ -46,6 +46,44 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
   }
 }
 
+// 13-channel fp32 NHWC -> 16-channel bf16 planes.  A block takes kPackPix consecutive pixels: the 13*kPackPix floats are
+// read as coalesced float4s into shared memory (the per-pixel stride of 52 bytes defeats direct vector loads), then
+// every thread emits 16-byte output units (pixel, half) -- fully coalesced both ways.
+constexpr int kPackPix = 512;
+__global__ void __launch_bounds__(256) pack_input13_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           long long n_pixels, int planes) {
+  __shared__ __align__(16) float s[kPackPix * 13];
+  const long long pix0 = (long long)blockIdx.x * kPackPix;
+  const float4* src = reinterpret_cast<const float4*>(x + pix0 * 13);
+#pragma unroll
+  for (int k = 0; k < (kPackPix * 13 / 4 + 255) / 256; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    if (i < kPackPix * 13 / 4) reinterpret_cast<float4*>(s)[i] = __ldg(src + i);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kPackPix * 2 / 256; ++k) {
+    const int u = threadIdx.x + 256 * k;
+    const int pix = u >> 1, g = u & 1;
+    const float* sp = s + pix * 13 + g * 8;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = g * 8 + 2 * i;
+      const float v0 = c0 < 13 ? sp[2 * i] : 0.f;
+      const float v1 = c0 + 1 < 13 ? sp[2 * i + 1] : 0.f;
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v0, h0, l0);
+      split_bf16(v1, h1, l1);
+      hi[i] = pack_bf16x2(h0, h1);
+      lo[i] = pack_bf16x2(l0, l1);
+    }
+    __nv_bfloat16* dst = out + (pix0 + pix) * 16 + g * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (planes == 2) *reinterpret_cast<uint4*>(dst + n_pixels * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight packing: one thread per (co, ci, tap)
 // ---------------------------------------------------------------------------------------------
@@ -146,21 +184,35 @@ __global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
         const int x0 = (int)fx, y0 = (int)fy;
         const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
         const long long src_map = (long long)batch * j + b;
+        // all four taps' loads are issued before any is consumed (one memory round trip per source instead of four)
+        float wgt[4];
+        bool inb[4];
+        const __nv_bfloat16* sp[4];
+        bool any = false;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
-          const float wgt = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
-          if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;  // zeros padding (warp-uniform branch)
-          const __nv_bfloat16* sp = x + ((src_map * H + yy) * W + xx) * C;
+          inb[t] = xx >= 0 && xx < W && yy >= 0 && yy < H;
+          any |= inb[t];
+          wgt[t] = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
+          sp[t] = x + ((src_map * H + yy) * W + xx) * C;
+        }
+        if (!any) continue;   // the whole footprint falls outside the source map (warp-uniform)
 #pragma unroll
-          for (int v = 0; v < VEC_PER_LANE; ++v) {
-            const int c0 = (v * 32 + lane) * 8;
-            if (c0 < C) {
-              uint4 q = __ldg(reinterpret_cast<const uint4*>(sp + c0));
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-              uint4 ql = make_uint4(0, 0, 0, 0);
-              if (planes == 2) ql = __ldg(reinterpret_cast<const uint4*>(sp + plane_stride + c0));
-              const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql);
+        for (int v = 0; v < VEC_PER_LANE; ++v) {
+          const int c0 = (v * 32 + lane) * 8;
+          if (c0 < C) {
+            uint4 q[4], ql[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {   // predicated loads: out-of-range taps are zeros padding and cost no traffic
+              q[t] = inb[t] ? __ldg(reinterpret_cast<const uint4*>(sp[t] + c0)) : make_uint4(0, 0, 0, 0);
+              ql[t] = (planes == 2 && inb[t]) ? __ldg(reinterpret_cast<const uint4*>(sp[t] + plane_stride + c0))
+                                              : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q[t]);
+              const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql[t]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float2 f = __bfloat1622float2(h2[e]);
@@ -168,8 +220,8 @@ __global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
                   const float2 g = __bfloat1622float2(l2[e]);
                   f.x += g.x; f.y += g.y;
                 }
-                acc[v][2 * e] += wgt * f.x;
-                acc[v][2 * e + 1] += wgt * f.y;
+                acc[v][2 * e] += wgt[t] * f.x;
+                acc[v][2 * e + 1] += wgt[t] * f.y;
               }
             }
           }
@@ -233,8 +285,14 @@ extern "C" int v2x_pack_input(const float* x, void* out, int64_t n_pixels, int32
   V2X_REQUIRE(c > 0 && c_pad >= c && c_pad % 8 == 0, "c_pad must be a multiple of 8 and >= c");
   V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
   const long long total = (long long)n_pixels * (c_pad / 8);
-  pack_input_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(out), n_pixels, c, c_pad, planes);
+  if (c == 13 && c_pad == 16 && n_pixels % kPackPix == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // the BEV input of the path (V2VNet.py:51): coalesced float4 reads staged through shared memory
+    pack_input13_kernel<<<(unsigned)(n_pixels / kPackPix), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<__nv_bfloat16*>(out), n_pixels, planes);
+  } else {
+    pack_input_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<__nv_bfloat16*>(out), n_pixels, c, c_pad, planes);
+  }
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }

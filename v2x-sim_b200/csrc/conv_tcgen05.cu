@@ -55,6 +55,10 @@ struct ConvDev {
   int halo;                  // 1: 16x8 output tile, one 18x10 halo box per channel block feeds all 9 taps
   int num_b_tiles;           // weight tiles of the resident operand (= taps * sum(cblocks))
   uint32_t epi_off, epi_warp_bytes;  // per-warp output staging buffers (after the operand rings)
+  // fused 1x1 tail (V2X_EPI_TAIL_F32_SPLIT): second GEMM on the bf16 ReLU output of this conv, never written to HBM
+  int tail_cout, tail_cout_pad;
+  const float* tail_bias;
+  uint32_t tail_w_off, tail_a_off;   // smem: tail weights [planes][<=64 rows][128 B], A2 tile [planes][128 rows][128 B]
   int ctas_per_sm;           // 2: small-N layers run two co-resident CTAs per SM (two MMA issue streams, eight epilogue warps)
   int debug_mode;            // profiling ablations (v2x_set_debug_mode): 1 = no MMA, 2 = no TMA, 3 = no stores, 4 = no epilogue work
   int cout, cout_pad;
@@ -231,8 +235,7 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 }
 
 constexpr uint32_t kStageActPlane = 32u * 64u;    // bf16 chunk: 32 pixels x 32 channels
-constexpr uint32_t kStageF32Row = 128u + 16u;     // fp32 chunk row: 32 channels + 16 bytes of padding (bank spread)
-constexpr uint32_t kStageF32 = 32u * kStageF32Row;
+constexpr uint32_t kStageF32 = 32u * 128u;        // fp32 chunk: 32 pixels x 32 channels, 16-byte units XOR-swizzled by pixel
 
 // park 16 bf16 channels (two 16-byte units: 2*half, 2*half+1) of this lane's pixel
 template <int PLANES>
@@ -280,6 +283,52 @@ __device__ __forceinline__ void flush_act(uint32_t stage, int lane, int nunits, 
       }
     }
   }
+}
+
+// fp32 NHWC output of one 32-column chunk (channels ch0 .. ch0+31 of [0, cout), split between out0 / out1 like
+// V2X_EPI_F32_SPLIT): every lane parks its pixel's (v + bias) in the staging buffer, then lane -> unit (lane & 7) of
+// pixels (lane >> 3) + 4j writes it back, 128 contiguous bytes per pixel.
+template <bool HALO>
+__device__ __forceinline__ void f32_chunk_out(uint32_t stage, int lane, int quad, const float* v0, const float* v1, bool two,
+                                              const float* bias32, int ch0, int cout, int split, float* o0, float* o1,
+                                              long long tile_pix, int oh0, int ow0, int h_out, int w_out, bool no_store) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias32);
+  const uint32_t srow = stage + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = b4[q];
+    st_shared_v4(srow + ((((uint32_t)q) ^ sw) << 4), __float_as_uint(v0[4 * q] + b.x), __float_as_uint(v0[4 * q + 1] + b.y),
+                 __float_as_uint(v0[4 * q + 2] + b.z), __float_as_uint(v0[4 * q + 3] + b.w));
+  }
+  if (two) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = b4[4 + q];
+      st_shared_v4(srow + ((((uint32_t)(4 + q)) ^ sw) << 4), __float_as_uint(v1[4 * q] + b.x),
+                   __float_as_uint(v1[4 * q + 1] + b.y), __float_as_uint(v1[4 * q + 2] + b.z),
+                   __float_as_uint(v1[4 * q + 3] + b.w));
+    }
+  }
+  __syncwarp();
+  const int u = lane & 7;
+  const int ch = ch0 + 4 * u;
+  const int c1 = cout - split;
+  if (u < (two ? 8 : 4) && ch < cout && !no_store) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int pix = (lane >> 3) + 4 * j;
+      const int prow = quad * 32 + pix;
+      const int ph = HALO ? (prow >> 3) : (prow >> 4), pw = HALO ? (prow & 7) : (prow & 15);
+      if (oh0 + ph < h_out && ow0 + pw < w_out) {
+        const uint4 v = ld_shared_v4(stage + (uint32_t)pix * 128u + ((((uint32_t)u) ^ ((uint32_t)pix & 7u)) << 4));
+        const long long pi = tile_pix + (long long)ph * w_out + pw;
+        float* dst = ch < split ? o0 + pi * split + ch : o1 + pi * c1 + (ch - split);
+        *reinterpret_cast<uint4*>(dst) = v;
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -342,10 +391,11 @@ template <int BN, int PLANES, int KSTEPS, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                  const __grid_constant__ CUtensorMap tmA1,
                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                 const __grid_constant__ CUtensorMap tmT,
                                                                  const ConvDev p) {
   constexpr int KC = 16 * KSTEPS;
   constexpr uint32_t ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+  constexpr uint32_t TMEM_COLS = BN == 64 ? 256u : 2 * ACC_STRIDE;  // BN == 64: + the fused tail's accumulator (cols 128..191)
   constexpr uint32_t A_TILE = 128u * KC * 2u;                             // bytes
   constexpr uint32_t B_TILE = ((uint32_t)BN * KC * 2u + 1023u) & ~1023u;  // bytes (1 KB aligned)
   constexpr uint32_t ROW = KC * 2u;                                      // bytes of one pixel's channel block
@@ -355,11 +405,11 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
   constexpr uint32_t LAYOUT = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
   constexpr int TILE_H = HALO ? 16 : kTileH, TILE_W = HALO ? 8 : kTileW;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 5];
+  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 6];
   __shared__ uint32_t tmem_slot;
   __shared__ int4 ktab[kMaxKBlocks];  // per k-block: {channel coord, dw, dh, src | hp << 1}
   __shared__ __align__(16) float s_bias[BN];
-  __shared__ float s_bhn[64];
+  __shared__ __align__(16) float s_bhn[64];   // GRU: b_hh_n; fused tail: its bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
@@ -372,6 +422,8 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
   const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 3]);  // [2]
   const uint32_t bar_bfull = smem_u32(&bars[2 * kMaxStages + 5]);   // weight ring of the halo + streamed-B mode
   const uint32_t bar_bempty = smem_u32(&bars[3 * kMaxStages + 5]);
+  const uint32_t bar_tail = smem_u32(&bars[4 * kMaxStages + 5]);    // fused tail GEMM finished
+  const bool has_tail = p.epilogue == V2X_EPI_TAIL_F32_SPLIT;
   const uint32_t bring_base = smem_base + p.b_ring_off;
   const bool halo_stream = HALO && !p.b_resident;
 
@@ -400,15 +452,18 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
   }
   for (int i = threadIdx.x; i < BN; i += kNumThreads) s_bias[i] = p.bias[n0 + i];
   if (p.epilogue == V2X_EPI_GRU && threadIdx.x < 64) s_bhn[threadIdx.x] = p.gru_bhn[blockIdx.y * 64 + threadIdx.x];
+  if (has_tail && threadIdx.x < 64) s_bhn[threadIdx.x] = threadIdx.x < p.tail_cout_pad ? p.tail_bias[threadIdx.x] : 0.f;
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA0);
     if (p.nsrc > 1) prefetch_tmap(&tmA1);
     prefetch_tmap(&tmB);
+    if (has_tail) prefetch_tmap(&tmT);
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_bres, 1);
+    mbar_init(bar_tail, 1);
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(bar_bfull + 8 * s, 1);
       mbar_init(bar_bempty + 8 * s, 1);
@@ -433,7 +488,13 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
   if (warp == 0) {
     // ===== TMA producer =====
     if (p.b_resident && elect_one()) {
-      mbar_expect_tx(bar_bres, (uint32_t)p.num_b_tiles * PLANES * (uint32_t)(BN * KC * 2));
+      const uint32_t tail_bytes = has_tail ? (uint32_t)PLANES * (uint32_t)p.tail_cout_pad * 128u : 0u;
+      mbar_expect_tx(bar_bres, (uint32_t)p.num_b_tiles * PLANES * (uint32_t)(BN * KC * 2) + tail_bytes);
+      if (has_tail) {
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl)
+          tma_load_2d(smem_base + p.tail_w_off + pl * 8192u, &tmT, bar_bres, 0, pl * p.tail_cout_pad);
+      }
       for (int k = 0; k < p.num_b_tiles; ++k)
 #pragma unroll
         for (int pl = 0; pl < PLANES; ++pl)
@@ -701,11 +762,8 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
           if (valid && !dbg_no_store) epi_f32_nchw16(p, ti.n_img, oh, ow, n0 + c16 * 16, v0, s_bias + c16 * 16);
         }
       } else if (p.epilogue == V2X_EPI_F32_SPLIT) {
-        // fp32 NHWC heads / gate pre-activations: 32-column chunks staged as [pixel][32 floats (+pad)]
+        // fp32 NHWC heads / gate pre-activations: 32-column chunks staged as [pixel][32 floats]
         const long long tile_pix = ((long long)ti.n_img * p.h_out + oh0) * p.w_out + ow0;
-        float* const o0 = reinterpret_cast<float*>(p.out0);
-        float* const o1 = reinterpret_cast<float*>(p.out1);
-        const int c1 = p.cout - p.split;
 #pragma unroll 1
         for (int c32 = 0; c32 < (BN + 31) / 32; ++c32) {
           const int ch0 = n0 + c32 * 32;
@@ -716,40 +774,95 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
           if (two) tmem_ld16_async(taddr + c32 * 32 + 16, v1);
           tmem_ld_wait16(v0);
           if (two) tmem_ld_wait16(v1);
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c32 * 32);
-          const uint32_t srow = stage + (uint32_t)lane * kStageF32Row;
+          f32_chunk_out<HALO>(stage, lane, quad, v0, v1, two, s_bias + c32 * 32, ch0, p.cout, p.split,
+                              reinterpret_cast<float*>(p.out0), reinterpret_cast<float*>(p.out1), tile_pix, oh0, ow0,
+                              p.h_out, p.w_out, dbg_no_store);
+        }
+      } else if (has_tail) {
+        if constexpr (BN == 64) {
+          // ---- fused 1x1 tail: relu(acc + bias) -> bf16 -> A2 tile in smem -> second GEMM -> fp32 split output ----
+          // phase 1: this warp's 32 pixels x 64 channels into the K-major SWIZZLE_128B A2 tile (row = TMEM lane)
+          const uint32_t a2 = smem_base + p.tail_a_off;
+          const uint32_t a2row = a2 + (uint32_t)row * 128u;
+          const uint32_t rsw = (uint32_t)row & 7u;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b = b4[q];
-            st_shared_v4(srow + 16 * q, __float_as_uint(v0[4 * q] + b.x), __float_as_uint(v0[4 * q + 1] + b.y),
-                         __float_as_uint(v0[4 * q + 2] + b.z), __float_as_uint(v0[4 * q + 3] + b.w));
-          }
-          if (two) {
+          for (int c32 = 0; c32 < 2; ++c32) {
+            float v0[16], v1[16];
+            tmem_ld16_async(taddr + c32 * 32, v0);
+            tmem_ld16_async(taddr + c32 * 32 + 16, v1);
+            tmem_ld_wait16(v0);
+            tmem_ld_wait16(v1);
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + c32 * 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 b = b4[4 + q];
-              st_shared_v4(srow + 64 + 16 * q, __float_as_uint(v1[4 * q] + b.x), __float_as_uint(v1[4 * q + 1] + b.y),
-                           __float_as_uint(v1[4 * q + 2] + b.z), __float_as_uint(v1[4 * q + 3] + b.w));
+              const float4 b0 = b4[q], b1 = b4[4 + q];
+              v0[4 * q + 0] = fmaxf(v0[4 * q + 0] + b0.x, 0.f); v0[4 * q + 1] = fmaxf(v0[4 * q + 1] + b0.y, 0.f);
+              v0[4 * q + 2] = fmaxf(v0[4 * q + 2] + b0.z, 0.f); v0[4 * q + 3] = fmaxf(v0[4 * q + 3] + b0.w, 0.f);
+              v1[4 * q + 0] = fmaxf(v1[4 * q + 0] + b1.x, 0.f); v1[4 * q + 1] = fmaxf(v1[4 * q + 1] + b1.y, 0.f);
+              v1[4 * q + 2] = fmaxf(v1[4 * q + 2] + b1.z, 0.f); v1[4 * q + 3] = fmaxf(v1[4 * q + 3] + b1.w, 0.f);
+            }
+            uint32_t hi[8], lo[8];
+            pack16<PLANES>(v0, hi, lo);
+            st_shared_v4(a2row + ((((uint32_t)(4 * c32 + 0)) ^ rsw) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(a2row + ((((uint32_t)(4 * c32 + 1)) ^ rsw) << 4), hi[4], hi[5], hi[6], hi[7]);
+            if (PLANES == 2) {
+              st_shared_v4(a2row + 16384u + ((((uint32_t)(4 * c32 + 0)) ^ rsw) << 4), lo[0], lo[1], lo[2], lo[3]);
+              st_shared_v4(a2row + 16384u + ((((uint32_t)(4 * c32 + 1)) ^ rsw) << 4), lo[4], lo[5], lo[6], lo[7]);
+            }
+            pack16<PLANES>(v1, hi, lo);
+            st_shared_v4(a2row + ((((uint32_t)(4 * c32 + 2)) ^ rsw) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(a2row + ((((uint32_t)(4 * c32 + 3)) ^ rsw) << 4), hi[4], hi[5], hi[6], hi[7]);
+            if (PLANES == 2) {
+              st_shared_v4(a2row + 16384u + ((((uint32_t)(4 * c32 + 2)) ^ rsw) << 4), lo[0], lo[1], lo[2], lo[3]);
+              st_shared_v4(a2row + 16384u + ((((uint32_t)(4 * c32 + 3)) ^ rsw) << 4), lo[4], lo[5], lo[6], lo[7]);
             }
           }
+          // the conv accumulator is drained: hand it back to the MMA warp before the tail GEMM
+          tc_fence_before();
           __syncwarp();
-          const int u = lane & 7;
-          const int ch = ch0 + 4 * u;
-          if (u < (two ? 8 : 4) && ch < p.cout && !dbg_no_store) {
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc_buf);
+          fence_proxy_async_smem();                                  // A2 (generic-proxy writes) -> visible to the tensor core
+          asm volatile("bar.sync 1, 128;" ::: "memory");            // all four epilogue warps have written their rows
+          const uint32_t tmem_t = tmem_base + 128u;                  // tail accumulator: columns 128 .. 128+tail_cout_pad
+          if (warp == 2) {
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t idesc_t = make_idesc_bf16_m128((uint32_t)p.tail_cout_pad);
+              const uint64_t da2 = make_smem_desc(a2, 1024u, 2u);
+              const uint64_t dw2 = make_smem_desc(smem_base + p.tail_w_off, 1024u, 2u);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int pix = (lane >> 3) + 4 * j;
-              const int prow = quad * 32 + pix;
-              const int ph = HALO ? (prow >> 3) : (prow >> 4), pw = HALO ? (prow & 7) : (prow & 15);
-              if (oh0 + ph < p.h_out && ow0 + pw < p.w_out) {
-                const uint4 v = ld_shared_v4(stage + (uint32_t)pix * kStageF32Row + 16u * u);
-                const long long pi = tile_pix + (long long)ph * p.w_out + pw;
-                float* dst = ch < p.split ? o0 + pi * p.split + ch : o1 + pi * c1 + (ch - p.split);
-                *reinterpret_cast<uint4*>(dst) = v;
+              for (int kk = 0; kk < 4; ++kk) {
+                umma_bf16(tmem_t, da2 + 2 * kk, dw2 + 2 * kk, idesc_t, kk == 0 ? 0u : 1u);
+                if (PLANES == 2) {
+                  umma_bf16(tmem_t, da2 + 2 * kk, dw2 + 2 * kk + (8192u >> 4), idesc_t, 1);
+                  umma_bf16(tmem_t, da2 + 2 * kk + (16384u >> 4), dw2 + 2 * kk, idesc_t, 1);
+                }
               }
+              umma_commit(bar_tail);
             }
+            __syncwarp();
           }
-          __syncwarp();
+          mbar_wait(bar_tail, it & 1);
+          tc_fence_after();
+          // phase 2: tail accumulator + bias -> fp32 NHWC split output; staging reuses this warp's own A2 rows
+          const uint32_t tstage = a2 + (uint32_t)(quad * 32) * 128u;
+          const uint32_t taddr2 = tmem_t + ((uint32_t)(quad * 32) << 16);
+          const long long tile_pix = ((long long)ti.n_img * p.h_out + oh0) * p.w_out + ow0;
+#pragma unroll 1
+          for (int c32 = 0; c32 * 32 < p.tail_cout; ++c32) {
+            const bool two = c32 * 32 + 16 < p.tail_cout;
+            float v0[16], v1[16];
+            tmem_ld16_async(taddr2 + c32 * 32, v0);
+            if (two) tmem_ld16_async(taddr2 + c32 * 32 + 16, v1);
+            tmem_ld_wait16(v0);
+            if (two) tmem_ld_wait16(v1);
+            f32_chunk_out<HALO>(tstage, lane, quad, v0, v1, two, s_bhn + c32 * 32, c32 * 32, p.tail_cout, p.split,
+                                reinterpret_cast<float*>(p.out0), reinterpret_cast<float*>(p.out1), tile_pix, oh0, ow0,
+                                p.h_out, p.w_out, dbg_no_store);
+          }
+          tc_fence_before();   // orders this tile's tcgen05.ld of the tail accumulator before the next tile's barrier + MMA
+          ++it;
+          continue;
         }
       } else {
         o.tile_p = reinterpret_cast<__nv_bfloat16*>(p.out0) +
@@ -1043,6 +1156,16 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
     case V2X_EPI_F32_NCHW:
       V2X_REQUIRE(!p->upsample2x, "upsample2x only with EPI_ACT");
       break;
+    case V2X_EPI_TAIL_F32_SPLIT:
+      V2X_REQUIRE(bn == 64 && p->cout == 64 && p->cout_pad == 64, "fused tail needs cout == block_n == 64");
+      V2X_REQUIRE(p->tail_weights && p->tail_bias, "fused tail needs tail_weights / tail_bias");
+      V2X_REQUIRE(p->tail_cout > 0 && p->tail_cout <= p->tail_cout_pad && p->tail_cout_pad <= 64 && p->tail_cout_pad % 16 == 0,
+                  "tail_cout_pad must be a multiple of 16, <= 64");
+      V2X_REQUIRE(p->out1 != nullptr || p->split >= p->tail_cout, "fused tail needs out1");
+      V2X_REQUIRE(p->split > 0 && p->split <= p->tail_cout && p->split % 4 == 0 && p->tail_cout % 4 == 0, "bad tail split");
+      V2X_REQUIRE(!p->upsample2x, "upsample2x only with EPI_ACT");
+      d.tail_cout = p->tail_cout; d.tail_cout_pad = p->tail_cout_pad; d.tail_bias = p->tail_bias;
+      break;
     case V2X_EPI_GRU:
       V2X_REQUIRE(bn == 192 && p->cout % 192 == 0 && p->cout_pad == p->cout, "GRU epilogue needs block_n 192");
       V2X_REQUIRE(p->gru_bhn != nullptr, "GRU epilogue needs gru_bhn");
@@ -1073,7 +1196,7 @@ static int sm_count() {
 
 template <int BN, int PLANES, int KSTEPS, bool HALO>
 static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                     size_t smem, cudaStream_t stream) {
+                     const CUtensorMap& t, size_t smem, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -1091,7 +1214,7 @@ static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap&
   const int rounds = (d.m_tiles + ctas_x - 1) / ctas_x;
   ctas_x = (d.m_tiles + rounds - 1) / rounds;
   dim3 grid(ctas_x, d.n_tiles);
-  conv_tc_kernel<BN, PLANES, KSTEPS, HALO><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, d);
+  conv_tc_kernel<BN, PLANES, KSTEPS, HALO><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, t, d);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }
@@ -1105,9 +1228,12 @@ using namespace v2x;
 static int plan_smem(const v2x_conv_params* p, ConvDev& d, uint32_t budget, size_t* smem_out) {
   const int bn = p->block_n;
   // output staging of the four epilogue warps comes off the top of the budget
+  const bool tail = p->epilogue == V2X_EPI_TAIL_F32_SPLIT;
   d.epi_warp_bytes = p->epilogue == V2X_EPI_F32_SPLIT ? kStageF32
-                     : p->epilogue == V2X_EPI_F32_NCHW ? 0u : (uint32_t)p->planes * kStageActPlane;
-  const uint32_t epi_bytes = 4u * d.epi_warp_bytes;
+                     : (p->epilogue == V2X_EPI_F32_NCHW || tail) ? 0u : (uint32_t)p->planes * kStageActPlane;
+  // fused tail: its weights [planes][8 KB] and the A2 tile [planes][16 KB] (which doubles as the fp32 output staging)
+  const uint32_t tail_bytes = tail ? (uint32_t)p->planes * (8192u + 16384u) : 0u;
+  const uint32_t epi_bytes = 4u * d.epi_warp_bytes + tail_bytes;
   budget -= epi_bytes;
   // Shared-memory plan.  Small weight operands (all of [block_n x K], e.g. the C=32 layers at 256x256)
   // stay resident for the CTA's lifetime so only activations stream; otherwise weights ride in the
@@ -1195,6 +1321,9 @@ static int plan_smem(const v2x_conv_params* p, ConvDev& d, uint32_t budget, size
   smem_total = (size_t)d.b_region_bytes + (size_t)stages * d.stage_bytes + 1024;
   }
   d.epi_off = (uint32_t)(smem_total - 1024);
+  d.tail_w_off = d.epi_off + 4u * d.epi_warp_bytes;
+  d.tail_a_off = d.tail_w_off + (uint32_t)p->planes * 8192u;
+  V2X_REQUIRE(!tail || (d.b_resident && d.epi_off % 1024u == 0), "fused tail needs resident weights");
   *smem_out = smem_total + epi_bytes;
   return V2X_OK;
 }
@@ -1255,11 +1384,19 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
     rc = encode_map(&tmB, p->weights, 2, dims, str, box, d.kc);
     if (rc) return rc;
   }
+  CUtensorMap tmT = tmB;
+  if (p->epilogue == V2X_EPI_TAIL_F32_SPLIT) {  // tail weights [planes][tail_cout_pad][64] bf16, one box per plane
+    cuuint64_t dims[2] = {64, (cuuint64_t)p->planes * p->tail_cout_pad};
+    cuuint64_t str[1] = {64 * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)p->tail_cout_pad};
+    rc = encode_map(&tmT, p->tail_weights, 2, dims, str, box, 64);
+    if (rc) return rc;
+  }
   V2X_REQUIRE(d.num_k <= kMaxKBlocks, "too many k-blocks (%d > %d)", d.num_k, kMaxKBlocks);
 #define V2X_LAUNCH(BN_, KS_, HALO_)                                                                      \
   if (bn == BN_ && d.kc == 16 * KS_ && (d.halo != 0) == HALO_)                                           \
-    return p->planes == 1 ? launch_tc<BN_, 1, KS_, HALO_>(d, tmA[0], tmA[1], tmB, smem, stream)          \
-                          : launch_tc<BN_, 2, KS_, HALO_>(d, tmA[0], tmA[1], tmB, smem, stream);
+    return p->planes == 1 ? launch_tc<BN_, 1, KS_, HALO_>(d, tmA[0], tmA[1], tmB, tmT, smem, stream)     \
+                          : launch_tc<BN_, 2, KS_, HALO_>(d, tmA[0], tmA[1], tmB, tmT, smem, stream);
   // kc = 16 only occurs for the 13(16)-channel input layer, kc = 32 for the 32/96-channel layers;
   // halo mode needs resident weights, i.e. the small-N layers
   V2X_LAUNCH(32, 1, true) V2X_LAUNCH(32, 2, true) V2X_LAUNCH(32, 4, true)

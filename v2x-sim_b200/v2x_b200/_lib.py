@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libv2x_b200.so")
 
-EPI_ACT, EPI_F32_SPLIT, EPI_GRU, EPI_F32_NCHW = 0, 1, 2, 3
+EPI_ACT, EPI_F32_SPLIT, EPI_GRU, EPI_F32_NCHW, EPI_TAIL_F32_SPLIT = 0, 1, 2, 3, 4
 
 
 class ConvParams(C.Structure):
@@ -46,6 +46,10 @@ class ConvParams(C.Structure):
         ("map_offset", C.c_int32),
         ("reserved", C.c_int32 * 3),
         ("gru_add", C.c_void_p),
+        ("tail_weights", C.c_void_p),
+        ("tail_bias", C.c_void_p),
+        ("tail_cout", C.c_int32),
+        ("tail_cout_pad", C.c_int32),
     ]
 
 

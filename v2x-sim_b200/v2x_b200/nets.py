@@ -17,9 +17,13 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from .ops import EPI_ACT, EPI_F32_SPLIT, EPI_GRU, ConvLaunch, PackedConv
+from .ops import EPI_ACT, EPI_F32_SPLIT, EPI_GRU, EPI_TAIL_F32_SPLIT, ConvLaunch, PackedConv
+
+import os
 
 H0 = W0 = 256
+# the two head convs run as one launch (EPI_TAIL_F32_SPLIT); V2X_NO_FUSE_HEADS=1 keeps the two-launch form (A/B tests)
+FUSE_HEADS = not os.environ.get("V2X_NO_FUSE_HEADS")
 IN_C, IN_C_PAD = 13, 16
 
 
@@ -145,11 +149,17 @@ class DetPlan:
         return h
 
     def build_heads(self, hw: HeadWeights, x8):
-        t = self.conv(hw.head1, [x8], "head1")
+        """cls / reg heads (DetModelBase.py:283-296, 319-329): conv3x3+BN+ReLU (both heads stacked, 64 rows) and the
+        block-diagonal 1x1 as ONE launch -- the 64-channel intermediate lives only in shared memory."""
         n_cls = hw.n_cls
         n_loc = hw.head2.cout - n_cls
         self.cls = torch.empty((self.n, H0, W0, n_cls), dtype=torch.float32, device=self.device)
         self.loc = torch.empty((self.n, H0, W0, n_loc), dtype=torch.float32, device=self.device)
+        if FUSE_HEADS and hw.head1.cout == 64 and hw.head2.cout_pad <= 64 and hw.head2.cout_pad % 16 == 0:
+            self.add(ConvLaunch(hw.head1, [x8], epilogue=EPI_TAIL_F32_SPLIT, relu=True, out0=self.cls, out1=self.loc,
+                                split=n_cls, block_n=64, tail=hw.head2))
+            return
+        t = self.conv(hw.head1, [x8], "head1")
         self.add(ConvLaunch(hw.head2, [t], epilogue=EPI_F32_SPLIT, relu=False, out0=self.cls, out1=self.loc,
                             split=n_cls, block_n=hw.head2.cout))
 

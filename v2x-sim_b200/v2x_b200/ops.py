@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import EPI_ACT, EPI_F32_NCHW, EPI_F32_SPLIT, EPI_GRU, ConvParams, V2XError, check
+from ._lib import EPI_ACT, EPI_F32_NCHW, EPI_F32_SPLIT, EPI_GRU, EPI_TAIL_F32_SPLIT, ConvParams, V2XError, check
 
 BN_EPS = 1e-5  # nn.BatchNorm2d default (reference never overrides it)
 
@@ -204,7 +204,8 @@ class ConvLaunch:
 
     def __init__(self, pc: PackedConv, srcs: Sequence[torch.Tensor], *, epilogue=EPI_ACT, relu=True, upsample2x=False,
                  out0: torch.Tensor = None, out1: torch.Tensor = None, out_c_off=0, split=0, block_n=None,
-                 passthrough=None, num_agent=None, batch=0, agents=0, map_offset=0, gru_add=None, crosscheck=False):
+                 passthrough=None, num_agent=None, batch=0, agents=0, map_offset=0, gru_add=None, crosscheck=False,
+                 tail: Optional[PackedConv] = None):
         self.lib = require_gpu()
         planes, n, h_in, w_in, _ = srcs[0].shape
         assert planes == pc.planes
@@ -234,10 +235,16 @@ class ConvLaunch:
         p.num_agent = num_agent.data_ptr() if num_agent is not None else None
         p.batch, p.agents, p.map_offset = batch, agents, map_offset
         p.gru_add = gru_add.data_ptr() if gru_add is not None else None
+        if tail is not None:   # fused 1x1 conv on the ReLU output (EPI_TAIL_F32_SPLIT)
+            assert epilogue == EPI_TAIL_F32_SPLIT and tail.taps == 1 and tail.cins == [pc.cout] and tail.planes == planes
+            p.tail_weights, p.tail_bias = tail.weights.data_ptr(), tail.bias.data_ptr()
+            p.tail_cout, p.tail_cout_pad = tail.cout, tail.cout_pad
         self.p = p
-        self.keep = (pc, list(srcs), out0, out1, passthrough, num_agent, gru_add)
+        self.keep = (pc, list(srcs), out0, out1, passthrough, num_agent, gru_add, tail)
         self.fn = self.lib.v2x_conv_fwd_crosscheck if crosscheck else self.lib.v2x_conv_fwd
         self.flops = 2.0 * n * h_out * w_out * pc.cout * pc.taps * sum(pc.cins)
+        if tail is not None:
+            self.flops += 2.0 * n * h_out * w_out * tail.cout * pc.cout
 
     def __call__(self):
         check(self.fn(C.byref(self.p), _stream()), "v2x_conv_fwd")
