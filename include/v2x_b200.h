@@ -93,7 +93,12 @@ typedef struct v2x_conv_params {
   const int64_t* num_agent;  /* [batch][agents] (reference num_agent_tensor) or NULL           */
   int32_t batch, agents;     /* agent-major maps: global unit = batch * agent + b              */
   int32_t map_offset;        /* global unit index of this launch's map 0 (sharded plans), else 0 */
-  int32_t reserved[3];
+  int32_t gru_pre_act;       /* EPI_GRU: src[1] is a bf16 act tensor [planes][N][H][W][cout] of gate pre-activations (packed
+                                gate order, e.g. conv(mean, W_ih[:, C:]) + bias from an EPI_ACT launch with relu = 0); cin[1] must
+                                be 192 and the packed weights carry 192 extra K columns holding the identity
+                                (W[n][taps*cin[0] + j] = (n % 192 == j)), so every N tile accumulates its own window on the
+                                tensor core instead of loading it in the epilogue */
+  int32_t reserved[2];
   /* EPI_GRU, optional: fp32 [N*H*W][cout] (packed gate order) added to the gate pre-activations -- the round-invariant
      half conv(mean, W_ih[:, C:]) + bias, computed once per frame by an EPI_F32_SPLIT launch (split == cout) so the three
      GNN rounds only convolve the changing half (V2VNet.py:99: cat([h_i, mean]); the mean never changes). */

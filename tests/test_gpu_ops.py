@@ -377,3 +377,36 @@ def test_convgru_split_operands(impl, planes):
     err = rel_err(ops.act_to_float(out), ref)
     print("gru split %s planes=%d rel_err=%.3e" % (impl, planes, err))
     assert err < TOL[planes]
+
+
+@pytest.mark.parametrize("impl,planes", [("crosscheck", 2), ("crosscheck", 1), ("tc", 1)])
+@pytest.mark.parametrize("c", [64, 128])
+def test_convgru_pre_act_identity_columns(c, impl, planes):
+    """gru_pre_act: the round-invariant pre-activations are a bf16 act tensor accumulated by the round's own GEMM through
+    192 identity weight columns (no epilogue loads) -- must equal the oracle GRU on cat([h, mean]); c=128 has two N
+    tiles, so each must pick its own 192-column window.  The tensor-core path offers it in the halo + streamed-weight
+    mode, which needs the single-plane operand sizes (the bf16x3 plans keep the fp32 ``gru_add`` form)."""
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    from v2x_b200.ops import EPI_ACT, EPI_GRU, ConvLaunch
+    dev = _dev()
+    gen = synth._Gen(17)
+    sd = {"convgru.weight_ih_l0": gen.uniform((3 * c, 2 * c, 3, 3), -0.05, 0.05),
+          "convgru.weight_hh_l0": gen.uniform((3 * c, c, 3, 3), -0.05, 0.05),
+          "convgru.bias_ih_l0": gen.uniform((3 * c,), -0.5, 0.5),
+          "convgru.bias_hh_l0": gen.uniform((3 * c,), -0.5, 0.5)}
+    n = 2
+    hfeat, mean = gen.normal((n, c, 16, 16), 1.0), gen.normal((n, c, 16, 16), 1.0)
+    ref = torch.cat([torch.flip(restate.convgru_zero_hidden(
+        torch.flip(torch.cat([hfeat[i], mean[i]], 0).unsqueeze(0), (2,)), sd), (2,)) for i in range(n)], 0)
+    gru_h, gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"], sd["convgru.bias_hh_l0"],
+                                      planes=planes, device=dev, pre_act=True)
+    a_h, a_m = to_act(hfeat, planes, dev), to_act(mean, planes, dev)
+    cc = impl == "crosscheck"
+    pre = ops.empty_act(planes, n, 16, 16, 3 * c, dev)
+    ConvLaunch(gru_m, [a_m], epilogue=EPI_ACT, relu=False, out0=pre, crosscheck=cc)()
+    out = torch.empty_like(a_h)
+    ConvLaunch(gru_h, [a_h, pre], epilogue=EPI_GRU, out0=out, crosscheck=cc)()
+    err = rel_err(ops.act_to_float(out), ref)
+    print("gru pre_act c=%d %s planes=%d rel_err=%.3e" % (c, impl, planes, err))
+    assert err < TOL[planes]

@@ -69,6 +69,7 @@ struct ConvDev {
   const float* bias;
   const float* gru_bhn;
   const float* gru_add;      // optional fp32 [pixel][cout] pre-activation term added to the gate accumulators
+  int gru_pre_act;           // src[1] = bf16 pre-activations [..][cout]; each N tile accumulates its window through identity weight columns
   const void* passthrough;
   const long long* num_agent;
   int batch, agents, map_offset;
@@ -434,6 +435,8 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
       const int s = k < p.cblocks[0] ? 0 : 1;
       const int cb = k - s * p.cblocks[0];
       e = make_int4(cb * KC, s * 9 * p.cblocks[0] + cb, p.cblocks[s], s);
+      // GRU pre-activation window: channels [n0, n0 + BN) of src[1], centre tap only, identity weight tile (bit 1 of e.w)
+      if (s == 1 && p.gru_pre_act) e = make_int4(n0 + cb * KC, 9 * p.cblocks[0] + cb, 0, 3);
     } else {
       const int k0 = p.taps * p.cblocks[0];
       const int s = k < k0 ? 0 : 1;
@@ -528,16 +531,18 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
           }
           __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
-          for (int t0 = 0; t0 < 9; t0 += p.b_taps) {
+          const bool single = (e.w & 2) != 0;   // identity block: one weight tile (tap step 0), centre tap only
+          const int ntaps = single ? 1 : 9, tstep = single ? 1 : p.b_taps;
+          for (int t0 = 0; t0 < ntaps; t0 += tstep) {
             mbar_wait(bar_bempty + 8 * bstage, bphase ^ 1);
             if (elect_one()) {
               const uint32_t bfull = bar_bfull + 8 * bstage;
               if (no_tma) {
                 mbar_arrive(bfull);
               } else {
-                mbar_expect_tx(bfull, (uint32_t)p.b_taps * PLANES * (uint32_t)(BN * KC * 2));
+                mbar_expect_tx(bfull, (uint32_t)tstep * PLANES * (uint32_t)(BN * KC * 2));
                 uint32_t sb = bring_base + bstage * p.b_stage_bytes;
-                for (int t = t0; t < t0 + p.b_taps; ++t)
+                for (int t = t0; t < t0 + tstep; ++t)
 #pragma unroll
                   for (int pl = 0; pl < PLANES; ++pl, sb += B_TILE)
                     tma_load_2d(sb, &tmB, bfull, (e.y + t * e.z) * KC, pl * p.cout_pad + n0);
@@ -642,7 +647,30 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
               if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
             }
           };
-          if (p.b_taps == 3) issue_taps(std::integral_constant<int, 3>{});
+          if (ktab[kb].w & 2) {
+            // identity block (GRU pre-activations): centre tap of the halo tile x one weight tile
+            mbar_wait(bar_bfull + 8 * bstage, bphase);
+            tc_fence_after();
+            if (elect_one()) {
+              if (no_mma) {
+                mbar_arrive(bar_bempty + 8 * bstage);
+              } else {
+                const uint64_t db = desc_bring + (uint64_t)(bstage * bstage16);
+                constexpr uint32_t a_off = (uint32_t)(((kHaloW + 1) * ROW) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) {
+                  umma_bf16(tmem_d, da + (a_off + 2 * kk), db + 2 * kk, idesc, kk == 0 ? acc : 1u);
+                  if (PLANES == 2) {
+                    umma_bf16(tmem_d, da + (a_off + 2 * kk), db + (2 * kk + (B_TILE >> 4)), idesc, 1);
+                    umma_bf16(tmem_d, da + (a_off + 2 * kk + (A_BLOCK >> 4)), db + 2 * kk, idesc, 1);
+                  }
+                }
+                umma_commit(bar_bempty + 8 * bstage);
+              }
+            }
+            __syncwarp();
+            if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+          } else if (p.b_taps == 3) issue_taps(std::integral_constant<int, 3>{});
           else issue_taps(std::integral_constant<int, 1>{});
           acc = 1;
           if (elect_one()) {
@@ -1017,7 +1045,14 @@ __global__ void conv_ref_kernel(const ConvDev p) {
   for (int g = 0; g < 3; ++g)
     for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
   long long kbase = 0;
-  for (int s = 0; s < p.nsrc; ++s) {
+  const int nsrc_conv = p.gru_pre_act ? 1 : p.nsrc;
+  if (p.gru_pre_act) {  // src[1] = pre-activations [planes][N][H][W][cout] in packed gate order
+    const long long pre_plane = (long long)p.n_maps * p.h_out * p.w_out * p.cout;
+    const long long base = (((long long)n_img * p.h_out + oh) * p.w_out + ow) * p.cout;
+    for (int g = 0; g < ngate; ++g)
+      for (int i = 0; i < 16; ++i) acc[g][i] += ld_act(p, 1, base + prow[g] + i, pre_plane);
+  }
+  for (int s = 0; s < nsrc_conv; ++s) {
     const long long plane_stride = (long long)p.n_maps * h_in * w_in * p.cin[s];
     for (int tap = 0; tap < p.taps; ++tap) {
       const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap % 3 : 1;
@@ -1105,6 +1140,7 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
   V2X_REQUIRE(p->cout > 0 && p->cout_pad >= p->cout && p->cout_pad % bn == 0, "cout_pad must be a multiple of block_n");
   V2X_REQUIRE(p->cout % 16 == 0 || p->epilogue == V2X_EPI_F32_SPLIT || p->epilogue == V2X_EPI_F32_NCHW,
               "cout must be a multiple of 16");
+  V2X_REQUIRE(!p->gru_pre_act || p->epilogue == V2X_EPI_GRU, "gru_pre_act only with EPI_GRU");
   d = ConvDev{};
   d.n_maps = p->n_maps; d.h_out = p->h_out; d.w_out = p->w_out; d.stride = p->stride; d.taps = p->taps;
   d.planes = p->planes;
@@ -1115,10 +1151,11 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
     while (d.cin[s] % kc) kc >>= 1;
   d.kc = kc;
   d.num_k = 0; d.k_total = 0;
+  d.gru_pre_act = p->gru_pre_act;
   for (int s = 0; s < d.nsrc; ++s) {
     d.cblocks[s] = d.cin[s] / kc;
     d.num_k += p->taps * d.cblocks[s];
-    d.k_total += p->taps * d.cin[s];
+    d.k_total += (s == 1 && p->gru_pre_act) ? d.cin[s] : p->taps * d.cin[s];   // identity columns: one "tap"
   }
   // partial tiles are allowed: TMA zero-fills reads beyond the map, the epilogue masks stores beyond it
   d.tiles_w = (p->w_out + kTileW - 1) / kTileW;
@@ -1169,6 +1206,9 @@ static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
     case V2X_EPI_GRU:
       V2X_REQUIRE(bn == 192 && p->cout % 192 == 0 && p->cout_pad == p->cout, "GRU epilogue needs block_n 192");
       V2X_REQUIRE(p->gru_bhn != nullptr, "GRU epilogue needs gru_bhn");
+      V2X_REQUIRE(!p->gru_pre_act || (p->src[1] != nullptr && p->cin[1] == 192 && p->taps == 9 && p->stride == 1 &&
+                                      p->cin[0] % 64 == 0),
+                  "gru_pre_act needs src[1] (pre-activations), cin[1] == 192, a 3x3 stride-1 conv and cin[0] %% 64 == 0");
       V2X_REQUIRE(!p->upsample2x, "upsample2x only with EPI_ACT");
       V2X_REQUIRE(p->out_c_total >= p->out_c_off + p->cout / 3 && p->out_c_total % 8 == 0 && p->out_c_off % 8 == 0,
                   "bad output channel window");
@@ -1360,7 +1400,7 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
   CUtensorMap tmA[2], tmB;
   const int h_in = p->h_out * p->stride, w_in = p->w_out * p->stride;
   for (int s = 0; s < d.nsrc; ++s) {
-    const cuuint64_t C = (cuuint64_t)d.cin[s];
+    const cuuint64_t C = (s == 1 && d.gru_pre_act) ? (cuuint64_t)p->cout : (cuuint64_t)d.cin[s];
     const cuuint64_t NP = (cuuint64_t)p->n_maps * p->planes;
     if (p->stride == 1) {
       cuuint64_t dims[4] = {C, (cuuint64_t)w_in, (cuuint64_t)h_in, NP};
@@ -1393,6 +1433,7 @@ extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
     if (rc) return rc;
   }
   V2X_REQUIRE(d.num_k <= kMaxKBlocks, "too many k-blocks (%d > %d)", d.num_k, kMaxKBlocks);
+  V2X_REQUIRE(!d.gru_pre_act || (d.halo && !d.b_resident), "gru_pre_act needs the halo + streamed-weight mode (16 | H, 8 | W)");
 #define V2X_LAUNCH(BN_, KS_, HALO_)                                                                      \
   if (bn == BN_ && d.kc == 16 * KS_ && (d.halo != 0) == HALO_)                                           \
     return p->planes == 1 ? launch_tc<BN_, 1, KS_, HALO_>(d, tmA[0], tmA[1], tmB, tmT, smem, stream)     \

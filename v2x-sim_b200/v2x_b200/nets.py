@@ -24,6 +24,9 @@ import os
 H0 = W0 = 256
 # the two head convs run as one launch (EPI_TAIL_F32_SPLIT); V2X_NO_FUSE_HEADS=1 keeps the two-launch form (A/B tests)
 FUSE_HEADS = not os.environ.get("V2X_NO_FUSE_HEADS")
+# ConvGRU pre-activations ride the rounds' GEMM as a bf16 second source (gru_pre_act); V2X_GRU_ADD_F32=1 keeps the fp32
+# epilogue-add form (A/B tests)
+GRU_PRE_ACT = not os.environ.get("V2X_GRU_ADD_F32")
 IN_C, IN_C_PAD = 13, 16
 
 
@@ -138,13 +141,22 @@ class DetPlan:
         changes between rounds (neighbours are always warped from the original maps), so its contribution
         conv(mean, W_ih[:, C:]) + bias is computed once into fp32 pre-activations and added in each round's epilogue."""
         c3, hh, ww = x3.shape[-1], x3.shape[2], x3.shape[3]
-        self.gru_pre = torch.empty((self.n, hh, ww, 3 * c3), dtype=torch.float32, device=self.device)
-        self.add(ConvLaunch(self.gru_m, [mean], epilogue=EPI_F32_SPLIT, relu=False, out0=self.gru_pre, split=3 * c3))
+        if self.gru_h.gru_pre_act:
+            # pre-activations as a bf16 act tensor, accumulated by the rounds' own GEMM through identity weight columns
+            self.gru_pre = self.act("gru_pre", hh, ww, 3 * c3)
+            self.add(ConvLaunch(self.gru_m, [mean], epilogue=EPI_ACT, relu=False, out0=self.gru_pre))
+        else:
+            self.gru_pre = torch.empty((self.n, hh, ww, 3 * c3), dtype=torch.float32, device=self.device)
+            self.add(ConvLaunch(self.gru_m, [mean], epilogue=EPI_F32_SPLIT, relu=False, out0=self.gru_pre, split=3 * c3))
         h = x3
         for r in range(gnn_iter):
             out = self.act("h%d" % (r + 1), hh, ww, c3)
-            self.add(ConvLaunch(self.gru_h, [h], epilogue=EPI_GRU, out0=out, passthrough=x3, num_agent=self.num_agent,
-                                batch=batch, agents=agents, map_offset=map_offset, gru_add=self.gru_pre))
+            if self.gru_h.gru_pre_act:
+                self.add(ConvLaunch(self.gru_h, [h, self.gru_pre], epilogue=EPI_GRU, out0=out, passthrough=x3,
+                                    num_agent=self.num_agent, batch=batch, agents=agents, map_offset=map_offset))
+            else:
+                self.add(ConvLaunch(self.gru_h, [h], epilogue=EPI_GRU, out0=out, passthrough=x3, num_agent=self.num_agent,
+                                    batch=batch, agents=agents, map_offset=map_offset, gru_add=self.gru_pre))
             h = out
         return h
 
@@ -206,7 +218,8 @@ class V2VNetDetPlan(DetPlan):
         self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
         self.head_w = HeadWeights(sd, planes, dev)
         self.gru_h, self.gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"],
-                                                    sd["convgru.bias_hh_l0"], planes=planes, device=dev)
+                                                    sd["convgru.bias_hh_l0"], planes=planes, device=dev,
+                                                    pre_act=GRU_PRE_ACT and planes == 1)
         self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
 
@@ -347,7 +360,8 @@ class V2VNetDetShardedPlan(DetPlan):
         self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
         self.head_w = HeadWeights(sd, planes, dev)
         self.gru_h, self.gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"],
-                                                    sd["convgru.bias_hh_l0"], planes=planes, device=dev)
+                                                    sd["convgru.bias_hh_l0"], planes=planes, device=dev,
+                                                    pre_act=GRU_PRE_ACT and planes == 1)
         self.trans = torch.zeros((batch_total, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch_total, agents), agents, dtype=torch.int64, device=dev)
         trans, na, off = self.trans, self.num_agent, self.offset

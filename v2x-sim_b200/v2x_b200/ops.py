@@ -73,6 +73,7 @@ class PackedConv:
     planes: int
     gru_bhn: Optional[torch.Tensor] = None
     keep: list = field(default_factory=list)
+    gru_pre_act: bool = False   # weights carry 192 identity K columns for the pre-activation window (v2x_conv_params.gru_pre_act)
 
     @property
     def k_total(self):
@@ -128,11 +129,16 @@ def pack_gru(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True) -> PackedCo
     return pc
 
 
-def pack_gru_split(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True):
+def pack_gru_split(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True, pre_act=False):
     """The zero-hidden ConvGRU split in two operands: ``gru_m`` convolves the round-invariant neighbour mean
-    (W_ih[:, C:], carries the combined bias) once per frame into fp32 pre-activations; ``gru_h`` convolves the agent's
-    own state (W_ih[:, :C]) in every GNN round and adds them in its gate epilogue (``gru_add``).  Same arithmetic as
-    conv(cat([h, mean])) up to fp32 summation order; one third fewer FLOPs over three rounds."""
+    (W_ih[:, C:], carries the combined bias) once per frame into gate pre-activations; ``gru_h`` convolves the agent's
+    own state (W_ih[:, :C]) in every GNN round and adds them.  Same arithmetic as conv(cat([h, mean])) up to fp32
+    summation order; one third fewer FLOPs over three rounds.
+
+    pre_act=False: pre-activations are fp32 (an EPI_F32_SPLIT launch of ``gru_m``) and are added in ``gru_h``'s gate
+    epilogue (``gru_add``).  pre_act=True: they are a bf16 act tensor (EPI_ACT launch, relu=False) that ``gru_h`` takes
+    as a second source: 192 identity columns appended to its packed weights make every N tile accumulate its own window
+    on the tensor core, so the epilogue issues no global loads (``v2x_conv_params.gru_pre_act``)."""
     lib = require_gpu()
     device = device or w_ih.device
     c = w_ih.shape[0] // 3
@@ -143,6 +149,12 @@ def pack_gru_split(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True):
     bi, bh = _f32(b_ih, device), _f32(b_hh, device)
     check(lib.v2x_pack_gru_bias(_ptr(bi), _ptr(bh), c, _ptr(gru_m.bias), _ptr(bhn), _stream()), "v2x_pack_gru_bias")
     gru_h.gru_bhn = bhn     # gru_h.bias stays zero: the bias rides in gru_m's output
+    if pre_act:
+        eye = torch.zeros((planes, 3 * c, 192), dtype=torch.bfloat16, device=device)
+        eye[0] = torch.eye(192, dtype=torch.bfloat16, device=device).repeat(3 * c // 192, 1)   # row n -> column n % 192
+        gru_h.weights = torch.cat([gru_h.weights, eye], dim=2).contiguous()
+        gru_h.cins = [c, 192]
+        gru_h.gru_pre_act = True
     return gru_h, gru_m
 
 
@@ -209,8 +221,10 @@ class ConvLaunch:
         self.lib = require_gpu()
         planes, n, h_in, w_in, _ = srcs[0].shape
         assert planes == pc.planes
-        for s, cp in zip(srcs, pc.cins):
-            assert s.shape[-1] == cp and s.is_contiguous() and s.dtype == torch.bfloat16, (s.shape, cp)
+        for i, (s, cp) in enumerate(zip(srcs, pc.cins)):
+            want = pc.cout if (pc.gru_pre_act and i == 1) else cp    # the pre-activation source spans all cout channels
+            assert s.shape[-1] == want and s.is_contiguous() and s.dtype == torch.bfloat16, (s.shape, want)
+        assert not pc.gru_pre_act or (epilogue == EPI_GRU and len(srcs) == 2)
         h_out, w_out = h_in // pc.stride, w_in // pc.stride
         p = ConvParams()
         p.src[0] = srcs[0].data_ptr()
@@ -235,6 +249,7 @@ class ConvLaunch:
         p.num_agent = num_agent.data_ptr() if num_agent is not None else None
         p.batch, p.agents, p.map_offset = batch, agents, map_offset
         p.gru_add = gru_add.data_ptr() if gru_add is not None else None
+        p.gru_pre_act = int(pc.gru_pre_act)
         if tail is not None:   # fused 1x1 conv on the ReLU output (EPI_TAIL_F32_SPLIT)
             assert epilogue == EPI_TAIL_F32_SPLIT and tail.taps == 1 and tail.cins == [pc.cout] and tail.planes == planes
             p.tail_weights, p.tail_bias = tail.weights.data_ptr(), tail.bias.data_ptr()
@@ -242,7 +257,8 @@ class ConvLaunch:
         self.p = p
         self.keep = (pc, list(srcs), out0, out1, passthrough, num_agent, gru_add, tail)
         self.fn = self.lib.v2x_conv_fwd_crosscheck if crosscheck else self.lib.v2x_conv_fwd
-        self.flops = 2.0 * n * h_out * w_out * pc.cout * pc.taps * sum(pc.cins)
+        k_eff = pc.taps * pc.cins[0] + 192 if pc.gru_pre_act else pc.taps * sum(pc.cins)
+        self.flops = 2.0 * n * h_out * w_out * pc.cout * k_eff
         if tail is not None:
             self.flops += 2.0 * n * h_out * w_out * tail.cout * pc.cout
 
