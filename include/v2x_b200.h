@@ -198,6 +198,74 @@ int v2x_warp_gated_fwd(const void* x, void* out, const double* trans, const int6
                        int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes,
                        int32_t warp_flag, int32_t only_v2i, void* stream);
 
+/* ---- intermediate-fusion baselines (CP/models/det/base/FusionBase.py, CP/models/seg/FusionBase.py) ---------- */
+
+/*
+ * out[b,i] = reduce over {x[b,i]} U {warp_{j->i}(x[b,j]) : j != i present} ; mode 0 mean, 1 sum, 2 max.
+ * Same geometry / theta' / grid_sample semantics as v2x_warp_mean_fwd; agent slots i >= na[b] keep their own map.
+ * Replaces torch.mean/sum/max(torch.stack(neighbor_feat_list)) at MeanFusion.py:11-12, SumFusion.py:20-21,
+ * MaxFusion.py:20-21 (and CatFusion.py:23) plus the warps of DetModelBase.build_neighbors_feature_list (:171-209).
+ */
+int v2x_warp_reduce_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent, int32_t batch,
+                        int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t mode,
+                        int32_t only_v2i, void* stream);
+
+/*
+ * Pair scores of the learned fusion weights: s[b,i,k,p] = relu(conv1_4(relu(bn(conv1_3(relu(bn(conv1_2(
+ * relu(bn(conv1_1(cat[x_i, warp_{k->i}(x_k)]))))))))))) at pixel p (DiscoNet.py:132-155, AgentWiseWeightedFusion.py:44-76).
+ * q: act [planes][A*B][h][w][256] = conv1x1(x, [Wa ; Wb]) with conv1_1's BN folded (channels [0,128): tg half incl.
+ * bias, [128,256): neighbour half, no bias) -- conv1_1 is linear and pointwise, so it commutes with the warp.
+ * w2 [32][128], b2 [32], w3 [8][32], b3 [8], w4 [8], b4 [1]: fp32, BN(eval) already folded.
+ * scores: fp32 [B][A][A][h*w]; only participating (i, k < na[b]) entries are written.
+ */
+int v2x_pair_score_fwd(const void* q, float* scores, const double* trans, const int64_t* num_agent, const float* w2,
+                       const float* b2, const float* w3, const float* b3, const float* w4, const float* b4,
+                       int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t planes, int32_t only_v2i,
+                       void* stream);
+
+/*
+ * AgentWiseWeightedFusion.py:17-26,73-74: coef[b,i,:] = softmax_k relu(b5 + sum_p w5f[p] * s[b,i,k,p]) over k < na[b]
+ * (conv1_5 is a 32x32 "valid" conv over the whole map; w5f = its filter with rows mirrored, because scores live in
+ * the un-flipped domain).  coef: fp32 [B][A][A], zeros elsewhere.
+ */
+int v2x_agent_softmax_fwd(const float* scores, const float* w5f, const float* b5, const int64_t* num_agent,
+                          float* coef, int32_t batch, int32_t agents, int32_t hw, void* stream);
+
+/*
+ * out[b,i,p] = sum_k c * (k == i ? x[b,i,p] : warp_{k->i}(x[b,k])[p]) over participating k < na[b];
+ * coef_mode 0: c = coef[b][i][k] (AgentWiseWeightedFusion.py:27-34);
+ * coef_mode 1: coef = scores [B][A][A][h*w] and c = exp(s_k) / sum_k' exp(s_k') per pixel (DiscoNet.py:88-107).
+ * Agent slots i >= na[b] keep their own map.
+ */
+int v2x_warp_weighted_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent, const float* coef,
+                          int32_t coef_mode, int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c,
+                          int32_t planes, int32_t only_v2i, void* stream);
+
+/* out[unit] = x[unit] for agent slots absent from their scene (i >= na[b]); map_elems = h*w*c per map.  Restores
+ * FusionBase's "only present agents are rewritten" (FusionBase.py:41-63) after a fuse stage that touched every map. */
+int v2x_restore_absent_fwd(const void* x, void* out, const int64_t* num_agent, int32_t batch, int32_t agents,
+                           int64_t map_elems, int32_t planes, void* stream);
+
+/* ---- input densification on device (CP/datasets/V2XSimDet.py:291-302) ------------------------------------- */
+
+/*
+ * Sparse voxel index list -> dense occupancy BEV in the conv path's act layout.  Replaces, per agent and frame,
+ *   curr_voxels = np.zeros(dims, bool); curr_voxels[i0, i1, i2] = 1; np.rot90(curr_voxels, 3); .astype(np.float32)
+ * (V2XSimDet.py:294-302) + the dense H2D copy + v2x_pack_input.  idx: int32 [capacity][4] rows (map, i0, i1, i2);
+ * count: DEVICE int32 scalar = valid rows (<= capacity), read by the kernel so a captured graph replays with new
+ * counts; out: act [planes][n_maps][h][w][c_pad] (zeroed here, then 1.0 scattered; rot90_k3 != 0 applies
+ * np.rot90(., 3): voxel (i0, i1) -> pixel (i1, h - 1 - i0)); bad_count: DEVICE int32, incremented once per
+ * out-of-range row (such rows are dropped; the caller checks it -- numpy raises IndexError there).
+ */
+int v2x_voxelize_fwd(const int32_t* idx, const int32_t* count, int32_t capacity, void* out, int32_t n_maps, int32_t h,
+                     int32_t w, int32_t c, int32_t c_pad, int32_t planes, int32_t rot90_k3, int32_t* bad_count,
+                     void* stream);
+
+/* bool / uint8 NHWC occupancy [n_pixels][c] (non-zero = 1.0) -> act bf16 planes, channels zero-padded to c_pad: the
+ * `padded_voxel_points` array before its .astype(np.float32) (V2XSimDet.py:299-302), 13 instead of 52 bytes/pixel. */
+int v2x_pack_input_u8(const uint8_t* x, void* out, int64_t n_pixels, int32_t c, int32_t c_pad, int32_t planes,
+                      void* stream);
+
 /* ---- segmentation UNet pieces (CP/models/seg/SegModelBase.py) ------------------------------ */
 /* fp32 NCHW [n][c][h][w] (what SegModule.py:49 hands the model) -> act bf16 planes NHWC, channels zero-padded to c_pad */
 int v2x_pack_input_nchw(const float* x, void* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pad,

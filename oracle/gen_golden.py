@@ -184,12 +184,87 @@ def gen_convgru(tag, seed):
     print(tag, "ok")
 
 
+def gen_fusion_det(tag, kind, batch, seed, present=None, only_v2i=False):
+    """Result dict of the live det FusionBase-family model ``kind`` (kd_flag = 0)."""
+    m = ref_loader.ref_fusion_det(kind, only_v2i=only_v2i)
+    sd = synth.fusion_det_state(kind, seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(batch, 5, seed, present=present)
+    with torch.no_grad():
+        r = m(bevs, trans, nat, batch_size=batch)
+    if kind == "disco":
+        r = r[0]   # (result, save_agent_weight_list) when kd_flag == 0 (DiscoNet.py:125-129)
+    out = {"meta": np.asarray([batch, 5, seed, int(only_v2i)], dtype=np.int64), "kind": np.asarray(kind)}
+    if present is not None:
+        out["present"] = np.asarray(present, dtype=np.int64)
+    summarize("loc", r["loc"], out)
+    summarize("cls", r["cls"], out)
+    out["cls.argmax_count"], out["cls.argmax_checksum"] = argmax_checksum(r["cls"])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+    print(tag, "loc.sum", out["loc.sum"], "cls.sum", out["cls.sum"])
+
+
+def gen_fusion_seg(tag, kind, batch, seed, present=None, only_v2i=False):
+    m = ref_loader.ref_fusion_seg(kind, only_v2i=only_v2i)
+    sd = synth.seg_fusion_state(kind, seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x, trans, nat = synth.make_seg_scene(batch, 5, seed, present=present)
+    with torch.no_grad():
+        r = m(x, trans, nat)
+    out = {"meta": np.asarray([batch, 5, seed, int(only_v2i)], dtype=np.int64), "kind": np.asarray(kind)}
+    if present is not None:
+        out["present"] = np.asarray(present, dtype=np.int64)
+    summarize("logits", r, out)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+    print(tag, "logits.sum", out["logits.sum"])
+
+
+def gen_teacher(tag, n, seed):
+    m = ref_loader.ref_teacher()
+    sd = synth.fafnet_state(seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    with torch.no_grad():
+        r = m(synth.make_bevs(n, seed))
+    out = {"meta": np.asarray([n, seed], dtype=np.int64)}
+    for name, t in zip(("x8", "x7", "x6", "x5", "x3", "x4"), r):
+        summarize(name, t, out)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+    print(tag, "x8.sum", out["x8.sum"])
+
+
+FUSION_FIXTURES = [  # (tag, family, kind, batch, seed, present, only_v2i)
+    ("fusion_det_mean_seed5", "det", "mean", 1, 5, None, False),
+    ("fusion_det_max_seed6_present4", "det", "max", 1, 6, [4], False),
+    ("fusion_det_sum_seed7_v2i", "det", "sum", 1, 7, None, True),
+    ("fusion_det_cat_B2_seed8_present35", "det", "cat", 2, 8, [3, 5], False),
+    ("fusion_det_agent_seed9_present4", "det", "agent", 1, 9, [4], False),
+    ("fusion_det_disco_B2_seed10_present53", "det", "disco", 2, 10, [5, 3], False),
+    ("fusion_seg_mean_seed11_present4", "seg", "mean", 1, 11, [4], False),
+    ("fusion_seg_cat_seed12", "seg", "cat", 1, 12, None, False),
+    ("fusion_seg_agent_seed13", "seg", "agent", 1, 13, None, False),
+    ("fusion_seg_disco_seed14_present3", "seg", "disco", 1, 14, [3], False),
+]
+
+
+def gen_fusion_all():
+    for tag, family, kind, batch, seed, present, v2i in FUSION_FIXTURES:
+        (gen_fusion_det if family == "det" else gen_fusion_seg)(tag, kind, batch, seed, present=present, only_v2i=v2i)
+    gen_teacher("teacher_n1_seed3", 1, 3)
+
+
 def main():
     if not ref_loader.available():
         print("reference tree not available; golden fixtures can only be generated in the build container")
         return 1
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if "--fusion-only" in sys.argv:
+        gen_fusion_all()
+        return 0
+    gen_fusion_all()
     gen_warp("warp_small_seed3", 3)
     gen_convgru("convgru_small_seed4", 4)
     gen_fafnet("fafnet_n2_seed0", 2, 0)

@@ -106,6 +106,32 @@ def ref_seg_when2com(n_classes=8, num_agent=5, warp_flag=1):
     return W(_seg_config(), in_channels=13, n_classes=n_classes, warp_flag=warp_flag, num_agent=num_agent)
 
 
+_FUSION_CLASSES = {"mean": "MeanFusion", "max": "MaxFusion", "sum": "SumFusion", "cat": "CatFusion",
+                   "agent": "AgentWiseWeightedFusion", "disco": "DiscoNet"}
+
+
+def ref_fusion_det(kind, num_agent=5, kd_flag=0, only_v2i=False):
+    install()
+    name = _FUSION_CLASSES[kind]
+    cls = getattr(importlib.import_module("coperception.models.det." + name), name)
+    return cls(ref_config(), layer=3, kd_flag=kd_flag, num_agent=num_agent, only_v2i=only_v2i)
+
+
+def ref_fusion_seg(kind, n_classes=8, num_agent=5, only_v2i=False):
+    install()
+    name = _FUSION_CLASSES[kind]
+    cls = getattr(importlib.import_module("coperception.models.seg." + name), name)
+    if kind == "disco":
+        return cls(13, n_classes, num_agent, kd_flag=False, only_v2i=only_v2i)
+    return cls(13, n_classes, num_agent, 0, only_v2i)
+
+
+def ref_teacher():
+    install()
+    TeacherNet = importlib.import_module("coperception.models.det.TeacherNet").TeacherNet
+    return TeacherNet(ref_config())
+
+
 class cpu_cuda_shim:
     """Shim 3: neutralise the hard-coded ``.cuda()`` of seg When2Com_UNet (When2Com_UNet.py:245) for CPU runs."""
 

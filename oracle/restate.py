@@ -385,3 +385,105 @@ def seg_when2com_forward(x, trans_matrices, num_agent_tensor, sd, agent_num=5, w
     fused = torch.flip(torch.cat([fuse[:, i] for i in range(agent_num)], 0), (2,))
     logits = seg_decode(fused, x1, x2, x3, sd)
     return dict(logits=logits, attn=attn, fused=fused, x4=x4) if stages else logits
+
+
+# ---------------------------------------------------------------------------------------------
+# Intermediate-fusion baselines (CP/models/det/base/FusionBase.py, CP/models/seg/FusionBase.py)
+# ---------------------------------------------------------------------------------------------
+def _pair_weight_net(x, sd, p, agent_wise=False):
+    """PixelWeightedFusionSoftmax.forward (DiscoNet.py:149-155) / AgentWeightedFusion.forward
+    (AgentWiseWeightedFusion.py:66-76): 1x1 convs 2C->128->32->8->1 (+ the 32x32 conv1_5), ReLU after each."""
+    x = F.relu(_bn(F.conv2d(x, sd[p + "conv1_1.weight"], sd[p + "conv1_1.bias"]), sd, p + "bn1_1"))
+    x = F.relu(_bn(F.conv2d(x, sd[p + "conv1_2.weight"], sd[p + "conv1_2.bias"]), sd, p + "bn1_2"))
+    x = F.relu(_bn(F.conv2d(x, sd[p + "conv1_3.weight"], sd[p + "conv1_3.bias"]), sd, p + "bn1_3"))
+    x = F.relu(F.conv2d(x, sd[p + "conv1_4.weight"], sd[p + "conv1_4.bias"]))
+    if agent_wise:
+        x = F.relu(F.conv2d(x, sd[p + "conv1_5.weight"], sd[p + "conv1_5.bias"]))
+    return x
+
+
+def fuse_rule(kind, tg, nb, sd, seg=False):
+    """``fusion()`` of the FusionBase subclasses on the neighbour list ``nb`` (nb[0] is the target ``tg``):
+    MeanFusion.py:11-12, MaxFusion.py:20-21, SumFusion.py:20-21, CatFusion.py:22-26,
+    AgentWiseWeightedFusion.py:24-43, DiscoNet.py:80-107 (det) and their seg twins."""
+    if kind == "mean":
+        return torch.mean(torch.stack(nb), dim=0)
+    if kind == "max":
+        return torch.max(torch.stack(nb), dim=0).values
+    if kind == "sum":
+        return torch.sum(torch.stack(nb), dim=0)
+    if kind == "cat":
+        p = "modulation_layer_3." if seg else "_modulation_layer_3._"
+        mean = torch.mean(torch.stack(nb), dim=0)
+        cat = torch.cat([tg, mean], dim=0).unsqueeze(0)
+        y = F.conv2d(cat, sd[p + "conv1_1.weight"], sd[p + "conv1_1.bias"])
+        return F.relu(_bn(y, sd, p + "bn1_1")).squeeze(0)
+    if kind == "agent":
+        w = [_pair_weight_net(torch.cat([tg, f], dim=0).unsqueeze(0), sd, "agent_weighted_fusion.", True) for f in nb]
+        soft = torch.squeeze(F.softmax(torch.tensor([float(t) for t in w]).unsqueeze(0), dim=1), 0)
+        out = 0
+        for k in range(len(nb)):
+            out = out + soft[k] * nb[k]
+        return out
+    if kind == "disco":
+        e = [torch.exp(torch.squeeze(_pair_weight_net(torch.cat([tg, f], dim=0).unsqueeze(0), sd,
+                                                      "pixel_weighted_fusion."))) for f in nb]
+        total = sum(e)
+        out = 0
+        for k in range(len(nb)):
+            out = out + torch.div(e[k], total) * nb[k]
+        return out
+    raise ValueError(kind)
+
+
+def fusion_stage(kind, feat_maps, trans_matrices, num_agent_tensor, sd, batch_size, agent_num, only_v2i=False,
+                 seg=False):
+    """The per-scene / per-agent loop of FusionBase.forward (FusionBase.py:31-63; seg/FusionBase.py:38-73) incl. the
+    H flips (DetModelBase.py:71-92,53-69; SegModelBase.py:46-58,80-88).  feat_maps: [A*B,C,h,w] agent-major."""
+    c, h, w = feat_maps.shape[1:]
+    size = (1, c, h, w)
+    feat = torch.flip(feat_maps, (2,))
+    local = torch.stack([feat[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)
+    upd = local.clone()
+    for b in range(batch_size):
+        na = int(num_agent_tensor[b, 0])
+        for i in range(na):
+            tg = local[b, i]
+            nb = [tg]
+            for j in range(na):
+                if j != i:
+                    if only_v2i and i != 0 and j != 0:
+                        continue
+                    nb.append(feature_transformation(local, b, j, i, trans_matrices, size))
+            upd[b, i] = fuse_rule(kind, tg, nb, sd, seg=seg)
+    return torch.flip(torch.cat([upd[:, i] for i in range(agent_num)], 0), (2,))
+
+
+def fusion_det_forward(kind, bevs, trans_matrices, num_agent_tensor, sd, batch_size=1, agent_num=5, only_v2i=False,
+                       stages=False):
+    """det FusionBase.forward / DiscoNet.forward (kd_flag = 0 result dict)."""
+    enc = encode(bevs, sd, "u_encoder.")
+    fused = fusion_stage(kind, enc[3], trans_matrices, num_agent_tensor, sd, batch_size, agent_num, only_v2i)
+    dec_in = list(enc)
+    dec_in[3] = fused
+    dec = decode(*dec_in, sd, "decoder.", kd_flag=True)
+    res = heads(dec[0], sd)
+    if stages:
+        res = dict(res, enc=enc, fused=fused, dec=dec)
+    return res
+
+
+def seg_fusion_forward(kind, x, trans_matrices, num_agent_tensor, sd, agent_num=5, only_v2i=False, stages=False):
+    """seg FusionBase.forward (seg/FusionBase.py:25-84), kd_flag = False."""
+    x1, x2, x3, x4 = seg_encode(x, sd)
+    batch_size = x.size(0) // agent_num
+    fused = fusion_stage(kind, x4, trans_matrices, num_agent_tensor, sd, batch_size, agent_num, only_v2i, seg=True)
+    logits = seg_decode(fused, x1, x2, x3, sd)
+    return dict(logits=logits, x4=x4, fused=fused) if stages else logits
+
+
+def teacher_forward(bevs, sd):
+    """TeacherNet.forward == STPN_KD.forward (Backbone.py:251-257): (x_8, x_7, x_6, x_5, x_3, x_4)."""
+    enc = encode(bevs, sd, "stpn.")
+    dec = decode(*enc, sd, "stpn.", kd_flag=True)
+    return (*dec, enc[3], enc[4])

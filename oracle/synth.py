@@ -291,6 +291,61 @@ def seg_when2com_state(seed=0, n_classes=8):
     return sd
 
 
+# ---------------------------------------------------------------------------------------------
+# intermediate-fusion baselines (CP/models/det/base/FusionBase.py, CP/models/seg/FusionBase.py)
+# ---------------------------------------------------------------------------------------------
+FUSION_KINDS = ("mean", "max", "sum", "cat", "agent", "disco")
+
+
+def _pair_weight_net_state(sd, g, p, channel, agent_wise):
+    """PixelWeightedFusionSoftmax (DiscoNet.py:132-147) / AgentWeightedFusion (AgentWiseWeightedFusion.py:44-64).
+    The last layers are drawn positive so the ReLU'd scores are non-zero and differ between the list members (an
+    all-zero score map would make every fusion weight 1/n and hide indexing errors)."""
+    _conv(sd, g, p + "conv1_1", 128, 2 * channel, k=(1, 1))
+    _bn(sd, g, p + "bn1_1", 128)
+    _conv(sd, g, p + "conv1_2", 32, 128, k=(1, 1))
+    _bn(sd, g, p + "bn1_2", 32)
+    _conv(sd, g, p + "conv1_3", 8, 32, k=(1, 1))
+    _bn(sd, g, p + "bn1_3", 8)
+    sd[p + "conv1_4.weight"] = g.uniform((1, 8, 1, 1), 0.0, 0.8)
+    sd[p + "conv1_4.bias"] = g.uniform((1,), 0.0, 0.2)
+    if agent_wise:
+        sd[p + "conv1_5.weight"] = g.uniform((1, 1, 32, 32), 0.0, 4.0 / 1024)
+        sd[p + "conv1_5.bias"] = g.uniform((1,), 0.0, 0.2)
+
+
+def _fusion_extra_state(sd, g, kind, channel, seg):
+    if kind == "cat":
+        p = "modulation_layer_3." if seg else "_modulation_layer_3._"
+        _conv(sd, g, p + "conv1_1", channel, 2 * channel, k=(1, 1))
+        _bn(sd, g, p + "bn1_1", channel)
+    elif kind == "agent":
+        _pair_weight_net_state(sd, g, "agent_weighted_fusion.", channel, True)
+    elif kind == "disco":
+        _pair_weight_net_state(sd, g, "pixel_weighted_fusion.", channel, False)
+
+
+def fusion_det_state(kind, seed=0):
+    """state_dict of the det FusionBase family (IntermediateModelBase.py:24-25 + the subclass' fusion net)."""
+    assert kind in FUSION_KINDS
+    g = _Gen(seed)
+    sd = OrderedDict()
+    heads_state(sd, g)
+    backbone_state(sd, g, "u_encoder.")
+    backbone_state(sd, g, "decoder.")
+    _fusion_extra_state(sd, g, kind, 256, False)
+    return sd
+
+
+def seg_fusion_state(kind, seed=0, n_classes=8):
+    """state_dict of the seg FusionBase family (SegModelBase + the subclass' fusion net at C = 512)."""
+    assert kind in FUSION_KINDS
+    g = _Gen(seed)
+    sd = seg_unet_state(seed, n_classes, g=g)
+    _fusion_extra_state(sd, g, kind, 512, True)
+    return sd
+
+
 def make_seg_scene(batch=1, num_agent=5, seed=0, p=0.03, present=None):
     """(x [A*B,13,256,256] fp32 NCHW as SegModule.py:49 builds it, trans, num_agent_tensor)."""
     bevs, trans, nat = make_scene(batch, num_agent, seed, p=p, present=present)
@@ -336,3 +391,34 @@ def make_gt_from_detections(dets, seed=0, keep=0.7, jitter=0.25, extra=3):
         ex = base[None] + np.stack([cx, cy], axis=-1)[:, None, :]
         out.append(np.concatenate([g, ex], axis=0).reshape(-1, 8))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# sparse voxel inputs (CP/datasets/V2XSimDet.py:291-302)
+# ---------------------------------------------------------------------------------------------
+def make_voxel_indices(num_maps, seed=0, points=3000, dims=(256, 256, 13), duplicates=True):
+    """Per-map int32 [n, 3] voxel index lists like the dataset's ``voxel_indices_0`` (duplicates allowed, as a LiDAR
+    sweep quantised to voxels produces them)."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for m in range(num_maps):
+        n = points + 97 * m
+        idx = np.stack([rng.randint(0, d, size=n) for d in dims], 1).astype(np.int32)
+        if duplicates:
+            idx = np.concatenate([idx, idx[: n // 10]], 0)
+        out.append(idx)
+    return out
+
+
+def densify_voxels(indices, dims=(256, 256, 13)):
+    """Restatement of V2XSimDet.py:294-302 for one map: zeros(bool) -> scatter 1 -> np.rot90(., 3) -> float32."""
+    curr_voxels = np.zeros(dims, dtype=bool)
+    curr_voxels[indices[:, 0], indices[:, 1], indices[:, 2]] = 1
+    curr_voxels = np.rot90(curr_voxels, 3)
+    return np.ascontiguousarray(curr_voxels).astype(np.float32)
+
+
+def voxel_rows(index_lists):
+    """[(n_m, 3)] per map -> one int32 [sum n_m, 4] tensor of (map, i0, i1, i2) rows for v2x_voxelize_fwd."""
+    rows = [np.concatenate([np.full((len(ix), 1), m, dtype=np.int32), ix], 1) for m, ix in enumerate(index_lists)]
+    return torch.from_numpy(np.concatenate(rows, 0))

@@ -83,3 +83,28 @@ def test_dropin_state_dict_schema():
     import torch
     dp = torch.nn.DataParallel(m)
     dp.load_state_dict({"module." + k: v for k, v in want.items()}, strict=True)
+
+
+def test_fusion_family_state_dict_schema():
+    """Every class of CP/models/{det,seg}/__init__.py exists in the drop-in package with the reference's parameter names
+    (strict load of reference-format state dicts; the synthetic dicts are themselves pinned to the live reference by
+    tests/test_oracle_golden.py)."""
+    import coperception.models.det as det
+    import coperception.models.seg as seg
+    from oracle import synth
+    from v2x_b200 import default_det_config
+    names = {"mean": "MeanFusion", "max": "MaxFusion", "sum": "SumFusion", "cat": "CatFusion",
+             "agent": "AgentWiseWeightedFusion", "disco": "DiscoNet"}
+    for kind, name in names.items():
+        m = getattr(det, name)(default_det_config(), kd_flag=0)
+        m.load_state_dict(synth.fusion_det_state(kind, 0), strict=True)
+        cls = getattr(seg, name)
+        m = cls(13, 8, 5, kd_flag=False) if kind == "disco" else cls(13, 8, 5, 0, False)
+        m.load_state_dict(synth.seg_fusion_state(kind, 0), strict=True)
+    det.TeacherNet(default_det_config()).load_state_dict(synth.fafnet_state(0), strict=True)
+    for name in ("V2VNet", "When2com", "FaFNet", "TeacherNet", "DiscoNet", "SumFusion", "MeanFusion", "MaxFusion",
+                 "CatFusion", "AgentWiseWeightedFusion"):
+        assert hasattr(det, name), name
+    for name in ("UNet", "V2VNet", "When2Com_UNet", "MeanFusion", "MaxFusion", "SumFusion", "CatFusion",
+                 "AgentWiseWeightedFusion", "DiscoNet", "SegModelBase", "FusionBase"):
+        assert hasattr(seg, name), name

@@ -410,3 +410,54 @@ def test_convgru_pre_act_identity_columns(c, impl, planes):
     err = rel_err(ops.act_to_float(out), ref)
     print("gru pre_act c=%d %s planes=%d rel_err=%.3e" % (c, impl, planes, err))
     assert err < TOL[planes]
+
+
+def test_voxelize_and_u8_inputs_match_dense_pack():
+    """the on-device scatter + rot90 of sparse voxel rows, and the uint8 pack, produce bit-identical
+    act tensors to packing the dataset's dense fp32 BEV (V2XSimDet.py:294-302 restated in oracle.synth.densify_voxels)."""
+    from oracle import synth
+    from v2x_b200 import ops
+    ops.require_gpu()
+    lists = synth.make_voxel_indices(3, seed=5)
+    dense = torch.from_numpy(np.stack([synth.densify_voxels(ix) for ix in lists]))          # [3,256,256,13] fp32
+    want = ops.pack_input(dense.cuda(), 16, 2)
+    rows = synth.voxel_rows(lists).cuda()
+    cap = rows.shape[0] + 1000
+    idx = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+    idx[: rows.shape[0]] = rows
+    idx[rows.shape[0]:] = 7          # rows beyond `count` must be ignored
+    count = torch.tensor([rows.shape[0]], dtype=torch.int32, device="cuda")
+    bad = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    out = torch.full_like(want, 3.0)
+    ops.voxelize(idx, count, out, 13, bad, rot90=True)
+    assert torch.equal(out, want) and int(bad.item()) == 0
+    u8 = ops.pack_input_u8((dense > 0).cuda(), 16, 2)
+    assert torch.equal(u8, want)
+    # out-of-range rows are dropped and counted, never written
+    idx[0] = torch.tensor([0, 256, 0, 0], dtype=torch.int32)
+    idx[1] = torch.tensor([3, 0, 0, 0], dtype=torch.int32)
+    ops.voxelize(idx, count, out, 13, bad, rot90=True)
+    assert int(bad.item()) == 2
+
+
+def test_v2vnet_forward_from_voxels_and_u8_is_bit_identical():
+    from coperception.models.det import V2VNet
+    from oracle import synth
+    from v2x_b200 import default_det_config
+    sd = synth.v2vnet_det_state(1)
+    lists = synth.make_voxel_indices(5, seed=9, points=20000)
+    dense = torch.from_numpy(np.stack([synth.densify_voxels(ix) for ix in lists])).unsqueeze(1)   # [5,1,256,256,13]
+    _, trans, nat = synth.make_scene(1, 5, seed=9)
+    m = V2VNet(default_det_config(), 3, 3, 256, num_agent=5)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        a = {k: v.clone() for k, v in m(dense.cuda(), trans.cuda(), nat.cuda(), batch_size=1).items()}
+        b = {k: v.clone() for k, v in m((dense > 0).cuda(), trans.cuda(), nat.cuda(), batch_size=1).items()}
+        c = m.forward_voxels(synth.voxel_rows(lists).cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    for k in ("loc", "cls"):
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
+    with pytest.raises(IndexError):
+        bad = synth.voxel_rows(lists)
+        bad[0, 3] = 13
+        m.forward_voxels(bad.cuda(), trans.cuda(), nat.cuda(), batch_size=1)

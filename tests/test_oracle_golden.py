@@ -113,3 +113,63 @@ def test_seg_models(golden_dir, tag, kind):
             r = restate.seg_when2com_forward(x, trans, nat, synth.seg_when2com_state(seed), agent_num=a, warp_flag=warp,
                                              inference=str(g["inference"]))
     _check("logits", r, g)
+
+
+def _fusion_fixtures(family):
+    from oracle.gen_golden import FUSION_FIXTURES
+    return [f for f in FUSION_FIXTURES if f[1] == family]
+
+
+@pytest.mark.parametrize("fx", _fusion_fixtures("det"), ids=lambda f: f[0])
+def test_fusion_det(golden_dir, fx):
+    """FusionBase family (Mean/Max/Sum/Cat/AgentWise/DiscoNet det) restatement vs the live reference modules."""
+    tag, _, kind, batch, seed, present, v2i = fx
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    assert [int(v) for v in g["meta"]] == [batch, 5, seed, int(v2i)] and str(g["kind"]) == kind
+    sd = synth.fusion_det_state(kind, seed)
+    bevs, trans, nat = synth.make_scene(batch, 5, seed, present=present)
+    with torch.no_grad():
+        r = restate.fusion_det_forward(kind, bevs, trans, nat, sd, batch_size=batch, agent_num=5, only_v2i=v2i)
+    _check("loc", r["loc"], g)
+    _check("cls", r["cls"], g)
+
+
+@pytest.mark.parametrize("fx", _fusion_fixtures("seg"), ids=lambda f: f[0])
+def test_fusion_seg(golden_dir, fx):
+    tag, _, kind, batch, seed, present, v2i = fx
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    sd = synth.seg_fusion_state(kind, seed)
+    x, trans, nat = synth.make_seg_scene(batch, 5, seed, present=present)
+    with torch.no_grad():
+        r = restate.seg_fusion_forward(kind, x, trans, nat, sd, agent_num=5, only_v2i=v2i)
+    _check("logits", r, g)
+
+
+def test_teacher(golden_dir):
+    g = np.load(os.path.join(golden_dir, "teacher_n1_seed3.npz"))
+    n, seed = [int(v) for v in g["meta"]]
+    with torch.no_grad():
+        r = restate.teacher_forward(synth.make_bevs(n, seed), synth.fafnet_state(seed))
+    for name, t in zip(("x8", "x7", "x6", "x5", "x3", "x4"), r):
+        _check(name, t, g)
+
+
+def test_fusion_weights_are_not_degenerate():
+    """The synthetic pair-weight nets must produce non-uniform fusion weights, else the fixtures could not tell a
+    wrong (target, member) pairing from a right one."""
+    sd = synth.fusion_det_state("disco", 10)
+    g = torch.Generator().manual_seed(0)
+    tg, nb = torch.rand((256, 32, 32), generator=g), torch.rand((256, 32, 32), generator=g)
+    with torch.no_grad():
+        s0 = restate._pair_weight_net(torch.cat([tg, tg]).unsqueeze(0), sd, "pixel_weighted_fusion.")
+        s1 = restate._pair_weight_net(torch.cat([tg, nb]).unsqueeze(0), sd, "pixel_weighted_fusion.")
+    assert (s0 > 0).float().mean() > 0.5 and (s0 - s1).abs().mean() > 1e-2
+
+
+def test_densify_voxels_is_scatter_then_rot90():
+    """oracle.synth.densify_voxels (V2XSimDet.py:294-302): voxel (i0, i1, z) lands on pixel (i1, 255 - i0, z)."""
+    lists = synth.make_voxel_indices(1, seed=2, points=500)
+    d = synth.densify_voxels(lists[0])
+    assert d.dtype == np.float32 and d.shape == (256, 256, 13)
+    assert all(d[i1, 255 - i0, z] == 1.0 for i0, i1, z in lists[0])
+    assert int(d.sum()) == len(np.unique(lists[0], axis=0))

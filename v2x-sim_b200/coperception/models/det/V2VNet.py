@@ -37,8 +37,32 @@ class V2VNet(B200DetModel):
         if dev.type != "cuda":
             raise RuntimeError("v2x_b200 V2VNet needs CUDA tensors (no CPU fallback); got %s" % dev)
         assert bevs.shape[0] == batch_size * self.agent_num, "bevs must hold batch_size * num_agent maps"
-        key = ("v2v", int(batch_size), dev.index, self.precision)
+        # bool / uint8 occupancy grids (the dataset's array before .astype(np.float32)) are expanded on device
+        mode = "u8" if bevs.dtype in (torch.uint8, torch.bool) else "f32"
+        key = ("v2v", int(batch_size), dev.index, self.precision, mode)
         plan = self._get_plan(key, lambda: nets.V2VNetDetPlan(
             self._state(), int(batch_size), self.agent_num, gnn_iter=self.gnn_iter_num, planes=self._planes(),
-            device=dev, only_v2i=self.only_v2i))
-        return plan.forward(bevs.to(torch.float32), trans_matrices.to(torch.float64), num_agent_tensor.to(torch.int64))
+            device=dev, only_v2i=self.only_v2i, input_mode=mode))
+        if mode == "u8":
+            bevs = bevs.view(torch.uint8) if bevs.dtype == torch.bool else bevs
+        else:
+            bevs = bevs.to(torch.float32)
+        return plan.forward(bevs, trans_matrices.to(torch.float64), num_agent_tensor.to(torch.int64))
+
+    def forward_voxels(self, voxel_rows, trans_matrices, num_agent_tensor, batch_size=1, capacity=0):
+        """Extension of the reference surface: ``voxel_rows`` int32 [n, 4] = (map, i0, i1, i2), the
+        dataset's sparse ``voxel_indices_0`` of every map prefixed by its agent-major map index; the dense BEV
+        (scatter + np.rot90(., 3), V2XSimDet.py:294-299) is built on device.  Same result dict as forward()."""
+        from v2x_b200 import nets
+        self._check_eval()
+        dev = trans_matrices.device
+        if dev.type != "cuda":
+            raise RuntimeError("v2x_b200 V2VNet needs CUDA tensors (no CPU fallback); got %s" % dev)
+        cap = int(capacity) or max(32768 * batch_size * self.agent_num, int(voxel_rows.shape[0]))
+        key = ("v2v", int(batch_size), dev.index, self.precision, "voxels", cap)
+        plan = self._get_plan(key, lambda: nets.V2VNetDetPlan(
+            self._state(), int(batch_size), self.agent_num, gnn_iter=self.gnn_iter_num, planes=self._planes(),
+            device=dev, only_v2i=self.only_v2i, input_mode="voxels", voxel_capacity=cap))
+        out = plan.forward(voxel_rows, trans_matrices.to(torch.float64), num_agent_tensor.to(torch.int64))
+        plan.check_voxels()
+        return out

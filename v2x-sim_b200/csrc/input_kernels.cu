@@ -1,0 +1,100 @@
+// Input densification on device: the dataset builds every agent's dense 256x256x13 fp32 BEV on the host
+// from a sparse voxel index list (CP/datasets/V2XSimDet.py:291-302: zeros -> scatter 1 -> np.rot90(., 3) -> float32),
+// 3.4 MB per agent per frame over PCIe.  Here the index list (16 bytes per occupied voxel) or a bool/uint8 BEV
+// (13 bytes per pixel) is uploaded instead and expanded straight into the conv path's bf16 NHWC act layout.
+#include "common.cuh"
+
+namespace v2x {
+
+// idx: [capacity][4] int32 = (map, i0, i1, i2) with (i0, i1, i2) indexing the un-rotated [H][W][C] voxel grid;
+// count: device scalar, number of valid rows (so a captured CUDA graph replays with a new count).
+// np.rot90(m, 3)[r, c] = m[H - 1 - c, r]  =>  voxel (i0, i1) lands on pixel (r, c) = (i1, H - 1 - i0).
+__global__ void voxel_scatter_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ count, int capacity,
+                                     __nv_bfloat16* __restrict__ out, int n_maps, int H, int W, int C, int c_pad,
+                                     int rot90_k3, int* __restrict__ bad) {
+  const int n = min(*count, capacity);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(idx) + t);
+    const int map = v.x, i0 = v.y, i1 = v.z, z = v.w;
+    if (map < 0 || map >= n_maps || i0 < 0 || i0 >= H || i1 < 0 || i1 >= W || z < 0 || z >= C) {
+      atomicAdd(bad, 1);   // numpy would raise IndexError; reported to the host, never written
+      continue;
+    }
+    const int r = rot90_k3 ? i1 : i0;
+    const int c = rot90_k3 ? (H - 1 - i0) : i1;
+    out[(((long long)map * H + r) * W + c) * c_pad + z] = __float2bfloat16_rn(1.f);
+  }
+}
+
+// bool / uint8 NHWC [n_pixels][c] (non-zero == occupied, as ndarray.astype(np.float32) of a bool grid) -> act bf16
+// planes [planes][n_pixels][c_pad]; the lo plane of {0,1} values is all zeros.
+__global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n_pixels,
+                                     int c, int c_pad, int planes) {
+  const int groups = c_pad / 8;
+  const long long total = n_pixels * groups;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const long long pix = gid / groups;
+    const int g = (int)(gid - pix * groups);
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = g * 8 + 2 * i;
+      const float v0 = (c0 < c && __ldg(x + pix * c + c0)) ? 1.f : 0.f;
+      const float v1 = (c0 + 1 < c && __ldg(x + pix * c + c0 + 1)) ? 1.f : 0.f;
+      w[i] = pack_bf16x2(__float2bfloat16_rn(v0), __float2bfloat16_rn(v1));
+    }
+    __nv_bfloat16* dst = out + pix * c_pad + g * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (planes == 2) *reinterpret_cast<uint4*>(dst + n_pixels * c_pad) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+}  // namespace v2x
+
+using namespace v2x;
+
+extern "C" int v2x_voxelize_fwd(const int32_t* idx, const int32_t* count, int32_t capacity, void* out, int32_t n_maps,
+                                int32_t h, int32_t w, int32_t c, int32_t c_pad, int32_t planes, int32_t rot90_k3,
+                                int32_t* bad_count, void* stream) {
+  V2X_REQUIRE(idx && count && out && bad_count, "null pointer");
+  V2X_REQUIRE(capacity > 0 && n_maps > 0 && h > 0 && w > 0 && c > 0 && c_pad >= c && c_pad % 8 == 0, "bad geometry");
+  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  V2X_REQUIRE(!rot90_k3 || h == w, "rot90 needs a square grid");
+  V2X_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15) == 0, "idx must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = (size_t)planes * n_maps * h * w * c_pad * sizeof(__nv_bfloat16);
+  V2X_CUDA_TRY(cudaMemsetAsync(out, 0, bytes, s));
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  long long blocks = ((long long)capacity + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  voxel_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(idx, count, capacity, reinterpret_cast<__nv_bfloat16*>(out),
+                                                        n_maps, h, w, c, c_pad, rot90_k3, bad_count);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_pack_input_u8(const uint8_t* x, void* out, int64_t n_pixels, int32_t c, int32_t c_pad, int32_t planes,
+                                 void* stream) {
+  V2X_REQUIRE(x && out && n_pixels > 0, "null/empty input");
+  V2X_REQUIRE(c > 0 && c_pad >= c && c_pad % 8 == 0, "c_pad must be a multiple of 8 and >= c");
+  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const long long total = (long long)n_pixels * (c_pad / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  pack_input_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                          n_pixels, c, c_pad, planes);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}

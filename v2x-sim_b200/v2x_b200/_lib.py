@@ -76,6 +76,13 @@ SYMBOLS = [
     ("v2x_upsample_bilinear2_fwd", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_attn_scores_fwd", C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_warp_gated_fwd", C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_warp_reduce_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_pair_score_fwd", C.c_int, [_P] * 10 + [_I32] * 6 + [_P]),
+    ("v2x_agent_softmax_fwd", C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
+    ("v2x_warp_weighted_fwd", C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_voxelize_fwd", C.c_int, [_P, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    ("v2x_pack_input_u8", C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
+    ("v2x_restore_absent_fwd", C.c_int, [_P, _P, _P, _I32, _I32, _I64, _I32, _P]),
 ]
 
 _lib = None

@@ -99,13 +99,55 @@ class DetPlan:
         self.add(ConvLaunch(pc, srcs, out0=out, upsample2x=upsample2x, **kw))
         return out
 
+    def check_voxels(self):
+        """Voxel mode: raise (like numpy's IndexError at V2XSimDet.py:296) if any uploaded row was out of range.
+        Reads one device int32 -- a host sync, so callers on a latency-critical loop may skip it."""
+        bad = int(self.vox_bad.item())
+        if bad:
+            self.vox_bad.zero_()
+            raise IndexError("%d voxel rows were outside the %dx%dx%d grid / map range" % (bad, H0, W0, IN_C))
+
     # ---- encoder / decoder / heads (Backbone.py:89-242, DetModelBase.py:226-265) ----
-    def build_input(self):
-        self.bev_in = torch.zeros((self.n, 1, H0, W0, IN_C), dtype=torch.float32, device=self.device)
+    def build_input(self, mode="f32", voxel_capacity=0):
+        """The first launch of every plan: the caller's input -> act [P, N, 256, 256, 16].
+        mode "f32": fp32 BEV [N,1,256,256,13] (what the reference scripts hand the model, V2VNet.py:47-51);
+        mode "u8":  the same grid as bool/uint8 (V2XSimDet.py:299 before .astype(np.float32)): 4x fewer H2D bytes;
+        mode "voxels": sparse voxel rows (map, i0, i1, i2) int32, scattered + rot90'd on device (V2XSimDet.py:294-299,
+        SURVEY 8(f3)); ``voxel_capacity`` rows are reserved, the live count is a device scalar."""
+        self.input_mode = mode
         x_in = self.act("x_in", H0, W0, IN_C_PAD)
-        bev, planes = self.bev_in, self.planes
-        self.add(lambda: ops.pack_input(bev, IN_C_PAD, planes, out=x_in))
+        planes = self.planes
+        if mode == "f32":
+            self.bev_in = torch.zeros((self.n, 1, H0, W0, IN_C), dtype=torch.float32, device=self.device)
+            bev = self.bev_in
+            self.add(lambda: ops.pack_input(bev, IN_C_PAD, planes, out=x_in))
+        elif mode == "u8":
+            self.bev_in = torch.zeros((self.n, 1, H0, W0, IN_C), dtype=torch.uint8, device=self.device)
+            bev = self.bev_in
+            self.add(lambda: ops.pack_input_u8(bev, IN_C_PAD, planes, out=x_in))
+        elif mode == "voxels":
+            cap = int(voxel_capacity) or 32768 * self.n
+            self.vox_idx = torch.zeros((cap, 4), dtype=torch.int32, device=self.device)
+            self.vox_count = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            self.vox_bad = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            idx, cnt, bad = self.vox_idx, self.vox_count, self.vox_bad
+            self.add(lambda: ops.voxelize(idx, cnt, x_in, IN_C, bad, rot90=True))
+        else:
+            raise ValueError("input mode must be f32, u8 or voxels")
         return x_in
+
+    def set_bevs(self, bevs):
+        """Async copy of the step's input into the plan's static buffer: a dense BEV (modes f32 / u8) or, in voxel
+        mode, an int32 [n, 4] tensor of (map, i0, i1, i2) rows."""
+        if self.input_mode == "voxels":
+            n = int(bevs.shape[0])
+            if n > self.vox_idx.shape[0]:
+                raise ops.V2XError("%d voxel rows exceed the plan's capacity %d" % (n, self.vox_idx.shape[0]))
+            assert bevs.dtype == torch.int32 and bevs.dim() == 2 and bevs.shape[1] == 4
+            self.vox_idx[:n].copy_(bevs, non_blocking=True)
+            self.vox_count.fill_(n)
+        else:
+            self.bev_in.copy_(bevs.reshape(self.bev_in.shape), non_blocking=True)
 
     def build_encoder(self, w: BackboneWeights, x_in, tag="", upsample_x4=True):
         c = w.c
@@ -209,7 +251,7 @@ class V2VNetDetPlan(DetPlan):
     """det V2VNet forward (V2VNet.py:47-120) for ``batch`` scenes x ``agents`` agent slots."""
 
     def __init__(self, sd, batch: int, agents: int = 5, gnn_iter: int = 3, planes: int = 1, device="cuda",
-                 only_v2i=False):
+                 only_v2i=False, input_mode="f32", voxel_capacity=0):
         super().__init__(batch * agents, planes, device)
         ops.require_gpu()
         self.batch, self.agents, self.gnn_iter = batch, agents, gnn_iter
@@ -223,7 +265,7 @@ class V2VNetDetPlan(DetPlan):
         self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
 
-        x_in = self.build_input()
+        x_in = self.build_input(input_mode, voxel_capacity)
         x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
         c3 = x3.shape[-1]
         # neighbours are always warped from the ORIGINAL encoder maps (V2VNet.py:85-94), so the mean is
@@ -237,7 +279,7 @@ class V2VNetDetPlan(DetPlan):
 
     def set_inputs(self, bevs, trans_matrices, num_agent_tensor):
         """Async copies into the plan's static input buffers (host or device sources)."""
-        self.bev_in.copy_(bevs.reshape(self.bev_in.shape), non_blocking=True)
+        self.set_bevs(bevs)
         self.trans.copy_(trans_matrices.reshape(self.trans.shape), non_blocking=True)
         self.num_agent.copy_(num_agent_tensor.reshape(self.num_agent.shape), non_blocking=True)
 
@@ -250,20 +292,23 @@ class V2VNetDetPlan(DetPlan):
 class FaFNetPlan(DetPlan):
     """FaFNet / STPN forward: encoder -> decoder -> heads, no fusion (FaFNet.py:28-39)."""
 
-    def __init__(self, sd, n_maps: int, planes: int = 1, device="cuda"):
+    def __init__(self, sd, n_maps: int, planes: int = 1, device="cuda", heads: bool = True, input_mode="f32",
+                 voxel_capacity=0):
         super().__init__(n_maps, planes, device)
         ops.require_gpu()
         self.w = BackboneWeights(sd, "stpn.", planes, self.device, encoder=True, decoder=True)
-        self.head_w = HeadWeights(sd, planes, self.device)
-        x_in = self.build_input()
+        x_in = self.build_input(input_mode, voxel_capacity)
         x0, x1, x2, x3, x4u = self.build_encoder(self.w, x_in)
         x8 = self.build_decoder(self.w, x0, x1, x2, x3, x4u)
-        self.build_heads(self.head_w, x8)
+        self.has_heads = heads   # TeacherNet.forward returns the STPN layers only (TeacherNet.py:10-13)
+        if heads:
+            self.head_w = HeadWeights(sd, planes, self.device)
+            self.build_heads(self.head_w, x8)
 
     def forward(self, bevs):
-        self.bev_in.copy_(bevs.reshape(self.bev_in.shape), non_blocking=True)
+        self.set_bevs(bevs)
         self.run()
-        return self.result()
+        return self.result() if self.has_heads else None
 
 
 class When2comDetPlan(DetPlan):
@@ -439,3 +484,100 @@ class V2VNetDetShardedPlan(DetPlan):
         self.set_inputs(bevs_local, trans_matrices, num_agent_tensor)
         self.run()
         return self.result()
+
+
+def _pair_mlp(sd, p, dev):
+    """Layers 2..4 of PixelWeightedFusionSoftmax / AgentWeightedFusion (DiscoNet.py:136-155) with BN(eval) folded."""
+    w2, b2 = ops.fold_bn_1x1(sd[p + "conv1_2.weight"], sd[p + "conv1_2.bias"], _bn(sd, p + "bn1_2"), dev)
+    w3, b3 = ops.fold_bn_1x1(sd[p + "conv1_3.weight"], sd[p + "conv1_3.bias"], _bn(sd, p + "bn1_3"), dev)
+    w4, b4 = ops.fold_bn_1x1(sd[p + "conv1_4.weight"], sd[p + "conv1_4.bias"], None, dev)
+    return (w2, b2, w3, b3, w4.reshape(-1).contiguous(), b4)
+
+
+class FuseStage:
+    """The cross-agent fuse step of the FusionBase family on an agent-major layer map ``x`` (act [P, A*B, h, w, C]),
+    shared by the det (FusionBase.py:23-75, DiscoNet.py:36-129) and seg (seg/FusionBase.py:25-84) plans.
+
+    kind: "mean" | "sum" | "max" | "cat" | "agent" | "disco".  Adds its launches to ``plan`` and returns the fused act."""
+
+    KINDS = ("mean", "sum", "max", "cat", "agent", "disco")
+    PREFIX = {"cat_det": "_modulation_layer_3._", "cat_seg": "modulation_layer_3.", "agent": "agent_weighted_fusion.",
+              "disco": "pixel_weighted_fusion."}
+
+    def __init__(self, plan, kind, sd, x, trans, num_agent, batch, agents, *, only_v2i=False, seg=False):
+        assert kind in self.KINDS
+        dev, planes = plan.device, plan.planes
+        _, n, h, w, c = x.shape
+        na = num_agent
+        if kind in ("mean", "sum", "max"):
+            out = plan.act("fused", h, w, c)
+            plan.add(lambda: ops.warp_reduce(x, trans, na, batch, agents, kind, only_v2i=only_v2i, out=out))
+        elif kind == "cat":
+            # mean over the list, cat([tg, mean]) -> 1x1 conv + BN + ReLU (CatFusion.py:22-26,37-41) == a two-source conv
+            p = self.PREFIX["cat_seg" if seg else "cat_det"]
+            self.pc = ops.pack_conv(sd[p + "conv1_1.weight"], sd[p + "conv1_1.bias"], _bn(sd, p + "bn1_1"), cins=[c, c],
+                                    planes=planes, device=dev)
+            mean = plan.act("fuse_mean", h, w, c)
+            plan.add(lambda: ops.warp_reduce(x, trans, na, batch, agents, "mean", only_v2i=only_v2i, out=mean))
+            out = plan.conv(self.pc, [x, mean], "fused")
+            plan.add(lambda: ops.restore_absent(x, out, na, batch, agents))
+        else:
+            p = self.PREFIX[kind]
+            self.pc = ops.pack_pair_conv1(sd[p + "conv1_1.weight"], sd[p + "conv1_1.bias"], _bn(sd, p + "bn1_1"),
+                                          planes=planes, device=dev)
+            self.mlp = mlp = _pair_mlp(sd, p, dev)
+            q = plan.act("fuse_q", h, w, 256)
+            plan.add(ConvLaunch(self.pc, [x], epilogue=EPI_ACT, relu=False, out0=q))
+            self.scores = scores = torch.zeros((batch, agents, agents, h * w), dtype=torch.float32, device=dev)
+            plan.add(lambda: ops.pair_score(q, trans, na, batch, agents, mlp, only_v2i=only_v2i, out=scores))
+            out = plan.act("fused", h, w, c)
+            if kind == "disco":
+                plan.add(lambda: ops.warp_weighted(x, trans, na, scores, batch, agents, per_pixel=True,
+                                                   only_v2i=only_v2i, out=out))
+            else:
+                # conv1_5: 32x32 "valid" conv over the H-flipped score map -> one scalar per pair
+                # (AgentWiseWeightedFusion.py:65,74); scores are un-flipped here, so mirror the filter rows instead
+                w5 = sd[p + "conv1_5.weight"].detach().to(device=dev, dtype=torch.float32).reshape(h, w)
+                self.w5f = w5f = torch.flip(w5, (0,)).contiguous()
+                self.b5 = b5 = sd[p + "conv1_5.bias"].detach().to(device=dev, dtype=torch.float32).contiguous()
+                self.coef = coef = torch.zeros((batch, agents, agents), dtype=torch.float32, device=dev)
+                plan.add(lambda: ops.agent_softmax(scores, w5f, b5, na, out=coef))
+                plan.add(lambda: ops.warp_weighted(x, trans, na, coef, batch, agents, per_pixel=False,
+                                                   only_v2i=only_v2i, out=out))
+        self.out = out
+
+
+class FusionDetPlan(DetPlan):
+    """det intermediate-fusion baselines: encoder -> FuseStage(kind) at layer 3 -> decoder -> heads
+    (FusionBase.py:23-75; DiscoNet.py:36-129)."""
+
+    def __init__(self, sd, kind: str, batch: int, agents: int = 5, planes: int = 1, device="cuda", only_v2i=False):
+        super().__init__(batch * agents, planes, device)
+        ops.require_gpu()
+        self.batch, self.agents, self.kind = batch, agents, kind
+        dev = self.device
+        self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
+        self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
+        self.head_w = HeadWeights(sd, planes, dev)
+        self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
+        self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
+        x_in = self.build_input()
+        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
+        self.fuse = FuseStage(self, kind, sd, x3, self.trans, self.num_agent, batch, agents, only_v2i=only_v2i)
+        self.fused = self.fuse.out
+        x8 = self.build_decoder(self.dec_w, x0, x1, x2, self.fused, x4u)
+        self.build_heads(self.head_w, x8)
+
+    def forward(self, bevs, trans_matrices, num_agent_tensor):
+        self.bev_in.copy_(bevs.reshape(self.bev_in.shape), non_blocking=True)
+        self.trans.copy_(trans_matrices.reshape(self.trans.shape), non_blocking=True)
+        self.num_agent.copy_(num_agent_tensor.reshape(self.num_agent.shape), non_blocking=True)
+        self.run()
+        return self.result()
+
+    def kd_layers(self):
+        """(x_8, x_7, x_6, x_5, fused) as fp32 NCHW tensors -- what kd_flag == 1 forwards return (FusionBase.py:72-73).
+        x_5..x_7 only exist nearest-upsampled in the workspace; every 2x2 block holds one value."""
+        f = ops.act_to_float
+        return (f(self.ws["x8"]), f(self.ws["x7u"])[:, :, ::2, ::2].contiguous(), f(self.ws["x6u"])[:, :, ::2, ::2].contiguous(),
+                f(self.ws["x5u"])[:, :, ::2, ::2].contiguous(), f(self.fused))

@@ -195,3 +195,26 @@ class SegWhen2comPlan(_FusedSegPlan):
         self.add(lambda: ops.warp_gated(x4, trans, na, coef, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i,
                                         out=fused))
         self.build_decoder(self.w, fused, x1, x2, x3)
+
+
+class SegFusionPlan(_FusedSegPlan):
+    """seg intermediate-fusion baselines (seg/FusionBase.py:25-84): UNet encoder -> FuseStage(kind) on the 512-channel
+    layer-4 map -> down4 / up1..4 / outc."""
+
+    def __init__(self, sd, kind, batch, agents=5, planes=1, device="cuda", only_v2i=False):
+        from .nets import FuseStage
+        super().__init__(batch * agents, planes, device)
+        ops.require_gpu()
+        self._common(batch, agents)
+        self.kind = kind
+        self.w = SegUNetWeights(sd, planes, self.device)
+        x_in = self.build_input()
+        x1, x2, x3, x4 = self.build_encoder(self.w, x_in)
+        self.fuse = FuseStage(self, kind, sd, x4, self.trans, self.num_agent, batch, agents, only_v2i=only_v2i, seg=True)
+        self.fused = self.fuse.out
+        self.build_decoder(self.w, self.fused, x1, x2, x3)
+
+    def kd_layers(self):
+        """(x9, x8, x7, x6, x5, feat_mat) as fp32 NCHW (seg/FusionBase.py:81-82)."""
+        f = ops.act_to_float
+        return tuple(f(self.ws[k]) for k in ("x9", "x8", "x7", "x6", "x5")) + (f(self.fused),)

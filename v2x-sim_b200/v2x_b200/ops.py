@@ -60,6 +60,30 @@ def pack_input(x: torch.Tensor, c_pad: int, planes: int, out: Optional[torch.Ten
     return out
 
 
+def pack_input_u8(x: torch.Tensor, c_pad: int, planes: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bool / uint8 NHWC occupancy ``[..., H, W, C]`` (non-zero = 1.0) -> act ``[planes, N, H, W, c_pad]``."""
+    lib = require_gpu()
+    assert x.dtype in (torch.uint8, torch.bool) and x.is_contiguous() and x.is_cuda
+    h, w, c = x.shape[-3:]
+    n = x.numel() // (h * w * c)
+    if out is None:
+        out = empty_act(planes, n, h, w, c_pad, x.device)
+    check(lib.v2x_pack_input_u8(_ptr(x), _ptr(out), n * h * w, c, c_pad, planes, _stream()), "v2x_pack_input_u8")
+    return out
+
+
+def voxelize(idx: torch.Tensor, count: torch.Tensor, out: torch.Tensor, c: int, bad: torch.Tensor, rot90=True):
+    """Sparse voxel rows (map, i0, i1, i2) int32 [capacity, 4] (``count`` valid, a device int32 scalar) -> the dense
+    occupancy act ``out`` [planes, N, H, W, c_pad], incl. the dataset's np.rot90(., 3) (V2XSimDet.py:294-299)."""
+    lib = require_gpu()
+    assert idx.dtype == torch.int32 and idx.is_cuda and idx.is_contiguous() and idx.shape[1] == 4
+    assert count.dtype == torch.int32 and count.is_cuda and bad.dtype == torch.int32 and bad.is_cuda
+    planes, n, h, w, c_pad = out.shape
+    check(lib.v2x_voxelize_fwd(_ptr(idx), _ptr(count), idx.shape[0], _ptr(out), n, h, w, c, c_pad, planes, int(rot90),
+                               _ptr(bad), _stream()), "v2x_voxelize_fwd")
+    return out
+
+
 @dataclass
 class PackedConv:
     """Packed operand of one fused conv launch (weights bf16 [P, cout_pad, k_total], bias fp32)."""
@@ -371,4 +395,94 @@ def upsample_bilinear2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> t
     if out is None:
         out = empty_act(planes, n, 2 * h, 2 * w, c, x.device)
     check(lib.v2x_upsample_bilinear2_fwd(_ptr(x), _ptr(out), n, h, w, c, planes, _stream()), "v2x_upsample_bilinear2_fwd")
+    return out
+
+
+# ---- intermediate-fusion baselines (FusionBase family) ---------------------------------------
+REDUCE_MODES = {"mean": 0, "sum": 1, "max": 2}
+
+
+def warp_reduce(x, trans, num_agent, batch, agents, mode, *, only_v2i=False, out=None):
+    """out[b,i] = mean/sum/max over {x[b,i]} U {warp_{j->i} x[b,j]} (Mean/Sum/MaxFusion.fusion)."""
+    lib = require_gpu()
+    planes, n, h, w, c = x.shape
+    assert n == batch * agents and x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.v2x_warp_reduce_fwd(_ptr(x), _ptr(out), _ptr(trans), _ptr(num_agent), batch, agents, h, w, c, planes,
+                                  REDUCE_MODES[mode], int(only_v2i), _stream()), "v2x_warp_reduce_fwd")
+    return out
+
+
+def fold_bn_1x1(w, b, bn, device):
+    """BN(eval)-folded fp32 matrix / bias of a 1x1 conv: (W * s, (b - mean) * s + beta); bn may be None."""
+    w = _f32(w, device).reshape(w.shape[0], -1)
+    b = _f32(b, device)
+    if bn is None:
+        return w.contiguous(), b.contiguous()
+    gamma, beta, mean, var = [_f32(t, device) for t in bn]
+    s = gamma / torch.sqrt(var + BN_EPS)
+    return (w * s[:, None]).contiguous(), ((b - mean) * s + beta).contiguous()
+
+
+def pack_pair_conv1(w, b, bn, *, planes=1, device=None) -> PackedConv:
+    """First layer of the pair-weight nets (conv1_1 over cat[tg, nb], 2C -> 128, + BN) as ONE C -> 256 1x1 operand:
+    rows [0,128) = the tg half (carries the folded bias), rows [128,256) = the neighbour half (zero bias).  conv1_1 is
+    linear and pointwise, hence commutes with the bilinear warp (see v2x_pair_score_fwd)."""
+    device = device or w.device
+    c = w.shape[1] // 2
+    gamma, beta, mean, var = bn
+    w2 = torch.cat([w[:, :c], w[:, c:]], 0)
+    b2 = torch.cat([b, mean])                       # (b - mean) == 0 for the neighbour half
+    bn2 = (torch.cat([gamma, gamma]), torch.cat([beta, torch.zeros_like(beta)]), torch.cat([mean, mean]),
+           torch.cat([var, var]))
+    return pack_conv(w2, b2, bn2, cins=[c], planes=planes, device=device)
+
+
+def pair_score(q, trans, num_agent, batch, agents, mlp, *, only_v2i=False, out=None):
+    """scores[b,i,k,p] of the DiscoNet / AgentWise weight nets; ``mlp`` = (w2,b2,w3,b3,w4,b4) folded fp32."""
+    lib = require_gpu()
+    planes, n, h, w, c = q.shape
+    assert n == batch * agents and c == 256 and q.is_contiguous()
+    w2, b2, w3, b3, w4, b4 = mlp
+    assert tuple(w2.shape) == (32, 128) and tuple(w3.shape) == (8, 32) and w4.numel() == 8 and b4.numel() == 1
+    if out is None:
+        out = torch.zeros((batch, agents, agents, h * w), dtype=torch.float32, device=q.device)
+    check(lib.v2x_pair_score_fwd(_ptr(q), _ptr(out), _ptr(trans), _ptr(num_agent), _ptr(w2), _ptr(b2), _ptr(w3),
+                                 _ptr(b3), _ptr(w4), _ptr(b4), batch, agents, h, w, planes, int(only_v2i), _stream()),
+          "v2x_pair_score_fwd")
+    return out
+
+
+def agent_softmax(scores, w5f, b5, num_agent, *, out=None):
+    lib = require_gpu()
+    batch, agents, _, hw = scores.shape
+    assert w5f.numel() == hw and w5f.is_contiguous()
+    if out is None:
+        out = torch.empty((batch, agents, agents), dtype=torch.float32, device=scores.device)
+    check(lib.v2x_agent_softmax_fwd(_ptr(scores), _ptr(w5f), _ptr(b5), _ptr(num_agent), _ptr(out), batch, agents, hw,
+                                    _stream()), "v2x_agent_softmax_fwd")
+    return out
+
+
+def warp_weighted(x, trans, num_agent, coef, batch, agents, *, per_pixel, only_v2i=False, out=None):
+    """out[b,i] = sum_k c[b,i,k] * warp_{k->i}(x[b,k]); per_pixel: c = softmax_k of scores [B,A,A,H*W]."""
+    lib = require_gpu()
+    planes, n, h, w, c = x.shape
+    assert n == batch * agents and coef.dtype == torch.float32 and coef.is_contiguous()
+    assert coef.numel() == batch * agents * agents * (h * w if per_pixel else 1)
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.v2x_warp_weighted_fwd(_ptr(x), _ptr(out), _ptr(trans), _ptr(num_agent), _ptr(coef), int(per_pixel), batch,
+                                    agents, h, w, c, planes, int(only_v2i), _stream()), "v2x_warp_weighted_fwd")
+    return out
+
+
+def restore_absent(x, out, num_agent, batch, agents):
+    """out[unit] = x[unit] for agent slots absent from their scene."""
+    lib = require_gpu()
+    planes, n, h, w, c = x.shape
+    assert out.shape == x.shape and n == batch * agents
+    check(lib.v2x_restore_absent_fwd(_ptr(x), _ptr(out), _ptr(num_agent), batch, agents, h * w * c, planes, _stream()),
+          "v2x_restore_absent_fwd")
     return out
