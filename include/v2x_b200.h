@@ -266,6 +266,26 @@ int v2x_voxelize_fwd(const int32_t* idx, const int32_t* count, int32_t capacity,
 int v2x_pack_input_u8(const uint8_t* x, void* out, int64_t n_pixels, int32_t c, int32_t c_pad, int32_t planes,
                       void* stream);
 
+/* ---- detection post-processing on device (CP/utils/detection_util.py:256-373, CP/utils/postprocess.py:72-113) -- */
+
+/*
+ * Per agent map: score = softmax(cls)[..., 1]; candidates = score > score_thr (0.7 in the reference, postprocess.py:84),
+ * visited in descending score order (ties: higher anchor index first); boxes decoded from (loc, anchors) as
+ * bev_box_decode_torch + center_to_corner_box2d do (fp32); a candidate is dropped when its polygon IoU (fp64, rounded
+ * to fp32 like compute_iou's array) with an already kept box exceeds iou_thr (0.01 at detection_util.py:357-359).
+ *   cls [n_maps][n_anchors][2], loc [n_maps][n_anchors][6] fp32 (the model's outputs, device);
+ *   anchors fp32 [n_maps][n_anchors][6] (x, y, w, h, sin, cos), or one [n_anchors][6] table when anchors_shared != 0;
+ *   cap: candidates kept per map (1024 / 2048 / 4096), highest scores first -- cand_count[m] > cap means overflow and
+ *        must be treated as an error by the caller (the reference has no cap);
+ *   workspaces: keys_ws u64 [n_maps][cap], boxes_ws f32 [n_maps][cap][8];
+ *   outputs (pick order): sel_idx int32 [n_maps][cap] (anchor index = the reference's selected_idx), sel_score,
+ *        sel_corners [..][8] (x0,y0,..,x3,y3), sel_count [n_maps], cand_count [n_maps].
+ */
+int v2x_det_nms_fwd(const float* cls, const float* loc, const float* anchors, int32_t n_maps, int32_t n_anchors,
+                    int32_t anchors_shared, float score_thr, float iou_thr, int32_t cap, uint64_t* keys_ws,
+                    float* boxes_ws, int32_t* cand_count, int32_t* sel_idx, float* sel_score, float* sel_corners,
+                    int32_t* sel_count, void* stream);
+
 /* ---- segmentation UNet pieces (CP/models/seg/SegModelBase.py) ------------------------------ */
 /* fp32 NCHW [n][c][h][w] (what SegModule.py:49 hands the model) -> act bf16 planes NHWC, channels zero-padded to c_pad */
 int v2x_pack_input_nchw(const float* x, void* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pad,

@@ -82,6 +82,7 @@ SYMBOLS = [
     ("v2x_warp_weighted_fwd", C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_voxelize_fwd", C.c_int, [_P, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     ("v2x_pack_input_u8", C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
+    ("v2x_det_nms_fwd", C.c_int, [_P, _P, _P, _I32, _I32, _I32, _F32, _F32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("v2x_restore_absent_fwd", C.c_int, [_P, _P, _P, _I32, _I32, _I64, _I32, _P]),
 ]
 
