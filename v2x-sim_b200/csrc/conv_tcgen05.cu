@@ -332,6 +332,65 @@ __device__ __forceinline__ void f32_chunk_out(uint32_t stage, int lane, int quad
   __syncwarp();
 }
 
+// Lean variant of f32_chunk_out for the fused heads (V2X_EPI_TAIL_F32_SPLIT): everything that does not change from tile
+// to tile is hoisted into per-lane registers once per kernel -- the destination tensor / channel offset / pixel stride of
+// this lane's 16-byte unit (so the cls / loc split costs no divergent branch), the unit's four bias values (added on
+// the way out, so parking needs no bias loads) and the pixel walk of the write-back -- leaving per store one shared
+// load, four adds and one 64-bit add.  (profiles/r01_v9: the generic routine spent 60% of the heads' epilogue time on
+// address arithmetic, constant-bank loads and the split branch.)
+struct TailOut {
+  float* base[2];        // destination of this lane's unit in chunk 0 / 1 (tensor base + channel offset), or nullptr
+  long long stride[2];   // floats per pixel of that destination
+  float4 bias[2];
+};
+
+template <bool HALO>
+__device__ __forceinline__ void tail_chunk_out(uint32_t stage, int lane, int quad, const float* v0, const float* v1, bool two,
+                                               const TailOut& t, int c32, long long tile_pix, int oh0, int ow0, int h_out,
+                                               int w_out, bool full_tile, bool no_store) {
+  const uint32_t srow = stage + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    st_shared_v4(srow + ((((uint32_t)q) ^ sw) << 4), __float_as_uint(v0[4 * q]), __float_as_uint(v0[4 * q + 1]),
+                 __float_as_uint(v0[4 * q + 2]), __float_as_uint(v0[4 * q + 3]));
+  if (two) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      st_shared_v4(srow + ((((uint32_t)(4 + q)) ^ sw) << 4), __float_as_uint(v1[4 * q]), __float_as_uint(v1[4 * q + 1]),
+                   __float_as_uint(v1[4 * q + 2]), __float_as_uint(v1[4 * q + 3]));
+  }
+  __syncwarp();
+  float* const base = t.base[c32];
+  if (base != nullptr && !no_store) {
+    const uint32_t u = (uint32_t)lane & 7u;
+    const int l3 = lane >> 3;
+    const long long st = t.stride[c32];
+    const float4 b = t.bias[c32];
+    // pixel (l3 + 4j) of this warp's 32: tile row / column of the write-back walk
+    constexpr int ROWS_PER_QUAD = HALO ? 4 : 2;
+    float* const p0 = base + (tile_pix + (long long)(quad * ROWS_PER_QUAD) * w_out + l3) * st;
+    const long long row_step = (long long)w_out * st;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int dh = HALO ? (j >> 1) : (j >> 2);        // (l3 + 4j) / TILE_W
+      const int dw = HALO ? 4 * (j & 1) : 4 * (j & 3);  // (l3 + 4j) % TILE_W - l3
+      if (!full_tile) {
+        const int ph = quad * ROWS_PER_QUAD + dh, pw = dw + l3;
+        if (oh0 + ph >= h_out || ow0 + pw >= w_out) continue;
+      }
+      const uint32_t pix = (uint32_t)(l3 + 4 * j);
+      uint4 v = ld_shared_v4(stage + pix * 128u + ((u ^ (pix & 7u)) << 4));
+      v.x = __float_as_uint(__uint_as_float(v.x) + b.x);
+      v.y = __float_as_uint(__uint_as_float(v.y) + b.y);
+      v.z = __float_as_uint(__uint_as_float(v.z) + b.z);
+      v.w = __float_as_uint(__uint_as_float(v.w) + b.w);
+      *reinterpret_cast<uint4*>(p0 + dh * row_step + dw * st) = v;
+    }
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Tensor-core kernel: persistent, warp-specialised (192 threads)
 //   warp 0 : TMA producer (A boxes every stage; weights either streamed with A or loaded once per CTA
@@ -763,6 +822,20 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
       wb_w[j] = HALO ? (prow & 7) : (prow & 15);
       o.eo[j] = (wb_h[j] * up * Ws + wb_w[j] * up) * p.out_c_total;
     }
+    TailOut tout;
+    if (has_tail) {
+      const int c1 = p.tail_cout - p.split;
+#pragma unroll
+      for (int c32 = 0; c32 < 2; ++c32) {
+        const int ch = c32 * 32 + 4 * (lane & 7);
+        const bool act = ch < p.tail_cout;
+        tout.base[c32] = !act ? nullptr
+                              : ch < p.split ? reinterpret_cast<float*>(p.out0) + ch
+                                             : reinterpret_cast<float*>(p.out1) + (ch - p.split);
+        tout.stride[c32] = ch < p.split ? p.split : c1;
+        tout.bias[c32] = act ? *reinterpret_cast<const float4*>(s_bhn + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     int it = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, grid_stride);
@@ -876,17 +949,18 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
           const uint32_t tstage = a2 + (uint32_t)(quad * 32) * 128u;
           const uint32_t taddr2 = tmem_t + ((uint32_t)(quad * 32) << 16);
           const long long tile_pix = ((long long)ti.n_img * p.h_out + oh0) * p.w_out + ow0;
-#pragma unroll 1
-          for (int c32 = 0; c32 * 32 < p.tail_cout; ++c32) {
+          const bool full_tile = oh0 + TILE_H <= p.h_out && ow0 + TILE_W <= p.w_out;
+#pragma unroll
+          for (int c32 = 0; c32 < 2; ++c32) {
+            if (c32 * 32 >= p.tail_cout) break;
             const bool two = c32 * 32 + 16 < p.tail_cout;
             float v0[16], v1[16];
             tmem_ld16_async(taddr2 + c32 * 32, v0);
             if (two) tmem_ld16_async(taddr2 + c32 * 32 + 16, v1);
             tmem_ld_wait16(v0);
             if (two) tmem_ld_wait16(v1);
-            f32_chunk_out<HALO>(tstage, lane, quad, v0, v1, two, s_bhn + c32 * 32, c32 * 32, p.tail_cout, p.split,
-                                reinterpret_cast<float*>(p.out0), reinterpret_cast<float*>(p.out1), tile_pix, oh0, ow0,
-                                p.h_out, p.w_out, dbg_no_store);
+            tail_chunk_out<HALO>(tstage, lane, quad, v0, v1, two, tout, c32, tile_pix, oh0, ow0, p.h_out, p.w_out,
+                                 full_tile, dbg_no_store);
           }
           tc_fence_before();   // orders this tile's tcgen05.ld of the tail accumulator before the next tile's barrier + MMA
           ++it;
