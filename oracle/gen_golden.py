@@ -255,6 +255,50 @@ def gen_fusion_all():
     gen_teacher("teacher_n1_seed3", 1, 3)
 
 
+def gen_compress():
+    """compress_level > 0 (Backbone.py:74-87,138-141; SegModelBase.py:29-43): V2VNet det at level 2 (64 channels),
+    DiscoNet det at level 6 (4 channels: exercises the zero-padded narrow operand), seg UNet at level 3 (64 of 512)."""
+    # V2VNet det
+    m = ref_loader.ref_v2vnet_det(compress_level=2)
+    sd = synth.v2vnet_det_state(15, compress_level=2)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(1, 5, 15, present=[4])
+    with torch.no_grad():
+        r = m(bevs, trans, nat, batch_size=1)
+    out = {"meta": np.asarray([1, 5, 15, 2], dtype=np.int64), "present": np.asarray([4], dtype=np.int64)}
+    summarize("loc", r["loc"], out)
+    summarize("cls", r["cls"], out)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "compress_v2vnet_det_l2_seed15.npz"), **out)
+    print("compress_v2vnet_det_l2_seed15", out["loc.sum"])
+    # DiscoNet det, 4 compressed channels
+    m = ref_loader.ref_fusion_det("disco", compress_level=6)
+    sd = synth.fusion_det_state("disco", 16, compress_level=6)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(1, 5, 16)
+    with torch.no_grad():
+        r = m(bevs, trans, nat, batch_size=1)[0]
+    out = {"meta": np.asarray([1, 5, 16, 6], dtype=np.int64)}
+    summarize("loc", r["loc"], out)
+    summarize("cls", r["cls"], out)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "compress_disco_det_l6_seed16.npz"), **out)
+    print("compress_disco_det_l6_seed16", out["loc.sum"])
+    # seg UNet with kd outputs
+    m = ref_loader.ref_seg_unet(compress_level=3, kd_flag=True)
+    sd = synth.seg_unet_state(17, compress_level=3)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x, _, _ = synth.make_seg_scene(1, 2, 17)
+    with torch.no_grad():
+        r = m(x)
+    out = {"meta": np.asarray([1, 2, 17, 3], dtype=np.int64)}
+    for name, t in zip(("logits", "x9", "x8", "x7", "x6", "x5", "x4"), r):
+        summarize(name, t, out)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "compress_seg_unet_l3_kd_seed17.npz"), **out)
+    print("compress_seg_unet_l3_kd_seed17", out["logits.sum"])
+
+
 def main():
     if not ref_loader.available():
         print("reference tree not available; golden fixtures can only be generated in the build container")
@@ -264,7 +308,11 @@ def main():
     if "--fusion-only" in sys.argv:
         gen_fusion_all()
         return 0
+    if "--compress-only" in sys.argv:
+        gen_compress()
+        return 0
     gen_fusion_all()
+    gen_compress()
     gen_warp("warp_small_seed3", 3)
     gen_convgru("convgru_small_seed4", 4)
     gen_fafnet("fafnet_n2_seed0", 2, 0)

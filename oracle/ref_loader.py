@@ -71,10 +71,10 @@ def ref_v2vnet_det(gnn_iter_times=3, layer=3, layer_channel=256, num_agent=5, co
                   compress_level=compress_level)
 
 
-def ref_fafnet(num_agent=5, kd_flag=0):
+def ref_fafnet(num_agent=5, kd_flag=0, compress_level=0):
     install()
     FaFNet = importlib.import_module("coperception.models.det.FaFNet").FaFNet
-    return FaFNet(ref_config(), layer=3, kd_flag=kd_flag, num_agent=num_agent)
+    return FaFNet(ref_config(), layer=3, kd_flag=kd_flag, num_agent=num_agent, compress_level=compress_level)
 
 
 def ref_when2com_det(warp_flag=1, num_agent=5):
@@ -88,10 +88,10 @@ def _seg_config():
     return cfg
 
 
-def ref_seg_unet(n_classes=8):
+def ref_seg_unet(n_classes=8, compress_level=0, kd_flag=False):
     install()
     UNet = importlib.import_module("coperception.models.seg.UNet").UNet
-    return UNet(13, n_classes)
+    return UNet(13, n_classes, kd_flag=kd_flag, compress_level=compress_level)
 
 
 def ref_seg_v2vnet(n_classes=8, num_agent=5):
@@ -110,11 +110,12 @@ _FUSION_CLASSES = {"mean": "MeanFusion", "max": "MaxFusion", "sum": "SumFusion",
                    "agent": "AgentWiseWeightedFusion", "disco": "DiscoNet"}
 
 
-def ref_fusion_det(kind, num_agent=5, kd_flag=0, only_v2i=False):
+def ref_fusion_det(kind, num_agent=5, kd_flag=0, only_v2i=False, compress_level=0):
     install()
     name = _FUSION_CLASSES[kind]
     cls = getattr(importlib.import_module("coperception.models.det." + name), name)
-    return cls(ref_config(), layer=3, kd_flag=kd_flag, num_agent=num_agent, only_v2i=only_v2i)
+    return cls(ref_config(), layer=3, kd_flag=kd_flag, num_agent=num_agent, only_v2i=only_v2i,
+               compress_level=compress_level)
 
 
 def ref_fusion_seg(kind, n_classes=8, num_agent=5, only_v2i=False):

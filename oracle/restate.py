@@ -282,6 +282,10 @@ def seg_encode(x, sd, p=""):
     x2 = seg_down(x1, sd, p + "down1.")
     x3 = seg_down(x2, sd, p + "down2.")
     x4 = seg_down(x3, sd, p + "down3.")
+    if p + "com_compresser.weight" in sd:   # compress_level > 0 (UNet.py:30-32, seg/FusionBase.py:31-33, ...)
+        x4 = F.relu(_bn(F.conv2d(x4, sd[p + "com_compresser.weight"], sd[p + "com_compresser.bias"]), sd, p + "bn_compress"))
+        x4 = F.relu(_bn(F.conv2d(x4, sd[p + "com_decompresser.weight"], sd[p + "com_decompresser.bias"]), sd,
+                        p + "bn_decompress"))
     return x1, x2, x3, x4
 
 
@@ -462,7 +466,7 @@ def fusion_stage(kind, feat_maps, trans_matrices, num_agent_tensor, sd, batch_si
 def fusion_det_forward(kind, bevs, trans_matrices, num_agent_tensor, sd, batch_size=1, agent_num=5, only_v2i=False,
                        stages=False):
     """det FusionBase.forward / DiscoNet.forward (kd_flag = 0 result dict)."""
-    enc = encode(bevs, sd, "u_encoder.")
+    enc = encode(bevs, sd, "u_encoder.", compress_level=int("u_encoder.com_compresser.weight" in sd))
     fused = fusion_stage(kind, enc[3], trans_matrices, num_agent_tensor, sd, batch_size, agent_num, only_v2i)
     dec_in = list(enc)
     dec_in[3] = fused

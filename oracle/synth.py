@@ -242,13 +242,19 @@ def _double_conv(sd, g, p, cin, cmid, cout):
     _bn(sd, g, p + "4", cout)
 
 
-def seg_unet_state(seed=0, n_classes=8, g=None, sd=None):
-    """state_dict of seg UNet / the SegModelBase part of every seg model (SegModelBase.py:17-27)."""
+def seg_unet_state(seed=0, n_classes=8, g=None, sd=None, compress_level=0):
+    """state_dict of seg UNet / the SegModelBase part of every seg model (SegModelBase.py:17-43)."""
     g = g or _Gen(seed)
     sd = OrderedDict() if sd is None else sd
     for p, cin, cmid, cout in SEG_DOUBLE_CONVS:
         _double_conv(sd, g, p, cin, cmid, cout)
     _conv(sd, g, "outc.conv", n_classes, 64, k=(1, 1), gain=3.0)
+    if compress_level > 0:
+        cc = 512 // (2 ** compress_level)
+        _conv(sd, g, "com_compresser", cc, 512, k=(1, 1))
+        _bn(sd, g, "bn_compress", cc)
+        _conv(sd, g, "com_decompresser", 512, cc, k=(1, 1))
+        _bn(sd, g, "bn_decompress", 512)
     return sd
 
 
@@ -325,13 +331,13 @@ def _fusion_extra_state(sd, g, kind, channel, seg):
         _pair_weight_net_state(sd, g, "pixel_weighted_fusion.", channel, False)
 
 
-def fusion_det_state(kind, seed=0):
+def fusion_det_state(kind, seed=0, compress_level=0):
     """state_dict of the det FusionBase family (IntermediateModelBase.py:24-25 + the subclass' fusion net)."""
     assert kind in FUSION_KINDS
     g = _Gen(seed)
     sd = OrderedDict()
     heads_state(sd, g)
-    backbone_state(sd, g, "u_encoder.")
+    backbone_state(sd, g, "u_encoder.", compress_level=compress_level)
     backbone_state(sd, g, "decoder.")
     _fusion_extra_state(sd, g, kind, 256, False)
     return sd

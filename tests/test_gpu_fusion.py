@@ -214,3 +214,59 @@ def test_teacher_net(golden_dir):
     assert len(out) == 6
     for name, t, r in zip(("x8", "x7", "x6", "x5", "x3", "x4"), out, ref):
         assert t.shape == r.shape and rel_err(t, r) < 1e-3, name
+
+
+def test_compress_level_models(golden_dir):
+    """compress_level > 0 (optional compress / decompress of the communicated layer): V2VNet det level 2,
+    DiscoNet det level 6 (4 channels, zero-padded operand), seg UNet level 3 with its kd_flag tuple -- vs oracle + fixtures."""
+    import coperception.models.det as det
+    import coperception.models.seg as seg
+    from oracle import restate, synth
+    from oracle.gen_golden import STRIDE
+    from v2x_b200 import default_det_config
+
+    def golden_err(t, g, name):
+        sub = t.detach().float().cpu().contiguous().view(-1)[::STRIDE].numpy()
+        return float(np.abs(sub - g[name + ".sub"]).max() / np.abs(g[name + ".sub"]).max())
+
+    # V2VNet det
+    g = np.load(os.path.join(golden_dir, "compress_v2vnet_det_l2_seed15.npz"))
+    sd = synth.v2vnet_det_state(15, compress_level=2)
+    bevs, trans, nat = synth.make_scene(1, 5, 15, present=[4])
+    with torch.no_grad():
+        ref = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=5, gnn_iter=3, compress_level=2)
+    m = det.V2VNet(default_det_config(), 3, 3, 256, num_agent=5, compress_level=2)
+    m.load_state_dict(sd, strict=True)
+    m.precision = "bf16x3"
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    for k in ("loc", "cls"):
+        assert rel_err(out[k], ref[k]) < 1e-3 and golden_err(out[k], g, k) < 1e-3, k
+    # DiscoNet det, 4 compressed channels
+    g = np.load(os.path.join(golden_dir, "compress_disco_det_l6_seed16.npz"))
+    sd = synth.fusion_det_state("disco", 16, compress_level=6)
+    bevs, trans, nat = synth.make_scene(1, 5, 16)
+    with torch.no_grad():
+        ref = restate.fusion_det_forward("disco", bevs, trans, nat, sd, batch_size=1, agent_num=5)
+    m = det.DiscoNet(default_det_config(), layer=3, kd_flag=0, num_agent=5, compress_level=6)
+    m.load_state_dict(sd, strict=True)
+    m.precision = "bf16x3"
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out, _ = m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    for k in ("loc", "cls"):
+        assert rel_err(out[k], ref[k]) < 1e-3 and golden_err(out[k], g, k) < 1e-3, k
+    # seg UNet level 3, kd tuple
+    g = np.load(os.path.join(golden_dir, "compress_seg_unet_l3_kd_seed17.npz"))
+    sd = synth.seg_unet_state(17, compress_level=3)
+    x, _, _ = synth.make_seg_scene(1, 2, 17)
+    m = seg.UNet(13, 8, kd_flag=True, compress_level=3)
+    m.load_state_dict(sd, strict=True)
+    m.precision = "bf16x3"
+    m = m.cuda().eval()
+    with torch.no_grad():
+        tup = m(x.cuda())
+    assert len(tup) == 7
+    for name, t in zip(("logits", "x9", "x8", "x7", "x6", "x5", "x4"), tup):
+        assert list(t.shape) == list(g[name + ".shape"]) and golden_err(t, g, name) < 1e-3, name

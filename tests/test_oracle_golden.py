@@ -173,3 +173,27 @@ def test_densify_voxels_is_scatter_then_rot90():
     assert d.dtype == np.float32 and d.shape == (256, 256, 13)
     assert all(d[i1, 255 - i0, z] == 1.0 for i0, i1, z in lists[0])
     assert int(d.sum()) == len(np.unique(lists[0], axis=0))
+
+
+def test_compress_level(golden_dir):
+    """compress_level > 0: restatement vs the live reference (V2VNet det level 2, DiscoNet det level 6, seg UNet level 3
+    with its kd_flag tuple)."""
+    g = np.load(os.path.join(golden_dir, "compress_v2vnet_det_l2_seed15.npz"))
+    sd = synth.v2vnet_det_state(15, compress_level=2)
+    bevs, trans, nat = synth.make_scene(1, 5, 15, present=[4])
+    with torch.no_grad():
+        r = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=5, gnn_iter=3, compress_level=2)
+    _check("loc", r["loc"], g)
+    _check("cls", r["cls"], g)
+    g = np.load(os.path.join(golden_dir, "compress_disco_det_l6_seed16.npz"))
+    sd = synth.fusion_det_state("disco", 16, compress_level=6)
+    bevs, trans, nat = synth.make_scene(1, 5, 16)
+    with torch.no_grad():
+        r = restate.fusion_det_forward("disco", bevs, trans, nat, sd, batch_size=1, agent_num=5)
+    _check("loc", r["loc"], g)
+    _check("cls", r["cls"], g)
+    g = np.load(os.path.join(golden_dir, "compress_seg_unet_l3_kd_seed17.npz"))
+    sd = synth.seg_unet_state(17, compress_level=3)
+    x, _, _ = synth.make_seg_scene(1, 2, 17)
+    with torch.no_grad():
+        _check("logits", restate.seg_unet_forward(x, sd), g)

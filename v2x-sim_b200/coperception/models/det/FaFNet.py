@@ -11,8 +11,6 @@ class FaFNet(B200DetModel):
 
     def __init__(self, config, layer=3, in_channels=13, kd_flag=True, num_agent=5, compress_level=0):
         super().__init__(config, layer, in_channels, kd_flag, num_agent=num_agent)
-        if compress_level != 0:
-            raise NotImplementedError("compress_level > 0 is not built on the sm_100a path yet")
         self.stpn = BackboneParams(config.map_dims[2], compress_level)
 
     def forward(self, bevs, maps=None, vis=None, batch_size=None):

@@ -19,8 +19,6 @@ class V2VNet(B200DetModel):
         if layer != 3 or layer_channel != 256:
             raise NotImplementedError("v2x_b200 V2VNet fuses at layer 3 (256 channels) as the reference scripts do "
                                       "(train_codet.py:106-114)")
-        if compress_level != 0:
-            raise NotImplementedError("compress_level > 0 is not built on the sm_100a path yet")
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)
         self.layer_channel = layer_channel

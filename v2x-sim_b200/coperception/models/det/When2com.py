@@ -56,8 +56,8 @@ class When2com(B200DetModel):
         super().__init__(config, layer, in_channels, num_agent=num_agent, only_v2i=only_v2i)
         if layer != 3:
             raise NotImplementedError("v2x_b200 When2com communicates at layer 3 (the reference scripts' default)")
-        if compress_level != 0 or sparse or not has_query:
-            raise NotImplementedError("compress_level > 0 / sparse / has_query=False are not built on the sm_100a path")
+        if sparse or not has_query:
+            raise NotImplementedError("sparse / has_query=False are not built on the sm_100a path")
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)
         self.sparse, self.key_size, self.query_size = sparse, key_size, query_size

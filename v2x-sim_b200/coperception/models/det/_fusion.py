@@ -33,8 +33,6 @@ class FusionBase(B200DetModel):
         super().__init__(config, layer, in_channels, kd_flag, num_agent=num_agent, only_v2i=only_v2i)
         if layer != 3:
             raise NotImplementedError("v2x_b200 fusion models fuse at layer 3 as the reference scripts do")
-        if compress_level != 0:
-            raise NotImplementedError("compress_level > 0 is not built on the sm_100a path yet")
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)
         self.num_agent = 0   # the reference overwrites this per scene (FusionBase.py:16,41)

@@ -41,14 +41,21 @@ class OutConv(nn.Module):
 class SegModelBase(nn.Module):
     def __init__(self, n_channels, n_classes, bilinear=True, num_agent=5, compress_level=0, only_v2i=False):
         super().__init__()
-        if not bilinear or compress_level != 0:
-            raise NotImplementedError("v2x_b200 seg models implement the reference defaults (bilinear up, no compression)")
+        if not bilinear:
+            raise NotImplementedError("v2x_b200 seg models implement the reference default (bilinear upsampling)")
         self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bilinear
         self.num_agent, self.only_v2i, self.compress_level = num_agent, only_v2i, compress_level
         self.inc = DoubleConv(n_channels, 64)
         self.down1, self.down2, self.down3, self.down4 = Down(64, 128), Down(128, 256), Down(256, 512), Down(512, 512)
         self.up1, self.up2, self.up3, self.up4 = Up(1024, 256), Up(512, 128), Up(256, 64), Up(128, 64)
         self.outc = OutConv(64, n_classes)
+        if compress_level > 0:   # SegModelBase.py:29-43
+            assert compress_level <= 9
+            cc = 512 // (2 ** compress_level)
+            self.com_compresser = nn.Conv2d(512, cc, kernel_size=1, stride=1)
+            self.bn_compress = nn.BatchNorm2d(cc)
+            self.com_decompresser = nn.Conv2d(cc, 512, kernel_size=1, stride=1)
+            self.bn_decompress = nn.BatchNorm2d(512)
         self.precision = os.environ.get("V2X_PRECISION", "bf16")
         self.use_cuda_graph = os.environ.get("V2X_CUDA_GRAPH", "1") != "0"
         self._plans = {}

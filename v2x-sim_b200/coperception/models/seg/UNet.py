@@ -7,8 +7,6 @@ from .SegModelBase import SegModelBase
 class UNet(SegModelBase):
     def __init__(self, n_channels, n_classes, bilinear=True, num_agent=5, kd_flag=False, compress_level=0):
         super().__init__(n_channels, n_classes, bilinear, num_agent=num_agent, compress_level=compress_level)
-        if kd_flag:
-            raise NotImplementedError("kd_flag outputs are not exported by the sm_100a seg path yet")
         self.kd_flag = kd_flag
 
     def forward(self, x):
@@ -18,4 +16,9 @@ class UNet(SegModelBase):
         n = int(x.shape[0])
         plan = self._get_plan(("unet", n, x.device.index, self.precision),
                               lambda: nets_seg.SegUNetPlan(self._state(), n, planes=self._planes(), device=x.device))
-        return plan.forward(x.to(torch.float32).contiguous())
+        logits = plan.forward(x.to(torch.float32).contiguous())
+        if self.kd_flag:   # (logits, x9, x8, x7, x6, x5, x4) as UNet.py:41-42
+            from v2x_b200 import ops
+            return (logits, *[ops.act_to_float(plan.ws[k]) for k in ("x9", "x8", "x7", "x6", "x5")],
+                    ops.act_to_float(plan.x4))
+        return logits

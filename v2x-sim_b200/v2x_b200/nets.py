@@ -34,6 +34,25 @@ def _bn(sd, name):
     return (sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"])
 
 
+def pack_compress_pair(sd, prefix, planes, device):
+    """com_compresser (C -> C / 2^level, 1x1 + BN + ReLU) and com_decompresser (back to C) as two 1x1 conv operands.
+    The compressed width can be as small as 1 channel; it is zero-padded to 32 (zero weight rows with identity BN give
+    relu(0) = 0, and the decompresser's matching input columns are zero), which leaves the arithmetic unchanged."""
+    wc, bc = sd[prefix + "com_compresser.weight"], sd[prefix + "com_compresser.bias"]
+    wd, bd = sd[prefix + "com_decompresser.weight"], sd[prefix + "com_decompresser.bias"]
+    cc, c = wc.shape[0], wc.shape[1]
+    ccp = max(32, cc)
+    g, b, m, v = _bn(sd, prefix + "bn_compress")
+    if ccp != cc:
+        z = lambda t, fill: torch.cat([t, torch.full((ccp - cc,), fill, dtype=t.dtype, device=t.device)])  # noqa: E731
+        wc = torch.cat([wc, wc.new_zeros((ccp - cc,) + tuple(wc.shape[1:]))], 0)
+        bc, g, b, m, v = z(bc, 0.0), z(g, 1.0), z(b, 0.0), z(m, 0.0), z(v, 1.0)
+        wd = torch.cat([wd, wd.new_zeros((wd.shape[0], ccp - cc) + tuple(wd.shape[2:]))], 1)
+    comp = ops.pack_conv(wc, bc, (g, b, m, v), cins=[c], planes=planes, device=device)
+    decomp = ops.pack_conv(wd, bd, _bn(sd, prefix + "bn_decompress"), cins=[ccp], planes=planes, device=device)
+    return comp, decomp
+
+
 class BackboneWeights:
     """Packed operands of the used halves of a reference ``Backbone`` (encoder and/or decoder)."""
 
@@ -53,6 +72,9 @@ class BackboneWeights:
         for conv, bn, stride, cins in layers:
             self.c[conv] = ops.pack_conv(sd[prefix + conv + ".weight"], sd[prefix + conv + ".bias"],
                                          _bn(sd, prefix + bn), cins=cins, stride=stride, planes=planes, device=device)
+        if encoder and prefix + "com_compresser.weight" in sd:
+            # optional compress / decompress of the communicated layer x_3 (Backbone.py:74-87,138-141)
+            self.c["com_compresser"], self.c["com_decompresser"] = pack_compress_pair(sd, prefix, planes, device)
         if encoder:
             for name in ("conv3d_1", "conv3d_2"):
                 self.c[name] = ops.pack_conv(sd[prefix + name + ".conv3d.weight"], sd[prefix + name + ".conv3d.bias"],
@@ -165,6 +187,9 @@ class DetPlan:
         # in the detection decoder x_4 is only ever consumed through F.interpolate(x_4, 2) (Backbone.py:176):
         # store it upsampled.  (PolicyNet4 consumes the plain x_4, When2com.py:354.)
         x4 = self.conv(c["conv4_2"], [t], tag + ("x4u" if upsample_x4 else "x4"), upsample2x=upsample_x4)
+        if "com_compresser" in c:   # x_4 was computed from the uncompressed x_3 (Backbone.py:131-141)
+            t = self.conv(c["com_compresser"], [x3], tag + "x3c")
+            x3 = self.conv(c["com_decompresser"], [t], tag + "x3d")
         return x0, x1, x2, x3, x4
 
     def build_decoder(self, w: BackboneWeights, x0, x1, x2, x3, x4u, tag=""):
@@ -422,9 +447,12 @@ class V2VNetDetShardedPlan(DetPlan):
         t = self.conv(c["conv2_2"], [t], "x2b")
         x2 = self.conv(c["conv3d_2"], [t], "x2")
         t = self.conv(c["conv3_1"], [x2], "x3a")
-        x3 = self.conv(c["conv3_2"], [t], "x3")
+        x3 = x3_raw = self.conv(c["conv3_2"], [t], "x3")
+        if "com_compresser" in c:
+            t = self.conv(c["com_compresser"], [x3_raw], "x3c")
+            x3 = self.conv(c["com_decompresser"], [t], "x3d")
         self.stage_a = len(self.launches)            # ---- x_3 ready: the all-gather starts here
-        t = self.conv(c["conv4_1"], [x3], "x4a")
+        t = self.conv(c["conv4_1"], [x3_raw], "x4a")
         x4u = self.conv(c["conv4_2"], [t], "x4u", upsample2x=True)
         self.stage_b = len(self.launches)            # ---- x_4 branch done: wait for the gather
         c3 = x3.shape[-1]

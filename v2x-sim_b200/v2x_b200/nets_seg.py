@@ -34,6 +34,10 @@ class SegUNetWeights:
         self.down = [DoubleConvW(sd, P + "down%d.maxpool_conv.1.double_conv." % i,
                                  [sd[P + "down%d.maxpool_conv.1.double_conv.0.weight" % i].shape[1]], planes, device)
                      for i in ((1, 2, 3) if encoder_only else (1, 2, 3, 4))]
+        self.compress = None
+        if not encoder_only and P + "com_compresser.weight" in sd:   # SegModelBase.py:29-43
+            from .nets import pack_compress_pair
+            self.compress = pack_compress_pair(sd, P, planes, device)
         if not encoder_only:
             self.up = []
             for i in (1, 2, 3, 4):
@@ -74,6 +78,9 @@ class SegPlan(DetPlan):
         x2 = self.double_conv(w.down[0], [self.pool(x1, tag + "p1")], tag + "x2")
         x3 = self.double_conv(w.down[1], [self.pool(x2, tag + "p2")], tag + "x3")
         x4 = self.double_conv(w.down[2], [self.pool(x3, tag + "p3")], tag + "x4")
+        if w.compress is not None:   # UNet.py:30-32, seg/V2VNet.py:32-34, When2Com_UNet.py:163-165, seg/FusionBase.py:31-33
+            t = self.conv(w.compress[0], [x4], tag + "x4c")
+            x4 = self.conv(w.compress[1], [t], tag + "x4d")
         return x1, x2, x3, x4
 
     def build_decoder(self, w: SegUNetWeights, feat, x1, x2, x3):
@@ -104,6 +111,7 @@ class SegUNetPlan(SegPlan):
         self.w = SegUNetWeights(sd, planes, self.device)
         x_in = self.build_input()
         x1, x2, x3, x4 = self.build_encoder(self.w, x_in)
+        self.x4 = x4
         self.build_decoder(self.w, x4, x1, x2, x3)
 
     def forward(self, x):
