@@ -36,7 +36,7 @@ def main():
         # coincide and equal to fp32 reassociation error (<< the 1e-3 parity tolerance) otherwise.
         ident = all(torch.equal(out[k], ref_full[k][off:off + n]) for k in out)
         diff = max(((out[k] - ref_full[k][off:off + n]).abs().max() / ref_full[k].abs().max()).item() for k in out)
-        same = ident or diff < (2e-5 if planes == 2 else 2e-2)
+        same = ident or diff < (1e-4 if planes == 2 else 2e-2)
         msg = "rank %d planes=%d: graph==eager %s, sharded vs single-GPU slice: identical %s, rel diff %.2e" % (
             rank, planes, graph_same, ident, diff)
         if planes == 2 and rank == 0:
