@@ -98,7 +98,11 @@ typedef struct v2x_conv_params {
                                 be 192 and the packed weights carry 192 extra K columns holding the identity
                                 (W[n][taps*cin[0] + j] = (n % 192 == j)), so every N tile accumulates its own window on the
                                 tensor core instead of loading it in the epilogue */
-  int32_t reserved[2];
+  int32_t tap_pack;          /* EPI_ACT, 3x3 stride-1, cout == 32: the three horizontal filter taps are packed into the N
+                                dimension (weights [planes][96][3 * sum(cin)], row = kw*32 + co, k = (source, kh, ci);
+                                cout_pad == block_n == 96) and summed in the epilogue -- 3 MMAs of N = 96 per k-step instead
+                                of 9 of N = 32, whose cost is dominated by re-reading the A operand (csrc/conv_pack3.cu) */
+  int32_t reserved;
   /* EPI_GRU, optional: fp32 [N*H*W][cout] (packed gate order) added to the gate pre-activations -- the round-invariant
      half conv(mean, W_ih[:, C:]) + bias, computed once per frame by an EPI_F32_SPLIT launch (split == cout) so the three
      GNN rounds only convolve the changing half (V2VNet.py:99: cat([h_i, mean]); the mean never changes). */

@@ -79,10 +79,11 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("planes", [2, 1])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-@pytest.mark.parametrize("impl", ["crosscheck", "tc", "tc_nohalo"])
+@pytest.mark.parametrize("impl", ["crosscheck", "tc", "tc_nohalo", "tc_pack3"])
 def test_conv_bn_relu(impl, case, planes, monkeypatch):
     """impl: crosscheck = CUDA-core kernel; tc = tensor-core kernel (halo-tile mode where eligible);
-    tc_nohalo = tensor-core kernel with the per-tap box path forced for every layer."""
+    tc_nohalo = tensor-core kernel with the per-tap box path forced for every layer; tc_pack3 = the tap-packed kernel
+    (csrc/conv_pack3.cu) that the 32-output-channel 3x3 layers take by default."""
     from v2x_b200 import ops
     dev = _dev()
     if impl == "tc_nohalo":
@@ -98,7 +99,9 @@ def test_conv_bn_relu(impl, case, planes, monkeypatch):
     ref = ref_cbr(xs, wt, b, bn, stride)
     if up:
         ref = F.interpolate(ref, scale_factor=(2, 2))
-    pc = ops.pack_conv(wt, b, bn, cins=cins, stride=stride, planes=planes, device=dev)
+    pc = ops.pack_conv(wt, b, bn, cins=cins, stride=stride, planes=planes, device=dev, tap_pack=(impl == "tc_pack3"))
+    if impl == "tc_pack3" and not pc.tap_pack:
+        pytest.skip("layer is not eligible for tap packing (needs 3x3, stride 1, 32 output channels)")
     acts = []
     for x, cp in zip(xs, pc.cins):
         xp = F.pad(x, (0, 0, 0, 0, 0, cp - x.shape[1]))
@@ -461,3 +464,39 @@ def test_v2vnet_forward_from_voxels_and_u8_is_bit_identical():
         bad = synth.voxel_rows(lists)
         bad[0, 3] = 13
         m.forward_voxels(bad.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("geom", [(2, 8, 14), (1, 16, 20), (3, 24, 256), (1, 8, 5), (2, 256, 256)],
+                         ids=lambda g: "n%d_%dx%d" % g)
+@pytest.mark.parametrize("cins", [[13], [32], [64, 32], [96]], ids=lambda c: "cin" + "_".join(map(str, c)))
+def test_conv_tap_packed_geometries(cins, geom, planes):
+    """csrc/conv_pack3.cu on widths that are / are not multiples of its 14-pixel tile (partial right-edge tiles, maps
+    narrower than one tile), one and two sources, kc = 16 / 32, several maps; vs torch conv + BN + ReLU."""
+    from v2x_b200 import ops
+    dev = _dev()
+    n, h, w = geom
+    if h * w * n > 70000 and cins != [64, 32]:
+        pytest.skip("full-size map only for the conv8_1 shape")
+    g = torch.Generator().manual_seed(n * 1000 + h + w + sum(cins))
+    xs = [torch.randn((n, c, h, w), generator=g) for c in cins]
+    cin = sum(cins)
+    wt = (torch.rand((32, cin, 3, 3), generator=g) - 0.5) * (2.0 / (cin * 9) ** 0.5) * 1.7
+    b = torch.randn(32, generator=g) * 0.1
+    bn = rand_bn(32, g)
+    ref = ref_cbr(xs, wt, b, bn, 1)
+    pc = ops.pack_conv(wt, b, bn, cins=cins, planes=planes, device=dev, tap_pack=True)
+    assert pc.tap_pack and pc.weights.shape[1] == 96
+    acts = [to_act(F.pad(x, (0, 0, 0, 0, 0, cp - x.shape[1])), planes, dev) for x, cp in zip(xs, pc.cins)]
+    out = torch.full((planes, n, h, w, 32), 7.0, dtype=torch.bfloat16, device=dev)
+    ops.conv(pc, acts, out=out)
+    torch.cuda.synchronize()
+    err = rel_err(ops.act_to_float(out), ref)
+    print("pack3 cins=%s %s planes=%d rel_err=%.3e" % (cins, geom, planes, err))
+    assert err < TOL[planes], err
+    # relu = False path and a channel window inside a wider output tensor
+    wide = torch.zeros((planes, n, h, w, 64), dtype=torch.bfloat16, device=dev)
+    ops.ConvLaunch(pc, acts, relu=False, out0=wide, out_c_off=32)()
+    got = ops.act_to_float(wide)
+    assert got[:, :32].abs().max().item() == 0.0
+    assert rel_err(got[:, 32:], ref_cbr(xs, wt, b, bn, 1, relu=False)) < TOL[planes]

@@ -1197,6 +1197,13 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
   return V2X_OK;
 }
 
+// shared with conv_pack3.cu
+int encode_map_shared(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                      const cuuint32_t* box, int kc) {
+  return encode_map(m, base, rank, dims, strides_b, box, kc);
+}
+int launch_pack3(const v2x_conv_params* p, int debug_mode, cudaStream_t stream);
+
 static int g_debug_mode = 0;
 
 static int fill_dev(const v2x_conv_params* p, ConvDev& d) {
@@ -1443,6 +1450,8 @@ static int plan_smem(const v2x_conv_params* p, ConvDev& d, uint32_t budget, size
 }
 
 extern "C" int v2x_conv_fwd(const v2x_conv_params* p, void* stream_) {
+  V2X_REQUIRE(p != nullptr, "null params");
+  if (p->tap_pack) return launch_pack3(p, g_debug_mode, reinterpret_cast<cudaStream_t>(stream_));
   ConvDev d;
   int rc = fill_dev(p, d);
   if (rc) return rc;

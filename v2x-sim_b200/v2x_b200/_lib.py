@@ -45,7 +45,8 @@ class ConvParams(C.Structure):
         ("agents", C.c_int32),
         ("map_offset", C.c_int32),
         ("gru_pre_act", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("tap_pack", C.c_int32),
+        ("reserved", C.c_int32),
         ("gru_add", C.c_void_p),
         ("tail_weights", C.c_void_p),
         ("tail_bias", C.c_void_p),

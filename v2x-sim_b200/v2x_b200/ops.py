@@ -7,6 +7,7 @@ hand-written sm_100a kernels.  An ``act`` is a bf16 tensor ``[planes, N, H, W, C
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -98,6 +99,7 @@ class PackedConv:
     gru_bhn: Optional[torch.Tensor] = None
     keep: list = field(default_factory=list)
     gru_pre_act: bool = False   # weights carry 192 identity K columns for the pre-activation window (v2x_conv_params.gru_pre_act)
+    tap_pack: bool = False      # weights are [P, 96, 3 * sum(cins)]: horizontal taps packed into N (v2x_conv_params.tap_pack)
 
     @property
     def k_total(self):
@@ -108,8 +110,41 @@ def _f32(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+TAP_PACK = not os.environ.get("V2X_NO_TAP_PACK")   # A/B switch for the tap-packed 32-channel convs (csrc/conv_pack3.cu)
+
+
+def pack_conv_tap_packed(weight, bias, bn, *, cins: Sequence[int], planes=1, device=None) -> PackedConv:
+    """3x3 stride-1 conv with 32 output channels in the tap-packed form of csrc/conv_pack3.cu: the operand is
+    [planes, 96, 3 * sum(cins)] with row = kw * 32 + co and k = (source, kh, ci) -- built by handing the regular packer the
+    weights rearranged as a "3-tap" conv with 96 outputs (BN scale folded per row; rows 0..31 carry the folded bias)."""
+    lib = require_gpu()
+    device = device or weight.device
+    cout, cin_total = weight.shape[0], weight.shape[1]
+    assert cout == 32 and tuple(weight.shape[2:]) == (3, 3) and sum(cins) == cin_total
+    cin_pads = [((c + 15) // 16) * 16 for c in cins]
+    w = _f32(weight, device).permute(3, 0, 1, 2).reshape(3 * cout, cin_total, 3).contiguous()   # [kw*32+co][ci][kh]
+    rep = lambda t: None if t is None else _f32(t, device).repeat(3).contiguous()                # noqa: E731
+    b = rep(bias)
+    bnp = [rep(t) for t in bn] if bn is not None else [None] * 4
+    k_total = 3 * sum(cin_pads)
+    dst = torch.zeros((planes, 3 * cout, k_total), dtype=torch.bfloat16, device=device)
+    dst_bias = torch.zeros((3 * cout,), dtype=torch.float32, device=device)
+    ci_lo, k_off = 0, 0
+    for s, (c, cp) in enumerate(zip(cins, cin_pads)):
+        check(lib.v2x_pack_conv_weights(_ptr(w), _ptr(b), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]), _ptr(bnp[3]), BN_EPS,
+                                        3 * cout, cin_total, 3, ci_lo, ci_lo + c, cp, 0, 0, _ptr(dst), _ptr(dst_bias),
+                                        planes, 3 * cout, k_total, 0, k_off, int(s == 0), _stream()),
+              "v2x_pack_conv_weights(tap_pack)")
+        ci_lo += c
+        k_off += 3 * cp
+    pc = PackedConv(dst, dst_bias, cin_pads, 9, 1, cout, 3 * cout, planes)
+    pc.tap_pack = True
+    return pc
+
+
 def pack_conv(weight, bias, bn=None, *, cins: Sequence[int], cin_pads: Optional[Sequence[int]] = None, stride=1,
-              planes=1, device=None, vflip=False, gru=False, cout_pad: Optional[int] = None) -> PackedConv:
+              planes=1, device=None, vflip=False, gru=False, cout_pad: Optional[int] = None,
+              tap_pack: Optional[bool] = None) -> PackedConv:
     """BN-fold + reorder + bf16 split of one conv's weights, on device.
 
     weight: OIHW (or OI111 for the 1x1x1 Conv3D) fp32; ``cins`` = logical channels of each concat
@@ -120,6 +155,12 @@ def pack_conv(weight, bias, bn=None, *, cins: Sequence[int], cin_pads: Optional[
     cout, cin_total = weight.shape[0], weight.shape[1]
     taps = int(weight.numel() // (cout * cin_total))
     assert taps in (1, 9) and sum(cins) == cin_total
+    # tap packing pays where the layer is tensor-pipe bound, i.e. K is deep enough (conv8_1: 96 channels); the 13 / 32
+    # channel layers are epilogue / HBM bound and keep the leaner N = 32 epilogue (measured, profiles/r01_v10)
+    eligible = taps == 9 and stride == 1 and cout == 32 and cin_pads is None and cout_pad is None and not vflip \
+        and not gru and weight.dim() == 4
+    if eligible and (tap_pack is True or (tap_pack is None and TAP_PACK and cin_total >= 64)):
+        return pack_conv_tap_packed(weight, bias, bn, cins=cins, planes=planes, device=device)
     cin_pads = list(cin_pads) if cin_pads is not None else [((c + 15) // 16) * 16 for c in cins]
     cout_pad = cout_pad or cout   # zero rows up to a multiple of the N tile (e.g. the 8-class seg logits)
     k_total = taps * sum(cin_pads)
@@ -274,12 +315,17 @@ class ConvLaunch:
         p.batch, p.agents, p.map_offset = batch, agents, map_offset
         p.gru_add = gru_add.data_ptr() if gru_add is not None else None
         p.gru_pre_act = int(pc.gru_pre_act)
+        if pc.tap_pack:
+            assert epilogue == EPI_ACT and not upsample2x and h_out % 8 == 0, "tap-packed convs: plain EPI_ACT, 8 | H"
+            p.tap_pack, p.block_n = 1, 96
         if tail is not None:   # fused 1x1 conv on the ReLU output (EPI_TAIL_F32_SPLIT)
             assert epilogue == EPI_TAIL_F32_SPLIT and tail.taps == 1 and tail.cins == [pc.cout] and tail.planes == planes
             p.tail_weights, p.tail_bias = tail.weights.data_ptr(), tail.bias.data_ptr()
             p.tail_cout, p.tail_cout_pad = tail.cout, tail.cout_pad
         self.p = p
         self.keep = (pc, list(srcs), out0, out1, passthrough, num_agent, gru_add, tail)
+        if crosscheck and pc.tap_pack:
+            raise V2XError("the CUDA-core cross-check kernel takes the regular operand layout: pack with tap_pack=False")
         self.fn = self.lib.v2x_conv_fwd_crosscheck if crosscheck else self.lib.v2x_conv_fwd
         k_eff = pc.taps * pc.cins[0] + 192 if pc.gru_pre_act else pc.taps * sum(pc.cins)
         self.flops = 2.0 * n * h_out * w_out * pc.cout * k_eff
