@@ -103,6 +103,11 @@ class DetPlan:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.flops = 0.0
         self.n_kernels = 0
+        # optional fork/join: launches [side_lo, side_hi) run on a second stream, concurrently with the launches after
+        # them on the main stream, and are joined before launch `side_join` (see V2VNetDetPlan: the x_4 encoder branch
+        # runs beside the warp / first GRU launch, which leave most of the SMs' tensor pipes idle)
+        self.side_lo = self.side_hi = self.side_join = -1
+        self._side_stream = None
 
     def act(self, name, h, w, c):
         t = ops.empty_act(self.planes, self.n, h, w, c, self.device)
@@ -183,6 +188,7 @@ class DetPlan:
         x2 = self.conv(c["conv3d_2"], [t], tag + "x2")
         t = self.conv(c["conv3_1"], [x2], tag + "x3a")
         x3 = self.conv(c["conv3_2"], [t], tag + "x3")
+        self.x4_branch = (len(self.launches), len(self.launches) + 2)   # launch indices of conv4_1, conv4_2
         t = self.conv(c["conv4_1"], [x3], tag + "x4a")
         # in the detection decoder x_4 is only ever consumed through F.interpolate(x_4, 2) (Backbone.py:176):
         # store it upsampled.  (PolicyNet4 consumes the plain x_4, When2com.py:354.)
@@ -243,12 +249,33 @@ class DetPlan:
                             split=n_cls, block_n=hw.head2.cout))
 
     # ---- execution ----
+    def _issue(self):
+        """Issue the launch list on the current stream, forking [side_lo, side_hi) onto the side stream."""
+        if self.side_lo < 0 or os.environ.get("V2X_NO_SIDE_STREAM"):
+            for l in self.launches:
+                l()
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        main, side = torch.cuda.current_stream(), self._side_stream
+        for i, l in enumerate(self.launches):
+            if i == self.side_lo:
+                side.wait_stream(main)          # fork: the side branch sees everything issued so far
+            if i == self.side_join:
+                main.wait_stream(side)          # join
+            if self.side_lo <= i < self.side_hi:
+                with torch.cuda.stream(side):
+                    l()
+            else:
+                l()
+        if self.side_join >= len(self.launches) or self.side_join < 0:
+            main.wait_stream(side)
+
     def run(self):
         if self.graph is not None:
             self.graph.replay()
         else:
-            for l in self.launches:
-                l()
+            self._issue()
 
     def capture(self):
         """Record the whole forward into one CUDA graph (side stream warm-up first, as CUDA requires)."""
@@ -256,14 +283,12 @@ class DetPlan:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
-                for l in self.launches:
-                    l()
+                self._issue()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for l in self.launches:
-                l()
+            self._issue()
         self.graph = g
 
     def result(self):
@@ -299,6 +324,11 @@ class V2VNetDetPlan(DetPlan):
         trans, na = self.trans, self.num_agent
         self.add(lambda: ops.warp_mean(x3, trans, na, batch, agents, include_self=False, only_v2i=only_v2i, out=mean))
         h = self.build_gru_rounds(x3, mean, gnn_iter, batch, agents, 0)
+        # conv4_1 / conv4_2 only feed the decoder: they run on the side stream beside the warp + GRU launches and
+        # are joined before conv5_1 (without compression; with it the x_3 the fuse step reads is produced after them)
+        if "com_compresser" not in self.enc_w.c:
+            self.side_lo, self.side_hi = self.x4_branch
+            self.side_join = len(self.launches)
         x8 = self.build_decoder(self.dec_w, x0, x1, x2, h, x4u)
         self.build_heads(self.head_w, x8)
 
