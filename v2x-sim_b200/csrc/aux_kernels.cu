@@ -140,11 +140,14 @@ __global__ void pack_gru_bias_kernel(const float* __restrict__ b_ih, const float
 // (C = 256) reads; the four taps x (A-1) sources are accumulated in registers and the mean is
 // written once.  The maps are 32x32xC (0.5 MB each in bf16) and stay L2-resident.
 // ---------------------------------------------------------------------------------------------
-template <int VEC_PER_LANE>
-__global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                 const double* __restrict__ trans, const long long* __restrict__ num_agent, int batch,
-                                 int agents, int H, int W, int C, int planes, int include_self, int only_v2i,
-                                 int unit_offset, int unit_count) {
+constexpr int kWarpMaxAgents = 8;   // sources whose sample positions are precomputed in registers
+
+template <int VEC_PER_LANE, int PLANES>
+__global__ void __launch_bounds__(256) warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                        const double* __restrict__ trans,
+                                                        const long long* __restrict__ num_agent, int batch, int agents,
+                                                        int H, int W, int C, int include_self, int only_v2i,
+                                                        int unit_offset, int unit_count) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long total_pix = (long long)unit_count * H * W;                 // targets computed by this launch
@@ -165,21 +168,36 @@ __global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
     int count = 0;
     if (i < na) {
       const float gx = (2.f * ow + 1.f) / W - 1.f, gy = (2.f * oh + 1.f) / H - 1.f;
-      for (int j = 0; j < na; ++j) {
+      // phase 1: sample positions of every participating source (independent loads of the 4x4 poses issue together,
+      // so the pose fetch is one memory round trip per pixel instead of one per source)
+      float sx_[kWarpMaxAgents], sy_[kWarpMaxAgents];
+      unsigned use = 0;
+#pragma unroll
+      for (int j = 0; j < kWarpMaxAgents; ++j) {
+        sx_[j] = 0.f; sy_[j] = 0.f;
+        if (j >= na || j >= agents) continue;
         if (j == i && !include_self) continue;
         if (only_v2i && i != 0 && j != 0 && j != i) continue;  // DetModelBase.py:196-198
-        ++count;
+        use |= 1u << j;
         float t00, t01, t02, t10, t11, t12;
         if (j == i) {  // FusionBase-style self term: identity
           t00 = 1.f; t01 = 0.f; t02 = 0.f; t10 = 0.f; t11 = 1.f; t12 = 0.f;
         } else {
           const double* T = trans + ((((long long)b * agents + j) * agents + i) << 4);
           // theta' (un-flipped domain): [[T00, -T01, -T03/32], [-T10, T11, +T13/32]]
-          t00 = (float)T[0]; t01 = -(float)T[1]; t02 = -(float)T[3] * (1.f / 32.f);
-          t10 = -(float)T[4]; t11 = (float)T[5]; t12 = (float)T[7] * (1.f / 32.f);
+          t00 = (float)__ldg(T + 0); t01 = -(float)__ldg(T + 1); t02 = -(float)__ldg(T + 3) * (1.f / 32.f);
+          t10 = -(float)__ldg(T + 4); t11 = (float)__ldg(T + 5); t12 = (float)__ldg(T + 7) * (1.f / 32.f);
         }
         const float sx = t00 * gx + t01 * gy + t02, sy = t10 * gx + t11 * gy + t12;
-        const float ix = ((sx + 1.f) * W - 1.f) * 0.5f, iy = ((sy + 1.f) * H - 1.f) * 0.5f;
+        sx_[j] = ((sx + 1.f) * W - 1.f) * 0.5f;
+        sy_[j] = ((sy + 1.f) * H - 1.f) * 0.5f;
+      }
+      count = __popc(use);
+      // sources beyond the precomputed window (agents > 8) are not supported by this kernel (checked on the host)
+#pragma unroll
+      for (int j = 0; j < kWarpMaxAgents; ++j) {
+        if (!((use >> j) & 1u)) continue;
+        const float ix = sx_[j], iy = sy_[j];
         const float fx = floorf(ix), fy = floorf(iy);
         const int x0 = (int)fx, y0 = (int)fy;
         const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
@@ -206,8 +224,8 @@ __global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
 #pragma unroll
             for (int t = 0; t < 4; ++t) {   // predicated loads: out-of-range taps are zeros padding and cost no traffic
               q[t] = inb[t] ? __ldg(reinterpret_cast<const uint4*>(sp[t] + c0)) : make_uint4(0, 0, 0, 0);
-              ql[t] = (planes == 2 && inb[t]) ? __ldg(reinterpret_cast<const uint4*>(sp[t] + plane_stride + c0))
-                                              : make_uint4(0, 0, 0, 0);
+              if (PLANES == 2)
+                ql[t] = inb[t] ? __ldg(reinterpret_cast<const uint4*>(sp[t] + plane_stride + c0)) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -216,7 +234,7 @@ __global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float2 f = __bfloat1622float2(h2[e]);
-                if (planes == 2) {
+                if (PLANES == 2) {
                   const float2 g = __bfloat1622float2(l2[e]);
                   f.x += g.x; f.y += g.y;
                 }
@@ -244,7 +262,7 @@ __global__ void warp_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
           lo[e] = pack_bf16x2(l0, l1);
         }
         *reinterpret_cast<uint4*>(dp + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (planes == 2) *reinterpret_cast<uint4*>(dp + out_plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (PLANES == 2) *reinterpret_cast<uint4*>(dp + out_plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
   }
@@ -335,6 +353,7 @@ extern "C" int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, 
                                  void* stream) {
   V2X_REQUIRE(x && out && trans && num_agent, "null pointer");
   V2X_REQUIRE(batch > 0 && agents > 0 && h > 0 && w > 0, "empty geometry");
+  V2X_REQUIRE(agents <= v2x::kWarpMaxAgents, "at most %d agents per scene", v2x::kWarpMaxAgents);
   V2X_REQUIRE(c > 0 && c % 8 == 0 && c <= 1024, "channels must be a multiple of 8, <= 1024");
   V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
   if (unit_count <= 0) { unit_offset = 0; unit_count = batch * agents; }
@@ -346,12 +365,13 @@ extern "C" int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, 
   __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
   const long long* na = reinterpret_cast<const long long*>(num_agent);
   cudaStream_t s = (cudaStream_t)stream;
-  if (c <= 256)
-    warp_mean_kernel<1><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i, unit_offset, unit_count);
-  else if (c <= 512)
-    warp_mean_kernel<2><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i, unit_offset, unit_count);
-  else
-    warp_mean_kernel<4><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, include_self, only_v2i, unit_offset, unit_count);
+#define V2X_WARP_MEAN(VEC_, PL_)                                                                              \
+  warp_mean_kernel<VEC_, PL_><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, include_self, \
+                                                       only_v2i, unit_offset, unit_count)
+  if (c <= 256) { if (planes == 1) V2X_WARP_MEAN(1, 1); else V2X_WARP_MEAN(1, 2); }
+  else if (c <= 512) { if (planes == 1) V2X_WARP_MEAN(2, 1); else V2X_WARP_MEAN(2, 2); }
+  else { if (planes == 1) V2X_WARP_MEAN(4, 1); else V2X_WARP_MEAN(4, 2); }
+#undef V2X_WARP_MEAN
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }
