@@ -1,5 +1,6 @@
-// Tap-packed 3x3 convolution for the 32-output-channel layers at full resolution (conv_pre_1/2, conv8_1/2:
-// CP/models/det/backbone/Backbone.py:102-104,230-237) on the sm_100a tensor cores.
+// Tap-packed 3x3 convolution for the narrow-output decoder layers (conv8_1: 96 -> 32 at 256x256, conv7_1: 192 -> 64 at
+// 128x128; CP/models/det/backbone/Backbone.py:211-237) on the sm_100a tensor cores.  Output channels are processed in
+// groups of 32 (blockIdx.y); the text below describes one group.
 //
 // Why: a tcgen05.mma of M=128, K=16 re-reads its whole 128-row A sub-tile from shared memory whatever N is, so its cost
 // is max(N/2, (128+N)/4) cycles (tools/mma_probe.cu) -- at N = 32 the tensor pipe idles 60% of the time waiting for
@@ -40,6 +41,7 @@ struct Pack3Dev {
   int num_stages;
   int tiles_w, tiles_per_img, m_tiles;
   int relu, debug_mode;
+  int groups;                // cout / 32: CTAs with blockIdx.y = g own output channels [32g, 32g + 32)
   void* out0;
   int out_c_total, out_c_off;
   long long out_plane_stride;
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
   __shared__ __align__(16) float s_bias[32];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.y;                                           // 32-output-channel group of this CTA
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;    // resident weights, then the halo ring
   const uint32_t ring_base = smem_base + p.b_region_bytes;
   const uint32_t bar_full = smem_u32(&bars[0]);
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
   const uint32_t bar_tfull = smem_u32(&bars[2 * kP3MaxStages + 1]);    // [2]
   const uint32_t bar_tempty = smem_u32(&bars[2 * kP3MaxStages + 3]);   // [2]
 
-  if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias[grp * kP3N + threadIdx.x];
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA0);
     if (p.nsrc > 1) prefetch_tmap(&tmA1);
@@ -124,7 +127,8 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
           const int kcol = (s ? 3 * total_cin0 : 0) + kh * p.cin[s] + cb * KC;
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl)
-            tma_load_2d(smem_base + (uint32_t)((cbg * 3 + kh) * PLANES + pl) * B_TILE, &tmB, bar_bres, kcol, pl * kP3N);
+            tma_load_2d(smem_base + (uint32_t)((cbg * 3 + kh) * PLANES + pl) * B_TILE, &tmB, bar_bres, kcol,
+                        (pl * p.groups + grp) * kP3N);
         }
       }
     }
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
     const uint32_t srow = stg + (uint32_t)lane * 64u;
     const uint32_t ssw = (uint32_t)(lane >> 1) & 3u;
     const int unit = lane & 3;
-    __nv_bfloat16* const out = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.out_c_off + unit * 8;
+    __nv_bfloat16* const out = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.out_c_off + grp * 32 + unit * 8;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += grid_stride, ++it) {
       const int img = tile / p.tiles_per_img;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
 
 template <int PLANES, int KSTEPS>
 static int launch_pack3_t(const Pack3Dev& d, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, size_t smem,
-                          int ctas, cudaStream_t stream) {
+                          dim3 ctas, cudaStream_t stream) {
   static cudaError_t attr_err = cudaFuncSetAttribute(conv_pack3_kernel<PLANES, KSTEPS>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_pack3_kernel)");
@@ -310,14 +314,15 @@ static int launch_pack3_t(const Pack3Dev& d, const CUtensorMap& a0, const CUtens
 // Host side of v2x_conv_fwd for params with tap_pack != 0 (validated here; called from conv_tcgen05.cu).
 int launch_pack3(const v2x_conv_params* p, int debug_mode, cudaStream_t stream) {
   V2X_REQUIRE(p->src[0] && p->weights && p->bias && p->out0, "null src/weights/bias/out0");
-  V2X_REQUIRE(p->taps == 9 && p->stride == 1 && p->cout == 32 && p->cout_pad == kP3N && p->block_n == kP3N,
-              "tap_pack needs a 3x3 stride-1 conv with cout == 32 (cout_pad == block_n == 96)");
+  V2X_REQUIRE(p->taps == 9 && p->stride == 1 && p->cout > 0 && p->cout % 32 == 0 && p->cout_pad == 3 * p->cout &&
+                  p->block_n == kP3N,
+              "tap_pack needs a 3x3 stride-1 conv with 32 | cout, cout_pad == 3 * cout and block_n == 96");
   V2X_REQUIRE(p->epilogue == V2X_EPI_ACT && !p->upsample2x, "tap_pack supports the plain EPI_ACT epilogue only");
   V2X_REQUIRE(p->planes == 1 || p->planes == 2, "planes must be 1 or 2");
   V2X_REQUIRE(p->n_maps > 0 && p->h_out > 0 && p->w_out > 0 && p->h_out % kP3TileH == 0, "tap_pack needs 8 | H");
   V2X_REQUIRE(p->cin[0] > 0 && p->cin[0] % 16 == 0 && (p->src[1] == nullptr || (p->cin[1] > 0 && p->cin[1] % 16 == 0)),
               "channels per source must be multiples of 16");
-  V2X_REQUIRE(p->out_c_total >= p->out_c_off + 32 && p->out_c_total % 8 == 0 && p->out_c_off % 8 == 0,
+  V2X_REQUIRE(p->out_c_total >= p->out_c_off + p->cout && p->out_c_total % 8 == 0 && p->out_c_off % 8 == 0,
               "bad output channel window");
   Pack3Dev d{};
   d.n_maps = p->n_maps; d.h_out = p->h_out; d.w_out = p->w_out;
@@ -333,6 +338,7 @@ int launch_pack3(const v2x_conv_params* p, int debug_mode, cudaStream_t stream) 
   d.tiles_per_img = d.tiles_w * (p->h_out / kP3TileH);
   d.m_tiles = p->n_maps * d.tiles_per_img;
   d.relu = p->relu; d.debug_mode = debug_mode;
+  d.groups = p->cout / 32;
   d.out0 = p->out0; d.out_c_total = p->out_c_total; d.out_c_off = p->out_c_off;
   d.out_plane_stride = (long long)p->n_maps * p->h_out * p->w_out * p->out_c_total;
   d.bias = p->bias;
@@ -367,7 +373,7 @@ int launch_pack3(const v2x_conv_params* p, int debug_mode, cudaStream_t stream) 
   if (d.nsrc == 1) tmA[1] = tmA[0];
   {
     const cuuint64_t k_total = 3ull * (cuuint64_t)(d.cin[0] + d.cin[1]);
-    cuuint64_t dims[2] = {k_total, (cuuint64_t)p->planes * kP3N};
+    cuuint64_t dims[2] = {k_total, (cuuint64_t)p->planes * d.groups * kP3N};
     cuuint64_t str[1] = {k_total * 2};
     cuuint32_t box[2] = {(cuuint32_t)kc, kP3N};
     int rc = encode_map_shared(&tmB, p->weights, 2, dims, str, box, kc);
@@ -379,10 +385,12 @@ int launch_pack3(const v2x_conv_params* p, int debug_mode, cudaStream_t stream) 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  int ctas = sms * ctas_per_sm;
-  if (ctas > d.m_tiles) ctas = d.m_tiles;
-  const int rounds = (d.m_tiles + ctas - 1) / ctas;
-  ctas = (d.m_tiles + rounds - 1) / rounds;
+  int ctas_x = sms * ctas_per_sm / d.groups;
+  if (ctas_x < 1) ctas_x = 1;
+  if (ctas_x > d.m_tiles) ctas_x = d.m_tiles;
+  const int rounds = (d.m_tiles + ctas_x - 1) / ctas_x;
+  ctas_x = (d.m_tiles + rounds - 1) / rounds;
+  const dim3 ctas(ctas_x, d.groups);
 #define V2X_P3(KS_)                                                                              \
   if (kc == 16 * KS_)                                                                            \
     return p->planes == 1 ? launch_pack3_t<1, KS_>(d, tmA[0], tmA[1], tmB, smem, ctas, stream)   \

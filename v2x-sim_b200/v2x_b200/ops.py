@@ -114,16 +114,19 @@ TAP_PACK = not os.environ.get("V2X_NO_TAP_PACK")   # A/B switch for the tap-pack
 
 
 def pack_conv_tap_packed(weight, bias, bn, *, cins: Sequence[int], planes=1, device=None) -> PackedConv:
-    """3x3 stride-1 conv with 32 output channels in the tap-packed form of csrc/conv_pack3.cu: the operand is
-    [planes, 96, 3 * sum(cins)] with row = kw * 32 + co and k = (source, kh, ci) -- built by handing the regular packer the
-    weights rearranged as a "3-tap" conv with 96 outputs (BN scale folded per row; rows 0..31 carry the folded bias)."""
+    """3x3 stride-1 conv with 32 | cout in the tap-packed form of csrc/conv_pack3.cu: the operand is
+    [planes, cout/32 * 96, 3 * sum(cins)] with row = (group, kw, co) and k = (source, kh, ci) -- built by handing the
+    regular packer the weights rearranged as a "3-tap" conv with 3 * cout outputs (BN scale folded per row; rows
+    (group, kw = 0, co) carry the folded bias)."""
     lib = require_gpu()
     device = device or weight.device
     cout, cin_total = weight.shape[0], weight.shape[1]
-    assert cout == 32 and tuple(weight.shape[2:]) == (3, 3) and sum(cins) == cin_total
+    assert cout % 32 == 0 and tuple(weight.shape[2:]) == (3, 3) and sum(cins) == cin_total
+    g = cout // 32
     cin_pads = [((c + 15) // 16) * 16 for c in cins]
-    w = _f32(weight, device).permute(3, 0, 1, 2).reshape(3 * cout, cin_total, 3).contiguous()   # [kw*32+co][ci][kh]
-    rep = lambda t: None if t is None else _f32(t, device).repeat(3).contiguous()                # noqa: E731
+    # [cout, ci, kh, kw] -> [g, kw, 32, ci, kh] -> rows (g, kw, co)
+    w = _f32(weight, device).view(g, 32, cin_total, 3, 3).permute(0, 4, 1, 2, 3).reshape(3 * cout, cin_total, 3).contiguous()
+    rep = lambda t: None if t is None else _f32(t, device).view(g, 1, 32).expand(g, 3, 32).reshape(-1).contiguous()  # noqa: E731
     b = rep(bias)
     bnp = [rep(t) for t in bn] if bn is not None else [None] * 4
     k_total = 3 * sum(cin_pads)
@@ -157,9 +160,12 @@ def pack_conv(weight, bias, bn=None, *, cins: Sequence[int], cin_pads: Optional[
     assert taps in (1, 9) and sum(cins) == cin_total
     # tap packing pays where the layer is tensor-pipe bound, i.e. K is deep enough (conv8_1: 96 channels); the 13 / 32
     # channel layers are epilogue / HBM bound and keep the leaner N = 32 epilogue (measured, profiles/r01_v10)
-    eligible = taps == 9 and stride == 1 and cout == 32 and cin_pads is None and cout_pad is None and not vflip \
+    eligible = taps == 9 and stride == 1 and cout in (32, 64) and cin_pads is None and cout_pad is None and not vflip \
         and not gru and weight.dim() == 4
-    if eligible and (tap_pack is True or (tap_pack is None and TAP_PACK and cin_total >= 64)):
+    # 64-output layers with deep K (conv7_1: 192 channels) additionally stop re-streaming their 221 KB of weights from
+    # L2 for every M tile: each 32-channel group keeps its 110 KB operand resident
+    deep = cin_total >= (64 if cout == 32 else 128) and 3 * cin_total * 96 * 2 * planes <= 112 * 1024  # + >= 3 stages
+    if eligible and (tap_pack is True or (tap_pack is None and TAP_PACK and deep)):
         return pack_conv_tap_packed(weight, bias, bn, cins=cins, planes=planes, device=device)
     cin_pads = list(cin_pads) if cin_pads is not None else [((c + 15) // 16) * 16 for c in cins]
     cout_pad = cout_pad or cout   # zero rows up to a multiple of the N tile (e.g. the 8-class seg logits)
