@@ -35,7 +35,7 @@ def main():
     for i, r in enumerate(data):
         name = NAMES[i] if len(data) == len(NAMES) else str(i)
         out.append([name, r[ix["ID"]], r[ix["Kernel Name"]][:80], r[ix["Grid Size"]], r[ix["Block Size"]]] + [r[ix[c]] for c in cols])
-        if "conv_tc" in r[ix["Kernel Name"]]:
+        if "conv_tc" in r[ix["Kernel Name"]] or "conv_pack3" in r[ix["Kernel Name"]]:
             rd += to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]])
             wr += to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
     path = prefix + "_ncu_full_summary.csv"
