@@ -206,8 +206,8 @@ def time_launch_list(launches, reps=20):
 
 
 def run_ours(args, rank, world, local_rank):
-    from oracle import synth  # synthetic weights / inputs only (not on the measured path)
     from v2x_b200 import default_det_config, nets
+    from v2x_b200 import synthetic as synth   # seeded synthetic weights / inputs (nothing under oracle/ on this arm)
     from coperception.models.det import V2VNet
     import torch.distributed as dist
 
