@@ -4,7 +4,7 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "v2x-sim_b200")]
 import torch
-from oracle import synth
+from v2x_b200 import synthetic as synth
 from v2x_b200 import _lib, nets
 
 NAMES = ["pack_in","pre_1","pre_2","c1_1","c1_2","c3d_1","c2_1","c2_2","c3d_2","c3_1","c3_2","c4_1","c4_2","warp","gru_m","gru1","gru2","gru3","c5_1","c5_2","c6_1","c6_2","c7_1","c7_2","c8_1","c8_2","head1","head2"]

@@ -181,7 +181,7 @@ def plant_detections(sd, cls_ref, per_agent=150, loc_scale=0.05, score=0.7):
     """Planted-weight variant of a detection state_dict for the NMS / mAP parity runs.
 
     With seeded random weights no foreground score passes the reference's hard-coded 0.7 filter
-    (postprocess.py:84), so NMS / AP would compare empty sets.  Given the oracle's ``cls`` logits
+    (postprocess.py:84), so NMS / AP would compare empty sets.  Given the un-planted model's ``cls`` logits
     ``[N, H*W*A, 2]`` for the un-planted state, this returns a copy of ``sd`` whose
       * foreground bias ``classification.conv2.bias[1::2]`` is shifted so that about ``per_agent`` anchors
         per map score above ``score`` (channel = anchor*2 + class, DetModelBase.py:238-245), and
