@@ -237,7 +237,8 @@ def run_ours(args, rank, world, local_rank):
         from v2x_b200 import sharding
         gb, gt, gn = synth.make_scene(B * world, AGENTS, seed=0)      # the global batch: B * world scenes
         off, n_loc = sharding.unit_range(B * world * AGENTS, rank, world)
-        plan = nets.V2VNetDetShardedPlan(sd, B * world, AGENTS, rank, world, gnn_iter=GNN_ITER, planes=planes, device=dev)
+        plan = nets.V2VNetDetShardedPlan(sd, B * world, AGENTS, rank, world, gnn_iter=GNN_ITER, planes=planes, device=dev,
+                                         exchange=args.exchange)
         plan.set_inputs(gb[off:off + n_loc].to(dev), gt.to(dev), gn.to(dev))
         del gb
     else:
@@ -433,8 +434,11 @@ def run_ours(args, rank, world, local_rank):
                        "scenes_per_gpu_per_step": B, "agents": AGENTS, "precision": args.precision,
                        "l2": "no flush: per-step inputs %.0f MB and activations ~%.1f GB exceed the 126 MB L2"
                              % (B * 17.04, 0.4 * B),
-                       "parallelism": ("unit-sharded x%d (40 agent-major units per GPU), one NCCL all-gather of layer-3 "
-                                       "maps per step overlapped with the x_4 branch" % world) if unit_sharded
+                       "parallelism": ("unit-sharded x%d (40 agent-major units per GPU), one NCCL %s of layer-3 "
+                                       "maps per step overlapped with the x_4 branch"
+                                       % (world, "all-gather" if args.exchange == "allgather"
+                                          else "neighbour exchange (grouped send/recv of the 4 other agents' maps)"))
+                       if unit_sharded
                        else "scene-sharded x%d, no data-path collective" % world},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
@@ -470,6 +474,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", default="unit", choices=["unit", "scene"], help="multi-GPU partition (N > 1)")
+    ap.add_argument("--exchange", default="allgather", choices=["neighbours", "allgather"],
+                    help="unit-sharded x_3 exchange: one all-gather (default; measured at 2/4/8 GPUs), or NCCL send/recv of "
+                         "just the needed neighbour maps (equal at 2/4 GPUs, not yet measured at 8)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -68,3 +68,73 @@ def test_two_rank_sharded_forward_matches_unsharded():
         err, ok_planes = ret[r]
         assert err < 1e-4, (r, err)
         assert ok_planes
+
+
+@pytest.mark.parametrize("world,batch_total,agents", [(2, 2, 2), (2, 4, 5), (4, 8, 5), (4, 32, 5), (8, 64, 5), (8, 8, 5),
+                                                      (5, 3, 5), (8, 16, 6)])
+def test_neighbour_exchange_plan_is_complete_and_consistent(world, batch_total, agents):
+    """Simulate the targeted x_3 exchange on one process: after it, every rank holds its own maps and every map of the
+    other agents of its scenes, each received exactly once, and the k-th send of s to r pairs with r's k-th receive from s."""
+    import numpy as np
+    from v2x_b200 import sharding
+    units = batch_total * agents
+    n = units // world
+    truth = np.arange(units)
+    plans = [sharding.neighbour_exchange_plan(batch_total, agents, r, world) for r in range(world)]
+    for r in range(world):
+        sends, recvs = plans[r]
+        buf = np.full(units, -1)
+        buf[r * n:(r + 1) * n] = truth[r * n:(r + 1) * n]
+        for peer in range(world):
+            from_peer = [(gs, c) for (p, gs, c) in recvs if p == peer]
+            to_me = [(ls, c) for (q, ls, c) in plans[peer][0] if q == r] if peer != r else []
+            assert len(from_peer) == len(to_me)
+            for (gs, c), (ls, c2) in zip(from_peer, to_me):
+                assert c == c2 and gs == peer * n + ls       # pairs up in issue order
+                assert (buf[gs:gs + c] == -1).all()          # nothing is received twice
+                buf[gs:gs + c] = truth[peer * n + ls:peer * n + ls + c]
+        for u in range(r * n, (r + 1) * n):
+            b = u % batch_total
+            for j in range(agents):
+                assert buf[batch_total * j + b] == batch_total * j + b
+        received = int((buf >= 0).sum()) - n
+        assert received <= n * (agents - 1)
+
+
+def _worker_exchange(rank, world, port, ret):
+    for p in (ROOT, os.path.join(ROOT, "v2x-sim_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from v2x_b200 import sharding
+        B, A = 4, 5
+        n = B * A // world
+        full = torch.arange(2 * B * A * 3, dtype=torch.float32).view(2, B * A, 1, 1, 3).to(torch.bfloat16)
+        local = full[:, rank * n:(rank + 1) * n].contiguous()
+        out = torch.full_like(full, -1.0)
+        for w in sharding.exchange_neighbour_units(local, out, B, A):
+            w.wait()
+        ok = True
+        for u in range(rank * n, (rank + 1) * n):
+            for j in range(A):
+                g = B * j + u % B
+                ok = ok and bool(torch.equal(out[:, g], full[:, g]))
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_neighbour_exchange_over_gloo_world4():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_worker_exchange, args=(r, 4, port, ret)) for r in range(4)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert all(ret[r] for r in range(4))

@@ -20,7 +20,8 @@ def main():
     off, n = sharding.unit_range(B * A, rank, world)
     ok = True
     for planes in (2, 1):
-        plan = nets.V2VNetDetShardedPlan(sd, B, A, rank, world, planes=planes)
+        plan = nets.V2VNetDetShardedPlan(sd, B, A, rank, world, planes=planes,
+                                         exchange=os.environ.get("V2X_EXCHANGE", "neighbours" if planes == 2 else "allgather"))
         out = plan.forward(bevs[off:off + n].cuda(), trans.cuda(), nat.cuda())
         torch.cuda.synchronize()
         eager = {k: v.clone() for k, v in out.items()}

@@ -448,8 +448,12 @@ class V2VNetDetShardedPlan(DetPlan):
     overlap it.  The forward is three CUDA graphs (-> x_3 | x_4 branch | fuse + decoder + heads) around the collective."""
 
     def __init__(self, sd, batch_total: int, agents: int, rank: int, world: int, gnn_iter: int = 3, planes: int = 1,
-                 device="cuda", group=None, only_v2i=False):
+                 device="cuda", group=None, only_v2i=False, exchange=None):
         from . import sharding
+        # "allgather": one ncclAllGather of every unit's x_3; "neighbours": point-to-point exchange of just the maps of
+        # the other agents of this rank's scenes (sharding.exchange_neighbour_units)
+        self.exchange = exchange or os.environ.get("V2X_EXCHANGE", "allgather")
+        assert self.exchange in ("allgather", "neighbours")
         self.offset, n_loc = sharding.unit_range(batch_total * agents, rank, world)
         super().__init__(n_loc, planes, device)
         ops.require_gpu()
@@ -504,7 +508,12 @@ class V2VNetDetShardedPlan(DetPlan):
         seg = self._segments()
         for i in range(3):
             if i == 1:   # x_3 is final: exchange it while the x_4 branch runs
-                _, works = self.sharding.all_gather_units(self.x3_local, out=self.x3_all, group=self.group, async_op=True)
+                if self.exchange == "neighbours":
+                    works = self.sharding.exchange_neighbour_units(self.x3_local, self.x3_all, self.batch, self.agents,
+                                                                   group=self.group)
+                else:
+                    _, works = self.sharding.all_gather_units(self.x3_local, out=self.x3_all, group=self.group,
+                                                              async_op=True)
             if i == 2:
                 for w in works:
                     w.wait()   # stream-level wait: the fuse kernels queue behind the collective
