@@ -1,5 +1,6 @@
 // C-ABI plumbing: version, thread-local error string, device capability probe.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -18,6 +19,11 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return V2X_ERR_CUDA;
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("V2X_NO_PDL") == nullptr;
+  return on;
 }
 
 }  // namespace v2x

@@ -124,6 +124,16 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// launch_dependents: the next kernel in the stream (launched with the programmatic-serialization attribute) may start
+// its CTAs as soon as every CTA of this grid has executed this (or exited) -- its prologue (barrier init, TMEM
+// allocation, resident-weight loads) and, SM by SM, its first tiles overlap this grid's tail.
+// wait: blocks until every prerequisite grid has COMPLETED and its memory is visible; executed before the first
+// access to anything an earlier kernel produced.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();   // host: V2X_NO_PDL=1 disables the launch attribute (A/B switch)
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)

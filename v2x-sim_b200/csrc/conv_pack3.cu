@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
   const uint32_t tmem_base = tmem_slot;
   const int grid_stride = gridDim.x;
   const int total_cin0 = p.cin[0];
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
       }
     }
     __syncwarp();
+    pdl_wait();   // weights are constants; the activations were written by the previous kernel(s)
     int stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += grid_stride) {
       const int img = tile / p.tiles_per_img;
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
     }
   } else {
     // ===== epilogue warps: TMEM lane quadrant (warp & 3); lane = halo position (r, c) = (row >> 4, row & 15) =====
+    pdl_wait();
     const int quad = warp & 3;
     const bool no_store = p.debug_mode == 3;
     const bool relu = p.relu != 0;
@@ -306,8 +309,17 @@ static int launch_pack3_t(const Pack3Dev& d, const CUtensorMap& a0, const CUtens
   static cudaError_t attr_err = cudaFuncSetAttribute(conv_pack3_kernel<PLANES, KSTEPS>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_pack3_kernel)");
-  conv_pack3_kernel<PLANES, KSTEPS><<<ctas, kP3Threads, smem, stream>>>(a0, a1, b, d);
-  V2X_CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = ctas;
+  cfg.blockDim = dim3(kP3Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  V2X_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_pack3_kernel<PLANES, KSTEPS>, a0, a1, b, d));
   return V2X_OK;
 }
 

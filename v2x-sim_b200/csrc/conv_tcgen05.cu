@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
   const uint32_t tmem_base = tmem_slot;
   const bool is_gru = p.epilogue == V2X_EPI_GRU;
   const int grid_stride = gridDim.x;
+  pdl_launch_dependents();   // the next layer's CTAs may take over this SM as soon as this CTA exits (see common.cuh)
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -563,6 +564,7 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
           tma_load_2d(smem_base + (k * PLANES + pl) * B_TILE, &tmB, bar_bres, k * KC, pl * p.cout_pad + n0);
     }
     __syncwarp();
+    pdl_wait();   // weights above are constants; the activations below were written by the previous kernel(s)
     const bool no_tma = p.debug_mode == 2;
     int stage = 0, phase = 0, bstage = 0, bphase = 0;
     TileIter ti;
@@ -801,6 +803,7 @@ __global__ void __launch_bounds__(kNumThreads, BN <= 64 ? 2 : 1) conv_tc_kernel(
     }
   } else {
     // ===== epilogue warps =====
+    pdl_wait();   // before the first global store / passthrough read (cheap: nothing to do until the first tile is done)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int r_h = HALO ? (row >> 3) : (row >> 4), r_w = HALO ? (row & 7) : (row & 15);
@@ -1335,8 +1338,17 @@ static int launch_tc(const ConvDev& d, const CUtensorMap& a0, const CUtensorMap&
   const int rounds = (d.m_tiles + ctas_x - 1) / ctas_x;
   ctas_x = (d.m_tiles + rounds - 1) / rounds;
   dim3 grid(ctas_x, d.n_tiles);
-  conv_tc_kernel<BN, PLANES, KSTEPS, HALO><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, t, d);
-  V2X_CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  V2X_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, PLANES, KSTEPS, HALO>, a0, a1, b, t, d));
   return V2X_OK;
 }
 
