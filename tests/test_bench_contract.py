@@ -1,0 +1,49 @@
+"""bench.py's one-line JSON contract (the driver parses it): the reference arm on CPU, the measured arm on the GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def _run(args, timeout):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                       timeout=timeout, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, "bench.py must print exactly ONE line on stdout, got %d" % len(lines)
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    """`bench.py --impl reference` times the reference's CPU algorithm (oracle port) and prints the same schema with
+    impl = reference, zero transfer bytes and a cpu_baseline describing the run."""
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"], 600)
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["unit"] == "frames/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+@pytest.mark.gpu
+def test_measured_arm_line():
+    d = _run(["--steps", "3", "--warmup", "3", "--no-cpu-baseline"], 900)
+    assert (BASE_KEYS | {"roofline", "clocks", "gpu_launches", "e2e_detections"}) <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "bf16" and d["data"] == "synthetic"
+    assert d["value"] > 100 and d["gpu_launches"] == d["kernels_per_step"] * 3 > 0
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 8 * 5 * 256 * 256 * 13 * 4 + 8 * 25 * 16 * 8 + 8 * 5 * 8
+    assert e["d2h_bytes_per_step"] == 8 * 5 * 256 * 256 * 6 * (2 + 6) * 4 and 0 < e["value"] < d["value"]
+    assert d["e2e_detections"]["d2h_bytes_per_step"] < e["d2h_bytes_per_step"] // 100
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
