@@ -299,6 +299,38 @@ def gen_compress():
     print("compress_seg_unet_l3_kd_seed17", out["logits.sum"])
 
 
+def gen_layers():
+    """Communication at other encoder layers (DetModelBase.py:71-92): V2VNet at layer 2 (128 ch, 64x64, two GNN
+    rounds), DiscoNet at layer 2, MaxFusion at layer 1 (64 ch, 128x128)."""
+    def save(tag, r, meta):
+        out = {"meta": np.asarray(meta, dtype=np.int64)}
+        summarize("loc", r["loc"], out)
+        summarize("cls", r["cls"], out)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+        print(tag, out["loc.sum"])
+    m = ref_loader.ref_v2vnet_det(gnn_iter_times=2, layer=2, layer_channel=128)
+    sd = synth.v2vnet_det_state(18, layer_channel=128)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(1, 5, 18, present=[4])
+    with torch.no_grad():
+        save("layer2_v2vnet_det_seed18", m(bevs, trans, nat, batch_size=1), [1, 5, 18, 2])
+    m = ref_loader.ref_fusion_det("disco", layer=2)
+    sd = synth.fusion_det_state("disco", 19, channel=128)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(1, 5, 19)
+    with torch.no_grad():
+        save("layer2_disco_det_seed19", m(bevs, trans, nat, batch_size=1)[0], [1, 5, 19, 2])
+    m = ref_loader.ref_fusion_det("max", layer=1)
+    sd = synth.fusion_det_state("max", 20)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(1, 5, 20, present=[3])
+    with torch.no_grad():
+        save("layer1_max_det_seed20", m(bevs, trans, nat, batch_size=1), [1, 5, 20, 1])
+
+
 def main():
     if not ref_loader.available():
         print("reference tree not available; golden fixtures can only be generated in the build container")
@@ -311,8 +343,12 @@ def main():
     if "--compress-only" in sys.argv:
         gen_compress()
         return 0
+    if "--layers-only" in sys.argv:
+        gen_layers()
+        return 0
     gen_fusion_all()
     gen_compress()
+    gen_layers()
     gen_warp("warp_small_seed3", 3)
     gen_convgru("convgru_small_seed4", 4)
     gen_fafnet("fafnet_n2_seed0", 2, 0)

@@ -110,11 +110,11 @@ _FUSION_CLASSES = {"mean": "MeanFusion", "max": "MaxFusion", "sum": "SumFusion",
                    "agent": "AgentWiseWeightedFusion", "disco": "DiscoNet"}
 
 
-def ref_fusion_det(kind, num_agent=5, kd_flag=0, only_v2i=False, compress_level=0):
+def ref_fusion_det(kind, num_agent=5, kd_flag=0, only_v2i=False, compress_level=0, layer=3):
     install()
     name = _FUSION_CLASSES[kind]
     cls = getattr(importlib.import_module("coperception.models.det." + name), name)
-    return cls(ref_config(), layer=3, kd_flag=kd_flag, num_agent=num_agent, only_v2i=only_v2i,
+    return cls(ref_config(), layer=layer, kd_flag=kd_flag, num_agent=num_agent, only_v2i=only_v2i,
                compress_level=compress_level)
 
 

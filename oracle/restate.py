@@ -151,12 +151,13 @@ def v2vnet_fuse(x_3, trans_matrices, num_agent_tensor, sd, batch_size, agent_num
 
 
 def v2vnet_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=1, agent_num=5, gnn_iter=3,
-                       compress_level=0, stages=False):
-    """det V2VNet.forward (CP/models/det/V2VNet.py:47-120)."""
+                       compress_level=0, stages=False, layer=3):
+    """det V2VNet.forward (CP/models/det/V2VNet.py:47-120); ``layer`` = the communicated encoder layer
+    (DetModelBase.get_feature_maps_and_size / get_decoded_layers, :71-92, :211-224)."""
     enc = encode(bevs, sd, "u_encoder.", compress_level)
-    fused = v2vnet_fuse(enc[3], trans_matrices, num_agent_tensor, sd, batch_size, agent_num, gnn_iter)
+    fused = v2vnet_fuse(enc[layer], trans_matrices, num_agent_tensor, sd, batch_size, agent_num, gnn_iter)
     dec_in = list(enc)
-    dec_in[3] = fused
+    dec_in[layer] = fused
     x8 = decode(*dec_in, sd, "decoder.")[0]
     res = heads(x8, sd)
     if stages:
@@ -464,12 +465,12 @@ def fusion_stage(kind, feat_maps, trans_matrices, num_agent_tensor, sd, batch_si
 
 
 def fusion_det_forward(kind, bevs, trans_matrices, num_agent_tensor, sd, batch_size=1, agent_num=5, only_v2i=False,
-                       stages=False):
+                       stages=False, layer=3):
     """det FusionBase.forward / DiscoNet.forward (kd_flag = 0 result dict)."""
     enc = encode(bevs, sd, "u_encoder.", compress_level=int("u_encoder.com_compresser.weight" in sd))
-    fused = fusion_stage(kind, enc[3], trans_matrices, num_agent_tensor, sd, batch_size, agent_num, only_v2i)
+    fused = fusion_stage(kind, enc[layer], trans_matrices, num_agent_tensor, sd, batch_size, agent_num, only_v2i)
     dec_in = list(enc)
-    dec_in[3] = fused
+    dec_in[layer] = fused
     dec = decode(*dec_in, sd, "decoder.", kd_flag=True)
     res = heads(dec[0], sd)
     if stages:

@@ -185,7 +185,7 @@ def _fusion_extra_state(sd, g, kind, channel, seg):
         _pair_weight_net_state(sd, g, "pixel_weighted_fusion.", channel, False)
 
 
-def fusion_det_state(kind, seed=0, compress_level=0):
+def fusion_det_state(kind, seed=0, compress_level=0, channel=256):
     """state_dict of the det FusionBase family (IntermediateModelBase.py:24-25 + the subclass' fusion net)."""
     assert kind in FUSION_KINDS
     g = _Gen(seed)
@@ -193,7 +193,7 @@ def fusion_det_state(kind, seed=0, compress_level=0):
     heads_state(sd, g)
     backbone_state(sd, g, "u_encoder.", compress_level=compress_level)
     backbone_state(sd, g, "decoder.")
-    _fusion_extra_state(sd, g, kind, 256, False)
+    _fusion_extra_state(sd, g, kind, channel, False)
     return sd
 
 

@@ -270,3 +270,63 @@ def test_compress_level_models(golden_dir):
     assert len(tup) == 7
     for name, t in zip(("logits", "x9", "x8", "x7", "x6", "x5", "x4"), tup):
         assert list(t.shape) == list(g[name + ".shape"]) and golden_err(t, g, name) < 1e-3, name
+
+
+def test_other_communication_layers(golden_dir):
+    """communication at encoder layers other than 3 -- V2VNet at layer 2 (128 ch @ 64x64, two GNN rounds),
+    DiscoNet at layer 2, MaxFusion at layer 1 (64 ch @ 128x128) -- vs oracle and live-reference fixtures."""
+    import coperception.models.det as det
+    from oracle import restate, synth
+    from oracle.gen_golden import STRIDE
+    from v2x_b200 import default_det_config
+
+    def check(out, ref, g, what):
+        for k in ("loc", "cls"):
+            sub = out[k].detach().float().cpu().contiguous().view(-1)[::STRIDE].numpy()
+            eg = float(np.abs(sub - g[k + ".sub"]).max() / np.abs(g[k + ".sub"]).max())
+            e = rel_err(out[k], ref[k])
+            print("layers %s %s rel_err=%.3e golden=%.3e" % (what, k, e, eg))
+            assert e < 1e-3 and eg < 1e-3, (what, k)
+
+    g = np.load(os.path.join(golden_dir, "layer2_v2vnet_det_seed18.npz"))
+    sd = synth.v2vnet_det_state(18, layer_channel=128)
+    bevs, trans, nat = synth.make_scene(1, 5, 18, present=[4])
+    with torch.no_grad():
+        ref = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=5, gnn_iter=2, layer=2)
+    m = det.V2VNet(default_det_config(), 2, 2, 128, num_agent=5)
+    m.load_state_dict(sd, strict=True)
+    m.precision = "bf16x3"
+    m = m.cuda().eval()
+    with torch.no_grad():
+        check(m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1), ref, g, "v2vnet@2")
+    m.precision = "bf16"
+    m.invalidate()
+    with torch.no_grad():
+        out = m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    assert rel_err(out["loc"], ref["loc"]) < 5e-2
+
+    g = np.load(os.path.join(golden_dir, "layer2_disco_det_seed19.npz"))
+    sd = synth.fusion_det_state("disco", 19, channel=128)
+    bevs, trans, nat = synth.make_scene(1, 5, 19)
+    with torch.no_grad():
+        ref = restate.fusion_det_forward("disco", bevs, trans, nat, sd, batch_size=1, agent_num=5, layer=2)
+    m = det.DiscoNet(default_det_config(), layer=2, kd_flag=0, num_agent=5)
+    m.load_state_dict(sd, strict=True)
+    m.precision = "bf16x3"
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out, w = m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    check(out, ref, g, "disco@2")
+    assert w[0][0].shape == (64, 64)
+
+    g = np.load(os.path.join(golden_dir, "layer1_max_det_seed20.npz"))
+    sd = synth.fusion_det_state("max", 20)
+    bevs, trans, nat = synth.make_scene(1, 5, 20, present=[3])
+    with torch.no_grad():
+        ref = restate.fusion_det_forward("max", bevs, trans, nat, sd, batch_size=1, agent_num=5, layer=1)
+    m = det.MaxFusion(default_det_config(), layer=1, kd_flag=0, num_agent=5)
+    m.load_state_dict(sd, strict=True)
+    m.precision = "bf16x3"
+    m = m.cuda().eval()
+    with torch.no_grad():
+        check(m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1), ref, g, "max@1")

@@ -197,3 +197,27 @@ def test_compress_level(golden_dir):
     x, _, _ = synth.make_seg_scene(1, 2, 17)
     with torch.no_grad():
         _check("logits", restate.seg_unet_forward(x, sd), g)
+
+
+def test_other_communication_layers(golden_dir):
+    """Fusion at encoder layers other than 3 (DetModelBase.py:71-92, 211-224): restatement vs the live reference."""
+    g = np.load(os.path.join(golden_dir, "layer2_v2vnet_det_seed18.npz"))
+    sd = synth.v2vnet_det_state(18, layer_channel=128)
+    bevs, trans, nat = synth.make_scene(1, 5, 18, present=[4])
+    with torch.no_grad():
+        r = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=5, gnn_iter=2, layer=2)
+    _check("loc", r["loc"], g)
+    _check("cls", r["cls"], g)
+    g = np.load(os.path.join(golden_dir, "layer2_disco_det_seed19.npz"))
+    bevs, trans, nat = synth.make_scene(1, 5, 19)
+    with torch.no_grad():
+        r = restate.fusion_det_forward("disco", bevs, trans, nat, synth.fusion_det_state("disco", 19, channel=128),
+                                       batch_size=1, agent_num=5, layer=2)
+    _check("loc", r["loc"], g)
+    g = np.load(os.path.join(golden_dir, "layer1_max_det_seed20.npz"))
+    bevs, trans, nat = synth.make_scene(1, 5, 20, present=[3])
+    with torch.no_grad():
+        r = restate.fusion_det_forward("max", bevs, trans, nat, synth.fusion_det_state("max", 20), batch_size=1,
+                                       agent_num=5, layer=1)
+    _check("loc", r["loc"], g)
+    _check("cls", r["cls"], g)

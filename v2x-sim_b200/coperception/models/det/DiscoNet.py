@@ -8,7 +8,10 @@ class DiscoNet(FusionBase):
 
     def __init__(self, config, layer=3, in_channels=13, kd_flag=True, num_agent=5, compress_level=0, only_v2i=False):
         super().__init__(config, layer, in_channels, kd_flag, num_agent, compress_level, only_v2i)
-        self.pixel_weighted_fusion = PairWeightNet(256)
+        if layer == 3:        # DiscoNet.py:23-26: the weight net only exists for layers 3 and 2
+            self.pixel_weighted_fusion = PairWeightNet(256)
+        elif layer == 2:
+            self.pixel_weighted_fusion = PairWeightNet(128)
 
     def forward(self, bevs, trans_matrices, num_agent_tensor, batch_size=1):
         """kd_flag == 1: (result, x_8, x_7, x_6, x_5, fused); else (result, save_agent_weight_list) where the list holds,
@@ -18,7 +21,8 @@ class DiscoNet(FusionBase):
         plan, result = self._run(bevs, trans_matrices, num_agent_tensor, batch_size)
         if self.kd_flag == 1:
             return (result, *plan.kd_layers())
-        scores = plan.fuse.scores.view(batch_size, self.agent_num, self.agent_num, 32, 32)
+        hw = int(round(plan.fuse.scores.shape[-1] ** 0.5))
+        scores = plan.fuse.scores.view(batch_size, self.agent_num, self.agent_num, hw, hw)
         na = num_agent_tensor[:, 0].tolist()
         weights = []
         for b in range(batch_size):

@@ -16,9 +16,9 @@ class V2VNet(B200DetModel):
     def __init__(self, config, gnn_iter_times, layer, layer_channel, in_channels=13, num_agent=5, compress_level=0,
                  only_v2i=False):
         super().__init__(config, layer, in_channels, num_agent=num_agent, only_v2i=only_v2i)
-        if layer != 3 or layer_channel != 256:
-            raise NotImplementedError("v2x_b200 V2VNet fuses at layer 3 (256 channels) as the reference scripts do "
-                                      "(train_codet.py:106-114)")
+        if layer not in (1, 2, 3) or layer_channel != (32, 64, 128, 256, 512)[layer]:
+            raise NotImplementedError("v2x_b200 V2VNet communicates at layer 1, 2 or 3 with layer_channel = 64 / 128 / 256 "
+                                      "(the reference scripts use layer 3, train_codet.py:106-114)")
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)
         self.layer_channel = layer_channel
@@ -40,7 +40,7 @@ class V2VNet(B200DetModel):
         key = ("v2v", int(batch_size), dev.index, self.precision, mode)
         plan = self._get_plan(key, lambda: nets.V2VNetDetPlan(
             self._state(), int(batch_size), self.agent_num, gnn_iter=self.gnn_iter_num, planes=self._planes(),
-            device=dev, only_v2i=self.only_v2i, input_mode=mode))
+            device=dev, only_v2i=self.only_v2i, input_mode=mode, layer=self.layer))
         if mode == "u8":
             bevs = bevs.view(torch.uint8) if bevs.dtype == torch.bool else bevs
         else:
@@ -60,7 +60,7 @@ class V2VNet(B200DetModel):
         key = ("v2v", int(batch_size), dev.index, self.precision, "voxels", cap)
         plan = self._get_plan(key, lambda: nets.V2VNetDetPlan(
             self._state(), int(batch_size), self.agent_num, gnn_iter=self.gnn_iter_num, planes=self._planes(),
-            device=dev, only_v2i=self.only_v2i, input_mode="voxels", voxel_capacity=cap))
+            device=dev, only_v2i=self.only_v2i, input_mode="voxels", voxel_capacity=cap, layer=self.layer))
         out = plan.forward(voxel_rows, trans_matrices.to(torch.float64), num_agent_tensor.to(torch.int64))
         plan.check_voxels()
         return out

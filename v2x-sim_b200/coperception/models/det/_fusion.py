@@ -31,8 +31,8 @@ class FusionBase(B200DetModel):
 
     def __init__(self, config, layer=3, in_channels=13, kd_flag=True, num_agent=5, compress_level=0, only_v2i=False):
         super().__init__(config, layer, in_channels, kd_flag, num_agent=num_agent, only_v2i=only_v2i)
-        if layer != 3:
-            raise NotImplementedError("v2x_b200 fusion models fuse at layer 3 as the reference scripts do")
+        if layer not in (0, 1, 2, 3):
+            raise NotImplementedError("v2x_b200 fusion models fuse at layer 0..3 (the reference scripts use layer 3)")
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)
         self.num_agent = 0   # the reference overwrites this per scene (FusionBase.py:16,41)
@@ -49,7 +49,7 @@ class FusionBase(B200DetModel):
         key = (self.KIND, int(batch_size), dev.index, self.precision)
         plan = self._get_plan(key, lambda: nets.FusionDetPlan(
             self._state(), self.KIND, int(batch_size), self.agent_num, planes=self._planes(), device=dev,
-            only_v2i=self.only_v2i))
+            only_v2i=self.only_v2i, layer=self.layer))
         result = plan.forward(bevs.to(torch.float32), trans_matrices.to(torch.float64), num_agent_tensor.to(torch.int64))
         return plan, result
 

@@ -301,8 +301,11 @@ class V2VNetDetPlan(DetPlan):
     """det V2VNet forward (V2VNet.py:47-120) for ``batch`` scenes x ``agents`` agent slots."""
 
     def __init__(self, sd, batch: int, agents: int = 5, gnn_iter: int = 3, planes: int = 1, device="cuda",
-                 only_v2i=False, input_mode="f32", voxel_capacity=0):
+                 only_v2i=False, input_mode="f32", voxel_capacity=0, layer: int = 3):
         super().__init__(batch * agents, planes, device)
+        if layer not in (1, 2, 3):
+            raise ops.V2XError("V2VNet on the sm_100a path communicates at layer 1, 2 or 3 (the ConvGRU tile needs a "
+                               "multiple of 64 channels; layer 4 only exists 2x-upsampled in the workspace)")
         ops.require_gpu()
         self.batch, self.agents, self.gnn_iter = batch, agents, gnn_iter
         dev = self.device
@@ -317,19 +320,21 @@ class V2VNetDetPlan(DetPlan):
 
         x_in = self.build_input(input_mode, voxel_capacity)
         x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
-        c3 = x3.shape[-1]
+        xs = [x0, x1, x2, x3]
+        xl = xs[layer]              # the communicated layer (DetModelBase.get_feature_maps_and_size, :71-92)
+        cl, hl, wl = xl.shape[-1], xl.shape[2], xl.shape[3]
         # neighbours are always warped from the ORIGINAL encoder maps (V2VNet.py:85-94), so the mean is
         # round-invariant: one warp launch per frame instead of 60 grid_sample calls
-        mean = self.act("mean", 32, 32, c3)
+        mean = self.act("mean", hl, wl, cl)
         trans, na = self.trans, self.num_agent
-        self.add(lambda: ops.warp_mean(x3, trans, na, batch, agents, include_self=False, only_v2i=only_v2i, out=mean))
-        h = self.build_gru_rounds(x3, mean, gnn_iter, batch, agents, 0)
+        self.add(lambda: ops.warp_mean(xl, trans, na, batch, agents, include_self=False, only_v2i=only_v2i, out=mean))
+        xs[layer] = self.build_gru_rounds(xl, mean, gnn_iter, batch, agents, 0)
         # conv4_1 / conv4_2 only feed the decoder: they run on the side stream beside the warp + GRU launches and
-        # are joined before conv5_1 (without compression; with it the x_3 the fuse step reads is produced after them)
-        if "com_compresser" not in self.enc_w.c:
+        # are joined before conv5_1 (layer 3 without compression; otherwise the fuse input is produced after them)
+        if layer == 3 and "com_compresser" not in self.enc_w.c:
             self.side_lo, self.side_hi = self.x4_branch
             self.side_join = len(self.launches)
-        x8 = self.build_decoder(self.dec_w, x0, x1, x2, h, x4u)
+        x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], x4u)
         self.build_heads(self.head_w, x8)
 
     def set_inputs(self, bevs, trans_matrices, num_agent_tensor):
@@ -604,6 +609,9 @@ class FuseStage:
             else:
                 # conv1_5: 32x32 "valid" conv over the H-flipped score map -> one scalar per pair
                 # (AgentWiseWeightedFusion.py:65,74); scores are un-flipped here, so mirror the filter rows instead
+                if (h, w) != (32, 32):
+                    raise ops.V2XError("AgentWiseWeightedFusion's 32x32 conv1_5 only fits 32x32 maps (layer 3), as in "
+                                       "the reference (AgentWiseWeightedFusion.py:65)")
                 w5 = sd[p + "conv1_5.weight"].detach().to(device=dev, dtype=torch.float32).reshape(h, w)
                 self.w5f = w5f = torch.flip(w5, (0,)).contiguous()
                 self.b5 = b5 = sd[p + "conv1_5.bias"].detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -618,8 +626,11 @@ class FusionDetPlan(DetPlan):
     """det intermediate-fusion baselines: encoder -> FuseStage(kind) at layer 3 -> decoder -> heads
     (FusionBase.py:23-75; DiscoNet.py:36-129)."""
 
-    def __init__(self, sd, kind: str, batch: int, agents: int = 5, planes: int = 1, device="cuda", only_v2i=False):
+    def __init__(self, sd, kind: str, batch: int, agents: int = 5, planes: int = 1, device="cuda", only_v2i=False,
+                 layer: int = 3):
         super().__init__(batch * agents, planes, device)
+        if layer not in (0, 1, 2, 3):
+            raise ops.V2XError("fusion models on the sm_100a path fuse at layer 0..3 (layer 4 only exists 2x-upsampled)")
         ops.require_gpu()
         self.batch, self.agents, self.kind = batch, agents, kind
         dev = self.device
@@ -630,9 +641,10 @@ class FusionDetPlan(DetPlan):
         self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
         x_in = self.build_input()
         x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
-        self.fuse = FuseStage(self, kind, sd, x3, self.trans, self.num_agent, batch, agents, only_v2i=only_v2i)
-        self.fused = self.fuse.out
-        x8 = self.build_decoder(self.dec_w, x0, x1, x2, self.fused, x4u)
+        xs = [x0, x1, x2, x3]
+        self.fuse = FuseStage(self, kind, sd, xs[layer], self.trans, self.num_agent, batch, agents, only_v2i=only_v2i)
+        self.fused = xs[layer] = self.fuse.out
+        x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], x4u)
         self.build_heads(self.head_w, x8)
 
     def forward(self, bevs, trans_matrices, num_agent_tensor):
