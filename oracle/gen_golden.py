@@ -331,6 +331,71 @@ def gen_layers():
         save("layer1_max_det_seed20", m(bevs, trans, nat, batch_size=1), [1, 5, 20, 1])
 
 
+TRAIN_GRAD_KEYS = {
+    "v2vnet": ["u_encoder.conv_pre_1.weight", "u_encoder.bn_pre_1.weight", "u_encoder.conv1_1.weight",
+               "u_encoder.conv3d_1.conv3d.weight", "u_encoder.conv3_2.weight", "u_encoder.bn3_2.bias",
+               "u_encoder.conv4_2.weight", "convgru.weight_ih_l0", "convgru.bias_ih_l0", "convgru.bias_hh_l0",
+               "decoder.conv5_1.weight", "decoder.conv8_2.weight", "decoder.bn8_2.weight", "classification.conv1.weight",
+               "classification.conv2.bias", "regression.box_prediction.0.weight", "regression.box_prediction.3.weight"],
+    "fafnet": ["stpn.conv_pre_1.weight", "stpn.bn_pre_2.bias", "stpn.conv2_1.weight", "stpn.conv4_1.bias",
+               "stpn.conv6_1.weight", "stpn.bn7_2.weight", "stpn.conv8_1.weight", "classification.conv2.weight",
+               "regression.box_prediction.3.bias"],
+}
+TRAIN_BN_KEYS = {"v2vnet": ["u_encoder.bn_pre_1", "u_encoder.bn3_2", "u_encoder.conv3d_2.bn3d", "decoder.bn5_1",
+                            "decoder.bn8_2", "classification.bn1", "regression.box_prediction.1"],
+                 "fafnet": ["stpn.bn_pre_1", "stpn.bn4_2", "stpn.conv3d_1.bn3d", "stpn.bn8_2", "classification.bn1"]}
+
+
+def grad_stride(numel):
+    """Subsample stride of a gradient tensor in the training fixtures: about 4096 samples of the big ones."""
+    return max(1, numel // 4096) | 1
+
+
+def make_upstream(out, seed):
+    """Seeded d(loss)/d(out): dense small values, like the gradient of a mean-reduced loss (float64)."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    return {k: (torch.rand(out[k].shape, generator=g, dtype=torch.float64) - 0.5) * (2.0 / out[k].numel() ** 0.5)
+            for k in ("loc", "cls")}
+
+
+def gen_train_step(tag, kind, seed):
+    """One training step of the LIVE reference module in .train() mode: outputs, gradients of a spread of parameters
+    (strided subsample + L2 norm each) and the BN running buffers after the step.  SURVEY 8(f1) oracle pin."""
+    if kind == "v2vnet":
+        m, sd = ref_loader.ref_v2vnet_det(), synth.v2vnet_det_state(seed)
+        bevs, trans, nat = synth.make_scene(1, 5, seed, present=[4])
+        call = lambda: m(bevs, trans, nat, batch_size=1)                      # noqa: E731
+    else:
+        m, sd = ref_loader.ref_fafnet(kd_flag=0), synth.fafnet_state(seed)
+        bevs = synth.make_bevs(3, seed)
+        call = lambda: m(bevs)                                                 # noqa: E731
+    m.load_state_dict(sd, strict=True)
+    m.double().train()
+    bevs = bevs.double()
+    with ref_loader.float64_shim():
+        r = call()
+        up = make_upstream(r, seed)
+        torch.autograd.backward([r["cls"], r["loc"]], [up["cls"], up["loc"]])
+    assert r["loc"].dtype == torch.float64
+    out = {"meta": np.asarray([seed], dtype=np.int64), "kind": np.asarray(kind)}
+    for name in ("loc", "cls"):     # float64 fixtures (summarize() stores float32)
+        flat = r[name].detach().contiguous().view(-1)
+        out[name + ".shape"] = np.asarray(r[name].shape, dtype=np.int64)
+        out[name + ".sub"] = flat[::STRIDE].numpy().copy()
+    params = dict(m.named_parameters())
+    for k in TRAIN_GRAD_KEYS[kind]:
+        g = params[k].grad
+        out["grad." + k + ".sub"] = g.detach().reshape(-1)[::grad_stride(g.numel())].numpy().copy()   # float64
+        out["grad." + k + ".norm"] = np.float64(g.detach().double().norm().item())
+    state = m.state_dict()
+    for k in TRAIN_BN_KEYS[kind]:
+        out["bn." + k + ".running_mean"] = state[k + ".running_mean"].numpy().copy()
+        out["bn." + k + ".running_var"] = state[k + ".running_var"].numpy().copy()
+        out["bn." + k + ".num_batches_tracked"] = np.int64(state[k + ".num_batches_tracked"].item())
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
+    print(tag, "|grad first|", out["grad." + TRAIN_GRAD_KEYS[kind][0] + ".norm"])
+
+
 def main():
     if not ref_loader.available():
         print("reference tree not available; golden fixtures can only be generated in the build container")
@@ -346,9 +411,15 @@ def main():
     if "--layers-only" in sys.argv:
         gen_layers()
         return 0
+    if "--train-only" in sys.argv:
+        gen_train_step("train_step_v2vnet_seed21", "v2vnet", 21)
+        gen_train_step("train_step_fafnet_seed22", "fafnet", 22)
+        return 0
     gen_fusion_all()
     gen_compress()
     gen_layers()
+    gen_train_step("train_step_v2vnet_seed21", "v2vnet", 21)
+    gen_train_step("train_step_fafnet_seed22", "fafnet", 22)
     gen_warp("warp_small_seed3", 3)
     gen_convgru("convgru_small_seed4", 4)
     gen_fafnet("fafnet_n2_seed0", 2, 0)

@@ -18,7 +18,35 @@ import torch.nn.functional as F
 EPS = 1e-5  # nn.BatchNorm2d default
 
 
+_TRAIN = False      # set by ``training_mode()``: BatchNorm uses batch statistics and updates its running buffers
+BN_MOMENTUM = 0.1   # nn.BatchNorm2d / BatchNorm3d default (the reference never overrides it)
+
+
+class training_mode:
+    """``with restate.training_mode(): ...`` -- the restatement behaves like the reference module after ``.train()``:
+    every BatchNorm normalises with the statistics of the current batch (all A*B maps, padded agents included), updates
+    ``running_mean`` / ``running_var`` in place with momentum 0.1 (unbiased variance) and bumps ``num_batches_tracked``
+    (torch.nn.modules.batchnorm._BatchNorm.forward).  Nothing else on the path differs between train and eval
+    (no dropout; ``p_com_outage`` defaults to 0).  Used as the oracle of the training / backward row, SURVEY 8(f1):
+    gradients come from torch.autograd over these same functions."""
+
+    def __enter__(self):
+        global _TRAIN
+        self._prev, _TRAIN = _TRAIN, True
+        return self
+
+    def __exit__(self, *exc):
+        global _TRAIN
+        _TRAIN = self._prev
+        return False
+
+
 def _bn(x, sd, name):
+    if _TRAIN:
+        if name + ".num_batches_tracked" in sd:
+            sd[name + ".num_batches_tracked"] += 1
+        return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"],
+                            sd[name + ".weight"], sd[name + ".bias"], True, BN_MOMENTUM, EPS)
     return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"],
                         sd[name + ".weight"], sd[name + ".bias"], False, 0.0, EPS)
 
@@ -40,7 +68,9 @@ def encode(bevs, sd, p="u_encoder.", compress_level=0):
     """Backbone.encode (Backbone.py:89-143).  bevs: [N,1,256,256,13] (the model permutes to
     [N,1,13,256,256] first, V2VNet.py:51)."""
     x = bevs.permute(0, 1, 4, 2, 3)
-    x = x.reshape(-1, x.size(-3), x.size(-2), x.size(-1)).to(torch.float)
+    # Backbone.py:101 casts to torch.float; following the weights' dtype instead is identical in fp32 and lets the
+    # training oracle run in float64 (its fixtures are made from the live module under a float->double shim)
+    x = x.reshape(-1, x.size(-3), x.size(-2), x.size(-1)).to(sd[p + "conv_pre_1.weight"].dtype)
     x = cbr(x, sd, p, "conv_pre_1", "bn_pre_1")
     x = cbr(x, sd, p, "conv_pre_2", "bn_pre_2")
     x_1 = cbr(x, sd, p, "conv1_1", "bn1_1", stride=2)
@@ -96,8 +126,8 @@ def feature_transformation(local_com_mat, b, j, agent_idx, trans_matrices, size)
     (bilinear, zeros padding, align_corners=False)."""
     nb_agent = local_com_mat[b, j].unsqueeze(0)
     tfm = trans_matrices[b, j, agent_idx]
-    M = torch.hstack((tfm[:2, :2], -tfm[:2, 3:4])).float().unsqueeze(0)
-    mask = torch.tensor([[[1, 1, 4 / 128], [1, 1, 4 / 128]]])
+    M = torch.hstack((tfm[:2, :2], -tfm[:2, 3:4])).to(local_com_mat.dtype).unsqueeze(0)   # `.float()` in the reference
+    mask = torch.tensor([[[1, 1, 4 / 128], [1, 1, 4 / 128]]], dtype=M.dtype)
     M = M * mask
     grid = F.affine_grid(M, size=torch.Size(size), align_corners=False)
     return F.grid_sample(nb_agent, grid, mode="bilinear", padding_mode="zeros", align_corners=False).squeeze(0)
@@ -492,3 +522,24 @@ def teacher_forward(bevs, sd):
     enc = encode(bevs, sd, "stpn.")
     dec = decode(*enc, sd, "stpn.", kd_flag=True)
     return (*dec, enc[3], enc[4])
+
+
+# ---------------------------------------------------------------------------------------------
+# Training step oracle: train-mode forward + vector-Jacobian product
+# ---------------------------------------------------------------------------------------------
+def train_step_vjp(forward, sd, upstream):
+    """Run ``forward(sd)`` (a closure over one of the ``*_forward`` functions above) in training mode with every
+    floating-point parameter of ``sd`` as an autograd leaf, back-propagate ``sum_k <out[k], upstream[k]>`` and return
+    (outputs, {param name: grad}, sd after the step -- its BN running buffers are updated in place, as the module's are).
+    What FaFModule.step needs from the model (CoDetModule.py:217-310): the loss itself stays the reference's python and
+    only hands d(loss)/d(loc), d(loss)/d(cls) back."""
+    work = {}
+    for k, v in sd.items():
+        buf = k.endswith(("running_mean", "running_var", "num_batches_tracked"))
+        work[k] = v.clone() if buf else v.clone().requires_grad_(v.is_floating_point())
+    with training_mode():
+        out = forward(work)
+    keys = sorted(upstream)
+    torch.autograd.backward([out[k] for k in keys], [upstream[k] for k in keys])
+    grads = {k: v.grad for k, v in work.items() if v.requires_grad and v.grad is not None}
+    return {k: out[k].detach() for k in keys}, grads, {k: v.detach() for k, v in work.items()}
