@@ -1,0 +1,53 @@
+"""CPU proofs (against torch) of the host-side weight transforms in v2x_b200/transforms.py: the parity decomposition of
+a 3x3 conv over a nearest-2x-upsampled map, and the data gradients of the path's stride-1 / stride-2 3x3 convs as
+stride-1 correlations.  float64, so the identities hold to round-off."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from v2x_b200 import transforms as T
+
+
+def _rand(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed), dtype=torch.float64)
+
+
+@pytest.mark.parametrize("n,ci,co,h,w", [(1, 3, 4, 5, 6), (2, 8, 5, 4, 4), (1, 1, 1, 1, 1), (1, 4, 4, 7, 2)])
+def test_upsample_conv_parity_decomposition(n, ci, co, h, w):
+    """conv3x3(pad 1) of F.interpolate(x, 2) (Backbone.py:173-178) == four 2x2 correlations of x, interleaved."""
+    x, wt = _rand((n, ci, h, w), 1), _rand((co, ci, 3, 3), 2)
+    ref = F.conv2d(F.interpolate(x, scale_factor=(2, 2)), wt, padding=1)
+    got = T.upsample_conv_parity_apply(x, wt)
+    assert got.shape == ref.shape and (got - ref).abs().max().item() < 1e-12
+    weff = T.upsample_conv_parity_weights(wt)
+    assert set(weff) == {(0, 0), (0, 1), (1, 0), (1, 1)} and all(v.shape == (co, ci, 2, 2) for v in weff.values())
+    # every class sums all nine taps: a constant input far from the border gives the same value on all four parities
+    total = wt.sum((2, 3))
+    for v in weff.values():
+        assert (v.sum((2, 3)) - total).abs().max().item() < 1e-12
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_dgrad_stride1_is_a_correlation_with_rotated_transposed_weights(k):
+    x = _rand((2, 5, 6, 7), 3).requires_grad_(True)
+    wt = _rand((4, 5, k, k), 4)
+    y = F.conv2d(x, wt, padding=k // 2)
+    dy = _rand(tuple(y.shape), 5)
+    (ref,) = torch.autograd.grad(y, x, dy)
+    got = F.conv2d(dy, T.dgrad_weights_stride1(wt), padding=k // 2)
+    assert (got - ref).abs().max().item() < 1e-12
+
+
+@pytest.mark.parametrize("h,w", [(4, 6), (8, 8), (2, 2)])
+def test_dgrad_stride2_parity_decomposition(h, w):
+    """Data gradient of the path's 3x3 / stride 2 / pad 1 convs (Backbone.py:25,28,31,34) through four stride-1
+    sub-correlations of dy, one per input parity class: 1 + 2 + 2 + 4 = 9 taps."""
+    x = _rand((2, 3, h, w), 6).requires_grad_(True)
+    wt = _rand((5, 3, 3, 3), 7)
+    y = F.conv2d(x, wt, stride=2, padding=1)
+    dy = _rand(tuple(y.shape), 8)
+    (ref,) = torch.autograd.grad(y, x, dy)
+    got = T.dgrad_stride2_apply(dy, wt, (h, w))
+    assert (got - ref).abs().max().item() < 1e-12
+    parts = T.dgrad_parity_weights_stride2(wt)
+    assert sum(v[0].shape[2] * v[0].shape[3] for v in parts.values()) == 9
