@@ -108,3 +108,31 @@ def test_fusion_family_state_dict_schema():
     for name in ("UNet", "V2VNet", "When2Com_UNet", "MeanFusion", "MaxFusion", "SumFusion", "CatFusion",
                  "AgentWiseWeightedFusion", "DiscoNet", "SegModelBase", "FusionBase"):
         assert hasattr(seg, name), name
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under v2x-sim_b200/ may import it, and bench.py may only touch it in
+    its cpu_baseline / --impl reference leg (cpu_reference), never on the measured arm (run_ours)."""
+    import ast
+    import inspect
+    offenders = []
+    for d, _, files in os.walk(os.path.join(ROOT, "v2x-sim_b200")):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(d, f)).read())
+            for node in ast.walk(tree):
+                mods = []
+                if isinstance(node, ast.Import):
+                    mods = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom) and node.level == 0:
+                    mods = [node.module or ""]
+                if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+                    offenders.append(os.path.join(d, f))
+    assert not offenders, offenders
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert "oracle" not in inspect.getsource(bench.run_ours)
+    assert "from oracle import" in inspect.getsource(bench.cpu_reference)   # the one sanctioned use
