@@ -331,69 +331,100 @@ def gen_layers():
         save("layer1_max_det_seed20", m(bevs, trans, nat, batch_size=1), [1, 5, 20, 1])
 
 
-TRAIN_GRAD_KEYS = {
-    "v2vnet": ["u_encoder.conv_pre_1.weight", "u_encoder.bn_pre_1.weight", "u_encoder.conv1_1.weight",
-               "u_encoder.conv3d_1.conv3d.weight", "u_encoder.conv3_2.weight", "u_encoder.bn3_2.bias",
-               "u_encoder.conv4_2.weight", "convgru.weight_ih_l0", "convgru.bias_ih_l0", "convgru.bias_hh_l0",
-               "decoder.conv5_1.weight", "decoder.conv8_2.weight", "decoder.bn8_2.weight", "classification.conv1.weight",
-               "classification.conv2.bias", "regression.box_prediction.0.weight", "regression.box_prediction.3.weight"],
-    "fafnet": ["stpn.conv_pre_1.weight", "stpn.bn_pre_2.bias", "stpn.conv2_1.weight", "stpn.conv4_1.bias",
-               "stpn.conv6_1.weight", "stpn.bn7_2.weight", "stpn.conv8_1.weight", "classification.conv2.weight",
-               "regression.box_prediction.3.bias"],
-}
-TRAIN_BN_KEYS = {"v2vnet": ["u_encoder.bn_pre_1", "u_encoder.bn3_2", "u_encoder.conv3d_2.bn3d", "decoder.bn5_1",
-                            "decoder.bn8_2", "classification.bn1", "regression.box_prediction.1"],
-                 "fafnet": ["stpn.bn_pre_1", "stpn.bn4_2", "stpn.conv3d_1.bn3d", "stpn.bn8_2", "classification.bn1"]}
-
-
 def grad_stride(numel):
-    """Subsample stride of a gradient tensor in the training fixtures: about 4096 samples of the big ones."""
-    return max(1, numel // 4096) | 1
+    """Subsample stride of a gradient tensor in the training fixtures: about 512 samples of the big ones."""
+    return max(1, numel // 512) | 1
 
 
-def make_upstream(out, seed):
-    """Seeded d(loss)/d(out): dense small values, like the gradient of a mean-reduced loss (float64)."""
+TRAIN_CASES = {   # tag -> (kind, seed)
+    "train_step_v2vnet_seed21": ("v2vnet", 21),
+    "train_step_fafnet_seed22": ("fafnet", 22),
+    "train_step_when2com_seed23": ("when2com", 23),
+    "train_step_disco_seed24": ("disco", 24),
+    "train_step_seg_unet_seed25": ("seg_unet", 25),
+    "train_step_seg_v2vnet_seed26": ("seg_v2vnet", 26),
+}
+
+
+def train_case(kind, seed):
+    """(state_dict, inputs tuple, output keys) of a training-step case; shared by the generator and the CPU test."""
+    if kind == "v2vnet":
+        return synth.v2vnet_det_state(seed), synth.make_scene(1, 5, seed, present=[4]), ("loc", "cls")
+    if kind == "fafnet":
+        return synth.fafnet_state(seed), (synth.make_bevs(3, seed),), ("loc", "cls")
+    if kind == "when2com":
+        return synth.when2com_det_state(seed), synth.make_scene(1, 5, seed), ("loc", "cls")
+    if kind == "disco":
+        return synth.fusion_det_state("disco", seed), synth.make_scene(1, 5, seed, present=[4]), ("loc", "cls")
+    if kind == "seg_unet":
+        return synth.seg_unet_state(seed), (synth.make_seg_scene(1, 2, seed)[0],), ("logits",)
+    if kind == "seg_v2vnet":
+        return synth.seg_v2vnet_state(seed), synth.make_seg_scene(1, 5, seed, present=[4]), ("logits",)
+    raise ValueError(kind)
+
+
+def make_upstream(shapes, seed):
+    """Seeded d(loss)/d(out) per output key: dense small values, like the gradient of a mean-reduced loss (float64)."""
     g = torch.Generator().manual_seed(4000 + seed)
-    return {k: (torch.rand(out[k].shape, generator=g, dtype=torch.float64) - 0.5) * (2.0 / out[k].numel() ** 0.5)
-            for k in ("loc", "cls")}
+    return {k: (torch.rand(tuple(shapes[k]), generator=g, dtype=torch.float64) - 0.5) * (2.0 / float(np.prod(shapes[k])) ** 0.5)
+            for k in sorted(shapes)}
 
 
 def gen_train_step(tag, kind, seed):
-    """One training step of the LIVE reference module in .train() mode: outputs, gradients of a spread of parameters
-    (strided subsample + L2 norm each) and the BN running buffers after the step.  SURVEY 8(f1) oracle pin."""
-    if kind == "v2vnet":
-        m, sd = ref_loader.ref_v2vnet_det(), synth.v2vnet_det_state(seed)
-        bevs, trans, nat = synth.make_scene(1, 5, seed, present=[4])
-        call = lambda: m(bevs, trans, nat, batch_size=1)                      # noqa: E731
-    else:
-        m, sd = ref_loader.ref_fafnet(kd_flag=0), synth.fafnet_state(seed)
-        bevs = synth.make_bevs(3, seed)
-        call = lambda: m(bevs)                                                 # noqa: E731
+    """One training step of the LIVE reference module in .train() mode, in float64 (ref_loader.float64_shim): outputs,
+    the gradient of EVERY parameter that receives one (strided subsample + L2 norm) and every BatchNorm's running
+    buffers after the step.  SURVEY 8(f1) oracle pin."""
+    import contextlib
+    import io
+    sd, inputs, keys = train_case(kind, seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if kind == "v2vnet":
+            m = ref_loader.ref_v2vnet_det()
+        elif kind == "fafnet":
+            m = ref_loader.ref_fafnet(kd_flag=0)
+        elif kind == "when2com":
+            m = ref_loader.ref_when2com_det(warp_flag=1)
+        elif kind == "disco":
+            m = ref_loader.ref_fusion_det("disco")
+        elif kind == "seg_unet":
+            m = ref_loader.ref_seg_unet()
+        else:
+            m = ref_loader.ref_seg_v2vnet(num_agent=5)
     m.load_state_dict(sd, strict=True)
     m.double().train()
-    bevs = bevs.double()
-    with ref_loader.float64_shim():
-        r = call()
-        up = make_upstream(r, seed)
-        torch.autograd.backward([r["cls"], r["loc"]], [up["cls"], up["loc"]])
-    assert r["loc"].dtype == torch.float64
+    x = inputs[0].double()
+    with ref_loader.float64_shim(), contextlib.redirect_stdout(io.StringIO()):
+        if kind in ("fafnet", "seg_unet"):
+            r = m(x)
+        elif kind == "when2com":
+            r = m(x, inputs[1], inputs[2], training=True, MO_flag=True, batch_size=1)
+        elif kind == "seg_v2vnet":
+            r = m(x, inputs[1], inputs[2])
+        elif kind == "disco":
+            r = m(x, inputs[1], inputs[2], batch_size=1)[0]
+        else:
+            r = m(x, inputs[1], inputs[2], batch_size=1)
+        if not isinstance(r, dict):
+            r = {"logits": r}
+        up = make_upstream({k: r[k].shape for k in keys}, seed)
+        torch.autograd.backward([r[k] for k in sorted(keys)], [up[k] for k in sorted(keys)])
     out = {"meta": np.asarray([seed], dtype=np.int64), "kind": np.asarray(kind)}
-    for name in ("loc", "cls"):     # float64 fixtures (summarize() stores float32)
-        flat = r[name].detach().contiguous().view(-1)
+    for name in keys:
+        assert r[name].dtype == torch.float64
         out[name + ".shape"] = np.asarray(r[name].shape, dtype=np.int64)
-        out[name + ".sub"] = flat[::STRIDE].numpy().copy()
-    params = dict(m.named_parameters())
-    for k in TRAIN_GRAD_KEYS[kind]:
-        g = params[k].grad
-        out["grad." + k + ".sub"] = g.detach().reshape(-1)[::grad_stride(g.numel())].numpy().copy()   # float64
-        out["grad." + k + ".norm"] = np.float64(g.detach().double().norm().item())
-    state = m.state_dict()
-    for k in TRAIN_BN_KEYS[kind]:
-        out["bn." + k + ".running_mean"] = state[k + ".running_mean"].numpy().copy()
-        out["bn." + k + ".running_var"] = state[k + ".running_var"].numpy().copy()
-        out["bn." + k + ".num_batches_tracked"] = np.int64(state[k + ".num_batches_tracked"].item())
+        out[name + ".sub"] = r[name].detach().contiguous().view(-1)[::STRIDE].numpy().copy()
+    n_grads = 0
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        n_grads += 1
+        out["grad." + k + ".sub"] = p.grad.detach().reshape(-1)[::grad_stride(p.grad.numel())].numpy().copy()
+        out["grad." + k + ".norm"] = np.float64(p.grad.detach().norm().item())
+    for k, v in m.state_dict().items():
+        if k.endswith(("running_mean", "running_var")):
+            out["bn." + k] = v.numpy().copy()
     np.savez_compressed(os.path.join(GOLDEN_DIR, tag + ".npz"), **out)
-    print(tag, "|grad first|", out["grad." + TRAIN_GRAD_KEYS[kind][0] + ".norm"])
+    print(tag, "parameters with gradients:", n_grads)
 
 
 def main():
@@ -412,14 +443,14 @@ def main():
         gen_layers()
         return 0
     if "--train-only" in sys.argv:
-        gen_train_step("train_step_v2vnet_seed21", "v2vnet", 21)
-        gen_train_step("train_step_fafnet_seed22", "fafnet", 22)
+        for tag, (kind, seed) in TRAIN_CASES.items():
+            gen_train_step(tag, kind, seed)
         return 0
     gen_fusion_all()
     gen_compress()
     gen_layers()
-    gen_train_step("train_step_v2vnet_seed21", "v2vnet", 21)
-    gen_train_step("train_step_fafnet_seed22", "fafnet", 22)
+    for tag, (kind, seed) in TRAIN_CASES.items():
+        gen_train_step(tag, kind, seed)
     gen_warp("warp_small_seed3", 3)
     gen_convgru("convgru_small_seed4", 4)
     gen_fafnet("fafnet_n2_seed0", 2, 0)

@@ -235,7 +235,7 @@ def when2com_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=
     feat = torch.flip(x_3, (2,))
     local = torch.stack([feat[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)  # [B,A,C,H,W]
     if warp_flag == 1:
-        val_mat = torch.zeros(batch_size, agent_num, agent_num, c, h, w)
+        val_mat = torch.zeros(batch_size, agent_num, agent_num, c, h, w, dtype=local.dtype)
         for b in range(batch_size):
             na = int(num_agent_tensor[b, 0])
             for i in range(na):
@@ -309,6 +309,7 @@ def seg_up(x1, x2, sd, p):
 
 
 def seg_encode(x, sd, p=""):
+    x = x.to(sd[p + "inc.double_conv.0.weight"].dtype)   # fp32 in the reference; float64 for the training-oracle pin
     x1 = double_conv(x, sd, p + "inc.double_conv.")
     x2 = seg_down(x1, sd, p + "down1.")
     x3 = seg_down(x2, sd, p + "down2.")
@@ -385,7 +386,7 @@ def seg_when2com_forward(x, trans_matrices, num_agent_tensor, sd, agent_num=5, w
     feat = torch.flip(x4, (2,))
     local = torch.stack([feat[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)
     if warp_flag == 1:
-        val_mat = torch.zeros(batch_size, agent_num, agent_num, c, h, w)
+        val_mat = torch.zeros(batch_size, agent_num, agent_num, c, h, w, dtype=local.dtype)
         for b in range(batch_size):
             na = int(num_agent_tensor[b, 0])
             for i in range(na):

@@ -223,40 +223,48 @@ def test_other_communication_layers(golden_dir):
     _check("cls", r["cls"], g)
 
 
-@pytest.mark.parametrize("tag,kind", [("train_step_v2vnet_seed21", "v2vnet"), ("train_step_fafnet_seed22", "fafnet")])
-def test_train_step_oracle(golden_dir, tag, kind):
+def _train_cases():
+    from oracle.gen_golden import TRAIN_CASES
+    return [(tag, kind, seed) for tag, (kind, seed) in TRAIN_CASES.items()]
+
+
+@pytest.mark.parametrize("tag,kind,seed", _train_cases(), ids=[c[0] for c in _train_cases()])
+def test_train_step_oracle(golden_dir, tag, kind, seed):
     """SURVEY 8(f1) oracle pin: the restatement in training mode (BatchNorm batch statistics + running-buffer updates)
-    and its autograd vector-Jacobian product vs one training step of the LIVE reference module in .train() mode.
+    and its autograd vector-Jacobian product vs one training step of the LIVE reference module in .train() mode, for
+    det V2VNet / FaFNet / When2com (training=True) / DiscoNet and seg UNet / V2VNet.
     Both sides run in float64 (fixtures made under oracle.ref_loader.float64_shim): in float32 the BatchNorm backward of
     these seeded random nets amplifies summation-order noise to ~1% per gradient element, which would hide a wrong
-    algorithm; in float64 outputs, gradients and running buffers must agree to 1e-8."""
-    from oracle.gen_golden import TRAIN_BN_KEYS, TRAIN_GRAD_KEYS, grad_stride, make_upstream
+    algorithm; in float64 the outputs, the gradient of EVERY parameter that receives one and every BatchNorm running
+    buffer must agree to 1e-6 relative (measured 1e-12 .. 2e-8; the when2com path has one float32 constant)."""
+    from oracle.gen_golden import grad_stride, make_upstream, train_case
     g = np.load(os.path.join(golden_dir, tag + ".npz"))
-    seed = int(g["meta"][0])
-    dbl = lambda d: {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in d.items()}  # noqa: E731
-    if kind == "v2vnet":
-        sd = dbl(synth.v2vnet_det_state(seed))
-        bevs, trans, nat = synth.make_scene(1, 5, seed, present=[4])
-        fwd = lambda w: restate.v2vnet_det_forward(bevs, trans, nat, w, batch_size=1, agent_num=5, gnn_iter=3)  # noqa: E731
-    else:
-        sd = dbl(synth.fafnet_state(seed))
-        bevs = synth.make_bevs(3, seed)
-        fwd = lambda w: restate.fafnet_forward(bevs, w)                                                          # noqa: E731
-    shapes = {"loc": torch.empty(tuple(g["loc.shape"])), "cls": torch.empty(tuple(g["cls.shape"]))}
-    out, grads, after = restate.train_step_vjp(fwd, sd, make_upstream(shapes, seed))
-    for name in ("loc", "cls"):
+    sd, inputs, keys = train_case(kind, seed)
+    sd = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    wrap = lambda t: t if isinstance(t, dict) else {"logits": t}   # noqa: E731
+    fwd = {
+        "v2vnet": lambda w: restate.v2vnet_det_forward(*inputs, w, batch_size=1, agent_num=5, gnn_iter=3),
+        "fafnet": lambda w: restate.fafnet_forward(inputs[0], w),
+        "when2com": lambda w: restate.when2com_det_forward(*inputs, w, batch_size=1, agent_num=5, warp_flag=1, training=True),
+        "disco": lambda w: restate.fusion_det_forward("disco", *inputs, w, batch_size=1, agent_num=5),
+        "seg_unet": lambda w: wrap(restate.seg_unet_forward(inputs[0], w)),
+        "seg_v2vnet": lambda w: wrap(restate.seg_v2vnet_forward(*inputs, w, agent_num=5)),
+    }[kind]
+    out, grads, after = restate.train_step_vjp(fwd, sd, make_upstream({k: g[k + ".shape"] for k in keys}, seed))
+    for name in keys:
         assert out[name].dtype == torch.float64 and list(out[name].shape) == list(g[name + ".shape"])
         sub = out[name].contiguous().view(-1)[::STRIDE].numpy()
-        assert np.abs(sub - g[name + ".sub"]).max() < 1e-8 * np.abs(g[name + ".sub"]).max(), name
-    for k in TRAIN_GRAD_KEYS[kind]:
-        gr = grads[k]
-        ref = g["grad." + k + ".sub"]
+        assert np.abs(sub - g[name + ".sub"]).max() < 1e-6 * np.abs(g[name + ".sub"]).max(), name
+    ref_grads = sorted(k[5:-4] for k in g.files if k.startswith("grad.") and k.endswith(".sub"))
+    assert len(ref_grads) > 70 and set(ref_grads) == set(grads), set(ref_grads) ^ set(grads)
+    for k in ref_grads:
+        gr, ref = grads[k], g["grad." + k + ".sub"]
         sub = gr.reshape(-1)[::grad_stride(gr.numel())].numpy()
         # (a conv bias feeding a train-mode BatchNorm has an exactly-zero gradient: both sides hold 1e-16 round-off)
-        assert np.abs(sub - ref).max() < 1e-8 * np.abs(ref).max() + 1e-13, k
-        assert abs(gr.norm().item() - float(g["grad." + k + ".norm"])) < 1e-9 * float(g["grad." + k + ".norm"]) + 1e-13, k
-    for k in TRAIN_BN_KEYS[kind]:
-        assert np.abs(after[k + ".running_mean"].numpy() - g["bn." + k + ".running_mean"]).max() < 1e-10, k
-        assert np.abs(after[k + ".running_var"].numpy() - g["bn." + k + ".running_var"]).max() < 1e-10, k
-        assert int(after[k + ".num_batches_tracked"]) == int(g["bn." + k + ".num_batches_tracked"]) == 1
+        assert np.abs(sub - ref).max() < 1e-6 * np.abs(ref).max() + 1e-11, k
+        assert abs(gr.norm().item() - float(g["grad." + k + ".norm"])) < 1e-6 * float(g["grad." + k + ".norm"]) + 1e-11, k
+    bn = [k[3:] for k in g.files if k.startswith("bn.")]
+    assert len(bn) >= 20
+    for k in bn:
+        assert np.abs(after[k].numpy() - g["bn." + k]).max() < 1e-8, k
     assert restate._TRAIN is False      # the switch is restored: eval-mode behaviour is untouched
