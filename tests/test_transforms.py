@@ -51,3 +51,32 @@ def test_dgrad_stride2_parity_decomposition(h, w):
     assert (got - ref).abs().max().item() < 1e-12
     parts = T.dgrad_parity_weights_stride2(wt)
     assert sum(v[0].shape[2] * v[0].shape[3] for v in parts.values()) == 9
+
+
+def test_gru_zero_hidden_gate_backward_matches_autograd():
+    a = [_rand((2, 6, 4, 5), s).requires_grad_(True) for s in (10, 11, 12)]
+    b_hn = _rand((6,), 13).requires_grad_(True)
+    h, r, z, n = T.gru_zero_hidden_gates(a[0], a[1], a[2], b_hn[None, :, None, None])
+    # the same value as GRUCell with a zero hidden state (functional.py:95-105): n + z * (0 - n)
+    assert (h - (n + z * (0 - n))).abs().max().item() < 1e-15
+    dh = _rand(tuple(h.shape), 14)
+    ref = torch.autograd.grad(h, a + [b_hn], dh)
+    got = T.gru_zero_hidden_gates_backward(dh, r.detach(), z.detach(), n.detach(), b_hn.detach()[None, :, None, None])
+    for g_, r_ in zip(got, ref):
+        assert (g_ - r_).abs().max().item() < 1e-12
+
+
+def test_bn_train_forward_backward_match_torch():
+    x = _rand((3, 5, 4, 6), 20).requires_grad_(True)
+    gamma, beta = _rand((5,), 21).requires_grad_(True), _rand((5,), 22).requires_grad_(True)
+    rm, rv = torch.zeros(5, dtype=torch.float64), torch.ones(5, dtype=torch.float64)
+    ref = F.batch_norm(x, rm, rv, gamma, beta, True, 0.1, 1e-5)
+    y, mean, invstd, var_unbiased = T.bn_train_forward(x.detach(), gamma.detach(), beta.detach())
+    assert (y - ref).abs().max().item() < 1e-12
+    # running buffers as torch updates them: momentum 0.1, unbiased variance (what restate.training_mode pins)
+    assert (rm - 0.1 * mean).abs().max().item() < 1e-12 and (rv - (0.9 + 0.1 * var_unbiased)).abs().max().item() < 1e-12
+    dy = _rand(tuple(ref.shape), 23)
+    gx, gg, gb = torch.autograd.grad(ref, [x, gamma, beta], dy)
+    dx, dgamma, dbeta = T.bn_train_backward(dy, x.detach(), mean, invstd, gamma.detach())
+    assert (dx - gx).abs().max().item() < 1e-12 and (dgamma - gg).abs().max().item() < 1e-12
+    assert (dbeta - gb).abs().max().item() < 1e-12

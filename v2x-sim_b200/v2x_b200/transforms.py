@@ -1,4 +1,5 @@
-"""Host-side weight transforms that turn three operations of the path into plain stride-1 correlations, i.e. into
+"""Host-side weight transforms (and the element-wise backward formulas of the GRU gates / train-mode BatchNorm) that turn
+three operations of the path into plain stride-1 correlations, i.e. into
 launches the existing sm_100a conv kernels can run (pure index arithmetic on the reference-format OIHW weights; each
 identity is proven against torch on CPU in tests/test_transforms.py).  They are the operand-preparation half of
 
@@ -102,3 +103,51 @@ def dgrad_stride2_apply(dy: torch.Tensor, w: torch.Tensor, in_hw: Tuple[int, int
                 acc = acc + torch.einsum("io,nohw->nihw", wt[:, :, a, b], shifted)
         dx[:, :, qy::2, qx::2] = acc
     return dx
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Element-wise backward formulas the future backward epilogues will evaluate (proven against autograd on CPU)
+# ---------------------------------------------------------------------------------------------------------------------
+def gru_zero_hidden_gates(a_r, a_z, a_n, b_hn):
+    """Forward of the zero-hidden ConvGRU gates as the EPI_GRU epilogue computes them (functional.py:95-105 with h = 0):
+    a_* are the gate pre-activations (W_ih conv + b_ih [+ b_hh for r, z]), b_hn the hidden bias of the n gate,
+    broadcast over pixels.  Returns (h', r, z, n)."""
+    r, z = torch.sigmoid(a_r), torch.sigmoid(a_z)
+    n = torch.tanh(a_n + r * b_hn)
+    return (1.0 - z) * n, r, z, n
+
+
+def gru_zero_hidden_gates_backward(dh, r, z, n, b_hn):
+    """d(loss)/d(a_r, a_z, a_n) and d(loss)/d(b_hn) (summed over everything but the channel dim, which is dim 1) from
+    d(loss)/d(h') and the saved gate values: what the GRU conv's backward epilogue hands to its dgrad / wgrad GEMMs."""
+    dn = dh * (1.0 - z)
+    da_z = -dh * n * z * (1.0 - z)
+    da_n = dn * (1.0 - n * n)
+    da_r = da_n * b_hn * r * (1.0 - r)
+    reduce_dims = [d for d in range(dh.dim()) if d != 1]
+    db_hn = (da_n * r).sum(reduce_dims)
+    return da_r, da_z, da_n, db_hn
+
+
+def bn_train_forward(x, gamma, beta, eps=1e-5):
+    """Training-mode BatchNorm2d over (N, H, W) per channel: returns (y, mean, invstd, unbiased batch variance) -- the
+    statistics a conv epilogue would accumulate as per-channel sum / sum of squares."""
+    dims = [0, 2, 3]
+    mean = x.mean(dims)
+    var = x.var(dims, unbiased=False)
+    invstd = torch.rsqrt(var + eps)
+    y = (x - mean[None, :, None, None]) * (invstd * gamma)[None, :, None, None] + beta[None, :, None, None]
+    m = x.numel() // x.shape[1]
+    return y, mean, invstd, var * (m / max(m - 1, 1))
+
+
+def bn_train_backward(dy, x, mean, invstd, gamma):
+    """(dx, dgamma, dbeta) of training-mode BatchNorm2d from the saved batch statistics:
+    dx = gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat))."""
+    dims = [0, 2, 3]
+    xhat = (x - mean[None, :, None, None]) * invstd[None, :, None, None]
+    dbeta = dy.sum(dims)
+    dgamma = (dy * xhat).sum(dims)
+    m = x.numel() // x.shape[1]
+    dx = (gamma * invstd)[None, :, None, None] * (dy - dbeta[None, :, None, None] / m - xhat * dgamma[None, :, None, None] / m)
+    return dx, dgamma, dbeta
