@@ -480,9 +480,21 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    if args.gpus > 1 and args.impl == "ours" and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` typed directly: relaunch as one rank per GPU (the driver launches torchrun itself)
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        os.dup2(_REAL_STDOUT, 1)
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+                                  str(args.gpus), "--master-addr", "127.0.0.1", "--master-port", str(port),
+                                  os.path.abspath(__file__)] + sys.argv[1:])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and args.impl == "ours":
+        print("bench.py: --gpus %d but WORLD_SIZE=%d; measuring %d rank(s)" % (args.gpus, world, world), file=sys.stderr)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return 0
