@@ -343,6 +343,9 @@ TRAIN_CASES = {   # tag -> (kind, seed)
     "train_step_disco_seed24": ("disco", 24),
     "train_step_seg_unet_seed25": ("seg_unet", 25),
     "train_step_seg_v2vnet_seed26": ("seg_v2vnet", 26),
+    "train_step_cat_seed27": ("cat", 27),
+    "train_step_agent_seed28": ("agent", 28),
+    "train_step_seg_when2com_seed29": ("seg_when2com", 29),
 }
 
 
@@ -354,8 +357,10 @@ def train_case(kind, seed):
         return synth.fafnet_state(seed), (synth.make_bevs(3, seed),), ("loc", "cls")
     if kind == "when2com":
         return synth.when2com_det_state(seed), synth.make_scene(1, 5, seed), ("loc", "cls")
-    if kind == "disco":
-        return synth.fusion_det_state("disco", seed), synth.make_scene(1, 5, seed, present=[4]), ("loc", "cls")
+    if kind in ("disco", "cat", "agent"):
+        return synth.fusion_det_state(kind, seed), synth.make_scene(1, 5, seed, present=[4]), ("loc", "cls")
+    if kind == "seg_when2com":
+        return synth.seg_when2com_state(seed), synth.make_seg_scene(1, 5, seed), ("logits",)
     if kind == "seg_unet":
         return synth.seg_unet_state(seed), (synth.make_seg_scene(1, 2, seed)[0],), ("logits",)
     if kind == "seg_v2vnet":
@@ -384,8 +389,10 @@ def gen_train_step(tag, kind, seed):
             m = ref_loader.ref_fafnet(kd_flag=0)
         elif kind == "when2com":
             m = ref_loader.ref_when2com_det(warp_flag=1)
-        elif kind == "disco":
-            m = ref_loader.ref_fusion_det("disco")
+        elif kind in ("disco", "cat", "agent"):
+            m = ref_loader.ref_fusion_det(kind)
+        elif kind == "seg_when2com":
+            m = ref_loader.ref_seg_when2com(num_agent=5, warp_flag=1)
         elif kind == "seg_unet":
             m = ref_loader.ref_seg_unet()
         else:
@@ -393,15 +400,19 @@ def gen_train_step(tag, kind, seed):
     m.load_state_dict(sd, strict=True)
     m.double().train()
     x = inputs[0].double()
-    with ref_loader.float64_shim(), contextlib.redirect_stdout(io.StringIO()):
+    with ref_loader.float64_shim(), ref_loader.cpu_cuda_shim(), contextlib.redirect_stdout(io.StringIO()):
         if kind in ("fafnet", "seg_unet"):
             r = m(x)
+        elif kind == "seg_when2com":
+            r = m(x, inputs[1], inputs[2], training=True)
         elif kind == "when2com":
             r = m(x, inputs[1], inputs[2], training=True, MO_flag=True, batch_size=1)
         elif kind == "seg_v2vnet":
             r = m(x, inputs[1], inputs[2])
         elif kind == "disco":
             r = m(x, inputs[1], inputs[2], batch_size=1)[0]
+        elif kind in ("cat", "agent"):
+            r = m(x, inputs[1], inputs[2], batch_size=1)
         else:
             r = m(x, inputs[1], inputs[2], batch_size=1)
         if not isinstance(r, dict):
@@ -444,7 +455,8 @@ def main():
         return 0
     if "--train-only" in sys.argv:
         for tag, (kind, seed) in TRAIN_CASES.items():
-            gen_train_step(tag, kind, seed)
+            if not os.path.exists(os.path.join(GOLDEN_DIR, tag + ".npz")) or "--force" in sys.argv:
+                gen_train_step(tag, kind, seed)
         return 0
     gen_fusion_all()
     gen_compress()

@@ -456,7 +456,9 @@ def fuse_rule(kind, tg, nb, sd, seg=False):
         return F.relu(_bn(y, sd, p + "bn1_1")).squeeze(0)
     if kind == "agent":
         w = [_pair_weight_net(torch.cat([tg, f], dim=0).unsqueeze(0), sd, "agent_weighted_fusion.", True) for f in nb]
-        soft = torch.squeeze(F.softmax(torch.tensor([float(t) for t in w]).unsqueeze(0), dim=1), 0)
+        # torch.tensor(list of 0-dim tensors) copies the values OUT of the autograd graph (so the weight net receives no
+        # gradient in the reference, AgentWiseWeightedFusion.py:24-26) and keeps their dtype
+        soft = torch.squeeze(F.softmax(torch.tensor([float(t) for t in w], dtype=tg.dtype).unsqueeze(0), dim=1), 0)
         out = 0
         for k in range(len(nb)):
             out = out + soft[k] * nb[k]

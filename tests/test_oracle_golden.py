@@ -247,6 +247,9 @@ def test_train_step_oracle(golden_dir, tag, kind, seed):
         "fafnet": lambda w: restate.fafnet_forward(inputs[0], w),
         "when2com": lambda w: restate.when2com_det_forward(*inputs, w, batch_size=1, agent_num=5, warp_flag=1, training=True),
         "disco": lambda w: restate.fusion_det_forward("disco", *inputs, w, batch_size=1, agent_num=5),
+        "cat": lambda w: restate.fusion_det_forward("cat", *inputs, w, batch_size=1, agent_num=5),
+        "agent": lambda w: restate.fusion_det_forward("agent", *inputs, w, batch_size=1, agent_num=5),
+        "seg_when2com": lambda w: wrap(restate.seg_when2com_forward(*inputs, w, agent_num=5, warp_flag=1, training=True)),
         "seg_unet": lambda w: wrap(restate.seg_unet_forward(inputs[0], w)),
         "seg_v2vnet": lambda w: wrap(restate.seg_v2vnet_forward(*inputs, w, agent_num=5)),
     }[kind]
