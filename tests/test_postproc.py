@@ -127,3 +127,62 @@ def test_planted_pipeline_on_oracle_outputs():
     ap5, _ = pp.eval_map(dets, gts, 0.5)
     ap7, _ = pp.eval_map(dets, gts, 0.7)
     assert 0.3 < ap7 <= ap5 <= 1.0
+
+
+def _clip_iou_port(qa, qb):
+    """Line-by-line python port of quad_iou_f64 (csrc/postproc_kernels.cu): Sutherland-Hodgman clip of A by the four
+    half-planes of B (B made counter-clockwise), shoelace areas.  Kept in step with the CUDA source so that the
+    ALGORITHM the GPU NMS runs is checked on CPU against the oracle's independent construction (vertices-inside +
+    edge crossings + angular sort)."""
+    a = [[float(qa[i][0]), float(qa[i][1])] for i in range(4)]
+    b = [[float(qb[i][0]), float(qb[i][1])] for i in range(4)]
+
+    def signed_area2(p):
+        n = len(p)
+        return sum(p[i][0] * p[(i + 1) % n][1] - p[(i + 1) % n][0] * p[i][1] for i in range(n))
+
+    sb = signed_area2(b)
+    area_a, area_b = 0.5 * abs(signed_area2(a)), 0.5 * abs(sb)
+    if sb < 0.0:
+        b[1], b[3] = b[3], b[1]
+    n = 4
+    for e in range(4):
+        if n == 0:
+            break
+        ex0, ey0 = b[e]
+        dx, dy = b[(e + 1) & 3][0] - ex0, b[(e + 1) & 3][1] - ey0
+        tmp = []
+        for i in range(n):
+            j = 0 if i + 1 == n else i + 1
+            ci = dx * (a[i][1] - ey0) - dy * (a[i][0] - ex0)
+            cj = dx * (a[j][1] - ey0) - dy * (a[j][0] - ex0)
+            if ci >= 0.0 and len(tmp) < 8:
+                tmp.append([a[i][0], a[i][1]])
+            if (ci >= 0.0) != (cj >= 0.0) and len(tmp) < 8:
+                t = ci / (ci - cj)
+                tmp.append([a[i][0] + t * (a[j][0] - a[i][0]), a[i][1] + t * (a[j][1] - a[i][1])])
+        a, n = tmp, len(tmp)
+    if n < 3:
+        return 0.0
+    inter = 0.5 * abs(signed_area2(a))
+    uni = area_a + area_b - inter
+    return inter / uni if uni > 0.0 else 0.0
+
+
+def test_gpu_iou_algorithm_port_matches_oracle_on_random_quads():
+    rng = np.random.RandomState(7)
+    worst = 0.0
+    for k in range(1500):
+        a = sq(rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(0.5, 4), rng.uniform(0, math.pi))
+        b = sq(rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(0.5, 4), rng.uniform(0, math.pi))
+        a[:, 0] *= rng.uniform(0.5, 2.0)            # rectangles, not only squares
+        if k % 3 == 0:
+            b = b[::-1].copy()                       # clockwise vertex order
+        if k % 50 == 0:
+            b = a.copy()                             # identical boxes
+        if k % 70 == 0:
+            b = a + np.array([a[1, 0] - a[0, 0], a[1, 1] - a[0, 1]])   # sharing one edge exactly
+        ref = float(pp.quad_iou(a, b[None])[0])
+        got = _clip_iou_port(a.astype(np.float32), b.astype(np.float32))
+        worst = max(worst, abs(got - ref))
+    assert worst < 5e-6, worst          # float32 corners on the port's side (as the kernel receives them)
