@@ -80,3 +80,35 @@ def test_bn_train_forward_backward_match_torch():
     dx, dgamma, dbeta = T.bn_train_backward(dy, x.detach(), mean, invstd, gamma.detach())
     assert (dx - gx).abs().max().item() < 1e-12 and (dgamma - gg).abs().max().item() < 1e-12
     assert (dbeta - gb).abs().max().item() < 1e-12
+
+
+@pytest.mark.parametrize("co,ci,h,w", [(32, 5, 8, 14), (64, 3, 16, 20), (32, 2, 8, 5)])
+def test_tap_packed_conv_emulation(co, ci, h, w):
+    """The arithmetic of csrc/conv_pack3.cu emulated with torch: per halo position q (pitch 16, origin one pixel up-left
+    of the 8 x 14 output tile) Y[q, (g, kw, co)] = sum_{kh, ci} halo[q + 16 kh, ci] * rows[(g, kw, co), ci, kh], then
+    out[p] = Y[p, kw=0] + Y[p + 1, kw=1] + Y[p + 2, kw=2] -- equals conv3x3(pad 1), including partial right-edge tiles."""
+    x, wt = _rand((1, ci, h, w), 30), _rand((co, ci, 3, 3), 31)
+    ref = F.conv2d(x, wt, padding=1)
+    rows = T.tap_packed_rows(wt)                                  # [co/32*96, ci, 3]
+    g = co // 32
+    out = torch.zeros_like(ref)
+    for oh0 in range(0, h, 8):
+        for ow0 in range(0, w, 14):
+            halo = torch.zeros((ci, 10, 16), dtype=torch.float64)   # TMA box: rows oh0-1 .. oh0+8, cols ow0-1 .. ow0+14
+            for r in range(10):
+                for c in range(16):
+                    yy, xx = oh0 - 1 + r, ow0 - 1 + c
+                    if 0 <= yy < h and 0 <= xx < w:
+                        halo[:, r, c] = x[0, :, yy, xx]
+            flat = halo.reshape(ci, 160)
+            # 128 "TMEM lanes": lane q reads halo position q + 16 kh for filter row kh
+            y = torch.zeros((128, g * 96), dtype=torch.float64)
+            for kh in range(3):
+                a = flat[:, 16 * kh:16 * kh + 128].t()             # [128 lanes, ci]
+                y += a @ rows[:, :, kh].t()                         # [128, g*96]
+            y = y.view(128, g, 3, 32)
+            for q in range(128):
+                r, c = q >> 4, q & 15
+                if c < 14 and oh0 + r < h and ow0 + c < w:
+                    out[0, :, oh0 + r, ow0 + c] = (y[q, :, 0] + y[q + 1, :, 1] + y[q + 2, :, 2]).reshape(co)
+    assert (out - ref).abs().max().item() < 1e-12

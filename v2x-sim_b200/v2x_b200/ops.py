@@ -124,8 +124,8 @@ def pack_conv_tap_packed(weight, bias, bn, *, cins: Sequence[int], planes=1, dev
     assert cout % 32 == 0 and tuple(weight.shape[2:]) == (3, 3) and sum(cins) == cin_total
     g = cout // 32
     cin_pads = [((c + 15) // 16) * 16 for c in cins]
-    # [cout, ci, kh, kw] -> [g, kw, 32, ci, kh] -> rows (g, kw, co)
-    w = _f32(weight, device).view(g, 32, cin_total, 3, 3).permute(0, 4, 1, 2, 3).reshape(3 * cout, cin_total, 3).contiguous()
+    from .transforms import tap_packed_rows
+    w = tap_packed_rows(_f32(weight, device))   # [cout, ci, kh, kw] -> rows (g, kw, co) x [ci, kh]; proven in tests/test_transforms.py
     rep = lambda t: None if t is None else _f32(t, device).view(g, 1, 32).expand(g, 3, 32).reshape(-1).contiguous()  # noqa: E731
     b = rep(bias)
     bnp = [rep(t) for t in bn] if bn is not None else [None] * 4

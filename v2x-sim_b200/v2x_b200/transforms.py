@@ -57,6 +57,16 @@ def upsample_conv_parity_apply(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor
     return y
 
 
+def tap_packed_rows(w: torch.Tensor) -> torch.Tensor:
+    """OIHW 3x3 weights with 32 | O -> the row arrangement of the tap-packed conv kernel (csrc/conv_pack3.cu):
+    [O/32 * 96, I, 3] with row = (group, kw, co) and the last dim = kh.  With Y[q, (g, kw, co)] = sum_{kh, ci}
+    x[q + kh * PITCH, ci] * rows[(g, kw, co), ci, kh] the conv output is out[p, 32 g + co] = sum_kw Y[p + kw, (g, kw, co)]
+    (p, q linear positions in a halo whose origin is one pixel up-left of the output tile)."""
+    o, i = w.shape[0], w.shape[1]
+    assert w.dim() == 4 and tuple(w.shape[2:]) == (3, 3) and o % 32 == 0
+    return w.view(o // 32, 32, i, 3, 3).permute(0, 4, 1, 2, 3).reshape(3 * o, i, 3).contiguous()
+
+
 def dgrad_weights_stride1(w: torch.Tensor) -> torch.Tensor:
     """OIHW weights of ``y = conv2d(x, w, padding=k//2)`` (stride 1, odd k) -> weights ``wt`` [I, O, k, k] with
     ``dL/dx = conv2d(dL/dy, wt, padding=k//2)``: input / output channels swapped, filter rotated by 180 degrees."""
