@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- frames/sec of the 5-agent V2VNet detection forward on B200 (BASELINE.json metric).
+"""bench.py -- frames/sec of the collaborative-perception forward on B200 (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            our sm_100a path (one rank per GPU)
-  python bench.py --impl reference ...                      the reference CPU path (oracle port) on host cores
+  python bench.py --impl reference ...                      the UNMODIFIED reference modules on the host's cores
+  python bench.py --config {v2v_det,faf_lower,w2c_seg,faf_upper_dp}   the BASELINE.json configs (default v2v_det)
 
-A *frame* is one scene: all 5 agents' 256x256x13 BEVs -> all agents' loc/cls (BASELINE.json,
-SURVEY.md section 8(d)).  A *step* is one forward over ``--scenes`` scenes per GPU (default 8, so the
-step's inputs, 8 x 17 MB fp32, exceed the 126 MB L2 and nothing survives between timed steps).
+Default (= the metric, BASELINE configs[1]; configs[3] under torchrun): 5-agent V2VNet detection.  A *frame* is one
+scene: all 5 agents' 256x256x13 BEVs -> all agents' loc/cls.  A *step* is one forward over
+``--scenes`` scenes per GPU (default 8, so the step's inputs, 8 x 17 MB fp32, exceed the 126 MB L2 and nothing survives
+between timed steps).
 
   value  frames/s with inputs resident in HBM, CUDA-graph replay, CUDA events on the launch stream
-  e2e    frames/s through the drop-in ``coperception.models.det.V2VNet.forward`` with pinned HOST
-         inputs: H2D of bevs/trans/num_agent and D2H of loc+cls (fp32, as the reference's predict_all
-         moves them, CoDetModule.py:484-511 -> detection_util.py:256) inside the timed region
-  roofline   the conv implicit-GEMM kernel family: algorithmic conv FLOPs / summed live per-launch time
-  cpu_baseline  the oracle port (the reference's CPU algorithm) on this host, bounded sample
+  e2e    frames/s through the drop-in ``coperception.models.*`` module call with pinned HOST inputs: H2D of the
+         inputs and D2H of the full fp32 result inside the timed region (what the reference's predict_all moves,
+         CoDetModule.py:484-511 -> detection_util.py:256)
+  roofline   the conv implicit-GEMM kernel family: algorithmic conv FLOPs / live conv launch time, against the
+             measured bf16 tensor peaks (burst AND sustained fractions; algorithmic AND executed FLOPs)
+  cpu_baseline  the live reference module (oracle/_ref, staged by oracle/make_ref.py) on this host, bounded sample;
+                the oracle port is timed beside it and both s/frame are printed
+
+Precision (v2x_b200/precision.py): ``--precision mixed`` (default) is the mode every drop-in module defaults to and the
+mode tests/test_gpu_nets.py holds to the north-star 1e-3; ``fp16x3`` and ``bf16`` are the exact-er / faster ends.
 
 Multi-GPU (N > 1), weak scaling, 8 scenes x 5 agents = 40 units per GPU, timing = max over ranks of the device
 time between barriers:
@@ -21,6 +28,7 @@ time between barriers:
                 on different GPUs; the only data-path collective is one NCCL all-gather of the layer-3 maps per
                 step, overlapped with the x_4 encoder branch (BASELINE configs[3])
   --shard scene            every rank keeps whole scenes; no data-path collective at all
+The other configs are replicas only (no exchange step in their forward): every rank runs its own batch.
 """
 from __future__ import annotations
 
@@ -41,9 +49,26 @@ import torch  # noqa: E402
 
 AGENTS = 5
 GNN_ITER = 3
-# algorithmic conv/linear FLOPs per frame (A=5), SURVEY.md section 8(d) / BASELINE.md section 2
-GFLOP_PER_FRAME = 264.51
-METRIC = "frames/sec 5-agent V2VNet fwd"
+# arithmetic type of the path per precision mode (a name, not a precision claim: parity is tests/test_gpu_nets.py)
+DTYPE_OF = {"mixed": "fp16 hi/lo operands, 1-3 tensor-core passes per layer, fp32 accumulate (1e-3 parity mode)",
+            "fp16x3": "fp16 hi/lo operands, 3 tensor-core passes, fp32 accumulate", "bf16": "bf16"}
+
+# BASELINE.json configs.  gflop = algorithmic conv/linear FLOPs per unit; executed FLOPs differ
+# (see the roofline note).  ``maps_per_unit`` = BEV maps one unit holds; ``units`` = default units per GPU per step.
+CONFIGS = {
+    "v2v_det": dict(metric="frames/sec 5-agent V2VNet fwd", unit="frames/s", gflop=264.51, maps_per_unit=5, units=8,
+                    workload="V2VNet 5-agent detection fwd, 256x256x13 BEV, gnn_iter=3, layer=3 (BASELINE configs[1])"),
+    "faf_lower": dict(metric="agent-frames/sec FaFNet lowerbound (no fusion) fwd", unit="agent-frames/s", gflop=31.16,
+                      maps_per_unit=1, units=40,
+                      workload="FaFNet / STPN single-agent detection fwd, 256x256x13 BEV (BASELINE configs[0])"),
+    "w2c_seg": dict(metric="frames/sec 5-agent When2Com_UNet seg fwd", unit="frames/s", gflop=581.38, maps_per_unit=5,
+                    units=4, workload="when2com 5-agent BEV segmentation fwd (warp_flag=1, inference=activated), "
+                                      "256x256x13 BEV -> 8-class logits (BASELINE configs[2])"),
+    "faf_upper_dp": dict(metric="frames/sec 6-agent FaFNet upperbound fwd", unit="frames/s", gflop=186.96,
+                         maps_per_unit=6, units=4,
+                         workload="FaFNet upperbound early-fusion detection fwd, 6 agents (RSU+5) per scene, batch 32 "
+                                  "scenes over 8 GPUs = 4 scenes x 6 maps per GPU, data parallel (BASELINE configs[4])"),
+}
 
 
 def measured_peaks():
@@ -51,23 +76,26 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
-        return {"tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1450.0))),
+        return {"tflops_sustained": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1450.0))),
                 "tflops_burst": float(d.get("bf16_tflops", 0.0)), "hbm_gbs": float(d.get("hbm_gbs", 0.0)),
-                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
-    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
             "source": "fallback (B200_PROFILING.md: 1.59 PF burst / ~1.4 PF sustained)"}
 
 
-def conv_traffic(scenes):
+def conv_traffic(config, precision, units):
     """dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of one step, from the committed
-    ncu --set full capture (profiles/conv_traffic.json); None when the capture was taken at another batch size."""
-    path = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    ncu --set full capture (profiles/conv_traffic.json); None when no capture matches this config / mode / batch."""
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
             d = json.load(f)
-        return float(d["conv_dram_bytes_per_step"]) if int(d["scenes_per_step"]) == scenes else None
+        for rec in d.get("captures", [d]):
+            if (rec.get("config", "v2v_det") == config and rec.get("precision", "bf16") == precision
+                    and int(rec["scenes_per_step"]) == units):
+                return float(rec["conv_dram_bytes_per_step"])
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler:
@@ -131,58 +159,149 @@ def _anchor_table():
     return a.reshape(-1, 6).astype(np.float32)
 
 
-def cpu_reference(steps, warmup, scenes=1):
-    """The reference's CPU algorithm (oracle port, literal restatement incl. the W_hh conv over the zero
-    hidden state and per-round warps) on this host's cores.  torch's CPU backend gets slower, not faster,
-    when handed every core of a big host for these small convolutions, so the thread count is chosen
-    from {8, 16, 32, 64, all} by one probe forward each and the best one is used and reported.
-    Returns (frames/s, seconds per frame, threads)."""
-    from oracle import restate, synth
-    sd = synth.v2vnet_det_state(0)
-    bevs, trans, nat = synth.make_scene(scenes, AGENTS, seed=0)
+# =====================================================================================================================
+# reference arm: the reference's own CPU implementation of the path on the host's cores
+# =====================================================================================================================
+def _cpu_forwards(config):
+    """{"reference": fn or None, "port": fn} -- one forward of ONE unit of ``config`` on the CPU.
+    reference = the UNMODIFIED reference nn.Module (from /root/reference in the build container, from the copy staged
+    under oracle/_ref by oracle/make_ref.py on the GPU box); port = the restatement in oracle/restate.py."""
+    import contextlib
+    import io
+    from oracle import ref_loader, restate, synth
+    fns = {"reference": None}
+    quiet = lambda: contextlib.redirect_stdout(io.StringIO())  # noqa: E731  (the reference prints from its constructors)
+    if config == "v2v_det":
+        sd = synth.v2vnet_det_state(0)
+        bevs, trans, nat = synth.make_scene(1, AGENTS, seed=0)
+        fns["port"] = lambda: restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=AGENTS,
+                                                         gnn_iter=GNN_ITER)
+        if ref_loader.available():
+            with quiet():
+                m = ref_loader.ref_v2vnet_det(GNN_ITER, 3, 256, num_agent=AGENTS)
+            m.load_state_dict(sd, strict=True)
+            m.eval()
+            fns["reference"] = lambda: m(bevs, trans, nat, batch_size=1)
+    elif config in ("faf_lower", "faf_upper_dp"):
+        n = CONFIGS[config]["maps_per_unit"]
+        sd = synth.fafnet_state(0)
+        bevs = synth.make_bevs(n, 0)
+        fns["port"] = lambda: restate.fafnet_forward(bevs, sd)
+        if ref_loader.available():
+            with quiet():
+                m = ref_loader.ref_fafnet(num_agent=n, kd_flag=0)
+            m.load_state_dict(sd, strict=True)
+            m.eval()
+            fns["reference"] = lambda: m(bevs)
+    elif config == "w2c_seg":
+        sd = synth.seg_when2com_state(0)
+        x, trans, nat = synth.make_seg_scene(1, AGENTS, 0)
+        fns["port"] = lambda: restate.seg_when2com_forward(x, trans, nat, sd, agent_num=AGENTS, warp_flag=1,
+                                                           inference="activated")
+        if ref_loader.available():
+            with quiet():
+                m = ref_loader.ref_seg_when2com(num_agent=AGENTS, warp_flag=1)
+            m.load_state_dict(sd, strict=True)
+            m.eval()
 
-    def fwd():
+            def ref_fwd():
+                with ref_loader.cpu_cuda_shim(), quiet():   # When2Com_UNet.py:225,245 hard-code .cuda()
+                    return m(x, trans, nat, inference="activated", training=False)
+            fns["reference"] = ref_fwd
+    else:
+        raise ValueError(config)
+    return fns
+
+
+def cpu_reference(config, steps, warmup):
+    """Times the reference's CPU implementation of one unit of ``config`` on this host's cores.  torch's CPU backend
+    gets slower, not faster, when handed every core of a big host for these small convolutions, so the thread count is
+    chosen from {8, 16, 32, 64, all} by one probe forward each and the best one is used and reported.
+    Returns dict(kind, units_per_s, s_per_unit, threads, port_s_per_unit, ref_s_per_unit)."""
+    fns = _cpu_forwards(config)
+    kind = "reference" if fns["reference"] is not None else "port"
+    main = fns[kind]
+
+    def timed(fn):
         t0 = time.perf_counter()
         with torch.no_grad():
-            restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=scenes, agent_num=AGENTS, gnn_iter=GNN_ITER)
+            fn()
         return time.perf_counter() - t0
 
     ncpu = os.cpu_count() or 1
     best_t, best_n = None, None
     for n in sorted({min(c, ncpu) for c in (8, 16, 32, 64, ncpu)}):
         torch.set_num_threads(n)
-        fwd()
-        dt = fwd()
+        timed(main)
+        dt = timed(main)
         if best_t is None or dt < best_t:
             best_t, best_n = dt, n
         if dt > 20.0:
             break
     torch.set_num_threads(best_n)
-    times = [fwd() for _ in range(warmup + steps)][warmup:]
-    times.sort()
+    times = sorted([timed(main) for _ in range(warmup + steps)][warmup:])
     med = times[len(times) // 2]
-    return scenes / med, med / scenes, best_n
+    other = None
+    if kind == "reference":      # the oracle port beside it, same threads (2 forwards after a warm-up, best)
+        timed(fns["port"])
+        other = min(timed(fns["port"]) for _ in range(2))
+    return dict(kind=kind, units_per_s=1.0 / med, s_per_unit=med, threads=best_n,
+                ref_s_per_unit=med if kind == "reference" else None, port_s_per_unit=other if kind == "reference" else med)
+
+
+def _cpu_sample_text(r, steps, unit_name):
+    txt = "%d timed forwards of 1 %s, median %.3f s; torch CPU fp32, best of {8,16,32,64,all} threads = %d" % (
+        steps, unit_name, r["s_per_unit"], r["threads"])
+    if r["kind"] == "reference":
+        txt += "; live reference module %.3f s vs oracle port %.3f s per %s" % (r["ref_s_per_unit"], r["port_s_per_unit"],
+                                                                                 unit_name)
+    else:
+        txt += "; reference tree not found (neither /root/reference nor oracle/_ref): timed the oracle port"
+    return txt
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
-    fps, spf, threads = cpu_reference(steps, warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": spf * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "V2VNet 5-agent detection fwd, 256x256x13 BEV, 1 scene/step, reference CPU path"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": "%d timed forwards of 1 scene (5 agents), median; torch CPU fp32, best of "
-                                       "{8,16,32,64,all} threads = %d" % (steps, threads)},
-            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    r = cpu_reference(args.config, steps, warmup)
+    unit_name = "scene (%d agents)" % cfg["maps_per_unit"] if cfg["maps_per_unit"] > 1 else "agent map"
+    line = {"impl": "reference", "metric": cfg["metric"], "value": r["units_per_s"], "unit": cfg["unit"],
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["s_per_unit"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"] + "; reference CPU path, 1 %s per step (the reference loops over "
+                                                     "scenes and agents in python, V2VNet.py:66-107, so its "
+                                                     "frames/s does not depend on the batch)" % unit_name},
+            "cpu_baseline": {"value": r["units_per_s"], "unit": cfg["unit"], "cores": r["threads"], "kind": r["kind"],
+                             "sample": _cpu_sample_text(r, steps, unit_name),
+                             "reference_s_per_unit": r["ref_s_per_unit"], "port_s_per_unit": r["port_s_per_unit"]},
+            "e2e": {"value": r["units_per_s"], "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
+def cpu_baseline_subprocess(args):
+    """The cpu_baseline leg of our arm: `bench.py --impl reference` in a child process (the reference's `coperception`
+    package must not shadow the drop-in one that this process has imported)."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
+                              "--steps", "3", "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                             timeout=600, text=True).stdout
+        d = json.loads(out.strip().splitlines()[-1])
+        return d["cpu_baseline"]
+    except Exception as e:   # noqa: BLE001
+        return {"value": None, "unit": CONFIGS[args.config]["unit"], "cores": None, "kind": "unavailable",
+                "sample": "cpu baseline child failed: %r" % (e,)}
+
+
+# =====================================================================================================================
+# our arm
+# =====================================================================================================================
 def time_launch_list(launches, reps=20):
     """Device time (ms) of one pass over `launches`: the list is captured into a CUDA graph (like the timed step, so
     no host launch gaps leak in) and replayed `reps` times between CUDA events on the replay stream."""
+    if not launches:
+        return 0.0
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -205,16 +324,131 @@ def time_launch_list(launches, reps=20):
     return e0.elapsed_time(e1) / reps
 
 
-def run_ours(args, rank, world, local_rank):
+class Timer:
+    """K steps between barriers + synchronize, CUDA events on the launch stream, MAX over ranks."""
+
+    def __init__(self, dev, world):
+        self.dev, self.world = dev, world
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def run(self, fn, steps):
+        torch.cuda.synchronize()
+        self.barrier()
+        torch.cuda.synchronize()
+        self.e0.record()
+        fn(steps)
+        self.e1.record()
+        torch.cuda.synchronize()
+        self.barrier()
+        t = torch.tensor([self.e0.elapsed_time(self.e1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+class HostPipeline:
+    """The e2e loop: every step's inputs come from pinned host memory and its outputs land in pinned host memory;
+    H2D of step i+1 and D2H of step i-1 overlap the forward of step i (three streams, two buffers)."""
+    NBUF = 2
+
+    def __init__(self, dev, host_inputs, call, out_shapes, out_dtype=torch.float32):
+        self.dev, self.call = dev, call
+        n = self.NBUF
+        self.h_in = [[t.clone().pin_memory() for t in host_inputs] for _ in range(n)]
+        self.d_in = [[torch.empty_like(t, device=dev) for t in host_inputs] for _ in range(n)]
+        self.h_out = [[torch.empty(s, dtype=out_dtype).pin_memory() for s in out_shapes] for _ in range(n)]
+        self.d_out = [[torch.empty(s, dtype=out_dtype, device=dev) for s in out_shapes] for _ in range(n)]
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.in_ready = [torch.cuda.Event() for _ in range(n)]
+        self.in_free = [torch.cuda.Event() for _ in range(n)]
+        self.out_ready = [torch.cuda.Event() for _ in range(n)]
+        self.out_free = [torch.cuda.Event() for _ in range(n)]
+        self.h2d = sum(t.numel() * t.element_size() for t in host_inputs)
+        self.d2h = sum(t.numel() * t.element_size() for t in self.h_out[0])
+
+    def steps(self, k):
+        main = torch.cuda.current_stream()
+        for i in range(k):
+            b = i % self.NBUF
+            with torch.cuda.stream(self.s_in):
+                self.s_in.wait_event(self.in_free[b])
+                for d, h in zip(self.d_in[b], self.h_in[b]):
+                    d.copy_(h, non_blocking=True)
+                self.in_ready[b].record(self.s_in)
+            main.wait_event(self.in_ready[b])
+            with torch.no_grad():
+                outs = self.call(*self.d_in[b])
+            self.in_free[b].record(main)
+            main.wait_event(self.out_free[b])
+            for d, o in zip(self.d_out[b], outs):     # the module aliases its static buffers (alias_outputs): snapshot
+                d.copy_(o.reshape(d.shape), non_blocking=True)
+            self.out_ready[b].record(main)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.out_ready[b])
+                for h, d in zip(self.h_out[b], self.d_out[b]):
+                    h.copy_(d, non_blocking=True)
+                self.out_free[b].record(self.s_out)
+        main.wait_stream(self.s_out)
+        main.wait_stream(self.s_in)
+
+
+def roofline_of(plan, cfg, args, units, step_ms):
+    """Roofline of the conv kernel family of ``plan``: the conv launches of one step replayed back to back on ONE stream,
+    timed live with CUDA events (the step itself may overlap a side branch with the warp kernel, so "step minus the
+    other kernels" would credit hidden time to the convs)."""
+    peaks = measured_peaks()
+    conv_launches = [l for l in plan.launches if getattr(l, "flops", 0.0) > 0]
+    other_launches = [l for l in plan.launches if getattr(l, "flops", 0.0) == 0]
+    other_ms = time_launch_list(other_launches)
+    conv_ms = time_launch_list(conv_launches)
+    alg = cfg["gflop"] * 1e9 * units
+    executed = sum(l.flops for l in conv_launches)                        # MACs the launches really do (one pass)
+    pipe = sum(l.flops * max(1, getattr(l, "mma_passes", 1)) for l in conv_launches)   # x tensor-core passes per k-step
+    achieved = alg / (conv_ms * 1e-3) / 1e12
+    burst = peaks["tflops_burst"] or peaks["tflops_sustained"]
+    return {"bound": "tensor",
+            "kernel": "v2x::conv_tc_kernel<BN,PLANES,MMAS,KSTEPS,HALO> + conv_pack3_kernel (the %d conv launches of a step)"
+                      % len(conv_launches),
+            "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+            "peak_source": peaks["source"] + ": bf16_tflops (burst) -- the timed region is ~%.0f ms of back-to-back conv "
+                           "launches at full clocks, the burst regime; frac_sustained uses bf16_tflops_sustained" % (20 * conv_ms),
+            "frac_sustained": achieved / peaks["tflops_sustained"],
+            "executed_tflops": executed / (conv_ms * 1e-3) / 1e12, "frac_executed": executed / (conv_ms * 1e-3) / 1e12 / burst,
+            "tensor_pipe_tflops": pipe / (conv_ms * 1e-3) / 1e12, "frac_tensor_pipe": pipe / (conv_ms * 1e-3) / 1e12 / burst,
+            "traffic": conv_traffic(args.config, args.precision, units),
+            "traffic_unit": "bytes of DRAM read+write per step over the conv launches (ncu --set full, profiles/conv_traffic.json)",
+            "conv_ms_per_step": conv_ms, "other_kernels_ms_per_step": other_ms, "conv_share_of_step": conv_ms / step_ms,
+            "launches_per_step": {"conv": len(conv_launches), "other": len(other_launches)},
+            "algorithmic_gflop_per_unit": cfg["gflop"], "executed_gflop_per_unit": executed / units / 1e9,
+            "note": "achieved/frac: ALGORITHMIC FLOPs (SURVEY 8(d)) / serial conv kernel time.  executed_*: the multiply-"
+                    "accumulates the launches really perform -- fewer than algorithmic where work is hoisted (V2VNet: the "
+                    "round-invariant mean half of the ConvGRU input is convolved once, 228.3 instead of 264.5 GFLOP/frame), "
+                    "slightly more where operands are padded (13->16 input channels, block-diagonal head 1x1, tap-pack edge "
+                    "columns).  tensor_pipe_*: executed FLOPs x tensor-core passes per k-step (fp16 hi/lo modes issue 1-3 "
+                    "MMAs per k-step) = what the tensor pipe actually sustains.  conv + other can exceed the step because "
+                    "the x_4 branch overlaps the warp kernel"}
+
+
+def _clocks(sampler, rank):
+    return sampler.stop() if rank == 0 else None
+
+
+def run_v2v_det(args, rank, world, local_rank):
     from v2x_b200 import default_det_config, nets
     from v2x_b200 import synthetic as synth   # seeded synthetic weights / inputs (nothing under oracle/ on this arm)
     from coperception.models.det import V2VNet
-    import torch.distributed as dist
 
+    cfg = CONFIGS["v2v_det"]
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    planes = {"bf16": 1, "bf16x3": 2}[args.precision]
-    B = args.scenes
+    planes = args.precision      # plans take a precision mode name wherever they take ``planes``
+    B = args.scenes or cfg["units"]
     sd = synth.v2vnet_det_state(0)
     bevs, trans, nat = synth.make_scene(B, AGENTS, seed=rank)
     # Planted head biases (synthetic-data helper): with plain random weights about half of all anchors pass
@@ -226,10 +460,7 @@ def run_ours(args, rank, world, local_rank):
     sd = synth.plant_detections(sd, cls0, per_agent=150)
     del probe, cls0
     torch.cuda.empty_cache()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    timer = Timer(dev, world)
 
     # ---------------- value: device-resident inputs, graph replay ----------------
     unit_sharded = world > 1 and args.shard == "unit"
@@ -246,27 +477,17 @@ def run_ours(args, rank, world, local_rank):
         plan.set_inputs(bevs.to(dev), trans.to(dev), nat.to(dev))
     torch.cuda.synchronize()
     plan.capture()
-    for _ in range(args.warmup):
-        plan.run()
-    torch.cuda.synchronize()
+
+    def replay(k):
+        for _ in range(k):
+            plan.run()
+
+    replay(args.warmup)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        plan.run()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = timer.run(replay, args.steps)
+    clocks = _clocks(sampler, rank)
     frames = B * world * args.steps
     value = frames / (ms_total * 1e-3)
 
@@ -274,75 +495,31 @@ def run_ours(args, rank, world, local_rank):
     model = V2VNet(default_det_config(), GNN_ITER, 3, 256, num_agent=AGENTS)
     model.load_state_dict(sd, strict=True)
     model.precision = args.precision
+    model.alias_outputs = True    # the pipeline snapshots each step's outputs itself
     model = model.to(dev).eval()
-    NBUF = 2
-    h_bev = [bevs.clone().pin_memory() for _ in range(NBUF)]
-    h_trans = [trans.clone().pin_memory() for _ in range(NBUF)]
-    h_nat = [nat.clone().pin_memory() for _ in range(NBUF)]
-    d_bev = [torch.empty_like(bevs, device=dev) for _ in range(NBUF)]
-    d_trans = [torch.empty_like(trans, device=dev) for _ in range(NBUF)]
-    d_nat = [torch.empty_like(nat, device=dev) for _ in range(NBUF)]
     n_maps = B * AGENTS
-    h_loc = [torch.empty((n_maps, 256, 256, 6, 1, 6), dtype=torch.float32).pin_memory() for _ in range(NBUF)]
-    h_cls = [torch.empty((n_maps, 256 * 256 * 6, 2), dtype=torch.float32).pin_memory() for _ in range(NBUF)]
-    d_loc = [torch.empty((n_maps, 256, 256, 6, 1, 6), dtype=torch.float32, device=dev) for _ in range(NBUF)]
-    d_cls = [torch.empty((n_maps, 256 * 256 * 6, 2), dtype=torch.float32, device=dev) for _ in range(NBUF)]
-    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    main = torch.cuda.current_stream()
-    in_ready = [torch.cuda.Event() for _ in range(NBUF)]
-    in_free = [torch.cuda.Event() for _ in range(NBUF)]
-    out_ready = [torch.cuda.Event() for _ in range(NBUF)]
-    out_free = [torch.cuda.Event() for _ in range(NBUF)]
 
-    def e2e_steps(k):
-        """Software-pipelined: H2D of step i+1 and D2H of step i-1 overlap the forward of step i
-        (three streams); every step's inputs come from host memory and its outputs land in host memory."""
-        for i in range(k):
-            b = i % NBUF
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(in_free[b])
-                d_bev[b].copy_(h_bev[b], non_blocking=True)
-                d_trans[b].copy_(h_trans[b], non_blocking=True)
-                d_nat[b].copy_(h_nat[b], non_blocking=True)
-                in_ready[b].record(s_in)
-            main.wait_event(in_ready[b])
-            with torch.no_grad():
-                out = model(d_bev[b], d_trans[b], d_nat[b], batch_size=B)
-            in_free[b].record(main)
-            main.wait_event(out_free[b])
-            d_loc[b].copy_(out["loc"], non_blocking=True)  # plan outputs are reused next step: snapshot them
-            d_cls[b].copy_(out["cls"], non_blocking=True)
-            out_ready[b].record(main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(out_ready[b])
-                h_loc[b].copy_(d_loc[b], non_blocking=True)
-                h_cls[b].copy_(d_cls[b], non_blocking=True)
-                out_free[b].record(s_out)
-        main.wait_stream(s_out)
-        main.wait_stream(s_in)
+    def call(d_bev, d_trans, d_nat):
+        out = model(d_bev, d_trans, d_nat, batch_size=B)
+        return out["loc"], out["cls"]
 
-    e2e_steps(max(2, args.warmup))
-    torch.cuda.synchronize()
-    barrier()
-    e0.record()
-    e2e_steps(args.steps)
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    pipe = HostPipeline(dev, [bevs, trans, nat], call, [(n_maps, 256, 256, 6, 1, 6), (n_maps, 256 * 256 * 6, 2)])
+    pipe.steps(max(2, args.warmup))
+    e2e_ms = timer.run(pipe.steps, args.steps)
     e2e_value = frames / (e2e_ms * 1e-3)
-    h2d = bevs.numel() * 4 + trans.numel() * 8 + nat.numel() * 8
-    d2h = (h_loc[0].numel() + h_cls[0].numel()) * 4
+    h2d, d2h = pipe.h2d, pipe.d2h
+    s_in, s_out = pipe.s_in, pipe.s_out
+    in_ready, in_free, out_ready, out_free = pipe.in_ready, pipe.in_free, pipe.out_ready, pipe.out_free
+    h_trans, h_nat = [p[1] for p in pipe.h_in], [p[2] for p in pipe.h_in]
+    d_trans, d_nat = [p[1] for p in pipe.d_in], [p[2] for p in pipe.d_in]
+    NBUF = pipe.NBUF
+    del pipe.h_out, pipe.d_out
+    main = torch.cuda.current_stream()
 
     # ---------------- e2e_detections: uint8 BEVs in, kept boxes out (SURVEY 8(f2)+(f3)) ----------------
     # The same forward, fed the dataset's bool occupancy grid (V2XSimDet.py:299, before .astype(np.float32)) and followed
     # by the on-device apply_nms_det, so only the kept boxes cross PCIe -- what test_codet.py consumes per frame.
-    from v2x_b200 import postproc
     from v2x_b200.postproc import DetPostprocessor
-    del d_loc, d_cls, h_loc, h_cls
     h_u8 = [(bevs > 0).to(torch.uint8).pin_memory() for _ in range(NBUF)]
     d_u8 = [torch.empty_like(h_u8[0], device=dev) for _ in range(NBUF)]
     anchors = torch.from_numpy(_anchor_table()).to(dev)
@@ -373,17 +550,7 @@ def run_ours(args, rank, world, local_rank):
         main.wait_stream(s_in)
 
     det_steps(max(2, args.warmup))
-    torch.cuda.synchronize()
-    barrier()
-    e0.record()
-    det_steps(args.steps)
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    det_ms = float(t.item())
+    det_ms = timer.run(det_steps, args.steps)
     dets = posts[(args.steps - 1) % NBUF].unpack(h_det[(args.steps - 1) % NBUF])
     det_info = {"value": frames / (det_ms * 1e-3), "unit": "frames/s", "ms_per_step": det_ms / args.steps,
                 "h2d_bytes_per_step": h_u8[0].numel() + trans.numel() * 8 + nat.numel() * 8,
@@ -394,43 +561,12 @@ def run_ours(args, rank, world, local_rank):
 
     if rank != 0:
         return
-    # ---------------- roofline of the conv kernel family ----------------
-    # conv time per step = the conv launches of one step replayed back to back on ONE stream, timed live with CUDA
-    # events on that stream (the step itself overlaps the x_4 branch with the warp kernel on a side stream, so
-    # "step minus the other kernels" would credit hidden time to the convs).
-    peaks = measured_peaks()
-    conv_launches = [l for l in plan.launches if getattr(l, "flops", 0.0) > 0]
-    other_launches = [l for l in plan.launches if getattr(l, "flops", 0.0) == 0]
-    other_ms = time_launch_list(other_launches)
-    step_ms = ms_total / args.steps
-    conv_ms = time_launch_list(conv_launches)
-    alg_flops = GFLOP_PER_FRAME * 1e9 * B
-    achieved = alg_flops / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor",
-                "kernel": "v2x::conv_tc_kernel<BN,PLANES,KSTEPS,HALO> (the %d conv launches of a step)" % len(conv_launches),
-                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": conv_traffic(B), "traffic_unit": "bytes of DRAM read+write per step over the conv launches (ncu --set full, profiles/conv_traffic.json)",
-                "peak_source": peaks["source"],
-                "conv_ms_per_step": conv_ms, "other_kernels_ms_per_step": other_ms,
-                "conv_share_of_step": conv_ms / step_ms,
-                "launches_per_step": {"conv": len(conv_launches), "other": len(other_launches)},
-                "algorithmic_gflop_per_frame": GFLOP_PER_FRAME,
-                "note": "algorithmic FLOPs (SURVEY 8(d)) / serial conv kernel time; executed FLOPs are ~1% higher "
-                        "(13->16 channel pad, block-diagonal head 1x1, tap-pack edge columns); conv + other can exceed "
-                        "the step because the x_4 branch overlaps the warp kernel"}
-
-    # ---------------- CPU baseline (oracle port) on this host, bounded sample ----------------
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only
-        fps, spf, threads = cpu_reference(3, 1)
-        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "3 timed forwards of 1 scene (5 agents), median %.3f s/frame; torch CPU fp32, best of "
-                         "{8,16,32,64,all} threads" % spf}
-
-    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+    roofline = roofline_of(plan, cfg, args, B, ms_total / args.steps)
+    cpu = cpu_baseline_subprocess(args) if (not args.no_cpu_baseline and world == 1) else None   # rank 0 at N = 1 only
+    line = {"metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if planes == 1 else "bf16x3", "data": "synthetic",
-            "config": {"workload": "V2VNet 5-agent detection fwd, 256x256x13 BEV, gnn_iter=3, layer=3 (BASELINE configs[1])",
+            "vs_baseline": None, "dtype": DTYPE_OF[args.precision], "data": "synthetic",
+            "config": {"workload": cfg["workload"],
                        "scenes_per_gpu_per_step": B, "agents": AGENTS, "precision": args.precision,
                        "l2": "no flush: per-step inputs %.0f MB and activations ~%.1f GB exceed the 126 MB L2"
                              % (B * 17.04, 0.4 * B),
@@ -440,12 +576,97 @@ def run_ours(args, rank, world, local_rank):
                                           else "neighbour exchange (grouped send/recv of the 4 other agents' maps)"))
                        if unit_sharded
                        else "scene-sharded x%d, no data-path collective" % world},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": cfg["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "api": "coperception.models.det.V2VNet.forward (pinned host in/out, 3-stream pipeline)"},
             "e2e_detections": det_info,
             "gpu_launches": plan.n_kernels * args.steps,
             "kernels_per_step": plan.n_kernels,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    emit(line)
+
+
+def run_generic(args, rank, world, local_rank):
+    """BASELINE configs 0 / 2 / 4: FaFNet lower / upper bound, When2Com_UNet seg.  Replicas only across GPUs: the forward
+    of these models has no cross-GPU exchange step (config 4 is plain data parallel), so every rank runs its own batch."""
+    from v2x_b200 import default_det_config, nets, nets_seg
+    from v2x_b200 import synthetic as synth
+
+    cfg = CONFIGS[args.config]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    U = args.scenes or cfg["units"]
+    mpu = cfg["maps_per_unit"]
+    n_maps = U * mpu
+    timer = Timer(dev, world)
+    if args.config in ("faf_lower", "faf_upper_dp"):
+        from coperception.models.det import FaFNet
+        sd = synth.fafnet_state(0)
+        bevs = synth.make_bevs(n_maps, seed=rank)
+        plan = nets.FaFNetPlan(sd, n_maps, planes=args.precision, device=dev)
+        plan.set_bevs(bevs.to(dev))
+        model = FaFNet(default_det_config(), kd_flag=0, num_agent=mpu)
+        host_inputs = [bevs]
+        out_shapes = [(n_maps, 256, 256, 6, 1, 6), (n_maps, 256 * 256 * 6, 2)]
+
+        def call(d_bev):
+            out = model(d_bev, batch_size=U)
+            return out["loc"], out["cls"]
+        api = "coperception.models.det.FaFNet.forward"
+    else:
+        from coperception.models.seg import When2Com_UNet
+        sd = synth.seg_when2com_state(0)
+        x, trans, nat = synth.make_seg_scene(U, AGENTS, seed=rank)
+        plan = nets_seg.SegWhen2comPlan(sd, U, AGENTS, planes=args.precision, device=dev, warp_flag=1, inference="activated")
+        plan.set_x(x.to(dev))
+        plan.trans.copy_(trans.to(dev))
+        plan.num_agent.copy_(nat.to(dev))
+        model = When2Com_UNet(default_det_config(), n_classes=8, warp_flag=1, num_agent=AGENTS)
+        host_inputs = [x, trans, nat]
+        out_shapes = [(n_maps, 8, 256, 256)]
+
+        def call(d_x, d_trans, d_nat):
+            return (model(d_x, d_trans, d_nat, inference="activated", training=False),)
+        api = "coperception.models.seg.When2Com_UNet.forward"
+    model.load_state_dict(sd, strict=True)
+    model.precision = args.precision
+    model.alias_outputs = True
+    model = model.to(dev).eval()
+    torch.cuda.synchronize()
+    plan.capture()
+
+    def replay(k):
+        for _ in range(k):
+            plan.run()
+
+    replay(args.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timer.run(replay, args.steps)
+    clocks = _clocks(sampler, rank)
+    units = U * world * args.steps
+    value = units / (ms_total * 1e-3)
+
+    pipe = HostPipeline(dev, host_inputs, call, out_shapes)
+    pipe.steps(max(2, args.warmup))
+    e2e_ms = timer.run(pipe.steps, args.steps)
+    if rank != 0:
+        return
+    roofline = roofline_of(plan, cfg, args, U, ms_total / args.steps)
+    cpu = cpu_baseline_subprocess(args) if (not args.no_cpu_baseline and world == 1) else None
+    in_mb = sum(t.numel() * t.element_size() for t in host_inputs) / 1e6
+    line = {"metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": DTYPE_OF[args.precision], "data": "synthetic",
+            "config": {"workload": cfg["workload"], "units_per_gpu_per_step": U, "maps_per_unit": mpu,
+                       "precision": args.precision,
+                       "l2": "no flush: per-step inputs %.0f MB and activations exceed the 126 MB L2" % in_mb,
+                       "parallelism": "replicas x%d (no exchange step in this forward), no data-path collective" % world},
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": cfg["unit"], "h2d_bytes_per_step": pipe.h2d,
+                    "d2h_bytes_per_step": pipe.d2h, "ms_per_step": e2e_ms / args.steps,
+                    "api": api + " (pinned host in/out, 3-stream pipeline)"},
+            "gpu_launches": plan.n_kernels * args.steps, "kernels_per_step": plan.n_kernels,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     emit(line)
 
@@ -470,13 +691,16 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scenes", type=int, default=8, help="scenes (frames) per GPU per step")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--config", default="v2v_det", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: v2v_det (the metric; default), faf_lower, w2c_seg, faf_upper_dp")
+    ap.add_argument("--scenes", type=int, default=0, help="units (scenes / agent maps) per GPU per step; 0 = the config's default")
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "fp16x3", "bf16"],
+                    help="v2x_b200/precision.py: mixed (default; the mode the 1e-3 parity tests assert), fp16x3, bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", default="unit", choices=["unit", "scene"], help="multi-GPU partition (N > 1)")
+    ap.add_argument("--shard", default="unit", choices=["unit", "scene"], help="multi-GPU partition of v2v_det (N > 1)")
     ap.add_argument("--exchange", default="allgather", choices=["neighbours", "allgather"],
-                    help="unit-sharded x_3 exchange: one all-gather (default; measured at 2/4/8 GPUs), or NCCL send/recv of "
-                         "just the needed neighbour maps (equal at 2/4 GPUs, not yet measured at 8)")
+                    help="unit-sharded x_3 exchange: one all-gather (default), or NCCL send/recv of just the needed "
+                         "neighbour maps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -504,7 +728,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        (run_v2v_det if args.config == "v2v_det" else run_generic)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

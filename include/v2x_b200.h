@@ -14,11 +14,16 @@
  *   - the caller owns every buffer; nothing is retained after the call returns;
  *   - return 0 on success, <0 on error; v2x_last_error() returns a thread-local message.
  *
- * Activation layout ("act"): NHWC bf16 with `planes` planes, plane p at element offset
- * p * N*H*W*C.  planes == 1 is plain bf16.  planes == 2 stores x as hi + lo with
- * hi = bf16(x), lo = bf16(x - hi); convolutions then accumulate hi*hi + hi*lo + lo*hi on the
- * tensor cores (3 bf16 MMAs, fp32 accumulate: ~16 mantissa bits, "bf16x3"), which is what the
- * 1e-3 parity tests use.  Weights are packed the same way.
+ * Activation layout ("act"): NHWC, 16-bit elements, `planes` planes, plane p at element offset
+ * p * N*H*W*C.  The plane count fixes the storage format:
+ *   planes == 1 (V2X_FMT_BF16) : one bf16 plane -- the throughput mode BASELINE.json's config names;
+ *   planes == 2 (V2X_FMT_F16X2): x = hi + lo with hi = fp16(x) (saturating), lo = fp16(x - hi): ~22 mantissa
+ *                                bits.  A convolution over such tensors issues `mmas` tensor-core passes per
+ *                                k-step (fp32 accumulate): 3 = hi*hi + hi*w_lo + a_lo*w_hi (weights packed
+ *                                V2X_FMT_F16X2, "fp16x3"), 2 = hi*hi + a_lo*w_hi (weights one fp16 plane,
+ *                                V2X_FMT_F16), 1 = hi*hi only (the lo plane of the input is not read).  The
+ *                                per-layer choice that meets the 1e-3 parity contract at the least tensor
+ *                                time is the "mixed" precision of v2x_b200/nets.py.
  */
 #ifndef V2X_B200_H_
 #define V2X_B200_H_
@@ -28,6 +33,11 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* storage formats of act tensors (== their plane count) and of packed weights */
+#define V2X_FMT_BF16 1   /* one bf16 plane                                      */
+#define V2X_FMT_F16X2 2  /* fp16 hi plane + fp16 lo plane                       */
+#define V2X_FMT_F16 3    /* one fp16 plane (packed weights of mmas = 1 / 2)     */
 
 #define V2X_OK 0
 #define V2X_ERR_ARG -1
@@ -41,11 +51,11 @@ const char* v2x_last_error(void);
 int v2x_device_ok(void);
 
 /* ---- epilogue modes of v2x_conv_fwd -------------------------------------------------- */
-#define V2X_EPI_ACT 0      /* y = [relu](acc + bias) -> act (bf16 planes), optional 2x nearest upsample on store */
+#define V2X_EPI_ACT 0      /* y = [relu](acc + bias) -> act, optional 2x nearest upsample on store */
 #define V2X_EPI_F32_SPLIT 1 /* y = acc + bias -> fp32 NHWC, channels [0,split) to out0, [split,cout) to out1     */
 #define V2X_EPI_F32_NCHW 3  /* y = acc + bias -> fp32 NCHW [N][cout][H][W] in out0 (segmentation logits)                       */
 #define V2X_EPI_GRU 2      /* zero-hidden ConvGRU gate epilogue, see v2x_conv_params                           */
-#define V2X_EPI_TAIL_F32_SPLIT 4 /* t = relu(acc + bias) (bf16 planes, kept in shared memory, never stored);
+#define V2X_EPI_TAIL_F32_SPLIT 4 /* t = relu(acc + bias) (act format, kept in shared memory, never stored);
                                     y = tail_weights * t + tail_bias -> fp32 NHWC split like V2X_EPI_F32_SPLIT:
                                     the detection heads' conv3x3+BN+ReLU -> conv1x1 pair in ONE launch
                                     (DetModelBase.py:283-296, 319-329); needs cout == block_n == 64              */
@@ -63,14 +73,16 @@ int v2x_device_ok(void);
  */
 typedef struct v2x_conv_params {
   /* inputs: up to two sources, concatenated along channels (src0 channels first) */
-  const void* src[2];  /* act, [planes][N][Hin][Win][cin[s]] bf16; src[1] may be NULL          */
+  const void* src[2];  /* act, [planes][N][Hin][Win][cin[s]]; src[1] may be NULL          */
   int32_t cin[2];      /* channels per source (multiple of 16)                                 */
   int32_t n_maps;      /* N                                                                    */
   int32_t h_out, w_out;/* output spatial size (multiple of 8 / 16); input is stride * output   */
   int32_t stride;      /* 1 or 2                                                               */
   int32_t taps;        /* 9 (3x3, pad 1) or 1 (1x1)                                            */
-  int32_t planes;      /* 1 (bf16) or 2 (bf16x3 split precision) -- inputs, weights and output */
-  /* packed weights from v2x_pack_conv_weights: [planes][cout_pad][k_total] bf16, bias fp32    */
+  int32_t planes;      /* storage format of the inputs and the output: 1 (bf16) or 2 (fp16 hi/lo)   */
+  /* packed weights from v2x_pack_conv_weights, bias fp32: [cout_pad][k_total] bf16 (planes == 1),
+     [2][cout_pad][k_total] fp16 hi/lo (planes == 2, mmas == 3) or [cout_pad][k_total] fp16
+     (planes == 2, mmas == 1 or 2)                                                             */
   const void* weights;
   const float* bias;   /* [cout_pad]                                                           */
   int32_t cout;        /* logical output channels                                              */
@@ -93,7 +105,7 @@ typedef struct v2x_conv_params {
   const int64_t* num_agent;  /* [batch][agents] (reference num_agent_tensor) or NULL           */
   int32_t batch, agents;     /* agent-major maps: global unit = batch * agent + b              */
   int32_t map_offset;        /* global unit index of this launch's map 0 (sharded plans), else 0 */
-  int32_t gru_pre_act;       /* EPI_GRU: src[1] is a bf16 act tensor [planes][N][H][W][cout] of gate pre-activations (packed
+  int32_t gru_pre_act;       /* EPI_GRU: src[1] is an act tensor [planes][N][H][W][cout] of gate pre-activations (packed
                                 gate order, e.g. conv(mean, W_ih[:, C:]) + bias from an EPI_ACT launch with relu = 0); cin[1] must
                                 be 192 and the packed weights carry 192 extra K columns holding the identity
                                 (W[n][taps*cin[0] + j] = (n % 192 == j)), so every N tile accumulates its own window on the
@@ -102,12 +114,12 @@ typedef struct v2x_conv_params {
                                 dimension (weights [planes][96][3 * sum(cin)], row = kw*32 + co, k = (source, kh, ci);
                                 cout_pad == block_n == 96) and summed in the epilogue -- 3 MMAs of N = 96 per k-step instead
                                 of 9 of N = 32, whose cost is dominated by re-reading the A operand (csrc/conv_pack3.cu) */
-  int32_t reserved;
+  int32_t mmas;              /* planes == 2 only: tensor-core passes per k-step, 3 (0 means 3), 2 or 1 -- see the file header */
   /* EPI_GRU, optional: fp32 [N*H*W][cout] (packed gate order) added to the gate pre-activations -- the round-invariant
      half conv(mean, W_ih[:, C:]) + bias, computed once per frame by an EPI_F32_SPLIT launch (split == cout) so the three
      GNN rounds only convolve the changing half (V2VNet.py:99: cat([h_i, mean]); the mean never changes). */
   const float* gru_add;
-  /* V2X_EPI_TAIL_F32_SPLIT: the fused 1x1 conv. tail_weights = packed [planes][tail_cout_pad][cout] bf16 (K-major, as
+  /* V2X_EPI_TAIL_F32_SPLIT: the fused 1x1 conv. tail_weights = packed [planes][tail_cout_pad][cout] (same format as the acts, K-major, as
      v2x_pack_conv_weights writes a taps == 1 operand), tail_bias fp32 [tail_cout_pad]; channels [0,split) of the tail
      output go to out0 (row stride split), [split,tail_cout) to out1 (row stride tail_cout - split). */
   const void* tail_weights;
@@ -123,7 +135,7 @@ int v2x_conv_fwd_crosscheck(const v2x_conv_params* p, void* stream);
 
 /*
  * Weight packing (one-time, on device).  Writes a block of the packed operand:
- *   dst[(plane)][row_off + perm(co)][k_off + tap' * cin_pad + (ci - ci_lo)] = split_bf16(w[co][ci][tap] * s[co])
+ *   dst[(plane)][row_off + perm(co)][k_off + tap' * cin_pad + (ci - ci_lo)] = fmt(w[co][ci][tap] * s[co])
  *   bias[row_off + perm(co)] = (b[co] - mean[co]) * s[co] + beta[co],  s = gamma / sqrt(var + eps)  (s = 1 without BN)
  * w is OIHW fp32 ([cout][cin_total][taps]); ci in [ci_lo, ci_hi) selects one concat source;
  * cin_pad >= ci_hi - ci_lo (extra k columns must already be zero: memset dst first);
@@ -135,7 +147,7 @@ int v2x_conv_fwd_crosscheck(const v2x_conv_params* p, void* stream);
 int v2x_pack_conv_weights(const float* w, const float* b, const float* bn_gamma, const float* bn_beta,
                           const float* bn_mean, const float* bn_var, float eps, int32_t cout, int32_t cin_total,
                           int32_t taps, int32_t ci_lo, int32_t ci_hi, int32_t cin_pad, int32_t vflip,
-                          int32_t gru_gates, void* dst, float* dst_bias, int32_t planes, int32_t cout_pad,
+                          int32_t gru_gates, void* dst, float* dst_bias, int32_t fmt /* V2X_FMT_* */, int32_t cout_pad,
                           int32_t k_total, int32_t row_off, int32_t k_off, int32_t write_bias, void* stream);
 
 /* bias / b_hh_n vectors of the zero-hidden GRU epilogue (functional.py:95-105 with hidden == 0):
@@ -143,7 +155,7 @@ int v2x_pack_conv_weights(const float* w, const float* b, const float* bn_gamma,
 int v2x_pack_gru_bias(const float* b_ih, const float* b_hh, int32_t c, float* bias, float* bhn, void* stream);
 
 /*
- * fp32 NHWC occupancy/feature input -> act bf16 planes with channels zero-padded to c_pad.
+ * fp32 NHWC occupancy/feature input -> act with channels zero-padded to c_pad.
  * Replaces x.to(torch.float) + the NCHW view at Backbone.py:100-101 (memory is already NHWC,
  * V2VNet.py:51).
  */
@@ -265,7 +277,7 @@ int v2x_voxelize_fwd(const int32_t* idx, const int32_t* count, int32_t capacity,
                      int32_t w, int32_t c, int32_t c_pad, int32_t planes, int32_t rot90_k3, int32_t* bad_count,
                      void* stream);
 
-/* bool / uint8 NHWC occupancy [n_pixels][c] (non-zero = 1.0) -> act bf16 planes, channels zero-padded to c_pad: the
+/* bool / uint8 NHWC occupancy [n_pixels][c] (non-zero = 1.0) -> act, channels zero-padded to c_pad: the
  * `padded_voxel_points` array before its .astype(np.float32) (V2XSimDet.py:299-302), 13 instead of 52 bytes/pixel. */
 int v2x_pack_input_u8(const uint8_t* x, void* out, int64_t n_pixels, int32_t c, int32_t c_pad, int32_t planes,
                       void* stream);
@@ -291,7 +303,7 @@ int v2x_det_nms_fwd(const float* cls, const float* loc, const float* anchors, in
                     int32_t* sel_count, void* stream);
 
 /* ---- segmentation UNet pieces (CP/models/seg/SegModelBase.py) ------------------------------ */
-/* fp32 NCHW [n][c][h][w] (what SegModule.py:49 hands the model) -> act bf16 planes NHWC, channels zero-padded to c_pad */
+/* fp32 NCHW [n][c][h][w] (what SegModule.py:49 hands the model) -> act NHWC, channels zero-padded to c_pad */
 int v2x_pack_input_nchw(const float* x, void* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pad,
                         int32_t planes, void* stream);
 /* nn.MaxPool2d(2) (SegModelBase.py:113): act [n][2*h_out][2*w_out][c] -> [n][h_out][w_out][c] */
@@ -301,7 +313,7 @@ int v2x_maxpool2_fwd(const void* x, void* out, int32_t n, int32_t h_out, int32_t
 int v2x_upsample_bilinear2_fwd(const void* x, void* out, int32_t n, int32_t h_in, int32_t w_in, int32_t c,
                                int32_t planes, void* stream);
 
-/* act (bf16 planes, NHWC) -> fp32 NCHW, for returning intermediate maps to torch callers */
+/* act (NHWC) -> fp32 NCHW, for returning intermediate maps to torch callers */
 int v2x_act_to_nchw_f32(const void* act, float* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t planes,
                         void* stream);
 

@@ -1,0 +1,136 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU emulation of the operand precisions the sm_100a conv kernels can run in.
+
+Every conv of the restated V2VNet det forward is re-run with its activations / weights rounded the way a candidate
+kernel mode stores them (fp32 accumulation, like the TMEM accumulators), and the end-to-end error against the fp32
+oracle is reported in the metric of tests/test_gpu_nets.py (max-abs error / max-abs value).  This is what decided
+which modes were built; it costs no GPU time.
+
+  python -m oracle.precision_study            # table of modes
+"""
+from __future__ import annotations
+
+import sys
+
+import torch
+import torch.nn.functional as F
+
+from . import restate, synth
+
+_real_conv2d = F.conv2d
+
+
+def q_bf16(x):
+    return x.bfloat16().float()
+
+
+def q_fp16(x):
+    return x.half().float()
+
+
+def q_split(q):
+    def f(x):
+        hi = q(x)
+        return hi + q(x - hi)
+    return f
+
+
+def ident(x):
+    return x
+
+
+QUANT = {"f32": ident, "bf16": q_bf16, "fp16": q_fp16, "bf16x2": q_split(q_bf16), "fp16x2": q_split(q_fp16)}
+
+# candidate kernel modes: (activation storage, weight storage, MMAs per k-step)
+MODES = {
+    "bf16":          ("bf16", "bf16", 1),
+    "fp16":          ("fp16", "fp16", 1),
+    "bf16x3":        ("bf16x2", "bf16x2", 3),
+    "fp16a2":        ("fp16x2", "fp16", 2),     # activations hi/lo, weights single fp16
+    "fp16w2":        ("fp16", "fp16x2", 2),     # activations single fp16, weights hi/lo
+    "fp16x3":        ("fp16x2", "fp16x2", 3),
+}
+
+
+class emulate:
+    """with emulate(policy): every F.conv2d inside oracle.restate rounds (x, w) per ``policy(x, w) -> (qa, qw)``."""
+
+    def __init__(self, policy):
+        self.policy = policy
+
+    def __enter__(self):
+        pol = self.policy
+
+        def conv2d(x, w, b=None, *a, **k):
+            qa, qw = pol(x, w)
+            return _real_conv2d(QUANT[qa](x), QUANT[qw](w), b, *a, **k)
+        restate.F.conv2d = conv2d
+        return self
+
+    def __exit__(self, *exc):
+        restate.F.conv2d = _real_conv2d
+        return False
+
+
+def rel_err(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def heavy(x, w):
+    """The tensor-bound launches of the V2VNet det step: K = 9 * cin >= 1728 (GRU, conv5_1 .. conv8_1 are cat inputs)."""
+    cin = w.shape[1]
+    return cin * w.shape[2] * w.shape[3] >= 1700 and cin not in (256, 512) or w.shape[0] == 768
+
+
+def run(seed=0, batch=1, agents=5):
+    sd = synth.v2vnet_det_state(seed)
+    bevs, trans, nat = synth.make_scene(batch, agents, seed)
+    with torch.no_grad():
+        ref = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=batch, agent_num=agents, gnn_iter=3)
+    rows = []
+    policies = {name: (lambda x, w, m=m: (m[0], m[1])) for name, m in MODES.items()}
+    # mixed: tensor-bound layers in a 2-MMA mode, everything else at full split precision
+    for light, hv in (("fp16x3", "fp16w2"), ("fp16x3", "fp16a2"), ("fp16w2", "fp16x3"), ("fp16", "fp16x3"),
+                      ("fp16x3", "fp16")):
+        policies["light=%s heavy=%s" % (light, hv)] = (
+            lambda x, w, l=MODES[light], h=MODES[hv]: (h[0], h[1]) if heavy(x, w) else (l[0], l[1]))
+    for name, pol in policies.items():
+        with torch.no_grad(), emulate(pol):
+            out = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=batch, agent_num=agents, gnn_iter=3)
+        flips = int((out["cls"].argmax(-1) != ref["cls"].argmax(-1)).sum())
+        rows.append((name, rel_err(out["loc"], ref["loc"]), rel_err(out["cls"], ref["cls"]), flips))
+        print("%-34s loc %.2e  cls %.2e  argmax flips %d / %d" % (rows[-1] + (ref["cls"].numel() // 2,)), flush=True)
+    return rows
+
+
+if __name__ == "__main__":
+    run(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+
+
+def per_layer(seed=0, batch=1, agents=5, cheap=("fp16a2", "fp16w2", "fp16")):
+    """Error contribution of each conv: everything at fp16x3 except ONE layer in a cheaper mode."""
+    sd = synth.v2vnet_det_state(seed)
+    bevs, trans, nat = synth.make_scene(batch, agents, seed)
+    names = {v.data_ptr(): k for k, v in sd.items() if v.dim() >= 4}
+    with torch.no_grad():
+        ref = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=batch, agent_num=agents, gnn_iter=3)
+    used = []
+
+    def name_of(w):
+        return names.get(w.data_ptr()) or names.get(w._base.data_ptr() if w._base is not None else 0, "?")
+
+    def probe(x, w):
+        if name_of(w) not in used:
+            used.append(name_of(w))
+        return ("f32", "f32")
+    with torch.no_grad(), emulate(probe):
+        restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=batch, agent_num=agents, gnn_iter=3)
+    res = {}
+    for layer in used:
+        for m in cheap:
+            def pol(x, w, layer=layer, m=m):
+                return MODES[m][:2] if name_of(w) == layer else MODES["fp16x3"][:2]
+            with torch.no_grad(), emulate(pol):
+                out = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=batch, agent_num=agents, gnn_iter=3)
+            res[(layer, m)] = max(rel_err(out["loc"], ref["loc"]), rel_err(out["cls"], ref["cls"]))
+        print("%-42s " % layer + "  ".join("%s %.2e" % (m, res[(layer, m)]) for m in cheap), flush=True)
+    return res

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- import the LIVE reference modules from /root/reference.
 
-Only usable in the build container (the GPU box has no /root/reference).  Three shims,
+In the build container the modules come from /root/reference; on the GPU box from the staged copy under
+oracle/_ref (oracle/make_ref.py).  Three shims,
 none of which touches reference files:
   1. ``import coperception`` fails (CP/__init__.py:4 -> datasets -> shapely), so namespace
      stubs for the packages are pre-seeded in ``sys.modules`` with ``__path__`` pointing into
@@ -17,7 +18,11 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("V2X_REFERENCE_ROOT", "/root/reference/coperception")
+# where the reference lives: $V2X_REFERENCE_ROOT, else the read-only tree of the build container, else the copy
+# staged by oracle/make_ref.py (git-ignored oracle/_ref, which travels to the GPU box)
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF_ROOT = os.environ.get("V2X_REFERENCE_ROOT") or (
+    "/root/reference/coperception" if os.path.isdir("/root/reference/coperception/coperception/models/det") else _STAGED)
 CP = os.path.join(REF_ROOT, "coperception")
 
 

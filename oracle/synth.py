@@ -31,16 +31,8 @@ if _SRC not in sys.path:
 # the generators bench.py also uses live in the product package; re-exported here so fixtures and benchmark agree
 from v2x_b200.synthetic import (BACKBONE_BNS, BACKBONE_CONVS, BOX_CODE, CATEGORY_NUM, MAP_DIMS, NUM_ANCHORS,  # noqa: E402,F401
                                 _Gen, _bn, _conv, backbone_state, heads_state, make_bevs, make_poses, make_scene,
-                                make_trans_matrices, plant_detections, v2vnet_det_state)
-
-
-def fafnet_state(seed=0, compress_level=0):
-    """state_dict of FaFNet (FaFNet.py:17-25; NonIntermediateModelBase.py:24: ``stpn``)."""
-    g = _Gen(seed)
-    sd = OrderedDict()
-    heads_state(sd, g)
-    backbone_state(sd, g, "stpn.", compress_level=compress_level)
-    return sd
+                                make_trans_matrices, plant_detections, v2vnet_det_state, fafnet_state, SEG_DOUBLE_CONVS,
+                                _double_conv, seg_unet_state, seg_when2com_state, make_seg_scene)
 
 
 def when2com_det_state(seed=0):
@@ -73,45 +65,6 @@ def when2com_det_state(seed=0):
     return sd
 
 
-# ---------------------------------------------------------------------------------------------
-# segmentation models (CP/models/seg/SegModelBase.py:17-27 channel plan)
-# ---------------------------------------------------------------------------------------------
-SEG_DOUBLE_CONVS = [  # (prefix, cin, cmid, cout)
-    ("inc.double_conv.", 13, 64, 64),
-    ("down1.maxpool_conv.1.double_conv.", 64, 128, 128),
-    ("down2.maxpool_conv.1.double_conv.", 128, 256, 256),
-    ("down3.maxpool_conv.1.double_conv.", 256, 512, 512),
-    ("down4.maxpool_conv.1.double_conv.", 512, 512, 512),
-    ("up1.conv.double_conv.", 1024, 512, 256),
-    ("up2.conv.double_conv.", 512, 256, 128),
-    ("up3.conv.double_conv.", 256, 128, 64),
-    ("up4.conv.double_conv.", 128, 64, 64),
-]
-
-
-def _double_conv(sd, g, p, cin, cmid, cout):
-    _conv(sd, g, p + "0", cmid, cin)
-    _bn(sd, g, p + "1", cmid)
-    _conv(sd, g, p + "3", cout, cmid)
-    _bn(sd, g, p + "4", cout)
-
-
-def seg_unet_state(seed=0, n_classes=8, g=None, sd=None, compress_level=0):
-    """state_dict of seg UNet / the SegModelBase part of every seg model (SegModelBase.py:17-43)."""
-    g = g or _Gen(seed)
-    sd = OrderedDict() if sd is None else sd
-    for p, cin, cmid, cout in SEG_DOUBLE_CONVS:
-        _double_conv(sd, g, p, cin, cmid, cout)
-    _conv(sd, g, "outc.conv", n_classes, 64, k=(1, 1), gain=3.0)
-    if compress_level > 0:
-        cc = 512 // (2 ** compress_level)
-        _conv(sd, g, "com_compresser", cc, 512, k=(1, 1))
-        _bn(sd, g, "bn_compress", cc)
-        _conv(sd, g, "com_decompresser", 512, cc, k=(1, 1))
-        _bn(sd, g, "bn_decompress", 512)
-    return sd
-
-
 def seg_v2vnet_state(seed=0, n_classes=8):
     """seg V2VNet (CP/models/seg/V2VNet.py:9-23): SegModelBase + Conv2dGRU(1024 -> 512)."""
     g = _Gen(seed)
@@ -122,32 +75,6 @@ def seg_v2vnet_state(seed=0, n_classes=8):
     sd["convgru.weight_hh_l0"] = g.uniform((3 * c, c, 3, 3), -bw, bw)
     sd["convgru.bias_ih_l0"] = g.uniform((3 * c,), -0.5, 0.5)
     sd["convgru.bias_hh_l0"] = g.uniform((3 * c,), -0.5, 0.5)
-    return sd
-
-
-def seg_when2com_state(seed=0, n_classes=8):
-    """seg When2Com_UNet (CP/models/seg/When2Com_UNet.py:10-91): SegModelBase + key/query MLPs + attention
-    + PolicyNet4 (own inc/down1-3 + conv1..5, :310-339)."""
-    g = _Gen(seed)
-    sd = seg_unet_state(seed, n_classes, g=g)
-
-    def linear(name, out_f, in_f, gain=3.0):
-        b = math.sqrt(gain / in_f)
-        sd[name + ".weight"] = g.uniform((out_f, in_f), -b, b)
-        sd[name + ".bias"] = g.uniform((out_f,), -0.1, 0.1)
-
-    for net, out in (("key_net", 1024), ("query_net", 32)):
-        linear(net + ".fc.0", 256, 4096, gain=6.0)
-        linear(net + ".fc.2", 128, 256, gain=6.0)
-        linear(net + ".fc.4", out, 128)
-    sd["attention_net.linear.weight"] = g.uniform((1024, 32), -0.03, 0.03)
-    sd["attention_net.linear.bias"] = g.uniform((1024,), -0.02, 0.02)
-    for p, cin, cmid, cout in SEG_DOUBLE_CONVS[:4]:
-        _double_conv(sd, g, "query_key_net." + p, cin, cmid, cout)
-    for name, cout, cin in (("conv1", 512, 512), ("conv2", 256, 512), ("conv3", 256, 256), ("conv4", 256, 256),
-                            ("conv5", 256, 256)):
-        _conv(sd, g, "query_key_net.%s.cbr_unit.0" % name, cout, cin)
-        _bn(sd, g, "query_key_net.%s.cbr_unit.1" % name, cout)
     return sd
 
 
@@ -204,12 +131,6 @@ def seg_fusion_state(kind, seed=0, n_classes=8):
     sd = seg_unet_state(seed, n_classes, g=g)
     _fusion_extra_state(sd, g, kind, 512, True)
     return sd
-
-
-def make_seg_scene(batch=1, num_agent=5, seed=0, p=0.03, present=None):
-    """(x [A*B,13,256,256] fp32 NCHW as SegModule.py:49 builds it, trans, num_agent_tensor)."""
-    bevs, trans, nat = make_scene(batch, num_agent, seed, p=p, present=present)
-    return bevs[:, 0].permute(0, 3, 1, 2).contiguous(), trans, nat
 
 
 def make_gt_from_detections(dets, seed=0, keep=0.7, jitter=0.25, extra=3):

@@ -22,7 +22,8 @@ def _run(args, timeout):
 
 
 def test_reference_arm_line():
-    """`bench.py --impl reference` times the reference's CPU algorithm (oracle port) and prints the same schema with
+    """`bench.py --impl reference` times the LIVE reference module on the host's cores (from /root/reference here, from the
+    copy staged under oracle/_ref on the GPU box; the oracle port only if neither exists) and prints the same schema with
     impl = reference, zero transfer bytes and a cpu_baseline describing the run."""
     d = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"], 600)
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
@@ -30,7 +31,10 @@ def test_reference_arm_line():
     assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    from oracle import ref_loader
+    if ref_loader.available():
+        assert cb["kind"] == "reference" and cb["reference_s_per_unit"] > 0 and cb["port_s_per_unit"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
@@ -38,12 +42,29 @@ def test_reference_arm_line():
 def test_measured_arm_line():
     d = _run(["--steps", "3", "--warmup", "3", "--no-cpu-baseline"], 900)
     assert (BASE_KEYS | {"roofline", "clocks", "gpu_launches", "e2e_detections"}) <= set(d)
-    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "bf16" and d["data"] == "synthetic"
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"].startswith("fp16 hi/lo") and d["data"] == "synthetic"
+    assert d["config"]["precision"] == "mixed"      # the default = the mode the 1e-3 parity tests assert
     assert d["value"] > 100 and d["gpu_launches"] == d["kernels_per_step"] * 3 > 0
     r = d["roofline"]
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert 0 < r["frac_executed"] < r["frac"] < r["frac_tensor_pipe"] < 1   # V2VNet hoists work (executed < algorithmic); mixed runs 1-3 passes
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 8 * 5 * 256 * 256 * 13 * 4 + 8 * 25 * 16 * 8 + 8 * 5 * 8
     assert e["d2h_bytes_per_step"] == 8 * 5 * 256 * 256 * 6 * (2 + 6) * 4 and 0 < e["value"] < d["value"]
     assert d["e2e_detections"]["d2h_bytes_per_step"] < e["d2h_bytes_per_step"] // 100
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+@pytest.mark.parametrize("config,unit", [("faf_lower", "agent-frames/s"), ("w2c_seg", "frames/s"), ("faf_upper_dp", "frames/s")])
+def test_reference_arm_other_configs(config, unit):
+    d = _run(["--impl", "reference", "--config", config, "--steps", "1", "--warmup", "1"], 900)
+    assert d["impl"] == "reference" and d["unit"] == unit and d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("config", ["faf_lower", "w2c_seg", "faf_upper_dp"])
+def test_measured_arm_other_configs(config):
+    d = _run(["--config", config, "--steps", "2", "--warmup", "3", "--no-cpu-baseline"], 900)
+    assert (BASE_KEYS | {"roofline", "clocks", "gpu_launches"}) <= set(d)
+    assert d["value"] > 0 and 0 < d["e2e"]["value"] < d["value"] and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert 0 < d["roofline"]["frac"] < 1 and d["gpu_launches"] == d["kernels_per_step"] * 2

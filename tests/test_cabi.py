@@ -145,5 +145,6 @@ def test_product_never_imports_the_oracle():
                 return True
         return False
 
-    assert not imports_oracle(bench.run_ours)
-    assert imports_oracle(bench.cpu_reference)   # the one sanctioned use: the CPU baseline / reference arm
+    for fn in (bench.run_v2v_det, bench.run_generic, bench.roofline_of, bench.HostPipeline.steps, bench.cpu_baseline_subprocess):
+        assert not imports_oracle(fn), fn
+    assert imports_oracle(bench._cpu_forwards)   # the one sanctioned use: the CPU baseline / reference arm

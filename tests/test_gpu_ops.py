@@ -1,6 +1,6 @@
 """GPU parity of the individual kernels (through the C ABI) against the CPU oracle / torch fp32.
 
-Tolerances: planes=2 ("bf16x3" split precision) must meet the north-star 1e-3 relative bound and
+Tolerances: planes=2 (fp16 hi/lo split storage, 3 MMA passes: "fp16x3") must meet the north-star 1e-3 relative bound and
 in practice sits near 1e-5; planes=1 (plain bf16 storage) is checked against the same fp32 oracle
 with a bf16-sized bound (operands and outputs are rounded to 8 mantissa bits)."""
 import os
@@ -382,13 +382,13 @@ def test_convgru_split_operands(impl, planes):
     assert err < TOL[planes]
 
 
-@pytest.mark.parametrize("impl,planes", [("crosscheck", 2), ("crosscheck", 1), ("tc", 1)])
+@pytest.mark.parametrize("impl,planes", [("crosscheck", 1), ("tc", 1)])
 @pytest.mark.parametrize("c", [64, 128])
 def test_convgru_pre_act_identity_columns(c, impl, planes):
     """gru_pre_act: the round-invariant pre-activations are a bf16 act tensor accumulated by the round's own GEMM through
     192 identity weight columns (no epilogue loads) -- must equal the oracle GRU on cat([h, mean]); c=128 has two N
     tiles, so each must pick its own 192-column window.  The tensor-core path offers it in the halo + streamed-weight
-    mode, which needs the single-plane operand sizes (the bf16x3 plans keep the fp32 ``gru_add`` form)."""
+    mode with bf16 (planes = 1) storage only; the fp16 hi/lo plans keep the fp32 ``gru_add`` form (refused loudly otherwise)."""
     from oracle import restate, synth
     from v2x_b200 import ops
     from v2x_b200.ops import EPI_ACT, EPI_GRU, ConvLaunch
@@ -491,7 +491,7 @@ def test_conv_tap_packed_geometries(cins, geom, planes, cout):
     pc = ops.pack_conv(wt, b, bn, cins=cins, planes=planes, device=dev, tap_pack=True)
     assert pc.tap_pack and pc.weights.shape[1] == 3 * cout
     acts = [to_act(F.pad(x, (0, 0, 0, 0, 0, cp - x.shape[1])), planes, dev) for x, cp in zip(xs, pc.cins)]
-    out = torch.full((planes, n, h, w, cout), 7.0, dtype=torch.bfloat16, device=dev)
+    out = torch.full((planes, n, h, w, cout), 7.0, dtype=ops.act_dtype(planes), device=dev)
     if planes == 2 and cin >= 192:
         # 2 x 110 KB of resident weights leave no room for the halo ring: refused loudly (pack_conv never picks it)
         from v2x_b200 import V2XError
@@ -504,8 +504,67 @@ def test_conv_tap_packed_geometries(cins, geom, planes, cout):
     print("pack3 cins=%s %s planes=%d rel_err=%.3e" % (cins, geom, planes, err))
     assert err < TOL[planes], err
     # relu = False path and a channel window inside a wider output tensor
-    wide = torch.zeros((planes, n, h, w, 32 + cout), dtype=torch.bfloat16, device=dev)
+    wide = torch.zeros((planes, n, h, w, 32 + cout), dtype=ops.act_dtype(planes), device=dev)
     ops.ConvLaunch(pc, acts, relu=False, out0=wide, out_c_off=32)()
     got = ops.act_to_float(wide)
     assert got[:, :32].abs().max().item() == 0.0
     assert rel_err(got[:, 32:], ref_cbr(xs, wt, b, bn, 1, relu=False)) < TOL[planes]
+
+
+MMA_TOL = {3: 1e-4, 2: 1.5e-3, 1: 3e-3}   # single conv, max-abs error / max-abs value: both split | weights 11-bit | both 11-bit
+
+
+@pytest.mark.parametrize("mmas", [3, 2, 1])
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[0] in ("c32_s1", "c64_s1", "c32_s2", "c64_1x1", "cat_64_32",
+                                                                      "cat_512_256", "c256_n512_up")],
+                         ids=lambda c: c[0])
+@pytest.mark.parametrize("impl", ["crosscheck", "tc", "tc_nohalo", "tc_pack3"])
+def test_conv_mma_passes(impl, case, mmas, monkeypatch):
+    """fp16 hi/lo storage (planes = 2) with 3 / 2 / 1 tensor-core passes per k-step (v2x_conv_params.mmas): the packed
+    weights are [2][..] fp16 hi/lo, one fp16 plane, one fp16 plane; the output is always written as hi/lo.  The
+    tensor-core kernels must agree with the CUDA-core cross-check of the SAME operand precision to summation order."""
+    from v2x_b200 import ops
+    dev = _dev()
+    if impl == "tc_nohalo":
+        monkeypatch.setenv("V2X_NO_HALO", "1")
+    name, cins, cout, stride, taps, n, h, w, up = case
+    g = torch.Generator().manual_seed(sum(ord(ch) for ch in name) + mmas)
+    k = 3 if taps == 9 else 1
+    xs = [torch.randn((n, c, h, w), generator=g) for c in cins]
+    cin = sum(cins)
+    wt = (torch.rand((cout, cin, k, k), generator=g) - 0.5) * (2.0 / (cin * taps) ** 0.5) * 1.7
+    b = torch.randn(cout, generator=g) * 0.1
+    bn = rand_bn(cout, g)
+    ref = ref_cbr(xs, wt, b, bn, stride)
+    if up:
+        ref = F.interpolate(ref, scale_factor=(2, 2))
+    pc = ops.pack_conv(wt, b, bn, cins=cins, stride=stride, planes=2, device=dev, tap_pack=(impl == "tc_pack3"), mmas=mmas)
+    if impl == "tc_pack3" and not pc.tap_pack:
+        pytest.skip("layer is not eligible for tap packing")
+    assert pc.weights.shape[0] == (2 if mmas == 3 else 1) and pc.weights.dtype == torch.float16
+    acts = [to_act(F.pad(x, (0, 0, 0, 0, 0, cp - x.shape[1])), 2, dev) for x, cp in zip(xs, pc.cins)]
+    out = ops.conv(pc, acts, upsample2x=up, crosscheck=(impl == "crosscheck"))
+    torch.cuda.synchronize()
+    assert out.shape[0] == 2 and out.dtype == torch.float16
+    err = rel_err(ops.act_to_float(out), ref)
+    print("conv mmas=%d %s %s rel_err=%.3e" % (mmas, impl, name, err))
+    assert err < MMA_TOL[mmas], err
+    if impl in ("tc", "tc_nohalo") :
+        pc_ref = ops.pack_conv(wt, b, bn, cins=cins, stride=stride, planes=2, device=dev, tap_pack=False, mmas=mmas)
+        want = ops.act_to_float(ops.conv(pc_ref, acts, upsample2x=up, crosscheck=True))
+        assert rel_err(ops.act_to_float(out), want) < 5e-5   # same operands, different fp32 summation order (K up to 6912)
+
+
+def test_fp16_split_saturates_instead_of_overflowing():
+    """fp16 hi/lo storage: values beyond the fp16 range are clamped to +-65504 (hi) + the representable remainder (lo),
+    never inf / nan (common.cuh::f16x2_sat)."""
+    from v2x_b200 import ops
+    dev = _dev()
+    x = torch.tensor([1e6, -1e6, 65504.0, 70000.0, 1e-7, 0.3333333], dtype=torch.float32)
+    x = torch.cat([x, torch.zeros(16 - x.numel())]).view(1, 1, 1, 16)
+    act = ops.pack_input(x.to(dev), 16, 2)
+    back = ops.act_to_float(act).cpu().view(-1)
+    assert torch.isfinite(back).all()
+    assert back[0] == 2 * 65504.0 and back[1] == -2 * 65504.0      # hi and lo both saturate
+    assert back[2] == 65504.0 and abs(back[3] - 70000.0) < 1.0
+    assert abs(back[5] - 0.3333333) < 1e-7

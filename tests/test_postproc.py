@@ -186,3 +186,108 @@ def test_gpu_iou_algorithm_port_matches_oracle_on_random_quads():
         got = _clip_iou_port(a.astype(np.float32), b.astype(np.float32))
         worst = max(worst, abs(got - ref))
     assert worst < 5e-6, worst          # float32 corners on the port's side (as the kernel receives them)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Exact-arithmetic pin of the polygon IoU.  The reference computes IoU with shapely
+# (postprocess.py:42-52: Polygon(a).intersection(Polygon(b)).area / union area); shapely / GEOS are absent from this
+# image, so the strongest pin available is an INDEPENDENT implementation in exact rational arithmetic: Sutherland-Hodgman
+# clipping over fractions.Fraction of the float64 corner values (every float is a rational, so the clip vertices, the
+# shoelace areas and the IoU are exact -- no tolerance, no epsilon).  oracle/postproc.quad_iou (float64, a different
+# construction: vertices-inside + edge crossings + angular sort) must agree with it to 1e-12.
+# ---------------------------------------------------------------------------------------------------------------------
+def _exact_iou(qa, qb):
+    from fractions import Fraction as Fr
+
+    def F(p):
+        return [(Fr(float(x)), Fr(float(y))) for x, y in p]
+
+    def area2(p):   # twice the signed area
+        n = len(p)
+        return sum(p[i][0] * p[(i + 1) % n][1] - p[(i + 1) % n][0] * p[i][1] for i in range(n))
+
+    a, b = F(qa), F(qb)
+    if area2(a) < 0:
+        a = a[::-1]
+    if area2(b) < 0:
+        b = b[::-1]
+    poly = a
+    for e in range(4):
+        if not poly:
+            break
+        (x0, y0), (x1, y1) = b[e], b[(e + 1) % 4]
+        dx, dy = x1 - x0, y1 - y0
+        side = [dx * (p[1] - y0) - dy * (p[0] - x0) for p in poly]
+        out = []
+        for i in range(len(poly)):
+            j = (i + 1) % len(poly)
+            if side[i] >= 0:
+                out.append(poly[i])
+            if (side[i] > 0 and side[j] < 0) or (side[i] < 0 and side[j] > 0):
+                t = side[i] / (side[i] - side[j])
+                out.append((poly[i][0] + t * (poly[j][0] - poly[i][0]), poly[i][1] + t * (poly[j][1] - poly[i][1])))
+        poly = out
+    inter = abs(area2(poly)) / 2 if len(poly) >= 3 else Fr(0)
+    union = abs(area2(a)) / 2 + abs(area2(b)) / 2 - inter
+    return inter / union if union > 0 else Fr(0)
+
+
+def _random_quad(rng):
+    q = sq(rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(0.5, 4), rng.uniform(0, math.pi))
+    q[:, 0] *= rng.uniform(0.5, 2.0)
+    return q
+
+
+def test_quad_iou_matches_exact_rational_clipping_on_random_quads():
+    rng = np.random.RandomState(11)
+    worst = 0.0
+    for k in range(1600):
+        a, b = _random_quad(rng), _random_quad(rng)
+        if k % 3 == 0:
+            b = b[::-1].copy()                                            # clockwise vertex order
+        if k % 50 == 0:
+            b = a.copy()                                                  # identical boxes -> exactly 1
+        if k % 70 == 0:
+            b = a + np.array([a[1, 0] - a[0, 0], a[1, 1] - a[0, 1]])      # sharing one edge -> exactly 0
+        if k % 90 == 0:
+            b = a * 0.5 + a.mean(0) * 0.5                                 # strictly nested
+        exact = _exact_iou(a, b)
+        got = float(pp.quad_intersection_area(a[None], b[None])[0])
+        union = float(pp._area(a[None])[0] + pp._area(b[None])[0]) - got
+        worst = max(worst, abs(got / union - float(exact)))
+        # the float32 value the NMS compares (postprocess.py:41: iou array is float32)
+        assert abs(float(pp.quad_iou(a, b[None])[0]) - float(np.float32(float(exact)))) <= 2e-7
+    assert worst < 1e-12, worst
+
+
+def test_quad_iou_around_the_nms_threshold():
+    """Adversarial cases at the 0.01 IoU threshold of apply_nms_det (detection_util.py:357-359 -> postprocess.py:106
+    ``iou > threshold``): two 2 x 4 boxes slid apart until their IoU is a hair above / below 0.01; the suppress
+    decision of the restated NMS must equal the decision made on the exact rational IoU (compared in float32, as the
+    reference's float32 iou array is)."""
+    thr = np.float32(0.01)
+    base = np.array([[-1.0, -2.0], [-1.0, 2.0], [1.0, 2.0], [1.0, -2.0]])
+    w, h = 2.0, 4.0
+    decided = 0
+    for ang in (0.0, 0.3, 1.1, math.pi / 4):
+        c, s = math.cos(ang), math.sin(ang)
+        rot = np.array([[c, -s], [s, c]])
+        a = base @ rot.T
+        # axis-aligned overlap of width d: IoU = d*h / (2*w*h - d*h) = thr  ->  d = 2*w*thr / (1 + thr)
+        d0 = 2 * w * 0.01 / 1.01
+        for rel in (-1e-3, -1e-5, -1e-7, -1e-9, 0.0, 1e-9, 1e-7, 1e-5, 1e-3):
+            d = d0 * (1 + rel)
+            b = (base + np.array([w - d, 0.0])) @ rot.T
+            exact = _exact_iou(a, b)
+            want = np.float32(float(exact)) > thr
+            got32 = pp.quad_iou(a, b[None])[0]
+            assert abs(float(got32) - float(exact)) < 1e-9
+            # the float64 IoU is within 1e-12 of the exact one, so both round to the same float32 (unless the exact value
+            # sat within 1e-12 of a float32 rounding boundary, which none of these do): the decisions must agree
+            assert got32 == np.float32(float(exact)), (ang, rel, float(exact), float(got32))
+            assert bool(got32 > thr) == bool(want)
+            boxes = np.stack([a, b]).astype(np.float64)
+            keep = pp.non_max_suppression(boxes, np.array([0.9, 0.8], dtype=np.float32), 0.01)
+            assert (len(keep) == 1) == bool(want)
+            decided += int(bool(want))
+    assert 12 <= decided <= 24     # both sides of the threshold were exercised

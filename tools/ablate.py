@@ -23,7 +23,7 @@ def time_launches(plan, iters=5):
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-    planes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    planes = sys.argv[2] if len(sys.argv) > 2 else "bf16"   # precision mode name
     lib = _lib.load()
     sd = synth.v2vnet_det_state(0)
     bevs, trans, nat = synth.make_scene(B, 5, 0)
@@ -40,7 +40,7 @@ def main():
         fl = getattr(plan.launches[i], "flops", 0.0)
         print("%-8s %9.0f %9.0f %9.0f %9.0f %9.0f %9.0f   %6.1f %7.0f" % (name, res["full"][i], res["noMMA"][i], res["noTMA"][i], res["noST"][i], res["noEPI"][i], res["full2"][i], fl / 1e9, fl / (res["full"][i] * 1e-6) / 1e12 if fl else 0))
     print("total", {k: round(sum(v)) for k, v in res.items()})
-    json.dump({"names": NAMES, "us": res}, open(os.path.join(ROOT, "gpurun_out", "ablate_B%d_P%d.json" % (B, planes)), "w"))
+    json.dump({"names": NAMES, "us": res}, open(os.path.join(ROOT, "gpurun_out", "ablate_B%d_%s.json" % (B, planes)), "w"))
 
 if __name__ == "__main__":
     main()

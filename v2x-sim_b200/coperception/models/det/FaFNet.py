@@ -27,6 +27,9 @@ class FaFNet(B200DetModel):
         result = plan.forward(bevs.to(torch.float32))
         if self.kd_flag == 1:
             # (result, x_8, x_7, x_6, x_5, x_3) as FaFNet.py:36-37; x_7/x_6/x_5 are stored 2x-upsampled
-            f = {k: ops.act_to_float(plan.ws[k]) for k in ("x8", "x7u", "x6u", "x5u", "x3")}
-            return result, f["x8"], f["x7u"][:, :, ::2, ::2], f["x6u"][:, :, ::2, ::2], f["x5u"][:, :, ::2, ::2], f["x3"]
+            # x_3 is encoded_layers[3], i.e. AFTER com_compresser / com_decompresser when compress_level > 0
+            # (Backbone.py:138-141): the workspace holds that map as "x3d"
+            x3 = "x3d" if "x3d" in plan.ws else "x3"
+            f = {k: ops.act_to_float(plan.ws[k]) for k in ("x8", "x7u", "x6u", "x5u", x3)}
+            return result, f["x8"], f["x7u"][:, :, ::2, ::2], f["x6u"][:, :, ::2, ::2], f["x5u"][:, :, ::2, ::2], f[x3]
         return result

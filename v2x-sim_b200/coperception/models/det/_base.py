@@ -1,19 +1,144 @@
 """Shared host logic of the drop-in detection modules: plan cache, precision mode, input staging."""
+import functools
 import os
+import warnings
 
 import torch
 import torch.nn as nn
 
 from ._schema import ClassificationHead, SingleRegressionHead, check_config
 
-_PLANES = {"bf16": 1, "bf16x3": 2}
+
+def on_input_device(forward):
+    """Run a module forward with the CUDA device of its first CUDA tensor argument current: plan construction, graph
+    capture and every launch then use that device's streams / kernels even when the caller's current device differs
+    (a model on cuda:1 called while cuda:0 is current; DataParallel replicas)."""
+    @functools.wraps(forward)
+    def wrapped(self, *args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                with torch.cuda.device(a.device):
+                    return forward(self, *args, **kwargs)
+        return forward(self, *args, **kwargs)
+    return wrapped
 
 
-class B200DetModel(nn.Module):
+class PlanCacheMixin:
+    """Plan cache shared by the det and seg drop-in modules.
+
+    Packed sm_100a operands are caches derived from the nn.Parameters.  They are rebuilt on ``load_state_dict``,
+    ``.to()/.cuda()/.half()`` (``_apply``) and ``train()/eval()``, and -- because every plan key carries a fingerprint of
+    the parameters' and buffers' (storage pointer, in-place version counter) -- also after any in-place edit that torch
+    tracks (``p.copy_`` / ``p.add_`` under no_grad, ``torch.nn.init.*``, optimizer steps, EMA / teacher sync).  Edits made
+    through ``p.data`` bypass the version counter: call ``invalidate()`` after them, or set ``model.verify_weights = True``
+    (env V2X_VERIFY_WEIGHTS=1) to add a checksum of the values to the fingerprint (costs a host sync per forward).
+
+    Outputs: a plan writes into static buffers that the next forward overwrites.  The modules therefore return CLONES
+    (fresh tensors, like the reference); set ``model.alias_outputs = True`` to get the static buffers themselves and
+    save the copy (the throughput benchmark does) -- then consume a result before the next forward."""
+
+    def __init_subclass__(cls, **kw):
+        # every forward a subclass defines runs on its inputs' device and hands back fresh tensors (see ``_out``)
+        super().__init_subclass__(**kw)
+        for name in ("forward", "forward_voxels"):
+            fn = cls.__dict__.get(name)
+            if fn is not None and not getattr(fn, "_v2x_wrapped", False):
+                dev_fn = on_input_device(fn)
+
+                @functools.wraps(fn)
+                def wrapped(self, *a, _dev_fn=dev_fn, **k):
+                    return self._out(_dev_fn(self, *a, **k))
+                wrapped._v2x_wrapped = True
+                setattr(cls, name, wrapped)
+
+    def _init_plan_cache(self):
+        from v2x_b200 import precision
+        self.precision = precision.DEFAULT      # "mixed" | "fp16x3" | "bf16" (v2x_b200/precision.py); env V2X_PRECISION
+        self.use_cuda_graph = os.environ.get("V2X_CUDA_GRAPH", "1") != "0"
+        self.alias_outputs = False
+        self.verify_weights = os.environ.get("V2X_VERIFY_WEIGHTS", "0") == "1"
+        self._plans = {}
+        self._static_ptrs = set()     # data_ptr of every plan's static output buffers
+        self._warned_grad = False
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self):
+        self._plans = {}
+        self._static_ptrs = set()
+
+    def train(self, mode=True):
+        self.invalidate()
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def _planes(self):
+        """The precision mode handed to the plans (they accept a Precision wherever they take ``planes``)."""
+        from v2x_b200 import precision
+        return precision.resolve(self.precision)
+
+    def _fingerprint(self):
+        ts = list(self.parameters()) + list(self.buffers())
+        fp = 0
+        for t in ts:
+            fp = (fp * 1000003 + t.data_ptr() + 7919 * t._version) & 0xFFFFFFFFFFFF
+        if self.verify_weights:
+            # edits made through ``p.data`` bypass torch's version counters: opt-in checksum of the values themselves
+            # (one fused norm over all tensors + a host sync per forward -- a debugging aid, not for the hot loop)
+            fl = [t.detach().float() for t in ts if t.is_floating_point()]
+            norms = torch.stack(torch._foreach_norm(fl)).double()
+            w = torch.arange(1, norms.numel() + 1, device=norms.device, dtype=torch.float64)
+            fp ^= hash(round(float((norms * w).sum().item()), 9))
+        return fp
+
+    def _warn_no_grad_graph(self):
+        if not self._warned_grad and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            self._warned_grad = True
+            warnings.warn("%s: the sm_100a forward is computed by custom kernels and its outputs carry no autograd graph; "
+                          "call it under torch.no_grad() (training through this path is not built)" % type(self).__name__,
+                          stacklevel=3)
+
+    def _state(self):
+        return {k: v.detach() for k, v in self.state_dict().items()}
+
+    def _get_plan(self, key, factory):
+        fp = self._fingerprint()
+        hit = self._plans.get(key)
+        if hit is not None and hit[0] == fp:
+            return hit[1]
+        plan = factory()
+        if self.use_cuda_graph:
+            plan.capture()
+        self._plans[key] = (fp, plan)
+        for name in ("loc", "cls", "logits"):
+            t = getattr(plan, name, None)
+            if isinstance(t, torch.Tensor):
+                self._static_ptrs.add(t.data_ptr())
+        return plan
+
+    def _plan_list(self):
+        return [p for _, p in self._plans.values()]
+
+    def _out(self, result):
+        """Replace every returned tensor that aliases a plan's static output buffer by a clone (unless ``alias_outputs``)."""
+        if self.alias_outputs or result is None:
+            return result
+        if isinstance(result, dict):
+            return {k: self._out(v) for k, v in result.items()}
+        if isinstance(result, (tuple, list)):
+            return type(result)(self._out(v) for v in result)
+        if isinstance(result, torch.Tensor) and result.data_ptr() in self._static_ptrs:
+            return result.clone()
+        return result
+
+
+class B200DetModel(PlanCacheMixin, nn.Module):
     """nn.Module surface of DetModelBase (CP/models/det/base/DetModelBase.py:26-51) whose forward runs on
-    libv2x_b200.so.  ``precision``: "bf16" (default; activations/weights stored in bf16, fp32 accumulate)
-    or "bf16x3" (hi/lo split operands, 3 MMAs, ~fp32-grade parity) -- also settable through the
-    V2X_PRECISION environment variable."""
+    libv2x_b200.so.  ``precision``: "mixed" (default: fp16 hi/lo activations, per-layer 1-3 tensor-core passes,
+    inside the 1e-3 parity contract), "fp16x3" (3 passes everywhere, ~1e-5) or "bf16" (one bf16 plane, ~2e-2, the
+    raw-throughput mode) -- see v2x_b200/precision.py; the default is also settable through V2X_PRECISION."""
 
     def __init__(self, config, layer=3, in_channels=13, kd_flag=True, p_com_outage=0.0, num_agent=5, only_v2i=False):
         super().__init__()
@@ -31,44 +156,11 @@ class B200DetModel(nn.Module):
         self.layer = layer
         self.p_com_outage = p_com_outage
         self.only_v2i = only_v2i
-        self.precision = os.environ.get("V2X_PRECISION", "bf16")
-        self.use_cuda_graph = os.environ.get("V2X_CUDA_GRAPH", "1") != "0"
-        self._plans = {}
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
-
-    # packed operands are caches derived from the nn.Parameters
-    def invalidate(self):
-        self._plans = {}
-
-    def train(self, mode=True):
-        self.invalidate()
-        return super().train(mode)
-
-    def _apply(self, fn, *a, **k):
-        self.invalidate()
-        return super()._apply(fn, *a, **k)
-
-    def _planes(self):
-        if self.precision not in _PLANES:
-            raise ValueError("precision must be one of %s" % list(_PLANES))
-        return _PLANES[self.precision]
+        self._init_plan_cache()
 
     def _check_eval(self):
         if self.training:
             raise NotImplementedError(
                 "the sm_100a path implements inference (model.eval()); the training/backward step "
                 "(SURVEY.md section 8(f1)) is not built yet")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            pass  # outputs are produced by custom kernels and carry no autograd graph
-
-    def _state(self):
-        return {k: v.detach() for k, v in self.state_dict().items()}
-
-    def _get_plan(self, key, factory):
-        plan = self._plans.get(key)
-        if plan is None:
-            plan = factory()
-            if self.use_cuda_graph:
-                plan.capture()
-            self._plans[key] = plan
-        return plan
+        self._warn_no_grad_graph()

@@ -8,7 +8,7 @@ import os
 import torch
 import torch.nn as nn
 
-_PLANES = {"bf16": 1, "bf16x3": 2}
+from ..det._base import PlanCacheMixin
 
 
 class DoubleConv(nn.Module):
@@ -38,7 +38,7 @@ class OutConv(nn.Module):
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
 
 
-class SegModelBase(nn.Module):
+class SegModelBase(PlanCacheMixin, nn.Module):
     def __init__(self, n_channels, n_classes, bilinear=True, num_agent=5, compress_level=0, only_v2i=False):
         super().__init__()
         if not bilinear:
@@ -56,39 +56,11 @@ class SegModelBase(nn.Module):
             self.bn_compress = nn.BatchNorm2d(cc)
             self.com_decompresser = nn.Conv2d(cc, 512, kernel_size=1, stride=1)
             self.bn_decompress = nn.BatchNorm2d(512)
-        self.precision = os.environ.get("V2X_PRECISION", "bf16")
-        self.use_cuda_graph = os.environ.get("V2X_CUDA_GRAPH", "1") != "0"
-        self._plans = {}
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
-
-    def invalidate(self):
-        self._plans = {}
-
-    def train(self, mode=True):
-        self.invalidate()
-        return super().train(mode)
-
-    def _apply(self, fn, *a, **k):
-        self.invalidate()
-        return super()._apply(fn, *a, **k)
-
-    def _planes(self):
-        return _PLANES[self.precision]
+        self._init_plan_cache()
 
     def _check(self, x):
         if self.training:
             raise NotImplementedError("the sm_100a path implements inference (model.eval()); training is not built yet")
+        self._warn_no_grad_graph()
         if x.device.type != "cuda":
             raise RuntimeError("v2x_b200 seg models need CUDA tensors (no CPU fallback); got %s" % x.device)
-
-    def _state(self):
-        return {k: v.detach() for k, v in self.state_dict().items()}
-
-    def _get_plan(self, key, factory):
-        plan = self._plans.get(key)
-        if plan is None:
-            plan = factory()
-            if self.use_cuda_graph:
-                plan.capture()
-            self._plans[key] = plan
-        return plan

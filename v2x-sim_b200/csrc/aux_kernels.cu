@@ -7,14 +7,17 @@
 namespace v2x {
 
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  // per DEVICE (a process may drive several GPUs; cudaGetDevice follows the caller's torch.cuda.device guard)
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev & 63;
+  if (n[slot] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[slot] = v > 0 ? v : 148;
   }
-  return n;
+  return n[slot];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -34,11 +37,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
       const int c0 = g * 8 + 2 * i;
       const float v0 = c0 < c ? __ldg(x + pix * c + c0) : 0.f;
       const float v1 = c0 + 1 < c ? __ldg(x + pix * c + c0 + 1) : 0.f;
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v0, h0, l0);
-      split_bf16(v1, h1, l1);
-      hi[i] = pack_bf16x2(h0, h1);
-      lo[i] = pack_bf16x2(l0, l1);
+      act_pack2(v0, v1, planes, hi[i], lo[i]);
     }
     __nv_bfloat16* dst = out + pix * c_pad + g * 8;
     *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -72,11 +71,7 @@ __global__ void __launch_bounds__(256) pack_input13_kernel(const float* __restri
       const int c0 = g * 8 + 2 * i;
       const float v0 = c0 < 13 ? sp[2 * i] : 0.f;
       const float v1 = c0 + 1 < 13 ? sp[2 * i + 1] : 0.f;
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v0, h0, l0);
-      split_bf16(v1, h1, l1);
-      hi[i] = pack_bf16x2(h0, h1);
-      lo[i] = pack_bf16x2(l0, l1);
+      act_pack2(v0, v1, planes, hi[i], lo[i]);
     }
     __nv_bfloat16* dst = out + (pix0 + pix) * 16 + g * 8;
     *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -98,7 +93,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout,
                                     int cin_total, int taps, int ci_lo, int ci_hi, int cin_pad, int vflip, int gates,
-                                    __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_bias, int planes,
+                                    uint16_t* __restrict__ dst, float* __restrict__ dst_bias, int planes,
                                     int cout_pad, int k_total, int row_off, int k_off, int write_bias) {
   const int cin = ci_hi - ci_lo;
   const long long total = (long long)cout * cin * taps;
@@ -113,8 +108,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
     if (vflip && taps == 9) tp = (2 - tap / 3) * 3 + tap % 3;
     const int row = row_off + gru_perm(co, gates, cout);
     const long long k = (long long)k_off + (long long)tp * cin_pad + ci;
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
+    uint16_t hi, lo;
+    act_split1(v, planes, hi, lo);   // planes = storage format: 1 bf16, 2 fp16 hi/lo, 3 fp16 hi only
     dst[(long long)row * k_total + k] = hi;
     if (planes == 2) dst[((long long)cout_pad + row) * k_total + k] = lo;
     if (write_bias && ci == 0 && tap == 0) {
@@ -229,15 +224,11 @@ __global__ void __launch_bounds__(256) warp_mean_kernel(const __nv_bfloat16* __r
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q[t]);
-              const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql[t]);
+              const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&q[t]);
+              const uint32_t* l2 = reinterpret_cast<const uint32_t*>(&ql[t]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float2 f = __bfloat1622float2(h2[e]);
-                if (PLANES == 2) {
-                  const float2 g = __bfloat1622float2(l2[e]);
-                  f.x += g.x; f.y += g.y;
-                }
+                const float2 f = act_unpack2<PLANES>(h2[e], PLANES == 2 ? l2[e] : 0u);
                 acc[v][2 * e] += wgt[t] * f.x;
                 acc[v][2 * e + 1] += wgt[t] * f.y;
               }
@@ -255,11 +246,7 @@ __global__ void __launch_bounds__(256) warp_mean_kernel(const __nv_bfloat16* __r
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(acc[v][2 * e] * inv, h0, l0);
-          split_bf16(acc[v][2 * e + 1] * inv, h1, l1);
-          hi[e] = pack_bf16x2(h0, h1);
-          lo[e] = pack_bf16x2(l0, l1);
+          act_pack2<PLANES>(acc[v][2 * e] * inv, acc[v][2 * e + 1] * inv, hi[e], lo[e]);
         }
         *reinterpret_cast<uint4*>(dp + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         if (PLANES == 2) *reinterpret_cast<uint4*>(dp + out_plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -279,9 +266,7 @@ __global__ void act_to_nchw_kernel(const __nv_bfloat16* __restrict__ act, float*
     const int ch = (int)((gid / ((long long)w * h)) % c);
     const int im = (int)(gid / ((long long)w * h * c));
     const long long src = (((long long)im * h + y) * w + x) * c + ch;
-    float v = __bfloat162float(act[src]);
-    if (planes == 2) v += __bfloat162float(act[src + total]);
-    out[gid] = v;
+    out[gid] = act_load1(act + src, total, planes);
   }
 }
 
@@ -324,7 +309,7 @@ extern "C" int v2x_pack_conv_weights(const float* w, const float* b, const float
   V2X_REQUIRE(w && dst, "null weights/dst");
   V2X_REQUIRE(cout > 0 && taps > 0 && 0 <= ci_lo && ci_lo < ci_hi && ci_hi <= cin_total, "bad channel range");
   V2X_REQUIRE(cin_pad >= ci_hi - ci_lo, "cin_pad too small");
-  V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  V2X_REQUIRE(planes >= 1 && planes <= 3, "format must be V2X_FMT_BF16 (1), V2X_FMT_F16X2 (2) or V2X_FMT_F16 (3)");
   V2X_REQUIRE(row_off >= 0 && row_off + cout <= cout_pad, "rows out of range");
   V2X_REQUIRE(k_off >= 0 && k_off + taps * cin_pad <= k_total, "k range out of bounds");
   V2X_REQUIRE(!bn_gamma || (bn_beta && bn_mean && bn_var), "incomplete BN parameters");
@@ -333,7 +318,7 @@ extern "C" int v2x_pack_conv_weights(const float* w, const float* b, const float
   const long long total = (long long)cout * (ci_hi - ci_lo) * taps;
   pack_weights_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       w, b, bn_gamma, bn_beta, bn_mean, bn_var, eps, cout, cin_total, taps, ci_lo, ci_hi, cin_pad, vflip, gru_gates,
-      reinterpret_cast<__nv_bfloat16*>(dst), dst_bias, planes, cout_pad, k_total, row_off, k_off, write_bias);
+      reinterpret_cast<uint16_t*>(dst), dst_bias, planes, cout_pad, k_total, row_off, k_off, write_bias);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }
@@ -416,8 +401,7 @@ __global__ void linear_kernel(const void* __restrict__ x, const float* __restric
     for (int i = lane; i < in_f; i += 32) {
       const int ch = ch_base + i / hw, px = i % hw;
       const long long idx = ((long long)map * hw + px) * c + ch;
-      float v = __bfloat162float(xa[idx]);
-      if (planes == 2) v += __bfloat162float(xa[idx + plane_stride]);
+      const float v = act_load1(xa + idx, plane_stride, planes);
       acc = fmaf(__ldg(wr + i), v, acc);
     }
   }
@@ -541,17 +525,13 @@ __global__ void warp_gated_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
           const int c0 = (v * 32 + lane) * 8;
           if (c0 < C) {
             uint4 qv = __ldg(reinterpret_cast<const uint4*>(sp + c0));
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+            const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&qv);
             uint4 ql = make_uint4(0, 0, 0, 0);
             if (planes == 2) ql = __ldg(reinterpret_cast<const uint4*>(sp + plane_stride + c0));
-            const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql);
+            const uint32_t* l2 = reinterpret_cast<const uint32_t*>(&ql);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float2 f = __bfloat1622float2(h2[e]);
-              if (planes == 2) {
-                const float2 g = __bfloat1622float2(l2[e]);
-                f.x += g.x; f.y += g.y;
-              }
+              const float2 f = act_unpack2(h2[e], l2[e], planes);
               acc[v][2 * e] += wgt * f.x;
               acc[v][2 * e + 1] += wgt * f.y;
             }
@@ -567,11 +547,7 @@ __global__ void warp_gated_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(acc[v][2 * e], h0, l0);
-          split_bf16(acc[v][2 * e + 1], h1, l1);
-          hi[e] = pack_bf16x2(h0, h1);
-          lo[e] = pack_bf16x2(l0, l1);
+          act_pack2(acc[v][2 * e], acc[v][2 * e + 1], planes, hi[e], lo[e]);
         }
         *reinterpret_cast<uint4*>(dp + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         if (planes == 2) *reinterpret_cast<uint4*>(dp + plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -659,46 +635,12 @@ __global__ void pack_input_nchw_kernel(const float* __restrict__ x, __nv_bfloat1
       const int c0 = g * 8 + 2 * i;
       const float v0 = c0 < c ? __ldg(x + ((long long)im * c + c0) * hw + pix) : 0.f;
       const float v1 = c0 + 1 < c ? __ldg(x + ((long long)im * c + c0 + 1) * hw + pix) : 0.f;
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v0, h0, l0);
-      split_bf16(v1, h1, l1);
-      hi[i] = pack_bf16x2(h0, h1);
-      lo[i] = pack_bf16x2(l0, l1);
+      act_pack2(v0, v1, planes, hi[i], lo[i]);
     }
     __nv_bfloat16* dst = out + ((long long)im * hw + pix) * c_pad + g * 8;
     *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (planes == 2) *reinterpret_cast<uint4*>(dst + (long long)n * hw * c_pad) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
-}
-
-__device__ __forceinline__ void load8(const __nv_bfloat16* p, long long plane_stride, int planes, float* v) {
-  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
-  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-  uint4 ql = make_uint4(0, 0, 0, 0);
-  if (planes == 2) ql = __ldg(reinterpret_cast<const uint4*>(p + plane_stride));
-  const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float2 f = __bfloat1622float2(h2[e]);
-    if (planes == 2) {
-      const float2 g = __bfloat1622float2(l2[e]);
-      f.x += g.x; f.y += g.y;
-    }
-    v[2 * e] = f.x; v[2 * e + 1] = f.y;
-  }
-}
-__device__ __forceinline__ void store8(__nv_bfloat16* p, long long plane_stride, int planes, const float* v) {
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v[2 * e], h0, l0);
-    split_bf16(v[2 * e + 1], h1, l1);
-    hi[e] = pack_bf16x2(h0, h1);
-    lo[e] = pack_bf16x2(l0, l1);
-  }
-  *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  if (planes == 2) *reinterpret_cast<uint4*>(p + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // nn.MaxPool2d(2) (SegModelBase.py:113): act [n][2h][2w][c] -> [n][h][w][c]
@@ -714,17 +656,17 @@ __global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
     const int ox = (int)(pix % w), oy = (int)((pix / w) % h), im = (int)(pix / ((long long)w * h));
     float m[8], v[8];
     const __nv_bfloat16* base = x + (((long long)im * 2 * h + 2 * oy) * 2 * w + 2 * ox) * c + g * 8;
-    load8(base, in_plane, planes, m);
-    load8(base + c, in_plane, planes, v);
+    act_load8(base, in_plane, planes, m);
+    act_load8(base + c, in_plane, planes, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
-    load8(base + (long long)2 * w * c, in_plane, planes, v);
+    act_load8(base + (long long)2 * w * c, in_plane, planes, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
-    load8(base + (long long)2 * w * c + c, in_plane, planes, v);
+    act_load8(base + (long long)2 * w * c + c, in_plane, planes, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
-    store8(out + pix * c + g * 8, out_plane, planes, m);
+    act_store8(out + pix * c + g * 8, out_plane, planes, m);
   }
 }
 
@@ -749,14 +691,14 @@ __global__ void upsample_bilinear2_kernel(const __nv_bfloat16* __restrict__ x, _
     const float wy1 = fy - (float)y0, wx1 = fx - (float)x0, wy0 = 1.f - wy1, wx0 = 1.f - wx1;
     const __nv_bfloat16* b = x + (long long)im * h * w * c + g * 8;
     float a00[8], a01[8], a10[8], a11[8], r[8];
-    load8(b + ((long long)y0 * w + x0) * c, in_plane, planes, a00);
-    load8(b + ((long long)y0 * w + x1) * c, in_plane, planes, a01);
-    load8(b + ((long long)y1 * w + x0) * c, in_plane, planes, a10);
-    load8(b + ((long long)y1 * w + x1) * c, in_plane, planes, a11);
+    act_load8(b + ((long long)y0 * w + x0) * c, in_plane, planes, a00);
+    act_load8(b + ((long long)y0 * w + x1) * c, in_plane, planes, a01);
+    act_load8(b + ((long long)y1 * w + x0) * c, in_plane, planes, a10);
+    act_load8(b + ((long long)y1 * w + x1) * c, in_plane, planes, a11);
 #pragma unroll
     for (int e = 0; e < 8; ++e)  // same association as ATen's upsample_bilinear2d: rows first, then columns
       r[e] = wy0 * (wx0 * a00[e] + wx1 * a01[e]) + wy1 * (wx0 * a10[e] + wx1 * a11[e]);
-    store8(out + pix * c + g * 8, out_plane, planes, r);
+    act_store8(out + pix * c + g * 8, out_plane, planes, r);
   }
 }
 

@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -30,7 +31,12 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// bf16 split precision: x ~= hi + lo, both bf16 (about 16 mantissa bits together)
+// Storage formats of act / packed-weight tensors (include/v2x_b200.h):
+//   planes == 1 (V2X_FMT_BF16)  : one bf16 plane
+//   planes == 2 (V2X_FMT_F16X2) : x ~= hi + lo, two fp16 planes (about 22 mantissa bits together); hi saturates at the
+//                                 largest finite fp16 instead of overflowing to inf
+//   V2X_FMT_F16 (3, packed weights only): the hi plane alone
+// Elements are addressed as 16-bit units whatever the format (the kernels keep __nv_bfloat16* as "a 16-bit element").
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
@@ -39,6 +45,90 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// two fp32 -> packed fp16x2 (a in the low half), round-to-nearest-even, saturating to +-65504
+__device__ __forceinline__ uint32_t f16x2_sat(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ float2 f16x2_to_float2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+
+// (a, b) -> packed pair(s) in the storage format of a `planes`-plane tensor; lo is only meaningful for planes == 2
+template <int PLANES>
+__device__ __forceinline__ void act_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (PLANES == 2) {
+    hi = f16x2_sat(a, b);
+    const float2 h = f16x2_to_float2(hi);
+    lo = f16x2_sat(a - h.x, b - h.y);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = 0u;
+  }
+}
+__device__ __forceinline__ void act_pack2(float a, float b, int planes, uint32_t& hi, uint32_t& lo) {
+  if (planes == 2) act_pack2<2>(a, b, hi, lo);
+  else act_pack2<1>(a, b, hi, lo);
+}
+template <int PLANES>
+__device__ __forceinline__ float2 act_unpack2(uint32_t hi, uint32_t lo) {
+  if (PLANES == 2) {
+    float2 f = f16x2_to_float2(hi);
+    const float2 g = f16x2_to_float2(lo);
+    f.x += g.x; f.y += g.y;
+    return f;
+  }
+  return bf16x2_to_float2(hi);
+}
+__device__ __forceinline__ float2 act_unpack2(uint32_t hi, uint32_t lo, int planes) {
+  return planes == 2 ? act_unpack2<2>(hi, lo) : act_unpack2<1>(hi, lo);
+}
+// one element of a `planes`-plane tensor (lo plane `plane_stride` elements after the hi plane)
+__device__ __forceinline__ float act_load1(const __nv_bfloat16* p, long long plane_stride, int fmt) {
+  if (fmt == 2)
+    return __half2float(*reinterpret_cast<const __half*>(p)) + __half2float(*reinterpret_cast<const __half*>(p + plane_stride));
+  if (fmt == 3) return __half2float(*reinterpret_cast<const __half*>(p));   // the hi plane alone
+  return __bfloat162float(*p);
+}
+// one value -> the 16-bit storage element(s)
+__device__ __forceinline__ void act_split1(float x, int fmt, uint16_t& hi, uint16_t& lo) {
+  if (fmt == 1) {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi = __bfloat16_as_ushort(h);
+    lo = 0;
+  } else {
+    const uint32_t h = f16x2_sat(x, 0.f);
+    hi = (uint16_t)(h & 0xFFFFu);
+    const float hf = f16x2_to_float2(h).x;
+    lo = (uint16_t)(f16x2_sat(x - hf, 0.f) & 0xFFFFu);
+  }
+}
+// 8 consecutive channels (16 bytes per plane) <-> fp32
+__device__ __forceinline__ void act_load8(const __nv_bfloat16* p, long long plane_stride, int planes, float* v) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  uint4 ql = make_uint4(0, 0, 0, 0);
+  if (planes == 2) ql = __ldg(reinterpret_cast<const uint4*>(p + plane_stride));
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(&q);
+  const uint32_t* l = reinterpret_cast<const uint32_t*>(&ql);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = act_unpack2(h[e], l[e], planes);
+    v[2 * e] = f.x; v[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void act_store8(__nv_bfloat16* p, long long plane_stride, int planes, const float* v) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) act_pack2(v[2 * e], v[2 * e + 1], planes, hi[e], lo[e]);
+  *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (planes == 2) *reinterpret_cast<uint4*>(p + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -215,6 +305,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // kind::f16 instruction descriptor: bf16 A/B (K-major), fp32 accumulate, M = 128
 __host__ __device__ constexpr uint32_t make_idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// same with fp16 A/B (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16_m128(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// operand format follows the storage format: 1 plane = bf16, 2 planes = fp16 hi/lo
+template <int PLANES>
+__host__ __device__ constexpr uint32_t make_idesc_m128(uint32_t n) {
+  return PLANES == 2 ? make_idesc_f16_m128(n) : make_idesc_bf16_m128(n);
 }
 
 }  // namespace v2x

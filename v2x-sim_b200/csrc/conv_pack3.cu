@@ -22,6 +22,8 @@
 //              memory for the CTA's lifetime.
 //   Persistent, warp-specialised like conv_tc_kernel: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue,
 //   two TMEM accumulators (2 x 128 columns), two co-resident CTAs per SM when the operands fit.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace v2x {
@@ -60,15 +62,18 @@ __device__ __forceinline__ uint4 p3_ld_shared_v4(uint32_t addr) {
 
 constexpr uint32_t kP3StagePlane = 32u * 64u;   // one warp's 32 pixels x 32 bf16 channels
 
-template <int PLANES, int KSTEPS>
+template <int PLANES, int MMAS, int KSTEPS>
 __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
     conv_pack3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB, const Pack3Dev p) {
   constexpr int KC = 16 * KSTEPS;
+  // operand planes actually read (see conv_tc.cuh): MMAS = 3 both split, 2 activations split only, 1 hi planes only
+  constexpr int PA = (PLANES == 2 && MMAS >= 2) ? 2 : 1;
+  constexpr int PW = (PLANES == 2 && MMAS == 3) ? 2 : 1;
   constexpr uint32_t ROW = KC * 2u;                                     // bytes of one pixel's channel block
   constexpr uint32_t A_BOX = (uint32_t)(kP3HaloH * kP3HaloW) * ROW;     // 160 halo pixels (multiple of 1 KB)
   constexpr uint32_t B_TILE = (uint32_t)kP3N * ROW;                     // 96 weight rows (multiple of 1 KB)
-  constexpr uint32_t STAGE = PLANES * A_BOX;
+  constexpr uint32_t STAGE = PA * A_BOX;
   constexpr uint32_t SBO = 8u * ROW;
   constexpr uint32_t LAYOUT = KC == 64 ? 2u : KC == 32 ? 4u : 6u;
   constexpr uint32_t ACC_STRIDE = 128u, TMEM_COLS = 256u;
@@ -120,15 +125,15 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
     const bool no_tma = p.debug_mode == 2;
     if (elect_one()) {
       // resident weights: tile (cb_g, kh) at smem_base + ((cb_g * 3 + kh) * PLANES + pl) * B_TILE
-      mbar_expect_tx(bar_bres, (uint32_t)p.num_cb * 3u * PLANES * B_TILE);
+      mbar_expect_tx(bar_bres, (uint32_t)p.num_cb * 3u * PW * B_TILE);
       for (int cbg = 0; cbg < p.num_cb; ++cbg) {
         const int s = cbg < p.cblocks[0] ? 0 : 1;
         const int cb = cbg - s * p.cblocks[0];
         for (int kh = 0; kh < 3; ++kh) {
           const int kcol = (s ? 3 * total_cin0 : 0) + kh * p.cin[s] + cb * KC;
 #pragma unroll
-          for (int pl = 0; pl < PLANES; ++pl)
-            tma_load_2d(smem_base + (uint32_t)((cbg * 3 + kh) * PLANES + pl) * B_TILE, &tmB, bar_bres, kcol,
+          for (int pl = 0; pl < PW; ++pl)
+            tma_load_2d(smem_base + (uint32_t)((cbg * 3 + kh) * PW + pl) * B_TILE, &tmB, bar_bres, kcol,
                         (pl * p.groups + grp) * kP3N);
         }
       }
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
             mbar_expect_tx(full, STAGE);
             const uint32_t sa = ring_base + (uint32_t)stage * STAGE;
 #pragma unroll
-            for (int pl = 0; pl < PLANES; ++pl)
+            for (int pl = 0; pl < PA; ++pl)
               tma_load_4d(sa + pl * A_BOX, s ? &tmA1 : &tmA0, full, cb * KC, ow0 - 1, oh0 - 1, pl * p.n_maps + img);
           }
         }
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_bf16_m128(kP3N);
+    constexpr uint32_t idesc = make_idesc_m128<PLANES>(kP3N);
     const bool no_mma = p.debug_mode == 1;
     mbar_wait(bar_bres, 0);
     const uint64_t desc_ring = make_smem_desc(ring_base, SBO, LAYOUT);
@@ -182,18 +187,16 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
             mbar_arrive(bar_empty + 8 * stage);
           } else {
             const uint64_t da = desc_ring + (uint64_t)((uint32_t)stage * (STAGE >> 4));
-            const uint64_t db = desc_b + (uint64_t)((uint32_t)(cbg * 3 * PLANES) * (B_TILE >> 4));
+            const uint64_t db = desc_b + (uint64_t)((uint32_t)(cbg * 3 * PW) * (B_TILE >> 4));
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
               const uint32_t a_off = (uint32_t)(kh * kP3HaloW) * (ROW >> 4);
-              const uint32_t b_off = (uint32_t)(kh * PLANES) * (B_TILE >> 4);
+              const uint32_t b_off = (uint32_t)(kh * PW) * (B_TILE >> 4);
 #pragma unroll
               for (int kk = 0; kk < KSTEPS; ++kk) {
                 umma_bf16(tmem_d, da + (a_off + 2 * kk), db + (b_off + 2 * kk), idesc, (cbg | kh | kk) == 0 ? 0u : 1u);
-                if (PLANES == 2) {
-                  umma_bf16(tmem_d, da + (a_off + 2 * kk), db + (b_off + 2 * kk + (B_TILE >> 4)), idesc, 1u);
-                  umma_bf16(tmem_d, da + (a_off + 2 * kk + (A_BOX >> 4)), db + (b_off + 2 * kk), idesc, 1u);
-                }
+                if (PW == 2) umma_bf16(tmem_d, da + (a_off + 2 * kk), db + (b_off + 2 * kk + (B_TILE >> 4)), idesc, 1u);
+                if (PA == 2) umma_bf16(tmem_d, da + (a_off + 2 * kk + (A_BOX >> 4)), db + (b_off + 2 * kk), idesc, 1u);
               }
             }
             umma_commit(bar_empty + 8 * stage);
@@ -259,15 +262,7 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
         }
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const __nv_bfloat162 h = __floats2bfloat162_rn(y0[c16 * 16 + 2 * i], y0[c16 * 16 + 2 * i + 1]);
-          hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-          if (PLANES == 2) {
-            const float2 hf = __bfloat1622float2(h);
-            const __nv_bfloat162 l = __floats2bfloat162_rn(y0[c16 * 16 + 2 * i] - hf.x, y0[c16 * 16 + 2 * i + 1] - hf.y);
-            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-          }
-        }
+        for (int i = 0; i < 8; ++i) act_pack2<PLANES>(y0[c16 * 16 + 2 * i], y0[c16 * 16 + 2 * i + 1], hi[i], lo[i]);
         const uint32_t u0 = (((uint32_t)(2 * c16)) ^ ssw) << 4, u1 = (((uint32_t)(2 * c16 + 1)) ^ ssw) << 4;
         p3_st_shared_v4(srow + u0, hi[0], hi[1], hi[2], hi[3]);
         p3_st_shared_v4(srow + u1, hi[4], hi[5], hi[6], hi[7]);
@@ -303,12 +298,22 @@ __global__ void __launch_bounds__(kP3Threads, PLANES == 1 ? 2 : 1)
   }
 }
 
-template <int PLANES, int KSTEPS>
+template <int PLANES, int MMAS, int KSTEPS>
 static int launch_pack3_t(const Pack3Dev& d, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, size_t smem,
                           dim3 ctas, cudaStream_t stream) {
-  static cudaError_t attr_err = cudaFuncSetAttribute(conv_pack3_kernel<PLANES, KSTEPS>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_pack3_kernel)");
+  static std::mutex mu;       // function attributes are per device
+  static uint64_t done_mask = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!((done_mask >> (dev & 63)) & 1ull)) {
+      cudaError_t attr_err = cudaFuncSetAttribute(conv_pack3_kernel<PLANES, MMAS, KSTEPS>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_pack3_kernel)");
+      done_mask |= 1ull << (dev & 63);
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = ctas;
   cfg.blockDim = dim3(kP3Threads);
@@ -319,7 +324,7 @@ static int launch_pack3_t(const Pack3Dev& d, const CUtensorMap& a0, const CUtens
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  V2X_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_pack3_kernel<PLANES, KSTEPS>, a0, a1, b, d));
+  V2X_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_pack3_kernel<PLANES, MMAS, KSTEPS>, a0, a1, b, d));
   return V2X_OK;
 }
 
@@ -356,8 +361,11 @@ int launch_pack3(const v2x_conv_params* p, int debug_mode, cudaStream_t stream) 
   d.bias = p->bias;
   const uint32_t row = (uint32_t)kc * 2u;
   const uint32_t a_box = (uint32_t)(kP3HaloH * kP3HaloW) * row, b_tile = (uint32_t)kP3N * row;
-  const uint32_t stage = (uint32_t)p->planes * a_box;
-  d.b_region_bytes = (uint32_t)d.num_cb * 3u * p->planes * b_tile;
+  V2X_REQUIRE(p->mmas >= 0 && p->mmas <= 3 && (p->planes == 2 || p->mmas <= 1), "mmas must be 1..3 (0 = default), and > 1 only with planes == 2");
+  const int mmas = p->planes == 2 ? (p->mmas == 0 ? 3 : p->mmas) : 1;
+  const int pa = mmas >= 2 ? 2 : 1, pw = mmas == 3 ? 2 : 1;
+  const uint32_t stage = (uint32_t)pa * a_box;
+  d.b_region_bytes = (uint32_t)d.num_cb * 3u * pw * b_tile;
   const uint32_t epi = 4u * (uint32_t)p->planes * kP3StagePlane;
   // two co-resident CTAs per SM (bf16) when weights + >= 3 stages fit in half the shared memory
   int ctas_per_sm = 1;
@@ -385,7 +393,7 @@ int launch_pack3(const v2x_conv_params* p, int debug_mode, cudaStream_t stream) 
   if (d.nsrc == 1) tmA[1] = tmA[0];
   {
     const cuuint64_t k_total = 3ull * (cuuint64_t)(d.cin[0] + d.cin[1]);
-    cuuint64_t dims[2] = {k_total, (cuuint64_t)p->planes * d.groups * kP3N};
+    cuuint64_t dims[2] = {k_total, (cuuint64_t)pw * d.groups * kP3N};
     cuuint64_t str[1] = {k_total * 2};
     cuuint32_t box[2] = {(cuuint32_t)kc, kP3N};
     int rc = encode_map_shared(&tmB, p->weights, 2, dims, str, box, kc);
@@ -403,10 +411,12 @@ int launch_pack3(const v2x_conv_params* p, int debug_mode, cudaStream_t stream) 
   const int rounds = (d.m_tiles + ctas_x - 1) / ctas_x;
   ctas_x = (d.m_tiles + rounds - 1) / rounds;
   const dim3 ctas(ctas_x, d.groups);
-#define V2X_P3(KS_)                                                                              \
-  if (kc == 16 * KS_)                                                                            \
-    return p->planes == 1 ? launch_pack3_t<1, KS_>(d, tmA[0], tmA[1], tmB, smem, ctas, stream)   \
-                          : launch_pack3_t<2, KS_>(d, tmA[0], tmA[1], tmB, smem, ctas, stream);
+#define V2X_P3(KS_)                                                                                  \
+  if (kc == 16 * KS_)                                                                                \
+    return p->planes == 1 ? launch_pack3_t<1, 1, KS_>(d, tmA[0], tmA[1], tmB, smem, ctas, stream)    \
+           : mmas == 3    ? launch_pack3_t<2, 3, KS_>(d, tmA[0], tmA[1], tmB, smem, ctas, stream)    \
+           : mmas == 2    ? launch_pack3_t<2, 2, KS_>(d, tmA[0], tmA[1], tmB, smem, ctas, stream)    \
+                          : launch_pack3_t<2, 1, KS_>(d, tmA[0], tmA[1], tmB, smem, ctas, stream);
   V2X_P3(1) V2X_P3(2) V2X_P3(4)
 #undef V2X_P3
   set_error("tap_pack: no instantiation for kc %d", kc);

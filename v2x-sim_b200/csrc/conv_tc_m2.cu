@@ -1,0 +1,6 @@
+// Instantiations of conv_tc_kernel for storage planes = 2, MMA passes per k-step = 2 (see conv_tc.cuh).
+#include "conv_tc.cuh"
+
+namespace v2x {
+int conv_dispatch_m2(V2X_CONV_DISPATCH_ARGS) { return conv_dispatch<2, 2>(d, bn, a0, a1, b, t, smem, stream); }
+}  // namespace v2x

@@ -70,15 +70,11 @@ __device__ __forceinline__ bool gather_bilinear(const __nv_bfloat16* __restrict_
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q[t]);
-        const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql[t]);
+        const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&q[t]);
+        const uint32_t* l2 = reinterpret_cast<const uint32_t*>(&ql[t]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float2 f = __bfloat1622float2(h2[e]);
-          if (planes == 2) {
-            const float2 g = __bfloat1622float2(l2[e]);
-            f.x += g.x; f.y += g.y;
-          }
+          const float2 f = act_unpack2(h2[e], l2[e], planes);
           val[v][2 * e] += wgt[t] * f.x;
           val[v][2 * e + 1] += wgt[t] * f.y;
         }
@@ -101,15 +97,11 @@ __device__ __forceinline__ void load_pixel(const __nv_bfloat16* __restrict__ x, 
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + pix * C + c0));
       const uint4 ql = planes == 2 ? __ldg(reinterpret_cast<const uint4*>(x + plane_stride + pix * C + c0))
                                    : make_uint4(0, 0, 0, 0);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-      const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ql);
+      const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&q);
+      const uint32_t* l2 = reinterpret_cast<const uint32_t*>(&ql);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float2 f = __bfloat1622float2(h2[e]);
-        if (planes == 2) {
-          const float2 g = __bfloat1622float2(l2[e]);
-          f.x += g.x; f.y += g.y;
-        }
+        const float2 f = act_unpack2(h2[e], l2[e], planes);
         val[v][2 * e] = f.x;
         val[v][2 * e + 1] = f.y;
       }
@@ -127,11 +119,7 @@ __device__ __forceinline__ void store_pixel(__nv_bfloat16* __restrict__ out, lon
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(acc[v][2 * e], h0, l0);
-        split_bf16(acc[v][2 * e + 1], h1, l1);
-        hi[e] = pack_bf16x2(h0, h1);
-        lo[e] = pack_bf16x2(l0, l1);
+        act_pack2(acc[v][2 * e], acc[v][2 * e + 1], planes, hi[e], lo[e]);
       }
       *reinterpret_cast<uint4*>(out + pix * C + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       if (planes == 2)

@@ -11,7 +11,9 @@ namespace v2x {
 // np.rot90(m, 3)[r, c] = m[H - 1 - c, r]  =>  voxel (i0, i1) lands on pixel (r, c) = (i1, H - 1 - i0).
 __global__ void voxel_scatter_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ count, int capacity,
                                      __nv_bfloat16* __restrict__ out, int n_maps, int H, int W, int C, int c_pad,
-                                     int rot90_k3, int* __restrict__ bad) {
+                                     int rot90_k3, int* __restrict__ bad, int planes) {
+  // 1.0 in the storage format of the hi plane: bf16 0x3F80 (planes == 1), fp16 0x3C00 (planes == 2)
+  const __nv_bfloat16 one = __ushort_as_bfloat16(planes == 2 ? (unsigned short)0x3C00 : (unsigned short)0x3F80);
   const int n = min(*count, capacity);
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const int4 v = __ldg(reinterpret_cast<const int4*>(idx) + t);
@@ -22,7 +24,7 @@ __global__ void voxel_scatter_kernel(const int32_t* __restrict__ idx, const int3
     }
     const int r = rot90_k3 ? i1 : i0;
     const int c = rot90_k3 ? (H - 1 - i0) : i1;
-    out[(((long long)map * H + r) * W + c) * c_pad + z] = __float2bfloat16_rn(1.f);
+    out[(((long long)map * H + r) * W + c) * c_pad + z] = one;
   }
 }
 
@@ -42,7 +44,8 @@ __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat1
       const int c0 = g * 8 + 2 * i;
       const float v0 = (c0 < c && __ldg(x + pix * c + c0)) ? 1.f : 0.f;
       const float v1 = (c0 + 1 < c && __ldg(x + pix * c + c0 + 1)) ? 1.f : 0.f;
-      w[i] = pack_bf16x2(__float2bfloat16_rn(v0), __float2bfloat16_rn(v1));
+      uint32_t lo_unused;
+      act_pack2(v0, v1, planes, w[i], lo_unused);
     }
     __nv_bfloat16* dst = out + pix * c_pad + g * 8;
     *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -74,7 +77,7 @@ extern "C" int v2x_voxelize_fwd(const int32_t* idx, const int32_t* count, int32_
   long long blocks = ((long long)capacity + 255) / 256;
   if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
   voxel_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(idx, count, capacity, reinterpret_cast<__nv_bfloat16*>(out),
-                                                        n_maps, h, w, c, c_pad, rot90_k3, bad_count);
+                                                        n_maps, h, w, c, c_pad, rot90_k3, bad_count, planes);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }

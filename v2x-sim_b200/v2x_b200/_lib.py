@@ -46,7 +46,7 @@ class ConvParams(C.Structure):
         ("map_offset", C.c_int32),
         ("gru_pre_act", C.c_int32),
         ("tap_pack", C.c_int32),
-        ("reserved", C.c_int32),
+        ("mmas", C.c_int32),
         ("gru_add", C.c_void_p),
         ("tail_weights", C.c_void_p),
         ("tail_bias", C.c_void_p),

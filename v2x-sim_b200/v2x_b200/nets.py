@@ -16,7 +16,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import ops
+from . import ops, precision
 from .ops import EPI_ACT, EPI_F32_SPLIT, EPI_GRU, EPI_TAIL_F32_SPLIT, ConvLaunch, PackedConv
 
 import os
@@ -68,10 +68,13 @@ class BackboneWeights:
 
     def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, planes: int, device, encoder=True, decoder=True):
         self.c: Dict[str, PackedConv] = {}
+        prec = precision.resolve(planes)     # an int (1 / 2), a mode name or a Precision: per-layer MMA passes
+        planes = prec.planes
         layers = (self.ENC if encoder else []) + (self.DEC if decoder else [])
         for conv, bn, stride, cins in layers:
             self.c[conv] = ops.pack_conv(sd[prefix + conv + ".weight"], sd[prefix + conv + ".bias"],
-                                         _bn(sd, prefix + bn), cins=cins, stride=stride, planes=planes, device=device)
+                                         _bn(sd, prefix + bn), cins=cins, stride=stride, planes=planes, device=device,
+                                         mmas=prec.mmas(conv))
         if encoder and prefix + "com_compresser.weight" in sd:
             # optional compress / decompress of the communicated layer x_3 (Backbone.py:74-87,138-141)
             self.c["com_compresser"], self.c["com_decompresser"] = pack_compress_pair(sd, prefix, planes, device)
@@ -79,25 +82,28 @@ class BackboneWeights:
             for name in ("conv3d_1", "conv3d_2"):
                 self.c[name] = ops.pack_conv(sd[prefix + name + ".conv3d.weight"], sd[prefix + name + ".conv3d.bias"],
                                              _bn(sd, prefix + name + ".bn3d"), cins=[sd[prefix + name + ".conv3d.weight"].shape[1]],
-                                             planes=planes, device=device)
+                                             planes=planes, device=device, mmas=prec.mmas(name))
 
 
 class HeadWeights:
     def __init__(self, sd, planes, device):
+        prec = precision.resolve(planes)
+        planes = prec.planes
         self.head1, self.head2, self.n_cls = ops.pack_heads(
             sd["classification.conv1.weight"], sd["classification.conv1.bias"], _bn(sd, "classification.bn1"),
             sd["regression.box_prediction.0.weight"], sd["regression.box_prediction.0.bias"],
             _bn(sd, "regression.box_prediction.1"),
             sd["classification.conv2.weight"], sd["classification.conv2.bias"],
             sd["regression.box_prediction.3.weight"], sd["regression.box_prediction.3.bias"],
-            planes=planes, device=device)
+            planes=planes, device=device, mmas=prec.mmas("heads"))
 
 
 class DetPlan:
     """Shared machinery: workspace, launch list, graph capture."""
 
     def __init__(self, n_maps: int, planes: int, device):
-        self.n, self.planes, self.device = n_maps, planes, torch.device(device)
+        self.prec = precision.resolve(planes)
+        self.n, self.planes, self.device = n_maps, self.prec.planes, torch.device(device)
         self.launches: List = []
         self.ws: Dict[str, torch.Tensor] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -303,18 +309,19 @@ class V2VNetDetPlan(DetPlan):
     def __init__(self, sd, batch: int, agents: int = 5, gnn_iter: int = 3, planes: int = 1, device="cuda",
                  only_v2i=False, input_mode="f32", voxel_capacity=0, layer: int = 3):
         super().__init__(batch * agents, planes, device)
+        prec, planes = self.prec, self.prec.planes
         if layer not in (1, 2, 3):
             raise ops.V2XError("V2VNet on the sm_100a path communicates at layer 1, 2 or 3 (the ConvGRU tile needs a "
                                "multiple of 64 channels; layer 4 only exists 2x-upsampled in the workspace)")
         ops.require_gpu()
         self.batch, self.agents, self.gnn_iter = batch, agents, gnn_iter
         dev = self.device
-        self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
-        self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
-        self.head_w = HeadWeights(sd, planes, dev)
+        self.enc_w = BackboneWeights(sd, "u_encoder.", prec, dev, encoder=True, decoder=False)
+        self.dec_w = BackboneWeights(sd, "decoder.", prec, dev, encoder=False, decoder=True)
+        self.head_w = HeadWeights(sd, prec, dev)
         self.gru_h, self.gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"],
                                                     sd["convgru.bias_hh_l0"], planes=planes, device=dev,
-                                                    pre_act=GRU_PRE_ACT and planes == 1)
+                                                    pre_act=GRU_PRE_ACT and planes == 1, mmas=prec.mmas("gru"))
         self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
 
@@ -355,14 +362,15 @@ class FaFNetPlan(DetPlan):
     def __init__(self, sd, n_maps: int, planes: int = 1, device="cuda", heads: bool = True, input_mode="f32",
                  voxel_capacity=0):
         super().__init__(n_maps, planes, device)
+        prec, planes = self.prec, self.prec.planes
         ops.require_gpu()
-        self.w = BackboneWeights(sd, "stpn.", planes, self.device, encoder=True, decoder=True)
+        self.w = BackboneWeights(sd, "stpn.", prec, self.device, encoder=True, decoder=True)
         x_in = self.build_input(input_mode, voxel_capacity)
         x0, x1, x2, x3, x4u = self.build_encoder(self.w, x_in)
         x8 = self.build_decoder(self.w, x0, x1, x2, x3, x4u)
         self.has_heads = heads   # TeacherNet.forward returns the STPN layers only (TeacherNet.py:10-13)
         if heads:
-            self.head_w = HeadWeights(sd, planes, self.device)
+            self.head_w = HeadWeights(sd, prec, self.device)
             self.build_heads(self.head_w, x8)
 
     def forward(self, bevs):
@@ -380,14 +388,17 @@ class When2comDetPlan(DetPlan):
     def __init__(self, sd, batch: int, agents: int = 5, planes: int = 1, device="cuda", warp_flag=1,
                  inference="activated", training_pass_only=False, only_v2i=False):
         super().__init__(batch * agents, planes, device)
+        prec, planes = self.prec, self.prec.planes
         ops.require_gpu()
         dev = self.device
         self.batch, self.agents = batch, agents
         f32 = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
-        self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
-        self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
-        self.pol_w = BackboneWeights(sd, "query_key_net.lidar_encoder.", planes, dev, encoder=True, decoder=False)
-        self.head_w = HeadWeights(sd, planes, dev)
+        self.enc_w = BackboneWeights(sd, "u_encoder.", prec, dev, encoder=True, decoder=False)
+        self.dec_w = BackboneWeights(sd, "decoder.", prec, dev, encoder=False, decoder=True)
+        # the policy branch feeds DISCRETE gates (p > 0.2 / argmax): it always runs at full split precision
+        self.pol_w = BackboneWeights(sd, "query_key_net.lidar_encoder.", prec if planes == 1 else "fp16x3", dev,
+                                     encoder=True, decoder=False)
+        self.head_w = HeadWeights(sd, prec, dev)
         self.pol_convs = []
         for name, stride, cin in (("conv1", 1, 512), ("conv2", 1, 512), ("conv3", 2, 256), ("conv4", 1, 256),
                                   ("conv5", 2, 256)):
@@ -461,16 +472,17 @@ class V2VNetDetShardedPlan(DetPlan):
         assert self.exchange in ("allgather", "neighbours")
         self.offset, n_loc = sharding.unit_range(batch_total * agents, rank, world)
         super().__init__(n_loc, planes, device)
+        prec, planes = self.prec, self.prec.planes
         ops.require_gpu()
         self.sharding, self.group, self.world = sharding, group, world
         self.batch, self.agents, self.gnn_iter = batch_total, agents, gnn_iter
         dev = self.device
-        self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
-        self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
-        self.head_w = HeadWeights(sd, planes, dev)
+        self.enc_w = BackboneWeights(sd, "u_encoder.", prec, dev, encoder=True, decoder=False)
+        self.dec_w = BackboneWeights(sd, "decoder.", prec, dev, encoder=False, decoder=True)
+        self.head_w = HeadWeights(sd, prec, dev)
         self.gru_h, self.gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"],
                                                     sd["convgru.bias_hh_l0"], planes=planes, device=dev,
-                                                    pre_act=GRU_PRE_ACT and planes == 1)
+                                                    pre_act=GRU_PRE_ACT and planes == 1, mmas=prec.mmas("gru"))
         self.trans = torch.zeros((batch_total, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch_total, agents), agents, dtype=torch.int64, device=dev)
         trans, na, off = self.trans, self.num_agent, self.offset
@@ -629,14 +641,15 @@ class FusionDetPlan(DetPlan):
     def __init__(self, sd, kind: str, batch: int, agents: int = 5, planes: int = 1, device="cuda", only_v2i=False,
                  layer: int = 3):
         super().__init__(batch * agents, planes, device)
+        prec, planes = self.prec, self.prec.planes
         if layer not in (0, 1, 2, 3):
             raise ops.V2XError("fusion models on the sm_100a path fuse at layer 0..3 (layer 4 only exists 2x-upsampled)")
         ops.require_gpu()
         self.batch, self.agents, self.kind = batch, agents, kind
         dev = self.device
-        self.enc_w = BackboneWeights(sd, "u_encoder.", planes, dev, encoder=True, decoder=False)
-        self.dec_w = BackboneWeights(sd, "decoder.", planes, dev, encoder=False, decoder=True)
-        self.head_w = HeadWeights(sd, planes, dev)
+        self.enc_w = BackboneWeights(sd, "u_encoder.", prec, dev, encoder=True, decoder=False)
+        self.dec_w = BackboneWeights(sd, "decoder.", prec, dev, encoder=False, decoder=True)
+        self.head_w = HeadWeights(sd, prec, dev)
         self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
         x_in = self.build_input()

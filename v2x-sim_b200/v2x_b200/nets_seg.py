@@ -107,6 +107,7 @@ class SegUNetPlan(SegPlan):
 
     def __init__(self, sd, n_maps, planes=1, device="cuda"):
         super().__init__(n_maps, planes, device)
+        planes = self.planes   # ``planes`` may have been a mode name / Precision (v2x_b200/precision.py)
         ops.require_gpu()
         self.w = SegUNetWeights(sd, planes, self.device)
         x_in = self.build_input()
@@ -140,11 +141,13 @@ class SegV2VNetPlan(_FusedSegPlan):
 
     def __init__(self, sd, batch, agents=5, planes=1, device="cuda", only_v2i=False):
         super().__init__(batch * agents, planes, device)
+        planes = self.planes   # ``planes`` may have been a mode name / Precision (v2x_b200/precision.py)
         ops.require_gpu()
         self._common(batch, agents)
         self.w = SegUNetWeights(sd, planes, self.device)
         self.gru_h, self.gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"],
-                                                    sd["convgru.bias_hh_l0"], planes=planes, device=self.device)
+                                                    sd["convgru.bias_hh_l0"], planes=planes, device=self.device,
+                                                    mmas=self.prec.mmas("gru"))
         x_in = self.build_input()
         x1, x2, x3, x4 = self.build_encoder(self.w, x_in)
         c4 = x4.shape[-1]
@@ -161,6 +164,7 @@ class SegWhen2comPlan(_FusedSegPlan):
     def __init__(self, sd, batch, agents=5, planes=1, device="cuda", warp_flag=1, inference="activated",
                  training=False, only_v2i=False):
         super().__init__(batch * agents, planes, device)
+        planes = self.planes   # ``planes`` may have been a mode name / Precision (v2x_b200/precision.py)
         ops.require_gpu()
         dev = self.device
         self._common(batch, agents)
@@ -212,6 +216,7 @@ class SegFusionPlan(_FusedSegPlan):
     def __init__(self, sd, kind, batch, agents=5, planes=1, device="cuda", only_v2i=False):
         from .nets import FuseStage
         super().__init__(batch * agents, planes, device)
+        planes = self.planes   # ``planes`` may have been a mode name / Precision (v2x_b200/precision.py)
         ops.require_gpu()
         self._common(batch, agents)
         self.kind = kind

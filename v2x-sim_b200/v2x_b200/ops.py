@@ -1,8 +1,8 @@
 """Torch-facing wrappers of the C ABI: tensors in, tensors out, kernels from libv2x_b200.so.
 
 torch is plumbing here (device memory, streams); every FLOP of the path runs in the
-hand-written sm_100a kernels.  An ``act`` is a bf16 tensor ``[planes, N, H, W, C]``
-(planes = 1: bf16; planes = 2: bf16 hi/lo split, see include/v2x_b200.h).
+hand-written sm_100a kernels.  An ``act`` is a 16-bit tensor ``[planes, N, H, W, C]``
+(planes = 1: one bf16 plane; planes = 2: fp16 hi/lo split, see include/v2x_b200.h).
 """
 from __future__ import annotations
 
@@ -36,8 +36,23 @@ def require_gpu():
     return lib
 
 
+def act_dtype(planes):
+    """Storage format follows the plane count: one bf16 plane, or fp16 hi + fp16 lo (include/v2x_b200.h)."""
+    return torch.bfloat16 if planes == 1 else torch.float16
+
+
 def empty_act(planes, n, h, w, c, device):
-    return torch.empty((planes, n, h, w, c), dtype=torch.bfloat16, device=device)
+    return torch.empty((planes, n, h, w, c), dtype=act_dtype(planes), device=device)
+
+
+FMT_BF16, FMT_F16X2, FMT_F16 = 1, 2, 3
+
+
+def weight_fmt(planes, mmas):
+    """(storage format, planes) of a packed conv operand: bf16 | fp16 hi/lo (3 MMA passes) | one fp16 plane (1 or 2)."""
+    if planes == 1:
+        return FMT_BF16, 1
+    return (FMT_F16X2, 2) if mmas == 3 else (FMT_F16, 1)
 
 
 def act_to_float(act: torch.Tensor) -> torch.Tensor:
@@ -87,7 +102,9 @@ def voxelize(idx: torch.Tensor, count: torch.Tensor, out: torch.Tensor, c: int, 
 
 @dataclass
 class PackedConv:
-    """Packed operand of one fused conv launch (weights bf16 [P, cout_pad, k_total], bias fp32)."""
+    """Packed operand of one fused conv launch (weights [PW, cout_pad, k_total] in the format of
+    ``weight_fmt(planes, mmas)``, bias fp32).  ``planes`` = storage planes of the act tensors it is applied to,
+    ``mmas`` = tensor-core passes per k-step (1 for planes == 1; 1..3 for planes == 2, see v2x_b200/precision.py)."""
     weights: torch.Tensor
     bias: torch.Tensor
     cins: List[int]          # padded channels per source
@@ -100,6 +117,7 @@ class PackedConv:
     keep: list = field(default_factory=list)
     gru_pre_act: bool = False   # weights carry 192 identity K columns for the pre-activation window (v2x_conv_params.gru_pre_act)
     tap_pack: bool = False      # weights are [P, 96, 3 * sum(cins)]: horizontal taps packed into N (v2x_conv_params.tap_pack)
+    mmas: int = 0               # 0 = the format's default (1 for bf16, 3 for fp16 hi/lo)
 
     @property
     def k_total(self):
@@ -111,9 +129,10 @@ def _f32(t, device):
 
 
 TAP_PACK = not os.environ.get("V2X_NO_TAP_PACK")   # A/B switch for the tap-packed 32-channel convs (csrc/conv_pack3.cu)
+TAP_PACK_SPLIT = not os.environ.get("V2X_NO_TAP_PACK_SPLIT")   # ... for the shallow N = 32 layers in the fp16 hi/lo modes
 
 
-def pack_conv_tap_packed(weight, bias, bn, *, cins: Sequence[int], planes=1, device=None) -> PackedConv:
+def pack_conv_tap_packed(weight, bias, bn, *, cins: Sequence[int], planes=1, device=None, mmas=0) -> PackedConv:
     """3x3 stride-1 conv with 32 | cout in the tap-packed form of csrc/conv_pack3.cu: the operand is
     [planes, cout/32 * 96, 3 * sum(cins)] with row = (group, kw, co) and k = (source, kh, ci) -- built by handing the
     regular packer the weights rearranged as a "3-tap" conv with 3 * cout outputs (BN scale folded per row; rows
@@ -130,24 +149,26 @@ def pack_conv_tap_packed(weight, bias, bn, *, cins: Sequence[int], planes=1, dev
     b = rep(bias)
     bnp = [rep(t) for t in bn] if bn is not None else [None] * 4
     k_total = 3 * sum(cin_pads)
-    dst = torch.zeros((planes, 3 * cout, k_total), dtype=torch.bfloat16, device=device)
+    mmas = (3 if planes == 2 else 1) if not mmas else mmas
+    fmt, pw = weight_fmt(planes, mmas)
+    dst = torch.zeros((pw, 3 * cout, k_total), dtype=act_dtype(planes), device=device)
     dst_bias = torch.zeros((3 * cout,), dtype=torch.float32, device=device)
     ci_lo, k_off = 0, 0
     for s, (c, cp) in enumerate(zip(cins, cin_pads)):
         check(lib.v2x_pack_conv_weights(_ptr(w), _ptr(b), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]), _ptr(bnp[3]), BN_EPS,
                                         3 * cout, cin_total, 3, ci_lo, ci_lo + c, cp, 0, 0, _ptr(dst), _ptr(dst_bias),
-                                        planes, 3 * cout, k_total, 0, k_off, int(s == 0), _stream()),
+                                        fmt, 3 * cout, k_total, 0, k_off, int(s == 0), _stream()),
               "v2x_pack_conv_weights(tap_pack)")
         ci_lo += c
         k_off += 3 * cp
-    pc = PackedConv(dst, dst_bias, cin_pads, 9, 1, cout, 3 * cout, planes)
+    pc = PackedConv(dst, dst_bias, cin_pads, 9, 1, cout, 3 * cout, planes, mmas=mmas)
     pc.tap_pack = True
     return pc
 
 
 def pack_conv(weight, bias, bn=None, *, cins: Sequence[int], cin_pads: Optional[Sequence[int]] = None, stride=1,
               planes=1, device=None, vflip=False, gru=False, cout_pad: Optional[int] = None,
-              tap_pack: Optional[bool] = None) -> PackedConv:
+              tap_pack: Optional[bool] = None, mmas: int = 0) -> PackedConv:
     """BN-fold + reorder + bf16 split of one conv's weights, on device.
 
     weight: OIHW (or OI111 for the 1x1x1 Conv3D) fp32; ``cins`` = logical channels of each concat
@@ -164,35 +185,43 @@ def pack_conv(weight, bias, bn=None, *, cins: Sequence[int], cin_pads: Optional[
         and not gru and weight.dim() == 4
     # 64-output layers with deep K (conv7_1: 192 channels) additionally stop re-streaming their 221 KB of weights from
     # L2 for every M tile: each 32-channel group keeps its 110 KB operand resident
-    deep = cin_total >= (64 if cout == 32 else 128) and 3 * cin_total * 96 * 2 * planes <= 112 * 1024  # + >= 3 stages
-    if eligible and (tap_pack is True or (tap_pack is None and TAP_PACK and deep)):
-        return pack_conv_tap_packed(weight, bias, bn, cins=cins, planes=planes, device=device)
+    mmas = (3 if planes == 2 else 1) if not mmas else mmas
+    fmt, pw = weight_fmt(planes, mmas)
+    deep = cin_total >= (64 if cout == 32 else 128) and 3 * cin_total * 96 * 2 * pw <= 112 * 1024  # + >= 3 stages
+    # fp16 hi/lo storage: with 2-3 tensor-core passes per k-step even the shallow 32-output layers (conv_pre_*, conv8_2)
+    # are tensor-pipe bound at N = 32 (40 cycles per MMA for 16 cycles of math), so they take the tap-packed form too
+    # (measured r02: conv_pre_2 254 -> 193 us, conv8_2 258 -> 206 us; the 13-channel conv_pre_1 loses, K is too shallow)
+    split_n32 = (planes == 2 and mmas >= 2 and cout == 32 and cin_total >= 32 and TAP_PACK_SPLIT
+                 and 3 * cin_total * 96 * 2 * pw <= 112 * 1024)
+    if eligible and (tap_pack is True or (tap_pack is None and TAP_PACK and (deep or split_n32))):
+        return pack_conv_tap_packed(weight, bias, bn, cins=cins, planes=planes, device=device, mmas=mmas)
     cin_pads = list(cin_pads) if cin_pads is not None else [((c + 15) // 16) * 16 for c in cins]
     cout_pad = cout_pad or cout   # zero rows up to a multiple of the N tile (e.g. the 8-class seg logits)
     k_total = taps * sum(cin_pads)
     w = _f32(weight, device).reshape(cout, cin_total, taps)
     b = _f32(bias, device) if bias is not None else None
     bnp = [_f32(t, device) for t in bn] if bn is not None else [None] * 4
-    dst = torch.zeros((planes, cout_pad, k_total), dtype=torch.bfloat16, device=device)
+    dst = torch.zeros((pw, cout_pad, k_total), dtype=act_dtype(planes), device=device)
     dst_bias = torch.zeros((cout_pad,), dtype=torch.float32, device=device)
     ci_lo, k_off = 0, 0
     for s, (c, cp) in enumerate(zip(cins, cin_pads)):
         check(lib.v2x_pack_conv_weights(_ptr(w), _ptr(b), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]), _ptr(bnp[3]),
                                         BN_EPS, cout, cin_total, taps, ci_lo, ci_lo + c, cp, int(vflip),
-                                        3 if gru else 0, _ptr(dst), _ptr(dst_bias), planes, cout_pad, k_total, 0, k_off,
+                                        3 if gru else 0, _ptr(dst), _ptr(dst_bias), fmt, cout_pad, k_total, 0, k_off,
                                         int(s == 0 and not gru), _stream()), "v2x_pack_conv_weights")
         ci_lo += c
         k_off += taps * cp
-    return PackedConv(dst, dst_bias, cin_pads, taps, stride, cout, cout_pad, planes)
+    return PackedConv(dst, dst_bias, cin_pads, taps, stride, cout, cout_pad, planes, mmas=mmas)
 
 
-def pack_gru(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True) -> PackedConv:
+def pack_gru(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True, mmas=0) -> PackedConv:
     """Zero-hidden ConvGRU operand: W_ih rows gate-interleaved per 64 channels, filter rows mirrored so
     the GRU runs in the un-flipped domain.  W_hh is never needed (hidden == 0)."""
     lib = require_gpu()
     device = device or w_ih.device
     c = w_ih.shape[0] // 3
-    pc = pack_conv(w_ih, None, None, cins=[c, w_ih.shape[1] - c], planes=planes, device=device, vflip=vflip, gru=True)
+    pc = pack_conv(w_ih, None, None, cins=[c, w_ih.shape[1] - c], planes=planes, device=device, vflip=vflip, gru=True,
+                   mmas=mmas)
     bhn = torch.empty((c,), dtype=torch.float32, device=device)
     bi, bh = _f32(b_ih, device), _f32(b_hh, device)
     check(lib.v2x_pack_gru_bias(_ptr(bi), _ptr(bh), c, _ptr(pc.bias), _ptr(bhn), _stream()), "v2x_pack_gru_bias")
@@ -200,7 +229,7 @@ def pack_gru(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True) -> PackedCo
     return pc
 
 
-def pack_gru_split(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True, pre_act=False):
+def pack_gru_split(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True, pre_act=False, mmas=0):
     """The zero-hidden ConvGRU split in two operands: ``gru_m`` convolves the round-invariant neighbour mean
     (W_ih[:, C:], carries the combined bias) once per frame into gate pre-activations; ``gru_h`` convolves the agent's
     own state (W_ih[:, :C]) in every GNN round and adds them.  Same arithmetic as conv(cat([h, mean])) up to fp32
@@ -213,14 +242,15 @@ def pack_gru_split(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True, pre_a
     lib = require_gpu()
     device = device or w_ih.device
     c = w_ih.shape[0] // 3
-    gru_h = pack_conv(w_ih[:, :c], None, None, cins=[c], planes=planes, device=device, vflip=vflip, gru=True)
+    gru_h = pack_conv(w_ih[:, :c], None, None, cins=[c], planes=planes, device=device, vflip=vflip, gru=True, mmas=mmas)
     gru_m = pack_conv(w_ih[:, c:], None, None, cins=[w_ih.shape[1] - c], planes=planes, device=device, vflip=vflip,
-                      gru=True)
+                      gru=True, mmas=mmas)
     bhn = torch.empty((c,), dtype=torch.float32, device=device)
     bi, bh = _f32(b_ih, device), _f32(b_hh, device)
     check(lib.v2x_pack_gru_bias(_ptr(bi), _ptr(bh), c, _ptr(gru_m.bias), _ptr(bhn), _stream()), "v2x_pack_gru_bias")
     gru_h.gru_bhn = bhn     # gru_h.bias stays zero: the bias rides in gru_m's output
     if pre_act:
+        assert planes == 1, "gru_pre_act is a bf16 (planes == 1) feature"
         eye = torch.zeros((planes, 3 * c, 192), dtype=torch.bfloat16, device=device)
         eye[0] = torch.eye(192, dtype=torch.bfloat16, device=device).repeat(3 * c // 192, 1)   # row n -> column n % 192
         gru_h.weights = torch.cat([gru_h.weights, eye], dim=2).contiguous()
@@ -230,14 +260,17 @@ def pack_gru_split(w_ih, b_ih, b_hh, *, planes=1, device=None, vflip=True, pre_a
 
 
 def pack_heads(cls1_w, cls1_b, cls_bn, reg1_w, reg1_b, reg_bn, cls2_w, cls2_b, reg2_w, reg2_b, *, planes=1,
-               device=None):
+               device=None, mmas=0):
     """Detection heads (DetModelBase.py:268-351) as two launches: one 32->64 3x3 conv (cls.conv1|reg.0 rows
     stacked, BN folded, ReLU) and one block-diagonal 64->48 1x1 conv (cls.conv2 on channels 0..31, reg.3 on 32..63)."""
     lib = require_gpu()
     device = device or cls1_w.device
     c = cls1_w.shape[1]
     n1 = cls1_w.shape[0] + reg1_w.shape[0]
-    w1 = torch.zeros((planes, n1, 9 * c), dtype=torch.bfloat16, device=device)
+    mmas = (3 if planes == 2 else 1) if not mmas else mmas
+    fmt1, pw1 = weight_fmt(planes, mmas)
+    fmt2, pw2 = weight_fmt(planes, 3 if planes == 2 else 1)   # the 1x1 tail always runs at full precision (0.5% of the FLOPs)
+    w1 = torch.zeros((pw1, n1, 9 * c), dtype=act_dtype(planes), device=device)
     b1 = torch.zeros((n1,), dtype=torch.float32, device=device)
     row = 0
     for w, b, bn in ((cls1_w, cls1_b, cls_bn), (reg1_w, reg1_b, reg_bn)):
@@ -245,18 +278,18 @@ def pack_heads(cls1_w, cls1_b, cls_bn, reg1_w, reg1_b, reg_bn, cls2_w, cls2_b, r
         bnp = [_f32(t, device) for t in bn]
         check(lib.v2x_pack_conv_weights(_ptr(wf), _ptr(_f32(b, device)), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]),
                                         _ptr(bnp[3]), BN_EPS, w.shape[0], c, 9, 0, c, c, 0, 0, _ptr(w1), _ptr(b1),
-                                        planes, n1, 9 * c, row, 0, 1, _stream()), "v2x_pack_conv_weights(head1)")
+                                        fmt1, n1, 9 * c, row, 0, 1, _stream()), "v2x_pack_conv_weights(head1)")
         row += w.shape[0]
-    head1 = PackedConv(w1, b1, [c], 9, 1, n1, n1, planes)
+    head1 = PackedConv(w1, b1, [c], 9, 1, n1, n1, planes, mmas=mmas)
     n2 = cls2_w.shape[0] + reg2_w.shape[0]
-    w2 = torch.zeros((planes, n2, n1), dtype=torch.bfloat16, device=device)
+    w2 = torch.zeros((pw2, n2, n1), dtype=act_dtype(planes), device=device)
     b2 = torch.zeros((n2,), dtype=torch.float32, device=device)
     row, koff = 0, 0
     for w, b in ((cls2_w, cls2_b), (reg2_w, reg2_b)):
         ci = w.shape[1]
         wf = _f32(w, device).reshape(w.shape[0], ci, 1)
         check(lib.v2x_pack_conv_weights(_ptr(wf), _ptr(_f32(b, device)), None, None, None, None, BN_EPS, w.shape[0],
-                                        ci, 1, 0, ci, ci, 0, 0, _ptr(w2), _ptr(b2), planes, n2, n1, row, koff, 1,
+                                        ci, 1, 0, ci, ci, 0, 0, _ptr(w2), _ptr(b2), fmt2, n2, n1, row, koff, 1,
                                         _stream()), "v2x_pack_conv_weights(head2)")
         row += w.shape[0]
         koff += ci
@@ -294,7 +327,7 @@ class ConvLaunch:
         assert planes == pc.planes
         for i, (s, cp) in enumerate(zip(srcs, pc.cins)):
             want = pc.cout if (pc.gru_pre_act and i == 1) else cp    # the pre-activation source spans all cout channels
-            assert s.shape[-1] == want and s.is_contiguous() and s.dtype == torch.bfloat16, (s.shape, want)
+            assert s.shape[-1] == want and s.is_contiguous() and s.dtype == act_dtype(planes), (s.shape, s.dtype, want)
         assert not pc.gru_pre_act or (epilogue == EPI_GRU and len(srcs) == 2)
         h_out, w_out = h_in // pc.stride, w_in // pc.stride
         p = ConvParams()
@@ -321,6 +354,7 @@ class ConvLaunch:
         p.batch, p.agents, p.map_offset = batch, agents, map_offset
         p.gru_add = gru_add.data_ptr() if gru_add is not None else None
         p.gru_pre_act = int(pc.gru_pre_act)
+        p.mmas = pc.mmas
         if pc.tap_pack:
             assert epilogue == EPI_ACT and not upsample2x and h_out % 8 == 0, "tap-packed convs: plain EPI_ACT, 8 | H"
             p.tap_pack, p.block_n = 1, 96
@@ -334,6 +368,7 @@ class ConvLaunch:
             raise V2XError("the CUDA-core cross-check kernel takes the regular operand layout: pack with tap_pack=False")
         self.fn = self.lib.v2x_conv_fwd_crosscheck if crosscheck else self.lib.v2x_conv_fwd
         k_eff = pc.taps * pc.cins[0] + 192 if pc.gru_pre_act else pc.taps * sum(pc.cins)
+        self.mma_passes = (pc.mmas or 3) if planes == 2 else 1    # tensor-core passes per k-step (bench.py's pipe FLOPs)
         self.flops = 2.0 * n * h_out * w_out * pc.cout * k_eff
         if tail is not None:
             self.flops += 2.0 * n * h_out * w_out * tail.cout * pc.cout

@@ -27,7 +27,7 @@ def all_gather_units(local: torch.Tensor, out: torch.Tensor = None, group=None, 
     """All-gather per-unit tensors ``local`` [n_loc, ...] (or act planes [P, n_loc, ...]) into [n_loc * world, ...]
     (resp. [P, n_loc * world, ...]) in rank order == global unit order.  Returns (out, work-or-None list)."""
     world = dist.get_world_size(group)
-    planar = local.dim() == 5 and local.dtype == torch.bfloat16  # act layout [P, N, H, W, C]
+    planar = local.dim() == 5 and local.dtype in (torch.bfloat16, torch.float16)  # act layout [P, N, H, W, C]
     if planar:
         p, n = local.shape[0], local.shape[1]
         if out is None:
