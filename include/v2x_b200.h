@@ -317,6 +317,55 @@ int v2x_upsample_bilinear2_fwd(const void* x, void* out, int32_t n, int32_t h_in
 int v2x_act_to_nchw_f32(const void* act, float* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t planes,
                         void* stream);
 
+/* =====================================================================================================================
+ * Training step: train-mode BatchNorm, its backward, the byte movers of the backward graph and the weight
+ * gradient.  Data gradients run through v2x_conv_fwd with transposed / 180-degree-rotated packed weights.
+ * Replaces nn.BatchNorm2d in .train() mode (CP/models/det/backbone/Backbone.py:102-136, entered through
+ * CP/utils/CoDetModule.py:217-291 after model.train()) and torch.autograd's conv2d / batch_norm / relu / interpolate
+ * backward nodes (loss.backward(), CoDetModule.py:289-291).
+ * ===================================================================================================================== */
+/* per-channel sum / sum of squares of an act [planes][n_pixels][c] over all pixels (fp64); zeroes the outputs first */
+int v2x_bn_stats_fwd(const void* z, int64_t n_pixels, int32_t c, int32_t planes, double* sum, double* sumsq, void* stream);
+/* batch statistics -> scale = gamma * invstd, shift = beta - mean * scale, mean, invstd (fp32 [c]); updates the running
+ * buffers in place like nn.BatchNorm2d (momentum, UNBIASED batch variance); gamma / beta / running_* may be NULL */
+int v2x_bn_finalize(const double* sum, const double* sumsq, int64_t count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                    float* invstd, int32_t c, void* stream);
+/* y = [relu](z * scale + shift), act -> act */
+int v2x_bn_relu_apply_fwd(const void* z, void* y, int64_t n_pixels, int32_t c, int32_t planes, const float* scale,
+                          const float* shift, int32_t relu, void* stream);
+/* backward of y = relu(BN_train(z)): s1[c] = sum dyh (= d beta), s2[c] = sum dyh * xhat (= d gamma) with dyh = dy * [y > 0],
+ * dz = scale * (dyh - s1 / n - xhat * s2 / n); s1 / s2 are fp64 [c] outputs */
+int v2x_bn_relu_bwd(const void* dy, const void* z, void* dz, int64_t n_pixels, int32_t c, int32_t planes, const float* scale,
+                    const float* shift, const float* mean, const float* invstd, int32_t relu, double* s1, double* s2,
+                    void* stream);
+/* mode 0: zero-stuffing out[2i][2j] = in[i][j] (stride-2 data gradient as a stride-1 correlation); mode 1: nearest 2x
+ * upsample (F.interpolate, Backbone.py:176,195,214,233); mode 2: its backward (2x2 block sums).  (h_out, w_out) = size of `out` */
+int v2x_resample2(const void* in, void* out, int32_t n, int32_t h_out, int32_t w_out, int32_t c, int32_t planes, int32_t mode,
+                  void* stream);
+/* dst += src over act tensors of n_elems elements per plane */
+int v2x_act_add(void* dst, const void* src, int64_t n_elems, int32_t planes, void* stream);
+/* dw[co][ci_off + ci][tap] += scale * sum_pixels dz[.][co] * x[shifted][ci]  (fp32 OIHW gradient of a 3x3 pad-1 stride-1/2 or
+ * 1x1 conv; dz act [planes][n][h_out][w_out][co], x act [planes][n][h_out*stride][w_out*stride][ci]; co_log / ci_log = logical
+ * channels (<= the padded co / ci); x is one concat source covering filter input channels [ci_off, ci_off + ci_log) of ci_total) */
+int v2x_conv_wgrad(const void* dz, const void* x, int32_t n, int32_t h_out, int32_t w_out, int32_t co, int32_t ci, int32_t planes,
+                   int32_t stride, int32_t taps, float* dw, int32_t co_log, int32_t ci_log, int32_t ci_off, int32_t ci_total,
+                   float scale, void* stream);
+/* out[i] = (accumulate ? out[i] : 0) + scale * in[i]: fp64 per-channel sums -> fp32 parameter gradients */
+int v2x_scale_to_f32(const double* in, float* out, int32_t count, float scale, int32_t accumulate, void* stream);
+
+/* zero-hidden ConvGRU gates in train mode (functional.py:84-105 with h = 0): a = conv(cat[h, mean], W_ih) + b_ih as an act
+ * [n_pixels][3c] in [r | z | n] channel order, bhh fp32 [3c]; units (pixel / hw) whose agent slot is absent copy `pass` */
+int v2x_gru_gates_fwd(const void* a, const float* bhh, const void* pass, void* h, int64_t n_pixels, int32_t hw, int32_t c,
+                      int32_t planes, const int64_t* num_agent, int32_t batch, int32_t agents, void* stream);
+/* their backward: da (act [n_pixels][3c]), dpass = dh on absent units (else 0), dbhn[c] = sum da_n * r (fp64) */
+int v2x_gru_gates_bwd(const void* dh, const void* a, const float* bhh, void* da, void* dpass, int64_t n_pixels, int32_t hw,
+                      int32_t c, int32_t planes, const int64_t* num_agent, int32_t batch, int32_t agents, double* dbhn,
+                      void* stream);
+/* backward of v2x_warp_mean_fwd (grid_sample backward + mean): dx fp32 [A*B][h][w][c] (zeroed here) += scattered dmean */
+int v2x_warp_mean_bwd(const void* dmean, float* dx, const double* trans, const int64_t* num_agent, int32_t batch, int32_t agents,
+                      int32_t h, int32_t w, int32_t c, int32_t planes, int32_t include_self, int32_t only_v2i, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

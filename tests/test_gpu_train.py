@@ -1,0 +1,164 @@
+"""GPU: the training step -- train-mode forward + backward of the drop-in modules against the float64 CPU
+oracle (oracle/restate.py::train_step_vjp, itself pinned to one training step of the LIVE reference by
+tests/golden/train_step_*.npz) and against those fixtures directly.
+
+Tolerances.  Outputs: 1e-3 relative (max-abs / max-abs), like the eval forward.  Gradients: the BatchNorm backward of
+these seeded random nets amplifies summation-order noise (a 1e-7 relative weight perturbation moves conv_pre_1's gradient
+by 0.7%), so the reference's own float32 run sits ~1% per element from its float64 run; gradients
+are therefore held to direction and size -- cosine >= 0.999 and |norm ratio - 1| <= 2e-2 per parameter tensor, and
+relative L2 error <= 5e-2 -- rather than to an element-wise 1e-3.  BatchNorm running buffers: 1e-5 absolute."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
+
+
+def _check_grads(tag, got, want, golden, parity_log, zero_tol=1e-9):
+    worst = dict(cos=1.0, norm=0.0, l2=0.0)
+    n_checked = 0
+    for k, gw in want.items():
+        assert k in got and got[k] is not None, "no gradient for %s" % k
+        g = got[k].detach().double().cpu().reshape(-1)
+        w = gw.detach().double().reshape(-1)
+        nw = w.norm().item()
+        if nw < zero_tol:       # e.g. a conv bias in front of a train-mode BN: exactly zero up to rounding
+            assert g.norm().item() < 1e-6, (k, g.norm().item())
+            continue
+        cos = (g @ w / (g.norm() * w.norm())).item()
+        ratio = g.norm().item() / nw
+        l2 = ((g - w).norm() / w.norm()).item()
+        worst = dict(cos=min(worst["cos"], cos), norm=max(worst["norm"], abs(ratio - 1.0)), l2=max(worst["l2"], l2))
+        assert cos >= 0.999 and abs(ratio - 1.0) <= 2e-2 and l2 <= 5e-2, (k, cos, ratio, l2)
+        key = "grad." + k + ".norm"
+        if golden is not None and key in golden.files:     # the live reference's own gradient norm
+            assert abs(g.norm().item() / float(golden[key]) - 1.0) <= 2e-2, (k, g.norm().item(), float(golden[key]))
+        n_checked += 1
+    parity_log(tag, "train fp16x3", params_with_grad=n_checked, worst_cosine=worst["cos"], worst_norm_ratio_err=worst["norm"],
+               worst_rel_l2=worst["l2"])
+    print(tag, "gradients of %d parameters: worst cosine %.6f, worst |norm ratio - 1| %.2e, worst rel-L2 %.2e"
+          % (n_checked, worst["cos"], worst["norm"], worst["l2"]))
+    assert n_checked > 50
+
+
+def test_fafnet_train_step_matches_oracle(golden_dir, parity_log):
+    from coperception.models.det import FaFNet
+    from oracle import restate
+    from oracle.gen_golden import make_upstream, train_case
+    from v2x_b200 import default_det_config
+    golden = np.load(os.path.join(golden_dir, "train_step_fafnet_seed22.npz"))
+    sd, inputs, keys = train_case("fafnet", 22)
+    bevs = inputs[0]
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    shapes = {"loc": (bevs.shape[0], 256, 256, 6, 1, 6), "cls": (bevs.shape[0], 256 * 256 * 6, 2)}
+    up = make_upstream(shapes, 22)
+    out_ref, grads_ref, sd_after = restate.train_step_vjp(lambda s: restate.fafnet_forward(bevs.double(), s), sd64, up)
+
+    model = FaFNet(default_det_config(), kd_flag=0, num_agent=5)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    out = model(bevs.cuda(), batch_size=1)
+    for k in ("loc", "cls"):
+        e = _rel(out[k], out_ref[k])
+        print("fafnet train forward", k, "rel_err %.3e" % e)
+        assert out[k].shape == out_ref[k].shape and e < 1e-3
+    torch.autograd.backward([out["cls"], out["loc"]], [up["cls"].float().cuda(), up["loc"].float().cuda()])
+    torch.cuda.synchronize()
+    got = {k: p.grad for k, p in model.named_parameters()}
+    _check_grads("train_step_fafnet_seed22", got, grads_ref, golden, parity_log)
+    # BatchNorm running buffers after the step (momentum 0.1, unbiased variance), vs the oracle and the live reference
+    after = dict(model.named_buffers())
+    for k, v in sd_after.items():
+        if k.endswith(("running_mean", "running_var")):
+            assert (after[k].double().cpu() - v).abs().max().item() < 1e-5, k
+            assert np.abs(after[k].double().cpu().numpy() - golden["bn." + k]).max() < 1e-5, k
+        if k.endswith("num_batches_tracked"):
+            assert int(after[k]) == int(v)
+
+
+def test_fafnet_adam_loop_decreases_the_loss_like_the_oracle():
+    """Three optimizer steps of the reference's training recipe (Adam, CoDetModule.py:217-291) on a fixed batch with a
+    simple differentiable loss: the loss trajectory of the sm_100a path tracks torch autograd over the CPU oracle."""
+    from coperception.models.det import FaFNet
+    from oracle import restate, synth
+    from v2x_b200 import default_det_config
+    sd = synth.fafnet_state(31)
+    bevs = synth.make_bevs(2, 31)
+    g = torch.Generator().manual_seed(5)
+    t_cls = torch.randn((2, 256 * 256 * 6, 2), generator=g) * 0.1
+    t_loc = torch.randn((2, 256, 256, 6, 1, 6), generator=g) * 0.1
+
+    def loss_of(o, dev):
+        return ((o["cls"] - t_cls.to(dev)) ** 2).mean() + ((o["loc"] - t_loc.to(dev)) ** 2).mean()
+
+    model = FaFNet(default_det_config(), kd_flag=0, num_agent=5)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    ours = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = loss_of(model(bevs.cuda(), batch_size=1), "cuda")
+        loss.backward()
+        opt.step()
+        ours.append(loss.item())
+    # oracle: the same loop with torch autograd over the restatement (float32 CPU)
+    work = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("running_mean", "running_var")) else v.clone())
+            for k, v in sd.items()}
+    params = [v for v in work.values() if v.requires_grad]
+    opt_ref = torch.optim.Adam(params, lr=1e-3)
+    ref = []
+    for _ in range(3):
+        opt_ref.zero_grad()
+        with restate.training_mode():
+            loss = loss_of(restate.fafnet_forward(bevs, work), "cpu")
+        loss.backward()
+        opt_ref.step()
+        ref.append(loss.item())
+    print("adam loop losses ours", ours, "oracle", ref)
+    assert ours[2] < ours[0]
+    for a, b in zip(ours, ref):
+        assert abs(a - b) <= 2e-2 * abs(b)
+
+
+def test_v2vnet_train_step_matches_oracle(golden_dir, parity_log):
+    """det V2VNet in .train(): encoder -> warp / neighbour mean / 3 x ConvGRU (one absent agent slot) -> decoder -> heads;
+    gradients of every parameter that receives one, incl. convgru.* (warp backward, gate backward, mirrored filter)."""
+    from coperception.models.det import V2VNet
+    from oracle import restate
+    from oracle.gen_golden import make_upstream, train_case
+    from v2x_b200 import default_det_config
+    golden = np.load(os.path.join(golden_dir, "train_step_v2vnet_seed21.npz"))
+    sd, inputs, keys = train_case("v2vnet", 21)
+    bevs, trans, nat = inputs
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    shapes = {"loc": (bevs.shape[0], 256, 256, 6, 1, 6), "cls": (bevs.shape[0], 256 * 256 * 6, 2)}
+    up = make_upstream(shapes, 21)
+    out_ref, grads_ref, sd_after = restate.train_step_vjp(
+        lambda s: restate.v2vnet_det_forward(bevs.double(), trans, nat, s, batch_size=1, agent_num=5, gnn_iter=3), sd64, up)
+    model = V2VNet(default_det_config(), 3, 3, 256, num_agent=5)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    out = model(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    for k in ("loc", "cls"):
+        e = _rel(out[k], out_ref[k])
+        print("v2vnet train forward", k, "rel_err %.3e" % e)
+        assert e < 1e-3
+    torch.autograd.backward([out["cls"], out["loc"]], [up["cls"].float().cuda(), up["loc"].float().cuda()])
+    torch.cuda.synchronize()
+    got = {k: p.grad for k, p in model.named_parameters()}
+    # parameters the reference gives no gradient (the unused halves of the two Backbones) must get none here either
+    for k, g in got.items():
+        assert (g is not None) == (k in grads_ref), k
+    _check_grads("train_step_v2vnet_seed21", got, grads_ref, golden, parity_log)
+    after = dict(model.named_buffers())
+    for k, v in sd_after.items():
+        if k.endswith(("running_mean", "running_var")):
+            assert (after[k].double().cpu() - v).abs().max().item() < 1e-5, k

@@ -17,8 +17,18 @@ class FaFNet(B200DetModel):
         """Called with the fusion-model argument list by FaFModule (CoDetModule.py:254-256): ``maps`` /
         ``vis`` receive trans_matrices / num_agent_tensor and are ignored, as in the reference (Q12)."""
         from v2x_b200 import nets, ops
-        self._check_eval()
         dev = bevs.device
+        if self.training:
+            # train-mode forward (BatchNorm batch statistics + running-buffer update) with a backward pass behind
+            # torch.autograd: FaFModule.step's loss.backward() / optimizer.step() drive it (CoDetModule.py:283-291)
+            if dev.type != "cuda":
+                raise RuntimeError("v2x_b200 FaFNet needs CUDA tensors (no CPU fallback); got %s" % dev)
+            if self.kd_flag == 1 or hasattr(self.stpn, "com_compresser"):
+                raise NotImplementedError("training with kd_flag == 1 / compress_level > 0 is not built on the sm_100a path")
+            from v2x_b200.train import FaFNetTrainStep
+            loc, cls = FaFNetTrainStep.apply(self, bevs, *self.parameters())
+            return {"loc": loc, "cls": cls}
+        self._check_eval()
         if dev.type != "cuda":
             raise RuntimeError("v2x_b200 FaFNet needs CUDA tensors (no CPU fallback); got %s" % dev)
         n = int(bevs.shape[0])

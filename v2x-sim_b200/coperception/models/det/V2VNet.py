@@ -30,11 +30,19 @@ class V2VNet(B200DetModel):
         """bevs [A*B,1,256,256,13] (agent-major), trans_matrices [B,A,A,4,4], num_agent_tensor [B,A]
         -> {"loc": [A*B,256,256,6,1,6], "cls": [A*B,393216,2]} (fp32, on bevs.device)."""
         from v2x_b200 import nets
-        self._check_eval()
         dev = bevs.device
         if dev.type != "cuda":
             raise RuntimeError("v2x_b200 V2VNet needs CUDA tensors (no CPU fallback); got %s" % dev)
         assert bevs.shape[0] == batch_size * self.agent_num, "bevs must hold batch_size * num_agent maps"
+        if self.training:
+            # train-mode forward (BatchNorm batch statistics) with the backward pass behind torch.autograd, so the
+            # reference's FaFModule.step (loss.backward() / optimizer.step(), CoDetModule.py:283-291) drives it
+            if self.layer != 3 or self.compress_level > 0:
+                raise NotImplementedError("training on the sm_100a path: layer 3, compress_level 0 (the reference scripts' defaults)")
+            from v2x_b200.train import V2VNetTrainStep
+            loc, cls = V2VNetTrainStep.apply(self, bevs, trans_matrices, num_agent_tensor, int(batch_size), *self.parameters())
+            return {"loc": loc, "cls": cls}
+        self._check_eval()
         # bool / uint8 occupancy grids (the dataset's array before .astype(np.float32)) are expanded on device
         mode = "u8" if bevs.dtype in (torch.uint8, torch.bool) else "f32"
         key = ("v2v", int(batch_size), dev.index, self.precision, mode)

@@ -85,6 +85,18 @@ SYMBOLS = [
     ("v2x_pack_input_u8", C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
     ("v2x_det_nms_fwd", C.c_int, [_P, _P, _P, _I32, _I32, _I32, _F32, _F32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("v2x_restore_absent_fwd", C.c_int, [_P, _P, _P, _I32, _I32, _I64, _I32, _P]),
+    # training step
+    ("v2x_bn_stats_fwd", C.c_int, [_P, _I64, _I32, _I32, _P, _P, _P]),
+    ("v2x_bn_finalize", C.c_int, [_P, _P, _I64, _P, _P, _F32, _F32, _P, _P, _P, _P, _P, _P, _I32, _P]),
+    ("v2x_bn_relu_apply_fwd", C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _I32, _P]),
+    ("v2x_bn_relu_bwd", C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P]),
+    ("v2x_resample2", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_act_add", C.c_int, [_P, _P, _I64, _I32, _P]),
+    ("v2x_conv_wgrad", C.c_int, [_P, _P] + [_I32] * 8 + [_P] + [_I32] * 4 + [_F32, _P]),
+    ("v2x_scale_to_f32", C.c_int, [_P, _P, _I32, _F32, _I32, _P]),
+    ("v2x_gru_gates_fwd", C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _I32, _P]),
+    ("v2x_gru_gates_bwd", C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _I32, _P, _P]),
+    ("v2x_warp_mean_bwd", C.c_int, [_P, _P, _P, _P] + [_I32] * 8 + [_P]),
 ]
 
 _lib = None

@@ -376,6 +376,15 @@ class ConvLaunch:
     def __call__(self):
         check(self.fn(C.byref(self.p), _stream()), "v2x_conv_fwd")
 
+    @property
+    def label(self):
+        """Geometry tag for profiles: e.g. "96>32 k3 s1 256x256 n40 N96 x2" (x = tensor-core passes)."""
+        p = self.p
+        cin = "%d" % p.cin[0] + ("+%d" % p.cin[1] if p.cin[1] else "")
+        epi = {EPI_ACT: "", EPI_F32_SPLIT: " f32", EPI_GRU: " gru", EPI_F32_NCHW: " nchw", EPI_TAIL_F32_SPLIT: " +tail"}[p.epilogue]
+        return "%s>%d k%d s%d %dx%d n%d N%d x%d%s%s" % (cin, p.cout, 3 if p.taps == 9 else 1, p.stride, p.h_out, p.w_out,
+                                                        p.n_maps, p.block_n, self.mma_passes, " up2" if p.upsample2x else "", epi)
+
 
 def conv(pc: PackedConv, srcs, *, relu=True, upsample2x=False, out=None, block_n=None, crosscheck=False):
     """One-off fused conv + (folded BN) + ReLU -> act."""

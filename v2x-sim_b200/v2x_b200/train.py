@@ -1,0 +1,409 @@
+"""Training step of the detection backbone on the sm_100a kernels: train-mode forward (BatchNorm with
+batch statistics over all A*B maps + running-buffer update) and the backward pass, as a tape of kernel launches.
+
+What runs where
+  forward   conv (v2x_conv_fwd, raw output z = W * x + b, fp16 hi/lo, 3 tensor-core passes) -> v2x_bn_stats_fwd ->
+            v2x_bn_finalize (scale / shift + running buffers) -> v2x_bn_relu_apply_fwd
+  backward  v2x_bn_relu_bwd (ReLU mask + BN backward, d gamma / d beta) -> v2x_conv_wgrad (filter gradient) ->
+            data gradient = v2x_conv_fwd with the transposed, 180-degree-rotated filter (transforms.dgrad_weights_stride1;
+            stride-2 layers through v2x_resample2 zero-stuffing) -> v2x_act_add where a map feeds two consumers;
+            nearest-upsample backward = v2x_resample2 mode 2
+torch is plumbing (parameter storage, the autograd.Function boundary, the loss); no FLOP of the path runs in ATen.
+
+Reference semantics: CP/models/det/backbone/Backbone.py:89-242 in .train() mode, DetModelBase.py:226-351 (heads), entered
+through CP/utils/CoDetModule.py:217-291 (``loss.backward()``).  The loss stays the reference's python: it hands
+d(loss)/d(loc), d(loss)/d(cls) to ``backward``.
+
+Gradients are carried in the fp16 hi/lo act format scaled by a power of two S (chosen per step from the upstream
+gradient's magnitude, like a static AMP loss scale) so they sit in fp16's normal range; parameter gradients are unscaled
+in fp32 by the reducing kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import EPI_ACT, EPI_F32_SPLIT, check
+from .ops import ConvLaunch, _ptr, _stream
+from .transforms import dgrad_weights_stride1
+
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+PLANES = 2     # the training path always runs in the fp16 hi/lo format with 3 tensor-core passes (parity mode)
+
+
+class Var:
+    """A map on the tape: forward value (act [P, N, H, W, C]) and its accumulated gradient (same format, scaled by S)."""
+
+    def __init__(self, act: torch.Tensor, c_log: Optional[int] = None):
+        self.act = act
+        self.c_log = c_log if c_log is not None else act.shape[-1]
+        self.grad: Optional[torch.Tensor] = None
+
+    def add_grad(self, lib, g: torch.Tensor):
+        if self.grad is None:
+            self.grad = g
+        else:
+            check(lib.v2x_act_add(_ptr(self.grad), _ptr(g), g[0].numel(), PLANES, _stream()), "v2x_act_add")
+
+
+class Tape:
+    """One training step: forward ops push their backward closures; ``backward`` replays them in reverse."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor], device):
+        self.lib = ops.require_gpu()
+        self.p, self.b, self.dev = params, buffers, device
+        self.grads: Dict[str, torch.Tensor] = {}
+        self.back: List = []
+        self.scale = 1.0
+
+    # ---- helpers ----
+    def _f32(self, *shape):
+        return torch.zeros(shape, dtype=torch.float32, device=self.dev)
+
+    def _f64(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.dev)
+
+    def _param_grad(self, name):
+        if name not in self.grads:
+            self.grads[name] = torch.zeros_like(self.p[name], dtype=torch.float32)
+        return self.grads[name]
+
+    # ---- ops ----
+    def upsample2(self, x: Var) -> Var:
+        p, n, h, w, c = x.act.shape
+        out = ops.empty_act(p, n, 2 * h, 2 * w, c, self.dev)
+        check(self.lib.v2x_resample2(_ptr(x.act), _ptr(out), n, 2 * h, 2 * w, c, p, 1, _stream()), "v2x_resample2(up)")
+        y = Var(out, x.c_log)
+
+        def bwd():
+            if y.grad is None:
+                return
+            g = ops.empty_act(p, n, h, w, c, self.dev)
+            check(self.lib.v2x_resample2(_ptr(y.grad), _ptr(g), n, h, w, c, p, 2, _stream()), "v2x_resample2(sum)")
+            x.add_grad(self.lib, g)
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
+    def _conv_raw(self, wname, bname, srcs: List[Var], stride):
+        """z = conv(cat(srcs), W) + b (no BN fold, no ReLU) as one act; returns (z act, cins logical)."""
+        w = self.p[wname]
+        w4 = w.reshape(w.shape[0], w.shape[1], *(w.shape[-2:] if w.dim() >= 4 and w.shape[-1] == 3 else (1, 1)))
+        cins = [s.c_log for s in srcs]
+        pc = ops.pack_conv(w4, self.p[bname] if bname else None, None, cins=cins, stride=stride, planes=PLANES,
+                           device=self.dev, tap_pack=False, mmas=3)
+        z = ops.conv(pc, [s.act for s in srcs], relu=False)
+        return z, w4, cins
+
+    def _conv_backward(self, wname, w4, srcs: List[Var], cins, stride, dz: torch.Tensor, need_input_grad):
+        """Filter gradient (v2x_conv_wgrad per concat source) and data gradients (v2x_conv_fwd with the transposed,
+        rotated filter; stride 2 through zero-stuffing) of z = conv(cat(srcs), w4)."""
+        lib = self.lib
+        p, n, ho, wo, co_pad = dz.shape
+        co, ci_total, k = w4.shape[0], w4.shape[1], w4.shape[2]
+        taps = k * k
+        dw = self._param_grad(wname)
+        ci_off = 0
+        for s, c_log in zip(srcs, cins):
+            check(lib.v2x_conv_wgrad(_ptr(dz), _ptr(s.act), n, ho, wo, co_pad, s.act.shape[-1], p, stride, taps, _ptr(dw),
+                                     co, c_log, ci_off, ci_total, 1.0 / self.scale, _stream()), "v2x_conv_wgrad")
+            ci_off += c_log
+        ci_off = 0
+        dzin = dz
+        if stride == 2 and any(need_input_grad):
+            dzin = ops.empty_act(p, n, 2 * ho, 2 * wo, co_pad, self.dev)
+            check(lib.v2x_resample2(_ptr(dz), _ptr(dzin), n, 2 * ho, 2 * wo, co_pad, p, 0, _stream()), "v2x_resample2(stuff)")
+        for s, c_log, need in zip(srcs, cins, need_input_grad):
+            if need:
+                wt = dgrad_weights_stride1(w4[:, ci_off:ci_off + c_log])          # [c_log, co, k, k]
+                pcd = ops.pack_conv(wt, None, None, cins=[co], stride=1, planes=PLANES, device=self.dev, tap_pack=False,
+                                    mmas=3, cout_pad=s.act.shape[-1])
+                g = ops.empty_act(p, n, s.act.shape[2], s.act.shape[3], s.act.shape[-1], self.dev)
+                ConvLaunch(pcd, [dzin], relu=False, out0=g, epilogue=EPI_ACT)()
+                s.add_grad(lib, g)
+            ci_off += c_log
+
+    def cbr(self, conv: str, bn: str, srcs: List[Var], stride=1, need_input_grad=None, bias=True) -> Var:
+        """conv + BatchNorm(train) + ReLU (Backbone.py:102-136 in .train() mode)."""
+        lib = self.lib
+        need_input_grad = need_input_grad or [True] * len(srcs)
+        z, w4, cins = self._conv_raw(conv + ".weight", conv + ".bias" if bias else None, srcs, stride)
+        p, n, h, w, c = z.shape
+        npix = n * h * w
+        gamma, beta = self.p[bn + ".weight"], self.p[bn + ".bias"]
+        rm, rv = self.b[bn + ".running_mean"], self.b[bn + ".running_var"]
+        s0, s1 = self._f64(c), self._f64(c)
+        check(lib.v2x_bn_stats_fwd(_ptr(z), npix, c, p, _ptr(s0), _ptr(s1), _stream()), "v2x_bn_stats_fwd")
+        scale, shift, mean, invstd = (self._f32(c) for _ in range(4))
+        check(lib.v2x_bn_finalize(_ptr(s0), _ptr(s1), npix, _ptr(gamma), _ptr(beta), BN_EPS, BN_MOMENTUM, _ptr(rm), _ptr(rv),
+                                  _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), c, _stream()), "v2x_bn_finalize")
+        nbt = self.b.get(bn + ".num_batches_tracked")
+        if nbt is not None:
+            nbt += 1
+        y_act = torch.empty_like(z)
+        check(lib.v2x_bn_relu_apply_fwd(_ptr(z), _ptr(y_act), npix, c, p, _ptr(scale), _ptr(shift), 1, _stream()),
+              "v2x_bn_relu_apply_fwd")
+        y = Var(y_act)
+
+        def bwd():
+            if y.grad is None:
+                return
+            dz = torch.empty_like(z)
+            d1, d2 = self._f64(c), self._f64(c)
+            check(lib.v2x_bn_relu_bwd(_ptr(y.grad), _ptr(z), _ptr(dz), npix, c, p, _ptr(scale), _ptr(shift), _ptr(mean),
+                                      _ptr(invstd), 1, _ptr(d1), _ptr(d2), _stream()), "v2x_bn_relu_bwd")
+            inv = 1.0 / self.scale
+            check(lib.v2x_scale_to_f32(_ptr(d1), _ptr(self._param_grad(bn + ".bias")), c, inv, 1, _stream()), "d beta")
+            check(lib.v2x_scale_to_f32(_ptr(d2), _ptr(self._param_grad(bn + ".weight")), c, inv, 1, _stream()), "d gamma")
+            if bias:
+                self._param_grad(conv + ".bias")    # a conv bias in front of a train-mode BN has an exactly zero gradient
+            self._conv_backward(conv + ".weight", w4, srcs, cins, stride, dz, need_input_grad)
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
+    def conv1x1_out(self, conv: str, src: Var, out_f32: torch.Tensor) -> "OutVar":
+        """Final 1x1 conv with bias and fp32 NHWC output (heads' conv2 / box_prediction.3, DetModelBase.py:283-329)."""
+        lib = self.lib
+        w = self.p[conv + ".weight"]
+        w4 = w.reshape(w.shape[0], w.shape[1], 1, 1)
+        co = w4.shape[0]
+        co_pad = 32 if co <= 32 else ((co + 63) // 64) * 64    # a valid N tile of v2x_conv_fwd for any kc
+        pc = ops.pack_conv(w4, self.p[conv + ".bias"], None, cins=[src.c_log], planes=PLANES, device=self.dev, mmas=3,
+                           cout_pad=co_pad)
+        ConvLaunch(pc, [src.act], epilogue=EPI_F32_SPLIT, relu=False, out0=out_f32, split=co, block_n=min(co_pad, 64))()
+        ov = OutVar(out_f32)
+
+        def bwd():
+            if ov.upstream is None:
+                return
+            p, n, h, wd, _ = src.act.shape
+            up = (ov.upstream.reshape(n, h, wd, co).to(torch.float32) * self.scale).contiguous()
+            dz = ops.pack_input(up, co_pad, PLANES)
+            s0, s1 = self._f64(co_pad), self._f64(co_pad)
+            check(lib.v2x_bn_stats_fwd(_ptr(dz), n * h * wd, co_pad, PLANES, _ptr(s0), _ptr(s1), _stream()), "bias grad")
+            db = self._f32(co_pad)
+            check(lib.v2x_scale_to_f32(_ptr(s0), _ptr(db), co_pad, 1.0 / self.scale, 0, _stream()), "bias grad")
+            self._param_grad(conv + ".bias").add_(db[:co])
+            dw = self._param_grad(conv + ".weight")
+            check(lib.v2x_conv_wgrad(_ptr(dz), _ptr(src.act), n, h, wd, co_pad, src.act.shape[-1], PLANES, 1, 1, _ptr(dw), co,
+                                     src.c_log, 0, w4.shape[1], 1.0 / self.scale, _stream()), "v2x_conv_wgrad(1x1)")
+            wt = w4.transpose(0, 1).contiguous()                     # [cin, co, 1, 1]
+            pcd = ops.pack_conv(wt, None, None, cins=[co], cin_pads=[co_pad], planes=PLANES, device=self.dev, mmas=3)
+            g = torch.empty_like(src.act)
+            ConvLaunch(pcd, [dz], relu=False, out0=g, epilogue=EPI_ACT)()
+            src.add_grad(lib, g)
+        self.back.append(bwd)
+        return ov
+
+    def warp_mean(self, x: Var, trans, num_agent, batch, agents, only_v2i=False) -> Var:
+        """Neighbour mean of the warped maps (V2VNet.py:85-98; self excluded) with its backward (grid_sample backward)."""
+        lib = self.lib
+        out = ops.warp_mean(x.act, trans, num_agent, batch, agents, include_self=False, only_v2i=only_v2i)
+        m = Var(out)
+        p, n, h, w, c = x.act.shape
+
+        def bwd():
+            if m.grad is None:
+                return
+            dx = torch.empty((n, h, w, c), dtype=torch.float32, device=self.dev)
+            check(lib.v2x_warp_mean_bwd(_ptr(m.grad), _ptr(dx), _ptr(trans), _ptr(num_agent), batch, agents, h, w, c, p, 0,
+                                        int(only_v2i), _stream()), "v2x_warp_mean_bwd")
+            x.add_grad(lib, ops.pack_input(dx, c, p))
+            m.grad = None
+        self.back.append(bwd)
+        return m
+
+    def gru_round(self, h: Var, mean: Var, x_pass: Var, num_agent, batch, agents, prefix="convgru.") -> Var:
+        """One zero-hidden ConvGRU step on cat([h, mean]) (V2VNet.py:99-101; functional.py:84-105).  The kernels run in the
+        un-flipped domain, so the filter rows are mirrored; the filter gradient is accumulated in that
+        mirrored form under the key ``<prefix>weight_ih_l0`` and un-mirrored once at the end of the step."""
+        lib = self.lib
+        w_used = torch.flip(self.p[prefix + "weight_ih_l0"], (2,)).contiguous()      # index permutation, no arithmetic
+        c = w_used.shape[0] // 3
+        b_ih, b_hh = self.p[prefix + "bias_ih_l0"], self.p[prefix + "bias_hh_l0"]
+        pc = ops.pack_conv(w_used, b_ih, None, cins=[c, w_used.shape[1] - c], planes=PLANES, device=self.dev, tap_pack=False,
+                           mmas=3)
+        a = ops.conv(pc, [h.act, mean.act], relu=False)
+        p, n, hh, ww, _ = a.shape
+        npix, hw = n * hh * ww, hh * ww
+        out = torch.empty_like(h.act)
+        bhh = b_hh.to(torch.float32).contiguous()
+        check(lib.v2x_gru_gates_fwd(_ptr(a), _ptr(bhh), _ptr(x_pass.act), _ptr(out), npix, hw, c, p, _ptr(num_agent), batch, agents,
+                                    _stream()), "v2x_gru_gates_fwd")
+        y = Var(out)
+
+        def bwd():
+            if y.grad is None:
+                return
+            da = torch.empty_like(a)
+            dpass = torch.empty_like(h.act)
+            dbhn = self._f64(c)
+            check(lib.v2x_gru_gates_bwd(_ptr(y.grad), _ptr(a), _ptr(bhh), _ptr(da), _ptr(dpass), npix, hw, c, p, _ptr(num_agent),
+                                        batch, agents, _ptr(dbhn), _stream()), "v2x_gru_gates_bwd")
+            inv = 1.0 / self.scale
+            s0, s1 = self._f64(3 * c), self._f64(3 * c)
+            check(lib.v2x_bn_stats_fwd(_ptr(da), npix, 3 * c, p, _ptr(s0), _ptr(s1), _stream()), "sum da")
+            g_ih, g_hh = self._param_grad(prefix + "bias_ih_l0"), self._param_grad(prefix + "bias_hh_l0")
+            check(lib.v2x_scale_to_f32(_ptr(s0), _ptr(g_ih), 3 * c, inv, 1, _stream()), "d b_ih")
+            check(lib.v2x_scale_to_f32(_ptr(s0), _ptr(g_hh), 2 * c, inv, 1, _stream()), "d b_hh (r, z)")
+            check(lib.v2x_scale_to_f32(_ptr(dbhn), _ptr(g_hh[2 * c:]), c, inv, 1, _stream()), "d b_hh (n)")
+            self._param_grad(prefix + "weight_hh_l0")     # conv over the all-zero hidden state: exactly zero gradient
+            self._conv_backward(prefix + "weight_ih_l0", w_used, [h, mean], [c, w_used.shape[1] - c], 1, da, [True, True])
+            h.add_grad(lib, dpass)
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
+    def backward(self):
+        for fn in reversed(self.back):
+            fn()
+        self.back = []
+
+
+class OutVar:
+    def __init__(self, t):
+        self.value = t
+        self.upstream: Optional[torch.Tensor] = None
+
+
+def choose_scale(*upstreams) -> float:
+    """Power-of-two gradient scale S that puts the largest upstream magnitude near 2^9 (one host sync per step)."""
+    m = max(float(u.abs().max().item()) for u in upstreams if u is not None)
+    if not math.isfinite(m) or m <= 0.0:
+        return 1.0
+    return float(2.0 ** round(math.log2(512.0 / m)))
+
+
+# =====================================================================================================================
+# network builders
+# =====================================================================================================================
+def backbone_encode(t: Tape, pre: str, x_in: Var):
+    """Backbone.encode in train mode (Backbone.py:89-143); returns [x, x_1, x_2, x_3, x_4]."""
+    x = t.cbr(pre + "conv_pre_1", pre + "bn_pre_1", [x_in], need_input_grad=[False])
+    x0 = t.cbr(pre + "conv_pre_2", pre + "bn_pre_2", [x])
+    x = t.cbr(pre + "conv1_1", pre + "bn1_1", [x0], stride=2)
+    x = t.cbr(pre + "conv1_2", pre + "bn1_2", [x])
+    x1 = t.cbr(pre + "conv3d_1.conv3d", pre + "conv3d_1.bn3d", [x])
+    x = t.cbr(pre + "conv2_1", pre + "bn2_1", [x1], stride=2)
+    x = t.cbr(pre + "conv2_2", pre + "bn2_2", [x])
+    x2 = t.cbr(pre + "conv3d_2.conv3d", pre + "conv3d_2.bn3d", [x])
+    x = t.cbr(pre + "conv3_1", pre + "bn3_1", [x2], stride=2)
+    x3 = t.cbr(pre + "conv3_2", pre + "bn3_2", [x])
+    x = t.cbr(pre + "conv4_1", pre + "bn4_1", [x3], stride=2)
+    x4 = t.cbr(pre + "conv4_2", pre + "bn4_2", [x])
+    return [x0, x1, x2, x3, x4]
+
+
+def backbone_decode(t: Tape, pre: str, x0, x1, x2, x3, x4):
+    """Backbone.decode in train mode (Backbone.py:145-242): cat((up2(deep), skip)) -> two CBRs, four times."""
+    x = t.cbr(pre + "conv5_1", pre + "bn5_1", [t.upsample2(x4), x3])
+    x5 = t.cbr(pre + "conv5_2", pre + "bn5_2", [x])
+    x = t.cbr(pre + "conv6_1", pre + "bn6_1", [t.upsample2(x5), x2])
+    x6 = t.cbr(pre + "conv6_2", pre + "bn6_2", [x])
+    x = t.cbr(pre + "conv7_1", pre + "bn7_1", [t.upsample2(x6), x1])
+    x7 = t.cbr(pre + "conv7_2", pre + "bn7_2", [x])
+    x = t.cbr(pre + "conv8_1", pre + "bn8_1", [t.upsample2(x7), x0])
+    return t.cbr(pre + "conv8_2", pre + "bn8_2", [x])
+
+
+def det_heads(t: Tape, x8: Var, n: int):
+    """ClassificationHead / SingleRegressionHead in train mode (DetModelBase.py:268-351): fp32 NHWC outputs."""
+    dev = t.dev
+    h, w = x8.act.shape[2], x8.act.shape[3]
+    n_cls = t.p["classification.conv2.weight"].shape[0]
+    n_loc = t.p["regression.box_prediction.3.weight"].shape[0]
+    cls = torch.empty((n, h, w, n_cls), dtype=torch.float32, device=dev)
+    loc = torch.empty((n, h, w, n_loc), dtype=torch.float32, device=dev)
+    c1 = t.cbr("classification.conv1", "classification.bn1", [x8])
+    o_cls = t.conv1x1_out("classification.conv2", c1, cls)
+    r1 = t.cbr("regression.box_prediction.0", "regression.box_prediction.1", [x8])
+    o_loc = t.conv1x1_out("regression.box_prediction.3", r1, loc)
+    return o_loc, o_cls
+
+
+class FaFNetTrainStep(torch.autograd.Function):
+    """One train-mode forward of FaFNet / STPN (FaFNet.py:28-39) with its backward, behind torch.autograd so the
+    reference's ``loss.backward()`` / Adam step (CoDetModule.py:283-291) drive it unchanged.
+    Inputs: (module, bevs, *parameters in named_parameters() order); outputs (loc, cls) in the reference layout."""
+
+    @staticmethod
+    def forward(ctx, module, bevs, *params):
+        names = [k for k, _ in module.named_parameters()]
+        p = {k: v.detach() for k, v in zip(names, params)}
+        b = {k: v for k, v in module.named_buffers()}
+        dev = bevs.device
+        n = int(bevs.shape[0])
+        tape = Tape(p, b, dev)
+        x_in = Var(ops.pack_input(bevs.reshape(n, 256, 256, -1).to(torch.float32).contiguous(), 16, PLANES), c_log=int(bevs.shape[-1]))
+        enc = backbone_encode(tape, "stpn.", x_in)
+        x8 = backbone_decode(tape, "stpn.", *enc)
+        o_loc, o_cls = det_heads(tape, x8, n)
+        ctx.tape, ctx.names, ctx.o_loc, ctx.o_cls = tape, names, o_loc, o_cls
+        ctx.shapes = [v.shape for v in params]
+        loc = o_loc.value.view(n, 256, 256, 6, 1, 6)
+        cls = o_cls.value.view(n, -1, 2)
+        return loc, cls
+
+    @staticmethod
+    def backward(ctx, dloc, dcls):
+        tape = ctx.tape
+        ups = [u for u in (dloc, dcls) if u is not None]
+        tape.scale = choose_scale(*ups)
+        ctx.o_loc.upstream, ctx.o_cls.upstream = dloc, dcls
+        tape.backward()
+        grads = []
+        for k, shape in zip(ctx.names, ctx.shapes):
+            g = tape.grads.get(k)
+            grads.append(None if g is None else g.reshape(shape))
+        ctx.tape = None
+        return (None, None, *grads)
+
+
+class V2VNetTrainStep(torch.autograd.Function):
+    """One train-mode forward of det V2VNet (V2VNet.py:47-120: encoder -> 3 x [warp / neighbour mean / ConvGRU] at layer 3
+    -> decoder -> heads) with its backward.  Inputs: (module, bevs, trans_matrices, num_agent_tensor, batch_size,
+    *parameters in named_parameters() order)."""
+
+    @staticmethod
+    def forward(ctx, module, bevs, trans, nat, batch, *params):
+        names = [k for k, _ in module.named_parameters()]
+        p = {k: v.detach() for k, v in zip(names, params)}
+        b = {k: v for k, v in module.named_buffers()}
+        dev = bevs.device
+        n = int(bevs.shape[0])
+        agents = n // batch
+        tape = Tape(p, b, dev)
+        trans = trans.to(device=dev, dtype=torch.float64).contiguous()
+        nat = nat.to(device=dev, dtype=torch.int64).contiguous()
+        x_in = Var(ops.pack_input(bevs.reshape(n, 256, 256, -1).to(torch.float32).contiguous(), 16, PLANES), c_log=int(bevs.shape[-1]))
+        x0, x1, x2, x3, x4 = backbone_encode(tape, "u_encoder.", x_in)
+        mean = tape.warp_mean(x3, trans, nat, batch, agents, only_v2i=bool(module.only_v2i))
+        h = x3
+        for _ in range(module.gnn_iter_num):
+            h = tape.gru_round(h, mean, x3, nat, batch, agents)
+        x8 = backbone_decode(tape, "decoder.", x0, x1, x2, h, x4)
+        o_loc, o_cls = det_heads(tape, x8, n)
+        ctx.tape, ctx.names, ctx.o_loc, ctx.o_cls = tape, names, o_loc, o_cls
+        ctx.shapes = [v.shape for v in params]
+        return o_loc.value.view(n, 256, 256, 6, 1, 6), o_cls.value.view(n, -1, 2)
+
+    @staticmethod
+    def backward(ctx, dloc, dcls):
+        tape = ctx.tape
+        tape.scale = choose_scale(*[u for u in (dloc, dcls) if u is not None])
+        ctx.o_loc.upstream, ctx.o_cls.upstream = dloc, dcls
+        tape.backward()
+        k = "convgru.weight_ih_l0"
+        if k in tape.grads:
+            tape.grads[k] = torch.flip(tape.grads[k], (2,))      # back from the mirrored-row form the kernels ran in
+        grads = []
+        for name, shape in zip(ctx.names, ctx.shapes):
+            g = tape.grads.get(name)
+            grads.append(None if g is None else g.reshape(shape))
+        ctx.tape = None
+        return (None, None, None, None, None, *grads)
