@@ -366,6 +366,12 @@ int v2x_gru_gates_bwd(const void* dh, const void* a, const float* bhh, void* da,
 int v2x_warp_mean_bwd(const void* dmean, float* dx, const double* trans, const int64_t* num_agent, int32_t batch, int32_t agents,
                       int32_t h, int32_t w, int32_t c, int32_t planes, int32_t include_self, int32_t only_v2i, void* stream);
 
+/* v2x_conv_wgrad on the tensor cores: a GEMM with M = co, N = ci per filter tap, K = pixels whose operands are the NHWC act
+ * tensors themselves, consumed as MN-major UMMA operands (csrc/wgrad_tc.cu); same arguments and result */
+int v2x_conv_wgrad_tc(const void* dz, const void* x, int32_t n, int32_t h_out, int32_t w_out, int32_t co, int32_t ci, int32_t planes,
+                      int32_t stride, int32_t taps, float* dw, int32_t co_log, int32_t ci_log, int32_t ci_off, int32_t ci_total,
+                      float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -162,3 +162,47 @@ def test_v2vnet_train_step_matches_oracle(golden_dir, parity_log):
     for k, v in sd_after.items():
         if k.endswith(("running_mean", "running_var")):
             assert (after[k].double().cpu() - v).abs().max().item() < 1e-5, k
+
+
+WG_CASES = [  # name, co, ci (logical), stride, taps, n, h_out, w_out
+    ("c64_64", 64, 64, 1, 9, 2, 16, 32), ("c128_64", 128, 64, 1, 9, 1, 16, 16), ("c32_96", 32, 96, 1, 9, 1, 24, 40),
+    ("c256_128", 256, 128, 1, 9, 1, 8, 16), ("c32_32", 32, 32, 1, 9, 1, 16, 16), ("c32_13", 32, 13, 1, 9, 1, 16, 16),
+    ("c64_64_1x1", 64, 64, 1, 1, 1, 16, 16), ("c12_32_1x1", 12, 32, 1, 1, 1, 16, 16), ("s2_128_64", 128, 64, 2, 9, 1, 8, 8),
+    ("s2_64_32", 64, 32, 2, 9, 1, 8, 16), ("odd_hw", 64, 64, 1, 9, 1, 10, 20)]
+
+
+@pytest.mark.parametrize("impl", ["cuda", "tc"])
+@pytest.mark.parametrize("case", WG_CASES, ids=[c[0] for c in WG_CASES])
+def test_conv_wgrad_kernels(case, impl):
+    """v2x_conv_wgrad (CUDA cores) and v2x_conv_wgrad_tc (tcgen05, MN-major operands) vs torch's conv2d weight gradient:
+    channel counts below / above one 64-channel MN block, two concat-style channel offsets, stride 2 through the parity
+    view, 1x1, map sizes that are not multiples of the 4x16 K block (TMA zero fill)."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from v2x_b200 import ops
+    from v2x_b200._lib import check
+    name, co, ci, stride, taps, n, ho, wo = case
+    lib = ops.require_gpu()
+    if impl == "tc" and stride == 2 and ci % 64:
+        pytest.skip("stride-2 tensor-core wgrad needs 64 | ci (the training tape uses the CUDA-core kernel there)")
+    g = torch.Generator().manual_seed(sum(ord(ch) for ch in name))
+    k = 3 if taps == 9 else 1
+    x = torch.randn((n, ci, ho * stride, wo * stride), generator=g)
+    dz = torch.randn((n, co, ho, wo), generator=g)
+    w = torch.zeros((co, ci, k, k), requires_grad=True)
+    F.conv2d(x, w, stride=stride, padding=k // 2).backward(dz)
+    ref = w.grad
+    pad16 = lambda c: ((c + 15) // 16) * 16   # noqa: E731
+    xa = ops.pack_input(F.pad(x, (0, 0, 0, 0, 0, pad16(ci) - ci)).permute(0, 2, 3, 1).contiguous().cuda(), pad16(ci), 2)
+    da = ops.pack_input(F.pad(dz, (0, 0, 0, 0, 0, pad16(co) - co)).permute(0, 2, 3, 1).contiguous().cuda(), pad16(co), 2)
+    ci_total, ci_off = ci + 8, 8          # as one source of a concat: the filter has 8 more input channels in front
+    dw = torch.zeros((co, ci_total, k, k), dtype=torch.float32, device="cuda")
+    fn = lib.v2x_conv_wgrad_tc if impl == "tc" else lib.v2x_conv_wgrad
+    check(fn(C.c_void_p(da.data_ptr()), C.c_void_p(xa.data_ptr()), n, ho, wo, pad16(co), pad16(ci), 2, stride, taps,
+             C.c_void_p(dw.data_ptr()), co, ci, ci_off, ci_total, 0.5, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+          "wgrad")
+    torch.cuda.synchronize()
+    assert dw[:, :ci_off].abs().max().item() == 0.0
+    err = ((dw[:, ci_off:].cpu() - 0.5 * ref).abs().max() / (0.5 * ref).abs().max()).item()
+    print("wgrad %s %s rel_err %.3e" % (impl, name, err))
+    assert err < 2e-4, err

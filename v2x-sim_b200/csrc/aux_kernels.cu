@@ -377,39 +377,56 @@ extern "C" int v2x_act_to_nchw_f32(const void* act, float* out, int32_t n, int32
 // =============================================================================================
 namespace v2x {
 
-// y[r][o] = [relu](b[o] + sum_i w[o][i] * x[r][i]); one warp per output element, lanes stride the reduction.
-// in_mode 1 reads x from an act tensor [planes][rows][hw][c] in NCHW-flatten order (i = ch * hw + px), which is
+// y[r][o] = [relu](b[o] + sum_i w[o][i] * x[r][i]).  Block = (row r, group of kLinOut outputs): the input row is staged in
+// shared memory ONCE (for in_mode 1 that is the strided NCHW-order gather out of the NHWC act tensor -- the expensive part:
+// round 1 redid it for every output, 177 us for the 4096 -> 256 layer of the seg model), then each warp reduces its
+// outputs against it with coalesced float4 weight reads.
+// in_mode 1 reads x from an act tensor [planes][maps][hw][c] in NCHW-flatten order (i = ch * hw + px), which is
 // how `features_map.view(-1, n_feat)` flattens the policy maps (When2com.py:429).
-__global__ void linear_kernel(const void* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                              float* __restrict__ y, int rows, int in_f, int out_f, int relu, int in_mode, int hw,
-                              int c, int planes, int split, int maps) {
-  const int lane = threadIdx.x & 31;
-  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (gw >= (long long)rows * out_f) return;
-  const int r = (int)(gw / out_f), o = (int)(gw % out_f);
-  const float* wr = w + (long long)o * in_f;
-  float acc = 0.f;
+constexpr int kLinOut = 32;      // outputs per block (8 warps x 4)
+__global__ void __launch_bounds__(256) linear_kernel(const void* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ b, float* __restrict__ y, int rows, int in_f,
+                                                     int out_f, int relu, int in_mode, int hw, int c, int planes, int split,
+                                                     int maps) {
+  extern __shared__ __align__(16) float s_x[];     // [in_f]
+  const int r = blockIdx.y, o0 = blockIdx.x * kLinOut;
   if (in_mode == 0) {
     const float* xr = reinterpret_cast<const float*>(x) + (long long)r * in_f;
-    for (int i = lane; i < in_f; i += 32) acc = fmaf(__ldg(wr + i), __ldg(xr + i), acc);
+    for (int i = threadIdx.x; i < in_f; i += blockDim.x) s_x[i] = __ldg(xr + i);
   } else {
     // virtual row r of `.view(-1, in_f)` over maps flattened in NCHW order: map r / split, channels
-    // [(r % split) * c / split, ...) -- split > 1 reproduces the seg when2com quirk (When2Com_UNet.py:207-226, Q9)
+    // [(r % split) * c / split, ...) -- split > 1 reproduces the seg when2com quirk (When2Com_UNet.py:207-226, Q9).
+    // Gather pixel-major (consecutive threads -> consecutive channels of one pixel: coalesced), scatter into NCHW order.
     const __nv_bfloat16* xa = reinterpret_cast<const __nv_bfloat16*>(x);
     const long long plane_stride = (long long)maps * hw * c;
-    const int map = r / split, ch_base = (r % split) * (c / split);
-    for (int i = lane; i < in_f; i += 32) {
-      const int ch = ch_base + i / hw, px = i % hw;
-      const long long idx = ((long long)map * hw + px) * c + ch;
-      const float v = act_load1(xa + idx, plane_stride, planes);
-      acc = fmaf(__ldg(wr + i), v, acc);
+    const int map = r / split, cs = c / split, ch_base = (r % split) * cs;
+    for (int j = threadIdx.x; j < in_f; j += blockDim.x) {
+      const int px = j / cs, ch = j - px * cs;
+      s_x[ch * hw + px] = act_load1(xa + ((long long)map * hw + px) * c + ch_base + ch, plane_stride, planes);
     }
   }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = 0; k < kLinOut / 8; ++k) {
+    const int o = o0 + warp * (kLinOut / 8) + k;
+    if (o >= out_f) break;
+    const float* wr = w + (long long)o * in_f;
+    float acc = 0.f;
+    if ((in_f & 3) == 0) {
+      for (int i = lane * 4; i < in_f; i += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + i));
+        const float4 xv = *reinterpret_cast<const float4*>(s_x + i);
+        acc = fmaf(wv.x, xv.x, acc); acc = fmaf(wv.y, xv.y, acc); acc = fmaf(wv.z, xv.z, acc); acc = fmaf(wv.w, xv.w, acc);
+      }
+    } else {
+      for (int i = lane; i < in_f; i += 32) acc = fmaf(__ldg(wr + i), s_x[i], acc);
+    }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) {
-    acc += b ? b[o] : 0.f;
-    y[(long long)r * out_f + o] = relu ? fmaxf(acc, 0.f) : acc;
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      acc += b ? b[o] : 0.f;
+      y[(long long)r * out_f + o] = relu ? fmaxf(acc, 0.f) : acc;
+    }
   }
 }
 
@@ -424,15 +441,25 @@ __global__ void attn_scores_kernel(const float* __restrict__ keys, const float* 
   float* qp = sm;                    // [agents][ks]
   float* sc = sm + agents * ks;      // [agents][agents]
   const int b = blockIdx.x;
-  for (int idx = threadIdx.x; idx < agents * ks; idx += blockDim.x) {
-    const int j = idx / ks, d = idx - j * ks;
-    const float* q = querys + ((long long)batch * j + b) * qs;
-    float a = bw[d];
-    for (int t = 0; t < qs; ++t) a = fmaf(w[(long long)d * qs + t], q[t], a);
-    qp[idx] = a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // q'[j][d] = bw[d] + sum_t W[d][t] * q_j[t]: one warp per feature d, lanes over t (coalesced reads of W's row d; round 1
+  // walked W with a stride of qs floats per thread and took 100 us for 5 x 1024 features)
+  for (int d = warp; d < ks; d += nw) {
+    float wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) wv[u] = (lane + 32 * u) < qs ? __ldg(w + (long long)d * qs + lane + 32 * u) : 0.f;
+    for (int j = 0; j < agents; ++j) {
+      const float* q = querys + ((long long)batch * j + b) * qs;
+      float a = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (lane + 32 * u < qs) a = fmaf(wv[u], __ldg(q + lane + 32 * u), a);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane == 0) qp[j * ks + d] = a + bw[d];
+    }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int pair = warp; pair < agents * agents; pair += nw) {
     const int k = pair / agents, j = pair - k * agents;
     const float* key = keys + ((long long)batch * k + b) * ks;
@@ -566,9 +593,10 @@ extern "C" int v2x_linear_fwd(const void* x, const float* w, const float* b, flo
   V2X_REQUIRE(in_mode == 0 || (in_mode == 1 && hw > 0 && c > 0 && c % split == 0 && hw * (c / split) == in_f &&
                                maps > 0 && rows <= maps * split && (planes == 1 || planes == 2)),
               "bad act input geometry");
-  const long long threads = (long long)rows * out_f * 32;
-  linear_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, b, y, rows, in_f, out_f, relu,
-                                                                                    in_mode, hw, c, planes, split, maps);
+  V2X_REQUIRE((size_t)in_f * sizeof(float) <= 48 * 1024, "in_f too large for the staged linear kernel (<= 12288)");
+  const dim3 grid((unsigned)((out_f + v2x::kLinOut - 1) / v2x::kLinOut), (unsigned)rows);
+  linear_kernel<<<grid, 256, (size_t)in_f * sizeof(float), (cudaStream_t)stream>>>(x, w, b, y, rows, in_f, out_f, relu, in_mode,
+                                                                                hw, c, planes, split, maps);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }
@@ -577,11 +605,11 @@ extern "C" int v2x_attn_scores_fwd(const float* keys, const float* querys, const
                                    float* attn, float* coef, int32_t batch, int32_t agents, int32_t key_size,
                                    int32_t query_size, int32_t gate_mode, void* stream) {
   V2X_REQUIRE(keys && querys && w && bw && attn && coef, "null pointer");
-  V2X_REQUIRE(batch > 0 && agents > 0 && agents <= 8 && key_size > 0 && query_size > 0, "bad sizes");
+  V2X_REQUIRE(batch > 0 && agents > 0 && agents <= 8 && key_size > 0 && query_size > 0 && query_size <= 128, "bad sizes");
   V2X_REQUIRE(gate_mode >= 0 && gate_mode <= 2, "gate_mode must be 0 (softmax), 1 (activated) or 2 (argmax)");
   const size_t smem = ((size_t)agents * key_size + agents * agents) * sizeof(float);
   V2X_REQUIRE(smem <= 48 * 1024, "key_size too large for the score kernel");
-  attn_scores_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(keys, querys, w, bw, attn, coef, batch, agents, key_size,
+  attn_scores_kernel<<<batch, 1024, smem, (cudaStream_t)stream>>>(keys, querys, w, bw, attn, coef, batch, agents, key_size,
                                                               query_size, gate_mode);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
@@ -676,15 +704,18 @@ __global__ void upsample_bilinear2_kernel(const __nv_bfloat16* __restrict__ x, _
                                           int h, int w, int c, int planes) {
   const int groups = c / 8;
   const int oh_n = 2 * h, ow_n = 2 * w;
-  const long long total = (long long)n * oh_n * ow_n * groups;
   const long long in_plane = (long long)n * h * w * c, out_plane = (long long)n * oh_n * ow_n * c;
   const float sy = oh_n > 1 ? (float)(h - 1) / (float)(oh_n - 1) : 0.f;
   const float sx = ow_n > 1 ? (float)(w - 1) / (float)(ow_n - 1) : 0.f;
-  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-       gid += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(gid % groups);
-    const long long pix = gid / groups;
-    const int ox = (int)(pix % ow_n), oy = (int)((pix / ow_n) % oh_n), im = (int)(pix / ((long long)ow_n * oh_n));
+  // 32-bit index arithmetic (the 64-bit divisions of a flat index dominated round 1's version: 1.8 TB/s): blockIdx.y walks
+  // the output rows (image * oh_n + oy), the x dimension of the grid the (pixel, channel group) items of one row
+  const unsigned row_items = (unsigned)ow_n * (unsigned)groups;
+  for (unsigned row = blockIdx.y; row < (unsigned)n * (unsigned)oh_n; row += gridDim.y)
+  for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < row_items; it += gridDim.x * blockDim.x) {
+    const int g = (int)(it % (unsigned)groups);
+    const int ox = (int)(it / (unsigned)groups);
+    const int oy = (int)(row % (unsigned)oh_n), im = (int)(row / (unsigned)oh_n);
+    const long long pix = ((long long)im * oh_n + oy) * ow_n + ox;
     const float fy = oy * sy, fx = ox * sx;
     const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
     const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
@@ -730,8 +761,11 @@ extern "C" int v2x_upsample_bilinear2_fwd(const void* x, void* out, int32_t n, i
                                           int32_t planes, void* stream) {
   V2X_REQUIRE(x && out && n > 0 && h_in > 0 && w_in > 0 && c > 0 && c % 8 == 0, "bad geometry");
   V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
-  const long long total = (long long)n * 4 * h_in * w_in * (c / 8);
-  upsample_bilinear2_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+  const unsigned row_items = 2u * (unsigned)w_in * (unsigned)(c / 8);
+  unsigned rows = (unsigned)n * 2u * (unsigned)h_in;
+  if (rows > 65535u) rows = 65535u;
+  const dim3 grid((row_items + 255u) / 256u, rows);
+  upsample_bilinear2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n, h_in, w_in, c, planes);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;

@@ -93,6 +93,7 @@ SYMBOLS = [
     ("v2x_resample2", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_act_add", C.c_int, [_P, _P, _I64, _I32, _P]),
     ("v2x_conv_wgrad", C.c_int, [_P, _P] + [_I32] * 8 + [_P] + [_I32] * 4 + [_F32, _P]),
+    ("v2x_conv_wgrad_tc", C.c_int, [_P, _P] + [_I32] * 8 + [_P] + [_I32] * 4 + [_F32, _P]),
     ("v2x_scale_to_f32", C.c_int, [_P, _P, _I32, _F32, _I32, _P]),
     ("v2x_gru_gates_fwd", C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _I32, _P]),
     ("v2x_gru_gates_bwd", C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _I32, _P, _P]),

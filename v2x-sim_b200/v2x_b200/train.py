@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -32,6 +33,8 @@ from .ops import ConvLaunch, _ptr, _stream
 from .transforms import dgrad_weights_stride1
 
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+WGRAD_TC = os.environ.get("V2X_WGRAD", "tc") != "cuda"       # A/B switch: tensor-core vs CUDA-core weight gradient
+WGRAD_TC_MIN_C = int(os.environ.get("V2X_WGRAD_TC_MIN_C", "16"))
 PLANES = 2     # the training path always runs in the fp16 hi/lo format with 3 tensor-core passes (parity mode)
 
 
@@ -109,8 +112,13 @@ class Tape:
         dw = self._param_grad(wname)
         ci_off = 0
         for s, c_log in zip(srcs, cins):
-            check(lib.v2x_conv_wgrad(_ptr(dz), _ptr(s.act), n, ho, wo, co_pad, s.act.shape[-1], p, stride, taps, _ptr(dw),
-                                     co, c_log, ci_off, ci_total, 1.0 / self.scale, _stream()), "v2x_conv_wgrad")
+            # tensor-core wgrad (MN-major operands straight from the NHWC tensors); the CUDA-core kernel covers what it
+            # cannot take: the stride-2 layer with fewer than 64 input channels (conv1_1)
+            ci_phys = s.act.shape[-1]
+            use_tc = WGRAD_TC and (stride == 1 or ci_phys % 64 == 0) and min(ci_phys, co_pad) >= WGRAD_TC_MIN_C
+            fn = lib.v2x_conv_wgrad_tc if use_tc else lib.v2x_conv_wgrad
+            check(fn(_ptr(dz), _ptr(s.act), n, ho, wo, co_pad, ci_phys, p, stride, taps, _ptr(dw),
+                     co, c_log, ci_off, ci_total, 1.0 / self.scale, _stream()), "v2x_conv_wgrad")
             ci_off += c_log
         ci_off = 0
         dzin = dz
