@@ -3,7 +3,8 @@
 
   python bench.py --gpus N --steps K --warmup W            our sm_100a path (one rank per GPU)
   python bench.py --impl reference ...                      the UNMODIFIED reference modules on the host's cores
-  python bench.py --config {v2v_det,faf_lower,w2c_seg,faf_upper_dp}   the BASELINE.json configs (default v2v_det)
+  python bench.py --config {v2v_det,faf_lower,w2c_seg,faf_upper_dp,w2c_det}   the BASELINE.json configs (default v2v_det)
+                                                                             + when2com detection (unit-sharded under torchrun)
 
 Default (= the metric, BASELINE configs[1]; configs[3] under torchrun): 5-agent V2VNet detection.  A *frame* is one
 scene: all 5 agents' 256x256x13 BEVs -> all agents' loc/cls.  A *step* is one forward over
@@ -64,6 +65,10 @@ CONFIGS = {
     "w2c_seg": dict(metric="frames/sec 5-agent When2Com_UNet seg fwd", unit="frames/s", gflop=581.38, maps_per_unit=5,
                     units=4, workload="when2com 5-agent BEV segmentation fwd (warp_flag=1, inference=activated), "
                                       "256x256x13 BEV -> 8-class logits (BASELINE configs[2])"),
+    "w2c_det": dict(metric="frames/sec 5-agent When2com det fwd", unit="frames/s", gflop=308.44, maps_per_unit=5, units=8,
+                    workload="when2com / who2com 5-agent detection fwd (warp_flag=1, inference=activated: two decoder "
+                             "passes), 256x256x13 BEV; under torchrun the units are sharded and keys [units,1024] / "
+                             "queries [units,32] are all-gathered (SURVEY 8(e))"),
     "faf_upper_dp": dict(metric="frames/sec 6-agent FaFNet upperbound fwd", unit="frames/s", gflop=186.96,
                          maps_per_unit=6, units=4,
                          workload="FaFNet upperbound early-fusion detection fwd, 6 agents (RSU+5) per scene, batch 32 "
@@ -193,6 +198,17 @@ def _cpu_forwards(config):
             m.load_state_dict(sd, strict=True)
             m.eval()
             fns["reference"] = lambda: m(bevs)
+    elif config == "w2c_det":
+        sd = synth.when2com_det_state(0)
+        bevs, trans, nat = synth.make_scene(1, AGENTS, seed=0)
+        fns["port"] = lambda: restate.when2com_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=AGENTS, warp_flag=1,
+                                                           inference="activated")
+        if ref_loader.available():
+            with quiet():
+                m = ref_loader.ref_when2com_det(warp_flag=1, num_agent=AGENTS)
+            m.load_state_dict(sd, strict=True)
+            m.eval()
+            fns["reference"] = lambda: m(bevs, trans, nat, training=False, MO_flag=True, inference="activated", batch_size=1)
     elif config == "w2c_seg":
         sd = synth.seg_when2com_state(0)
         x, trans, nat = synth.make_seg_scene(1, AGENTS, 0)
@@ -599,6 +615,7 @@ def run_generic(args, rank, world, local_rank):
     mpu = cfg["maps_per_unit"]
     n_maps = U * mpu
     timer = Timer(dev, world)
+    sharded_note = None
     if args.config in ("faf_lower", "faf_upper_dp"):
         from coperception.models.det import FaFNet
         sd = synth.fafnet_state(0)
@@ -613,6 +630,35 @@ def run_generic(args, rank, world, local_rank):
             out = model(d_bev, batch_size=U)
             return out["loc"], out["cls"]
         api = "coperception.models.det.FaFNet.forward"
+    elif args.config == "w2c_det":
+        from coperception.models.det import When2com
+        sd = synth.when2com_det_state(0)
+        bevs, trans, nat = synth.make_scene(U, AGENTS, seed=rank)
+        if world > 1 and args.shard == "unit":
+            # unit-sharded: a scene's agents live on different GPUs; keys / queries are all-gathered every step
+            from v2x_b200 import sharding
+            gb, gt, gn = synth.make_scene(U * world, AGENTS, seed=0)
+            off, n_loc = sharding.unit_range(U * world * AGENTS, rank, world)
+            plan = nets.When2comDetShardedPlan(sd, U * world, AGENTS, rank, world, planes=args.precision, device=dev,
+                                               warp_flag=1, inference="activated")
+            plan.bev_in.copy_(gb[off:off + n_loc].reshape(plan.bev_in.shape).to(dev))
+            plan.trans.copy_(gt.to(dev))
+            plan.num_agent.copy_(gn.to(dev))
+            sharded_note = "unit-sharded x%d, NCCL all-gather of keys [units,1024] and queries [units,32] per step" % world
+            del gb
+        else:
+            plan = nets.When2comDetPlan(sd, U, AGENTS, planes=args.precision, device=dev, warp_flag=1, inference="activated")
+            plan.bev_in.copy_(bevs.reshape(plan.bev_in.shape).to(dev))
+            plan.trans.copy_(trans.to(dev))
+            plan.num_agent.copy_(nat.to(dev))
+        model = When2com(default_det_config(), layer=3, warp_flag=1, num_agent=AGENTS)
+        host_inputs = [bevs, trans, nat]
+        out_shapes = [(n_maps, 256, 256, 6, 1, 6), (n_maps, 256 * 256 * 6, 2)]
+
+        def call(d_bev, d_trans, d_nat):
+            out = model(d_bev, d_trans, d_nat, training=False, MO_flag=True, inference="activated", batch_size=U)
+            return out["loc"], out["cls"]
+        api = "coperception.models.det.When2com.forward"
     else:
         from coperception.models.seg import When2Com_UNet
         sd = synth.seg_when2com_state(0)
@@ -662,7 +708,8 @@ def run_generic(args, rank, world, local_rank):
             "config": {"workload": cfg["workload"], "units_per_gpu_per_step": U, "maps_per_unit": mpu,
                        "precision": args.precision,
                        "l2": "no flush: per-step inputs %.0f MB and activations exceed the 126 MB L2" % in_mb,
-                       "parallelism": "replicas x%d (no exchange step in this forward), no data-path collective" % world},
+                       "parallelism": sharded_note or
+                       "replicas x%d (no exchange step in this forward), no data-path collective" % world},
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": cfg["unit"], "h2d_bytes_per_step": pipe.h2d,
                     "d2h_bytes_per_step": pipe.d2h, "ms_per_step": e2e_ms / args.steps,
                     "api": api + " (pinned host in/out, 3-stream pipeline)"},

@@ -209,10 +209,13 @@ int v2x_attn_scores_fwd(const float* keys, const float* querys, const float* w, 
  *                val_mat[b,k,q] pairing (When2com.py:206-225,397-412); agents q >= na[b] give zeros
  *   warp_flag 0: out[b,q] = sum_{k<A} coef[b,k,q] * x[b,k]
  * Replaces the [B,A,A,C,H,W] val_mat + broadcast multiply + sum (never materialised here).
+ * Unit-sharded plans: targets [unit_offset, unit_offset + unit_count) of the agent-major units are computed (out is
+ * indexed locally) from an x tensor holding units [x_unit_offset, x_unit_offset + x_units); 0 counts = all units.
  */
 int v2x_warp_gated_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent, const float* coef,
                        int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes,
-                       int32_t warp_flag, int32_t only_v2i, void* stream);
+                       int32_t warp_flag, int32_t only_v2i, int32_t unit_offset, int32_t unit_count,
+                       int32_t x_unit_offset, int32_t x_units, void* stream);
 
 /* ---- intermediate-fusion baselines (CP/models/det/base/FusionBase.py, CP/models/seg/FusionBase.py) ---------- */
 

@@ -32,37 +32,7 @@ if _SRC not in sys.path:
 from v2x_b200.synthetic import (BACKBONE_BNS, BACKBONE_CONVS, BOX_CODE, CATEGORY_NUM, MAP_DIMS, NUM_ANCHORS,  # noqa: E402,F401
                                 _Gen, _bn, _conv, backbone_state, heads_state, make_bevs, make_poses, make_scene,
                                 make_trans_matrices, plant_detections, v2vnet_det_state, fafnet_state, SEG_DOUBLE_CONVS,
-                                _double_conv, seg_unet_state, seg_when2com_state, make_seg_scene)
-
-
-def when2com_det_state(seed=0):
-    """state_dict of det When2com(config, layer=3, warp_flag=..) (CP/models/det/When2com.py:22-92):
-    V2VNet-style heads / u_encoder / decoder plus key_net / query_net MLPs (:415-430), attention_net.linear
-    (:370) and query_key_net = PolicyNet4 (a full Backbone + five Conv2DBatchNormRelu, :335-359)."""
-    g = _Gen(seed)
-    sd = OrderedDict()
-    heads_state(sd, g)
-    backbone_state(sd, g, "u_encoder.")
-    backbone_state(sd, g, "decoder.")
-
-    def linear(name, out_f, in_f, gain=3.0):
-        b = math.sqrt(gain / in_f)
-        sd[name + ".weight"] = g.uniform((out_f, in_f), -b, b)
-        sd[name + ".bias"] = g.uniform((out_f,), -0.1, 0.1)
-
-    for net, out in (("key_net", 1024), ("query_net", 32)):
-        linear(net + ".fc.0", 256, 4096, gain=6.0)
-        linear(net + ".fc.2", 128, 256, gain=6.0)
-        linear(net + ".fc.4", out, 128)
-    # small so that the 5x5 softmax is neither uniform nor one-hot
-    sd["attention_net.linear.weight"] = g.uniform((1024, 32), -0.03, 0.03)
-    sd["attention_net.linear.bias"] = g.uniform((1024,), -0.02, 0.02)
-    backbone_state(sd, g, "query_key_net.lidar_encoder.")
-    for name, cout, cin in (("conv1", 512, 512), ("conv2", 256, 512), ("conv3", 256, 256), ("conv4", 256, 256),
-                            ("conv5", 256, 256)):
-        _conv(sd, g, "query_key_net.%s.cbr_unit.0" % name, cout, cin)
-        _bn(sd, g, "query_key_net.%s.cbr_unit.1" % name, cout)
-    return sd
+                                _double_conv, seg_unet_state, seg_when2com_state, make_seg_scene, when2com_det_state)
 
 
 def seg_v2vnet_state(seed=0, n_classes=8):

@@ -55,14 +55,15 @@ def test_measured_arm_line():
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
 
 
-@pytest.mark.parametrize("config,unit", [("faf_lower", "agent-frames/s"), ("w2c_seg", "frames/s"), ("faf_upper_dp", "frames/s")])
+@pytest.mark.parametrize("config,unit", [("faf_lower", "agent-frames/s"), ("w2c_seg", "frames/s"), ("faf_upper_dp", "frames/s"),
+                                         ("w2c_det", "frames/s")])
 def test_reference_arm_other_configs(config, unit):
     d = _run(["--impl", "reference", "--config", config, "--steps", "1", "--warmup", "1"], 900)
     assert d["impl"] == "reference" and d["unit"] == unit and d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("config", ["faf_lower", "w2c_seg", "faf_upper_dp"])
+@pytest.mark.parametrize("config", ["faf_lower", "w2c_seg", "faf_upper_dp", "w2c_det"])
 def test_measured_arm_other_configs(config):
     d = _run(["--config", config, "--steps", "2", "--warmup", "3", "--no-cpu-baseline"], 900)
     assert (BASE_KEYS | {"roofline", "clocks", "gpu_launches"}) <= set(d)

@@ -1,6 +1,6 @@
 """Multi-GPU correctness of the unit-sharded V2VNet plan (run under torchrun, one rank per GPU):
 every rank's slice of loc/cls must equal the same slice of the single-GPU plan (bit-identical: same kernels, same
-per-unit math) and match the CPU oracle within the bf16x3 tolerance."""
+per-unit math) and match the CPU oracle within the 1e-3 tolerance in the default "mixed" precision."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "v2x-sim_b200")]
@@ -19,9 +19,9 @@ def main():
     bevs, trans, nat = synth.make_scene(B, A, seed=7, present=present)
     off, n = sharding.unit_range(B * A, rank, world)
     ok = True
-    for planes in (2, 1):
+    for planes in ("mixed", "bf16"):
         plan = nets.V2VNetDetShardedPlan(sd, B, A, rank, world, planes=planes,
-                                         exchange=os.environ.get("V2X_EXCHANGE", "neighbours" if planes == 2 else "allgather"))
+                                         exchange=os.environ.get("V2X_EXCHANGE", "neighbours" if planes == "mixed" else "allgather"))
         out = plan.forward(bevs[off:off + n].cuda(), trans.cuda(), nat.cuda())
         torch.cuda.synchronize()
         eager = {k: v.clone() for k, v in out.items()}
@@ -37,10 +37,12 @@ def main():
         # coincide and equal to fp32 reassociation error (<< the 1e-3 parity tolerance) otherwise.
         ident = all(torch.equal(out[k], ref_full[k][off:off + n]) for k in out)
         diff = max(((out[k] - ref_full[k][off:off + n]).abs().max() / ref_full[k].abs().max()).item() for k in out)
-        same = ident or diff < (1e-4 if planes == 2 else 2e-2)
-        msg = "rank %d planes=%d: graph==eager %s, sharded vs single-GPU slice: identical %s, rel diff %.2e" % (
+        # mixed: remote neighbours arrive as their fp16 hi plane only (the GRU reads the mean through one 11-bit pass anyway,
+        # nets.V2VNetDetShardedPlan.exchange_planes), so the slice differs from the single-GPU plan by that rounding
+        same = ident or diff < (4e-4 if planes == "mixed" else 2e-2)
+        msg = "rank %d %s: graph==eager %s, sharded vs single-GPU slice: identical %s, rel diff %.2e" % (
             rank, planes, graph_same, ident, diff)
-        if planes == 2 and rank == 0:
+        if planes == "mixed" and rank == 0:
             with torch.no_grad():
                 o = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=B, agent_num=A)
             err = max(((out[k].cpu() - o[k][off:off + n]).abs().max() / o[k].abs().max()).item() for k in out)
@@ -48,6 +50,26 @@ def main():
             ok = ok and err < 1e-3
         print(msg, flush=True)
         ok = ok and graph_same and same
+        del plan, full
+    # ---- When2com: all-gather of keys [units,1024] / queries [units,32] (+ x_3 when warp_flag = 0) ----
+    sdw = synth.when2com_det_state(9)
+    for warp_flag, inference in ((1, "activated"), (0, "argmax_test")):
+        plan = nets.When2comDetShardedPlan(sdw, B, A, rank, world, planes="mixed", warp_flag=warp_flag, inference=inference)
+        out = plan.forward(bevs[off:off + n].cuda(), trans.cuda(), nat.cuda())
+        torch.cuda.synchronize()
+        eager = {k: v.clone() for k, v in out.items()}
+        plan.capture()
+        out = plan.forward(bevs[off:off + n].cuda(), trans.cuda(), nat.cuda())
+        torch.cuda.synchronize()
+        graph_same = all(torch.equal(eager[k], out[k]) for k in out)
+        full = nets.When2comDetPlan(sdw, B, A, planes="mixed", warp_flag=warp_flag, inference=inference)
+        ref_full = full.forward(bevs.cuda(), trans.cuda(), nat.cuda())
+        torch.cuda.synchronize()
+        diff = max(((out[k] - ref_full[k][off:off + n]).abs().max() / ref_full[k].abs().max()).item() for k in out)
+        gates = torch.equal(plan.coef > 0, full.coef > 0)
+        print("rank %d when2com warp=%d %s: graph==eager %s, gates identical %s, sharded vs single-GPU slice rel diff %.2e"
+              % (rank, warp_flag, inference, graph_same, gates, diff), flush=True)
+        ok = ok and graph_same and gates and diff < 1e-4
         del plan, full
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -499,16 +499,20 @@ template <int VEC_PER_LANE>
 __global__ void warp_gated_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                   const double* __restrict__ trans, const long long* __restrict__ num_agent,
                                   const float* __restrict__ coef, int batch, int agents, int H, int W, int C,
-                                  int planes, int warp_flag, int only_v2i) {
+                                  int planes, int warp_flag, int only_v2i, int unit_offset, int unit_count,
+                                  int x_unit_offset, int x_units) {
+  // unit-sharded plans: this launch computes targets [unit_offset, unit_offset + unit_count) of the agent-major units
+  // (output indexed locally) from an x tensor holding units [x_unit_offset, x_unit_offset + x_units)
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long total_pix = (long long)batch * agents * H * W;
-  const long long plane_stride = total_pix * C;
+  const long long total_pix = (long long)unit_count * H * W;
+  const long long plane_stride = (long long)x_units * H * W * C;
+  const long long out_plane_stride = total_pix * C;
   for (long long wid = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total_pix;
        wid += (long long)gridDim.x * warps_per_block) {
     const int ow = (int)(wid % W);
     const int oh = (int)((wid / W) % H);
-    const int map = (int)(wid / ((long long)W * H));
+    const int map = (int)(wid / ((long long)W * H)) + unit_offset;
     const int q = map / batch, b = map % batch;
     const int na = (int)num_agent[(long long)b * agents];
     float acc[VEC_PER_LANE][8];
@@ -522,7 +526,7 @@ __global__ void warp_gated_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
       const float cf = coef[((long long)b * agents + k) * agents + q];
       if (cf == 0.f) continue;
       if (warp_flag && only_v2i && k != q && k != 0 && q != 0) continue;
-      const long long src_map = warp_flag ? (long long)batch * q + b : (long long)batch * k + b;
+      const long long src_map = (warp_flag ? (long long)batch * q + b : (long long)batch * k + b) - x_unit_offset;
       float wts[4];
       int xs[4], ys[4];
       int ntap = 4;
@@ -577,7 +581,7 @@ __global__ void warp_gated_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
           act_pack2(acc[v][2 * e], acc[v][2 * e + 1], planes, hi[e], lo[e]);
         }
         *reinterpret_cast<uint4*>(dp + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (planes == 2) *reinterpret_cast<uint4*>(dp + plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (planes == 2) *reinterpret_cast<uint4*>(dp + out_plane_stride + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
   }
@@ -617,12 +621,22 @@ extern "C" int v2x_attn_scores_fwd(const float* keys, const float* querys, const
 
 extern "C" int v2x_warp_gated_fwd(const void* x, void* out, const double* trans, const int64_t* num_agent,
                                   const float* coef, int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c,
-                                  int32_t planes, int32_t warp_flag, int32_t only_v2i, void* stream) {
+                                  int32_t planes, int32_t warp_flag, int32_t only_v2i, int32_t unit_offset,
+                                  int32_t unit_count, int32_t x_unit_offset, int32_t x_units, void* stream) {
   V2X_REQUIRE(x && out && trans && num_agent && coef, "null pointer");
   V2X_REQUIRE(batch > 0 && agents > 0 && h > 0 && w > 0, "empty geometry");
   V2X_REQUIRE(c > 0 && c % 8 == 0 && c <= 1024, "channels must be a multiple of 8, <= 1024");
   V2X_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
-  const long long total_pix = (long long)batch * agents * h * w;
+  if (unit_count <= 0) { unit_offset = 0; unit_count = batch * agents; }
+  if (x_units <= 0) { x_unit_offset = 0; x_units = batch * agents; }
+  V2X_REQUIRE(unit_offset >= 0 && unit_offset + unit_count <= batch * agents, "target unit range out of bounds");
+  V2X_REQUIRE(x_unit_offset >= 0 && x_unit_offset + x_units <= batch * agents, "source unit range out of bounds");
+  // warp_flag 1 reads only the target's own map (val_mat[b,k,q] = q's map warped into k's frame); warp_flag 0
+  // reads every agent of the scene
+  V2X_REQUIRE(warp_flag ? (x_unit_offset <= unit_offset && unit_offset + unit_count <= x_unit_offset + x_units)
+                        : (x_unit_offset == 0 && x_units == batch * agents),
+              "x does not hold the units this launch reads");
+  const long long total_pix = (long long)unit_count * h * w;
   const int threads = 256;
   const unsigned grid = grid_for(total_pix * 32, threads, 8);
   const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -630,11 +644,14 @@ extern "C" int v2x_warp_gated_fwd(const void* x, void* out, const double* trans,
   const long long* na = reinterpret_cast<const long long*>(num_agent);
   cudaStream_t s = (cudaStream_t)stream;
   if (c <= 256)
-    warp_gated_kernel<1><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i);
+    warp_gated_kernel<1><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i, unit_offset, unit_count,
+                                                  x_unit_offset, x_units);
   else if (c <= 512)
-    warp_gated_kernel<2><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i);
+    warp_gated_kernel<2><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i, unit_offset, unit_count,
+                                                  x_unit_offset, x_units);
   else
-    warp_gated_kernel<4><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i);
+    warp_gated_kernel<4><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i, unit_offset, unit_count,
+                                                  x_unit_offset, x_units);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }

@@ -76,7 +76,7 @@ SYMBOLS = [
     ("v2x_maxpool2_fwd", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_upsample_bilinear2_fwd", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_attn_scores_fwd", C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
-    ("v2x_warp_gated_fwd", C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    ("v2x_warp_gated_fwd", C.c_int, [_P, _P, _P, _P, _P] + [_I32] * 12 + [_P]),
     ("v2x_warp_reduce_fwd", C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_pair_score_fwd", C.c_int, [_P] * 10 + [_I32] * 6 + [_P]),
     ("v2x_agent_softmax_fwd", C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),

@@ -509,6 +509,13 @@ class V2VNetDetShardedPlan(DetPlan):
         c3 = x3.shape[-1]
         self.x3_local = x3
         self.x3_all = ops.empty_act(planes, n_loc * world, 32, 32, c3, dev)
+        self.x3_all.zero_()
+        # Planes that cross the wire.  The gathered maps only feed the neighbour mean, and in the "mixed" precision the
+        # ConvGRU reads that mean through ONE tensor-core pass (its fp16 hi plane, 11 bits): sending the neighbours' lo
+        # planes would move twice the bytes for bits the consumer rounds away.  So only the hi plane of REMOTE units is
+        # exchanged (their lo plane stays zero); this rank's own units keep both planes.  Measured at 8 GPUs the all-gather
+        # of both planes (294 MB received per rank) left 0.33 ms of a 4.8 ms step exposed.  V2X_EXCHANGE_PLANES overrides.
+        self.exchange_planes = int(os.environ.get("V2X_EXCHANGE_PLANES", 0)) or (1 if (planes == 2 and prec.mmas("gru") == 1) else planes)
         x3_all = self.x3_all
         mean = self.act("mean", 32, 32, c3)
         self.add(lambda: ops.warp_mean(x3_all, trans, na, batch_total, agents, include_self=False, only_v2i=only_v2i,
@@ -525,12 +532,15 @@ class V2VNetDetShardedPlan(DetPlan):
         seg = self._segments()
         for i in range(3):
             if i == 1:   # x_3 is final: exchange it while the x_4 branch runs
+                ep = self.exchange_planes
                 if self.exchange == "neighbours":
-                    works = self.sharding.exchange_neighbour_units(self.x3_local, self.x3_all, self.batch, self.agents,
-                                                                   group=self.group)
+                    works = self.sharding.exchange_neighbour_units(self.x3_local[:ep], self.x3_all[:ep], self.batch,
+                                                                   self.agents, group=self.group)
                 else:
-                    _, works = self.sharding.all_gather_units(self.x3_local, out=self.x3_all, group=self.group,
+                    _, works = self.sharding.all_gather_units(self.x3_local[:ep], out=self.x3_all[:ep], group=self.group,
                                                               async_op=True)
+                if ep < self.planes:   # own units keep their lo plane
+                    self.x3_all[ep:, self.offset:self.offset + self.n].copy_(self.x3_local[ep:], non_blocking=True)
             if i == 2:
                 for w in works:
                     w.wait()   # stream-level wait: the fuse kernels queue behind the collective
@@ -566,6 +576,139 @@ class V2VNetDetShardedPlan(DetPlan):
 
     def forward(self, bevs_local, trans_matrices, num_agent_tensor):
         self.set_inputs(bevs_local, trans_matrices, num_agent_tensor)
+        self.run()
+        return self.result()
+
+
+class When2comDetShardedPlan(DetPlan):
+    """det When2com / who2com forward (eval), unit-sharded across ``world`` ranks ("When2com additionally
+    all-gathers keys [units,1024] and queries [units,32]").
+
+    Every rank runs both encoders, the key / query MLPs, the two decoder passes and the heads for its contiguous slice of
+    the agent-major units.  The exchange step: one NCCL all-gather of the keys and of the queries (rows = global units; a
+    few hundred KB) -- the 5x5 attention of every scene needs the keys of all its agents -- after which each rank evaluates
+    the (tiny) attention kernel for all scenes and fuses its own targets.  With warp_flag = 1 the fuse of target q reads
+    only q's OWN map warped into the other agents' frames (the reference's val_mat[b,k,q] pairing), so no
+    feature maps cross the wire at all; with warp_flag = 0 it reads every agent's map and x_3 is all-gathered too.
+    The forward is two CUDA graphs around the collectives."""
+
+    def __init__(self, sd, batch_total: int, agents: int, rank: int, world: int, planes=1, device="cuda", group=None,
+                 warp_flag=1, inference="activated", only_v2i=False):
+        from . import sharding
+        self.offset, n_loc = sharding.unit_range(batch_total * agents, rank, world)
+        super().__init__(n_loc, planes, device)
+        prec, planes = self.prec, self.prec.planes
+        ops.require_gpu()
+        self.sharding, self.group, self.world = sharding, group, world
+        self.batch, self.agents, self.warp_flag = batch_total, agents, warp_flag
+        dev = self.device
+        f32 = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        self.enc_w = BackboneWeights(sd, "u_encoder.", prec, dev, encoder=True, decoder=False)
+        self.dec_w = BackboneWeights(sd, "decoder.", prec, dev, encoder=False, decoder=True)
+        self.pol_w = BackboneWeights(sd, "query_key_net.lidar_encoder.", prec if planes == 1 else "fp16x3", dev,
+                                     encoder=True, decoder=False)
+        self.head_w = HeadWeights(sd, prec, dev)
+        self.pol_convs = []
+        for name, stride, cin in (("conv1", 1, 512), ("conv2", 1, 512), ("conv3", 2, 256), ("conv4", 1, 256),
+                                  ("conv5", 2, 256)):
+            pre = "query_key_net.%s.cbr_unit." % name
+            self.pol_convs.append(ops.pack_conv(sd[pre + "0.weight"], sd[pre + "0.bias"], _bn(sd, pre + "1"), cins=[cin],
+                                                stride=stride, planes=planes, device=dev))
+        self.mlp = {net: [(f32("%s.fc.%d.weight" % (net, i)), f32("%s.fc.%d.bias" % (net, i))) for i in (0, 2, 4)]
+                    for net in ("key_net", "query_net")}
+        self.att_w, self.att_b = f32("attention_net.linear.weight"), f32("attention_net.linear.bias")
+        self.trans = torch.zeros((batch_total, agents, agents, 4, 4), dtype=torch.float64, device=dev)
+        self.num_agent = torch.full((batch_total, agents), agents, dtype=torch.int64, device=dev)
+        trans, na, off = self.trans, self.num_agent, self.offset
+        units = batch_total * agents
+
+        x_in = self.build_input()
+        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
+        t = self.build_encoder(self.pol_w, x_in, tag="pol_", upsample_x4=False)[4]
+        for i, pc in enumerate(self.pol_convs):
+            t = self.conv(pc, [t], "pol_c%d" % (i + 1))
+        qk = t
+        feats = {}
+        for net in ("key_net", "query_net"):
+            (w0, b0), (w1, b1), (w2, b2) = self.mlp[net]
+            h0 = torch.empty((n_loc, w0.shape[0]), dtype=torch.float32, device=dev)
+            h1 = torch.empty((n_loc, w1.shape[0]), dtype=torch.float32, device=dev)
+            h2 = torch.empty((n_loc, w2.shape[0]), dtype=torch.float32, device=dev)
+            self.add(lambda w0=w0, b0=b0, h0=h0: ops.linear(qk, w0, b0, relu=True, out=h0, act_input=True))
+            self.add(lambda w1=w1, b1=b1, h0=h0, h1=h1: ops.linear(h0, w1, b1, relu=True, out=h1))
+            self.add(lambda w2=w2, b2=b2, h1=h1, h2=h2: ops.linear(h1, w2, b2, relu=False, out=h2))
+            feats[net] = h2
+        self.keys_local, self.querys_local = feats["key_net"], feats["query_net"]
+        self.stage_a = len(self.launches)            # ---- keys / queries (and x_3) ready: the exchange happens here
+        self.keys = torch.empty((units, self.keys_local.shape[1]), dtype=torch.float32, device=dev)
+        self.querys = torch.empty((units, self.querys_local.shape[1]), dtype=torch.float32, device=dev)
+        self.x3_local = x3
+        c3 = x3.shape[-1]
+        x_src, x_off = x3, off
+        if not warp_flag:
+            self.x3_all = ops.empty_act(planes, units, 32, 32, c3, dev)
+            x_src, x_off = self.x3_all, 0
+        self.attn = torch.empty((batch_total, agents, agents), dtype=torch.float32, device=dev)
+        self.coef = torch.empty((batch_total, agents, agents), dtype=torch.float32, device=dev)
+        gate = ops.GATE_MODES[inference]
+        keys, querys, attn, coef, aw, ab = self.keys, self.querys, self.attn, self.coef, self.att_w, self.att_b
+        self.add(lambda: ops.attn_scores(keys, querys, aw, ab, batch_total, agents, gate, attn=attn, coef=coef))
+        fuse1 = self.act("fuse1", 32, 32, c3)
+        self.add(lambda: ops.warp_gated(x_src, trans, na, attn, batch_total, agents, warp_flag=warp_flag, only_v2i=only_v2i,
+                                        out=fuse1, unit_offset=off, unit_count=n_loc, x_unit_offset=x_off))
+        x8 = self.build_decoder(self.dec_w, x0, x1, x2, fuse1, x4u)
+        if inference != "softmax":
+            fuse2 = self.act("fuse2", 32, 32, c3)
+            self.add(lambda: ops.warp_gated(x_src, trans, na, coef, batch_total, agents, warp_flag=warp_flag,
+                                            only_v2i=only_v2i, out=fuse2, unit_offset=off, unit_count=n_loc,
+                                            x_unit_offset=x_off))
+            x8 = self.build_decoder(self.dec_w, x8, x1, x2, fuse2, x4u, tag="p2_")
+        self.build_heads(self.head_w, x8)
+        self.graphs = None
+
+    def _segments(self):
+        return (self.launches[:self.stage_a], self.launches[self.stage_a:])
+
+    def _exchange(self):
+        self.sharding.all_gather_units(self.keys_local, out=self.keys, group=self.group)
+        self.sharding.all_gather_units(self.querys_local, out=self.querys, group=self.group)
+        if not self.warp_flag:
+            self.sharding.all_gather_units(self.x3_local, out=self.x3_all, group=self.group)
+
+    def run(self):
+        seg = self._segments()
+        for i in range(2):
+            if i == 1:
+                self._exchange()      # stream-ordered NCCL collectives between the two graphs
+            if self.graphs is not None:
+                self.graphs[i].replay()
+            else:
+                for l in seg[i]:
+                    l()
+
+    def capture(self):
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                for l in self.launches:
+                    l()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graphs = []
+        for seg in self._segments():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for l in seg:
+                    l()
+            graphs.append(g)
+        self.graphs = graphs
+
+    def forward(self, bevs_local, trans_matrices, num_agent_tensor):
+        """bevs_local: this rank's unit slice [n_loc,1,256,256,13]; poses / agent counts of ALL scenes."""
+        self.bev_in.copy_(bevs_local.reshape(self.bev_in.shape), non_blocking=True)
+        self.trans.copy_(trans_matrices.reshape(self.trans.shape), non_blocking=True)
+        self.num_agent.copy_(num_agent_tensor.reshape(self.num_agent.shape), non_blocking=True)
         self.run()
         return self.result()
 

@@ -452,15 +452,20 @@ def attn_scores(keys, querys, w, bw, batch, agents, gate_mode, attn=None, coef=N
     return attn, coef
 
 
-def warp_gated(x, trans, num_agent, coef, batch, agents, *, warp_flag=1, only_v2i=False, out=None):
-    """when2com fuse: out[b,q] = sum_k coef[b,k,q] * val[b,k,q] without materialising val_mat."""
+def warp_gated(x, trans, num_agent, coef, batch, agents, *, warp_flag=1, only_v2i=False, out=None, unit_offset=0,
+               unit_count=0, x_unit_offset=0):
+    """when2com fuse: out[b,q] = sum_k coef[b,k,q] * val[b,k,q] without materialising val_mat.
+    ``unit_offset/unit_count`` restrict the computed targets to a slice of the agent-major units (unit-sharded plans);
+    ``x`` then holds units [x_unit_offset, x_unit_offset + x.shape[1])."""
     lib = require_gpu()
     planes, n, h, w, c = x.shape
-    assert n == batch * agents and coef.dtype == torch.float32 and coef.is_contiguous()
+    full = unit_count <= 0
+    assert (n == batch * agents if full else True) and coef.dtype == torch.float32 and coef.is_contiguous()
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty_like(x) if full else empty_act(planes, unit_count, h, w, c, x.device)
     check(lib.v2x_warp_gated_fwd(_ptr(x), _ptr(out), _ptr(trans), _ptr(num_agent), _ptr(coef), batch, agents, h, w, c,
-                                 planes, int(warp_flag), int(only_v2i), _stream()), "v2x_warp_gated_fwd")
+                                 planes, int(warp_flag), int(only_v2i), unit_offset, 0 if full else unit_count,
+                                 0 if full else x_unit_offset, 0 if full else n, _stream()), "v2x_warp_gated_fwd")
     return out
 
 
