@@ -1,0 +1,120 @@
+"""CPU tests of the host-side logic added in round 2: precision modes / per-layer pass policy, the plan-cache fingerprint
+and output-aliasing rules of the drop-in modules, the staged-reference recipe, bench.py's config table."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_precision_modes_and_policy(monkeypatch):
+    from v2x_b200 import precision
+    assert precision.resolve(1).name == "bf16" and precision.resolve(2).name == "fp16x3"
+    assert precision.resolve("bf16x3").name == "fp16x3"          # round-1 name kept as an alias
+    assert precision.resolve(None).name == precision.DEFAULT == os.environ.get("V2X_PRECISION", "mixed")
+    with pytest.raises(ValueError):
+        precision.resolve("fp8")
+    bf, x3, mx = precision.resolve("bf16"), precision.resolve("fp16x3"), precision.resolve("mixed")
+    assert (bf.planes, x3.planes, mx.planes) == (1, 2, 2)
+    for layer in ("conv_pre_1", "conv5_1", "gru", "heads"):
+        assert bf.mmas(layer) == 1 and x3.mmas(layer) == 3
+    # the measured policy: GRU 1 pass, conv5_1 2 passes, everything else 3
+    assert mx.mmas("gru") == 1 and mx.mmas("conv5_1") == 2
+    assert all(mx.mmas(l) == 3 for l in ("conv_pre_1", "conv4_2", "conv6_1", "conv7_1", "conv8_1", "conv8_2", "heads"))
+    monkeypatch.setenv("V2X_MIXED_POLICY", "gru=2,conv8_1=2")
+    assert mx.mmas("gru") == 2 and mx.mmas("conv8_1") == 2 and mx.mmas("conv5_1") == 3
+    assert precision.resolve(mx) is mx and mx == precision.Precision("mixed") and hash(mx) == hash(precision.Precision("mixed"))
+
+
+def test_weight_format_of_each_pass_count():
+    from v2x_b200 import ops
+    assert ops.weight_fmt(1, 1) == (ops.FMT_BF16, 1)
+    assert ops.weight_fmt(2, 3) == (ops.FMT_F16X2, 2)
+    assert ops.weight_fmt(2, 2) == (ops.FMT_F16, 1) and ops.weight_fmt(2, 1) == (ops.FMT_F16, 1)
+    assert ops.act_dtype(1) == torch.bfloat16 and ops.act_dtype(2) == torch.float16
+
+
+def _v2v():
+    from coperception.models.det import V2VNet
+    from v2x_b200 import default_det_config
+    return V2VNet(default_det_config(), 3, 3, 256, num_agent=5)
+
+
+def test_default_precision_and_fingerprint_on_cpu():
+    """The plan cache is keyed by a fingerprint of every parameter's (pointer, version): tracked in-place edits change it,
+    reads do not; `verify_weights` adds a value checksum that also sees edits through .data."""
+    m = _v2v()
+    assert m.precision == os.environ.get("V2X_PRECISION", "mixed") and m.alias_outputs is False
+    f0 = m._fingerprint()
+    assert m._fingerprint() == f0
+    with torch.no_grad():
+        m.classification.conv2.bias.add_(1.0)
+    f1 = m._fingerprint()
+    assert f1 != f0
+    m.classification.conv2.bias.data.add_(1.0)       # bypasses the version counter
+    assert m._fingerprint() == f1
+    m.verify_weights = True
+    f2 = m._fingerprint()
+    m.classification.conv2.bias.data.add_(1.0)
+    assert m._fingerprint() != f2
+    sd = m.state_dict()
+    m._plans["x"] = (0, object())
+    m.load_state_dict(sd)
+    assert m._plans == {}                             # load_state_dict invalidates
+
+
+def test_outputs_are_cloned_unless_aliased():
+    m = _v2v()
+    static = torch.zeros(4)
+    m._static_ptrs.add(static.data_ptr())
+    other = torch.ones(3)
+    out = m._out({"cls": static.view(2, 2), "loc": other})
+    assert out["cls"].data_ptr() != static.data_ptr() and out["loc"] is other
+    tup = m._out((static, (other, static)))
+    assert tup[0].data_ptr() != static.data_ptr() and tup[1][0] is other and tup[1][1].data_ptr() != static.data_ptr()
+    m.alias_outputs = True
+    assert m._out({"cls": static})["cls"] is static
+
+
+def test_forward_refuses_cpu_tensors_and_eval_warning_is_once():
+    m = _v2v().eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros((5, 1, 256, 256, 13)), torch.zeros((1, 5, 5, 4, 4)), torch.full((1, 5), 5), batch_size=1)
+
+
+def test_training_is_offered_where_built_and_refused_elsewhere():
+    """FaFNet / det V2VNet route .train() forwards to the training tape (which needs CUDA tensors); the others raise."""
+    from coperception.models.det import FaFNet, When2com
+    from v2x_b200 import default_det_config
+    f = FaFNet(default_det_config(), kd_flag=0).train()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        f(torch.zeros((1, 1, 256, 256, 13)))
+    with pytest.raises(NotImplementedError):
+        FaFNet(default_det_config(), kd_flag=1).train()(torch.zeros((1, 1, 256, 256, 13)))
+    w = When2com(default_det_config(), layer=3).train()
+    with pytest.raises(NotImplementedError):
+        w(torch.zeros((5, 1, 256, 256, 13)), torch.zeros((1, 5, 5, 4, 4)), torch.full((1, 5), 5), batch_size=1)
+
+
+def test_make_ref_stages_the_reference_and_ref_loader_finds_it(tmp_path, monkeypatch):
+    from oracle import make_ref
+    if not os.path.isdir(os.path.join(make_ref.SRC, "models", "det")):
+        pytest.skip("reference tree only exists in the build container")
+    monkeypatch.setattr(make_ref, "DST", str(tmp_path / "_ref" / "coperception"))
+    make_ref.main(quiet=True)
+    for rel in ("models/det/V2VNet.py", "models/seg/When2Com_UNet.py", "configs/Config.py", "utils/convolutional_rnn/module.py"):
+        assert os.path.exists(os.path.join(make_ref.DST, rel)), rel
+    assert not any(f.endswith(".so") for _, _, fs in os.walk(make_ref.DST) for f in fs)
+
+
+def test_bench_config_table():
+    spec = importlib.util.spec_from_file_location("bench_cfg", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert set(bench.CONFIGS) >= {"v2v_det", "faf_lower", "w2c_seg", "faf_upper_dp", "w2c_det"}
+    # algorithmic GFLOP per unit, SURVEY.md section 8(d)
+    assert bench.CONFIGS["v2v_det"]["gflop"] == 264.51 and bench.CONFIGS["faf_lower"]["gflop"] == 31.16
+    assert bench.CONFIGS["w2c_seg"]["gflop"] == 581.38 and abs(bench.CONFIGS["faf_upper_dp"]["gflop"] - 6 * 31.16) < 1e-9
+    assert set(bench.DTYPE_OF) == {"mixed", "fp16x3", "bf16"}
