@@ -375,6 +375,14 @@ int v2x_conv_wgrad_tc(const void* dz, const void* x, int32_t n, int32_t h_out, i
                       int32_t stride, int32_t taps, float* dw, int32_t co_log, int32_t ci_log, int32_t ci_off, int32_t ci_total,
                       float scale, void* stream);
 
+/* nn.MaxPool2d(2) backward: x act [n][2h][2w][c] (the forward input), dy act [n][h][w][c] -> dx act like x (gradient to the
+ * first maximum of each window, SegModelBase.py:113) */
+int v2x_maxpool2_bwd(const void* x, const void* dy, void* dx, int32_t n, int32_t h_out, int32_t w_out, int32_t c, int32_t planes,
+                     void* stream);
+/* nn.Upsample(x2, bilinear, align_corners=True) backward (SegModelBase.py:125): dy act [n][2h][2w][c] -> dx fp32 [n][h][w][c] */
+int v2x_upsample_bilinear2_bwd(const void* dy, float* dx, int32_t n, int32_t h_in, int32_t w_in, int32_t c, int32_t planes,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

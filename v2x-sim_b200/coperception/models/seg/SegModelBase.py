@@ -59,8 +59,18 @@ class SegModelBase(PlanCacheMixin, nn.Module):
         self._init_plan_cache()
 
     def _check(self, x):
-        if self.training:
-            raise NotImplementedError("the sm_100a path implements inference (model.eval()); training is not built yet")
-        self._warn_no_grad_graph()
         if x.device.type != "cuda":
             raise RuntimeError("v2x_b200 seg models need CUDA tensors (no CPU fallback); got %s" % x.device)
+        if self.training:
+            raise NotImplementedError("the sm_100a path trains seg UNet and seg V2VNet; this model only implements "
+                                      "inference (model.eval())")
+        self._warn_no_grad_graph()
+
+    def _train_forward(self, x, fuse=None):
+        """Train-mode forward with a backward pass behind torch.autograd (v2x_b200/train.py::SegTrainStep)."""
+        if self.compress_level > 0 or getattr(self, "kd_flag", False):
+            raise NotImplementedError("training with compress_level > 0 / kd_flag is not built on the sm_100a path")
+        if x.device.type != "cuda":
+            raise RuntimeError("v2x_b200 seg models need CUDA tensors (no CPU fallback); got %s" % x.device)
+        from v2x_b200.train import SegTrainStep
+        return SegTrainStep.apply(self, fuse, x, *self.parameters())

@@ -12,6 +12,8 @@ class UNet(SegModelBase):
     def forward(self, x):
         """x [N,13,256,256] fp32 -> logits [N,n_classes,256,256]."""
         from v2x_b200 import nets_seg
+        if self.training:
+            return self._train_forward(x)
         self._check(x)
         n = int(x.shape[0])
         plan = self._get_plan(("unet", n, x.device.index, self.precision),

@@ -14,8 +14,10 @@ class V2VNet(SegModelBase):
 
     def forward(self, x, trans_matrices, num_agent_tensor):
         from v2x_b200 import nets_seg
-        self._check(x)
         batch = int(x.shape[0]) // self.num_agent
+        if self.training:
+            return self._train_forward(x, (trans_matrices, num_agent_tensor, batch, self.num_agent, bool(self.only_v2i)))
+        self._check(x)
         plan = self._get_plan(("v2v", batch, x.device.index, self.precision),
                               lambda: nets_seg.SegV2VNetPlan(self._state(), batch, self.num_agent, planes=self._planes(),
                                                              device=x.device, only_v2i=self.only_v2i))

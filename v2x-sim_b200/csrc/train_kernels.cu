@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
                                                              int relu, double* __restrict__ out0, double* __restrict__ out1) {
-  __shared__ double s0[1024], s1[1024];
+  extern __shared__ double s_red[];     // [2][c]
+  double* s0 = s_red;
+  double* s1 = s_red + c;
   const int groups = c / 8;
   const int lanes = blockDim.x / groups;          // pixel lanes per block (host guarantees groups <= 128 -> lanes >= 2)
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
@@ -460,6 +462,77 @@ __global__ void __launch_bounds__(256) warp_mean_bwd_kernel(const __nv_bfloat16*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Segmentation UNet pieces, backward (CP/models/seg/SegModelBase.py:113,125 under loss.backward()).
+// ---------------------------------------------------------------------------------------------
+// nn.MaxPool2d(2) backward: the gradient of an output pixel goes to the FIRST maximum of its 2x2 window in scan order
+// (ATen keeps a value only if it is strictly greater than the running maximum), the other three get zero.
+__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                    __nv_bfloat16* __restrict__ dx, int n, int h, int w, int c, int planes) {
+  const int groups = c / 8;
+  const long long total = (long long)n * h * w * groups;
+  const long long in_plane = (long long)n * 4 * h * w * c, out_plane = (long long)n * h * w * c;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(gid % groups);
+    const long long pix = gid / groups;
+    const int ox = (int)(pix % w), oy = (int)((pix / w) % h), im = (int)(pix / ((long long)w * h));
+    const long long base = (((long long)im * 2 * h + 2 * oy) * 2 * w + 2 * ox) * c + g * 8;
+    const long long off[4] = {0, (long long)c, (long long)2 * w * c, (long long)2 * w * c + c};
+    float v[4][8], d[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) act_load8(x + base + off[t], in_plane, planes, v[t]);
+    act_load8(dy + pix * c + g * 8, out_plane, planes, d);
+    int arg[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int a = 0;
+      float m = v[0][e];
+#pragma unroll
+      for (int t = 1; t < 4; ++t)
+        if (v[t][e] > m) { m = v[t][e]; a = t; }
+      arg[e] = a;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = arg[e] == t ? d[e] : 0.f;
+      act_store8(dx + base + off[t], in_plane, planes, o);
+    }
+  }
+}
+
+// nn.Upsample(scale_factor=2, bilinear, align_corners=True) backward: scatter of dy [n][2h][2w][c] into dx fp32 [n][h][w][c]
+// (zeroed by the caller) with the forward's interpolation weights
+__global__ void upsample_bilinear2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ dx, int n, int h, int w,
+                                              int c, int planes) {
+  const int groups = c / 8;
+  const int oh_n = 2 * h, ow_n = 2 * w;
+  const long long total = (long long)n * oh_n * ow_n * groups;
+  const long long plane = (long long)n * oh_n * ow_n * c;
+  const float sy = oh_n > 1 ? (float)(h - 1) / (float)(oh_n - 1) : 0.f;
+  const float sx = ow_n > 1 ? (float)(w - 1) / (float)(ow_n - 1) : 0.f;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(gid % groups);
+    const long long pix = gid / groups;
+    const int ox = (int)(pix % ow_n), oy = (int)((pix / ow_n) % oh_n), im = (int)(pix / ((long long)ow_n * oh_n));
+    const float fy = oy * sy, fx = ox * sx;
+    const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float wy1 = fy - (float)y0, wx1 = fx - (float)x0, wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+    float d[8];
+    act_load8(dy + pix * c + g * 8, plane, planes, d);
+    float* b = dx + (long long)im * h * w * c + g * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(b + ((long long)y0 * w + x0) * c + e, wy0 * wx0 * d[e]);
+      atomicAdd(b + ((long long)y0 * w + x1) * c + e, wy0 * wx1 * d[e]);
+      atomicAdd(b + ((long long)y1 * w + x0) * c + e, wy1 * wx0 * d[e]);
+      atomicAdd(b + ((long long)y1 * w + x1) * c + e, wy1 * wx1 * d[e]);
+    }
+  }
+}
+
 // out[i] (+)= scale * (float)in[i]   (per-channel double sums -> fp32 parameter gradients)
 __global__ void scale_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int count, float scale, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -477,12 +550,12 @@ using namespace v2x;
 extern "C" int v2x_bn_stats_fwd(const void* z, int64_t n_pixels, int32_t c, int32_t planes, double* sum, double* sumsq,
                                 void* stream) {
   V2X_REQUIRE(z && sum && sumsq && n_pixels > 0, "null/empty");
-  V2X_CHECK_ACT(c, planes);
+  V2X_REQUIRE(c > 0 && c % 8 == 0 && c <= 2048 && (planes == 1 || planes == 2), "channels: multiple of 8, <= 2048; planes 1 or 2");
   cudaStream_t s = (cudaStream_t)stream;
   V2X_CUDA_TRY(cudaMemsetAsync(sum, 0, sizeof(double) * c, s));
   V2X_CUDA_TRY(cudaMemsetAsync(sumsq, 0, sizeof(double) * c, s));
   const int lanes = 256 / (c / 8);
-  channel_reduce_kernel<0><<<grid_cap((n_pixels + lanes - 1) / lanes * 256, 256, 4), 256, 0, s>>>(
+  channel_reduce_kernel<0><<<grid_cap((n_pixels + lanes - 1) / lanes * 256, 256, 4), 256, 2 * c * sizeof(double), s>>>(
       reinterpret_cast<const __nv_bfloat16*>(z), nullptr, n_pixels, c, planes, nullptr, nullptr, nullptr, nullptr, 0, sum, sumsq);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
@@ -517,7 +590,7 @@ extern "C" int v2x_bn_relu_bwd(const void* dy, const void* z, void* dz, int64_t 
   V2X_CUDA_TRY(cudaMemsetAsync(s1, 0, sizeof(double) * c, s));
   V2X_CUDA_TRY(cudaMemsetAsync(s2, 0, sizeof(double) * c, s));
   const int lanes = 256 / (c / 8);
-  channel_reduce_kernel<1><<<grid_cap((n_pixels + lanes - 1) / lanes * 256, 256, 4), 256, 0, s>>>(
+  channel_reduce_kernel<1><<<grid_cap((n_pixels + lanes - 1) / lanes * 256, 256, 4), 256, 2 * c * sizeof(double), s>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(z), n_pixels, c, planes, scale, shift,
       mean, invstd, relu, s1, s2);
   bn_relu_bwd_apply_kernel<<<grid_cap(n_pixels * (c / 8), 256, 8), 256, 0, s>>>(
@@ -635,6 +708,29 @@ extern "C" int v2x_warp_mean_bwd(const void* dmean, float* dx, const double* tra
   warp_mean_bwd_kernel<<<grid_cap(total_pix * 32, 256, 8), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(dmean), dx, trans, reinterpret_cast<const long long*>(num_agent), batch, agents, h, w,
       c, planes, include_self, only_v2i);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_maxpool2_bwd(const void* x, const void* dy, void* dx, int32_t n, int32_t h_out, int32_t w_out, int32_t c,
+                                int32_t planes, void* stream) {
+  V2X_REQUIRE(x && dy && dx && n > 0 && h_out > 0 && w_out > 0, "null/empty");
+  V2X_CHECK_ACT(c, planes);
+  maxpool2_bwd_kernel<<<grid_cap((long long)n * h_out * w_out * (c / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<__nv_bfloat16*>(dx), n,
+      h_out, w_out, c, planes);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_upsample_bilinear2_bwd(const void* dy, float* dx, int32_t n, int32_t h_in, int32_t w_in, int32_t c,
+                                          int32_t planes, void* stream) {
+  V2X_REQUIRE(dy && dx && n > 0 && h_in > 0 && w_in > 0, "null/empty");
+  V2X_CHECK_ACT(c, planes);
+  cudaStream_t s = (cudaStream_t)stream;
+  V2X_CUDA_TRY(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)n * h_in * w_in * c, s));
+  upsample_bilinear2_bwd_kernel<<<grid_cap((long long)n * 4 * h_in * w_in * (c / 8), 256, 8), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), dx, n, h_in, w_in, c, planes);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }

@@ -28,7 +28,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import EPI_ACT, EPI_F32_SPLIT, check
+from ._lib import EPI_ACT, EPI_F32_NCHW, EPI_F32_SPLIT, check
 from .ops import ConvLaunch, _ptr, _stream
 from .transforms import dgrad_weights_stride1
 
@@ -92,6 +92,38 @@ class Tape:
         self.back.append(bwd)
         return y
 
+    def maxpool2(self, x: Var) -> Var:
+        """nn.MaxPool2d(2) (SegModelBase.py:113) with its backward."""
+        lib = self.lib
+        y = Var(ops.maxpool2(x.act), x.c_log)
+        p, n, h2, w2, c = x.act.shape
+
+        def bwd():
+            if y.grad is None:
+                return
+            g = torch.empty_like(x.act)
+            check(lib.v2x_maxpool2_bwd(_ptr(x.act), _ptr(y.grad), _ptr(g), n, h2 // 2, w2 // 2, c, p, _stream()), "v2x_maxpool2_bwd")
+            x.add_grad(lib, g)
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
+    def upsample_bilinear2(self, x: Var) -> Var:
+        """nn.Upsample(scale_factor=2, bilinear, align_corners=True) (SegModelBase.py:125) with its backward."""
+        lib = self.lib
+        y = Var(ops.upsample_bilinear2(x.act), x.c_log)
+        p, n, h, w, c = x.act.shape
+
+        def bwd():
+            if y.grad is None:
+                return
+            dx = torch.empty((n, h, w, c), dtype=torch.float32, device=self.dev)
+            check(lib.v2x_upsample_bilinear2_bwd(_ptr(y.grad), _ptr(dx), n, h, w, c, p, _stream()), "v2x_upsample_bilinear2_bwd")
+            x.add_grad(lib, ops.pack_input(dx, c, p))
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
     def _conv_raw(self, wname, bname, srcs: List[Var], stride):
         """z = conv(cat(srcs), W) + b (no BN fold, no ReLU) as one act; returns (z act, cins logical)."""
         w = self.p[wname]
@@ -131,7 +163,10 @@ class Tape:
                 pcd = ops.pack_conv(wt, None, None, cins=[co], stride=1, planes=PLANES, device=self.dev, tap_pack=False,
                                     mmas=3, cout_pad=s.act.shape[-1])
                 g = ops.empty_act(p, n, s.act.shape[2], s.act.shape[3], s.act.shape[-1], self.dev)
-                ConvLaunch(pcd, [dzin], relu=False, out0=g, epilogue=EPI_ACT)()
+                # very deep K (the seg GRU's data gradient: 9 x 1536 channels): an N tile of 128 keeps the hi/lo weight ring
+                # of the halo + streamed-weight mode inside shared memory (the per-tap path is limited to 160 k-blocks)
+                bn = 128 if (k * k * co_pad // 64 > 160 and pcd.cout % 128 == 0) else None
+                ConvLaunch(pcd, [dzin], relu=False, out0=g, epilogue=EPI_ACT, block_n=bn)()
                 s.add_grad(lib, g)
             ci_off += c_log
 
@@ -174,8 +209,9 @@ class Tape:
         self.back.append(bwd)
         return y
 
-    def conv1x1_out(self, conv: str, src: Var, out_f32: torch.Tensor) -> "OutVar":
-        """Final 1x1 conv with bias and fp32 NHWC output (heads' conv2 / box_prediction.3, DetModelBase.py:283-329)."""
+    def conv1x1_out(self, conv: str, src: Var, out_f32: torch.Tensor, nchw=False) -> "OutVar":
+        """Final 1x1 conv with bias and fp32 output: NHWC (heads' conv2 / box_prediction.3, DetModelBase.py:283-329) or, with
+        ``nchw``, [N, C, H, W] (the seg models' OutConv logits, SegModelBase.py:145-151)."""
         lib = self.lib
         w = self.p[conv + ".weight"]
         w4 = w.reshape(w.shape[0], w.shape[1], 1, 1)
@@ -183,15 +219,22 @@ class Tape:
         co_pad = 32 if co <= 32 else ((co + 63) // 64) * 64    # a valid N tile of v2x_conv_fwd for any kc
         pc = ops.pack_conv(w4, self.p[conv + ".bias"], None, cins=[src.c_log], planes=PLANES, device=self.dev, mmas=3,
                            cout_pad=co_pad)
-        ConvLaunch(pc, [src.act], epilogue=EPI_F32_SPLIT, relu=False, out0=out_f32, split=co, block_n=min(co_pad, 64))()
+        if nchw:
+            ConvLaunch(pc, [src.act], epilogue=EPI_F32_NCHW, relu=False, out0=out_f32, block_n=min(co_pad, 64))()
+        else:
+            ConvLaunch(pc, [src.act], epilogue=EPI_F32_SPLIT, relu=False, out0=out_f32, split=co, block_n=min(co_pad, 64))()
         ov = OutVar(out_f32)
 
         def bwd():
             if ov.upstream is None:
                 return
             p, n, h, wd, _ = src.act.shape
-            up = (ov.upstream.reshape(n, h, wd, co).to(torch.float32) * self.scale).contiguous()
-            dz = ops.pack_input(up, co_pad, PLANES)
+            if nchw:
+                up = (ov.upstream.reshape(n, co, h, wd).to(torch.float32) * self.scale).contiguous()
+                dz = ops.pack_input_nchw(up, co_pad, PLANES)
+            else:
+                up = (ov.upstream.reshape(n, h, wd, co).to(torch.float32) * self.scale).contiguous()
+                dz = ops.pack_input(up, co_pad, PLANES)
             s0, s1 = self._f64(co_pad), self._f64(co_pad)
             check(lib.v2x_bn_stats_fwd(_ptr(dz), n * h * wd, co_pad, PLANES, _ptr(s0), _ptr(s1), _stream()), "bias grad")
             db = self._f32(co_pad)
@@ -208,10 +251,11 @@ class Tape:
         self.back.append(bwd)
         return ov
 
-    def warp_mean(self, x: Var, trans, num_agent, batch, agents, only_v2i=False) -> Var:
-        """Neighbour mean of the warped maps (V2VNet.py:85-98; self excluded) with its backward (grid_sample backward)."""
+    def warp_mean(self, x: Var, trans, num_agent, batch, agents, only_v2i=False, include_self=False) -> Var:
+        """Neighbour mean of the warped maps (det V2VNet.py:85-98: self excluded; seg V2VNet.py:55-74: self included) with
+        its backward (grid_sample backward)."""
         lib = self.lib
-        out = ops.warp_mean(x.act, trans, num_agent, batch, agents, include_self=False, only_v2i=only_v2i)
+        out = ops.warp_mean(x.act, trans, num_agent, batch, agents, include_self=include_self, only_v2i=only_v2i)
         m = Var(out)
         p, n, h, w, c = x.act.shape
 
@@ -219,8 +263,8 @@ class Tape:
             if m.grad is None:
                 return
             dx = torch.empty((n, h, w, c), dtype=torch.float32, device=self.dev)
-            check(lib.v2x_warp_mean_bwd(_ptr(m.grad), _ptr(dx), _ptr(trans), _ptr(num_agent), batch, agents, h, w, c, p, 0,
-                                        int(only_v2i), _stream()), "v2x_warp_mean_bwd")
+            check(lib.v2x_warp_mean_bwd(_ptr(m.grad), _ptr(dx), _ptr(trans), _ptr(num_agent), batch, agents, h, w, c, p,
+                                        int(include_self), int(only_v2i), _stream()), "v2x_warp_mean_bwd")
             x.add_grad(lib, ops.pack_input(dx, c, p))
             m.grad = None
         self.back.append(bwd)
@@ -415,3 +459,75 @@ class V2VNetTrainStep(torch.autograd.Function):
             grads.append(None if g is None else g.reshape(shape))
         ctx.tape = None
         return (None, None, None, None, None, *grads)
+
+
+# =====================================================================================================================
+# segmentation models (CP/models/seg/SegModelBase.py:91-151, UNet.py:24-44, seg/V2VNet.py:25-92) in train mode
+# =====================================================================================================================
+def seg_double_conv(t: Tape, p: str, srcs, need_input_grad=None) -> Var:
+    x = t.cbr(p + "0", p + "1", srcs, need_input_grad=need_input_grad)
+    return t.cbr(p + "3", p + "4", [x])
+
+
+def seg_encode(t: Tape, x_in: Var):
+    x1 = seg_double_conv(t, "inc.double_conv.", [x_in], need_input_grad=[False])
+    x2 = seg_double_conv(t, "down1.maxpool_conv.1.double_conv.", [t.maxpool2(x1)])
+    x3 = seg_double_conv(t, "down2.maxpool_conv.1.double_conv.", [t.maxpool2(x2)])
+    x4 = seg_double_conv(t, "down3.maxpool_conv.1.double_conv.", [t.maxpool2(x3)])
+    return x1, x2, x3, x4
+
+
+def seg_decode(t: Tape, feat: Var, x1, x2, x3, n: int):
+    """down4 / up1..4 (cat([skip, bilinear_up])) / outc -> fp32 NCHW logits."""
+    x5 = seg_double_conv(t, "down4.maxpool_conv.1.double_conv.", [t.maxpool2(feat)])
+    x = seg_double_conv(t, "up1.conv.double_conv.", [feat, t.upsample_bilinear2(x5)])
+    x = seg_double_conv(t, "up2.conv.double_conv.", [x3, t.upsample_bilinear2(x)])
+    x = seg_double_conv(t, "up3.conv.double_conv.", [x2, t.upsample_bilinear2(x)])
+    x = seg_double_conv(t, "up4.conv.double_conv.", [x1, t.upsample_bilinear2(x)])
+    n_cls = t.p["outc.conv.weight"].shape[0]
+    logits = torch.empty((n, n_cls, x.act.shape[2], x.act.shape[3]), dtype=torch.float32, device=t.dev)
+    return t.conv1x1_out("outc.conv", x, logits, nchw=True)
+
+
+class SegTrainStep(torch.autograd.Function):
+    """One train-mode forward of seg UNet (``fuse`` = None) or seg V2VNet (``fuse`` = (trans, num_agent, batch, agents,
+    only_v2i): one GNN round on the 512-channel layer-4 map, neighbour mean INCLUDING self) with its backward, so the
+    reference's SegModule.step (CP/utils/SegModule.py:45-120: loss -> backward -> optimizer) drives it unchanged.
+    Inputs: (module, fuse, x [N,13,256,256], *parameters in named_parameters() order) -> logits [N, classes, 256, 256]."""
+
+    @staticmethod
+    def forward(ctx, module, fuse, x, *params):
+        names = [k for k, _ in module.named_parameters()]
+        p = {k: v.detach() for k, v in zip(names, params)}
+        b = {k: v for k, v in module.named_buffers()}
+        dev = x.device
+        n = int(x.shape[0])
+        tape = Tape(p, b, dev)
+        x_in = Var(ops.pack_input_nchw(x.to(torch.float32).contiguous(), 16, PLANES), c_log=int(x.shape[1]))
+        x1, x2, x3, x4 = seg_encode(tape, x_in)
+        feat = x4
+        if fuse is not None:
+            trans, nat, batch, agents, only_v2i = fuse
+            trans = trans.to(device=dev, dtype=torch.float64).contiguous()
+            nat = nat.to(device=dev, dtype=torch.int64).contiguous()
+            mean = tape.warp_mean(x4, trans, nat, batch, agents, only_v2i=only_v2i, include_self=True)
+            for _ in range(module.gnn_iter_num):
+                feat = tape.gru_round(feat, mean, x4, nat, batch, agents)
+        out = seg_decode(tape, feat, x1, x2, x3, n)
+        ctx.tape, ctx.names, ctx.out = tape, names, out
+        ctx.shapes = [v.shape for v in params]
+        return out.value
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        tape = ctx.tape
+        tape.scale = choose_scale(dlogits)
+        ctx.out.upstream = dlogits
+        tape.backward()
+        k = "convgru.weight_ih_l0"
+        if k in tape.grads:
+            tape.grads[k] = torch.flip(tape.grads[k], (2,))
+        grads = [None if tape.grads.get(name) is None else tape.grads[name].reshape(shape)
+                 for name, shape in zip(ctx.names, ctx.shapes)]
+        ctx.tape = None
+        return (None, None, None, *grads)
