@@ -420,7 +420,7 @@ def roofline_of(plan, cfg, args, units, step_ms):
     other kernels" would credit hidden time to the convs)."""
     peaks = measured_peaks()
     conv_launches = [l for l in plan.launches if getattr(l, "flops", 0.0) > 0]
-    other_launches = [l for l in plan.launches if getattr(l, "flops", 0.0) == 0]
+    other_launches = [l for l in plan.launches if getattr(l, "flops", 0.0) == 0 and not getattr(l, "collective", False)]
     other_ms = time_launch_list(other_launches)
     conv_ms = time_launch_list(conv_launches)
     alg = cfg["gflop"] * 1e9 * units
@@ -507,6 +507,15 @@ def run_v2v_det(args, rank, world, local_rank):
     frames = B * world * args.steps
     value = frames / (ms_total * 1e-3)
 
+    if args.value_only:
+        if getattr(plan, "peer", None) is not None:
+            plan.peer.check()
+        if rank == 0:
+            emit({"metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps,
+                  "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "value_only": True,
+                  "exchange": args.exchange if unit_sharded else None, "precision": args.precision, "clocks": clocks})
+        return
+
     # ---------------- e2e: drop-in module, pinned host buffers, H2D + D2H in the timed region ----------------
     model = V2VNet(default_det_config(), GNN_ITER, 3, 256, num_agent=AGENTS)
     model.load_state_dict(sd, strict=True)
@@ -586,10 +595,14 @@ def run_v2v_det(args, rank, world, local_rank):
                        "scenes_per_gpu_per_step": B, "agents": AGENTS, "precision": args.precision,
                        "l2": "no flush: per-step inputs %.0f MB and activations ~%.1f GB exceed the 126 MB L2"
                              % (B * 17.04, 0.4 * B),
-                       "parallelism": ("unit-sharded x%d (40 agent-major units per GPU), one NCCL %s of layer-3 "
-                                       "maps per step overlapped with the x_4 branch"
-                                       % (world, "all-gather" if args.exchange == "allgather"
-                                          else "neighbour exchange (grouped send/recv of the 4 other agents' maps)"))
+                       "parallelism": (("unit-sharded x%d (40 agent-major units per GPU), layer-3 maps pushed by a kernel "
+                                        "into every rank's NVLink peer memory (no host-issued collective; the forward is "
+                                        "one CUDA graph), overlapped with the x_4 branch" % world)
+                                       if args.exchange == "push" else
+                                       ("unit-sharded x%d (40 agent-major units per GPU), one NCCL %s of layer-3 "
+                                        "maps per step overlapped with the x_4 branch"
+                                        % (world, "all-gather" if args.exchange == "allgather"
+                                           else "neighbour exchange (grouped send/recv of the 4 other agents' maps)")))
                        if unit_sharded
                        else "scene-sharded x%d, no data-path collective" % world},
             "e2e": {"value": e2e_value, "unit": cfg["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -744,8 +757,10 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "fp16x3", "bf16"],
                     help="v2x_b200/precision.py: mixed (default; the mode the 1e-3 parity tests assert), fp16x3, bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-only", action="store_true",
+                    help="development A/B runs: print only the device-resident value line (no e2e legs, no roofline)")
     ap.add_argument("--shard", default="unit", choices=["unit", "scene"], help="multi-GPU partition of v2v_det (N > 1)")
-    ap.add_argument("--exchange", default="allgather", choices=["neighbours", "allgather"],
+    ap.add_argument("--exchange", default="allgather", choices=["neighbours", "allgather", "push"],
                     help="unit-sharded x_3 exchange: one all-gather (default), or NCCL send/recv of just the needed "
                          "neighbour maps")
     args = ap.parse_args()

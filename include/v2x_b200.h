@@ -383,6 +383,45 @@ int v2x_maxpool2_bwd(const void* x, const void* dy, void* dx, int32_t n, int32_t
 int v2x_upsample_bilinear2_bwd(const void* dy, float* dx, int32_t n, int32_t h_in, int32_t w_in, int32_t c, int32_t planes,
                                void* stream);
 
+/* ---- multi-GPU exchange over NVLink peer memory (one process per GPU) -------------------------
+ *
+ * The unit-sharded plans exchange the layer-3 maps x_3 once per forward ("ncclAllGather of x_3 ... issued right after
+ * conv3_2", replacing the neighbour reads of CP/models/det/V2VNet.py:85-94 when a scene's agents live on different
+ * GPUs).  These entry points do that exchange from the device: every rank owns a peer-visible REGION
+ *   [ flag block (V2X_PEER_FLAG_BYTES): ready[8], consumed[8] uint64 step numbers | payload ]
+ * and pushes its own maps into its slot of every rank's region with plain stores that travel over NVLink; readiness is
+ * published through the flag blocks (st.release.sys / ld.acquire.sys), so there is no host-issued collective and the
+ * whole forward is one CUDA graph.  Per step, on one stream:  v2x_peer_begin -> v2x_peer_push -> v2x_peer_wait ->
+ * (the fuse kernel reads the region) -> v2x_peer_done.  Every rank must run the same number of steps.
+ * v2x_peer_alloc / v2x_peer_open / v2x_peer_close / v2x_peer_free are set-up calls: they DO allocate device memory and
+ * synchronise (the exception to the conventions above); handles travel between the processes by any host channel
+ * (v2x_b200/sharding.py uses a torch.distributed all-gather of the 64 bytes).  host_* arguments are HOST pointers.
+ */
+#define V2X_PEER_HANDLE_BYTES 64
+#define V2X_PEER_FLAG_BYTES 4096
+/* cudaMalloc a zeroed region of `bytes`, return its device pointer and its CUDA IPC handle (64 bytes) */
+int v2x_peer_alloc(int64_t bytes, void** host_ptr_out, void* host_handle_out);
+/* map another rank's region into this process (cudaIpcOpenMemHandle, peer access enabled lazily) / unmap it */
+int v2x_peer_open(const void* host_handle, void** host_ptr_out);
+int v2x_peer_close(void* ptr);
+int v2x_peer_free(void* ptr);
+/* step += 1 (device uint64 `step`), then wait until every other rank has consumed step - 1 (flags of the LOCAL region).
+ * A wait that exceeds timeout_ms stores 100 + rank-waited-for into *err (device int32) and gives up instead of hanging. */
+int v2x_peer_begin(const void* flags_local, void* step, int32_t rank, int32_t world, int32_t timeout_ms, int32_t* err,
+                   void* stream);
+/* copy src (act planes [p][elems_per_plane], plane stride src_plane_stride elements) into host_dst[r] (this rank's slot in
+ * rank r's payload, plane stride dst_plane_stride) for every r < world, host_dst_planes[r] planes each (0 = skip); when all
+ * stores are done, publish ready[rank] = step in every region (host_flag_regions[r] = base of rank r's region).
+ * `counter`: device uint32, zero before the first call. */
+int v2x_peer_push(const void* src, int64_t elems_per_plane, int64_t src_plane_stride, void* const* host_dst,
+                  const int32_t* host_dst_planes, int64_t dst_plane_stride, void* const* host_flag_regions,
+                  const void* step, void* counter, int32_t rank, int32_t world, void* stream);
+/* wait until ready[r] >= step for every other rank r (error code 200 + r on timeout) */
+int v2x_peer_wait(const void* flags_local, const void* step, int32_t rank, int32_t world, int32_t timeout_ms, int32_t* err,
+                  void* stream);
+/* publish consumed[rank] = step in every region: the payload of this step may be overwritten */
+int v2x_peer_done(void* const* host_flag_regions, const void* step, int32_t rank, int32_t world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,3 +149,56 @@ def test_forward_under_enable_grad_warns_once():
         model(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
         model(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
     assert sum("no autograd graph" in str(x.message) for x in w) == 1
+
+
+@pytest.mark.gpu
+def test_peer_region_single_rank_protocol():
+    """The device-side exchange (csrc/peer_kernels.cu, sharding.PeerRegion) with world = 1: the step counter advances, the
+    push lands every plane of the source in the payload slot it names, flags carry the step number, no wait times out.
+    (Cross-process mapping of the regions is what tools/multigpu_check.py with V2X_EXCHANGE=push checks on 2+ GPUs.)"""
+    import torch
+    from v2x_b200 import ops, sharding
+    ops.require_gpu()
+    dev = torch.device("cuda")
+    planes, n, elems = 2, 3, 32 * 32 * 64
+    region = sharding.PeerRegion(planes * 5 * elems * 2, 0, 1, device=dev)
+    payload = region.payload((planes, 5, elems), torch.float16)
+    assert payload.data_ptr() == region.payload_ptr(0) and float(payload.abs().max()) == 0.0
+    for step in range(1, 4):
+        src = torch.randn((planes, n, elems), device=dev).half()
+        region.begin()
+        region.push(src, 2 * elems, 5 * elems, [planes])     # units 2..4 of the payload
+        region.wait()
+        region.done()
+        torch.cuda.synchronize()
+        region.check()
+        assert int(region.step.item()) == step
+        assert torch.equal(payload[:, 2:5], src) and float(payload[:, :2].abs().max()) == 0.0
+        flags = region._bytes[:sharding.PEER_FLAG_BYTES].view(torch.int64)
+        assert int(flags[0]) == step and int(flags[8]) == step      # ready[0], consumed[0]
+    region.close()
+
+
+@pytest.mark.gpu
+def test_sharded_plan_push_exchange_world1_matches_unsharded_plan():
+    """V2VNetDetShardedPlan with the device-side push exchange (one CUDA graph: x_4 branch forked beside begin / push /
+    wait / fuse) on a single rank reproduces the unsharded plan bit for bit, eagerly and as a replayed graph."""
+    import torch
+    from v2x_b200 import nets, synthetic
+    sd = synthetic.v2vnet_det_state(3)
+    bevs, trans, nat = synthetic.make_scene(2, 5, seed=3, present=[5, 3])
+    args = (bevs.cuda(), trans.cuda(), nat.cuda())
+    full = nets.V2VNetDetPlan(sd, 2, 5, planes="mixed")
+    want = {k: v.clone() for k, v in full.forward(*args).items()}
+    plan = nets.V2VNetDetShardedPlan(sd, 2, 5, 0, 1, planes="mixed", exchange="push")
+    got = {k: v.clone() for k, v in plan.forward(*args).items()}
+    plan.capture()
+    for _ in range(3):
+        rep = plan.forward(*args)
+    torch.cuda.synchronize()
+    plan.peer.check()
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+        assert torch.equal(rep[k], want[k]), k
+    assert int(plan.peer.step.item()) == 1 + 2 + 3      # eager forward, two warm-up steps of capture(), three replays
+    plan.close()

@@ -568,3 +568,86 @@ def test_fp16_split_saturates_instead_of_overflowing():
     assert back[0] == 2 * 65504.0 and back[1] == -2 * 65504.0      # hi and lo both saturate
     assert back[2] == 65504.0 and abs(back[3] - 70000.0) < 1.0
     assert abs(back[5] - 0.3333333) < 1e-7
+
+
+def _random_poses(B, A, seed, kind):
+    """[B, A, A, 4, 4] float64: 'rigid' = the synthetic pose generator; 'scaled' = non-rigid matrices whose tile footprint
+    does not fit the staged box (the kernel must take its direct path); 'far' = translations that push most footprints off
+    the map; 'zero' = all-zero matrices (every sample lands on the map centre)."""
+    from oracle import synth
+    t = synth.make_trans_matrices(B, A, seed)
+    if kind == "scaled":
+        t[..., :2, :2] *= 2.7
+    elif kind == "far":
+        t[..., :2, 3] *= 3.0
+    elif kind == "zero":
+        t.zero_()
+    return t
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("poses", ["rigid", "scaled", "far", "zero"])
+@pytest.mark.parametrize("geom", [(64, 32, 32), (128, 20, 28), (512, 16, 16)], ids=lambda g: "c%d_%dx%d" % g)
+def test_warp_staged_matches_direct_kernels(geom, poses, planes, monkeypatch):
+    """The shared-memory-staged warp + fuse kernel (csrc/warp_staged.cuh) against the direct one-warp-per-pixel gathers it
+    replaces (the default; V2X_WARP_STAGED=1 selects the staged kernel), for every fuse rule of the path: V2VNet mean (self excluded / included, only_v2i, a slice
+    of target units), Mean / Sum / Max fusion, the when2com gated sum and the AgentWise / DiscoNet weighted sums; maps that
+    are not a multiple of the 8x8 tile, absent agent slots, non-rigid poses (box too large -> direct path per term)."""
+    from v2x_b200 import ops
+    dev = _dev()
+    C, H, W = geom
+    B, A = 2, 5
+    g = torch.Generator().manual_seed(C + H + len(poses))
+    x = to_act(torch.randn((A * B, C, H, W), generator=g), planes, dev)
+    trans = _random_poses(B, A, 7, poses).to(dev)
+    nat = torch.tensor([[5] * A, [3] * A], dtype=torch.long, device=dev)
+    coef_g = torch.rand((B, A, A), generator=g).to(dev)
+    coef_g[0, 1, 2] = 0.0
+    scores = torch.randn((B, A, A, H * W), generator=g).to(dev)
+    calls = {
+        "mean": lambda: ops.warp_mean(x, trans, nat, B, A),
+        "mean_self_v2i": lambda: ops.warp_mean(x, trans, nat, B, A, include_self=True, only_v2i=True),
+        "mean_slice": lambda: ops.warp_mean(x, trans, nat, B, A, unit_offset=3, unit_count=4),
+        "reduce_mean": lambda: ops.warp_reduce(x, trans, nat, B, A, "mean"),
+        "reduce_sum_v2i": lambda: ops.warp_reduce(x, trans, nat, B, A, "sum", only_v2i=True),
+        "reduce_max": lambda: ops.warp_reduce(x, trans, nat, B, A, "max"),
+        "gated": lambda: ops.warp_gated(x, trans, nat, coef_g, B, A, warp_flag=1),
+        "gated_slice": lambda: ops.warp_gated(x, trans, nat, coef_g, B, A, warp_flag=1, unit_offset=2, unit_count=5),
+        "weighted_pair": lambda: ops.warp_weighted(x, trans, nat, coef_g, B, A, per_pixel=False),
+        "weighted_pixel_v2i": lambda: ops.warp_weighted(x, trans, nat, scores, B, A, per_pixel=True, only_v2i=True),
+    }
+    worst = 0.0
+    for name, fn in calls.items():
+        monkeypatch.setenv("V2X_WARP_STAGED", "0")
+        want = ops.act_to_float(fn())
+        monkeypatch.setenv("V2X_WARP_STAGED", "1")
+        got = ops.act_to_float(fn())
+        torch.cuda.synchronize()
+        assert got.shape == want.shape, name
+        err = ((got - want).abs().max() / want.abs().max().clamp_min(1e-6)).item()
+        worst = max(worst, err)
+        # same taps and weights, fp32 accumulation (association differs slightly), then one rounding to the storage format
+        assert err <= (1e-5 if planes == 2 else 8e-3), (name, err)
+    print("warp staged vs direct %s %s planes=%d worst rel diff %.2e" % (geom, poses, planes, worst))
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+def test_warp_staged_mean_matches_oracle(planes):
+    """The staged kernel on its own against the oracle's feature_transformation + mean (flipped domain), 64 channels."""
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    dev = _dev()
+    B, A, C = 2, 4, 64
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((A * B, C, 32, 32), generator=g)
+    trans = synth.make_trans_matrices(B, A, 5)
+    nat = torch.full((B, A), A, dtype=torch.long)
+    local = torch.stack([torch.flip(x, (2,))[B * i: B * (i + 1)] for i in range(A)], 1)
+    out = ops.act_to_float(ops.warp_mean(to_act(x, planes, dev), trans.to(dev), nat.to(dev), B, A)).cpu()
+    worst = 0.0
+    for i in range(A):
+        for b in range(B):
+            nb = [restate.feature_transformation(local, b, j, i, trans, (1, C, 32, 32)) for j in range(A) if j != i]
+            worst = max(worst, rel_err(out[B * i + b], torch.flip(torch.stack(nb).mean(0), (1,))))
+    print("staged warp_mean vs oracle planes=%d rel_err=%.3e" % (planes, worst))
+    assert worst < TOL[planes]

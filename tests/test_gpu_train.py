@@ -21,10 +21,27 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
 
 
-def _buffers_close(got, want):
-    """BatchNorm running buffers: 1e-5 absolute + 1e-5 relative (deep seg layers carry variances of O(10))."""
-    got, want = got.detach().double().cpu(), want.detach().double().cpu()
-    return bool(((got - want).abs() <= 1e-5 + 1e-5 * want.abs()).all())
+def _check_buffers(tag, after, want_sd, parity_log, golden=None, rtol=1e-5):
+    """BatchNorm running buffers after one step vs the float64 oracle (and the live reference's, when the fixture holds
+    them): |got - want| <= 1e-5 + rtol * |want| (deep seg layers carry variances of O(10)).  The worst measured error, in
+    units of that bound, goes on record."""
+    worst, worst_key, worst_abs = 0.0, None, 0.0
+    for k, v in want_sd.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(after[k]) == int(v), k
+            continue
+        if not k.endswith(("running_mean", "running_var")):
+            continue
+        wants = [v] + ([torch.from_numpy(golden["bn." + k])] if golden is not None and "bn." + k in golden.files else [])
+        got = after[k].detach().double().cpu()
+        for w in wants:
+            w = w.detach().double().cpu()
+            err = ((got - w).abs() / (1e-5 + rtol * w.abs())).max().item()
+            if err > worst:
+                worst, worst_key, worst_abs = err, k, (got - w).abs().max().item()
+    print(tag, "BN running buffers: worst error %.2f x (1e-5 + %.0e*|v|) at %s (abs %.2e)" % (worst, rtol, worst_key, worst_abs))
+    parity_log(tag, "train fp16x3 bn buffers", worst_over_bound=worst, rtol=rtol, worst_abs=worst_abs, worst_key=str(worst_key))
+    assert worst <= 1.0, (worst_key, worst, worst_abs)
 
 
 def _check_grads(tag, got, want, golden, parity_log, zero_tol=1e-9, min_params=50):
@@ -80,13 +97,7 @@ def test_fafnet_train_step_matches_oracle(golden_dir, parity_log):
     got = {k: p.grad for k, p in model.named_parameters()}
     _check_grads("train_step_fafnet_seed22", got, grads_ref, golden, parity_log)
     # BatchNorm running buffers after the step (momentum 0.1, unbiased variance), vs the oracle and the live reference
-    after = dict(model.named_buffers())
-    for k, v in sd_after.items():
-        if k.endswith(("running_mean", "running_var")):
-            assert _buffers_close(after[k], v), k
-            assert _buffers_close(after[k], torch.from_numpy(golden["bn." + k])), k
-        if k.endswith("num_batches_tracked"):
-            assert int(after[k]) == int(v)
+    _check_buffers("train_step_fafnet_seed22", dict(model.named_buffers()), sd_after, parity_log, golden=golden)
 
 
 def test_fafnet_adam_loop_decreases_the_loss_like_the_oracle():
@@ -164,10 +175,7 @@ def test_v2vnet_train_step_matches_oracle(golden_dir, parity_log):
     for k, g in got.items():
         assert (g is not None) == (k in grads_ref), k
     _check_grads("train_step_v2vnet_seed21", got, grads_ref, golden, parity_log)
-    after = dict(model.named_buffers())
-    for k, v in sd_after.items():
-        if k.endswith(("running_mean", "running_var")):
-            assert _buffers_close(after[k], v), k
+    _check_buffers("train_step_v2vnet_seed21", dict(model.named_buffers()), sd_after, parity_log)
 
 
 WG_CASES = [  # name, co, ci (logical), stride, taps, n, h_out, w_out
@@ -247,7 +255,4 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     for k, g in got.items():
         assert (g is not None) == (k in grads_ref), k
     _check_grads("train_step_%s_seed%d" % (kind, seed), got, grads_ref, golden, parity_log, min_params=40)
-    after = dict(model.named_buffers())
-    for k, v in sd_after.items():
-        if k.endswith(("running_mean", "running_var")):
-            assert _buffers_close(after[k], v), k
+    _check_buffers("train_step_%s_seed%d" % (kind, seed), dict(model.named_buffers()), sd_after, parity_log)

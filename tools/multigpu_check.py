@@ -48,12 +48,16 @@ def main():
             err = max(((out[k].cpu() - o[k][off:off + n]).abs().max() / o[k].abs().max()).item() for k in out)
             msg += ", vs oracle rel_err %.3e" % err
             ok = ok and err < 1e-3
+        if plan.peer is not None:
+            plan.peer.check()          # no wait of the device-side exchange ever timed out
+            msg += ", exchange: device-side push over NVLink peer memory (one graph)"
+            plan.close()
         print(msg, flush=True)
         ok = ok and graph_same and same
         del plan, full
     # ---- When2com: all-gather of keys [units,1024] / queries [units,32] (+ x_3 when warp_flag = 0) ----
     sdw = synth.when2com_det_state(9)
-    for warp_flag, inference in ((1, "activated"), (0, "argmax_test")):
+    for warp_flag, inference in (() if os.environ.get("V2X_CHECK_ONLY") == "v2v" else ((1, "activated"), (0, "argmax_test"))):
         plan = nets.When2comDetShardedPlan(sdw, B, A, rank, world, planes="mixed", warp_flag=warp_flag, inference=inference)
         out = plan.forward(bevs[off:off + n].cuda(), trans.cuda(), nat.cuda())
         torch.cuda.synchronize()

@@ -3,6 +3,7 @@
 // All are HBM/L2-bound byte movers: coalesced 16-byte accesses, grids sized in multiples of the SM
 // count, no tensor cores.  Reference call sites: see include/v2x_b200.h.
 #include "common.cuh"
+#include "warp_staged.cuh"
 
 namespace v2x {
 
@@ -350,6 +351,12 @@ extern "C" int v2x_warp_mean_fwd(const void* x, void* out, const double* trans, 
   __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
   const long long* na = reinterpret_cast<const long long*>(num_agent);
   cudaStream_t s = (cudaStream_t)stream;
+  if (v2x::warp_staged_ok(c)) {   // source footprints staged in shared memory (warp_staged.cuh)
+    v2x::WarpFuseArgs a{xi, xo, trans, na, nullptr, batch, agents, h, w, c, 0, include_self, only_v2i,
+                        unit_offset, unit_count, 0, batch * agents};
+    V2X_CUDA_TRY(v2x::launch_warp_fuse_staged<v2x::WF_MEAN>(a, planes, s));
+    return V2X_OK;
+  }
 #define V2X_WARP_MEAN(VEC_, PL_)                                                                              \
   warp_mean_kernel<VEC_, PL_><<<grid, threads, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, include_self, \
                                                        only_v2i, unit_offset, unit_count)
@@ -643,6 +650,12 @@ extern "C" int v2x_warp_gated_fwd(const void* x, void* out, const double* trans,
   __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
   const long long* na = reinterpret_cast<const long long*>(num_agent);
   cudaStream_t s = (cudaStream_t)stream;
+  if (warp_flag && v2x::warp_staged_ok(c)) {   // the warped variant: footprints staged in shared memory (warp_staged.cuh)
+    v2x::WarpFuseArgs a{xi, xo, trans, na, coef, batch, agents, h, w, c, 0, 1, only_v2i,
+                        unit_offset, unit_count, x_unit_offset, x_units};
+    V2X_CUDA_TRY(v2x::launch_warp_fuse_staged<v2x::WF_GATED>(a, planes, s));
+    return V2X_OK;
+  }
   if (c <= 256)
     warp_gated_kernel<1><<<grid, threads, 0, s>>>(xi, xo, trans, na, coef, batch, agents, h, w, c, planes, warp_flag, only_v2i, unit_offset, unit_count,
                                                   x_unit_offset, x_units);

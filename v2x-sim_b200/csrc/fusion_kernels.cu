@@ -3,6 +3,7 @@
 // All work in the UN-flipped domain with the same theta' as warp_mean_kernel (aux_kernels.cu); all are L2/HBM-bound
 // gathers over 32x32xC maps: one warp per output pixel, lanes over channels in 16-byte vectors, fp32 accumulation.
 #include "common.cuh"
+#include "warp_staged.cuh"
 
 namespace v2x {
 
@@ -427,6 +428,12 @@ extern "C" int v2x_warp_reduce_fwd(const void* x, void* out, const double* trans
   __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
   const long long* na = reinterpret_cast<const long long*>(num_agent);
   cudaStream_t s = (cudaStream_t)stream;
+  if (v2x::warp_staged_ok(c)) {   // source footprints staged in shared memory (warp_staged.cuh)
+    v2x::WarpFuseArgs a{xi, xo, trans, na, nullptr, batch, agents, h, w, c, mode, 1, only_v2i,
+                        0, batch * agents, 0, batch * agents};
+    V2X_CUDA_TRY(v2x::launch_warp_fuse_staged<v2x::WF_REDUCE>(a, planes, s));
+    return V2X_OK;
+  }
   if (c <= 256)
     warp_reduce_kernel<1><<<grid, 256, 0, s>>>(xi, xo, trans, na, batch, agents, h, w, c, planes, mode, only_v2i);
   else if (c <= 512)
@@ -475,6 +482,12 @@ extern "C" int v2x_warp_weighted_fwd(const void* x, void* out, const double* tra
   __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
   const long long* na = reinterpret_cast<const long long*>(num_agent);
   cudaStream_t s = (cudaStream_t)stream;
+  if (v2x::warp_staged_ok(c)) {   // source footprints staged in shared memory (warp_staged.cuh)
+    v2x::WarpFuseArgs a{xi, xo, trans, na, coef, batch, agents, h, w, c, coef_mode, 1, only_v2i,
+                        0, batch * agents, 0, batch * agents};
+    V2X_CUDA_TRY(v2x::launch_warp_fuse_staged<v2x::WF_WEIGHTED>(a, planes, s));
+    return V2X_OK;
+  }
   if (c <= 256)
     warp_weighted_kernel<1><<<grid, 256, 0, s>>>(xi, xo, trans, na, coef, coef_mode, batch, agents, h, w, c, planes, only_v2i);
   else if (c <= 512)

@@ -100,6 +100,15 @@ SYMBOLS = [
     ("v2x_warp_mean_bwd", C.c_int, [_P, _P, _P, _P] + [_I32] * 8 + [_P]),
     ("v2x_maxpool2_bwd", C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_upsample_bilinear2_bwd", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    # x_3 exchange over NVLink peer memory
+    ("v2x_peer_alloc", C.c_int, [_I64, C.POINTER(_P), _P]),
+    ("v2x_peer_open", C.c_int, [_P, C.POINTER(_P)]),
+    ("v2x_peer_close", C.c_int, [_P]),
+    ("v2x_peer_free", C.c_int, [_P]),
+    ("v2x_peer_begin", C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    ("v2x_peer_push", C.c_int, [_P, _I64, _I64, C.POINTER(_P), C.POINTER(_I32), _I64, C.POINTER(_P), _P, _P, _I32, _I32, _P]),
+    ("v2x_peer_wait", C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    ("v2x_peer_done", C.c_int, [C.POINTER(_P), _P, _I32, _I32, _P]),
 ]
 
 _lib = None

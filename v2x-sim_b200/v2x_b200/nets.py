@@ -456,6 +456,19 @@ class When2comDetPlan(DetPlan):
         return self.result()
 
 
+class PeerStep:
+    """One kernel of the device-side exchange (sharding.PeerRegion): it synchronises with the other ranks, so tools that
+    replay a subset of a plan's launches on one rank (bench.roofline_of, profilers) must skip it (``collective``)."""
+    collective = True
+    flops = 0.0
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self):
+        self.fn()
+
+
 class V2VNetDetShardedPlan(DetPlan):
     """det V2VNet forward, unit-sharded across ``world`` ranks (one process per GPU).
 
@@ -469,7 +482,7 @@ class V2VNetDetShardedPlan(DetPlan):
         # "allgather": one ncclAllGather of every unit's x_3; "neighbours": point-to-point exchange of just the maps of
         # the other agents of this rank's scenes (sharding.exchange_neighbour_units)
         self.exchange = exchange or os.environ.get("V2X_EXCHANGE", "allgather")
-        assert self.exchange in ("allgather", "neighbours")
+        assert self.exchange in ("allgather", "neighbours", "push")
         self.offset, n_loc = sharding.unit_range(batch_total * agents, rank, world)
         super().__init__(n_loc, planes, device)
         prec, planes = self.prec, self.prec.planes
@@ -508,8 +521,16 @@ class V2VNetDetShardedPlan(DetPlan):
         self.stage_b = len(self.launches)            # ---- x_4 branch done: wait for the gather
         c3 = x3.shape[-1]
         self.x3_local = x3
-        self.x3_all = ops.empty_act(planes, n_loc * world, 32, 32, c3, dev)
-        self.x3_all.zero_()
+        self.peer = None
+        if self.exchange == "push":
+            # device-side exchange over NVLink peer memory: x3_all lives in this rank's peer-visible region and every rank
+            # stores its own maps straight into it (sharding.PeerRegion, csrc/peer_kernels.cu)
+            x3_bytes = planes * n_loc * world * 32 * 32 * c3 * 2
+            self.peer = sharding.PeerRegion(x3_bytes, rank, world, group=group, device=dev)
+            self.x3_all = self.peer.payload((planes, n_loc * world, 32, 32, c3), ops.act_dtype(planes))
+        else:
+            self.x3_all = ops.empty_act(planes, n_loc * world, 32, 32, c3, dev)
+            self.x3_all.zero_()
         # Planes that cross the wire.  The gathered maps only feed the neighbour mean, and in the "mixed" precision the
         # ConvGRU reads that mean through ONE tensor-core pass (its fp16 hi plane, 11 bits): sending the neighbours' lo
         # planes would move twice the bytes for bits the consumer rounds away.  So only the hi plane of REMOTE units is
@@ -518,9 +539,22 @@ class V2VNetDetShardedPlan(DetPlan):
         self.exchange_planes = int(os.environ.get("V2X_EXCHANGE_PLANES", 0)) or (1 if (planes == 2 and prec.mmas("gru") == 1) else planes)
         x3_all = self.x3_all
         mean = self.act("mean", 32, 32, c3)
+        if self.peer is not None:
+            # begin (peers have consumed the previous step) -> push own maps into every region + publish -> wait for all
+            # ranks' maps; the x_4 branch [stage_a, stage_b) runs beside all of it on the side stream of the ONE graph
+            peer, ep = self.peer, self.exchange_planes
+            dst_planes = [planes if r == rank else ep for r in range(world)]
+            unit_elems = 32 * 32 * c3
+            self.add(PeerStep(peer.begin))
+            self.add(PeerStep(lambda: peer.push(x3, off * unit_elems, n_loc * world * unit_elems, dst_planes)))
+            self.add(PeerStep(peer.wait))
         self.add(lambda: ops.warp_mean(x3_all, trans, na, batch_total, agents, include_self=False, only_v2i=only_v2i,
                                        out=mean, unit_offset=off, unit_count=n_loc))
+        if self.peer is not None:
+            self.add(PeerStep(self.peer.done))
         h = self.build_gru_rounds(x3, mean, gnn_iter, batch_total, agents, off)
+        if self.peer is not None:
+            self.side_lo, self.side_hi, self.side_join = self.stage_a, self.stage_b, len(self.launches)
         x8 = self.build_decoder(self.dec_w, x0, x1, x2, h, x4u)
         self.build_heads(self.head_w, x8)
         self.graphs = None
@@ -529,6 +563,8 @@ class V2VNetDetShardedPlan(DetPlan):
         return (self.launches[:self.stage_a], self.launches[self.stage_a:self.stage_b], self.launches[self.stage_b:])
 
     def run(self):
+        if self.peer is not None:     # one graph, no host-issued collective
+            return DetPlan.run(self)
         seg = self._segments()
         for i in range(3):
             if i == 1:   # x_3 is final: exchange it while the x_4 branch runs
@@ -551,6 +587,13 @@ class V2VNetDetShardedPlan(DetPlan):
                     l()
 
     def capture(self):
+        if self.peer is not None:
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.barrier(group=self.group)   # line the ranks up: the waits of the warm-up steps have a time limit
+            DetPlan.capture(self)     # two eager warm-up steps on every rank (they exchange like real ones), then one graph
+            self.peer.check()
+            return
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -567,6 +610,15 @@ class V2VNetDetShardedPlan(DetPlan):
                     l()
             graphs.append(g)
         self.graphs = graphs
+
+    def close(self):
+        """Release the peer-memory region of the "push" exchange (collective across the ranks; no-op otherwise)."""
+        if self.peer is not None:
+            self.graph = None
+            self.x3_all = None
+            self.launches = []
+            self.peer.close()
+            self.peer = None
 
     def set_inputs(self, bevs_local, trans_matrices, num_agent_tensor):
         """bevs_local: this rank's unit slice [n_loc,1,256,256,13]; poses / agent counts of ALL scenes."""
@@ -687,6 +739,13 @@ class When2comDetShardedPlan(DetPlan):
                     l()
 
     def capture(self):
+        if self.peer is not None:
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.barrier(group=self.group)   # line the ranks up: the waits of the warm-up steps have a time limit
+            DetPlan.capture(self)     # two eager warm-up steps on every rank (they exchange like real ones), then one graph
+            self.peer.check()
+            return
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

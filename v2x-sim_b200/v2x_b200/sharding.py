@@ -99,3 +99,135 @@ def exchange_neighbour_units(local: torch.Tensor, out: torch.Tensor, batch_total
         for peer, gs, c in recvs:
             ops.append(dist.P2POp(dist.irecv, out[p, gs:gs + c], peer, group))
     return dist.batch_isend_irecv(ops) if ops else []
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Device-side exchange over NVLink peer memory (csrc/peer_kernels.cu): every rank owns a peer-visible region
+# [flag block | payload]; ranks push their maps straight into each other's payload and synchronise through the flag
+# blocks, so the forward needs no host-issued collective and is ONE CUDA graph.  torch.distributed is only used once, at
+# set-up, to hand the 64-byte CUDA IPC handles around.
+# ---------------------------------------------------------------------------------------------------------------------
+PEER_HANDLE_BYTES = 64
+PEER_FLAG_BYTES = 4096
+PEER_TIMEOUT_MS = 20000
+
+
+class _RawCudaBuffer:
+    """Exposes a raw device allocation through __cuda_array_interface__ so torch can view it without copying."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerRegion:
+    """This rank's peer-visible region plus the mapped regions of every other rank of the (single-node) group.
+
+    ``payload(shape, dtype)`` views the local payload as a tensor; ``payload_ptr(r)`` is the device address of rank r's
+    payload as seen from THIS process; ``begin/push/wait/done`` enqueue the four kernels of one exchange step on the
+    current stream (capturable into a CUDA graph); ``check()`` raises if a wait ever timed out."""
+
+    def __init__(self, payload_bytes: int, rank: int, world: int, group=None, device="cuda"):
+        import ctypes as C
+        from . import ops
+        from ._lib import check
+        if world > 8:
+            raise ops.V2XError("the peer-memory exchange supports up to 8 ranks (one NVSwitch domain)")
+        self.lib = ops.require_gpu()
+        self.rank, self.world, self.group, self.device = rank, world, group, torch.device(device)
+        self.nbytes = PEER_FLAG_BYTES + ((int(payload_bytes) + 255) // 256) * 256
+        ptr, handle = C.c_void_p(), (C.c_uint8 * PEER_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            check(self.lib.v2x_peer_alloc(self.nbytes, C.byref(ptr), handle), "v2x_peer_alloc")
+            self.local_ptr = int(ptr.value)
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+            if world > 1:
+                gathered = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(gathered, mine, group=group)
+            else:
+                gathered = [mine]
+            self.ptrs = []
+            for r in range(world):
+                if r == rank:
+                    self.ptrs.append(self.local_ptr)
+                    continue
+                h = (C.c_uint8 * PEER_HANDLE_BYTES)(*gathered[r].cpu().tolist())
+                p = C.c_void_p()
+                check(self.lib.v2x_peer_open(h, C.byref(p)), "v2x_peer_open(rank %d)" % r)
+                self.ptrs.append(int(p.value))
+            self._raw = _RawCudaBuffer(self.local_ptr, self.nbytes)
+            self._bytes = torch.as_tensor(self._raw, device=self.device)
+            assert self._bytes.data_ptr() == self.local_ptr, "torch copied the peer region instead of viewing it"
+            self.step = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+            torch.cuda.synchronize(self.device)
+        if world > 1:
+            dist.barrier(group=group)        # every region is zeroed and mapped before anyone pushes
+        self._regions = (C.c_void_p * world)(*self.ptrs)
+
+    def payload(self, shape, dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        assert PEER_FLAG_BYTES + nb <= self.nbytes
+        return self._bytes[PEER_FLAG_BYTES:PEER_FLAG_BYTES + nb].view(dtype).view(*shape)
+
+    def payload_ptr(self, r: int) -> int:
+        return self.ptrs[r] + PEER_FLAG_BYTES
+
+    def begin(self):
+        from . import ops
+        from ._lib import check
+        check(self.lib.v2x_peer_begin(self.local_ptr, self.step.data_ptr(), self.rank, self.world, PEER_TIMEOUT_MS,
+                                      self.err.data_ptr(), ops._stream()), "v2x_peer_begin")
+
+    def push(self, src: torch.Tensor, dst_elem_offset: int, dst_plane_stride: int, dst_planes):
+        """src: act planes [P, n, ...] (contiguous); lands at element ``dst_elem_offset`` of plane 0 of every rank's
+        payload (16-bit elements), ``dst_planes[r]`` planes for rank r."""
+        import ctypes as C
+        from . import ops
+        from ._lib import check
+        assert src.is_contiguous() and src.element_size() == 2
+        per_plane = src[0].numel()
+        dst = (C.c_void_p * self.world)(*[self.payload_ptr(r) + 2 * dst_elem_offset for r in range(self.world)])
+        planes = (C.c_int32 * self.world)(*[int(p) for p in dst_planes])
+        check(self.lib.v2x_peer_push(src.data_ptr(), per_plane, per_plane, dst, planes, dst_plane_stride, self._regions,
+                                     self.step.data_ptr(), self.counter.data_ptr(), self.rank, self.world, ops._stream()),
+              "v2x_peer_push")
+
+    def wait(self):
+        from . import ops
+        from ._lib import check
+        check(self.lib.v2x_peer_wait(self.local_ptr, self.step.data_ptr(), self.rank, self.world, PEER_TIMEOUT_MS,
+                                     self.err.data_ptr(), ops._stream()), "v2x_peer_wait")
+
+    def done(self):
+        from . import ops
+        from ._lib import check
+        check(self.lib.v2x_peer_done(self._regions, self.step.data_ptr(), self.rank, self.world, ops._stream()),
+              "v2x_peer_done")
+
+    def check(self):
+        """Host-side check (synchronises): raises if any wait of this rank timed out since the last check."""
+        from . import ops
+        code = int(self.err.item())
+        if code:
+            self.err.zero_()
+            raise ops.V2XError("peer exchange: rank %d timed out waiting for rank %d (%s flag) after %d ms" %
+                               (self.rank, code % 100, "consumed" if code < 200 else "ready", PEER_TIMEOUT_MS))
+
+    def close(self):
+        """Unmap the other ranks' regions, then (after a barrier: nobody still maps it) free the local one.  Collective."""
+        if getattr(self, "ptrs", None) is None:
+            return
+        from ._lib import check
+        torch.cuda.synchronize(self.device)
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                check(self.lib.v2x_peer_close(p), "v2x_peer_close")
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self._bytes = self._raw = None
+        check(self.lib.v2x_peer_free(self.local_ptr), "v2x_peer_free")
+        self.ptrs = None
