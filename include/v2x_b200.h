@@ -369,6 +369,13 @@ int v2x_gru_gates_bwd(const void* dh, const void* a, const float* bhh, void* da,
 int v2x_warp_mean_bwd(const void* dmean, float* dx, const double* trans, const int64_t* num_agent, int32_t batch, int32_t agents,
                       int32_t h, int32_t w, int32_t c, int32_t planes, int32_t include_self, int32_t only_v2i, void* stream);
 
+/* backward of v2x_warp_reduce_fwd (Mean / Sum / Max fusion): dx fp32 [A*B][h][w][c] (zeroed here) += dout scattered through the
+ * members' bilinear taps (mode 0 scaled by 1/count; mode 2 routed, per channel, to the first member attaining the maximum,
+ * recomputed from the forward input x, which only mode 2 reads); absent agent slots pass their gradient through */
+int v2x_warp_reduce_bwd(const void* dout, const void* x, float* dx, const double* trans, const int64_t* num_agent, int32_t batch,
+                        int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t mode, int32_t only_v2i,
+                        void* stream);
+
 /* v2x_conv_wgrad on the tensor cores: a GEMM with M = co, N = ci per filter tap, K = pixels whose operands are the NHWC act
  * tensors themselves, consumed as MN-major UMMA operands (csrc/wgrad_tc.cu); same arguments and result */
 int v2x_conv_wgrad_tc(const void* dz, const void* x, int32_t n, int32_t h_out, int32_t w_out, int32_t co, int32_t ci, int32_t planes,

@@ -346,6 +346,9 @@ TRAIN_CASES = {   # tag -> (kind, seed)
     "train_step_cat_seed27": ("cat", 27),
     "train_step_agent_seed28": ("agent", 28),
     "train_step_seg_when2com_seed29": ("seg_when2com", 29),
+    "train_step_mean_seed32": ("mean", 32),
+    "train_step_sum_seed33": ("sum", 33),
+    "train_step_max_seed34": ("max", 34),
 }
 
 
@@ -357,7 +360,7 @@ def train_case(kind, seed):
         return synth.fafnet_state(seed), (synth.make_bevs(3, seed),), ("loc", "cls")
     if kind == "when2com":
         return synth.when2com_det_state(seed), synth.make_scene(1, 5, seed), ("loc", "cls")
-    if kind in ("disco", "cat", "agent"):
+    if kind in ("disco", "cat", "agent", "mean", "sum", "max"):
         return synth.fusion_det_state(kind, seed), synth.make_scene(1, 5, seed, present=[4]), ("loc", "cls")
     if kind == "seg_when2com":
         return synth.seg_when2com_state(seed), synth.make_seg_scene(1, 5, seed), ("logits",)
@@ -389,7 +392,7 @@ def gen_train_step(tag, kind, seed):
             m = ref_loader.ref_fafnet(kd_flag=0)
         elif kind == "when2com":
             m = ref_loader.ref_when2com_det(warp_flag=1)
-        elif kind in ("disco", "cat", "agent"):
+        elif kind in ("disco", "cat", "agent", "mean", "sum", "max"):
             m = ref_loader.ref_fusion_det(kind)
         elif kind == "seg_when2com":
             m = ref_loader.ref_seg_when2com(num_agent=5, warp_flag=1)

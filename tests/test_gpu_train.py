@@ -256,3 +256,90 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
         assert (g is not None) == (k in grads_ref), k
     _check_grads("train_step_%s_seed%d" % (kind, seed), got, grads_ref, golden, parity_log, min_params=40)
     _check_buffers("train_step_%s_seed%d" % (kind, seed), dict(model.named_buffers()), sd_after, parity_log)
+
+
+@pytest.mark.parametrize("kind", ["mean", "sum", "max"])
+def test_fusion_train_step_matches_oracle(kind, golden_dir, parity_log):
+    """MeanFusion / SumFusion / MaxFusion in .train() (FusionBase.py:23-75 under FaFModule.step): encoder -> fuse of the
+    warped member maps at layer 3 (one absent agent slot keeps its own map) -> decoder -> heads; the fuse backward is
+    grid_sample backward through the members' bilinear taps (max: routed to the first member attaining the maximum)."""
+    from coperception.models import det as det_models
+    from oracle import restate
+    from oracle.gen_golden import make_upstream, train_case
+    from v2x_b200 import default_det_config
+    seed = {"mean": 32, "sum": 33, "max": 34}[kind]
+    tag = "train_step_%s_seed%d" % (kind, seed)
+    golden = np.load(os.path.join(golden_dir, tag + ".npz"))
+    sd, inputs, keys = train_case(kind, seed)
+    bevs, trans, nat = inputs
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    shapes = {"loc": (bevs.shape[0], 256, 256, 6, 1, 6), "cls": (bevs.shape[0], 256 * 256 * 6, 2)}
+    up = make_upstream(shapes, seed)
+    out_ref, grads_ref, sd_after = restate.train_step_vjp(
+        lambda s: restate.fusion_det_forward(kind, bevs.double(), trans, nat, s, batch_size=1, agent_num=5), sd64, up)
+    cls_ = {"mean": det_models.MeanFusion, "sum": det_models.SumFusion, "max": det_models.MaxFusion}[kind]
+    model = cls_(default_det_config(), layer=3, kd_flag=0, num_agent=5)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    out = model(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    for k in ("loc", "cls"):
+        e = _rel(out[k], out_ref[k])
+        print(kind, "fusion train forward", k, "rel_err %.3e" % e)
+        assert out[k].shape == out_ref[k].shape and e < 1e-3
+    torch.autograd.backward([out["cls"], out["loc"]], [up["cls"].float().cuda(), up["loc"].float().cuda()])
+    torch.cuda.synchronize()
+    got = {k: p.grad for k, p in model.named_parameters()}
+    for k, g in got.items():
+        assert (g is not None) == (k in grads_ref), k
+    _check_grads(tag, got, grads_ref, golden, parity_log)
+    _check_buffers(tag, dict(model.named_buffers()), sd_after, parity_log, golden=golden)
+
+
+@pytest.mark.parametrize("mode", ["mean", "sum", "max"])
+def test_warp_reduce_bwd_matches_autograd(mode):
+    """v2x_warp_reduce_bwd against torch autograd through grid_sample + mean / sum / max over the member stack (the
+    reference's own ops, flipped domain), two scenes with 5 and 3 present agents, only_v2i on and off."""
+    import ctypes as C
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    from v2x_b200._lib import check
+    lib = ops.require_gpu()
+    B, A, Cc, H = 2, 5, 16, 32
+    present = [5, 3]
+    g = torch.Generator().manual_seed(11)
+    trans = synth.make_trans_matrices(B, A, 11, present=present)
+    nat = torch.tensor([[p] * A for p in present], dtype=torch.long)
+    for only_v2i in (False, True):
+        x = torch.randn((A * B, Cc, H, H), generator=g, dtype=torch.float64).requires_grad_(True)   # un-flipped, agent-major
+        dout = torch.randn((A * B, Cc, H, H), generator=g, dtype=torch.float64)
+        feat = torch.flip(x, (2,))
+        local = torch.stack([feat[B * i: B * (i + 1)] for i in range(A)], 1)          # [B, A, C, H, W], flipped domain
+        outs = [None] * (A * B)
+        for b in range(B):
+            for i in range(A):
+                if i >= present[b]:
+                    outs[B * i + b] = local[b, i]
+                    continue
+                members = [local[b, i]]
+                for j in range(present[b]):
+                    if j != i and not (only_v2i and i != 0 and j != 0):
+                        members.append(restate.feature_transformation(local, b, j, i, trans, (1, Cc, H, H)))
+                st = torch.stack(members)
+                outs[B * i + b] = st.mean(0) if mode == "mean" else st.sum(0) if mode == "sum" else st.max(0).values
+        fused = torch.flip(torch.stack(outs), (2,))
+        fused.backward(dout)
+        to_act = lambda t: ops.pack_input(t.float().permute(0, 2, 3, 1).contiguous().cuda(), Cc, 2)   # noqa: E731
+        dx = torch.empty((A * B, H, H, Cc), dtype=torch.float32, device="cuda")
+        check(lib.v2x_warp_reduce_bwd(C.c_void_p(to_act(dout).data_ptr()), C.c_void_p(to_act(x.detach()).data_ptr()),
+                                      C.c_void_p(dx.data_ptr()), C.c_void_p(trans.cuda().data_ptr()), C.c_void_p(nat.cuda().data_ptr()),
+                                      B, A, H, H, Cc, 2, ops.REDUCE_MODES[mode], int(only_v2i),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "v2x_warp_reduce_bwd")
+        torch.cuda.synchronize()
+        want = x.grad.permute(0, 2, 3, 1)
+        diff = (dx.cpu().double() - want).abs() / want.abs().max()
+        err = diff.max().item()
+        n_bad = int((diff > 1e-4).sum())
+        print("warp_reduce_bwd %s only_v2i=%d rel_err %.3e, elements off by > 1e-4: %d" % (mode, only_v2i, err, n_bad))
+        # max: a near-tie between two members (closer than the fp32 / float64 difference of the two sides) may pick another
+        # winner for a handful of the 164 k elements; everything else must agree
+        assert (n_bad <= 8) if mode == "max" else (err < 1e-4), (err, n_bad)

@@ -249,6 +249,9 @@ def test_train_step_oracle(golden_dir, tag, kind, seed):
         "disco": lambda w: restate.fusion_det_forward("disco", *inputs, w, batch_size=1, agent_num=5),
         "cat": lambda w: restate.fusion_det_forward("cat", *inputs, w, batch_size=1, agent_num=5),
         "agent": lambda w: restate.fusion_det_forward("agent", *inputs, w, batch_size=1, agent_num=5),
+        "mean": lambda w: restate.fusion_det_forward("mean", *inputs, w, batch_size=1, agent_num=5),
+        "sum": lambda w: restate.fusion_det_forward("sum", *inputs, w, batch_size=1, agent_num=5),
+        "max": lambda w: restate.fusion_det_forward("max", *inputs, w, batch_size=1, agent_num=5),
         "seg_when2com": lambda w: wrap(restate.seg_when2com_forward(*inputs, w, agent_num=5, warp_flag=1, training=True)),
         "seg_unet": lambda w: wrap(restate.seg_unet_forward(inputs[0], w)),
         "seg_v2vnet": lambda w: wrap(restate.seg_v2vnet_forward(*inputs, w, agent_num=5)),

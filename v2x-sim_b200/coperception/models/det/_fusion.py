@@ -33,6 +33,7 @@ class FusionBase(B200DetModel):
         super().__init__(config, layer, in_channels, kd_flag, num_agent=num_agent, only_v2i=only_v2i)
         if layer not in (0, 1, 2, 3):
             raise NotImplementedError("v2x_b200 fusion models fuse at layer 0..3 (the reference scripts use layer 3)")
+        self.compress_level = compress_level
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)
         self.num_agent = 0   # the reference overwrites this per scene (FusionBase.py:16,41)
@@ -41,8 +42,19 @@ class FusionBase(B200DetModel):
         from v2x_b200 import nets
         if self.KIND is None:
             raise NotImplementedError("Please implement this method for specific fusion strategies")
-        self._check_eval()
         dev = bevs.device
+        if self.training and self.KIND in ("mean", "sum", "max"):
+            # train-mode forward with a backward pass behind torch.autograd (v2x_b200/train.py::FusionTrainStep): the
+            # parameter-free fuse rules; Cat / AgentWise / DiscoNet (per-pair BatchNorm calls, KD) still refuse below
+            if dev.type != "cuda":
+                raise RuntimeError("v2x_b200 fusion models need CUDA tensors (no CPU fallback); got %s" % dev)
+            if self.layer != 3 or self.compress_level > 0 or self.kd_flag == 1:
+                raise NotImplementedError("training on the sm_100a path: layer 3, compress_level 0, kd_flag 0")
+            from v2x_b200.train import FusionTrainStep
+            loc, cls = FusionTrainStep.apply(self, self.KIND, bevs, trans_matrices, num_agent_tensor, int(batch_size),
+                                             *self.parameters())
+            return None, {"loc": loc, "cls": cls}
+        self._check_eval()
         if dev.type != "cuda":
             raise RuntimeError("v2x_b200 fusion models need CUDA tensors (no CPU fallback); got %s" % dev)
         assert bevs.shape[0] == batch_size * self.agent_num, "bevs must hold batch_size * num_agent maps"

@@ -463,6 +463,120 @@ __global__ void __launch_bounds__(256) warp_mean_bwd_kernel(const __nv_bfloat16*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward of the Mean / Sum / Max fusion reduce (v2x_warp_reduce_fwd; MeanFusion.py:11-12, SumFusion.py:20-21,
+// MaxFusion.py:20-21 under loss.backward()): members of target i = {i} U {present j != i allowed by only_v2i};
+//   mean / sum : dx[b,j][tap] += w_tap * s * dout[b,i][pixel],  dx[b,i][pixel] += s * dout   (s = 1/count or 1)
+//   max        : per channel the gradient goes to the FIRST member (list order: self, then ascending j) that attains the
+//                maximum -- torch.max(torch.stack(list), 0) on CPU -- i.e. through that member's four bilinear taps; the
+//                member values are recomputed from the saved forward input x
+// Absent agent slots keep their own map in the forward (FusionBase.py:41-63), so their gradient passes straight through.
+// One warp per (target unit, output pixel), lanes over channels; fp32 atomics into dx [A*B][H][W][C] (zeroed by the caller).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_reduce_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                              const __nv_bfloat16* __restrict__ x, float* __restrict__ dx,
+                                                              const double* __restrict__ trans,
+                                                              const long long* __restrict__ num_agent, int batch, int agents,
+                                                              int H, int W, int C, int planes, int mode, int only_v2i) {
+  constexpr int kMaxA = 8;
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total_pix = (long long)batch * agents * H * W;
+  const long long plane = total_pix * C;
+  for (long long wid = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total_pix;
+       wid += (long long)gridDim.x * warps_per_block) {
+    const int ow = (int)(wid % W), oh = (int)((wid / W) % H);
+    const int map = (int)(wid / ((long long)W * H));
+    const int i = map / batch, b = map % batch;
+    const int na = min((int)num_agent[(long long)b * agents], agents);
+    if (i >= na) {   // pass-through
+      for (int c0 = lane * 8; c0 < C; c0 += 256) {
+        float d[8];
+        act_load8(dout + wid * C + c0, plane, planes, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(dx + wid * C + c0 + e, d[e]);
+      }
+      continue;
+    }
+    // sample positions of the participating neighbours
+    const float gx = (2.f * ow + 1.f) / W - 1.f, gy = (2.f * oh + 1.f) / H - 1.f;
+    float sx_[kMaxA], sy_[kMaxA];
+    unsigned use = 0;
+    int count = 1;
+#pragma unroll
+    for (int j = 0; j < kMaxA; ++j) {
+      sx_[j] = 0.f; sy_[j] = 0.f;
+      if (j >= na || j == i) continue;
+      if (only_v2i && i != 0 && j != 0) continue;
+      use |= 1u << j;
+      ++count;
+      const double* T = trans + ((((long long)b * agents + j) * agents + i) << 4);
+      const float t00 = (float)T[0], t01 = -(float)T[1], t02 = -(float)T[3] * (1.f / 32.f);
+      const float t10 = -(float)T[4], t11 = (float)T[5], t12 = (float)T[7] * (1.f / 32.f);
+      const float sx = t00 * gx + t01 * gy + t02, sy = t10 * gx + t11 * gy + t12;
+      sx_[j] = ((sx + 1.f) * W - 1.f) * 0.5f;
+      sy_[j] = ((sy + 1.f) * H - 1.f) * 0.5f;
+    }
+    const float s = mode == 0 ? 1.f / (float)count : 1.f;
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float d[8];
+      act_load8(dout + wid * C + c0, plane, planes, d);
+      int who[8];   // max mode: winning member per channel (-1 = self)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) who[e] = -1;
+      if (mode == 2) {
+        float best[8];
+        act_load8(x + wid * C + c0, plane, planes, best);
+#pragma unroll
+        for (int j = 0; j < kMaxA; ++j) {
+          if (!((use >> j) & 1u)) continue;
+          const float fx = floorf(sx_[j]), fy = floorf(sy_[j]);
+          const int x0 = (int)fx, y0 = (int)fy;
+          const float wx1 = sx_[j] - fx, wy1 = sy_[j] - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+          float val[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) val[e] = 0.f;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+            if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+            const float wgt = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
+            float f[8];
+            act_load8(x + ((((long long)batch * j + b) * H + yy) * W + xx) * C + c0, plane, planes, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) val[e] += wgt * f[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (val[e] > best[e]) { best[e] = val[e]; who[e] = j; }
+        }
+      }
+      // self term
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (mode != 2 || who[e] < 0) atomicAdd(dx + wid * C + c0 + e, s * d[e]);
+      // neighbour terms: grid_sample backward through the four taps
+#pragma unroll
+      for (int j = 0; j < kMaxA; ++j) {
+        if (!((use >> j) & 1u)) continue;
+        const float fx = floorf(sx_[j]), fy = floorf(sy_[j]);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float wx1 = sx_[j] - fx, wy1 = sy_[j] - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+          if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+          const float wgt = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0) * s;
+          float* dst = dx + ((((long long)batch * j + b) * H + yy) * W + xx) * C + c0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (mode != 2 || who[e] == j) atomicAdd(dst + e, wgt * d[e]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Segmentation UNet pieces, backward (CP/models/seg/SegModelBase.py:113,125 under loss.backward()).
 // ---------------------------------------------------------------------------------------------
 // nn.MaxPool2d(2) backward: the gradient of an output pixel goes to the FIRST maximum of its 2x2 window in scan order
@@ -708,6 +822,24 @@ extern "C" int v2x_warp_mean_bwd(const void* dmean, float* dx, const double* tra
   warp_mean_bwd_kernel<<<grid_cap(total_pix * 32, 256, 8), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(dmean), dx, trans, reinterpret_cast<const long long*>(num_agent), batch, agents, h, w,
       c, planes, include_self, only_v2i);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_warp_reduce_bwd(const void* dout, const void* x, float* dx, const double* trans, const int64_t* num_agent,
+                                   int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t mode,
+                                   int32_t only_v2i, void* stream) {
+  V2X_REQUIRE(dout && dx && trans && num_agent && batch > 0 && agents > 0 && agents <= 8 && h > 0 && w > 0,
+              "null/empty (agents <= 8)");
+  V2X_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (mean), 1 (sum) or 2 (max)");
+  V2X_REQUIRE(mode != 2 || x, "max mode needs the forward input x");
+  V2X_CHECK_ACT(c, planes);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total_pix = (long long)batch * agents * h * w;
+  V2X_CUDA_TRY(cudaMemsetAsync(dx, 0, sizeof(float) * total_pix * c, s));
+  warp_reduce_bwd_kernel<<<grid_cap(total_pix * 32, 256, 8), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(x), dx, trans,
+      reinterpret_cast<const long long*>(num_agent), batch, agents, h, w, c, planes, mode, only_v2i);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }

@@ -270,6 +270,25 @@ class Tape:
         self.back.append(bwd)
         return m
 
+    def warp_reduce(self, x: Var, trans, num_agent, batch, agents, mode: str, only_v2i=False) -> Var:
+        """Mean / Sum / Max fusion of the warped member maps (FusionBase.py:41-63 with MeanFusion.py:11-12,
+        SumFusion.py:20-21, MaxFusion.py:20-21; absent agent slots keep their own map) with its backward."""
+        lib = self.lib
+        out = ops.warp_reduce(x.act, trans, num_agent, batch, agents, mode, only_v2i=only_v2i)
+        y = Var(out)
+        p, n, h, w, c = x.act.shape
+
+        def bwd():
+            if y.grad is None:
+                return
+            dx = torch.empty((n, h, w, c), dtype=torch.float32, device=self.dev)
+            check(lib.v2x_warp_reduce_bwd(_ptr(y.grad), _ptr(x.act), _ptr(dx), _ptr(trans), _ptr(num_agent), batch, agents, h, w,
+                                          c, p, ops.REDUCE_MODES[mode], int(only_v2i), _stream()), "v2x_warp_reduce_bwd")
+            x.add_grad(lib, ops.pack_input(dx, c, p))
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
     def gru_round(self, h: Var, mean: Var, x_pass: Var, num_agent, batch, agents, prefix="convgru.") -> Var:
         """One zero-hidden ConvGRU step on cat([h, mean]) (V2VNet.py:99-101; functional.py:84-105).  The kernels run in the
         un-flipped domain, so the filter rows are mirrored; the filter gradient is accumulated in that
@@ -459,6 +478,43 @@ class V2VNetTrainStep(torch.autograd.Function):
             grads.append(None if g is None else g.reshape(shape))
         ctx.tape = None
         return (None, None, None, None, None, *grads)
+
+
+class FusionTrainStep(torch.autograd.Function):
+    """One train-mode forward of the parameter-free intermediate-fusion baselines -- MeanFusion / SumFusion / MaxFusion
+    (FusionBase.py:23-75: encoder -> fuse of the warped member maps at layer 3 -> decoder -> heads) -- with its backward.
+    Inputs: (module, kind, bevs, trans_matrices, num_agent_tensor, batch_size, *parameters in named_parameters() order)."""
+
+    @staticmethod
+    def forward(ctx, module, kind, bevs, trans, nat, batch, *params):
+        names = [k for k, _ in module.named_parameters()]
+        p = {k: v.detach() for k, v in zip(names, params)}
+        b = {k: v for k, v in module.named_buffers()}
+        dev = bevs.device
+        n = int(bevs.shape[0])
+        agents = n // batch
+        tape = Tape(p, b, dev)
+        trans = trans.to(device=dev, dtype=torch.float64).contiguous()
+        nat = nat.to(device=dev, dtype=torch.int64).contiguous()
+        x_in = Var(ops.pack_input(bevs.reshape(n, 256, 256, -1).to(torch.float32).contiguous(), 16, PLANES), c_log=int(bevs.shape[-1]))
+        x0, x1, x2, x3, x4 = backbone_encode(tape, "u_encoder.", x_in)
+        fused = tape.warp_reduce(x3, trans, nat, batch, agents, kind, only_v2i=bool(module.only_v2i))
+        x8 = backbone_decode(tape, "decoder.", x0, x1, x2, fused, x4)
+        o_loc, o_cls = det_heads(tape, x8, n)
+        ctx.tape, ctx.names, ctx.o_loc, ctx.o_cls = tape, names, o_loc, o_cls
+        ctx.shapes = [v.shape for v in params]
+        return o_loc.value.view(n, 256, 256, 6, 1, 6), o_cls.value.view(n, -1, 2)
+
+    @staticmethod
+    def backward(ctx, dloc, dcls):
+        tape = ctx.tape
+        tape.scale = choose_scale(*[u for u in (dloc, dcls) if u is not None])
+        ctx.o_loc.upstream, ctx.o_cls.upstream = dloc, dcls
+        tape.backward()
+        grads = [None if tape.grads.get(name) is None else tape.grads[name].reshape(shape)
+                 for name, shape in zip(ctx.names, ctx.shapes)]
+        ctx.tape = None
+        return (None, None, None, None, None, None, *grads)
 
 
 # =====================================================================================================================
