@@ -222,15 +222,15 @@ def test_conv_wgrad_kernels(case, impl):
     assert err < 2e-4, err
 
 
-@pytest.mark.parametrize("kind", ["seg_unet", "seg_v2vnet"])
+@pytest.mark.parametrize("kind", ["seg_unet", "seg_v2vnet", "seg_mean", "seg_max"])
 def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     """seg UNet / seg V2VNet in .train() (what train_seg.py drives through SegModule.step): DoubleConv stacks with batch
     statistics, MaxPool2d and bilinear-upsample backward, fp32 NCHW logits; V2VNet adds one GNN round at 512 channels with
     the self-inclusive neighbour mean."""
-    from coperception.models.seg import UNet, V2VNet
+    from coperception.models.seg import MaxFusion, MeanFusion, UNet, V2VNet
     from oracle import restate
     from oracle.gen_golden import make_upstream, train_case
-    seed = {"seg_unet": 25, "seg_v2vnet": 26}[kind]
+    seed = {"seg_unet": 25, "seg_v2vnet": 26, "seg_mean": 35, "seg_max": 36}[kind]
     golden = np.load(os.path.join(golden_dir, "train_step_%s_seed%d.npz" % (kind, seed)))
     sd, inputs, keys = train_case(kind, seed)
     x = inputs[0]
@@ -239,6 +239,9 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     if kind == "seg_unet":
         fwd = lambda s: {"logits": restate.seg_unet_forward(x.double(), s)}   # noqa: E731
         model = UNet(13, 8)
+    elif kind in ("seg_mean", "seg_max"):    # seg FusionBase family (seg/FusionBase.py:25-84): parameter-free fuse of x4
+        fwd = lambda s: {"logits": restate.seg_fusion_forward(kind[4:], x.double(), inputs[1], inputs[2], s, agent_num=5)}   # noqa: E731
+        model = (MeanFusion if kind == "seg_mean" else MaxFusion)(13, 8, num_agent=5)
     else:
         fwd = lambda s: {"logits": restate.seg_v2vnet_forward(x.double(), inputs[1], inputs[2], s, agent_num=5)}   # noqa: E731
         model = V2VNet(13, 8, num_agent=5)
@@ -258,16 +261,18 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     _check_buffers("train_step_%s_seed%d" % (kind, seed), dict(model.named_buffers()), sd_after, parity_log)
 
 
-@pytest.mark.parametrize("kind", ["mean", "sum", "max"])
+@pytest.mark.parametrize("kind", ["mean", "sum", "max", "cat"])
 def test_fusion_train_step_matches_oracle(kind, golden_dir, parity_log):
-    """MeanFusion / SumFusion / MaxFusion in .train() (FusionBase.py:23-75 under FaFModule.step): encoder -> fuse of the
-    warped member maps at layer 3 (one absent agent slot keeps its own map) -> decoder -> heads; the fuse backward is
-    grid_sample backward through the members' bilinear taps (max: routed to the first member attaining the maximum)."""
+    """MeanFusion / SumFusion / MaxFusion / CatFusion in .train() (FusionBase.py:23-75 under FaFModule.step): encoder -> fuse
+    of the warped member maps at layer 3 (one absent agent slot keeps its own map) -> decoder -> heads; the fuse backward is
+    grid_sample backward through the members' bilinear taps (max: routed to the first member attaining the maximum);
+    CatFusion adds its modulation layer, whose BatchNorm the reference evaluates once per present agent (per-map statistics,
+    one running-buffer update per call)."""
     from coperception.models import det as det_models
     from oracle import restate
     from oracle.gen_golden import make_upstream, train_case
     from v2x_b200 import default_det_config
-    seed = {"mean": 32, "sum": 33, "max": 34}[kind]
+    seed = {"mean": 32, "sum": 33, "max": 34, "cat": 27}[kind]
     tag = "train_step_%s_seed%d" % (kind, seed)
     golden = np.load(os.path.join(golden_dir, tag + ".npz"))
     sd, inputs, keys = train_case(kind, seed)
@@ -277,7 +282,8 @@ def test_fusion_train_step_matches_oracle(kind, golden_dir, parity_log):
     up = make_upstream(shapes, seed)
     out_ref, grads_ref, sd_after = restate.train_step_vjp(
         lambda s: restate.fusion_det_forward(kind, bevs.double(), trans, nat, s, batch_size=1, agent_num=5), sd64, up)
-    cls_ = {"mean": det_models.MeanFusion, "sum": det_models.SumFusion, "max": det_models.MaxFusion}[kind]
+    cls_ = {"mean": det_models.MeanFusion, "sum": det_models.SumFusion, "max": det_models.MaxFusion,
+            "cat": det_models.CatFusion}[kind]
     model = cls_(default_det_config(), layer=3, kd_flag=0, num_agent=5)
     model.load_state_dict(sd, strict=True)
     model = model.cuda().train()
@@ -330,8 +336,9 @@ def test_warp_reduce_bwd_matches_autograd(mode):
         fused.backward(dout)
         to_act = lambda t: ops.pack_input(t.float().permute(0, 2, 3, 1).contiguous().cuda(), Cc, 2)   # noqa: E731
         dx = torch.empty((A * B, H, H, Cc), dtype=torch.float32, device="cuda")
-        check(lib.v2x_warp_reduce_bwd(C.c_void_p(to_act(dout).data_ptr()), C.c_void_p(to_act(x.detach()).data_ptr()),
-                                      C.c_void_p(dx.data_ptr()), C.c_void_p(trans.cuda().data_ptr()), C.c_void_p(nat.cuda().data_ptr()),
+        d_act, x_act, t_dev, n_dev = to_act(dout), to_act(x.detach()), trans.cuda(), nat.cuda()   # kept alive across the launch
+        check(lib.v2x_warp_reduce_bwd(C.c_void_p(d_act.data_ptr()), C.c_void_p(x_act.data_ptr()), C.c_void_p(dx.data_ptr()),
+                                      C.c_void_p(t_dev.data_ptr()), C.c_void_p(n_dev.data_ptr()),
                                       B, A, H, H, Cc, 2, ops.REDUCE_MODES[mode], int(only_v2i),
                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "v2x_warp_reduce_bwd")
         torch.cuda.synchronize()

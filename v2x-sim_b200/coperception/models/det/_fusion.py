@@ -43,9 +43,9 @@ class FusionBase(B200DetModel):
         if self.KIND is None:
             raise NotImplementedError("Please implement this method for specific fusion strategies")
         dev = bevs.device
-        if self.training and self.KIND in ("mean", "sum", "max"):
+        if self.training and self.KIND in ("mean", "sum", "max", "cat"):
             # train-mode forward with a backward pass behind torch.autograd (v2x_b200/train.py::FusionTrainStep): the
-            # parameter-free fuse rules; Cat / AgentWise / DiscoNet (per-pair BatchNorm calls, KD) still refuse below
+            # parameter-free fuse rules and CatFusion; AgentWise / DiscoNet (weight nets called per pair, KD) refuse below
             if dev.type != "cuda":
                 raise RuntimeError("v2x_b200 fusion models need CUDA tensors (no CPU fallback); got %s" % dev)
             if self.layer != 3 or self.compress_level > 0 or self.kd_flag == 1:

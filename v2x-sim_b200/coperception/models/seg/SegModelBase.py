@@ -62,8 +62,8 @@ class SegModelBase(PlanCacheMixin, nn.Module):
         if x.device.type != "cuda":
             raise RuntimeError("v2x_b200 seg models need CUDA tensors (no CPU fallback); got %s" % x.device)
         if self.training:
-            raise NotImplementedError("the sm_100a path trains seg UNet and seg V2VNet; this model only implements "
-                                      "inference (model.eval())")
+            raise NotImplementedError("the sm_100a path trains seg UNet, seg V2VNet and seg Mean / Sum / Max fusion; this model "
+                                      "only implements inference (model.eval())")
         self._warn_no_grad_graph()
 
     def _train_forward(self, x, fuse=None):

@@ -289,6 +289,67 @@ class Tape:
         self.back.append(bwd)
         return y
 
+    def cat_modulate(self, x: Var, mean: Var, num_agent, batch, agents, prefix="_modulation_layer_3.") -> Var:
+        """CatFusion's ModulationLayer3 in train mode (CatFusion.py:23-41): relu(bn(conv1x1(cat[tg, mean]))) evaluated by the
+        reference ONCE PER PRESENT AGENT with a batch of one map, in the order scene-major / agent-minor (FusionBase.py:40-63)
+        -- so the BatchNorm statistics are per map (1024 pixels) and the running buffers take one momentum update per call,
+        in that order.  The 1x1 conv runs as one launch over all maps; statistics / normalise / backward run per map.
+        Absent agent slots keep their own map."""
+        lib = self.lib
+        conv, bn = prefix + "_conv1_1", prefix + "_bn1_1"
+        z, w4, cins = self._conv_raw(conv + ".weight", conv + ".bias", [x, mean], 1)
+        p, n, h, w, c = z.shape
+        hw = h * w
+        gamma, beta = self.p[bn + ".weight"], self.p[bn + ".bias"]
+        rm, rv = self.b[bn + ".running_mean"], self.b[bn + ".running_var"]
+        na = num_agent[:, 0].tolist()                     # host copy: the call order is data dependent (one sync per step)
+        order = [batch * i + b for b in range(batch) for i in range(min(int(na[b]), agents))]
+        present = set(order)
+        out = x.act.clone()                                # absent slots: own map
+        saved = {}
+        for u in order:
+            zu = z[:, u:u + 1].contiguous()
+            s0, s1 = self._f64(c), self._f64(c)
+            check(lib.v2x_bn_stats_fwd(_ptr(zu), hw, c, p, _ptr(s0), _ptr(s1), _stream()), "v2x_bn_stats_fwd")
+            scale, shift, mu, invstd = (self._f32(c) for _ in range(4))
+            check(lib.v2x_bn_finalize(_ptr(s0), _ptr(s1), hw, _ptr(gamma), _ptr(beta), BN_EPS, BN_MOMENTUM, _ptr(rm), _ptr(rv),
+                                      _ptr(scale), _ptr(shift), _ptr(mu), _ptr(invstd), c, _stream()), "v2x_bn_finalize")
+            yu = torch.empty_like(zu)
+            check(lib.v2x_bn_relu_apply_fwd(_ptr(zu), _ptr(yu), hw, c, p, _ptr(scale), _ptr(shift), 1, _stream()),
+                  "v2x_bn_relu_apply_fwd")
+            out[:, u:u + 1].copy_(yu)
+            saved[u] = (zu, scale, shift, mu, invstd)
+        nbt = self.b.get(bn + ".num_batches_tracked")
+        if nbt is not None:
+            nbt += len(order)
+        y = Var(out)
+
+        def bwd():
+            if y.grad is None:
+                return
+            inv = 1.0 / self.scale
+            dz = torch.zeros_like(z)
+            for u in order:
+                zu, scale, shift, mu, invstd = saved[u]
+                dyu = y.grad[:, u:u + 1].contiguous()
+                dzu = torch.empty_like(zu)
+                d1, d2 = self._f64(c), self._f64(c)
+                check(lib.v2x_bn_relu_bwd(_ptr(dyu), _ptr(zu), _ptr(dzu), hw, c, p, _ptr(scale), _ptr(shift), _ptr(mu),
+                                          _ptr(invstd), 1, _ptr(d1), _ptr(d2), _stream()), "v2x_bn_relu_bwd")
+                check(lib.v2x_scale_to_f32(_ptr(d1), _ptr(self._param_grad(bn + ".bias")), c, inv, 1, _stream()), "d beta")
+                check(lib.v2x_scale_to_f32(_ptr(d2), _ptr(self._param_grad(bn + ".weight")), c, inv, 1, _stream()), "d gamma")
+                dz[:, u:u + 1].copy_(dzu)
+            self._param_grad(conv + ".bias")      # in front of a train-mode BN: exactly zero gradient
+            self._conv_backward(conv + ".weight", w4, [x, mean], cins, 1, dz, [True, True])
+            absent = [u for u in range(n) if u not in present]
+            if absent:                            # pass-through of the slots the fuse did not rewrite
+                g = torch.zeros_like(x.act)
+                g[:, absent] = y.grad[:, absent]
+                x.add_grad(lib, g)
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
     def gru_round(self, h: Var, mean: Var, x_pass: Var, num_agent, batch, agents, prefix="convgru.") -> Var:
         """One zero-hidden ConvGRU step on cat([h, mean]) (V2VNet.py:99-101; functional.py:84-105).  The kernels run in the
         un-flipped domain, so the filter rows are mirrored; the filter gradient is accumulated in that
@@ -481,8 +542,8 @@ class V2VNetTrainStep(torch.autograd.Function):
 
 
 class FusionTrainStep(torch.autograd.Function):
-    """One train-mode forward of the parameter-free intermediate-fusion baselines -- MeanFusion / SumFusion / MaxFusion
-    (FusionBase.py:23-75: encoder -> fuse of the warped member maps at layer 3 -> decoder -> heads) -- with its backward.
+    """One train-mode forward of the intermediate-fusion baselines MeanFusion / SumFusion / MaxFusion / CatFusion
+    (FusionBase.py:23-75: encoder -> fuse of the warped member maps at layer 3 -> decoder -> heads) with its backward.
     Inputs: (module, kind, bevs, trans_matrices, num_agent_tensor, batch_size, *parameters in named_parameters() order)."""
 
     @staticmethod
@@ -498,7 +559,11 @@ class FusionTrainStep(torch.autograd.Function):
         nat = nat.to(device=dev, dtype=torch.int64).contiguous()
         x_in = Var(ops.pack_input(bevs.reshape(n, 256, 256, -1).to(torch.float32).contiguous(), 16, PLANES), c_log=int(bevs.shape[-1]))
         x0, x1, x2, x3, x4 = backbone_encode(tape, "u_encoder.", x_in)
-        fused = tape.warp_reduce(x3, trans, nat, batch, agents, kind, only_v2i=bool(module.only_v2i))
+        if kind == "cat":     # CatFusion.py:23-27: mean of the member stack, then the modulation layer on cat[tg, mean]
+            mean = tape.warp_reduce(x3, trans, nat, batch, agents, "mean", only_v2i=bool(module.only_v2i))
+            fused = tape.cat_modulate(x3, mean, nat, batch, agents)
+        else:
+            fused = tape.warp_reduce(x3, trans, nat, batch, agents, kind, only_v2i=bool(module.only_v2i))
         x8 = backbone_decode(tape, "decoder.", x0, x1, x2, fused, x4)
         o_loc, o_cls = det_heads(tape, x8, n)
         ctx.tape, ctx.names, ctx.o_loc, ctx.o_cls = tape, names, o_loc, o_cls
@@ -546,8 +611,9 @@ def seg_decode(t: Tape, feat: Var, x1, x2, x3, n: int):
 
 
 class SegTrainStep(torch.autograd.Function):
-    """One train-mode forward of seg UNet (``fuse`` = None) or seg V2VNet (``fuse`` = (trans, num_agent, batch, agents,
-    only_v2i): one GNN round on the 512-channel layer-4 map, neighbour mean INCLUDING self) with its backward, so the
+    """One train-mode forward of seg UNet (``fuse`` = None), seg V2VNet (``fuse`` = (trans, num_agent, batch, agents,
+    only_v2i): one GNN round on the 512-channel layer-4 map, neighbour mean INCLUDING self) or seg Mean / Sum / Max fusion
+    (``fuse`` = (..., kind)) with its backward, so the
     reference's SegModule.step (CP/utils/SegModule.py:45-120: loss -> backward -> optimizer) drives it unchanged.
     Inputs: (module, fuse, x [N,13,256,256], *parameters in named_parameters() order) -> logits [N, classes, 256, 256]."""
 
@@ -563,12 +629,16 @@ class SegTrainStep(torch.autograd.Function):
         x1, x2, x3, x4 = seg_encode(tape, x_in)
         feat = x4
         if fuse is not None:
-            trans, nat, batch, agents, only_v2i = fuse
+            trans, nat, batch, agents, only_v2i = fuse[:5]
+            kind = fuse[5] if len(fuse) > 5 else "v2v"
             trans = trans.to(device=dev, dtype=torch.float64).contiguous()
             nat = nat.to(device=dev, dtype=torch.int64).contiguous()
-            mean = tape.warp_mean(x4, trans, nat, batch, agents, only_v2i=only_v2i, include_self=True)
-            for _ in range(module.gnn_iter_num):
-                feat = tape.gru_round(feat, mean, x4, nat, batch, agents)
+            if kind == "v2v":
+                mean = tape.warp_mean(x4, trans, nat, batch, agents, only_v2i=only_v2i, include_self=True)
+                for _ in range(module.gnn_iter_num):
+                    feat = tape.gru_round(feat, mean, x4, nat, batch, agents)
+            else:   # seg MeanFusion / SumFusion / MaxFusion (seg/FusionBase.py:25-84): parameter-free fuse of the layer-4 maps
+                feat = tape.warp_reduce(x4, trans, nat, batch, agents, kind, only_v2i=only_v2i)
         out = seg_decode(tape, feat, x1, x2, x3, n)
         ctx.tape, ctx.names, ctx.out = tape, names, out
         ctx.shapes = [v.shape for v in params]
