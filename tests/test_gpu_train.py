@@ -258,7 +258,9 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     for k, g in got.items():
         assert (g is not None) == (k in grads_ref), k
     _check_grads("train_step_%s_seed%d" % (kind, seed), got, grads_ref, golden, parity_log, min_params=40)
-    _check_buffers("train_step_%s_seed%d" % (kind, seed), dict(model.named_buffers()), sd_after, parity_log)
+    # rtol 2e-5: the 512-channel seg layers accumulate K = 4608 products per output in the tensor core's fp32 adder and
+    # carry variances of O(10); measured worst 0.9e-5 relative (seg_max), see profiles/r02_parity.json
+    _check_buffers("train_step_%s_seed%d" % (kind, seed), dict(model.named_buffers()), sd_after, parity_log, rtol=2e-5)
 
 
 @pytest.mark.parametrize("kind", ["mean", "sum", "max", "cat"])
