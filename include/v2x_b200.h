@@ -376,6 +376,12 @@ int v2x_warp_reduce_bwd(const void* dout, const void* x, float* dx, const double
                         int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t mode, int32_t only_v2i,
                         void* stream);
 
+/* backward of v2x_warp_gated_fwd (when2com fuse): dcoef fp32 [B][A][A] (zeroed here) = <dout[b,q], val[b,k,q]> and dx fp32
+ * [A*B][h][w][c] (zeroed here) += coef[b,k,q] * dout[b,q] scattered through val[b,k,q]'s taps; x is the forward input */
+int v2x_warp_gated_bwd(const void* dout, const void* x, float* dx, float* dcoef, const float* coef, const double* trans,
+                       const int64_t* num_agent, int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes,
+                       int32_t warp_flag, int32_t only_v2i, void* stream);
+
 /* v2x_conv_wgrad on the tensor cores: a GEMM with M = co, N = ci per filter tap, K = pixels whose operands are the NHWC act
  * tensors themselves, consumed as MN-major UMMA operands (csrc/wgrad_tc.cu); same arguments and result */
 int v2x_conv_wgrad_tc(const void* dz, const void* x, int32_t n, int32_t h_out, int32_t w_out, int32_t co, int32_t ci, int32_t planes,

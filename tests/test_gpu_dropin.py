@@ -51,13 +51,16 @@ def test_fafnet_module_kd_outputs():
 
 
 def test_train_mode_is_refused_where_not_built():
-    """FaFNet and det V2VNet train on the sm_100a path (tests/test_gpu_train.py); the other models still refuse loudly."""
-    from coperception.models.det import When2com
+    """FaFNet, det V2VNet, det When2com, Mean / Sum / Max / Cat fusion and seg UNet / V2VNet / Mean / Sum / Max fusion train on
+    the sm_100a path (tests/test_gpu_train.py); the models whose weight nets the reference calls per agent pair (DiscoNet,
+    AgentWiseWeightedFusion) and the seg when2com still refuse loudly."""
+    from coperception.models.det import AgentWiseWeightedFusion, DiscoNet
     from v2x_b200 import default_det_config
-    model = When2com(default_det_config(), layer=3, warp_flag=1, num_agent=5).cuda().train()
-    with pytest.raises(NotImplementedError):
-        model(torch.zeros((5, 1, 256, 256, 13), device="cuda"), torch.zeros((1, 5, 5, 4, 4), device="cuda"),
-              torch.full((1, 5), 5, device="cuda"), batch_size=1)
+    for cls in (DiscoNet, AgentWiseWeightedFusion):
+        model = cls(default_det_config(), layer=3, kd_flag=0, num_agent=5).cuda().train()
+        with pytest.raises(NotImplementedError):
+            model(torch.zeros((5, 1, 256, 256, 13), device="cuda"), torch.zeros((1, 5, 5, 4, 4), device="cuda"),
+                  torch.full((1, 5), 5, device="cuda"), batch_size=1)
 
 
 def _v2v_model(seed=2):

@@ -58,6 +58,7 @@ class When2com(B200DetModel):
             raise NotImplementedError("v2x_b200 When2com communicates at layer 3 (the reference scripts' default)")
         if sparse or not has_query:
             raise NotImplementedError("sparse / has_query=False are not built on the sm_100a path")
+        self.compress_level = compress_level
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)
         self.sparse, self.key_size, self.query_size = sparse, key_size, query_size
@@ -76,12 +77,23 @@ class When2com(B200DetModel):
     def forward(self, bevs, trans_matrices, num_agent_tensor, maps=None, vis=None, training=True, MO_flag=True,
                 inference="activated", batch_size=1):
         from v2x_b200 import nets
-        self._check_eval()
         if not MO_flag:
             raise NotImplementedError("MO_flag=False (single query) is not built on the sm_100a path")
         dev = bevs.device
         if dev.type != "cuda":
             raise RuntimeError("v2x_b200 When2com needs CUDA tensors (no CPU fallback); got %s" % dev)
+        if self.training:
+            # model.train(): the train-mode forward with a backward pass behind torch.autograd, as FaFModule.step drives
+            # it (CoDetModule.py:232-247 calls the model with its default training=True)
+            if not training:
+                raise NotImplementedError("model.train() with training=False (the gated second pass) is not built")
+            if self.compress_level > 0:
+                raise NotImplementedError("training with compress_level > 0 is not built on the sm_100a path")
+            from v2x_b200.train import When2comTrainStep
+            loc, cls = When2comTrainStep.apply(self, bevs, trans_matrices, num_agent_tensor, int(batch_size),
+                                               *self.parameters())
+            return {"loc": loc, "cls": cls}
+        self._check_eval()
         if inference not in ("softmax", "activated", "argmax_test"):
             raise ValueError("Incorrect inference mode")
         key = ("w2c", int(batch_size), dev.index, self.precision, bool(training), inference)

@@ -577,6 +577,81 @@ __global__ void __launch_bounds__(256) warp_reduce_bwd_kernel(const __nv_bfloat1
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward of the when2com gated fuse (v2x_warp_gated_fwd; When2com.py:199-225 val_mat + :397-412 weighted sum under
+// loss.backward()).  With val[b,k,q] = (k == q ? x[b,q] : warp(x[b,q], T[b,q,k])) (warp_flag 1, SURVEY Q8 pairing) or
+// x[b,k] (warp_flag 0) and out[b,q] = sum_k coef[b,k,q] * val[b,k,q]:
+//   dcoef[b,k,q] = < dout[b,q], val[b,k,q] >                          (sum over pixels and channels; fp32 atomics)
+//   dx           += coef[b,k,q] * (grid_sample backward of dout[b,q] through val[b,k,q]'s taps)
+// One warp per (target unit, output pixel), lanes over channels.  dx fp32 [A*B][H][W][C] and dcoef fp32 [B][A][A] are
+// zeroed by the launcher; dcoef carries the gradient scale of dout.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_gated_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                             const __nv_bfloat16* __restrict__ x, float* __restrict__ dx,
+                                                             float* __restrict__ dcoef, const float* __restrict__ coef,
+                                                             const double* __restrict__ trans,
+                                                             const long long* __restrict__ num_agent, int batch, int agents,
+                                                             int H, int W, int C, int planes, int warp_flag, int only_v2i) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total_pix = (long long)batch * agents * H * W;
+  const long long plane = total_pix * C;
+  for (long long wid = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total_pix;
+       wid += (long long)gridDim.x * warps_per_block) {
+    const int ow = (int)(wid % W), oh = (int)((wid / W) % H);
+    const int map = (int)(wid / ((long long)W * H));
+    const int q = map / batch, b = map % batch;
+    const int na = min((int)num_agent[(long long)b * agents], agents);
+    const int nterms = warp_flag ? (q < na ? na : 0) : agents;
+    const float gx = (2.f * ow + 1.f) / W - 1.f, gy = (2.f * oh + 1.f) / H - 1.f;
+    for (int k = 0; k < nterms; ++k) {
+      if (warp_flag && only_v2i && k != q && k != 0 && q != 0) continue;
+      const float cf = coef[((long long)b * agents + k) * agents + q];
+      const long long src_map = warp_flag ? (long long)batch * q + b : (long long)batch * k + b;
+      float wts[4];
+      int xs[4], ys[4];
+      int ntap = 4;
+      if (!warp_flag || k == q) {
+        ntap = 1; wts[0] = 1.f; xs[0] = ow; ys[0] = oh;
+      } else {
+        const double* T = trans + ((((long long)b * agents + q) * agents + k) << 4);
+        const float t00 = (float)T[0], t01 = -(float)T[1], t02 = -(float)T[3] * (1.f / 32.f);
+        const float t10 = -(float)T[4], t11 = (float)T[5], t12 = (float)T[7] * (1.f / 32.f);
+        const float sx = t00 * gx + t01 * gy + t02, sy = t10 * gx + t11 * gy + t12;
+        const float ix = ((sx + 1.f) * W - 1.f) * 0.5f, iy = ((sy + 1.f) * H - 1.f) * 0.5f;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          xs[t] = x0 + (t & 1); ys[t] = y0 + (t >> 1);
+          wts[t] = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
+        }
+      }
+      float dot = 0.f;
+      for (int c0 = lane * 8; c0 < C; c0 += 256) {
+        float d[8];
+        act_load8(dout + wid * C + c0, plane, planes, d);
+        for (int t = 0; t < ntap; ++t) {
+          if (xs[t] < 0 || xs[t] >= W || ys[t] < 0 || ys[t] >= H) continue;
+          const long long off = ((src_map * H + ys[t]) * W + xs[t]) * C + c0;
+          float f[8];
+          act_load8(x + off, plane, planes, f);
+          const float wc = wts[t] * cf;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            dot = fmaf(wts[t] * f[e], d[e], dot);
+            if (cf != 0.f) atomicAdd(dx + off + e, wc * d[e]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (lane == 0) atomicAdd(dcoef + ((long long)b * agents + k) * agents + q, dot);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Segmentation UNet pieces, backward (CP/models/seg/SegModelBase.py:113,125 under loss.backward()).
 // ---------------------------------------------------------------------------------------------
 // nn.MaxPool2d(2) backward: the gradient of an output pixel goes to the FIRST maximum of its 2x2 window in scan order
@@ -840,6 +915,23 @@ extern "C" int v2x_warp_reduce_bwd(const void* dout, const void* x, float* dx, c
   warp_reduce_bwd_kernel<<<grid_cap(total_pix * 32, 256, 8), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(x), dx, trans,
       reinterpret_cast<const long long*>(num_agent), batch, agents, h, w, c, planes, mode, only_v2i);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_warp_gated_bwd(const void* dout, const void* x, float* dx, float* dcoef, const float* coef,
+                                  const double* trans, const int64_t* num_agent, int32_t batch, int32_t agents, int32_t h,
+                                  int32_t w, int32_t c, int32_t planes, int32_t warp_flag, int32_t only_v2i, void* stream) {
+  V2X_REQUIRE(dout && x && dx && dcoef && coef && trans && num_agent, "null pointer");
+  V2X_REQUIRE(batch > 0 && agents > 0 && h > 0 && w > 0, "empty geometry");
+  V2X_CHECK_ACT(c, planes);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total_pix = (long long)batch * agents * h * w;
+  V2X_CUDA_TRY(cudaMemsetAsync(dx, 0, sizeof(float) * total_pix * c, s));
+  V2X_CUDA_TRY(cudaMemsetAsync(dcoef, 0, sizeof(float) * (size_t)batch * agents * agents, s));
+  warp_gated_bwd_kernel<<<grid_cap(total_pix * 32, 256, 8), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(x), dx, dcoef, coef, trans,
+      reinterpret_cast<const long long*>(num_agent), batch, agents, h, w, c, planes, warp_flag, only_v2i);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }

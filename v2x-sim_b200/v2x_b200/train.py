@@ -350,6 +350,30 @@ class Tape:
         self.back.append(bwd)
         return y
 
+    def gated_fuse(self, x: Var, coef: torch.Tensor, dcoef_out: Dict[str, torch.Tensor], trans, num_agent, batch, agents,
+                   warp_flag=1, only_v2i=False) -> Var:
+        """when2com fuse out[b,q] = sum_k coef[b,k,q] * val[b,k,q] (When2com.py:199-225, 397-412) with its backward: the map
+        gradient goes onto the tape, d(loss)/d(coef) (unscaled, fp32 [B,A,A]) is left in ``dcoef_out["dcoef"]`` for the
+        attention island that produced ``coef``."""
+        lib = self.lib
+        out = ops.warp_gated(x.act, trans, num_agent, coef, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i)
+        y = Var(out)
+        p, n, h, w, c = x.act.shape
+
+        def bwd():
+            if y.grad is None:
+                return
+            dx = torch.empty((n, h, w, c), dtype=torch.float32, device=self.dev)
+            dcoef = torch.empty((batch, agents, agents), dtype=torch.float32, device=self.dev)
+            check(lib.v2x_warp_gated_bwd(_ptr(y.grad), _ptr(x.act), _ptr(dx), _ptr(dcoef), _ptr(coef), _ptr(trans),
+                                         _ptr(num_agent), batch, agents, h, w, c, p, int(warp_flag), int(only_v2i), _stream()),
+                  "v2x_warp_gated_bwd")
+            dcoef_out["dcoef"] = dcoef * (1.0 / self.scale)
+            x.add_grad(lib, ops.pack_input(dx, c, p))
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
     def gru_round(self, h: Var, mean: Var, x_pass: Var, num_agent, batch, agents, prefix="convgru.") -> Var:
         """One zero-hidden ConvGRU step on cat([h, mean]) (V2VNet.py:99-101; functional.py:84-105).  The kernels run in the
         un-flipped domain, so the filter rows are mirrored; the filter gradient is accumulated in that
@@ -580,6 +604,94 @@ class FusionTrainStep(torch.autograd.Function):
                  for name, shape in zip(ctx.names, ctx.shapes)]
         ctx.tape = None
         return (None, None, None, None, None, None, *grads)
+
+
+class When2comTrainStep(torch.autograd.Function):
+    """One train-mode forward of det When2com / who2com with ``training=True`` (When2com.py:150-332: image encoder, policy
+    encoder PolicyNet4 = a second LidarEncoder + five conv/BN/ReLU, key / query MLPs, key-query attention with a softmax
+    over the keys, ONE decoder pass on the attention-weighted fuse, heads) with its backward.
+    The conv stacks, the fuse and their backward (99.99% of the step's FLOPs) run in the sm_100a kernels on the tape.  The
+    handshake itself -- three-layer MLPs on [units, 4096] vectors, a 32 -> 1024 linear layer and a 5 x 5 softmax per scene,
+    about 0.1 GFLOP per step -- is an "island" evaluated with torch autograd in fp32: its inputs (the policy features) come
+    off the tape, its output (the attention coefficients) feeds v2x_warp_gated_fwd, and in the backward
+    v2x_warp_gated_bwd's d(coef) is pushed through the island to the policy features and to the island's parameters.
+    Inputs: (module, bevs, trans_matrices, num_agent_tensor, batch_size, *parameters in named_parameters() order)."""
+
+    ISLAND = ("key_net.", "query_net.", "attention_net.")
+
+    @staticmethod
+    def forward(ctx, module, bevs, trans, nat, batch, *params):
+        import torch.nn.functional as F
+        names = [k for k, _ in module.named_parameters()]
+        p = {k: v.detach() for k, v in zip(names, params)}
+        b = {k: v for k, v in module.named_buffers()}
+        dev = bevs.device
+        n = int(bevs.shape[0])
+        agents = n // batch
+        tape = Tape(p, b, dev)
+        lib = tape.lib
+        trans = trans.to(device=dev, dtype=torch.float64).contiguous()
+        nat = nat.to(device=dev, dtype=torch.int64).contiguous()
+        x_in = Var(ops.pack_input(bevs.reshape(n, 256, 256, -1).to(torch.float32).contiguous(), 16, PLANES), c_log=int(bevs.shape[-1]))
+        x0, x1, x2, x3, x4 = backbone_encode(tape, "u_encoder.", x_in)
+        # policy branch (PolicyNet4, When2com.py:335-359): its own encoder, then conv1..conv5 (strides 1, 1, 2, 1, 2)
+        q = backbone_encode(tape, "query_key_net.lidar_encoder.", x_in)[4]
+        for i, stride in enumerate((1, 1, 2, 1, 2), start=1):
+            pre = "query_key_net.conv%d.cbr_unit." % i
+            q = tape.cbr(pre + "0", pre + "1", [q], stride=stride)
+        # ---- the handshake island (torch autograd, fp32) ----
+        island_names = [k for k in names if k.startswith(When2comTrainStep.ISLAND)]
+        with torch.enable_grad():
+            feat = ops.act_to_float(q.act).detach().requires_grad_(True)          # [N, 256, 4, 4] fp32, NCHW like the reference
+            ip = {k: p[k].detach().to(torch.float32).requires_grad_(True) for k in island_names}
+            flat = feat.reshape(n, -1)                                            # KmGenerator: features_map.view(-1, n_feat)
+
+            def mlp(pre):
+                hid = F.relu(F.linear(flat, ip[pre + "fc.0.weight"], ip[pre + "fc.0.bias"]))
+                hid = F.relu(F.linear(hid, ip[pre + "fc.2.weight"], ip[pre + "fc.2.bias"]))
+                return F.linear(hid, ip[pre + "fc.4.weight"], ip[pre + "fc.4.bias"])
+            keys, querys = mlp("key_net."), mlp("query_net.")
+            key_mat = torch.stack([keys[batch * i: batch * (i + 1)] for i in range(agents)], 1)        # [B, A, key_size]
+            query_mat = torch.stack([querys[batch * i: batch * (i + 1)] for i in range(agents)], 1)    # [B, A, query_size]
+            query = F.linear(query_mat, ip["attention_net.linear.weight"], ip["attention_net.linear.bias"])
+            attn = torch.softmax(torch.bmm(key_mat, query.transpose(2, 1)), dim=1)                      # [B, key, query]
+        coef = attn.detach().contiguous()
+        holder: Dict[str, torch.Tensor] = {}
+
+        def island_bwd():
+            dcoef = holder.get("dcoef")
+            if dcoef is None:
+                return
+            leaves = [feat] + [ip[k] for k in island_names]
+            grads = torch.autograd.grad(attn, leaves, grad_outputs=dcoef, allow_unused=True)
+            if grads[0] is not None:
+                if os.environ.get("V2X_TRAIN_DEBUG"):
+                    print("[when2com island] |d feat| max %.3e, x scale %.3e = %.3e; |dcoef| max %.3e" % (
+                        float(grads[0].abs().max()), tape.scale, float(grads[0].abs().max()) * tape.scale, float(dcoef.abs().max())))
+                g = (grads[0] * tape.scale).contiguous()
+                q.add_grad(lib, ops.pack_input_nchw(g, int(g.shape[1]), PLANES))
+            for k, gk in zip(island_names, grads[1:]):
+                if gk is not None:
+                    tape._param_grad(k).add_(gk)
+        tape.back.append(island_bwd)
+        fused = tape.gated_fuse(x3, coef, holder, trans, nat, batch, agents, warp_flag=int(module.warp_flag),
+                                only_v2i=bool(module.only_v2i))
+        x8 = backbone_decode(tape, "decoder.", x0, x1, x2, fused, x4)
+        o_loc, o_cls = det_heads(tape, x8, n)
+        ctx.tape, ctx.names, ctx.o_loc, ctx.o_cls = tape, names, o_loc, o_cls
+        ctx.shapes = [v.shape for v in params]
+        return o_loc.value.view(n, 256, 256, 6, 1, 6), o_cls.value.view(n, -1, 2)
+
+    @staticmethod
+    def backward(ctx, dloc, dcls):
+        tape = ctx.tape
+        tape.scale = choose_scale(*[u for u in (dloc, dcls) if u is not None])
+        ctx.o_loc.upstream, ctx.o_cls.upstream = dloc, dcls
+        tape.backward()
+        grads = [None if tape.grads.get(name) is None else tape.grads[name].reshape(shape)
+                 for name, shape in zip(ctx.names, ctx.shapes)]
+        ctx.tape = None
+        return (None, None, None, None, None, *grads)
 
 
 # =====================================================================================================================
