@@ -51,9 +51,9 @@ def test_fafnet_module_kd_outputs():
 
 
 def test_train_mode_is_refused_where_not_built():
-    """FaFNet, det V2VNet, det When2com, Mean / Sum / Max / Cat fusion and seg UNet / V2VNet / Mean / Sum / Max fusion train on
-    the sm_100a path (tests/test_gpu_train.py); the models whose weight nets the reference calls per agent pair (DiscoNet,
-    AgentWiseWeightedFusion) and the seg when2com still refuse loudly."""
+    """FaFNet, det V2VNet, det When2com, Mean / Sum / Max / Cat fusion and seg UNet / V2VNet / When2Com_UNet / Mean / Sum / Max
+    fusion train on the sm_100a path (tests/test_gpu_train.py); the models whose weight nets the reference calls per agent
+    pair (DiscoNet, AgentWiseWeightedFusion) still refuse loudly."""
     from coperception.models.det import AgentWiseWeightedFusion, DiscoNet
     from v2x_b200 import default_det_config
     for cls in (DiscoNet, AgentWiseWeightedFusion):

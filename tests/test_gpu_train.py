@@ -227,15 +227,15 @@ def test_conv_wgrad_kernels(case, impl):
     assert err < 2e-4, err
 
 
-@pytest.mark.parametrize("kind", ["seg_unet", "seg_v2vnet", "seg_mean", "seg_max"])
+@pytest.mark.parametrize("kind", ["seg_unet", "seg_v2vnet", "seg_mean", "seg_max", "seg_when2com"])
 def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     """seg UNet / seg V2VNet in .train() (what train_seg.py drives through SegModule.step): DoubleConv stacks with batch
     statistics, MaxPool2d and bilinear-upsample backward, fp32 NCHW logits; V2VNet adds one GNN round at 512 channels with
     the self-inclusive neighbour mean."""
-    from coperception.models.seg import MaxFusion, MeanFusion, UNet, V2VNet
+    from coperception.models.seg import MaxFusion, MeanFusion, UNet, V2VNet, When2Com_UNet
     from oracle import restate
     from oracle.gen_golden import make_upstream, train_case
-    seed = {"seg_unet": 25, "seg_v2vnet": 26, "seg_mean": 35, "seg_max": 36}[kind]
+    seed = {"seg_unet": 25, "seg_v2vnet": 26, "seg_mean": 35, "seg_max": 36, "seg_when2com": 29}[kind]
     golden = np.load(os.path.join(golden_dir, "train_step_%s_seed%d.npz" % (kind, seed)))
     sd, inputs, keys = train_case(kind, seed)
     x = inputs[0]
@@ -244,6 +244,11 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     if kind == "seg_unet":
         fwd = lambda s: {"logits": restate.seg_unet_forward(x.double(), s)}   # noqa: E731
         model = UNet(13, 8)
+    elif kind == "seg_when2com":             # When2Com_UNet with training=True (SegModule.py:66-89), warp_flag 1
+        fwd = lambda s: {"logits": restate.seg_when2com_forward(x.double(), inputs[1], inputs[2], s, agent_num=5, warp_flag=1,   # noqa: E731
+                                                                training=True)}
+        from v2x_b200 import default_det_config
+        model = When2Com_UNet(default_det_config(), n_classes=8, in_channels=13, warp_flag=1, num_agent=5)
     elif kind in ("seg_mean", "seg_max"):    # seg FusionBase family (seg/FusionBase.py:25-84): parameter-free fuse of x4
         fwd = lambda s: {"logits": restate.seg_fusion_forward(kind[4:], x.double(), inputs[1], inputs[2], s, agent_num=5)}   # noqa: E731
         model = (MeanFusion if kind == "seg_mean" else MaxFusion)(13, 8, num_agent=5)
@@ -253,7 +258,12 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     out_ref, grads_ref, sd_after = restate.train_step_vjp(fwd, sd64, up)
     model.load_state_dict(sd, strict=True)
     model = model.cuda().train()
-    out = model(x.cuda()) if kind == "seg_unet" else model(x.cuda(), inputs[1].cuda(), inputs[2].cuda())
+    if kind == "seg_unet":
+        out = model(x.cuda())
+    elif kind == "seg_when2com":
+        out = model(x.cuda(), inputs[1].cuda(), inputs[2].cuda(), training=True)
+    else:
+        out = model(x.cuda(), inputs[1].cuda(), inputs[2].cuda())
     e = _rel(out, out_ref["logits"])
     print(kind, "train forward logits rel_err %.3e" % e)
     assert out.shape == out_ref["logits"].shape and e < 1e-3

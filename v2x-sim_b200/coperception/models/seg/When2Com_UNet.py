@@ -37,9 +37,17 @@ class When2Com_UNet(SegModelBase):
     def forward(self, bevs, trans_matrices, num_agent_tensor, maps=None, vis=None, training=True, MO_flag=True,
                 inference="activated", batch_size=1):
         from v2x_b200 import nets_seg
-        self._check(bevs)
         if not MO_flag:
             raise NotImplementedError("MO_flag=False is not built on the sm_100a path")
+        if self.training:
+            # model.train(): train-mode forward with a backward pass behind torch.autograd, as SegModule.step drives it
+            # (SegModule.py:66-89 calls the model with training=True)
+            if not training:
+                raise NotImplementedError("model.train() with training=False (the gated pass) is not built")
+            batch = int(bevs.shape[0]) // self.num_agent
+            return self._train_forward(bevs, (trans_matrices, num_agent_tensor, batch, self.num_agent, bool(self.only_v2i),
+                                              "when2com", int(self.warp_flag)))
+        self._check(bevs)
         if inference not in ("softmax", "activated", "argmax_test"):
             raise ValueError("Incorrect inference mode")
         batch = int(bevs.shape[0]) // self.num_agent   # the reference recomputes it from the input (When2Com_UNet.py:166)

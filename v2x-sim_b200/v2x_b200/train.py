@@ -606,6 +606,56 @@ class FusionTrainStep(torch.autograd.Function):
         return (None, None, None, None, None, None, *grads)
 
 
+ISLAND_PREFIXES = ("key_net.", "query_net.", "attention_net.")
+
+
+def handshake_island(tape: Tape, q: Var, p: Dict[str, torch.Tensor], names, batch: int, agents: int):
+    """The when2com handshake between the policy features ``q`` (on the tape) and the fuse kernel: KmGenerator key / query
+    MLPs on ``features.view(-1, 4096)`` (When2com.py:415-430; for the seg model's 256 x 8 x 8 features that view makes FOUR
+    rows per map and rows 0..A*B-1 are taken as the agents' keys / queries, When2Com_UNet.py:207-226), the
+    32 -> 1024 linear layer on the queries, key . query scores and the softmax over the keys (When2com.py:374-412).
+    Evaluated with torch autograd in fp32 (about 0.1 GFLOP per step).  Returns (coef [B, key, query] fp32 for
+    v2x_warp_gated_fwd, holder): the fuse's backward leaves d(loss)/d(coef) in ``holder["dcoef"]`` and the closure
+    registered here -- it must sit on the tape BEFORE the fuse -- pushes it back to ``q`` and to the island's parameters."""
+    import torch.nn.functional as F
+    lib = tape.lib
+    island_names = [k for k in names if k.startswith(ISLAND_PREFIXES)]
+    with torch.enable_grad():
+        feat = ops.act_to_float(q.act).detach().requires_grad_(True)          # [N, 256, h, w] fp32, NCHW like the reference
+        ip = {k: p[k].detach().to(torch.float32).requires_grad_(True) for k in island_names}
+        flat = feat.reshape(-1, ip["key_net.fc.0.weight"].shape[1])           # KmGenerator: features_map.view(-1, n_feat)
+
+        def mlp(pre):
+            hid = F.relu(F.linear(flat, ip[pre + "fc.0.weight"], ip[pre + "fc.0.bias"]))
+            hid = F.relu(F.linear(hid, ip[pre + "fc.2.weight"], ip[pre + "fc.2.bias"]))
+            return F.linear(hid, ip[pre + "fc.4.weight"], ip[pre + "fc.4.bias"])
+        keys, querys = mlp("key_net."), mlp("query_net.")
+        key_mat = torch.stack([keys[batch * i: batch * (i + 1)] for i in range(agents)], 1)        # [B, A, key_size]
+        query_mat = torch.stack([querys[batch * i: batch * (i + 1)] for i in range(agents)], 1)    # [B, A, query_size]
+        query = F.linear(query_mat, ip["attention_net.linear.weight"], ip["attention_net.linear.bias"])
+        attn = torch.softmax(torch.bmm(key_mat, query.transpose(2, 1)), dim=1)                      # [B, key, query]
+    coef = attn.detach().contiguous()
+    holder: Dict[str, torch.Tensor] = {}
+
+    def island_bwd():
+        dcoef = holder.get("dcoef")
+        if dcoef is None:
+            return
+        leaves = [feat] + [ip[k] for k in island_names]
+        grads = torch.autograd.grad(attn, leaves, grad_outputs=dcoef, allow_unused=True)
+        if grads[0] is not None:
+            if os.environ.get("V2X_TRAIN_DEBUG"):
+                print("[when2com island] |d feat| max %.3e, x scale %.3e = %.3e; |dcoef| max %.3e" % (
+                    float(grads[0].abs().max()), tape.scale, float(grads[0].abs().max()) * tape.scale, float(dcoef.abs().max())))
+            g = (grads[0] * tape.scale).contiguous()
+            q.add_grad(lib, ops.pack_input_nchw(g, int(g.shape[1]), PLANES))
+        for k, gk in zip(island_names, grads[1:]):
+            if gk is not None:
+                tape._param_grad(k).add_(gk)
+    tape.back.append(island_bwd)
+    return coef, holder
+
+
 class When2comTrainStep(torch.autograd.Function):
     """One train-mode forward of det When2com / who2com with ``training=True`` (When2com.py:150-332: image encoder, policy
     encoder PolicyNet4 = a second LidarEncoder + five conv/BN/ReLU, key / query MLPs, key-query attention with a softmax
@@ -617,11 +667,8 @@ class When2comTrainStep(torch.autograd.Function):
     v2x_warp_gated_bwd's d(coef) is pushed through the island to the policy features and to the island's parameters.
     Inputs: (module, bevs, trans_matrices, num_agent_tensor, batch_size, *parameters in named_parameters() order)."""
 
-    ISLAND = ("key_net.", "query_net.", "attention_net.")
-
     @staticmethod
     def forward(ctx, module, bevs, trans, nat, batch, *params):
-        import torch.nn.functional as F
         names = [k for k, _ in module.named_parameters()]
         p = {k: v.detach() for k, v in zip(names, params)}
         b = {k: v for k, v in module.named_buffers()}
@@ -639,41 +686,7 @@ class When2comTrainStep(torch.autograd.Function):
         for i, stride in enumerate((1, 1, 2, 1, 2), start=1):
             pre = "query_key_net.conv%d.cbr_unit." % i
             q = tape.cbr(pre + "0", pre + "1", [q], stride=stride)
-        # ---- the handshake island (torch autograd, fp32) ----
-        island_names = [k for k in names if k.startswith(When2comTrainStep.ISLAND)]
-        with torch.enable_grad():
-            feat = ops.act_to_float(q.act).detach().requires_grad_(True)          # [N, 256, 4, 4] fp32, NCHW like the reference
-            ip = {k: p[k].detach().to(torch.float32).requires_grad_(True) for k in island_names}
-            flat = feat.reshape(n, -1)                                            # KmGenerator: features_map.view(-1, n_feat)
-
-            def mlp(pre):
-                hid = F.relu(F.linear(flat, ip[pre + "fc.0.weight"], ip[pre + "fc.0.bias"]))
-                hid = F.relu(F.linear(hid, ip[pre + "fc.2.weight"], ip[pre + "fc.2.bias"]))
-                return F.linear(hid, ip[pre + "fc.4.weight"], ip[pre + "fc.4.bias"])
-            keys, querys = mlp("key_net."), mlp("query_net.")
-            key_mat = torch.stack([keys[batch * i: batch * (i + 1)] for i in range(agents)], 1)        # [B, A, key_size]
-            query_mat = torch.stack([querys[batch * i: batch * (i + 1)] for i in range(agents)], 1)    # [B, A, query_size]
-            query = F.linear(query_mat, ip["attention_net.linear.weight"], ip["attention_net.linear.bias"])
-            attn = torch.softmax(torch.bmm(key_mat, query.transpose(2, 1)), dim=1)                      # [B, key, query]
-        coef = attn.detach().contiguous()
-        holder: Dict[str, torch.Tensor] = {}
-
-        def island_bwd():
-            dcoef = holder.get("dcoef")
-            if dcoef is None:
-                return
-            leaves = [feat] + [ip[k] for k in island_names]
-            grads = torch.autograd.grad(attn, leaves, grad_outputs=dcoef, allow_unused=True)
-            if grads[0] is not None:
-                if os.environ.get("V2X_TRAIN_DEBUG"):
-                    print("[when2com island] |d feat| max %.3e, x scale %.3e = %.3e; |dcoef| max %.3e" % (
-                        float(grads[0].abs().max()), tape.scale, float(grads[0].abs().max()) * tape.scale, float(dcoef.abs().max())))
-                g = (grads[0] * tape.scale).contiguous()
-                q.add_grad(lib, ops.pack_input_nchw(g, int(g.shape[1]), PLANES))
-            for k, gk in zip(island_names, grads[1:]):
-                if gk is not None:
-                    tape._param_grad(k).add_(gk)
-        tape.back.append(island_bwd)
+        coef, holder = handshake_island(tape, q, p, names, batch, agents)
         fused = tape.gated_fuse(x3, coef, holder, trans, nat, batch, agents, warp_flag=int(module.warp_flag),
                                 only_v2i=bool(module.only_v2i))
         x8 = backbone_decode(tape, "decoder.", x0, x1, x2, fused, x4)
@@ -702,11 +715,11 @@ def seg_double_conv(t: Tape, p: str, srcs, need_input_grad=None) -> Var:
     return t.cbr(p + "3", p + "4", [x])
 
 
-def seg_encode(t: Tape, x_in: Var):
-    x1 = seg_double_conv(t, "inc.double_conv.", [x_in], need_input_grad=[False])
-    x2 = seg_double_conv(t, "down1.maxpool_conv.1.double_conv.", [t.maxpool2(x1)])
-    x3 = seg_double_conv(t, "down2.maxpool_conv.1.double_conv.", [t.maxpool2(x2)])
-    x4 = seg_double_conv(t, "down3.maxpool_conv.1.double_conv.", [t.maxpool2(x3)])
+def seg_encode(t: Tape, x_in: Var, pre: str = ""):
+    x1 = seg_double_conv(t, pre + "inc.double_conv.", [x_in], need_input_grad=[False])
+    x2 = seg_double_conv(t, pre + "down1.maxpool_conv.1.double_conv.", [t.maxpool2(x1)])
+    x3 = seg_double_conv(t, pre + "down2.maxpool_conv.1.double_conv.", [t.maxpool2(x2)])
+    x4 = seg_double_conv(t, pre + "down3.maxpool_conv.1.double_conv.", [t.maxpool2(x3)])
     return x1, x2, x3, x4
 
 
@@ -749,6 +762,15 @@ class SegTrainStep(torch.autograd.Function):
                 mean = tape.warp_mean(x4, trans, nat, batch, agents, only_v2i=only_v2i, include_self=True)
                 for _ in range(module.gnn_iter_num):
                     feat = tape.gru_round(feat, mean, x4, nat, batch, agents)
+            elif kind == "when2com":
+                # seg When2Com_UNet with training=True (When2Com_UNet.py:144-307): policy branch = its own inc / down1..3
+                # + conv1..conv5 (strides 1, 1, 2, 1, 2) -> [N, 256, 8, 8]; handshake island; attention-weighted fuse of x4
+                q = seg_encode(tape, x_in, "query_key_net.")[3]
+                for i, stride in enumerate((1, 1, 2, 1, 2), start=1):
+                    cpre = "query_key_net.conv%d.cbr_unit." % i
+                    q = tape.cbr(cpre + "0", cpre + "1", [q], stride=stride)
+                coef, holder = handshake_island(tape, q, p, names, batch, agents)
+                feat = tape.gated_fuse(x4, coef, holder, trans, nat, batch, agents, warp_flag=int(fuse[6]), only_v2i=only_v2i)
             else:   # seg MeanFusion / SumFusion / MaxFusion (seg/FusionBase.py:25-84): parameter-free fuse of the layer-4 maps
                 feat = tape.warp_reduce(x4, trans, nat, batch, agents, kind, only_v2i=only_v2i)
         out = seg_decode(tape, feat, x1, x2, x3, n)
