@@ -227,15 +227,15 @@ def test_conv_wgrad_kernels(case, impl):
     assert err < 2e-4, err
 
 
-@pytest.mark.parametrize("kind", ["seg_unet", "seg_v2vnet", "seg_mean", "seg_max", "seg_when2com"])
+@pytest.mark.parametrize("kind", ["seg_unet", "seg_v2vnet", "seg_mean", "seg_max", "seg_cat", "seg_when2com"])
 def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     """seg UNet / seg V2VNet in .train() (what train_seg.py drives through SegModule.step): DoubleConv stacks with batch
     statistics, MaxPool2d and bilinear-upsample backward, fp32 NCHW logits; V2VNet adds one GNN round at 512 channels with
     the self-inclusive neighbour mean."""
-    from coperception.models.seg import MaxFusion, MeanFusion, UNet, V2VNet, When2Com_UNet
+    from coperception.models.seg import CatFusion, MaxFusion, MeanFusion, UNet, V2VNet, When2Com_UNet
     from oracle import restate
     from oracle.gen_golden import make_upstream, train_case
-    seed = {"seg_unet": 25, "seg_v2vnet": 26, "seg_mean": 35, "seg_max": 36, "seg_when2com": 29}[kind]
+    seed = {"seg_unet": 25, "seg_v2vnet": 26, "seg_mean": 35, "seg_max": 36, "seg_cat": 37, "seg_when2com": 29}[kind]
     golden = np.load(os.path.join(golden_dir, "train_step_%s_seed%d.npz" % (kind, seed)))
     sd, inputs, keys = train_case(kind, seed)
     x = inputs[0]
@@ -249,9 +249,12 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
                                                                 training=True)}
         from v2x_b200 import default_det_config
         model = When2Com_UNet(default_det_config(), n_classes=8, in_channels=13, warp_flag=1, num_agent=5)
-    elif kind in ("seg_mean", "seg_max"):    # seg FusionBase family (seg/FusionBase.py:25-84): parameter-free fuse of x4
+    elif kind in ("seg_mean", "seg_max", "seg_cat"):    # seg FusionBase family (seg/FusionBase.py:25-84): fuse of x4
         fwd = lambda s: {"logits": restate.seg_fusion_forward(kind[4:], x.double(), inputs[1], inputs[2], s, agent_num=5)}   # noqa: E731
-        model = (MeanFusion if kind == "seg_mean" else MaxFusion)(13, 8, num_agent=5)
+        if kind == "seg_cat":
+            model = CatFusion(13, 8, 5, 0, False)
+        else:
+            model = (MeanFusion if kind == "seg_mean" else MaxFusion)(13, 8, num_agent=5)
     else:
         fwd = lambda s: {"logits": restate.seg_v2vnet_forward(x.double(), inputs[1], inputs[2], s, agent_num=5)}   # noqa: E731
         model = V2VNet(13, 8, num_agent=5)

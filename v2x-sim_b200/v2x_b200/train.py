@@ -289,14 +289,14 @@ class Tape:
         self.back.append(bwd)
         return y
 
-    def cat_modulate(self, x: Var, mean: Var, num_agent, batch, agents, prefix="_modulation_layer_3.") -> Var:
+    def cat_modulate(self, x: Var, mean: Var, num_agent, batch, agents, conv="_modulation_layer_3._conv1_1",
+                     bn="_modulation_layer_3._bn1_1") -> Var:
         """CatFusion's ModulationLayer3 in train mode (CatFusion.py:23-41): relu(bn(conv1x1(cat[tg, mean]))) evaluated by the
         reference ONCE PER PRESENT AGENT with a batch of one map, in the order scene-major / agent-minor (FusionBase.py:40-63)
         -- so the BatchNorm statistics are per map (1024 pixels) and the running buffers take one momentum update per call,
         in that order.  The 1x1 conv runs as one launch over all maps; statistics / normalise / backward run per map.
         Absent agent slots keep their own map."""
         lib = self.lib
-        conv, bn = prefix + "_conv1_1", prefix + "_bn1_1"
         z, w4, cins = self._conv_raw(conv + ".weight", conv + ".bias", [x, mean], 1)
         p, n, h, w, c = z.shape
         hw = h * w
@@ -771,6 +771,10 @@ class SegTrainStep(torch.autograd.Function):
                     q = tape.cbr(cpre + "0", cpre + "1", [q], stride=stride)
                 coef, holder = handshake_island(tape, q, p, names, batch, agents)
                 feat = tape.gated_fuse(x4, coef, holder, trans, nat, batch, agents, warp_flag=int(fuse[6]), only_v2i=only_v2i)
+            elif kind == "cat":   # seg CatFusion (seg/CatFusion.py:8-34): mean, then the per-agent modulation layer
+                mean = tape.warp_reduce(x4, trans, nat, batch, agents, "mean", only_v2i=only_v2i)
+                feat = tape.cat_modulate(x4, mean, nat, batch, agents, conv="modulation_layer_3.conv1_1",
+                                         bn="modulation_layer_3.bn1_1")
             else:   # seg MeanFusion / SumFusion / MaxFusion (seg/FusionBase.py:25-84): parameter-free fuse of the layer-4 maps
                 feat = tape.warp_reduce(x4, trans, nat, batch, agents, kind, only_v2i=only_v2i)
         out = seg_decode(tape, feat, x1, x2, x3, n)
