@@ -118,3 +118,52 @@ def test_bench_config_table():
     assert bench.CONFIGS["v2v_det"]["gflop"] == 264.51 and bench.CONFIGS["faf_lower"]["gflop"] == 31.16
     assert bench.CONFIGS["w2c_seg"]["gflop"] == 581.38 and abs(bench.CONFIGS["faf_upper_dp"]["gflop"] - 6 * 31.16) < 1e-9
     assert set(bench.DTYPE_OF) == {"mixed", "fp16x3", "bf16"}
+
+
+def test_warp_staged_box_rule_covers_every_tap():
+    """csrc/warp_staged.cuh stages, per (8x8 output tile, member term), the bounding box of the tile's footprint in the
+    source map: the box of the four CORNER samples widened by 0.01 px, +1 for the bilinear taps, clipped to the map.  This
+    emulates that rule in float32 exactly as the kernel evaluates it (affine_grid + grid_sample, align_corners=False, theta'
+    of the un-flipped domain) and checks, over random rigid poses and map sizes incl. partial tiles, that (a) every in-map tap
+    of every output pixel lies inside the box -- so the kernel's direct-gather fallback for stray taps never triggers -- and
+    (b) the box never exceeds the 192 staged pixels (kWsCap), so rigid poses always take the staged path."""
+    import numpy as np
+    f32 = np.float32
+
+    def sample(t, ow, oh, W, H):
+        gx = (f32(2) * ow.astype(f32) + f32(1)) / f32(W) - f32(1)
+        gy = (f32(2) * oh.astype(f32) + f32(1)) / f32(H) - f32(1)
+        sx = t[0] * gx + t[1] * gy + t[2]
+        sy = t[3] * gx + t[4] * gy + t[5]
+        return ((sx + f32(1)) * f32(W) - f32(1)) * f32(0.5), ((sy + f32(1)) * f32(H) - f32(1)) * f32(0.5)
+
+    rng = np.random.default_rng(0)
+    stray, worst = 0, 0
+    for _ in range(400):
+        W = H = int(rng.choice([32, 64, 20, 28]))
+        yaw = rng.uniform(-np.pi, np.pi)
+        tx, ty = rng.uniform(-60, 60, 2)
+        c, s = np.cos(yaw), np.sin(yaw)
+        t = np.array([c, s, -tx / 32, -s, c, ty / 32], dtype=f32)     # [[T00, -T01, -T03/32], [-T10, T11, +T13/32]], T01 = -s
+        for th in range((H + 7) // 8):
+            for tw in range((W + 7) // 8):
+                oh0, ow0 = th * 8, tw * 8
+                cx, cy = sample(t, np.array([ow0, ow0 + 7, ow0, ow0 + 7]), np.array([oh0, oh0, oh0 + 7, oh0 + 7]), W, H)
+                bx0 = max(0, int(np.floor(cx.min() - f32(0.01))))
+                bx1 = min(W - 1, int(np.floor(cx.max() + f32(0.01))) + 1)
+                by0 = max(0, int(np.floor(cy.min() - f32(0.01))))
+                by1 = min(H - 1, int(np.floor(cy.max() + f32(0.01))) + 1)
+                pw, ph = np.meshgrid(np.arange(ow0, min(ow0 + 8, W)), np.arange(oh0, min(oh0 + 8, H)))
+                ix, iy = sample(t, pw.ravel(), ph.ravel(), W, H)
+                x0, y0 = np.floor(ix).astype(int), np.floor(iy).astype(int)
+                empty = bx0 > bx1 or by0 > by1
+                for dx in (0, 1):
+                    for dy in (0, 1):
+                        xx, yy = x0 + dx, y0 + dy
+                        in_map = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+                        in_box = (xx >= bx0) & (xx <= bx1) & (yy >= by0) & (yy <= by1) if not empty else np.zeros_like(in_map)
+                        stray += int((in_map & ~in_box).sum())
+                if not empty:
+                    worst = max(worst, (bx1 - bx0 + 1) * (by1 - by0 + 1))
+    assert stray == 0
+    assert worst <= 192, worst
