@@ -1,4 +1,6 @@
-"""Multi-GPU correctness of the unit-sharded V2VNet plan (run under torchrun, one rank per GPU):
+"""Multi-GPU parity check (test infrastructure: it imports the oracle; lives under tests/ for that reason, run by hand or by
+tools/gpu_push.sh under torchrun, one rank per GPU -- not collected by pytest).
+Multi-GPU correctness of the unit-sharded V2VNet plan:
 every rank's slice of loc/cls must equal the same slice of the single-GPU plan (bit-identical: same kernels, same
 per-unit math) and match the CPU oracle within the 1e-3 tolerance in the default "mixed" precision."""
 import os, sys

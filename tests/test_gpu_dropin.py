@@ -158,7 +158,7 @@ def test_forward_under_enable_grad_warns_once():
 def test_peer_region_single_rank_protocol():
     """The device-side exchange (csrc/peer_kernels.cu, sharding.PeerRegion) with world = 1: the step counter advances, the
     push lands every plane of the source in the payload slot it names, flags carry the step number, no wait times out.
-    (Cross-process mapping of the regions is what tools/multigpu_check.py with V2X_EXCHANGE=push checks on 2+ GPUs.)"""
+    (Cross-process mapping of the regions is what tests/multigpu_check.py with V2X_EXCHANGE=push checks on 2+ GPUs.)"""
     import torch
     from v2x_b200 import ops, sharding
     ops.require_gpu()
