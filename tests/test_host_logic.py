@@ -167,3 +167,58 @@ def test_warp_staged_box_rule_covers_every_tap():
                     worst = max(worst, (bx1 - bx0 + 1) * (by1 - by0 + 1))
     assert stray == 0
     assert worst <= 192, worst
+
+
+def test_peer_exchange_protocol_is_deadlock_free_and_never_overwrites_unread_maps():
+    """Discrete-event model of the device-side x_3 exchange (csrc/peer_kernels.cu): every rank runs, in its own stream
+    order, begin (step += 1; wait consumed[r] >= step - 1 for all r) -> push (write its slot of EVERY region, then publish
+    ready[rank] = step everywhere) -> wait (ready[r] >= step for all r) -> read (the fuse kernel reads its own region) ->
+    done (publish consumed[rank] = step everywhere).  Ranks are interleaved by a random scheduler (any rank whose next
+    kernel is not blocked may run: that is all stream order guarantees).  Checked over many schedules and world sizes:
+    no schedule deadlocks, every read sees exactly the maps of its own step from every rank, and no slot is overwritten
+    between the time it was published and the time its owner region's rank has read it (the region is single-buffered)."""
+    import random
+    for world in (1, 2, 3, 4, 8):
+        for trial in range(60):
+            rnd = random.Random(1000 * world + trial)
+            steps = 6
+            ready = [[0] * world for _ in range(world)]       # ready[region][writer]
+            consumed = [[0] * world for _ in range(world)]    # consumed[region][reader]
+            slot = [[0] * world for _ in range(world)]        # slot[region][writer] = step whose maps are stored there
+            pending_read = [[False] * world for _ in range(world)]   # published but not yet read by the region's rank
+            step = [0] * world
+            pc = [0] * world                                   # 0 begin, 1 push, 2 wait, 3 read, 4 done
+            done_steps = [0] * world
+            guard = 0
+            while min(done_steps) < steps:
+                guard += 1
+                assert guard < 100000
+                runnable = []
+                for r in range(world):
+                    if done_steps[r] >= steps:
+                        continue
+                    if pc[r] == 0 and not all(consumed[r][q] >= step[r] for q in range(world) if q != r):
+                        continue                                # begin: peers have not consumed my previous maps yet
+                    if pc[r] == 2 and not all(ready[r][q] >= step[r] for q in range(world) if q != r):
+                        continue                                # wait: not every rank's maps of this step have landed
+                    runnable.append(r)
+                assert runnable, "deadlock: world %d trial %d state %s %s" % (world, trial, pc, step)
+                r = rnd.choice(runnable)
+                if pc[r] == 0:
+                    step[r] += 1
+                elif pc[r] == 1:
+                    for region in range(world):
+                        assert not pending_read[region][r], "rank %d overwrote maps rank %d has not read" % (r, region)
+                        slot[region][r] = step[r]
+                        pending_read[region][r] = True
+                        ready[region][r] = step[r]
+                elif pc[r] == 3:
+                    assert all(slot[r][q] == step[r] for q in range(world)), (world, trial, r, slot[r], step[r])
+                    for q in range(world):
+                        pending_read[r][q] = False
+                elif pc[r] == 4:
+                    for region in range(world):
+                        consumed[region][r] = step[r]
+                    done_steps[r] += 1
+                pc[r] = (pc[r] + 1) % 5
+            assert step == [steps] * world
