@@ -369,12 +369,14 @@ int v2x_gru_gates_bwd(const void* dh, const void* a, const float* bhh, void* da,
 int v2x_warp_mean_bwd(const void* dmean, float* dx, const double* trans, const int64_t* num_agent, int32_t batch, int32_t agents,
                       int32_t h, int32_t w, int32_t c, int32_t planes, int32_t include_self, int32_t only_v2i, void* stream);
 
-/* backward of v2x_warp_reduce_fwd (Mean / Sum / Max fusion): dx fp32 [A*B][h][w][c] (zeroed here) += dout scattered through the
- * members' bilinear taps (mode 0 scaled by 1/count; mode 2 routed, per channel, to the first member attaining the maximum,
- * recomputed from the forward input x, which only mode 2 reads); absent agent slots pass their gradient through */
-int v2x_warp_reduce_bwd(const void* dout, const void* x, float* dx, const double* trans, const int64_t* num_agent, int32_t batch,
-                        int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t mode, int32_t only_v2i,
-                        void* stream);
+/* backward of v2x_warp_reduce_fwd (Mean / Sum / Max fusion) and of v2x_warp_weighted_fwd with per-pair coefficients
+ * (AgentWiseWeightedFusion): dx fp32 [A*B][h][w][c] (zeroed here) += dout scattered through the members' bilinear taps
+ * (mode 0 scaled by 1/count; mode 2 routed, per channel, to the first member attaining the maximum, recomputed from the
+ * forward input x, which only mode 2 reads; mode 3 scaled by the constant coef[b][i][k], fp32 [B][A][A], else unused);
+ * absent agent slots pass their gradient through */
+int v2x_warp_reduce_bwd(const void* dout, const void* x, float* dx, const float* coef, const double* trans,
+                        const int64_t* num_agent, int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c,
+                        int32_t planes, int32_t mode, int32_t only_v2i, void* stream);
 
 /* backward of v2x_warp_gated_fwd (when2com fuse): dcoef fp32 [B][A][A] (zeroed here) = <dout[b,q], val[b,k,q]> and dx fp32
  * [A*B][h][w][c] (zeroed here) += coef[b,k,q] * dout[b,q] scattered through val[b,k,q]'s taps; x is the forward input */

@@ -51,16 +51,16 @@ def test_fafnet_module_kd_outputs():
 
 
 def test_train_mode_is_refused_where_not_built():
-    """FaFNet, det V2VNet, det When2com, Mean / Sum / Max / Cat fusion and seg UNet / V2VNet / When2Com_UNet / Mean / Sum / Max
-    fusion train on the sm_100a path (tests/test_gpu_train.py); the models whose weight nets the reference calls per agent
-    pair (DiscoNet, AgentWiseWeightedFusion) still refuse loudly."""
-    from coperception.models.det import AgentWiseWeightedFusion, DiscoNet
+    """Every model except DiscoNet trains on the sm_100a path (tests/test_gpu_train.py); DiscoNet -- whose per-pair weight
+    net is trained through the per-pixel softmax -- and KD training still refuse loudly."""
+    from coperception.models.det import DiscoNet, MeanFusion
     from v2x_b200 import default_det_config
-    for cls in (DiscoNet, AgentWiseWeightedFusion):
-        model = cls(default_det_config(), layer=3, kd_flag=0, num_agent=5).cuda().train()
-        with pytest.raises(NotImplementedError):
-            model(torch.zeros((5, 1, 256, 256, 13), device="cuda"), torch.zeros((1, 5, 5, 4, 4), device="cuda"),
-                  torch.full((1, 5), 5, device="cuda"), batch_size=1)
+    args = (torch.zeros((5, 1, 256, 256, 13), device="cuda"), torch.zeros((1, 5, 5, 4, 4), device="cuda"),
+            torch.full((1, 5), 5, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        DiscoNet(default_det_config(), layer=3, kd_flag=0, num_agent=5).cuda().train()(*args, batch_size=1)
+    with pytest.raises(NotImplementedError):      # kd_flag = 1 returns the intermediate maps for the distillation loss
+        MeanFusion(default_det_config(), layer=3, kd_flag=1, num_agent=5).cuda().train()(*args, batch_size=1)
 
 
 def _v2v_model(seed=2):

@@ -21,11 +21,18 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
 
 
+PER_CALL_NETS = ("agent_weighted_fusion.",)
+
+
 def _check_buffers(tag, after, want_sd, parity_log, golden=None, rtol=1e-5):
     """BatchNorm running buffers after one step vs the float64 oracle (and the live reference's, when the fixture holds
     them): |got - want| <= 1e-5 + rtol * |want| (deep seg layers carry variances of O(10)).  The worst measured error, in
     units of that bound, goes on record."""
+    # BatchNorm layers of the AgentWise weight net see ONE map per call (1024 pixels of unit-variance features) and ~20
+    # sequential momentum updates per step: their batch statistics carry the 1e-4 error of the conv in front of them without
+    # the averaging over maps the backbone layers enjoy (measured 2e-4 absolute); they are held to 1e-3 absolute
     worst, worst_key, worst_abs = 0.0, None, 0.0
+    worst_pc = 0.0
     for k, v in want_sd.items():
         if k.endswith("num_batches_tracked"):
             assert int(after[k]) == int(v), k
@@ -36,12 +43,19 @@ def _check_buffers(tag, after, want_sd, parity_log, golden=None, rtol=1e-5):
         got = after[k].detach().double().cpu()
         for w in wants:
             w = w.detach().double().cpu()
+            if k.startswith(PER_CALL_NETS):
+                worst_pc = max(worst_pc, (got - w).abs().max().item())
+                continue
             err = ((got - w).abs() / (1e-5 + rtol * w.abs())).max().item()
             if err > worst:
                 worst, worst_key, worst_abs = err, k, (got - w).abs().max().item()
     print(tag, "BN running buffers: worst error %.2f x (1e-5 + %.0e*|v|) at %s (abs %.2e)" % (worst, rtol, worst_key, worst_abs))
-    parity_log(tag, "train fp16x3 bn buffers", worst_over_bound=worst, rtol=rtol, worst_abs=worst_abs, worst_key=str(worst_key))
+    parity_log(tag, "train fp16x3 bn buffers", worst_over_bound=worst, rtol=rtol, worst_abs=worst_abs, worst_key=str(worst_key),
+               per_call_weight_net_worst_abs=worst_pc)
+    if worst_pc:
+        print(tag, "per-call weight-net BN buffers: worst abs error %.2e (bound 1e-3)" % worst_pc)
     assert worst <= 1.0, (worst_key, worst, worst_abs)
+    assert worst_pc <= 1e-3, worst_pc
 
 
 def _check_grads(tag, got, want, golden, parity_log, zero_tol=1e-9, min_params=50, norm_tol=None):
@@ -228,15 +242,15 @@ def test_conv_wgrad_kernels(case, impl):
     assert err < 2e-4, err
 
 
-@pytest.mark.parametrize("kind", ["seg_unet", "seg_v2vnet", "seg_mean", "seg_max", "seg_cat", "seg_when2com"])
+@pytest.mark.parametrize("kind", ["seg_unet", "seg_v2vnet", "seg_mean", "seg_max", "seg_cat", "seg_agent", "seg_when2com"])
 def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     """seg UNet / seg V2VNet in .train() (what train_seg.py drives through SegModule.step): DoubleConv stacks with batch
     statistics, MaxPool2d and bilinear-upsample backward, fp32 NCHW logits; V2VNet adds one GNN round at 512 channels with
     the self-inclusive neighbour mean."""
-    from coperception.models.seg import CatFusion, MaxFusion, MeanFusion, UNet, V2VNet, When2Com_UNet
+    from coperception.models.seg import AgentWiseWeightedFusion, CatFusion, MaxFusion, MeanFusion, UNet, V2VNet, When2Com_UNet
     from oracle import restate
     from oracle.gen_golden import make_upstream, train_case
-    seed = {"seg_unet": 25, "seg_v2vnet": 26, "seg_mean": 35, "seg_max": 36, "seg_cat": 37, "seg_when2com": 29}[kind]
+    seed = {"seg_unet": 25, "seg_v2vnet": 26, "seg_mean": 35, "seg_max": 36, "seg_cat": 37, "seg_agent": 38, "seg_when2com": 29}[kind]
     golden = np.load(os.path.join(golden_dir, "train_step_%s_seed%d.npz" % (kind, seed)))
     sd, inputs, keys = train_case(kind, seed)
     x = inputs[0]
@@ -250,10 +264,12 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
                                                                 training=True)}
         from v2x_b200 import default_det_config
         model = When2Com_UNet(default_det_config(), n_classes=8, in_channels=13, warp_flag=1, num_agent=5)
-    elif kind in ("seg_mean", "seg_max", "seg_cat"):    # seg FusionBase family (seg/FusionBase.py:25-84): fuse of x4
+    elif kind in ("seg_mean", "seg_max", "seg_cat", "seg_agent"):    # seg FusionBase family (seg/FusionBase.py:25-84): fuse of x4
         fwd = lambda s: {"logits": restate.seg_fusion_forward(kind[4:], x.double(), inputs[1], inputs[2], s, agent_num=5)}   # noqa: E731
         if kind == "seg_cat":
             model = CatFusion(13, 8, 5, 0, False)
+        elif kind == "seg_agent":
+            model = AgentWiseWeightedFusion(13, 8, 5, 0, False)
         else:
             model = (MeanFusion if kind == "seg_mean" else MaxFusion)(13, 8, num_agent=5)
     else:
@@ -284,18 +300,19 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     _check_buffers("train_step_%s_seed%d" % (kind, seed), dict(model.named_buffers()), sd_after, parity_log, rtol=2e-5)
 
 
-@pytest.mark.parametrize("kind", ["mean", "sum", "max", "cat"])
+@pytest.mark.parametrize("kind", ["mean", "sum", "max", "cat", "agent"])
 def test_fusion_train_step_matches_oracle(kind, golden_dir, parity_log):
     """MeanFusion / SumFusion / MaxFusion / CatFusion in .train() (FusionBase.py:23-75 under FaFModule.step): encoder -> fuse
     of the warped member maps at layer 3 (one absent agent slot keeps its own map) -> decoder -> heads; the fuse backward is
     grid_sample backward through the members' bilinear taps (max: routed to the first member attaining the maximum);
     CatFusion adds its modulation layer, whose BatchNorm the reference evaluates once per present agent (per-map statistics,
-    one running-buffer update per call)."""
+    one running-buffer update per call); AgentWiseWeightedFusion mixes the members with the softmax of per-pair scalars that
+    the reference DETACHES (the weight net gets no gradient but its BatchNorm buffers are updated call by call)."""
     from coperception.models import det as det_models
     from oracle import restate
     from oracle.gen_golden import make_upstream, train_case
     from v2x_b200 import default_det_config
-    seed = {"mean": 32, "sum": 33, "max": 34, "cat": 27}[kind]
+    seed = {"mean": 32, "sum": 33, "max": 34, "cat": 27, "agent": 28}[kind]
     tag = "train_step_%s_seed%d" % (kind, seed)
     golden = np.load(os.path.join(golden_dir, tag + ".npz"))
     sd, inputs, keys = train_case(kind, seed)
@@ -306,7 +323,7 @@ def test_fusion_train_step_matches_oracle(kind, golden_dir, parity_log):
     out_ref, grads_ref, sd_after = restate.train_step_vjp(
         lambda s: restate.fusion_det_forward(kind, bevs.double(), trans, nat, s, batch_size=1, agent_num=5), sd64, up)
     cls_ = {"mean": det_models.MeanFusion, "sum": det_models.SumFusion, "max": det_models.MaxFusion,
-            "cat": det_models.CatFusion}[kind]
+            "cat": det_models.CatFusion, "agent": det_models.AgentWiseWeightedFusion}[kind]
     model = cls_(default_det_config(), layer=3, kd_flag=0, num_agent=5)
     model.load_state_dict(sd, strict=True)
     model = model.cuda().train()
@@ -361,7 +378,7 @@ def test_warp_reduce_bwd_matches_autograd(mode):
         dx = torch.empty((A * B, H, H, Cc), dtype=torch.float32, device="cuda")
         d_act, x_act, t_dev, n_dev = to_act(dout), to_act(x.detach()), trans.cuda(), nat.cuda()   # kept alive across the launch
         check(lib.v2x_warp_reduce_bwd(C.c_void_p(d_act.data_ptr()), C.c_void_p(x_act.data_ptr()), C.c_void_p(dx.data_ptr()),
-                                      C.c_void_p(t_dev.data_ptr()), C.c_void_p(n_dev.data_ptr()),
+                                      C.c_void_p(0), C.c_void_p(t_dev.data_ptr()), C.c_void_p(n_dev.data_ptr()),
                                       B, A, H, H, Cc, 2, ops.REDUCE_MODES[mode], int(only_v2i),
                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "v2x_warp_reduce_bwd")
         torch.cuda.synchronize()

@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(256) warp_mean_bwd_kernel(const __nv_bfloat16*
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) warp_reduce_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
                                                               const __nv_bfloat16* __restrict__ x, float* __restrict__ dx,
+                                                              const float* __restrict__ coef,
                                                               const double* __restrict__ trans,
                                                               const long long* __restrict__ num_agent, int batch, int agents,
                                                               int H, int W, int C, int planes, int mode, int only_v2i) {
@@ -517,6 +518,8 @@ __global__ void __launch_bounds__(256) warp_reduce_bwd_kernel(const __nv_bfloat1
       sy_[j] = ((sy + 1.f) * H - 1.f) * 0.5f;
     }
     const float s = mode == 0 ? 1.f / (float)count : 1.f;
+    // mode 3 (AgentWiseWeightedFusion.py:27-34): out = sum_k coef[b,i,k] * member_k with constant per-pair coefficients
+    const float* cf = mode == 3 ? coef + ((long long)b * agents + i) * agents : nullptr;
     for (int c0 = lane * 8; c0 < C; c0 += 256) {
       float d[8];
       act_load8(dout + wid * C + c0, plane, planes, d);
@@ -553,7 +556,7 @@ __global__ void __launch_bounds__(256) warp_reduce_bwd_kernel(const __nv_bfloat1
       // self term
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (mode != 2 || who[e] < 0) atomicAdd(dx + wid * C + c0 + e, s * d[e]);
+        if (mode != 2 || who[e] < 0) atomicAdd(dx + wid * C + c0 + e, (cf ? cf[i] : s) * d[e]);
       // neighbour terms: grid_sample backward through the four taps
 #pragma unroll
       for (int j = 0; j < kMaxA; ++j) {
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(256) warp_reduce_bwd_kernel(const __nv_bfloat1
         for (int t = 0; t < 4; ++t) {
           const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
           if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
-          const float wgt = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0) * s;
+          const float wgt = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0) * (cf ? cf[j] : s);
           float* dst = dx + ((((long long)batch * j + b) * H + yy) * W + xx) * C + c0;
 #pragma unroll
           for (int e = 0; e < 8; ++e)
@@ -901,19 +904,20 @@ extern "C" int v2x_warp_mean_bwd(const void* dmean, float* dx, const double* tra
   return V2X_OK;
 }
 
-extern "C" int v2x_warp_reduce_bwd(const void* dout, const void* x, float* dx, const double* trans, const int64_t* num_agent,
-                                   int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t mode,
-                                   int32_t only_v2i, void* stream) {
+extern "C" int v2x_warp_reduce_bwd(const void* dout, const void* x, float* dx, const float* coef, const double* trans,
+                                   const int64_t* num_agent, int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c,
+                                   int32_t planes, int32_t mode, int32_t only_v2i, void* stream) {
   V2X_REQUIRE(dout && dx && trans && num_agent && batch > 0 && agents > 0 && agents <= 8 && h > 0 && w > 0,
               "null/empty (agents <= 8)");
-  V2X_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (mean), 1 (sum) or 2 (max)");
+  V2X_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 (mean), 1 (sum), 2 (max) or 3 (per-pair coefficients)");
   V2X_REQUIRE(mode != 2 || x, "max mode needs the forward input x");
+  V2X_REQUIRE(mode != 3 || coef, "mode 3 needs coef [B][A][A]");
   V2X_CHECK_ACT(c, planes);
   cudaStream_t s = (cudaStream_t)stream;
   const long long total_pix = (long long)batch * agents * h * w;
   V2X_CUDA_TRY(cudaMemsetAsync(dx, 0, sizeof(float) * total_pix * c, s));
   warp_reduce_bwd_kernel<<<grid_cap(total_pix * 32, 256, 8), 256, 0, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(x), dx, trans,
+      reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(x), dx, coef, trans,
       reinterpret_cast<const long long*>(num_agent), batch, agents, h, w, c, planes, mode, only_v2i);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;

@@ -282,8 +282,9 @@ class Tape:
             if y.grad is None:
                 return
             dx = torch.empty((n, h, w, c), dtype=torch.float32, device=self.dev)
-            check(lib.v2x_warp_reduce_bwd(_ptr(y.grad), _ptr(x.act), _ptr(dx), _ptr(trans), _ptr(num_agent), batch, agents, h, w,
-                                          c, p, ops.REDUCE_MODES[mode], int(only_v2i), _stream()), "v2x_warp_reduce_bwd")
+            check(lib.v2x_warp_reduce_bwd(_ptr(y.grad), _ptr(x.act), _ptr(dx), _ptr(None), _ptr(trans), _ptr(num_agent), batch,
+                                          agents, h, w, c, p, ops.REDUCE_MODES[mode], int(only_v2i), _stream()),
+                  "v2x_warp_reduce_bwd")
             x.add_grad(lib, ops.pack_input(dx, c, p))
             y.grad = None
         self.back.append(bwd)
@@ -346,6 +347,67 @@ class Tape:
                 g = torch.zeros_like(x.act)
                 g[:, absent] = y.grad[:, absent]
                 x.add_grad(lib, g)
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
+    def agent_weighted_fuse(self, x: Var, trans, num_agent, batch, agents, only_v2i=False,
+                            prefix="agent_weighted_fusion.") -> Var:
+        """AgentWiseWeightedFusion in train mode (AgentWiseWeightedFusion.py:24-43, 44-76; seg twin): for every present target
+        i and list member k (self first, then the other present agents in ascending order) the weight net maps
+        cat[tg_i, warp_{k->i}(x_k)] to one scalar; the members are mixed with the softmax of those scalars.  The reference
+        rebuilds the scalars with ``torch.tensor([...])``, which DETACHES them: the weight net gets no gradient and the fuse
+        back-propagates to the maps only, with constant coefficients (v2x_warp_reduce_bwd mode 3).  The weight net still runs
+        in train mode -- BatchNorm statistics per call (one map), running buffers updated call by call in that order.
+        Its first layer (512 -> 128 over every pixel of every pair, 94% of its FLOPs) runs here as one 1x1-conv launch per
+        member slot over the warped maps (v2x_warp_weighted_fwd with a one-hot coefficient); the per-call tail
+        (BN, 128 -> 32 -> 8 -> 1 per pixel, the 32x32 conv1_5: 9 MFLOP per call, forward only) is evaluated with torch in
+        fp32, in the reference's call order, on the module's own running buffers."""
+        import torch.nn.functional as F
+        lib = self.lib
+        p_, n, h, w, c = x.act.shape
+        na = [min(int(v), agents) for v in num_agent[:, 0].tolist()]
+        f32 = lambda k: self.p[prefix + k].detach().to(torch.float32)   # noqa: E731
+        z1 = []
+        for k in range(agents):                     # member slot k: agent k's map warped into every target's frame
+            onehot = torch.zeros((batch, agents, agents), dtype=torch.float32, device=self.dev)
+            onehot[:, :, k] = 1.0
+            wk = Var(ops.warp_weighted(x.act, trans, num_agent, onehot, batch, agents, per_pixel=False, only_v2i=only_v2i))
+            zk, _, _ = self._conv_raw(prefix + "conv1_1.weight", prefix + "conv1_1.bias", [x, wk], 1)
+            z1.append(ops.act_to_float(zk))         # [units, 128, h, w] fp32
+        w5f = torch.flip(f32("conv1_5.weight").reshape(h, w), (0,))      # the 32x32 "valid" conv sees the H-flipped map
+        coef = torch.zeros((batch, agents, agents), dtype=torch.float32, device=self.dev)
+        with torch.no_grad():
+            for b in range(batch):
+                for i in range(na[b]):
+                    members = [i] + [k for k in range(na[b]) if k != i and not (only_v2i and i != 0 and k != 0)]
+                    scal = []
+                    for k in members:
+                        t = z1[k][batch * i + b: batch * i + b + 1]
+                        for li, cname in ((1, None), (2, "conv1_2"), (3, "conv1_3")):
+                            if cname is not None:
+                                t = F.conv2d(t, f32(cname + ".weight"), f32(cname + ".bias"))
+                            bn = prefix + "bn1_%d" % li
+                            t = F.relu(F.batch_norm(t, self.b[bn + ".running_mean"], self.b[bn + ".running_var"], f32("bn1_%d.weight" % li),
+                                                    f32("bn1_%d.bias" % li), True, BN_MOMENTUM, BN_EPS))
+                            nbt = self.b.get(bn + ".num_batches_tracked")
+                            if nbt is not None:
+                                nbt += 1
+                        t = F.relu(F.conv2d(t, f32("conv1_4.weight"), f32("conv1_4.bias")))
+                        scal.append(F.relu((t.reshape(h, w) * w5f).sum() + f32("conv1_5.bias").reshape(())))
+                    soft = torch.softmax(torch.stack(scal), 0)
+                    for m, k in enumerate(members):
+                        coef[b, i, k] = soft[m]
+        out = ops.warp_weighted(x.act, trans, num_agent, coef, batch, agents, per_pixel=False, only_v2i=only_v2i)
+        y = Var(out)
+
+        def bwd():
+            if y.grad is None:
+                return
+            dx = torch.empty((n, h, w, c), dtype=torch.float32, device=self.dev)
+            check(lib.v2x_warp_reduce_bwd(_ptr(y.grad), _ptr(x.act), _ptr(dx), _ptr(coef), _ptr(trans), _ptr(num_agent), batch,
+                                          agents, h, w, c, p_, 3, int(only_v2i), _stream()), "v2x_warp_reduce_bwd(coef)")
+            x.add_grad(lib, ops.pack_input(dx, c, p_))
             y.grad = None
         self.back.append(bwd)
         return y
@@ -583,7 +645,9 @@ class FusionTrainStep(torch.autograd.Function):
         nat = nat.to(device=dev, dtype=torch.int64).contiguous()
         x_in = Var(ops.pack_input(bevs.reshape(n, 256, 256, -1).to(torch.float32).contiguous(), 16, PLANES), c_log=int(bevs.shape[-1]))
         x0, x1, x2, x3, x4 = backbone_encode(tape, "u_encoder.", x_in)
-        if kind == "cat":     # CatFusion.py:23-27: mean of the member stack, then the modulation layer on cat[tg, mean]
+        if kind == "agent":
+            fused = tape.agent_weighted_fuse(x3, trans, nat, batch, agents, only_v2i=bool(module.only_v2i))
+        elif kind == "cat":     # CatFusion.py:23-27: mean of the member stack, then the modulation layer on cat[tg, mean]
             mean = tape.warp_reduce(x3, trans, nat, batch, agents, "mean", only_v2i=bool(module.only_v2i))
             fused = tape.cat_modulate(x3, mean, nat, batch, agents)
         else:
@@ -771,6 +835,8 @@ class SegTrainStep(torch.autograd.Function):
                     q = tape.cbr(cpre + "0", cpre + "1", [q], stride=stride)
                 coef, holder = handshake_island(tape, q, p, names, batch, agents)
                 feat = tape.gated_fuse(x4, coef, holder, trans, nat, batch, agents, warp_flag=int(fuse[6]), only_v2i=only_v2i)
+            elif kind == "agent":   # seg AgentWiseWeightedFusion: detached per-pair weights (see Tape.agent_weighted_fuse)
+                feat = tape.agent_weighted_fuse(x4, trans, nat, batch, agents, only_v2i=only_v2i)
             elif kind == "cat":   # seg CatFusion (seg/CatFusion.py:8-34): mean, then the per-agent modulation layer
                 mean = tape.warp_reduce(x4, trans, nat, batch, agents, "mean", only_v2i=only_v2i)
                 feat = tape.cat_modulate(x4, mean, nat, batch, agents, conv="modulation_layer_3.conv1_1",
