@@ -378,6 +378,13 @@ int v2x_warp_reduce_bwd(const void* dout, const void* x, float* dx, const float*
                         const int64_t* num_agent, int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c,
                         int32_t planes, int32_t mode, int32_t only_v2i, void* stream);
 
+/* backward of v2x_warp_weighted_fwd with coef_mode 1 (DiscoNet's per-pixel softmax of pair scores): dscores fp32
+ * [B][A][A][h*w] (zeroed here) = w_k (g_k - sum_m w_m g_m) with g_k = <dout, member_k> over channels, and dx fp32
+ * [A*B][h][w][c] (zeroed here) += w_k * dout scattered through member k's taps; x is the forward input */
+int v2x_warp_weighted_bwd(const void* dout, const void* x, float* dx, float* dscores, const float* scores, const double* trans,
+                          const int64_t* num_agent, int32_t batch, int32_t agents, int32_t h, int32_t w, int32_t c,
+                          int32_t planes, int32_t only_v2i, void* stream);
+
 /* backward of v2x_warp_gated_fwd (when2com fuse): dcoef fp32 [B][A][A] (zeroed here) = <dout[b,q], val[b,k,q]> and dx fp32
  * [A*B][h][w][c] (zeroed here) += coef[b,k,q] * dout[b,q] scattered through val[b,k,q]'s taps; x is the forward input */
 int v2x_warp_gated_bwd(const void* dout, const void* x, float* dx, float* dcoef, const float* coef, const double* trans,

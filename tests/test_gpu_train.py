@@ -21,14 +21,14 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
 
 
-PER_CALL_NETS = ("agent_weighted_fusion.",)
+PER_CALL_NETS = ("agent_weighted_fusion.", "pixel_weighted_fusion.")
 
 
 def _check_buffers(tag, after, want_sd, parity_log, golden=None, rtol=1e-5):
     """BatchNorm running buffers after one step vs the float64 oracle (and the live reference's, when the fixture holds
     them): |got - want| <= 1e-5 + rtol * |want| (deep seg layers carry variances of O(10)).  The worst measured error, in
     units of that bound, goes on record."""
-    # BatchNorm layers of the AgentWise weight net see ONE map per call (1024 pixels of unit-variance features) and ~20
+    # BatchNorm layers of the AgentWise / DiscoNet weight nets see ONE map per call (1024 pixels of unit-variance features) and ~20
     # sequential momentum updates per step: their batch statistics carry the 1e-4 error of the conv in front of them without
     # the averaging over maps the backbone layers enjoy (measured 2e-4 absolute); they are held to 1e-3 absolute
     worst, worst_key, worst_abs = 0.0, None, 0.0
@@ -79,7 +79,11 @@ def _check_grads(tag, got, want, golden, parity_log, zero_tol=1e-9, min_params=5
             worst_cos_key = k
         worst = dict(cos=min(worst["cos"], cos), norm=max(worst["norm"], abs(ratio - 1.0)), l2=max(worst["l2"], l2))
         nt = norm_tol(k) if norm_tol is not None else 2e-2
-        assert cos >= 0.999 and abs(ratio - 1.0) <= nt and l2 <= 5e-2, (k, cos, ratio, l2)
+        # the tail of DiscoNet's weight net sits behind BatchNorm layers that normalise ONE map per call, which amplifies the
+        # 1e-4 error of the conv in front of them (measured worst cosine 0.99913, rel-L2 4.2e-2 on conv1_3.weight,
+        # deterministic): 0.998 / 7e-2 there, 0.999 / 5e-2 everywhere else
+        cmin, l2max = (0.998, 7e-2) if k.startswith("pixel_weighted_fusion.") else (0.999, 5e-2)
+        assert cos >= cmin and abs(ratio - 1.0) <= nt and l2 <= l2max, (k, cos, ratio, l2)
         key = "grad." + k + ".norm"
         if golden is not None and key in golden.files:     # the live reference's own gradient norm
             assert abs(g.norm().item() / float(golden[key]) - 1.0) <= nt, (k, g.norm().item(), float(golden[key]))
@@ -300,7 +304,7 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     _check_buffers("train_step_%s_seed%d" % (kind, seed), dict(model.named_buffers()), sd_after, parity_log, rtol=2e-5)
 
 
-@pytest.mark.parametrize("kind", ["mean", "sum", "max", "cat", "agent"])
+@pytest.mark.parametrize("kind", ["mean", "sum", "max", "cat", "agent", "disco"])
 def test_fusion_train_step_matches_oracle(kind, golden_dir, parity_log):
     """MeanFusion / SumFusion / MaxFusion / CatFusion in .train() (FusionBase.py:23-75 under FaFModule.step): encoder -> fuse
     of the warped member maps at layer 3 (one absent agent slot keeps its own map) -> decoder -> heads; the fuse backward is
@@ -312,7 +316,7 @@ def test_fusion_train_step_matches_oracle(kind, golden_dir, parity_log):
     from oracle import restate
     from oracle.gen_golden import make_upstream, train_case
     from v2x_b200 import default_det_config
-    seed = {"mean": 32, "sum": 33, "max": 34, "cat": 27, "agent": 28}[kind]
+    seed = {"mean": 32, "sum": 33, "max": 34, "cat": 27, "agent": 28, "disco": 24}[kind]
     tag = "train_step_%s_seed%d" % (kind, seed)
     golden = np.load(os.path.join(golden_dir, tag + ".npz"))
     sd, inputs, keys = train_case(kind, seed)
@@ -323,11 +327,13 @@ def test_fusion_train_step_matches_oracle(kind, golden_dir, parity_log):
     out_ref, grads_ref, sd_after = restate.train_step_vjp(
         lambda s: restate.fusion_det_forward(kind, bevs.double(), trans, nat, s, batch_size=1, agent_num=5), sd64, up)
     cls_ = {"mean": det_models.MeanFusion, "sum": det_models.SumFusion, "max": det_models.MaxFusion,
-            "cat": det_models.CatFusion, "agent": det_models.AgentWiseWeightedFusion}[kind]
+            "cat": det_models.CatFusion, "agent": det_models.AgentWiseWeightedFusion, "disco": det_models.DiscoNet}[kind]
     model = cls_(default_det_config(), layer=3, kd_flag=0, num_agent=5)
     model.load_state_dict(sd, strict=True)
     model = model.cuda().train()
     out = model(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    if kind == "disco":       # DiscoNet.py:125-129 with kd_flag = 0: (result, save_agent_weight_list)
+        out = out[0]
     for k in ("loc", "cls"):
         e = _rel(out[k], out_ref[k])
         print(kind, "fusion train forward", k, "rel_err %.3e" % e)
@@ -339,6 +345,56 @@ def test_fusion_train_step_matches_oracle(kind, golden_dir, parity_log):
         assert (g is not None) == (k in grads_ref), k
     _check_grads(tag, got, grads_ref, golden, parity_log)
     _check_buffers(tag, dict(model.named_buffers()), sd_after, parity_log, golden=golden)
+
+
+@pytest.mark.parametrize("only_v2i", [0, 1])
+def test_warp_weighted_bwd_matches_autograd(only_v2i):
+    """v2x_warp_weighted_bwd (DiscoNet's per-pixel softmax fuse) against torch autograd through the reference formulation
+    (flipped domain, DiscoNet.py:80-107): gradient w.r.t. the maps and w.r.t. the pair scores."""
+    import ctypes as C
+    from oracle import restate, synth
+    from v2x_b200 import ops
+    from v2x_b200._lib import check
+    lib = ops.require_gpu()
+    B, A, Cc, H = 2, 5, 16, 32
+    present = [5, 3]
+    g = torch.Generator().manual_seed(17)
+    trans = synth.make_trans_matrices(B, A, 17, present=present)
+    nat = torch.tensor([[p] * A for p in present], dtype=torch.long)
+    x = torch.randn((A * B, Cc, H, H), generator=g, dtype=torch.float64).requires_grad_(True)   # un-flipped, agent-major
+    scores = torch.randn((B, A, A, H, H), generator=g, dtype=torch.float64).requires_grad_(True)  # un-flipped score maps
+    dout = torch.randn((A * B, Cc, H, H), generator=g, dtype=torch.float64)
+    feat = torch.flip(x, (2,))
+    local = torch.stack([feat[B * i: B * (i + 1)] for i in range(A)], 1)
+    sflip = torch.flip(scores, (3,))
+    outs = [None] * (A * B)
+    for b in range(B):
+        for i in range(A):
+            if i >= present[b]:
+                outs[B * i + b] = local[b, i]
+                continue
+            ks = [i] + [k for k in range(present[b]) if k != i and not (only_v2i and i != 0 and k != 0)]
+            nb = [local[b, i] if k == i else restate.feature_transformation(local, b, k, i, trans, (1, Cc, H, H)) for k in ks]
+            e = [torch.exp(sflip[b, i, k]) for k in ks]
+            tot = sum(e)
+            outs[B * i + b] = sum((e[m] / tot) * nb[m] for m in range(len(ks)))
+    out = torch.flip(torch.stack(outs), (2,))
+    out.backward(dout)
+    to_act = lambda t: ops.pack_input(t.float().permute(0, 2, 3, 1).contiguous().cuda(), Cc, 2)   # noqa: E731
+    d_act, x_act, t_dev, n_dev = to_act(dout), to_act(x.detach()), trans.cuda(), nat.cuda()
+    s_dev = scores.detach().float().reshape(B, A, A, H * H).cuda().contiguous()
+    dx = torch.empty((A * B, H, H, Cc), dtype=torch.float32, device="cuda")
+    ds = torch.empty((B, A, A, H * H), dtype=torch.float32, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+    check(lib.v2x_warp_weighted_bwd(P(d_act), P(x_act), P(dx), P(ds), P(s_dev), P(t_dev), P(n_dev), B, A, H, H, Cc, 2, only_v2i,
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "v2x_warp_weighted_bwd")
+    torch.cuda.synchronize()
+    want = x.grad.permute(0, 2, 3, 1)
+    e_x = ((dx.cpu().double() - want).abs().max() / want.abs().max()).item()
+    want_s = scores.grad.reshape(B, A, A, H * H)
+    e_s = ((ds.cpu().double() - want_s).abs().max() / want_s.abs().max()).item()
+    print("warp_weighted_bwd only_v2i=%d: dx rel_err %.3e, dscores rel_err %.3e" % (only_v2i, e_x, e_s))
+    assert e_x < 1e-4 and e_s < 1e-4
 
 
 @pytest.mark.parametrize("mode", ["mean", "sum", "max"])

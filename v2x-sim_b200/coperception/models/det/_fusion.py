@@ -43,7 +43,7 @@ class FusionBase(B200DetModel):
         if self.KIND is None:
             raise NotImplementedError("Please implement this method for specific fusion strategies")
         dev = bevs.device
-        if self.training and self.KIND in ("mean", "sum", "max", "cat", "agent"):
+        if self.training and self.KIND in ("mean", "sum", "max", "cat", "agent", "disco"):
             # train-mode forward with a backward pass behind torch.autograd (v2x_b200/train.py::FusionTrainStep): the
             # parameter-free fuse rules and CatFusion; AgentWise / DiscoNet (weight nets called per pair, KD) refuse below
             if dev.type != "cuda":

@@ -655,6 +655,120 @@ __global__ void __launch_bounds__(256) warp_gated_bwd_kernel(const __nv_bfloat16
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward of DiscoNet's per-pixel weighted fuse (v2x_warp_weighted_fwd, coef_mode 1; DiscoNet.py:80-107 under
+// loss.backward()): with members k of target i (self + participating present agents), w_k[p] = softmax_k(s[b,i,k,p]) and
+// out[b,i,p] = sum_k w_k[p] * member_k[p]:
+//   g_k[p]        = < dout[b,i,p,:], member_k[p,:] >            (dot over channels)
+//   ds[b,i,k,p]   = w_k[p] * (g_k[p] - sum_m w_m[p] g_m[p])     (softmax backward, per pixel)
+//   dx           += w_k[p] * (grid_sample backward of dout[b,i,p] through member k's taps)
+// One warp per (target unit, pixel), lanes over channels.  dx fp32 [A*B][H][W][C] and dscores fp32 [B][A][A][HW] are zeroed
+// by the launcher; dscores carries the gradient scale of dout.  Absent agent slots pass their gradient through.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_weighted_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                                const __nv_bfloat16* __restrict__ x, float* __restrict__ dx,
+                                                                float* __restrict__ dscores, const float* __restrict__ scores,
+                                                                const double* __restrict__ trans,
+                                                                const long long* __restrict__ num_agent, int batch, int agents,
+                                                                int H, int W, int C, int planes, int only_v2i) {
+  constexpr int kMaxA = 8;
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int HW = H * W;
+  const long long total_pix = (long long)batch * agents * HW;
+  const long long plane = total_pix * C;
+  for (long long wid = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total_pix;
+       wid += (long long)gridDim.x * warps_per_block) {
+    const int p = (int)(wid % HW);
+    const int ow = p % W, oh = p / W;
+    const int map = (int)(wid / HW);
+    const int i = map / batch, b = map % batch;
+    const int na = min((int)num_agent[(long long)b * agents], agents);
+    if (i >= na) {   // pass-through
+      for (int c0 = lane * 8; c0 < C; c0 += 256) {
+        float d[8];
+        act_load8(dout + wid * C + c0, plane, planes, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(dx + wid * C + c0 + e, d[e]);
+      }
+      continue;
+    }
+    const float* sb = scores + ((long long)b * agents + i) * agents * HW;
+    float wk[kMaxA], g[kMaxA];
+    unsigned use = 0;
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxA; ++k) {
+      wk[k] = 0.f; g[k] = 0.f;
+      if (k >= na) continue;
+      if (k != i && only_v2i && i != 0 && k != 0) continue;
+      use |= 1u << k;
+      m = fmaxf(m, sb[(long long)k * HW + p]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxA; ++k)
+      if ((use >> k) & 1u) { wk[k] = __expf(sb[(long long)k * HW + p] - m); sum += wk[k]; }
+    const float inv = 1.f / sum;
+    const float gx = (2.f * ow + 1.f) / W - 1.f, gy = (2.f * oh + 1.f) / H - 1.f;
+#pragma unroll
+    for (int k = 0; k < kMaxA; ++k) {
+      if (!((use >> k) & 1u)) continue;
+      wk[k] *= inv;
+      float wts[4];
+      int xs[4], ys[4];
+      int ntap = 4;
+      if (k == i) {
+        ntap = 1; wts[0] = 1.f; xs[0] = ow; ys[0] = oh;
+      } else {
+        const double* T = trans + ((((long long)b * agents + k) * agents + i) << 4);
+        const float t00 = (float)T[0], t01 = -(float)T[1], t02 = -(float)T[3] * (1.f / 32.f);
+        const float t10 = -(float)T[4], t11 = (float)T[5], t12 = (float)T[7] * (1.f / 32.f);
+        const float sx = t00 * gx + t01 * gy + t02, sy = t10 * gx + t11 * gy + t12;
+        const float ix = ((sx + 1.f) * W - 1.f) * 0.5f, iy = ((sy + 1.f) * H - 1.f) * 0.5f;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          xs[t] = x0 + (t & 1); ys[t] = y0 + (t >> 1);
+          wts[t] = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
+        }
+      }
+      const long long src_map = (long long)batch * k + b;
+      float dot = 0.f;
+      for (int c0 = lane * 8; c0 < C; c0 += 256) {
+        float d[8];
+        act_load8(dout + wid * C + c0, plane, planes, d);
+        for (int t = 0; t < ntap; ++t) {
+          if (xs[t] < 0 || xs[t] >= W || ys[t] < 0 || ys[t] >= H) continue;
+          const long long off = ((src_map * H + ys[t]) * W + xs[t]) * C + c0;
+          float f[8];
+          act_load8(x + off, plane, planes, f);
+          const float wc = wts[t] * wk[k];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            dot = fmaf(wts[t] * f[e], d[e], dot);
+            atomicAdd(dx + off + e, wc * d[e]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      g[k] = dot;
+    }
+    float G = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxA; ++k) G += wk[k] * g[k];
+    if (lane == 0) {
+      float* db = dscores + ((long long)b * agents + i) * agents * HW;
+#pragma unroll
+      for (int k = 0; k < kMaxA; ++k)
+        if ((use >> k) & 1u) db[(long long)k * HW + p] = wk[k] * (g[k] - G);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Segmentation UNet pieces, backward (CP/models/seg/SegModelBase.py:113,125 under loss.backward()).
 // ---------------------------------------------------------------------------------------------
 // nn.MaxPool2d(2) backward: the gradient of an output pixel goes to the FIRST maximum of its 2x2 window in scan order
@@ -936,6 +1050,23 @@ extern "C" int v2x_warp_gated_bwd(const void* dout, const void* x, float* dx, fl
   warp_gated_bwd_kernel<<<grid_cap(total_pix * 32, 256, 8), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(x), dx, dcoef, coef, trans,
       reinterpret_cast<const long long*>(num_agent), batch, agents, h, w, c, planes, warp_flag, only_v2i);
+  V2X_CUDA_TRY(cudaGetLastError());
+  return V2X_OK;
+}
+
+extern "C" int v2x_warp_weighted_bwd(const void* dout, const void* x, float* dx, float* dscores, const float* scores,
+                                     const double* trans, const int64_t* num_agent, int32_t batch, int32_t agents, int32_t h,
+                                     int32_t w, int32_t c, int32_t planes, int32_t only_v2i, void* stream) {
+  V2X_REQUIRE(dout && x && dx && dscores && scores && trans && num_agent, "null pointer");
+  V2X_REQUIRE(batch > 0 && agents > 0 && agents <= 8 && h > 0 && w > 0, "empty geometry (agents <= 8)");
+  V2X_CHECK_ACT(c, planes);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total_pix = (long long)batch * agents * h * w;
+  V2X_CUDA_TRY(cudaMemsetAsync(dx, 0, sizeof(float) * total_pix * c, s));
+  V2X_CUDA_TRY(cudaMemsetAsync(dscores, 0, sizeof(float) * total_pix * agents, s));
+  warp_weighted_bwd_kernel<<<grid_cap(total_pix * 32, 256, 8), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(x), dx, dscores, scores, trans,
+      reinterpret_cast<const long long*>(num_agent), batch, agents, h, w, c, planes, only_v2i);
   V2X_CUDA_TRY(cudaGetLastError());
   return V2X_OK;
 }

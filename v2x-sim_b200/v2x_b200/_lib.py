@@ -99,6 +99,7 @@ SYMBOLS = [
     ("v2x_gru_gates_bwd", C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _I32, _P, _P]),
     ("v2x_warp_mean_bwd", C.c_int, [_P, _P, _P, _P] + [_I32] * 8 + [_P]),
     ("v2x_warp_reduce_bwd", C.c_int, [_P, _P, _P, _P, _P, _P] + [_I32] * 8 + [_P]),
+    ("v2x_warp_weighted_bwd", C.c_int, [_P, _P, _P, _P, _P, _P, _P] + [_I32] * 7 + [_P]),
     ("v2x_warp_gated_bwd", C.c_int, [_P, _P, _P, _P, _P, _P, _P] + [_I32] * 8 + [_P]),
     ("v2x_maxpool2_bwd", C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     ("v2x_upsample_bilinear2_bwd", C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),

@@ -351,6 +351,118 @@ class Tape:
         self.back.append(bwd)
         return y
 
+    def warp_member(self, x: Var, k: int, trans, num_agent, batch, agents, only_v2i=False) -> Var:
+        """Agent k's map warped into every target's frame (identity where k is the target itself): one member slot of the
+        neighbour lists FusionBase builds (DetModelBase.py:171-209), as one launch over all targets, with its backward."""
+        lib = self.lib
+        onehot = torch.zeros((batch, agents, agents), dtype=torch.float32, device=self.dev)
+        onehot[:, :, k] = 1.0
+        y = Var(ops.warp_weighted(x.act, trans, num_agent, onehot, batch, agents, per_pixel=False, only_v2i=only_v2i))
+        p_, n, h, w, c = x.act.shape
+
+        def bwd():
+            if y.grad is None:
+                return
+            dx = torch.empty((n, h, w, c), dtype=torch.float32, device=self.dev)
+            check(lib.v2x_warp_reduce_bwd(_ptr(y.grad), _ptr(x.act), _ptr(dx), _ptr(onehot), _ptr(trans), _ptr(num_agent), batch,
+                                          agents, h, w, c, p_, 3, int(only_v2i), _stream()), "v2x_warp_reduce_bwd(member)")
+            x.add_grad(lib, ops.pack_input(dx, c, p_))
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
+    def conv_plain(self, conv: str, srcs: List[Var]) -> Var:
+        """1x1 / 3x3 conv + bias without BatchNorm or ReLU (the consumer normalises per call), with its backward.  Its bias
+        sits in front of a train-mode BatchNorm: exactly zero gradient."""
+        z, w4, cins = self._conv_raw(conv + ".weight", conv + ".bias", srcs, 1)
+        y = Var(z)
+
+        def bwd():
+            if y.grad is None:
+                return
+            self._param_grad(conv + ".bias")
+            self._conv_backward(conv + ".weight", w4, srcs, cins, 1, y.grad, [True] * len(srcs))
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
+    def disco_fuse(self, x: Var, trans, num_agent, batch, agents, only_v2i=False, prefix="pixel_weighted_fusion.") -> Var:
+        """DiscoNet's pixel-wise weighted fuse in train mode (DiscoNet.py:80-107, 132-155; kd_flag = 0): for every present
+        target i and list member k the weight net maps cat[tg_i, warp_{k->i}(x_k)] to a per-pixel score; the members are mixed
+        with the per-pixel softmax of the scores, and -- unlike AgentWise -- the weight net IS trained through it.
+        On the tape: the member warps (warp_member), the weight net's first layer as one 1x1-conv launch per member slot
+        (2C -> 128 on every pixel of every pair: 94% of its FLOPs; filter gradient on tcgen05) and the fuse
+        (v2x_warp_weighted_fwd / v2x_warp_weighted_bwd: map gradient + softmax backward per pixel).  Between them the per-call
+        tail of the weight net -- BatchNorm with per-call statistics (one map per call, running buffers updated call by call
+        in the reference's order), 128 -> 32 -> 8 -> 1 per pixel: 9 MFLOP per call -- is a torch-autograd island in fp32."""
+        import torch.nn.functional as F
+        lib = self.lib
+        p_, n, h, w, c = x.act.shape
+        hw = h * w
+        na = [min(int(v), agents) for v in num_agent[:, 0].tolist()]
+        zs = []
+        for k in range(agents):
+            wk = self.warp_member(x, k, trans, num_agent, batch, agents, only_v2i=only_v2i)
+            zs.append(self.conv_plain(prefix + "conv1_1", [x, wk]))
+        tail_names = [prefix + t for t in ("bn1_1.weight", "bn1_1.bias", "conv1_2.weight", "conv1_2.bias", "bn1_2.weight",
+                                           "bn1_2.bias", "conv1_3.weight", "conv1_3.bias", "bn1_3.weight", "bn1_3.bias",
+                                           "conv1_4.weight", "conv1_4.bias")]
+        calls = []                                   # (b, i, k, score map [hw]) in the reference's call order
+        with torch.enable_grad():
+            z1 = [ops.act_to_float(z.act).detach().requires_grad_(True) for z in zs]      # [units, 128, h, w] fp32 each
+            tp = {k: self.p[k].detach().to(torch.float32).requires_grad_(True) for k in tail_names}
+            for b in range(batch):
+                for i in range(na[b]):
+                    members = [i] + [k for k in range(na[b]) if k != i and not (only_v2i and i != 0 and k != 0)]
+                    for k in members:
+                        t = z1[k][batch * i + b: batch * i + b + 1]
+                        for li, cname in ((1, None), (2, "conv1_2"), (3, "conv1_3")):
+                            if cname is not None:
+                                t = F.conv2d(t, tp[prefix + cname + ".weight"], tp[prefix + cname + ".bias"])
+                            bn = prefix + "bn1_%d" % li
+                            t = F.relu(F.batch_norm(t, self.b[bn + ".running_mean"], self.b[bn + ".running_var"], tp[bn + ".weight"],
+                                                    tp[bn + ".bias"], True, BN_MOMENTUM, BN_EPS))
+                            nbt = self.b.get(bn + ".num_batches_tracked")
+                            if nbt is not None:
+                                nbt += 1
+                        t = F.relu(F.conv2d(t, tp[prefix + "conv1_4.weight"], tp[prefix + "conv1_4.bias"]))
+                        calls.append((b, i, k, t.reshape(hw)))
+        scores = torch.zeros((batch, agents, agents, hw), dtype=torch.float32, device=self.dev)
+        for b, i, k, sm in calls:
+            scores[b, i, k] = sm.detach()
+        holder: Dict[str, torch.Tensor] = {}
+
+        def island_bwd():
+            ds = holder.get("dscores")
+            if ds is None or not calls:
+                return
+            leaves = z1 + [tp[k] for k in tail_names]
+            grads = torch.autograd.grad([sm for _, _, _, sm in calls], leaves, grad_outputs=[ds[b, i, k] for b, i, k, _ in calls],
+                                        allow_unused=True)
+            for z, gz in zip(zs, grads[:len(z1)]):
+                if gz is not None:
+                    z.add_grad(lib, ops.pack_input_nchw((gz * self.scale).contiguous(), int(gz.shape[1]), PLANES))
+            for k, gk in zip(tail_names, grads[len(z1):]):
+                if gk is not None:
+                    self._param_grad(k).add_(gk)
+        self.back.append(island_bwd)
+        out = ops.warp_weighted(x.act, trans, num_agent, scores, batch, agents, per_pixel=True, only_v2i=only_v2i)
+        y = Var(out)
+
+        def bwd():
+            if y.grad is None:
+                return
+            dx = torch.empty((n, h, w, c), dtype=torch.float32, device=self.dev)
+            dscores = torch.empty((batch, agents, agents, hw), dtype=torch.float32, device=self.dev)
+            check(lib.v2x_warp_weighted_bwd(_ptr(y.grad), _ptr(x.act), _ptr(dx), _ptr(dscores), _ptr(scores), _ptr(trans),
+                                            _ptr(num_agent), batch, agents, h, w, c, p_, int(only_v2i), _stream()),
+                  "v2x_warp_weighted_bwd")
+            holder["dscores"] = dscores * (1.0 / self.scale)
+            x.add_grad(lib, ops.pack_input(dx, c, p_))
+            y.grad = None
+        self.back.append(bwd)
+        return y
+
     def agent_weighted_fuse(self, x: Var, trans, num_agent, batch, agents, only_v2i=False,
                             prefix="agent_weighted_fusion.") -> Var:
         """AgentWiseWeightedFusion in train mode (AgentWiseWeightedFusion.py:24-43, 44-76; seg twin): for every present target
@@ -645,7 +757,9 @@ class FusionTrainStep(torch.autograd.Function):
         nat = nat.to(device=dev, dtype=torch.int64).contiguous()
         x_in = Var(ops.pack_input(bevs.reshape(n, 256, 256, -1).to(torch.float32).contiguous(), 16, PLANES), c_log=int(bevs.shape[-1]))
         x0, x1, x2, x3, x4 = backbone_encode(tape, "u_encoder.", x_in)
-        if kind == "agent":
+        if kind == "disco":
+            fused = tape.disco_fuse(x3, trans, nat, batch, agents, only_v2i=bool(module.only_v2i))
+        elif kind == "agent":
             fused = tape.agent_weighted_fuse(x3, trans, nat, batch, agents, only_v2i=bool(module.only_v2i))
         elif kind == "cat":     # CatFusion.py:23-27: mean of the member stack, then the modulation layer on cat[tg, mean]
             mean = tape.warp_reduce(x3, trans, nat, batch, agents, "mean", only_v2i=bool(module.only_v2i))
@@ -835,6 +949,8 @@ class SegTrainStep(torch.autograd.Function):
                     q = tape.cbr(cpre + "0", cpre + "1", [q], stride=stride)
                 coef, holder = handshake_island(tape, q, p, names, batch, agents)
                 feat = tape.gated_fuse(x4, coef, holder, trans, nat, batch, agents, warp_flag=int(fuse[6]), only_v2i=only_v2i)
+            elif kind == "disco":   # seg DiscoNet (kd_flag False): trained per-pixel weights (see Tape.disco_fuse)
+                feat = tape.disco_fuse(x4, trans, nat, batch, agents, only_v2i=only_v2i)
             elif kind == "agent":   # seg AgentWiseWeightedFusion: detached per-pair weights (see Tape.agent_weighted_fuse)
                 feat = tape.agent_weighted_fuse(x4, trans, nat, batch, agents, only_v2i=only_v2i)
             elif kind == "cat":   # seg CatFusion (seg/CatFusion.py:8-34): mean, then the per-agent modulation layer
