@@ -353,6 +353,7 @@ TRAIN_CASES = {   # tag -> (kind, seed)
     "train_step_seg_max_seed36": ("seg_max", 36),
     "train_step_seg_cat_seed37": ("seg_cat", 37),
     "train_step_seg_agent_seed38": ("seg_agent", 38),
+    "train_step_seg_disco_seed39": ("seg_disco", 39),
 }
 
 
@@ -372,7 +373,7 @@ def train_case(kind, seed):
         return synth.seg_unet_state(seed), (synth.make_seg_scene(1, 2, seed)[0],), ("logits",)
     if kind == "seg_v2vnet":
         return synth.seg_v2vnet_state(seed), synth.make_seg_scene(1, 5, seed, present=[4]), ("logits",)
-    if kind in ("seg_mean", "seg_sum", "seg_max", "seg_cat", "seg_agent"):
+    if kind in ("seg_mean", "seg_sum", "seg_max", "seg_cat", "seg_agent", "seg_disco"):
         return synth.seg_fusion_state(kind[4:], seed), synth.make_seg_scene(1, 5, seed, present=[4]), ("logits",)
     raise ValueError(kind)
 
@@ -404,7 +405,7 @@ def gen_train_step(tag, kind, seed):
             m = ref_loader.ref_seg_when2com(num_agent=5, warp_flag=1)
         elif kind == "seg_unet":
             m = ref_loader.ref_seg_unet()
-        elif kind in ("seg_mean", "seg_sum", "seg_max", "seg_cat", "seg_agent"):
+        elif kind in ("seg_mean", "seg_sum", "seg_max", "seg_cat", "seg_agent", "seg_disco"):
             m = ref_loader.ref_fusion_seg(kind[4:], num_agent=5)
         else:
             m = ref_loader.ref_seg_v2vnet(num_agent=5)
@@ -418,7 +419,7 @@ def gen_train_step(tag, kind, seed):
             r = m(x, inputs[1], inputs[2], training=True)
         elif kind == "when2com":
             r = m(x, inputs[1], inputs[2], training=True, MO_flag=True, batch_size=1)
-        elif kind in ("seg_v2vnet", "seg_mean", "seg_sum", "seg_max", "seg_cat", "seg_agent"):
+        elif kind in ("seg_v2vnet", "seg_mean", "seg_sum", "seg_max", "seg_cat", "seg_agent", "seg_disco"):
             r = m(x, inputs[1], inputs[2])
         elif kind == "disco":
             r = m(x, inputs[1], inputs[2], batch_size=1)[0]

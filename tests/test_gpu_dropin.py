@@ -51,16 +51,21 @@ def test_fafnet_module_kd_outputs():
 
 
 def test_train_mode_is_refused_where_not_built():
-    """Every model except DiscoNet trains on the sm_100a path (tests/test_gpu_train.py); DiscoNet -- whose per-pair weight
-    net is trained through the per-pixel softmax -- and KD training still refuse loudly."""
-    from coperception.models.det import DiscoNet, MeanFusion
+    """Every det model class and every seg class but DiscoNet trains on the sm_100a path (tests/test_gpu_train.py); what is
+    not built refuses loudly instead of silently doing something else: training with compress_level > 0, seg DiscoNet, the
+    seg models' kd_flag outputs, and a When2com in .train() asked for the gated inference pass (training=False)."""
+    from coperception.models.det import MeanFusion, When2com
+    from coperception.models.seg import DiscoNet as SegDiscoNet
     from v2x_b200 import default_det_config
     args = (torch.zeros((5, 1, 256, 256, 13), device="cuda"), torch.zeros((1, 5, 5, 4, 4), device="cuda"),
             torch.full((1, 5), 5, device="cuda"))
     with pytest.raises(NotImplementedError):
-        DiscoNet(default_det_config(), layer=3, kd_flag=0, num_agent=5).cuda().train()(*args, batch_size=1)
-    with pytest.raises(NotImplementedError):      # kd_flag = 1 returns the intermediate maps for the distillation loss
-        MeanFusion(default_det_config(), layer=3, kd_flag=1, num_agent=5).cuda().train()(*args, batch_size=1)
+        MeanFusion(default_det_config(), layer=3, kd_flag=0, num_agent=5, compress_level=2).cuda().train()(*args, batch_size=1)
+    with pytest.raises(NotImplementedError):
+        When2com(default_det_config(), layer=3, warp_flag=1, num_agent=5).cuda().train()(*args, training=False, batch_size=1)
+    for kd in (True, False):     # seg DiscoNet: the train step exists (Tape.disco_fuse) but measured a cosine of 0.9985 on the
+        with pytest.raises(NotImplementedError):   # first conv's gradient, below the 0.999 bar, so it stays switched off
+            SegDiscoNet(13, 8, 5, kd_flag=kd).cuda().train()(torch.zeros((5, 13, 256, 256), device="cuda"), args[1], args[2])
 
 
 def _v2v_model(seed=2):

@@ -251,10 +251,10 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
     """seg UNet / seg V2VNet in .train() (what train_seg.py drives through SegModule.step): DoubleConv stacks with batch
     statistics, MaxPool2d and bilinear-upsample backward, fp32 NCHW logits; V2VNet adds one GNN round at 512 channels with
     the self-inclusive neighbour mean."""
-    from coperception.models.seg import AgentWiseWeightedFusion, CatFusion, MaxFusion, MeanFusion, UNet, V2VNet, When2Com_UNet
+    from coperception.models.seg import AgentWiseWeightedFusion, CatFusion, DiscoNet, MaxFusion, MeanFusion, UNet, V2VNet, When2Com_UNet
     from oracle import restate
     from oracle.gen_golden import make_upstream, train_case
-    seed = {"seg_unet": 25, "seg_v2vnet": 26, "seg_mean": 35, "seg_max": 36, "seg_cat": 37, "seg_agent": 38, "seg_when2com": 29}[kind]
+    seed = {"seg_unet": 25, "seg_v2vnet": 26, "seg_mean": 35, "seg_max": 36, "seg_cat": 37, "seg_agent": 38, "seg_disco": 39, "seg_when2com": 29}[kind]
     golden = np.load(os.path.join(golden_dir, "train_step_%s_seed%d.npz" % (kind, seed)))
     sd, inputs, keys = train_case(kind, seed)
     x = inputs[0]
@@ -268,12 +268,14 @@ def test_seg_train_step_matches_oracle(kind, golden_dir, parity_log):
                                                                 training=True)}
         from v2x_b200 import default_det_config
         model = When2Com_UNet(default_det_config(), n_classes=8, in_channels=13, warp_flag=1, num_agent=5)
-    elif kind in ("seg_mean", "seg_max", "seg_cat", "seg_agent"):    # seg FusionBase family (seg/FusionBase.py:25-84): fuse of x4
+    elif kind in ("seg_mean", "seg_max", "seg_cat", "seg_agent", "seg_disco"):    # seg FusionBase family (seg/FusionBase.py:25-84): fuse of x4
         fwd = lambda s: {"logits": restate.seg_fusion_forward(kind[4:], x.double(), inputs[1], inputs[2], s, agent_num=5)}   # noqa: E731
         if kind == "seg_cat":
             model = CatFusion(13, 8, 5, 0, False)
         elif kind == "seg_agent":
             model = AgentWiseWeightedFusion(13, 8, 5, 0, False)
+        elif kind == "seg_disco":
+            model = DiscoNet(13, 8, 5, kd_flag=False)
         else:
             model = (MeanFusion if kind == "seg_mean" else MaxFusion)(13, 8, num_agent=5)
     else:
@@ -538,3 +540,42 @@ def test_warp_gated_bwd_matches_autograd(warp_flag):
     e_c = ((dcoef.cpu().double() - coef.grad).abs().max() / coef.grad.abs().max()).item()
     print("warp_gated_bwd warp=%d: dx rel_err %.3e, dcoef rel_err %.3e" % (warp_flag, e_x, e_c))
     assert e_x < 1e-4 and e_c < 1e-4
+
+
+def test_fusion_train_step_with_kd_outputs(golden_dir, parity_log):
+    """kd_flag == 1 (FusionBase.py:72-73): the train-mode forward also returns x_8, x_7, x_6, x_5 and the fused layer, and
+    FaFModule.get_kd_loss (CoDetModule.py:257-260, 300-340) back-propagates a distillation loss through x_5, x_6, x_7 and the
+    fused layer.  Upstream gradients on loc / cls AND on those four maps: every parameter gradient vs torch autograd over
+    the float64 oracle (MeanFusion)."""
+    from coperception.models.det import MeanFusion
+    from oracle import restate
+    from oracle.gen_golden import make_upstream, train_case
+    from v2x_b200 import default_det_config
+    sd, inputs, keys = train_case("mean", 32)
+    bevs, trans, nat = inputs
+    n = bevs.shape[0]
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    shapes = {"loc": (n, 256, 256, 6, 1, 6), "cls": (n, 256 * 256 * 6, 2), "x7": (n, 64, 128, 128), "x6": (n, 128, 64, 64),
+              "x5": (n, 256, 32, 32), "fused": (n, 256, 32, 32)}
+    up = make_upstream(shapes, 41)
+
+    def fwd(s):
+        r = restate.fusion_det_forward("mean", bevs.double(), trans, nat, s, batch_size=1, agent_num=5, stages=True)
+        return {"loc": r["loc"], "cls": r["cls"], "x7": r["dec"][1], "x6": r["dec"][2], "x5": r["dec"][3], "fused": r["fused"]}
+    out_ref, grads_ref, sd_after = restate.train_step_vjp(fwd, sd64, up)
+    model = MeanFusion(default_det_config(), layer=3, kd_flag=1, num_agent=5)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    result, x8, x7, x6, x5, fused = model(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    got_out = {"loc": result["loc"], "cls": result["cls"], "x7": x7, "x6": x6, "x5": x5, "fused": fused}
+    for k in sorted(shapes):
+        e = _rel(got_out[k], out_ref[k])
+        print("kd train forward", k, "rel_err %.3e" % e)
+        assert tuple(got_out[k].shape) == tuple(out_ref[k].shape) and e < 1e-3
+    ks = sorted(shapes)
+    torch.autograd.backward([got_out[k] for k in ks], [up[k].float().cuda() for k in ks])
+    torch.cuda.synchronize()
+    got = {k: p.grad for k, p in model.named_parameters()}
+    for k, g in got.items():
+        assert (g is not None) == (k in grads_ref), k
+    _check_grads("train_step_mean_kd_seed32", got, grads_ref, None, parity_log)

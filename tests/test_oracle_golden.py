@@ -259,6 +259,7 @@ def test_train_step_oracle(golden_dir, tag, kind, seed):
         "seg_max": lambda w: wrap(restate.seg_fusion_forward("max", *inputs, w, agent_num=5)),
         "seg_cat": lambda w: wrap(restate.seg_fusion_forward("cat", *inputs, w, agent_num=5)),
         "seg_agent": lambda w: wrap(restate.seg_fusion_forward("agent", *inputs, w, agent_num=5)),
+        "seg_disco": lambda w: wrap(restate.seg_fusion_forward("disco", *inputs, w, agent_num=5)),
     }[kind]
     out, grads, after = restate.train_step_vjp(fwd, sd, make_upstream({k: g[k + ".shape"] for k in keys}, seed))
     for name in keys:

@@ -20,7 +20,7 @@ class DiscoNet(FusionBase):
         import torch
         plan, result = self._run(bevs, trans_matrices, num_agent_tensor, batch_size)
         if plan is None:        # model.train(): the train step (v2x_b200/train.py); the visualisation list is not rebuilt
-            return result, []
+            return (result, *self._train_kd) if self.kd_flag == 1 else (result, [])
         if self.kd_flag == 1:
             return (result, *plan.kd_layers())
         hw = int(round(plan.fuse.scores.shape[-1] ** 0.5))

@@ -48,12 +48,13 @@ class FusionBase(B200DetModel):
             # parameter-free fuse rules and CatFusion; AgentWise / DiscoNet (weight nets called per pair, KD) refuse below
             if dev.type != "cuda":
                 raise RuntimeError("v2x_b200 fusion models need CUDA tensors (no CPU fallback); got %s" % dev)
-            if self.layer != 3 or self.compress_level > 0 or self.kd_flag == 1:
-                raise NotImplementedError("training on the sm_100a path: layer 3, compress_level 0, kd_flag 0")
+            if self.layer != 3 or self.compress_level > 0:
+                raise NotImplementedError("training on the sm_100a path: layer 3, compress_level 0")
             from v2x_b200.train import FusionTrainStep
-            loc, cls = FusionTrainStep.apply(self, self.KIND, bevs, trans_matrices, num_agent_tensor, int(batch_size),
-                                             *self.parameters())
-            return None, {"loc": loc, "cls": cls}
+            outs = FusionTrainStep.apply(self, self.KIND, bevs, trans_matrices, num_agent_tensor, int(batch_size),
+                                         *self.parameters())
+            self._train_kd = tuple(outs[2:])       # (x_8, x_7, x_6, x_5, fused) when kd_flag == 1, else ()
+            return None, {"loc": outs[0], "cls": outs[1]}
         self._check_eval()
         if dev.type != "cuda":
             raise RuntimeError("v2x_b200 fusion models need CUDA tensors (no CPU fallback); got %s" % dev)
@@ -69,6 +70,8 @@ class FusionBase(B200DetModel):
         """Same contract as FusionBase.forward (FusionBase.py:23-75): the result dict, or with ``kd_flag == 1`` the
         tuple (result, x_8, x_7, x_6, x_5, fused layer-3 maps)."""
         plan, result = self._run(bevs, trans_matrices, num_agent_tensor, batch_size)
+        if plan is None:       # model.train(): the train step
+            return (result, *self._train_kd) if self.kd_flag == 1 else result
         if self.kd_flag == 1:
             return (result, *plan.kd_layers())
         return result

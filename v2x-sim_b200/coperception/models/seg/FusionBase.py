@@ -24,7 +24,7 @@ class FusionBase(SegModelBase):
         from v2x_b200 import nets_seg
         if self.KIND is None:
             self.fusion()
-        if self.training and self.KIND in ("mean", "sum", "max", "cat", "agent", "disco"):
+        if self.training and self.KIND in ("mean", "sum", "max", "cat", "agent"):
             # train-mode forward with a backward pass behind torch.autograd (v2x_b200/train.py::SegTrainStep)
             batch = int(x.shape[0]) // self.num_agent
             return self._train_forward(x, (trans_matrices, num_agent_tensor, batch, self.num_agent, bool(self.only_v2i),

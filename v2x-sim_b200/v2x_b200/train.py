@@ -629,8 +629,9 @@ def backbone_encode(t: Tape, pre: str, x_in: Var):
     return [x0, x1, x2, x3, x4]
 
 
-def backbone_decode(t: Tape, pre: str, x0, x1, x2, x3, x4):
-    """Backbone.decode in train mode (Backbone.py:145-242): cat((up2(deep), skip)) -> two CBRs, four times."""
+def backbone_decode(t: Tape, pre: str, x0, x1, x2, x3, x4, kd: bool = False):
+    """Backbone.decode in train mode (Backbone.py:145-242): cat((up2(deep), skip)) -> two CBRs, four times.
+    ``kd``: return [x_8, x_7, x_6, x_5] (what STPN_KD / the kd_flag forwards hand to the distillation loss)."""
     x = t.cbr(pre + "conv5_1", pre + "bn5_1", [t.upsample2(x4), x3])
     x5 = t.cbr(pre + "conv5_2", pre + "bn5_2", [x])
     x = t.cbr(pre + "conv6_1", pre + "bn6_1", [t.upsample2(x5), x2])
@@ -638,7 +639,8 @@ def backbone_decode(t: Tape, pre: str, x0, x1, x2, x3, x4):
     x = t.cbr(pre + "conv7_1", pre + "bn7_1", [t.upsample2(x6), x1])
     x7 = t.cbr(pre + "conv7_2", pre + "bn7_2", [x])
     x = t.cbr(pre + "conv8_1", pre + "bn8_1", [t.upsample2(x7), x0])
-    return t.cbr(pre + "conv8_2", pre + "bn8_2", [x])
+    x8 = t.cbr(pre + "conv8_2", pre + "bn8_2", [x])
+    return [x8, x7, x6, x5] if kd else x8
 
 
 def det_heads(t: Tape, x8: Var, n: int):
@@ -766,17 +768,28 @@ class FusionTrainStep(torch.autograd.Function):
             fused = tape.cat_modulate(x3, mean, nat, batch, agents)
         else:
             fused = tape.warp_reduce(x3, trans, nat, batch, agents, kind, only_v2i=bool(module.only_v2i))
-        x8 = backbone_decode(tape, "decoder.", x0, x1, x2, fused, x4)
+        kd = int(getattr(module, "kd_flag", 0)) == 1
+        dec = backbone_decode(tape, "decoder.", x0, x1, x2, fused, x4, kd=kd)
+        x8 = dec[0] if kd else dec
         o_loc, o_cls = det_heads(tape, x8, n)
         ctx.tape, ctx.names, ctx.o_loc, ctx.o_cls = tape, names, o_loc, o_cls
         ctx.shapes = [v.shape for v in params]
-        return o_loc.value.view(n, 256, 256, 6, 1, 6), o_cls.value.view(n, -1, 2)
+        # kd_flag == 1 (FusionBase.py:72-73, DiscoNet.py:125-127): the decoder maps x_8, x_7, x_6, x_5 and the fused layer
+        # also leave the step, as fp32 NCHW tensors WITH gradients -- FaFModule.get_kd_loss (CoDetModule.py:257-260) pulls the
+        # student's x_5, x_6, x_7 and fused layer towards the teacher's
+        ctx.kd_vars = (dec + [fused]) if kd else []
+        extra = tuple(ops.act_to_float(v.act)[:, :v.c_log].contiguous() for v in ctx.kd_vars)
+        return (o_loc.value.view(n, 256, 256, 6, 1, 6), o_cls.value.view(n, -1, 2), *extra)
 
     @staticmethod
-    def backward(ctx, dloc, dcls):
+    def backward(ctx, dloc, dcls, *dkd):
         tape = ctx.tape
-        tape.scale = choose_scale(*[u for u in (dloc, dcls) if u is not None])
+        tape.scale = choose_scale(*[u for u in (dloc, dcls, *dkd) if u is not None])
         ctx.o_loc.upstream, ctx.o_cls.upstream = dloc, dcls
+        for v, g in zip(ctx.kd_vars, dkd):          # distillation gradients enter the tape at the maps they belong to
+            if g is not None:
+                gs = (g.to(torch.float32) * tape.scale).contiguous()
+                v.add_grad(tape.lib, ops.pack_input_nchw(gs, int(v.act.shape[-1]), PLANES))
         tape.backward()
         grads = [None if tape.grads.get(name) is None else tape.grads[name].reshape(shape)
                  for name, shape in zip(ctx.names, ctx.shapes)]
