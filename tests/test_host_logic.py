@@ -85,17 +85,28 @@ def test_forward_refuses_cpu_tensors_and_eval_warning_is_once():
 
 
 def test_training_is_offered_where_built_and_refused_elsewhere():
-    """FaFNet / det V2VNet route .train() forwards to the training tape (which needs CUDA tensors); the others raise."""
-    from coperception.models.det import FaFNet, When2com
+    """.train() forwards are routed to the training tape (which needs CUDA tensors: no CPU fallback) for every model that
+    trains on the path; what is not built -- FaFNet's kd tuple, compressed training, seg DiscoNet, a When2com in .train()
+    asked for the gated inference pass -- raises NotImplementedError before touching the device."""
+    from coperception.models.det import DiscoNet, FaFNet, MeanFusion, When2com
+    from coperception.models.seg import DiscoNet as SegDiscoNet, MeanFusion as SegMeanFusion
     from v2x_b200 import default_det_config
-    f = FaFNet(default_det_config(), kd_flag=0).train()
+    cfg = default_det_config()
+    det_args = (torch.zeros((5, 1, 256, 256, 13)), torch.zeros((1, 5, 5, 4, 4)), torch.full((1, 5), 5))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
-        f(torch.zeros((1, 1, 256, 256, 13)))
+        FaFNet(cfg, kd_flag=0).train()(torch.zeros((1, 1, 256, 256, 13)))
+    for model in (When2com(cfg, layer=3), MeanFusion(cfg, layer=3, kd_flag=0), MeanFusion(cfg, layer=3, kd_flag=1),
+                  DiscoNet(cfg, layer=3, kd_flag=1)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            model.train()(*det_args, batch_size=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SegMeanFusion(13, 8, num_agent=5).train()(torch.zeros((5, 13, 256, 256)), det_args[1], det_args[2])
     with pytest.raises(NotImplementedError):
-        FaFNet(default_det_config(), kd_flag=1).train()(torch.zeros((1, 1, 256, 256, 13)))
-    w = When2com(default_det_config(), layer=3).train()
+        FaFNet(cfg, kd_flag=1).train()(torch.zeros((1, 1, 256, 256, 13)))
     with pytest.raises(NotImplementedError):
-        w(torch.zeros((5, 1, 256, 256, 13)), torch.zeros((1, 5, 5, 4, 4)), torch.full((1, 5), 5), batch_size=1)
+        MeanFusion(cfg, layer=3, kd_flag=0, compress_level=2).train()(*det_args, batch_size=1)
+    with pytest.raises(NotImplementedError):
+        SegDiscoNet(13, 8, 5, kd_flag=False).train()(torch.zeros((5, 13, 256, 256)), det_args[1], det_args[2])
 
 
 def test_make_ref_stages_the_reference_and_ref_loader_finds_it(tmp_path, monkeypatch):

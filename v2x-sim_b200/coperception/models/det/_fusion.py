@@ -44,12 +44,12 @@ class FusionBase(B200DetModel):
             raise NotImplementedError("Please implement this method for specific fusion strategies")
         dev = bevs.device
         if self.training and self.KIND in ("mean", "sum", "max", "cat", "agent", "disco"):
-            # train-mode forward with a backward pass behind torch.autograd (v2x_b200/train.py::FusionTrainStep): the
-            # parameter-free fuse rules and CatFusion; AgentWise / DiscoNet (weight nets called per pair, KD) refuse below
-            if dev.type != "cuda":
-                raise RuntimeError("v2x_b200 fusion models need CUDA tensors (no CPU fallback); got %s" % dev)
+            # train-mode forward with a backward pass behind torch.autograd (v2x_b200/train.py::FusionTrainStep), every
+            # fuse rule, with or without the kd_flag outputs
             if self.layer != 3 or self.compress_level > 0:
                 raise NotImplementedError("training on the sm_100a path: layer 3, compress_level 0")
+            if dev.type != "cuda":
+                raise RuntimeError("v2x_b200 fusion models need CUDA tensors (no CPU fallback); got %s" % dev)
             from v2x_b200.train import FusionTrainStep
             outs = FusionTrainStep.apply(self, self.KIND, bevs, trans_matrices, num_agent_tensor, int(batch_size),
                                          *self.parameters())

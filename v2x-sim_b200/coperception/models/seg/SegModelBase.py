@@ -59,11 +59,11 @@ class SegModelBase(PlanCacheMixin, nn.Module):
         self._init_plan_cache()
 
     def _check(self, x):
+        if self.training:
+            raise NotImplementedError("the sm_100a path trains every seg model except DiscoNet; this model only implements "
+                                      "inference (model.eval())")
         if x.device.type != "cuda":
             raise RuntimeError("v2x_b200 seg models need CUDA tensors (no CPU fallback); got %s" % x.device)
-        if self.training:
-            raise NotImplementedError("the sm_100a path trains seg UNet, seg V2VNet and seg Mean / Sum / Max fusion; this model "
-                                      "only implements inference (model.eval())")
         self._warn_no_grad_graph()
 
     def _train_forward(self, x, fuse=None):
