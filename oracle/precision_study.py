@@ -102,7 +102,7 @@ def run(seed=0, batch=1, agents=5):
     return rows
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "fp8"):
     run(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 
 
@@ -134,3 +134,77 @@ def per_layer(seed=0, batch=1, agents=5, cheap=("fp16a2", "fp16w2", "fp16")):
             res[(layer, m)] = max(rel_err(out["loc"], ref["loc"]), rel_err(out["cls"], ref["cls"]))
         print("%-42s " % layer + "  ".join("%s %.2e" % (m, res[(layer, m)]) for m in cheap), flush=True)
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Study for the NEXT kernel mode: keep the main pass in fp16 and run the two correction
+# passes of fp16x3 -- hi * w_lo and a_lo * w_hi, each 2^-11 of the product -- as FP8 (e5m2) tensor-core passes, which issue
+# at twice the fp16 rate on sm_100a (kind::f8f6f4): 1 + 1/2 + 1/2 = 2 pass-equivalents instead of 3.
+# e5m2 spans 2^-16 .. 2^15 (31 binades, 2 mantissa bits): with a static power-of-two split per layer (the activation side
+# scaled down by 2^s, the weight-lo side up by 2^s, so the product needs no rescaling in the accumulator) both operands of
+# each correction pass fit.  `python -m oracle.precision_study fp8` emulates exactly that on the CPU.
+# ---------------------------------------------------------------------------------------------------------------------
+def q_e5m2(x, shift):
+    """x -> e5m2(x * 2^shift) * 2^-shift (round to nearest even, saturating to the largest finite e5m2)."""
+    s = float(2.0 ** shift)
+    y = (x * s).clamp(-57344.0, 57344.0)
+    return y.to(torch.float8_e5m2).float() / s
+
+
+def fp8_corrected_conv(x, w, b, args, kwargs, shift_w=8, shift_a=8):
+    x_hi, w_hi = q_fp16(x), q_fp16(w)
+    x_lo, w_lo = q_fp16(x - x_hi), q_fp16(w - w_hi)
+    main = _real_conv2d(x_hi, w_hi, b, *args, **kwargs)
+    c1 = _real_conv2d(q_e5m2(x_hi, -shift_w), q_e5m2(w_lo, shift_w), None, *args, **kwargs)      # hi * w_lo
+    c2 = _real_conv2d(q_e5m2(x_lo, shift_a), q_e5m2(w_hi, -shift_a), None, *args, **kwargs)      # a_lo * w_hi
+    return main + c1 + c2
+
+
+class emulate_fp8:
+    """Every conv as fp16 main pass + two e5m2 correction passes, except where ``keep(x, w)`` names another MODES entry."""
+
+    def __init__(self, keep=None, shift_w=8, shift_a=8):
+        self.keep, self.sw, self.sa = keep, shift_w, shift_a
+
+    def __enter__(self):
+        def conv2d(x, w, b=None, *a, **k):
+            m = self.keep(x, w) if self.keep else None
+            if m is not None:
+                return _real_conv2d(QUANT[MODES[m][0]](x), QUANT[MODES[m][1]](w), b, *a, **k)
+            return fp8_corrected_conv(x, w, b, a, k, self.sw, self.sa)
+        restate.F.conv2d = conv2d
+        return self
+
+    def __exit__(self, *exc):
+        restate.F.conv2d = _real_conv2d
+        return False
+
+
+def run_fp8(seed=0):
+    """V2VNet det (5 agents) and FaFNet (2 maps): end-to-end error of the fp8-corrected mode next to fp16x3 / fp16a2 / fp16."""
+    sd = synth.v2vnet_det_state(seed)
+    bevs, trans, nat = synth.make_scene(1, 5, seed)
+    fsd = synth.fafnet_state(seed)
+    fbev = synth.make_bevs(2, seed)
+    with torch.no_grad():
+        ref = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=5, gnn_iter=3)
+        fref = restate.fafnet_forward(fbev, fsd)
+    is_gru = lambda x, w: "fp16" if w.shape[0] == 768 else None       # noqa: E731  (the ConvGRU stays 1 pass, as in `mixed`)
+    cases = [("fp16x3 (3 passes)", emulate(lambda x, w: MODES["fp16x3"][:2])),
+             ("fp16a2 (2 passes, weights single-rounded)", emulate(lambda x, w: MODES["fp16a2"][:2])),
+             ("fp16 (1 pass)", emulate(lambda x, w: MODES["fp16"][:2])),
+             ("fp16 + 2 x e5m2 corrections (2 pass-equivalents)", emulate_fp8()),
+             ("same, ConvGRU at 1 fp16 pass (1.7 pass-equivalents on V2VNet)", emulate_fp8(keep=is_gru)),
+             ("same, shifts 6 / 6", emulate_fp8(shift_w=6, shift_a=6)),
+             ("same, shifts 10 / 10", emulate_fp8(shift_w=10, shift_a=10))]
+    for name, ctx in cases:
+        with torch.no_grad(), ctx:
+            out = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=5, gnn_iter=3)
+            fout = restate.fafnet_forward(fbev, fsd)
+        print("%-66s v2v loc %.2e cls %.2e | faf loc %.2e cls %.2e" % (
+            name, rel_err(out["loc"], ref["loc"]), rel_err(out["cls"], ref["cls"]),
+            rel_err(fout["loc"], fref["loc"]), rel_err(fout["cls"], fref["cls"])), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "fp8":
+    run_fp8()
