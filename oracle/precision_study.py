@@ -204,6 +204,20 @@ def run_fp8(seed=0):
         print("%-66s v2v loc %.2e cls %.2e | faf loc %.2e cls %.2e" % (
             name, rel_err(out["loc"], ref["loc"]), rel_err(out["cls"], ref["cls"]),
             rel_err(fout["loc"], fref["loc"]), rel_err(fout["cls"], fref["cls"])), flush=True)
+    # the other BASELINE models: seg When2Com_UNet (softmax fuse: no thresholded gate in the way) and seg UNet
+    wsd = synth.seg_when2com_state(seed)
+    wx, wtrans, wnat = synth.make_seg_scene(1, 5, seed)
+    usd = synth.seg_unet_state(seed)
+    with torch.no_grad():
+        wref = restate.seg_when2com_forward(wx, wtrans, wnat, wsd, agent_num=5, warp_flag=1, inference="softmax")
+        uref = restate.seg_unet_forward(wx[:2], usd)
+    for name, mk in (("fp16x3 (3 passes)", lambda: emulate(lambda x, w: MODES["fp16x3"][:2])),
+                     ("fp16 (1 pass)", lambda: emulate(lambda x, w: MODES["fp16"][:2])),
+                     ("fp16 + 2 x e5m2 corrections (2 pass-equivalents)", lambda: emulate_fp8())):
+        with torch.no_grad(), mk():
+            wout = restate.seg_when2com_forward(wx, wtrans, wnat, wsd, agent_num=5, warp_flag=1, inference="softmax")
+            uout = restate.seg_unet_forward(wx[:2], usd)
+        print("%-66s seg when2com logits %.2e | seg unet logits %.2e" % (name, rel_err(wout, wref), rel_err(uout, uref)), flush=True)
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "fp8":
