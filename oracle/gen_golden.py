@@ -57,18 +57,19 @@ def gen_v2vnet(tag, batch, seed, present=None, gnn_iter=3):
     print(tag, "loc.sum", out["loc.sum"], "cls.sum", out["cls.sum"])
 
 
-def gen_when2com(tag, batch, seed, warp_flag, inference, present=None):
+def gen_when2com(tag, batch, seed, warp_flag, inference, present=None, has_query=True, sparse=False, layer=3):
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
-        m = ref_loader.ref_when2com_det(warp_flag=warp_flag)
-    sd = synth.when2com_det_state(seed)
+        m = ref_loader.ref_when2com_det(warp_flag=warp_flag, has_query=has_query, sparse=sparse, layer=layer)
+    sd = synth.when2com_det_state(seed, has_query=has_query)
     m.load_state_dict(sd, strict=True)
     m.eval()
     bevs, trans, nat = synth.make_scene(batch, 5, seed, present=present)
-    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()), ref_loader.to_cuda_shim():
         r = m(bevs, trans, nat, training=False, MO_flag=True, inference=inference, batch_size=batch)
-    out = {"meta": np.asarray([batch, 5, seed, warp_flag], dtype=np.int64), "inference": np.asarray(inference)}
+    out = {"meta": np.asarray([batch, 5, seed, warp_flag], dtype=np.int64), "inference": np.asarray(inference),
+           "options": np.asarray([int(has_query), int(sparse), layer], dtype=np.int64)}
     if present is not None:
         out["present"] = np.asarray(present, dtype=np.int64)
     summarize("loc", r["loc"], out)
@@ -78,7 +79,7 @@ def gen_when2com(tag, batch, seed, warp_flag, inference, present=None):
     print(tag, "loc.sum", out["loc.sum"], "cls.sum", out["cls.sum"])
 
 
-def gen_seg(tag, kind, batch, seed, present=None, inference="activated", warp_flag=1):
+def gen_seg(tag, kind, batch, seed, present=None, inference="activated", warp_flag=1, has_query=True, sparse=False):
     """kind in {"unet", "v2vnet", "when2com"}; logits [N,8,256,256] of the live seg models."""
     import contextlib
     import io
@@ -90,10 +91,11 @@ def gen_seg(tag, kind, batch, seed, present=None, inference="activated", warp_fl
         elif kind == "v2vnet":
             m, sd = ref_loader.ref_seg_v2vnet(num_agent=a), synth.seg_v2vnet_state(seed)
         else:
-            m, sd = ref_loader.ref_seg_when2com(num_agent=a, warp_flag=warp_flag), synth.seg_when2com_state(seed)
+            m = ref_loader.ref_seg_when2com(num_agent=a, warp_flag=warp_flag, has_query=has_query, sparse=sparse)
+            sd = synth.seg_when2com_state(seed, has_query=has_query)
     m.load_state_dict(sd, strict=True)
     m.eval()
-    with torch.no_grad(), ref_loader.cpu_cuda_shim(), contextlib.redirect_stdout(io.StringIO()):
+    with torch.no_grad(), ref_loader.cpu_cuda_shim(), ref_loader.to_cuda_shim(), contextlib.redirect_stdout(io.StringIO()):
         if kind == "unet":
             r = m(x)
         elif kind == "v2vnet":
@@ -102,6 +104,8 @@ def gen_seg(tag, kind, batch, seed, present=None, inference="activated", warp_fl
             r = m(x, trans, nat, inference=inference, training=False)
     out = {"meta": np.asarray([batch, a, seed, warp_flag], dtype=np.int64), "inference": np.asarray(inference),
            "kind": np.asarray(kind)}
+    if kind == "when2com" and (not has_query or sparse):
+        out["options"] = np.asarray([int(has_query), int(sparse)], dtype=np.int64)
     if present is not None:
         out["present"] = np.asarray(present, dtype=np.int64)
     summarize("logits", r, out)
@@ -450,6 +454,17 @@ def gen_train_step(tag, kind, seed):
     print(tag, "parameters with gradients:", n_grads)
 
 
+def gen_options():
+    """The when2com constructor options beside the scripts' defaults: has_query=False (ones as queries), sparse=True
+    (a no-op in the reference: same fixture values as sparse=False) and det layer=2."""
+    gen_when2com("when2com_det_noquery_activated_seed41", 1, 41, 1, "activated", has_query=False)
+    gen_when2com("when2com_det_layer2_sparse_activated_seed42_present4", 1, 42, 1, "activated", present=[4], sparse=True,
+                 layer=2)
+    gen_when2com("when2com_det_layer2_noquery_nowarp_softmax_B2_seed43", 2, 43, 0, "softmax", has_query=False, layer=2)
+    gen_seg("seg_when2com_noquery_sparse_activated_seed44", "when2com", 1, 44, inference="activated", warp_flag=1,
+            has_query=False, sparse=True)
+
+
 def main():
     if not ref_loader.available():
         print("reference tree not available; golden fixtures can only be generated in the build container")
@@ -465,6 +480,9 @@ def main():
     if "--layers-only" in sys.argv:
         gen_layers()
         return 0
+    if "--options-only" in sys.argv:
+        gen_options()
+        return 0
     if "--train-only" in sys.argv:
         for tag, (kind, seed) in TRAIN_CASES.items():
             if not os.path.exists(os.path.join(GOLDEN_DIR, tag + ".npz")) or "--force" in sys.argv:
@@ -473,6 +491,7 @@ def main():
     gen_fusion_all()
     gen_compress()
     gen_layers()
+    gen_options()
     for tag, (kind, seed) in TRAIN_CASES.items():
         gen_train_step(tag, kind, seed)
     gen_warp("warp_small_seed3", 3)

@@ -82,10 +82,10 @@ def ref_fafnet(num_agent=5, kd_flag=0, compress_level=0):
     return FaFNet(ref_config(), layer=3, kd_flag=kd_flag, num_agent=num_agent, compress_level=compress_level)
 
 
-def ref_when2com_det(warp_flag=1, num_agent=5):
+def ref_when2com_det(warp_flag=1, num_agent=5, has_query=True, sparse=False, layer=3):
     install()
     When2com = importlib.import_module("coperception.models.det.When2com").When2com
-    return When2com(ref_config(), layer=3, warp_flag=warp_flag, num_agent=num_agent)
+    return When2com(ref_config(), layer=layer, warp_flag=warp_flag, num_agent=num_agent, has_query=has_query, sparse=sparse)
 
 
 def _seg_config():
@@ -105,10 +105,11 @@ def ref_seg_v2vnet(n_classes=8, num_agent=5):
     return V2VNet(13, n_classes, num_agent=num_agent)
 
 
-def ref_seg_when2com(n_classes=8, num_agent=5, warp_flag=1):
+def ref_seg_when2com(n_classes=8, num_agent=5, warp_flag=1, has_query=True, sparse=False):
     install()
     W = importlib.import_module("coperception.models.seg.When2Com_UNet").When2Com_UNet
-    return W(_seg_config(), in_channels=13, n_classes=n_classes, warp_flag=warp_flag, num_agent=num_agent)
+    return W(_seg_config(), in_channels=13, n_classes=n_classes, warp_flag=warp_flag, num_agent=num_agent,
+             has_query=has_query, sparse=sparse)
 
 
 _FUSION_CLASSES = {"mean": "MeanFusion", "max": "MaxFusion", "sum": "SumFusion", "cat": "CatFusion",
@@ -150,6 +151,22 @@ class cpu_cuda_shim:
     def __exit__(self, *exc):
         import torch
         torch.Tensor.cuda = self._t
+        return False
+
+
+class to_cuda_shim:
+    """``torch.ones(...).to("cuda")`` (det When2com.py:245, the has_query=False branch) becomes a no-op for CPU runs."""
+
+    def __enter__(self):
+        import torch
+        self._to = torch.Tensor.to
+        orig = self._to
+        torch.Tensor.to = lambda t, *a, **k: t if (a and isinstance(a[0], str) and a[0] == "cuda") else orig(t, *a, **k)
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.to = self._to
         return False
 
 

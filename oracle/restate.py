@@ -225,14 +225,18 @@ def km_generator(maps, sd, p):
 
 
 def when2com_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=1, agent_num=5, warp_flag=1,
-                         inference="activated", training=False, only_v2i=False, stages=False):
-    """det When2com.forward (When2com.py:150-332), layer = 3, has_query, MO_flag.  Eval-mode semantics:
-    ``inference`` in {"softmax", "activated", "argmax_test"}; training=True stops after the first decoder pass."""
+                         inference="activated", training=False, only_v2i=False, stages=False, has_query=True, layer=3):
+    """det When2com.forward (When2com.py:150-332), MO_flag=True.  Eval-mode semantics: ``inference`` in {"softmax",
+    "activated", "argmax_test"}; training=True stops after the first decoder pass.  ``has_query=False``: every agent's
+    query is a vector of ones (When2com.py:241-245).  ``layer`` in {2, 3}: the communicated encoder layer (:167-190; the
+    reference's argmax_test branch only exists for layer 3, :289-291).  ``sparse`` is not a parameter: the reference hands
+    it to the attention module, which never reads it (:374-412)."""
     enc = encode(bevs, sd, "u_encoder.")
     x, x_1, x_2, x_3, x_4 = enc
-    c, h, w = x_3.shape[1:]
+    assert layer in (2, 3) and not (layer != 3 and inference == "argmax_test" and not training)
+    c, h, w = enc[layer].shape[1:]
     size = (1, c, h, w)
-    feat = torch.flip(x_3, (2,))
+    feat = torch.flip(enc[layer], (2,))
     local = torch.stack([feat[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)  # [B,A,C,H,W]
     if warp_flag == 1:
         val_mat = torch.zeros(batch_size, agent_num, agent_num, c, h, w, dtype=local.dtype)
@@ -250,7 +254,8 @@ def when2com_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=
         val_mat = local
     qk = policy_net4(bevs, sd)
     keys = km_generator(qk, sd, "key_net.")
-    querys = km_generator(qk, sd, "query_net.")
+    querys = km_generator(qk, sd, "query_net.") if has_query else keys.new_ones(
+        (keys.shape[0], sd["attention_net.linear.weight"].shape[1]))
     key_mat = torch.stack([keys[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)      # [B,A,1024]
     query_mat = torch.stack([querys[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)  # [B,A,32]
     # MIMOGeneralDotProductAttention.forward (When2com.py:374-412)
@@ -265,8 +270,13 @@ def when2com_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=
     def to_batch(f):  # agents_to_batch (DetModelBase.py:53-69): agent-major + flip back
         return torch.flip(torch.cat([f[:, i] for i in range(agent_num)], 0), (2,))
 
+    def dec(x0, fused):   # the fused map replaces the communicated layer (:262-270)
+        skips = [x0, x_1, x_2, x_3]
+        skips[layer] = fused
+        return decode(*skips, x_4, sd, "decoder.")[0]
+
     fuse1 = to_batch(weighted(attn))
-    x_dec = decode(x, x_1, x_2, fuse1, x_4, sd, "decoder.")[0]
+    x_dec = dec(x, fuse1)
     prob = attn + torch.eye(agent_num).view(1, agent_num, agent_num) * 0.001
     fuse2 = None
     if not training:
@@ -279,7 +289,7 @@ def when2com_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=
                 coef = F.one_hot(prob.max(dim=1)[1], num_classes=agent_num).float().transpose(1, 2)  # argmax_select (:94-123)
             fuse2 = to_batch(weighted(coef))
             # NOTE: the layer-0 skip input of the second pass is the OUTPUT of the first pass (`x` was overwritten, :266-270)
-            x_dec = decode(x_dec, x_1, x_2, fuse2, x_4, sd, "decoder.")[0]
+            x_dec = dec(x_dec, fuse2)
         else:
             raise ValueError("Incorrect inference mode")
     res = heads(x_dec, sd)
@@ -375,7 +385,7 @@ def seg_policy_net4(x, sd, p="query_key_net."):
 
 
 def seg_when2com_forward(x, trans_matrices, num_agent_tensor, sd, agent_num=5, warp_flag=1, inference="activated",
-                         training=False, only_v2i=False, stages=False):
+                         training=False, only_v2i=False, stages=False, has_query=True):
     """seg When2Com_UNet.forward (When2Com_UNet.py:144-307).  Reproduces the key/query row quirk: PolicyNet4 emits
     256*8*8 = 16384 features per map but KmGenerator views them as rows of 4096 (:381-392), and rows 0..A*B-1 of the
     resulting [4*A*B, .] matrices are taken as the agents' keys / queries (:207-226)."""
@@ -401,7 +411,9 @@ def seg_when2com_forward(x, trans_matrices, num_agent_tensor, sd, agent_num=5, w
         val_mat = local
     qk = seg_policy_net4(x, sd)
     keys = km_generator(qk, sd, "key_net.")      # [4*A*B, 1024]
-    querys = km_generator(qk, sd, "query_net.")  # [4*A*B, 32]
+    # has_query=False: every agent's query is a vector of ones (When2Com_UNet.py:219-225)
+    querys = km_generator(qk, sd, "query_net.") if has_query else keys.new_ones(
+        (keys.shape[0], sd["attention_net.linear.weight"].shape[1]))  # [4*A*B, 32]
     key_mat = torch.stack([keys[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)
     query_mat = torch.stack([querys[batch_size * i: batch_size * (i + 1)] for i in range(agent_num)], 1)
     query = F.linear(query_mat, sd["attention_net.linear.weight"], sd["attention_net.linear.bias"])

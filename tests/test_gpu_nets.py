@@ -120,7 +120,12 @@ def test_v2vnet_graph_replay_matches_eager():
 @pytest.mark.parametrize("tag", ["when2com_det_warp_activated_seed2", "when2com_det_nowarp_argmax_seed3_present4",
                                  "when2com_det_warp_softmax_B2_seed4"])
 def test_when2com_det_forward(tag, mode, golden_dir, parity_log):
+    check_when2com_det(tag, mode, golden_dir, parity_log)
+
+
+def check_when2com_det(tag, mode, golden_dir, parity_log):
     """det When2com / who2com through the drop-in module, vs oracle + live-reference fixture.
+    Constructor options beside the defaults (has_query, sparse, layer) come from the fixture (tests/test_gpu_zz_options.py).
 
     The eval gate is DISCRETE (p > 0.2 / argmax over keys, When2com.py:94-148): a gate that the oracle's own attention
     puts within the path's measured attention error of its threshold may legitimately land on the other side.  Stated
@@ -134,12 +139,14 @@ def test_when2com_det_forward(tag, mode, golden_dir, parity_log):
     batch, a, seed, warp = [int(v) for v in g["meta"]]
     inference = str(g["inference"])
     present = [int(v) for v in g["present"]] if "present" in g.files else None
-    sd = synth.when2com_det_state(seed)
+    opts = [int(v) for v in g["options"]] if "options" in g.files else [1, 0, 3]
+    has_query, sparse, layer = bool(opts[0]), bool(opts[1]), opts[2]
+    sd = synth.when2com_det_state(seed, has_query=has_query)
     bevs, trans, nat = synth.make_scene(batch, a, seed, present=present)
     with torch.no_grad():
         ref = restate.when2com_det_forward(bevs, trans, nat, sd, batch_size=batch, agent_num=a, warp_flag=warp,
-                                           inference=inference, stages=True)
-    model = When2com(default_det_config(), layer=3, warp_flag=warp, num_agent=a)
+                                           inference=inference, stages=True, has_query=has_query, layer=layer)
+    model = When2com(default_det_config(), layer=layer, warp_flag=warp, num_agent=a, has_query=has_query, sparse=sparse)
     model.load_state_dict(sd, strict=True)
     model.precision = mode
     model = model.cuda().eval()

@@ -54,6 +54,10 @@ CASES = [("seg_unet_seed0", "unet"), ("seg_v2vnet_seed1_present4", "v2vnet"),
 @pytest.mark.parametrize("mode", ["mixed", "fp16x3", "bf16"])
 @pytest.mark.parametrize("tag,kind", CASES, ids=[c[0] for c in CASES])
 def test_seg_models(tag, kind, mode, golden_dir, parity_log):
+    check_seg_model(tag, kind, mode, golden_dir, parity_log)
+
+
+def check_seg_model(tag, kind, mode, golden_dir, parity_log):
     from coperception.models.seg import UNet, V2VNet, When2Com_UNet
     from oracle import restate, synth
     from oracle.gen_golden import STRIDE
@@ -74,11 +78,13 @@ def test_seg_models(tag, kind, mode, golden_dir, parity_log):
             ref = restate.seg_v2vnet_forward(x, trans, nat, sd, agent_num=a)
             model = V2VNet(13, 8, num_agent=a)
         else:
-            sd = synth.seg_when2com_state(seed)
+            opts = [int(v) for v in g["options"]] if "options" in g.files else [1, 0]   # (has_query, sparse)
+            sd = synth.seg_when2com_state(seed, has_query=bool(opts[0]))
             st = restate.seg_when2com_forward(x, trans, nat, sd, agent_num=a, warp_flag=warp, inference=inference,
-                                              stages=True)
+                                              stages=True, has_query=bool(opts[0]))
             ref, attn_ref = st["logits"], st["attn"]
-            model = When2Com_UNet(default_det_config(), n_classes=8, warp_flag=warp, num_agent=a)
+            model = When2Com_UNet(default_det_config(), n_classes=8, warp_flag=warp, num_agent=a, has_query=bool(opts[0]),
+                                  sparse=bool(opts[1]))
     model.load_state_dict(sd, strict=True)
     model.precision = mode
     model = model.cuda().eval()

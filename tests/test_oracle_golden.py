@@ -80,25 +80,39 @@ def test_v2vnet_det(golden_dir, tag):
     assert np.abs(cnt - g["cls.argmax_count"]).max() <= 4
 
 
-@pytest.mark.parametrize("tag", ["when2com_det_warp_activated_seed2", "when2com_det_nowarp_argmax_seed3_present4",
-                                 "when2com_det_warp_softmax_B2_seed4"])
+WHEN2COM_DET_FIXTURES = ["when2com_det_warp_activated_seed2", "when2com_det_nowarp_argmax_seed3_present4",
+                         "when2com_det_warp_softmax_B2_seed4",
+                         # constructor options beside the scripts' defaults (oracle/gen_golden.py::gen_options)
+                         "when2com_det_noquery_activated_seed41", "when2com_det_layer2_sparse_activated_seed42_present4",
+                         "when2com_det_layer2_noquery_nowarp_softmax_B2_seed43"]
+
+
+def when2com_options(g):
+    """(has_query, sparse, layer) of a when2com fixture (absent = the defaults True, False, 3)."""
+    o = [int(v) for v in g["options"]] if "options" in g.files else [1, 0, 3]
+    return bool(o[0]), bool(o[1]), (o[2] if len(o) > 2 else 3)
+
+
+@pytest.mark.parametrize("tag", WHEN2COM_DET_FIXTURES)
 def test_when2com_det(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, tag + ".npz"))
     batch, a, seed, warp = [int(v) for v in g["meta"]]
     inference = str(g["inference"])
     present = [int(v) for v in g["present"]] if "present" in g.files else None
-    sd = synth.when2com_det_state(seed)
+    has_query, _, layer = when2com_options(g)      # `sparse` never reaches the arithmetic (When2com.py:374-412)
+    sd = synth.when2com_det_state(seed, has_query=has_query)
     bevs, trans, nat = synth.make_scene(batch, a, seed, present=present)
     with torch.no_grad():
         r = restate.when2com_det_forward(bevs, trans, nat, sd, batch_size=batch, agent_num=a, warp_flag=warp,
-                                         inference=inference)
+                                         inference=inference, has_query=has_query, layer=layer)
     _check("loc", r["loc"], g)
     _check("cls", r["cls"], g)
 
 
 @pytest.mark.parametrize("tag,kind", [("seg_unet_seed0", "unet"), ("seg_v2vnet_seed1_present4", "v2vnet"),
                                       ("seg_when2com_warp_activated_seed2", "when2com"),
-                                      ("seg_when2com_nowarp_activated_seed3", "when2com")])
+                                      ("seg_when2com_nowarp_activated_seed3", "when2com"),
+                                      ("seg_when2com_noquery_sparse_activated_seed44", "when2com")])
 def test_seg_models(golden_dir, tag, kind):
     g = np.load(os.path.join(golden_dir, tag + ".npz"))
     batch, a, seed, warp = [int(v) for v in g["meta"]]
@@ -110,8 +124,9 @@ def test_seg_models(golden_dir, tag, kind):
         elif kind == "v2vnet":
             r = restate.seg_v2vnet_forward(x, trans, nat, synth.seg_v2vnet_state(seed), agent_num=a)
         else:
-            r = restate.seg_when2com_forward(x, trans, nat, synth.seg_when2com_state(seed), agent_num=a, warp_flag=warp,
-                                             inference=str(g["inference"]))
+            has_query = when2com_options(g)[0]
+            r = restate.seg_when2com_forward(x, trans, nat, synth.seg_when2com_state(seed, has_query=has_query),
+                                             agent_num=a, warp_flag=warp, inference=str(g["inference"]), has_query=has_query)
     _check("logits", r, g)
 
 

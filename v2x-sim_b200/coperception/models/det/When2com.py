@@ -54,31 +54,38 @@ class When2com(B200DetModel):
                  has_query=True, sparse=False, layer=3, warp_flag=1, image_size=512, shared_img_encoder="unified",
                  key_size=1024, query_size=32, num_agent=5, compress_level=0, only_v2i=False):
         super().__init__(config, layer, in_channels, num_agent=num_agent, only_v2i=only_v2i)
-        if layer != 3:
-            raise NotImplementedError("v2x_b200 When2com communicates at layer 3 (the reference scripts' default)")
-        if sparse or not has_query:
-            raise NotImplementedError("sparse / has_query=False are not built on the sm_100a path")
+        if layer not in (2, 3):
+            raise NotImplementedError("v2x_b200 When2com communicates at layer 2 or 3 (the reference scripts use 3)")
         self.compress_level = compress_level
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)
+        # ``sparse`` is accepted and, exactly as in the reference, changes nothing: it is handed to
+        # MIMOGeneralDotProductAttention.forward, which never reads it (When2com.py:255-257, 374-412 -- always nn.Softmax;
+        # the live reference gives bit-identical outputs for sparse=True / False, profiles/r02_reference_option_probe.txt)
         self.sparse, self.key_size, self.query_size = sparse, key_size, query_size
         self.shared_img_encoder, self.has_query, self.warp_flag = shared_img_encoder, has_query, warp_flag
         self.key_net = KmGenerator(out_size=key_size, input_feat_sz=image_size / 32)
         self.attention_net = MIMOGeneralDotProductAttention(query_size, key_size, warp_flag)
         self.query_key_net = PolicyNet4(in_channels=in_channels)
-        self.query_net = KmGenerator(out_size=query_size, input_feat_sz=image_size / 32)
+        if has_query:      # without it every agent's query is a vector of ones (When2com.py:66-69, 241-245)
+            self.query_net = KmGenerator(out_size=query_size, input_feat_sz=image_size / 32)
         # parameter groups the reference exposes (When2com.py:72-88)
         self.attention_paras = list(self.attention_net.parameters())
         self.img_net_paras = list(self.u_encoder.parameters()) + list(self.decoder.parameters())
         self.policy_net_paras = (list(self.query_key_net.parameters()) + list(self.key_net.parameters())
-                                 + self.attention_paras + list(self.query_net.parameters()))
+                                 + self.attention_paras)
+        if has_query:
+            self.policy_net_paras = self.policy_net_paras + list(self.query_net.parameters())
         self.all_paras = self.img_net_paras + self.policy_net_paras
 
     def forward(self, bevs, trans_matrices, num_agent_tensor, maps=None, vis=None, training=True, MO_flag=True,
                 inference="activated", batch_size=1):
         from v2x_b200 import nets
         if not MO_flag:
-            raise NotImplementedError("MO_flag=False (single query) is not built on the sm_100a path")
+            # the reference itself cannot run this: with a single query prob_action is [B, A, 1] and the reshape of the
+            # A x A ``small_bis`` at When2com.py:273-274 raises (profiles/r02_reference_option_probe.txt)
+            raise NotImplementedError("MO_flag=False raises in the reference too (When2com.py:274 reshapes an A x A "
+                                      "identity to [1, A, 1]); it is not built on the sm_100a path")
         dev = bevs.device
         if dev.type != "cuda":
             raise RuntimeError("v2x_b200 When2com needs CUDA tensors (no CPU fallback); got %s" % dev)
@@ -89,6 +96,9 @@ class When2com(B200DetModel):
                 raise NotImplementedError("model.train() with training=False (the gated second pass) is not built")
             if self.compress_level > 0:
                 raise NotImplementedError("training with compress_level > 0 is not built on the sm_100a path")
+            if not self.has_query or self.layer != 3:
+                raise NotImplementedError("training on the sm_100a path: has_query=True, layer 3 (the reference "
+                                          "scripts' defaults)")
             from v2x_b200.train import When2comTrainStep
             loc, cls = When2comTrainStep.apply(self, bevs, trans_matrices, num_agent_tensor, int(batch_size),
                                                *self.parameters())
@@ -96,8 +106,12 @@ class When2com(B200DetModel):
         self._check_eval()
         if inference not in ("softmax", "activated", "argmax_test"):
             raise ValueError("Incorrect inference mode")
+        if self.layer != 3 and inference == "argmax_test" and not training:
+            raise NotImplementedError("argmax_test only exists for layer 3 in the reference (When2com.py:289-291 hands "
+                                      "the fused map to the decoder's layer-3 slot whatever self.layer is)")
         key = ("w2c", int(batch_size), dev.index, self.precision, bool(training), inference)
         plan = self._get_plan(key, lambda: nets.When2comDetPlan(
             self._state(), int(batch_size), self.agent_num, planes=self._planes(), device=dev, warp_flag=self.warp_flag,
-            inference=inference, training_pass_only=bool(training), only_v2i=self.only_v2i))
+            inference=inference, training_pass_only=bool(training), only_v2i=self.only_v2i, has_query=self.has_query,
+            layer=self.layer))
         return plan.forward(bevs.to(torch.float32), trans_matrices.to(torch.float64), num_agent_tensor.to(torch.int64))

@@ -380,15 +380,25 @@ class FaFNetPlan(DetPlan):
 
 
 class When2comDetPlan(DetPlan):
-    """det When2com / who2com forward in eval mode (CP/models/det/When2com.py:150-332, layer 3, has_query, MO_flag).
+    """det When2com / who2com forward in eval mode (CP/models/det/When2com.py:150-332, MO_flag=True).
 
     encoder -> [policy encoder + 5 convs -> key/query MLPs -> attention scores] -> gated fuse -> decoder -> (eval:
-    re-gated fuse -> second decoder pass whose layer-0 skip is the first pass's output) -> heads."""
+    re-gated fuse -> second decoder pass whose layer-0 skip is the first pass's output) -> heads.
+
+    ``has_query=False``: every agent's query is a vector of ones (When2com.py:241-245) -- the query MLP is not run and
+    the attention kernel reads a constant buffer.  ``layer`` 2 or 3: the communicated encoder layer (:167-190); the
+    reference's argmax_test branch is written for layer 3 only (:289-291 hands the fused map to the decoder's layer-3
+    slot and crashes on a layer-2 map, profiles/r02_reference_option_probe.txt), so that combination is refused."""
 
     def __init__(self, sd, batch: int, agents: int = 5, planes: int = 1, device="cuda", warp_flag=1,
-                 inference="activated", training_pass_only=False, only_v2i=False):
+                 inference="activated", training_pass_only=False, only_v2i=False, has_query=True, layer: int = 3):
         super().__init__(batch * agents, planes, device)
         prec, planes = self.prec, self.prec.planes
+        if layer not in (2, 3):
+            raise ops.V2XError("When2com on the sm_100a path communicates at layer 2 or 3 (layer 4 only exists "
+                               "2x-upsampled in the workspace)")
+        if layer != 3 and inference == "argmax_test" and not training_pass_only:
+            raise ops.V2XError("argmax_test only exists for layer 3 in the reference (When2com.py:289-291)")
         ops.require_gpu()
         dev = self.device
         self.batch, self.agents = batch, agents
@@ -405,8 +415,9 @@ class When2comDetPlan(DetPlan):
             pre = "query_key_net.%s.cbr_unit." % name
             self.pol_convs.append(ops.pack_conv(sd[pre + "0.weight"], sd[pre + "0.bias"], _bn(sd, pre + "1"), cins=[cin],
                                                 stride=stride, planes=planes, device=dev))
+        nets_used = ("key_net", "query_net") if has_query else ("key_net",)
         self.mlp = {net: [(f32("%s.fc.%d.weight" % (net, i)), f32("%s.fc.%d.bias" % (net, i))) for i in (0, 2, 4)]
-                    for net in ("key_net", "query_net")}
+                    for net in nets_used}
         self.att_w, self.att_b = f32("attention_net.linear.weight"), f32("attention_net.linear.bias")
         self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
@@ -419,8 +430,9 @@ class When2comDetPlan(DetPlan):
         for i, pc in enumerate(self.pol_convs):
             t = self.conv(pc, [t], "pol_c%d" % (i + 1))
         qk = t
-        feats = {}
-        for net in ("key_net", "query_net"):
+        # has_query=False: query = ones(batch, 1, query_size) for every agent (When2com.py:241-245)
+        feats = {"query_net": torch.ones((n, self.att_w.shape[1]), dtype=torch.float32, device=dev)}
+        for net in nets_used:
             (w0, b0), (w1, b1), (w2, b2) = self.mlp[net]
             h0 = torch.empty((n, w0.shape[0]), dtype=torch.float32, device=dev)
             h1 = torch.empty((n, w1.shape[0]), dtype=torch.float32, device=dev)
@@ -435,17 +447,21 @@ class When2comDetPlan(DetPlan):
         gate = ops.GATE_MODES[inference]
         keys, querys, attn, coef, aw, ab = self.keys, self.querys, self.attn, self.coef, self.att_w, self.att_b
         self.add(lambda: ops.attn_scores(keys, querys, aw, ab, batch, agents, gate, attn=attn, coef=coef))
-        # ---- pass 1: softmax-weighted fuse -> decoder ----
-        c3 = x3.shape[-1]
-        fuse1 = self.act("fuse1", 32, 32, c3)
-        self.add(lambda: ops.warp_gated(x3, trans, na, attn, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i,
+        # ---- pass 1: softmax-weighted fuse of the communicated layer -> decoder ----
+        xs = [x0, x1, x2, x3]
+        xl = xs[layer]
+        cl, hl, wl = xl.shape[-1], xl.shape[2], xl.shape[3]
+        fuse1 = self.act("fuse1", hl, wl, cl)
+        self.add(lambda: ops.warp_gated(xl, trans, na, attn, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i,
                                         out=fuse1))
-        x8 = self.build_decoder(self.dec_w, x0, x1, x2, fuse1, x4u)
+        xs[layer] = fuse1
+        x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], x4u)
         if not training_pass_only and inference != "softmax":
-            fuse2 = self.act("fuse2", 32, 32, c3)
-            self.add(lambda: ops.warp_gated(x3, trans, na, coef, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i,
+            fuse2 = self.act("fuse2", hl, wl, cl)
+            self.add(lambda: ops.warp_gated(xl, trans, na, coef, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i,
                                             out=fuse2))
-            x8 = self.build_decoder(self.dec_w, x8, x1, x2, fuse2, x4u, tag="p2_")
+            xs[0], xs[layer] = x8, fuse2     # the layer-0 skip of the second pass is the first pass's output (:266-270)
+            x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], x4u, tag="p2_")
         self.build_heads(self.head_w, x8)
 
     def forward(self, bevs, trans_matrices, num_agent_tensor):
@@ -739,13 +755,6 @@ class When2comDetShardedPlan(DetPlan):
                     l()
 
     def capture(self):
-        if self.peer is not None:
-            if self.world > 1:
-                import torch.distributed as dist
-                dist.barrier(group=self.group)   # line the ranks up: the waits of the warm-up steps have a time limit
-            DetPlan.capture(self)     # two eager warm-up steps on every rank (they exchange like real ones), then one graph
-            self.peer.check()
-            return
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -159,10 +159,11 @@ class SegV2VNetPlan(_FusedSegPlan):
 
 
 class SegWhen2comPlan(_FusedSegPlan):
-    """seg When2Com_UNet.forward (When2Com_UNet.py:144-307), incl. the key/query row quirk."""
+    """seg When2Com_UNet.forward (When2Com_UNet.py:144-307), incl. the key/query row quirk.
+    ``has_query=False``: every agent's query is a vector of ones (:219-225); the query MLP is not run."""
 
     def __init__(self, sd, batch, agents=5, planes=1, device="cuda", warp_flag=1, inference="activated",
-                 training=False, only_v2i=False):
+                 training=False, only_v2i=False, has_query=True):
         super().__init__(batch * agents, planes, device)
         planes = self.planes   # ``planes`` may have been a mode name / Precision (v2x_b200/precision.py)
         ops.require_gpu()
@@ -178,7 +179,7 @@ class SegWhen2comPlan(_FusedSegPlan):
             self.pol_convs.append(ops.pack_conv(sd[pre + "0.weight"], sd[pre + "0.bias"], _bn(sd, pre + "1"), cins=[cin],
                                                 stride=stride, planes=planes, device=dev))
         self.mlp = {net: [(f32("%s.fc.%d.weight" % (net, i)), f32("%s.fc.%d.bias" % (net, i))) for i in (0, 2, 4)]
-                    for net in ("key_net", "query_net")}
+                    for net in (("key_net", "query_net") if has_query else ("key_net",))}
         self.att_w, self.att_b = f32("attention_net.linear.weight"), f32("attention_net.linear.bias")
         trans, na, n = self.trans, self.num_agent, self.n
 
@@ -188,8 +189,8 @@ class SegWhen2comPlan(_FusedSegPlan):
         for i, pc in enumerate(self.pol_convs):
             t = self.conv(pc, [t], "pol_c%d" % (i + 1))
         qk = t   # [N, 8, 8, 256]: 16384 features per map, viewed as 4 rows of 4096 (Q9); rows 0..N-1 are used
-        feats = {}
-        for net in ("key_net", "query_net"):
+        feats = {"query_net": torch.ones((n, self.att_w.shape[1]), dtype=torch.float32, device=dev)}
+        for net in self.mlp:
             (w0, b0), (w1, b1), (w2, b2) = self.mlp[net]
             h0 = torch.empty((n, w0.shape[0]), dtype=torch.float32, device=dev)
             h1 = torch.empty((n, w1.shape[0]), dtype=torch.float32, device=dev)

@@ -251,9 +251,9 @@ def seg_unet_state(seed=0, n_classes=8, g=None, sd=None, compress_level=0):
     return sd
 
 
-def seg_when2com_state(seed=0, n_classes=8):
+def seg_when2com_state(seed=0, n_classes=8, has_query=True):
     """seg When2Com_UNet (CP/models/seg/When2Com_UNet.py:10-91): SegModelBase + key/query MLPs + attention
-    + PolicyNet4 (own inc/down1-3 + conv1..5, :310-339)."""
+    + PolicyNet4 (own inc/down1-3 + conv1..5, :310-339).  ``has_query=False``: the same tensors without ``query_net.*``."""
     g = _Gen(seed)
     sd = seg_unet_state(seed, n_classes, g=g)
 
@@ -274,6 +274,12 @@ def seg_when2com_state(seed=0, n_classes=8):
                             ("conv5", 256, 256)):
         _conv(sd, g, "query_key_net.%s.cbr_unit.0" % name, cout, cin)
         _bn(sd, g, "query_key_net.%s.cbr_unit.1" % name, cout)
+    if not has_query:
+        for k in [k for k in sd if k.startswith("query_net.")]:
+            del sd[k]
+    if not has_query:
+        for k in [k for k in sd if k.startswith("query_net.")]:
+            del sd[k]
     return sd
 
 
@@ -283,10 +289,11 @@ def make_seg_scene(batch=1, num_agent=5, seed=0, p=0.03, present=None):
     return bevs[:, 0].permute(0, 3, 1, 2).contiguous(), trans, nat
 
 
-def when2com_det_state(seed=0):
+def when2com_det_state(seed=0, has_query=True):
     """state_dict of det When2com(config, layer=3, warp_flag=..) (CP/models/det/When2com.py:22-92):
     V2VNet-style heads / u_encoder / decoder plus key_net / query_net MLPs (:415-430), attention_net.linear
-    (:370) and query_key_net = PolicyNet4 (a full Backbone + five Conv2DBatchNormRelu, :335-359)."""
+    (:370) and query_key_net = PolicyNet4 (a full Backbone + five Conv2DBatchNormRelu, :335-359).
+    ``has_query=False``: the same tensors without ``query_net.*`` (the module is not constructed, :66-69)."""
     g = _Gen(seed)
     sd = OrderedDict()
     heads_state(sd, g)
@@ -310,4 +317,7 @@ def when2com_det_state(seed=0):
                             ("conv5", 256, 256)):
         _conv(sd, g, "query_key_net.%s.cbr_unit.0" % name, cout, cin)
         _bn(sd, g, "query_key_net.%s.cbr_unit.1" % name, cout)
+    if not has_query:
+        for k in [k for k in sd if k.startswith("query_net.")]:
+            del sd[k]
     return sd
