@@ -358,6 +358,9 @@ TRAIN_CASES = {   # tag -> (kind, seed)
     "train_step_seg_cat_seed37": ("seg_cat", 37),
     "train_step_seg_agent_seed38": ("seg_agent", 38),
     "train_step_seg_disco_seed39": ("seg_disco", 39),
+    # compress_level > 0 in .train() (Backbone.py:138-141 / UNet.py:30-32 with train-mode BatchNorm on the pair)
+    "train_step_v2vnet_c2_seed45": ("v2vnet_c2", 45),
+    "train_step_seg_unet_c3_seed46": ("seg_unet_c3", 46),
 }
 
 
@@ -365,6 +368,10 @@ def train_case(kind, seed):
     """(state_dict, inputs tuple, output keys) of a training-step case; shared by the generator and the CPU test."""
     if kind == "v2vnet":
         return synth.v2vnet_det_state(seed), synth.make_scene(1, 5, seed, present=[4]), ("loc", "cls")
+    if kind == "v2vnet_c2":
+        return synth.v2vnet_det_state(seed, compress_level=2), synth.make_scene(1, 5, seed, present=[4]), ("loc", "cls")
+    if kind == "seg_unet_c3":
+        return synth.seg_unet_state(seed, compress_level=3), (synth.make_seg_scene(1, 2, seed)[0],), ("logits",)
     if kind == "fafnet":
         return synth.fafnet_state(seed), (synth.make_bevs(3, seed),), ("loc", "cls")
     if kind == "when2com":
@@ -399,6 +406,10 @@ def gen_train_step(tag, kind, seed):
     with contextlib.redirect_stdout(io.StringIO()):
         if kind == "v2vnet":
             m = ref_loader.ref_v2vnet_det()
+        elif kind == "v2vnet_c2":
+            m = ref_loader.ref_v2vnet_det(compress_level=2)
+        elif kind == "seg_unet_c3":
+            m = ref_loader.ref_seg_unet(compress_level=3)
         elif kind == "fafnet":
             m = ref_loader.ref_fafnet(kd_flag=0)
         elif kind == "when2com":
@@ -417,7 +428,7 @@ def gen_train_step(tag, kind, seed):
     m.double().train()
     x = inputs[0].double()
     with ref_loader.float64_shim(), ref_loader.cpu_cuda_shim(), contextlib.redirect_stdout(io.StringIO()):
-        if kind in ("fafnet", "seg_unet"):
+        if kind in ("fafnet", "seg_unet", "seg_unet_c3"):
             r = m(x)
         elif kind == "seg_when2com":
             r = m(x, inputs[1], inputs[2], training=True)

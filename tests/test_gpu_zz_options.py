@@ -44,3 +44,84 @@ def test_when2com_refuses_what_the_reference_cannot_run():
             m(bevs.cuda(), trans.cuda(), nat.cuda(), training=False, MO_flag=False, batch_size=1)
         with pytest.raises(NotImplementedError):
             m(bevs.cuda(), trans.cuda(), nat.cuda(), training=False, inference="argmax_test", batch_size=1)
+
+
+def test_v2vnet_compressed_train_step_matches_oracle(golden_dir, parity_log):
+    """det V2VNet(compress_level=2) in .train(): the compresser pair of the communicated layer (Backbone.py:138-141) with
+    train-mode BatchNorm on the tape; x_4 is computed from the uncompressed x_3, so x_3 collects two gradients."""
+    import os
+
+    import numpy as np
+    import torch
+    from coperception.models.det import V2VNet
+    from oracle import restate
+    from oracle.gen_golden import make_upstream, train_case
+    from test_gpu_train import _check_buffers, _check_grads, _rel
+    from v2x_b200 import default_det_config
+    tag, seed = "train_step_v2vnet_c2_seed45", 45
+    golden = np.load(os.path.join(golden_dir, tag + ".npz"))
+    sd, (bevs, trans, nat), _ = train_case("v2vnet_c2", seed)
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    up = make_upstream({"loc": (bevs.shape[0], 256, 256, 6, 1, 6), "cls": (bevs.shape[0], 256 * 256 * 6, 2)}, seed)
+    out_ref, grads_ref, sd_after = restate.train_step_vjp(
+        lambda s: restate.v2vnet_det_forward(bevs.double(), trans, nat, s, batch_size=1, agent_num=5, gnn_iter=3,
+                                             compress_level=2), sd64, up)
+    model = V2VNet(default_det_config(), 3, 3, 256, num_agent=5, compress_level=2)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    out = model(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    for k in ("loc", "cls"):
+        e = _rel(out[k], out_ref[k])
+        print("v2vnet compress 2 train forward", k, "rel_err %.3e" % e)
+        assert e < 1e-3
+    torch.autograd.backward([out["cls"], out["loc"]], [up["cls"].float().cuda(), up["loc"].float().cuda()])
+    torch.cuda.synchronize()
+    got = {k: p.grad for k, p in model.named_parameters()}
+    for k, g in got.items():
+        assert (g is not None) == (k in grads_ref), k
+    assert "u_encoder.com_compresser.weight" in grads_ref and "u_encoder.bn_decompress.weight" in grads_ref
+    _check_grads(tag, got, grads_ref, golden, parity_log)
+    _check_buffers(tag, dict(model.named_buffers()), sd_after, parity_log, golden=golden)
+
+
+def test_seg_unet_compressed_train_step_matches_oracle(golden_dir, parity_log):
+    """seg UNet(compress_level=3) in .train() (UNet.py:30-32: the pair replaces x4 for the whole decoder)."""
+    import os
+
+    import numpy as np
+    import torch
+    from coperception.models.seg import UNet
+    from oracle import restate
+    from oracle.gen_golden import make_upstream, train_case
+    from test_gpu_train import _check_buffers, _check_grads, _rel
+    tag, seed = "train_step_seg_unet_c3_seed46", 46
+    golden = np.load(os.path.join(golden_dir, tag + ".npz"))
+    sd, (x,), _ = train_case("seg_unet_c3", seed)
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    up = make_upstream({"logits": (x.shape[0], 8, 256, 256)}, seed)
+    out_ref, grads_ref, sd_after = restate.train_step_vjp(lambda s: {"logits": restate.seg_unet_forward(x.double(), s)}, sd64, up)
+    model = UNet(13, 8, compress_level=3)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    out = model(x.cuda())
+    e = _rel(out, out_ref["logits"])
+    print("seg unet compress 3 train forward logits rel_err %.3e" % e)
+    assert out.shape == out_ref["logits"].shape and e < 1e-3
+    out.backward(up["logits"].float().cuda())
+    torch.cuda.synchronize()
+    got = {k: p.grad for k, p in model.named_parameters()}
+    for k, g in got.items():
+        assert (g is not None) == (k in grads_ref), k
+    _check_grads(tag, got, grads_ref, golden, parity_log, min_params=40)
+    _check_buffers(tag, dict(model.named_buffers()), sd_after, parity_log, golden=golden, rtol=2e-5)
+
+
+def test_training_refuses_fewer_than_32_compressed_channels():
+    import torch
+    from coperception.models.det import V2VNet
+    from oracle import synth
+    from v2x_b200 import default_det_config
+    bevs, trans, nat = synth.make_scene(1, 5, 0)
+    m = V2VNet(default_det_config(), 3, 3, 256, num_agent=5, compress_level=4).cuda().train()
+    with pytest.raises(NotImplementedError):
+        m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)

@@ -259,6 +259,8 @@ def test_train_step_oracle(golden_dir, tag, kind, seed):
     wrap = lambda t: t if isinstance(t, dict) else {"logits": t}   # noqa: E731
     fwd = {
         "v2vnet": lambda w: restate.v2vnet_det_forward(*inputs, w, batch_size=1, agent_num=5, gnn_iter=3),
+        "v2vnet_c2": lambda w: restate.v2vnet_det_forward(*inputs, w, batch_size=1, agent_num=5, gnn_iter=3, compress_level=2),
+        "seg_unet_c3": lambda w: wrap(restate.seg_unet_forward(inputs[0], w)),
         "fafnet": lambda w: restate.fafnet_forward(inputs[0], w),
         "when2com": lambda w: restate.when2com_det_forward(*inputs, w, batch_size=1, agent_num=5, warp_flag=1, training=True),
         "disco": lambda w: restate.fusion_det_forward("disco", *inputs, w, batch_size=1, agent_num=5),

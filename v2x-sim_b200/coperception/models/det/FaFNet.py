@@ -21,8 +21,8 @@ class FaFNet(B200DetModel):
         if self.training:
             # train-mode forward (BatchNorm batch statistics + running-buffer update) with a backward pass behind
             # torch.autograd: FaFModule.step's loss.backward() / optimizer.step() drive it (CoDetModule.py:283-291)
-            if self.kd_flag == 1 or hasattr(self.stpn, "com_compresser"):
-                raise NotImplementedError("training with kd_flag == 1 / compress_level > 0 is not built on the sm_100a path")
+            if self.kd_flag == 1 or (hasattr(self.stpn, "com_compresser") and self.stpn.com_compresser.out_channels < 32):
+                raise NotImplementedError("training with kd_flag == 1 / compress_level > 3 is not built on the sm_100a path")
             if dev.type != "cuda":
                 raise RuntimeError("v2x_b200 FaFNet needs CUDA tensors (no CPU fallback); got %s" % dev)
             from v2x_b200.train import FaFNetTrainStep

@@ -37,8 +37,8 @@ class V2VNet(B200DetModel):
         if self.training:
             # train-mode forward (BatchNorm batch statistics) with the backward pass behind torch.autograd, so the
             # reference's FaFModule.step (loss.backward() / optimizer.step(), CoDetModule.py:283-291) drives it
-            if self.layer != 3 or self.compress_level > 0:
-                raise NotImplementedError("training on the sm_100a path: layer 3, compress_level 0 (the reference scripts' defaults)")
+            if self.layer != 3 or self.compress_level > 3:
+                raise NotImplementedError("training on the sm_100a path: layer 3, compress_level 0..3")
             from v2x_b200.train import V2VNetTrainStep
             loc, cls = V2VNetTrainStep.apply(self, bevs, trans_matrices, num_agent_tensor, int(batch_size), *self.parameters())
             return {"loc": loc, "cls": cls}

@@ -94,8 +94,9 @@ class When2com(B200DetModel):
             # it (CoDetModule.py:232-247 calls the model with its default training=True)
             if not training:
                 raise NotImplementedError("model.train() with training=False (the gated second pass) is not built")
-            if self.compress_level > 0:
-                raise NotImplementedError("training with compress_level > 0 is not built on the sm_100a path")
+            if self.compress_level > 3:
+                raise NotImplementedError("training with compress_level > 3 (fewer than 32 compressed channels) is not "
+                                          "built on the sm_100a path")
             if not self.has_query or self.layer != 3:
                 raise NotImplementedError("training on the sm_100a path: has_query=True, layer 3 (the reference "
                                           "scripts' defaults)")

@@ -46,8 +46,8 @@ class FusionBase(B200DetModel):
         if self.training and self.KIND in ("mean", "sum", "max", "cat", "agent", "disco"):
             # train-mode forward with a backward pass behind torch.autograd (v2x_b200/train.py::FusionTrainStep), every
             # fuse rule, with or without the kd_flag outputs
-            if self.layer != 3 or self.compress_level > 0:
-                raise NotImplementedError("training on the sm_100a path: layer 3, compress_level 0")
+            if self.layer != 3 or self.compress_level > 3:
+                raise NotImplementedError("training on the sm_100a path: layer 3, compress_level 0..3")
             if dev.type != "cuda":
                 raise RuntimeError("v2x_b200 fusion models need CUDA tensors (no CPU fallback); got %s" % dev)
             from v2x_b200.train import FusionTrainStep

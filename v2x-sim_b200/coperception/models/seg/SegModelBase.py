@@ -68,8 +68,9 @@ class SegModelBase(PlanCacheMixin, nn.Module):
 
     def _train_forward(self, x, fuse=None):
         """Train-mode forward with a backward pass behind torch.autograd (v2x_b200/train.py::SegTrainStep)."""
-        if self.compress_level > 0 or getattr(self, "kd_flag", False):
-            raise NotImplementedError("training with compress_level > 0 / kd_flag is not built on the sm_100a path")
+        if self.compress_level > 4 or getattr(self, "kd_flag", False):
+            raise NotImplementedError("training with compress_level > 4 (fewer than 32 compressed channels) / kd_flag is "
+                                      "not built on the sm_100a path")
         if x.device.type != "cuda":
             raise RuntimeError("v2x_b200 seg models need CUDA tensors (no CPU fallback); got %s" % x.device)
         from v2x_b200.train import SegTrainStep

@@ -612,8 +612,26 @@ def choose_scale(*upstreams) -> float:
 # =====================================================================================================================
 # network builders
 # =====================================================================================================================
+MIN_COMPRESSED_CHANNELS = 32    # narrowest train-mode BatchNorm the tape's kernels take without channel padding
+
+
+def compress_pair(t: Tape, pre: str, x: Var) -> Var:
+    """com_compresser -> BN -> ReLU -> com_decompresser -> BN -> ReLU of the communicated layer in train mode
+    (Backbone.py:138-141, SegModelBase.py:29-43 as applied at UNet.py:30-32): two 1x1 ``cbr`` steps on the tape.  The
+    eval plans zero-pad a compressed width below 32 (nets.pack_compress_pair); a train-mode BatchNorm over padded channels
+    would need padded affine / running buffers, so training takes >= 32 compressed channels (det compress_level <= 3,
+    seg <= 4) and refuses the rest."""
+    cc = int(t.p[pre + "com_compresser.weight"].shape[0])
+    if cc < MIN_COMPRESSED_CHANNELS:
+        raise NotImplementedError("training with %d compressed channels is not built on the sm_100a path (>= %d: "
+                                  "compress_level <= 3 for det, <= 4 for seg)" % (cc, MIN_COMPRESSED_CHANNELS))
+    c = t.cbr(pre + "com_compresser", pre + "bn_compress", [x])
+    return t.cbr(pre + "com_decompresser", pre + "bn_decompress", [c])
+
+
 def backbone_encode(t: Tape, pre: str, x_in: Var):
-    """Backbone.encode in train mode (Backbone.py:89-143); returns [x, x_1, x_2, x_3, x_4]."""
+    """Backbone.encode in train mode (Backbone.py:89-143); returns [x, x_1, x_2, x_3, x_4].  With compress_level > 0 the
+    returned x_3 went through the compresser pair; x_4 was computed from the uncompressed map (:131-141)."""
     x = t.cbr(pre + "conv_pre_1", pre + "bn_pre_1", [x_in], need_input_grad=[False])
     x0 = t.cbr(pre + "conv_pre_2", pre + "bn_pre_2", [x])
     x = t.cbr(pre + "conv1_1", pre + "bn1_1", [x0], stride=2)
@@ -626,6 +644,8 @@ def backbone_encode(t: Tape, pre: str, x_in: Var):
     x3 = t.cbr(pre + "conv3_2", pre + "bn3_2", [x])
     x = t.cbr(pre + "conv4_1", pre + "bn4_1", [x3], stride=2)
     x4 = t.cbr(pre + "conv4_2", pre + "bn4_2", [x])
+    if pre + "com_compresser.weight" in t.p:
+        x3 = compress_pair(t, pre, x3)
     return [x0, x1, x2, x3, x4]
 
 
@@ -911,6 +931,8 @@ def seg_encode(t: Tape, x_in: Var, pre: str = ""):
     x2 = seg_double_conv(t, pre + "down1.maxpool_conv.1.double_conv.", [t.maxpool2(x1)])
     x3 = seg_double_conv(t, pre + "down2.maxpool_conv.1.double_conv.", [t.maxpool2(x2)])
     x4 = seg_double_conv(t, pre + "down3.maxpool_conv.1.double_conv.", [t.maxpool2(x3)])
+    if pre + "com_compresser.weight" in t.p:     # the model's own encoder only; PolicyNet4 has no compresser
+        x4 = compress_pair(t, pre, x4)
     return x1, x2, x3, x4
 
 
