@@ -268,3 +268,92 @@ def test_seg_train_tape_wiring(fake, case):
     got = {k for k, p in zip(names, params) if p.grad is not None}
     assert "inc.double_conv.0.weight" in got and "outc.conv.bias" in got
     assert ("com_compresser.weight" in got) == (case == "unet_c3")
+
+
+# ---- unit-sharded plans (one rank of a gloo group; the collectives run for real on the CPU tensors) -----------------
+@pytest.fixture
+def gloo_single(tmp_path):
+    import torch.distributed as dist
+    if dist.is_initialized():
+        pytest.skip("a process group is already initialised in this process")
+    dist.init_process_group("gloo", rank=0, world_size=1, store=dist.FileStore(str(tmp_path / "store"), 1))
+    yield dist
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["allgather", "neighbours"])
+def test_v2vnet_sharded_plan_wiring(fake, gloo_single, exchange):
+    from v2x_b200 import nets
+    plan = nets.V2VNetDetShardedPlan(synth.v2vnet_det_state(1), 2, 5, 0, 1, planes="mixed", device="cpu", exchange=exchange)
+    bevs, trans, nat = synth.make_scene(2, 5, 1)
+    out = plan.forward(bevs, trans, nat)
+    assert tuple(out["cls"].shape) == (10, 256 * 256 * 6, 2) and plan.exchange_planes == 1
+    assert len(plan._segments()) == 3 and sum(len(s) for s in plan._segments()) == len(plan.launches)
+
+
+@pytest.mark.parametrize("warp_flag", [0, 1])
+def test_when2com_sharded_plan_wiring(fake, gloo_single, warp_flag):
+    from v2x_b200 import nets
+    plan = nets.When2comDetShardedPlan(synth.when2com_det_state(3), 1, 5, 0, 1, planes="mixed", device="cpu", warp_flag=warp_flag)
+    bevs, trans, nat = synth.make_scene(1, 5, 3)
+    out = plan.forward(bevs, trans, nat)
+    assert tuple(out["loc"].shape) == (5, 256, 256, 6, 1, 6)
+    assert hasattr(plan, "x3_all") == (not warp_flag)     # feature maps cross the wire only without the warp
+
+
+def test_plan_classes_only_read_attributes_they_define():
+    """Static check (AST) over the product package: every ``self.x`` a class reads is assigned somewhere in the class, one
+    of its in-package bases or subclasses, or comes from a base outside the package.  (A ``capture()`` reading a
+    ``self.peer`` its class never set survived a round because no CPU test could execute it.)"""
+    import ast
+    import os
+    root = os.path.dirname(os.path.abspath(_lib.__file__))
+    classes = {}
+    for fn in sorted(os.listdir(root)):
+        if not fn.endswith(".py"):
+            continue
+        for node in ast.walk(ast.parse(open(os.path.join(root, fn)).read())):
+            if not isinstance(node, ast.ClassDef):
+                continue
+            assigned, read = set(), {}
+            for b in node.body:
+                if isinstance(b, (ast.FunctionDef, ast.ClassDef)):
+                    assigned.add(b.name)
+                elif isinstance(b, ast.Assign):
+                    assigned.update(t.id for t in b.targets if isinstance(t, ast.Name))
+                elif isinstance(b, ast.AnnAssign) and isinstance(b.target, ast.Name):
+                    assigned.add(b.target.id)
+            for n in ast.walk(node):
+                if isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "self":
+                    if isinstance(n.ctx, ast.Store):
+                        assigned.add(n.attr)
+                    else:
+                        read.setdefault(n.attr, n.lineno)
+            bases = [b.id if isinstance(b, ast.Name) else getattr(b, "attr", "?") for b in node.bases]
+            classes[node.name] = (bases, assigned, read, fn)
+
+    def lineage(name, seen=None):     # the class, its in-package ancestors; None if a base lives outside the package
+        seen = seen or set()
+        if name in seen:
+            return set()
+        seen.add(name)
+        out = {name}
+        for b in classes[name][0]:
+            if b not in classes:
+                return None
+            up = lineage(b, seen)
+            if up is None:
+                return None
+            out |= up
+        return out
+
+    problems = []
+    for name, (bases, assigned, read, fn) in classes.items():
+        line = lineage(name)
+        if line is None:
+            continue
+        family = set(line)
+        family |= {n for n in classes if (lineage(n) or set()) & {name}}       # subclasses may set what a base reads
+        have = set().union(*(classes[n][1] for n in family))
+        problems += ["%s:%d %s.%s" % (fn, ln, name, a) for a, ln in read.items() if a not in have]
+    assert not problems, problems
