@@ -86,8 +86,9 @@ def test_forward_refuses_cpu_tensors_and_eval_warning_is_once():
 
 def test_training_is_offered_where_built_and_refused_elsewhere():
     """.train() forwards are routed to the training tape (which needs CUDA tensors: no CPU fallback) for every model that
-    trains on the path; what is not built -- FaFNet's kd tuple, compressed training, seg DiscoNet, a When2com in .train()
-    asked for the gated inference pass -- raises NotImplementedError before touching the device."""
+    trains on the path; what is not built -- FaFNet's kd tuple, fewer than 32 compressed channels, seg DiscoNet, a When2com
+    without its query net or asked for the gated inference pass in .train() -- raises NotImplementedError before touching
+    the device."""
     from coperception.models.det import DiscoNet, FaFNet, MeanFusion, When2com
     from coperception.models.seg import DiscoNet as SegDiscoNet, MeanFusion as SegMeanFusion
     from v2x_b200 import default_det_config
@@ -103,8 +104,12 @@ def test_training_is_offered_where_built_and_refused_elsewhere():
         SegMeanFusion(13, 8, num_agent=5).train()(torch.zeros((5, 13, 256, 256)), det_args[1], det_args[2])
     with pytest.raises(NotImplementedError):
         FaFNet(cfg, kd_flag=1).train()(torch.zeros((1, 1, 256, 256, 13)))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):       # compressed training: >= 32 compressed channels
         MeanFusion(cfg, layer=3, kd_flag=0, compress_level=2).train()(*det_args, batch_size=1)
+    with pytest.raises(NotImplementedError):
+        MeanFusion(cfg, layer=3, kd_flag=0, compress_level=4).train()(*det_args, batch_size=1)
+    with pytest.raises(NotImplementedError):
+        When2com(cfg, layer=3, has_query=False).train()(*det_args, batch_size=1)
     with pytest.raises(NotImplementedError):
         SegDiscoNet(13, 8, 5, kd_flag=False).train()(torch.zeros((5, 13, 256, 256)), det_args[1], det_args[2])
 

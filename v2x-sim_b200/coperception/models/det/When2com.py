@@ -86,12 +86,7 @@ class When2com(B200DetModel):
             # A x A ``small_bis`` at When2com.py:273-274 raises (profiles/r02_reference_option_probe.txt)
             raise NotImplementedError("MO_flag=False raises in the reference too (When2com.py:274 reshapes an A x A "
                                       "identity to [1, A, 1]); it is not built on the sm_100a path")
-        dev = bevs.device
-        if dev.type != "cuda":
-            raise RuntimeError("v2x_b200 When2com needs CUDA tensors (no CPU fallback); got %s" % dev)
-        if self.training:
-            # model.train(): the train-mode forward with a backward pass behind torch.autograd, as FaFModule.step drives
-            # it (CoDetModule.py:232-247 calls the model with its default training=True)
+        if self.training:       # what the training tape does not take is refused before the device is touched
             if not training:
                 raise NotImplementedError("model.train() with training=False (the gated second pass) is not built")
             if self.compress_level > 3:
@@ -100,6 +95,12 @@ class When2com(B200DetModel):
             if not self.has_query or self.layer != 3:
                 raise NotImplementedError("training on the sm_100a path: has_query=True, layer 3 (the reference "
                                           "scripts' defaults)")
+        dev = bevs.device
+        if dev.type != "cuda":
+            raise RuntimeError("v2x_b200 When2com needs CUDA tensors (no CPU fallback); got %s" % dev)
+        if self.training:
+            # model.train(): the train-mode forward with a backward pass behind torch.autograd, as FaFModule.step drives
+            # it (CoDetModule.py:232-247 calls the model with its default training=True)
             from v2x_b200.train import When2comTrainStep
             loc, cls = When2comTrainStep.apply(self, bevs, trans_matrices, num_agent_tensor, int(batch_size),
                                                *self.parameters())
