@@ -474,6 +474,20 @@ def gen_options():
     gen_when2com("when2com_det_layer2_noquery_nowarp_softmax_B2_seed43", 2, 43, 0, "softmax", has_query=False, layer=2)
     gen_seg("seg_when2com_noquery_sparse_activated_seed44", "when2com", 1, 44, inference="activated", warp_flag=1,
             has_query=False, sparse=True)
+    # communication at layer 4 (512 ch, 16x16): det When2com (activated: two decoder passes) and det V2VNet (two GNN rounds)
+    gen_when2com("when2com_det_layer4_activated_seed48", 1, 48, 1, "activated", layer=4)
+    m = ref_loader.ref_v2vnet_det(gnn_iter_times=2, layer=4, layer_channel=512)
+    sd = synth.v2vnet_det_state(47, layer_channel=512)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(1, 5, 47, present=[4])
+    with torch.no_grad():
+        r = m(bevs, trans, nat, batch_size=1)
+    out = {"meta": np.asarray([1, 5, 47, 4], dtype=np.int64)}
+    summarize("loc", r["loc"], out)
+    summarize("cls", r["cls"], out)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "layer4_v2vnet_det_seed47.npz"), **out)
+    print("layer4_v2vnet_det_seed47", out["loc.sum"])
 
 
 def main():

@@ -228,12 +228,12 @@ def when2com_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=
                          inference="activated", training=False, only_v2i=False, stages=False, has_query=True, layer=3):
     """det When2com.forward (When2com.py:150-332), MO_flag=True.  Eval-mode semantics: ``inference`` in {"softmax",
     "activated", "argmax_test"}; training=True stops after the first decoder pass.  ``has_query=False``: every agent's
-    query is a vector of ones (When2com.py:241-245).  ``layer`` in {2, 3}: the communicated encoder layer (:167-190; the
+    query is a vector of ones (When2com.py:241-245).  ``layer`` in {2, 3, 4}: the communicated encoder layer (:167-190; the
     reference's argmax_test branch only exists for layer 3, :289-291).  ``sparse`` is not a parameter: the reference hands
     it to the attention module, which never reads it (:374-412)."""
     enc = encode(bevs, sd, "u_encoder.")
     x, x_1, x_2, x_3, x_4 = enc
-    assert layer in (2, 3) and not (layer != 3 and inference == "argmax_test" and not training)
+    assert layer in (2, 3, 4) and not (layer != 3 and inference == "argmax_test" and not training)
     c, h, w = enc[layer].shape[1:]
     size = (1, c, h, w)
     feat = torch.flip(enc[layer], (2,))
@@ -271,9 +271,9 @@ def when2com_det_forward(bevs, trans_matrices, num_agent_tensor, sd, batch_size=
         return torch.flip(torch.cat([f[:, i] for i in range(agent_num)], 0), (2,))
 
     def dec(x0, fused):   # the fused map replaces the communicated layer (:262-270)
-        skips = [x0, x_1, x_2, x_3]
+        skips = [x0, x_1, x_2, x_3, x_4]
         skips[layer] = fused
-        return decode(*skips, x_4, sd, "decoder.")[0]
+        return decode(*skips, sd, "decoder.")[0]
 
     fuse1 = to_batch(weighted(attn))
     x_dec = dec(x, fuse1)

@@ -19,26 +19,7 @@ first_hardware_run = pytest.mark.xfail(strict=False, reason="first B200 run of t
                                        "budget was spent; oracle pinned and host wiring dry-run on the CPU)")
 
 
-@first_hardware_run
-@pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("tag", ["when2com_det_noquery_activated_seed41",
-                                 "when2com_det_layer2_sparse_activated_seed42_present4",
-                                 "when2com_det_layer2_noquery_nowarp_softmax_B2_seed43"])
-def test_when2com_det_options(tag, mode, golden_dir, parity_log):
-    """has_query=False (ones as every agent's query, When2com.py:241-245), sparse=True (a no-op in the reference,
-    :374-412) and layer=2 (:167-190), against the oracle and the live-reference fixtures."""
-    from test_gpu_nets import check_when2com_det
-    check_when2com_det(tag, mode, golden_dir, parity_log)
-
-
-@first_hardware_run
-@pytest.mark.parametrize("mode", MODES)
-def test_seg_when2com_options(mode, golden_dir, parity_log):
-    """seg When2Com_UNet(has_query=False, sparse=True) (When2Com_UNet.py:219-225, 408-446)."""
-    from test_gpu_seg import check_seg_model
-    check_seg_model("seg_when2com_noquery_sparse_activated_seed44", "when2com", mode, golden_dir, parity_log)
-
-
+# ---- host-logic refusals first: they launch no kernel, so nothing a later first-run case does can disturb them ----------
 def test_when2com_refuses_what_the_reference_cannot_run():
     """MO_flag=False and layer=2 + argmax_test raise in the reference itself (profiles/r02_reference_option_probe.txt)."""
     import torch
@@ -52,6 +33,40 @@ def test_when2com_refuses_what_the_reference_cannot_run():
             m(bevs.cuda(), trans.cuda(), nat.cuda(), training=False, MO_flag=False, batch_size=1)
         with pytest.raises(NotImplementedError):
             m(bevs.cuda(), trans.cuda(), nat.cuda(), training=False, inference="argmax_test", batch_size=1)
+
+
+def test_training_refuses_fewer_than_32_compressed_channels():
+    import torch
+    from coperception.models.det import V2VNet
+    from oracle import synth
+    from v2x_b200 import default_det_config
+    bevs, trans, nat = synth.make_scene(1, 5, 0)
+    m = V2VNet(default_det_config(), 3, 3, 256, num_agent=5, compress_level=4).cuda().train()
+    with pytest.raises(NotImplementedError):
+        m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+
+
+# ---- numerics cases ------------------------------------------------------------------------------------------------
+@first_hardware_run
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("tag", ["when2com_det_noquery_activated_seed41",
+                                 "when2com_det_layer2_sparse_activated_seed42_present4",
+                                 "when2com_det_layer2_noquery_nowarp_softmax_B2_seed43",
+                                 "when2com_det_layer4_activated_seed48"])
+def test_when2com_det_options(tag, mode, golden_dir, parity_log):
+    """has_query=False (ones as every agent's query, When2com.py:241-245), sparse=True (a no-op in the reference,
+    :374-412), layer=2 and layer=4 (:167-190; the fused 16x16 map reaches the decoder through DetPlan.upsample2), against
+    the oracle and the live-reference fixtures."""
+    from test_gpu_nets import check_when2com_det
+    check_when2com_det(tag, mode, golden_dir, parity_log)
+
+
+@first_hardware_run
+@pytest.mark.parametrize("mode", MODES)
+def test_seg_when2com_options(mode, golden_dir, parity_log):
+    """seg When2Com_UNet(has_query=False, sparse=True) (When2Com_UNet.py:219-225, 408-446)."""
+    from test_gpu_seg import check_seg_model
+    check_seg_model("seg_when2com_noquery_sparse_activated_seed44", "when2com", mode, golden_dir, parity_log)
 
 
 @first_hardware_run
@@ -126,12 +141,35 @@ def test_seg_unet_compressed_train_step_matches_oracle(golden_dir, parity_log):
     _check_buffers(tag, dict(model.named_buffers()), sd_after, parity_log, golden=golden, rtol=2e-5)
 
 
-def test_training_refuses_fewer_than_32_compressed_channels():
+@first_hardware_run
+@pytest.mark.parametrize("mode", MODES)
+def test_v2vnet_layer4(mode, golden_dir, parity_log):
+    """det V2VNet communicating at layer 4 (DetModelBase.py:71-92): 512-channel maps at 16 x 16, two GNN rounds, one
+    absent agent slot; the decoder reads the fused map 2x-upsampled (Backbone.py:176)."""
+    import os
+
+    import numpy as np
     import torch
     from coperception.models.det import V2VNet
-    from oracle import synth
+    from oracle import restate, synth
+    from test_gpu_nets import REL_TOL, _golden_sub, rel_err
     from v2x_b200 import default_det_config
-    bevs, trans, nat = synth.make_scene(1, 5, 0)
-    m = V2VNet(default_det_config(), 3, 3, 256, num_agent=5, compress_level=4).cuda().train()
-    with pytest.raises(NotImplementedError):
-        m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    tag = "layer4_v2vnet_det_seed47"
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    sd = synth.v2vnet_det_state(47, layer_channel=512)
+    bevs, trans, nat = synth.make_scene(1, 5, 47, present=[4])
+    with torch.no_grad():
+        ref = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=5, gnn_iter=2, layer=4)
+    m = V2VNet(default_det_config(), 2, 4, 512, num_agent=5)
+    m.load_state_dict(sd, strict=True)
+    m.precision = mode
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    torch.cuda.synchronize()
+    rec = {}
+    for k in ("loc", "cls"):
+        rec[k], rec[k + "_golden"] = rel_err(out[k], ref[k]), _golden_sub(out[k], g, k)
+    parity_log(tag, mode, **rec)
+    print("v2vnet@4 %s: %s" % (mode, rec))
+    assert all(v < REL_TOL[mode] for v in rec.values()), rec

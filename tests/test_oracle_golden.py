@@ -84,7 +84,7 @@ WHEN2COM_DET_FIXTURES = ["when2com_det_warp_activated_seed2", "when2com_det_nowa
                          "when2com_det_warp_softmax_B2_seed4",
                          # constructor options beside the scripts' defaults (oracle/gen_golden.py::gen_options)
                          "when2com_det_noquery_activated_seed41", "when2com_det_layer2_sparse_activated_seed42_present4",
-                         "when2com_det_layer2_noquery_nowarp_softmax_B2_seed43"]
+                         "when2com_det_layer2_noquery_nowarp_softmax_B2_seed43", "when2com_det_layer4_activated_seed48"]
 
 
 def when2com_options(g):
@@ -221,6 +221,13 @@ def test_other_communication_layers(golden_dir):
     bevs, trans, nat = synth.make_scene(1, 5, 18, present=[4])
     with torch.no_grad():
         r = restate.v2vnet_det_forward(bevs, trans, nat, sd, batch_size=1, agent_num=5, gnn_iter=2, layer=2)
+    _check("loc", r["loc"], g)
+    _check("cls", r["cls"], g)
+    g = np.load(os.path.join(golden_dir, "layer4_v2vnet_det_seed47.npz"))       # 512 channels at 16 x 16
+    bevs, trans, nat = synth.make_scene(1, 5, 47, present=[4])
+    with torch.no_grad():
+        r = restate.v2vnet_det_forward(bevs, trans, nat, synth.v2vnet_det_state(47, layer_channel=512), batch_size=1,
+                                       agent_num=5, gnn_iter=2, layer=4)
     _check("loc", r["loc"], g)
     _check("cls", r["cls"], g)
     g = np.load(os.path.join(golden_dir, "layer2_disco_det_seed19.npz"))

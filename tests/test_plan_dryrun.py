@@ -70,20 +70,24 @@ def test_fake_library_rejects_a_wrong_call(fake):
         fake.v2x_maxpool2_fwd(None, None, 1.5, 2, 3, 4, 5, None)    # a float where the header declares int32_t
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(layer=2), dict(layer=1), dict(compress=2), dict(compress=6), dict(input_mode="u8"),
+@pytest.mark.parametrize("kw", [dict(), dict(layer=2), dict(layer=1), dict(layer=4), dict(layer=4, planes="bf16"), dict(compress=2),
+                                dict(compress=6), dict(input_mode="u8"),
                                 dict(input_mode="voxels"), dict(only_v2i=True, planes="bf16"), dict(planes="fp16x3")],
                          ids=lambda k: "-".join("%s=%s" % kv for kv in k.items()) or "default")
 def test_v2vnet_det_plan_wiring(fake, kw):
     from v2x_b200 import nets
     kw = dict(kw)
     compress, layer = kw.pop("compress", 0), kw.get("layer", 3)
-    sd = synth.v2vnet_det_state(1, layer_channel=(32, 64, 128, 256)[layer], compress_level=compress)
+    sd = synth.v2vnet_det_state(1, layer_channel=(32, 64, 128, 256, 512)[layer], compress_level=compress)
     plan = nets.V2VNetDetPlan(sd, 2, 5, device="cpu", **dict(dict(planes="mixed"), **kw))
     _issue(plan)
     assert fake.calls["v2x_conv_fwd"] >= 25 and fake.calls["v2x_warp_mean_fwd"] == 1
     out = plan.result()
     assert tuple(out["loc"].shape) == (10, 256, 256, 6, 1, 6) and tuple(out["cls"].shape) == (10, 256 * 256 * 6, 2)
     assert ("x3d" in plan.ws) == (compress > 0)
+    if layer == 4:     # the GNN block runs on the plain 16x16 x_4; the decoder reads the fused map through the upsampling store
+        assert tuple(plan.ws["mean"].shape[2:]) == (16, 16, 512) and tuple(plan.ws["x4u"].shape[2:]) == (32, 32, 512)
+        assert not plan.gru_h.gru_pre_act and plan.side_lo < 0
 
 
 def test_fafnet_and_teacher_plan_wiring(fake):
@@ -97,7 +101,7 @@ def test_fafnet_and_teacher_plan_wiring(fake):
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(inference="softmax"), dict(inference="argmax_test", warp_flag=0),
-                                dict(training_pass_only=True), dict(has_query=False), dict(layer=2),
+                                dict(training_pass_only=True), dict(has_query=False), dict(layer=2), dict(layer=4),
                                 dict(layer=2, has_query=False, inference="softmax", warp_flag=0)],
                          ids=lambda k: "-".join("%s=%s" % kv for kv in k.items()) or "default")
 def test_when2com_det_plan_wiring(fake, kw):
@@ -110,7 +114,9 @@ def test_when2com_det_plan_wiring(fake, kw):
     assert fake.calls["v2x_warp_gated_fwd"] == (2 if two_pass else 1)
     assert fake.calls["v2x_linear_fwd"] == (6 if has_query else 3)       # key MLP (+ query MLP)
     layer = kw.get("layer", 3)
-    assert tuple(plan.ws["fuse1"].shape[2:]) == ((64, 64, 128) if layer == 2 else (32, 32, 256))
+    assert tuple(plan.ws["fuse1"].shape[2:]) == {2: (64, 64, 128), 3: (32, 32, 256), 4: (16, 16, 512)}[layer]
+    if layer == 4:
+        assert tuple(plan.ws["fuse1u"].shape[2:]) == (32, 32, 512) and tuple(plan.ws["fuse2u"].shape[2:]) == (32, 32, 512)
     if not has_query:
         assert bool((plan.querys == 1).all()) and tuple(plan.querys.shape) == (5, 32)
 
@@ -121,7 +127,11 @@ def test_when2com_det_plan_refuses_what_the_reference_cannot_run(fake):
     with pytest.raises(ops.V2XError):
         nets.When2comDetPlan(sd, 1, 5, device="cpu", layer=2, inference="argmax_test")
     with pytest.raises(ops.V2XError):
-        nets.When2comDetPlan(sd, 1, 5, device="cpu", layer=4)
+        nets.When2comDetPlan(sd, 1, 5, device="cpu", layer=4, inference="argmax_test")
+    with pytest.raises(ops.V2XError):
+        nets.When2comDetPlan(sd, 1, 5, device="cpu", layer=1)
+    with pytest.raises(ops.V2XError):      # the ConvGRU tile needs a multiple of 64 channels: layer 0 has 32
+        nets.V2VNetDetPlan(synth.v2vnet_det_state(3, layer_channel=32), 1, 5, device="cpu", layer=0)
 
 
 @pytest.mark.parametrize("kind", ["mean", "sum", "max", "cat", "agent", "disco"])

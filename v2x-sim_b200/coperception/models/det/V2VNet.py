@@ -16,8 +16,8 @@ class V2VNet(B200DetModel):
     def __init__(self, config, gnn_iter_times, layer, layer_channel, in_channels=13, num_agent=5, compress_level=0,
                  only_v2i=False):
         super().__init__(config, layer, in_channels, num_agent=num_agent, only_v2i=only_v2i)
-        if layer not in (1, 2, 3) or layer_channel != (32, 64, 128, 256, 512)[layer]:
-            raise NotImplementedError("v2x_b200 V2VNet communicates at layer 1, 2 or 3 with layer_channel = 64 / 128 / 256 "
+        if layer not in (1, 2, 3, 4) or layer_channel != (32, 64, 128, 256, 512)[layer]:
+            raise NotImplementedError("v2x_b200 V2VNet communicates at layer 1..4 with layer_channel = 64 / 128 / 256 / 512 "
                                       "(the reference scripts use layer 3, train_codet.py:106-114)")
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)

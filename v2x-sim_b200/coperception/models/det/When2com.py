@@ -54,8 +54,8 @@ class When2com(B200DetModel):
                  has_query=True, sparse=False, layer=3, warp_flag=1, image_size=512, shared_img_encoder="unified",
                  key_size=1024, query_size=32, num_agent=5, compress_level=0, only_v2i=False):
         super().__init__(config, layer, in_channels, num_agent=num_agent, only_v2i=only_v2i)
-        if layer not in (2, 3):
-            raise NotImplementedError("v2x_b200 When2com communicates at layer 2 or 3 (the reference scripts use 3)")
+        if layer not in (2, 3, 4):
+            raise NotImplementedError("When2com communicates at layer 2, 3 or 4 (When2com.py:167-190)")
         self.compress_level = compress_level
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)

@@ -132,6 +132,17 @@ class DetPlan:
         self.add(ConvLaunch(pc, srcs, out0=out, upsample2x=upsample2x, **kw))
         return out
 
+    def upsample2(self, x, out_name):
+        """Nearest 2x upsampling of an act through the conv kernel's upsampling store: a 1x1 identity operand without
+        ReLU.  Exact in every mode (bf16: v * 1; fp16 hi/lo: hi * 1 + lo * 1 in the fp32 accumulator, re-split on store).
+        Used where a FUSED layer-4 map feeds the decoder, which reads layer 4 only through F.interpolate(x_4, 2)
+        (Backbone.py:176); the un-fused x_4 is stored upsampled by its producer instead (build_encoder)."""
+        c = x.shape[-1]
+        eye = torch.eye(c, dtype=torch.float32, device=self.device).view(c, c, 1, 1)
+        pc = ops.pack_conv(eye, None, None, cins=[c], planes=self.planes, device=self.device,
+                           mmas=3 if self.planes == 2 else 1)
+        return self.conv(pc, [x], out_name, relu=False, upsample2x=True)
+
     def check_voxels(self):
         """Voxel mode: raise (like numpy's IndexError at V2XSimDet.py:296) if any uploaded row was out of range.
         Reads one device int32 -- a host sync, so callers on a latency-critical loop may skip it."""
@@ -310,24 +321,27 @@ class V2VNetDetPlan(DetPlan):
                  only_v2i=False, input_mode="f32", voxel_capacity=0, layer: int = 3):
         super().__init__(batch * agents, planes, device)
         prec, planes = self.prec, self.prec.planes
-        if layer not in (1, 2, 3):
-            raise ops.V2XError("V2VNet on the sm_100a path communicates at layer 1, 2 or 3 (the ConvGRU tile needs a "
-                               "multiple of 64 channels; layer 4 only exists 2x-upsampled in the workspace)")
+        if layer not in (1, 2, 3, 4):
+            raise ops.V2XError("V2VNet on the sm_100a path communicates at layer 1..4 (the ConvGRU tile needs a multiple "
+                               "of 64 channels: layer 0 has 32)")
         ops.require_gpu()
         self.batch, self.agents, self.gnn_iter = batch, agents, gnn_iter
         dev = self.device
         self.enc_w = BackboneWeights(sd, "u_encoder.", prec, dev, encoder=True, decoder=False)
         self.dec_w = BackboneWeights(sd, "decoder.", prec, dev, encoder=False, decoder=True)
         self.head_w = HeadWeights(sd, prec, dev)
+        # (the 512-channel layer-4 GRU takes the fp32 pre-activation form, like the seg V2VNet's 512-channel GRU)
         self.gru_h, self.gru_m = ops.pack_gru_split(sd["convgru.weight_ih_l0"], sd["convgru.bias_ih_l0"],
                                                     sd["convgru.bias_hh_l0"], planes=planes, device=dev,
-                                                    pre_act=GRU_PRE_ACT and planes == 1, mmas=prec.mmas("gru"))
+                                                    pre_act=GRU_PRE_ACT and planes == 1 and layer != 4,
+                                                    mmas=prec.mmas("gru"))
         self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
 
         x_in = self.build_input(input_mode, voxel_capacity)
-        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
-        xs = [x0, x1, x2, x3]
+        # layer 4: the GNN block needs the plain 16x16 x_4; the decoder gets the fused map upsampled afterwards
+        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in, upsample_x4=(layer != 4))
+        xs = [x0, x1, x2, x3, x4u]
         xl = xs[layer]              # the communicated layer (DetModelBase.get_feature_maps_and_size, :71-92)
         cl, hl, wl = xl.shape[-1], xl.shape[2], xl.shape[3]
         # neighbours are always warped from the ORIGINAL encoder maps (V2VNet.py:85-94), so the mean is
@@ -341,7 +355,9 @@ class V2VNetDetPlan(DetPlan):
         if layer == 3 and "com_compresser" not in self.enc_w.c:
             self.side_lo, self.side_hi = self.x4_branch
             self.side_join = len(self.launches)
-        x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], x4u)
+        if layer == 4:
+            xs[4] = self.upsample2(xs[4], "x4u")
+        x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], xs[4])
         self.build_heads(self.head_w, x8)
 
     def set_inputs(self, bevs, trans_matrices, num_agent_tensor):
@@ -394,9 +410,8 @@ class When2comDetPlan(DetPlan):
                  inference="activated", training_pass_only=False, only_v2i=False, has_query=True, layer: int = 3):
         super().__init__(batch * agents, planes, device)
         prec, planes = self.prec, self.prec.planes
-        if layer not in (2, 3):
-            raise ops.V2XError("When2com on the sm_100a path communicates at layer 2 or 3 (layer 4 only exists "
-                               "2x-upsampled in the workspace)")
+        if layer not in (2, 3, 4):
+            raise ops.V2XError("When2com communicates at layer 2, 3 or 4 (When2com.py:167-190)")
         if layer != 3 and inference == "argmax_test" and not training_pass_only:
             raise ops.V2XError("argmax_test only exists for layer 3 in the reference (When2com.py:289-291)")
         ops.require_gpu()
@@ -424,7 +439,8 @@ class When2comDetPlan(DetPlan):
         trans, na, n = self.trans, self.num_agent, self.n
 
         x_in = self.build_input()
-        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
+        # layer 4: the fuse reads the plain 16x16 x_4; the decoder gets each fused map upsampled (DetPlan.upsample2)
+        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in, upsample_x4=(layer != 4))
         # ---- policy branch: second encoder's x_4 -> 5 convs -> [N,4,4,256] -> key / query MLPs ----
         t = self.build_encoder(self.pol_w, x_in, tag="pol_", upsample_x4=False)[4]
         for i, pc in enumerate(self.pol_convs):
@@ -448,20 +464,21 @@ class When2comDetPlan(DetPlan):
         keys, querys, attn, coef, aw, ab = self.keys, self.querys, self.attn, self.coef, self.att_w, self.att_b
         self.add(lambda: ops.attn_scores(keys, querys, aw, ab, batch, agents, gate, attn=attn, coef=coef))
         # ---- pass 1: softmax-weighted fuse of the communicated layer -> decoder ----
-        xs = [x0, x1, x2, x3]
+        xs = [x0, x1, x2, x3, x4u]
         xl = xs[layer]
         cl, hl, wl = xl.shape[-1], xl.shape[2], xl.shape[3]
         fuse1 = self.act("fuse1", hl, wl, cl)
         self.add(lambda: ops.warp_gated(xl, trans, na, attn, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i,
                                         out=fuse1))
-        xs[layer] = fuse1
-        x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], x4u)
+        xs[layer] = fuse1 if layer != 4 else self.upsample2(fuse1, "fuse1u")
+        x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], xs[4])
         if not training_pass_only and inference != "softmax":
             fuse2 = self.act("fuse2", hl, wl, cl)
             self.add(lambda: ops.warp_gated(xl, trans, na, coef, batch, agents, warp_flag=warp_flag, only_v2i=only_v2i,
                                             out=fuse2))
-            xs[0], xs[layer] = x8, fuse2     # the layer-0 skip of the second pass is the first pass's output (:266-270)
-            x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], x4u, tag="p2_")
+            # the layer-0 skip of the second pass is the first pass's output (:266-270)
+            xs[0], xs[layer] = x8, (fuse2 if layer != 4 else self.upsample2(fuse2, "fuse2u"))
+            x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], xs[4], tag="p2_")
         self.build_heads(self.head_w, x8)
 
     def forward(self, bevs, trans_matrices, num_agent_tensor):
