@@ -58,7 +58,7 @@ def pytest_sessionfinish(session, exitstatus):
         return
     out_dir = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
-    path = os.path.join(out_dir, "parity.json")
+    path = os.path.join(out_dir, os.environ.get("V2X_PARITY_FILE", "parity.json"))   # child runs write their own file
     prev = []
     if os.path.exists(path) and os.environ.get("V2X_PARITY_APPEND"):
         prev = json.load(open(path))["records"]

@@ -238,3 +238,29 @@ def test_peer_exchange_protocol_is_deadlock_free_and_never_overwrites_unread_map
                     done_steps[r] += 1
                 pc[r] = (pc[r] + 1) % 5
             assert step == [steps] * world
+
+
+def test_child_runner_isolates_pass_fail_and_hang(tmp_path):
+    """tests/child_run.py (used by the never-run-on-hardware GPU cases): a passing selection passes, a failing one
+    reports its exit status, one that only skips is not a pass, and one that never returns is killed at the time limit."""
+    import time
+    sys_path = os.path.join(ROOT, "tests")
+    import sys
+    if sys_path not in sys.path:
+        sys.path.insert(0, sys_path)
+    from child_run import ran_and_passed, run_in_child
+    f = tmp_path / "test_tmp_cases.py"
+    f.write_text("import time, pytest\n"
+                 "def test_ok():\n    assert True\n"
+                 "def test_bad():\n    assert False\n"
+                 "def test_skip():\n    pytest.skip('no')\n"
+                 "def test_hang():\n    time.sleep(600)\n")
+    rc, tail = run_in_child(str(f), "test_ok", str(tmp_path / "ok.log"), 120)
+    assert ran_and_passed(rc, tail), tail
+    rc, tail = run_in_child(str(f), "test_bad", str(tmp_path / "bad.log"), 120)
+    assert rc == 1 and not ran_and_passed(rc, tail)
+    rc, tail = run_in_child(str(f), "test_skip", str(tmp_path / "skip.log"), 120)
+    assert rc == 0 and not ran_and_passed(rc, tail)
+    t0 = time.time()
+    rc, tail = run_in_child(str(f), "test_hang", str(tmp_path / "hang.log"), 8)
+    assert rc == "time limit of 8 s" and time.time() - t0 < 60 and not ran_and_passed(rc, tail)
