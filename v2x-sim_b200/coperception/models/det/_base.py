@@ -97,7 +97,7 @@ class PlanCacheMixin:
         if not self._warned_grad and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             self._warned_grad = True
             warnings.warn("%s: the sm_100a forward is computed by custom kernels and its outputs carry no autograd graph; "
-                          "call it under torch.no_grad() (training through this path is not built)" % type(self).__name__,
+                          "call it under torch.no_grad(), or model.train() for the training step" % type(self).__name__,
                           stacklevel=3)
 
     def _state(self):
@@ -160,7 +160,10 @@ class B200DetModel(PlanCacheMixin, nn.Module):
 
     def _check_eval(self):
         if self.training:
-            raise NotImplementedError(
-                "the sm_100a path implements inference (model.eval()); the training/backward step "
-                "(SURVEY.md section 8(f1)) is not built yet")
+            raise NotImplementedError("%s only implements inference (model.eval()) on the sm_100a path"
+                                      % type(self).__name__)
+        if self.p_com_outage:
+            # DetModelBase.outage() (DetModelBase.py:129-137) draws from numpy's global RNG per agent and round; the
+            # reference default is 0.0 and no model constructor exposes it
+            raise NotImplementedError("communication outage (p_com_outage > 0) is not built on the sm_100a path")
         self._warn_no_grad_graph()
