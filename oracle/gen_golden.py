@@ -488,6 +488,19 @@ def gen_options():
     summarize("cls", r["cls"], out)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "layer4_v2vnet_det_seed47.npz"), **out)
     print("layer4_v2vnet_det_seed47", out["loc.sum"])
+    # parameter-free fusion at layer 4 (the weight nets of Cat / AgentWise / DiscoNet only exist for layers 3 / 2)
+    m = ref_loader.ref_fusion_det("sum", layer=4)
+    sd = synth.fusion_det_state("sum", 49)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    bevs, trans, nat = synth.make_scene(1, 5, 49, present=[3])
+    with torch.no_grad():
+        r = m(bevs, trans, nat, batch_size=1)
+    out = {"meta": np.asarray([1, 5, 49, 4], dtype=np.int64)}
+    summarize("loc", r["loc"], out)
+    summarize("cls", r["cls"], out)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "layer4_sum_det_seed49.npz"), **out)
+    print("layer4_sum_det_seed49", out["loc.sum"])
 
 
 def main():

@@ -26,7 +26,7 @@ in_child_only = pytest.mark.skipif(not CHILD, reason="runs in a child process: t
 first_hardware_run = in_child_only      # the numerics cases below carry this marker
 
 GROUPS = ["test_when2com_det_options", "test_seg_when2com_options", "test_v2vnet_compressed_train_step_matches_oracle",
-          "test_seg_unet_compressed_train_step_matches_oracle", "test_v2vnet_layer4"]
+          "test_seg_unet_compressed_train_step_matches_oracle", "test_v2vnet_layer4", "test_sum_fusion_layer4"]
 CHILD_TIME_LIMIT_S = 600
 
 
@@ -199,4 +199,37 @@ def test_v2vnet_layer4(mode, golden_dir, parity_log):
         rec[k], rec[k + "_golden"] = rel_err(out[k], ref[k]), _golden_sub(out[k], g, k)
     parity_log(tag, mode, **rec)
     print("v2vnet@4 %s: %s" % (mode, rec))
+    assert all(v < REL_TOL[mode] for v in rec.values()), rec
+
+
+@first_hardware_run
+@pytest.mark.parametrize("mode", MODES)
+def test_sum_fusion_layer4(mode, golden_dir, parity_log):
+    """SumFusion at layer 4 (FusionBase.py:23-75 with DetModelBase.py:71-92): 512-channel 16 x 16 maps, two absent slots."""
+    import os
+
+    import numpy as np
+    import torch
+    from coperception.models.det import SumFusion
+    from oracle import restate, synth
+    from test_gpu_nets import REL_TOL, _golden_sub, rel_err
+    from v2x_b200 import default_det_config
+    tag = "layer4_sum_det_seed49"
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    sd = synth.fusion_det_state("sum", 49)
+    bevs, trans, nat = synth.make_scene(1, 5, 49, present=[3])
+    with torch.no_grad():
+        ref = restate.fusion_det_forward("sum", bevs, trans, nat, sd, batch_size=1, agent_num=5, layer=4)
+    m = SumFusion(default_det_config(), layer=4, kd_flag=0, num_agent=5)
+    m.load_state_dict(sd, strict=True)
+    m.precision = mode
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(bevs.cuda(), trans.cuda(), nat.cuda(), batch_size=1)
+    torch.cuda.synchronize()
+    rec = {}
+    for k in ("loc", "cls"):
+        rec[k], rec[k + "_golden"] = rel_err(out[k], ref[k]), _golden_sub(out[k], g, k)
+    parity_log(tag, mode, **rec)
+    print("sum@4 %s: %s" % (mode, rec))
     assert all(v < REL_TOL[mode] for v in rec.values()), rec

@@ -230,6 +230,13 @@ def test_other_communication_layers(golden_dir):
                                        agent_num=5, gnn_iter=2, layer=4)
     _check("loc", r["loc"], g)
     _check("cls", r["cls"], g)
+    g = np.load(os.path.join(golden_dir, "layer4_sum_det_seed49.npz"))
+    bevs, trans, nat = synth.make_scene(1, 5, 49, present=[3])
+    with torch.no_grad():
+        r = restate.fusion_det_forward("sum", bevs, trans, nat, synth.fusion_det_state("sum", 49), batch_size=1, agent_num=5,
+                                       layer=4)
+    _check("loc", r["loc"], g)
+    _check("cls", r["cls"], g)
     g = np.load(os.path.join(golden_dir, "layer2_disco_det_seed19.npz"))
     bevs, trans, nat = synth.make_scene(1, 5, 19)
     with torch.no_grad():

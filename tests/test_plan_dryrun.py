@@ -141,10 +141,13 @@ def test_fusion_det_plan_wiring(fake, kind):
     plan = nets.FusionDetPlan(sd, kind, 1, 5, planes="mixed", device="cpu")
     _issue(plan)
     assert tuple(plan.fused.shape) == (2, 5, 32, 32, 256)
-    if kind in ("mean", "sum", "max"):      # parameter-free rules also run at the shallower layers
+    if kind in ("mean", "sum", "max"):      # parameter-free rules also run at the other layers
         plan = nets.FusionDetPlan(sd, kind, 1, 5, planes="mixed", device="cpu", layer=1)
         _issue(plan)
         assert tuple(plan.fused.shape) == (2, 5, 128, 128, 64)
+        plan = nets.FusionDetPlan(sd, kind, 1, 5, planes="mixed", device="cpu", layer=4)
+        _issue(plan)
+        assert tuple(plan.fused.shape) == (2, 5, 16, 16, 512) and tuple(plan.ws["x4u"].shape) == (2, 5, 32, 32, 512)
 
 
 def test_seg_plan_wiring(fake):

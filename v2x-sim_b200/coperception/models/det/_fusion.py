@@ -31,8 +31,8 @@ class FusionBase(B200DetModel):
 
     def __init__(self, config, layer=3, in_channels=13, kd_flag=True, num_agent=5, compress_level=0, only_v2i=False):
         super().__init__(config, layer, in_channels, kd_flag, num_agent=num_agent, only_v2i=only_v2i)
-        if layer not in (0, 1, 2, 3):
-            raise NotImplementedError("v2x_b200 fusion models fuse at layer 0..3 (the reference scripts use layer 3)")
+        if layer not in (0, 1, 2, 3, 4):
+            raise NotImplementedError("fusion models fuse at layer 0..4 (DetModelBase.py:71-92)")
         self.compress_level = compress_level
         self.u_encoder = BackboneParams(in_channels, compress_level)
         self.decoder = BackboneParams(in_channels)

@@ -870,8 +870,8 @@ class FusionDetPlan(DetPlan):
                  layer: int = 3):
         super().__init__(batch * agents, planes, device)
         prec, planes = self.prec, self.prec.planes
-        if layer not in (0, 1, 2, 3):
-            raise ops.V2XError("fusion models on the sm_100a path fuse at layer 0..3 (layer 4 only exists 2x-upsampled)")
+        if layer not in (0, 1, 2, 3, 4):
+            raise ops.V2XError("fusion models fuse at layer 0..4 (DetModelBase.py:71-92)")
         ops.require_gpu()
         self.batch, self.agents, self.kind = batch, agents, kind
         dev = self.device
@@ -881,11 +881,14 @@ class FusionDetPlan(DetPlan):
         self.trans = torch.zeros((batch, agents, agents, 4, 4), dtype=torch.float64, device=dev)
         self.num_agent = torch.full((batch, agents), agents, dtype=torch.int64, device=dev)
         x_in = self.build_input()
-        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in)
-        xs = [x0, x1, x2, x3]
+        # layer 4: the fuse reads the plain 16x16 x_4; the decoder gets the fused map upsampled (DetPlan.upsample2)
+        x0, x1, x2, x3, x4u = self.build_encoder(self.enc_w, x_in, upsample_x4=(layer != 4))
+        xs = [x0, x1, x2, x3, x4u]
         self.fuse = FuseStage(self, kind, sd, xs[layer], self.trans, self.num_agent, batch, agents, only_v2i=only_v2i)
         self.fused = xs[layer] = self.fuse.out
-        x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], x4u)
+        if layer == 4:
+            xs[4] = self.upsample2(self.fused, "x4u")
+        x8 = self.build_decoder(self.dec_w, xs[0], xs[1], xs[2], xs[3], xs[4])
         self.build_heads(self.head_w, x8)
 
     def forward(self, bevs, trans_matrices, num_agent_tensor):
