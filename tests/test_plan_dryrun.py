@@ -255,6 +255,29 @@ def test_fusion_train_tape_wiring(fake, kind):
     assert "u_encoder.com_decompresser.weight" in got and "decoder.conv8_2.weight" in got
 
 
+def test_train_tape_option_combinations(fake):
+    """kd_flag = 1 outputs with upstream gradients, only_v2i, when2com without the warp and with compression."""
+    from coperception.models import det as det_models
+    from v2x_b200 import default_det_config
+    from v2x_b200.train import FusionTrainStep, When2comTrainStep
+    cfg = default_det_config()
+    bevs, trans, nat = synth.make_scene(1, 5, 8, present=[4])
+    for cls, kind in (("MaxFusion", "max"), ("DiscoNet", "disco")):
+        m = getattr(det_models, cls)(cfg, layer=3, kd_flag=1, num_agent=5, only_v2i=True).train()
+        params = [p.detach().requires_grad_(True) for p in m.parameters()]
+        outs = FusionTrainStep.apply(m, kind, bevs, trans, nat, 1, *params)
+        assert len(outs) == 7      # loc, cls, x_8, x_7, x_6, x_5, fused (FusionBase.py:72-73)
+        assert [tuple(o.shape[1:]) for o in outs[2:]] == [(32, 256, 256), (64, 128, 128), (128, 64, 64), (256, 32, 32),
+                                                          (256, 32, 32)]
+        torch.autograd.backward(list(outs), [torch.full_like(o, 1e-3) for o in outs])
+        assert params[0].grad is not None
+    m = det_models.When2com(cfg, layer=3, warp_flag=0, num_agent=5, compress_level=2).train()
+    grads = _det_step(When2comTrainStep, m, (bevs, trans, nat, 1), 5)
+    names = [k for k, _ in m.named_parameters()]
+    got = {k for k, g in zip(names, grads) if g is not None}
+    assert {"u_encoder.com_compresser.weight", "attention_net.linear.bias"} <= got
+
+
 @pytest.mark.parametrize("case", ["unet", "unet_c3", "v2v", "when2com", "mean", "cat"])
 def test_seg_train_tape_wiring(fake, case):
     from coperception.models import seg as seg_models
