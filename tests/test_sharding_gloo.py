@@ -138,3 +138,75 @@ def test_neighbour_exchange_over_gloo_world4():
         p.join(300)
         assert p.exitcode == 0
     assert all(ret[r] for r in range(4))
+
+
+def _worker_plans(rank, world, port, ret):
+    """Both unit-sharded PLAN classes on two ranks: kernels replaced by a fake library that validates every ctypes call
+    (tests/test_plan_dryrun.py), collectives real (gloo).  What crosses the wire is marked by rank so the exchange wiring
+    -- which buffer, which unit rows, which planes -- is checked exactly."""
+    import ctypes as C
+    for p in (ROOT, os.path.join(ROOT, "v2x-sim_b200"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import synth
+        from test_plan_dryrun import FakeLib
+        from v2x_b200 import nets, ops
+        torch.set_num_threads(2)
+        fake = FakeLib()
+        ops.require_gpu = lambda: fake
+        ops._stream = lambda: C.c_void_p(0)
+        torch.Tensor.is_cuda = property(lambda self: True)
+        B, A = 2, 5                       # 10 units, 5 per rank
+        res = {}
+        for exchange in ("allgather", "neighbours"):
+            plan = nets.V2VNetDetShardedPlan(synth.v2vnet_det_state(1), B, A, rank, world, planes="mixed", device="cpu",
+                                             exchange=exchange)
+            bevs, trans, nat = synth.make_scene(B, A, 1)
+            plan.x3_local.fill_(float(rank + 1))          # stands in for this rank's encoder output
+            plan.x3_all.zero_()
+            out = plan.forward(bevs[plan.offset:plan.offset + plan.n], trans, nat)
+            n = plan.n
+            hi, lo = plan.x3_all[0].float(), plan.x3_all[1].float()
+            own = slice(rank * n, rank * n + n)
+            other = slice((1 - rank) * n, (1 - rank) * n + n)
+            res[exchange] = (tuple(out["cls"].shape) == (n, 256 * 256 * 6, 2)
+                             and bool((hi[own] == rank + 1).all()) and bool((lo[own] == rank + 1).all())      # own units: both planes
+                             and bool((hi[other] == 2 - rank).all()) and bool((lo[other] == 0).all()))       # remote: hi plane only
+        for warp_flag in (1, 0):
+            plan = nets.When2comDetShardedPlan(synth.when2com_det_state(3), B, A, rank, world, planes="mixed", device="cpu",
+                                               warp_flag=warp_flag)
+            bevs, trans, nat = synth.make_scene(B, A, 3)
+            plan.keys_local.fill_(float(rank + 1))
+            plan.querys_local.fill_(float(10 * (rank + 1)))
+            plan.x3_local.fill_(float(rank + 1))
+            out = plan.forward(bevs[plan.offset:plan.offset + plan.n], trans, nat)
+            n = plan.n
+            ok = tuple(plan.keys.shape) == (B * A, 1024) and tuple(plan.querys.shape) == (B * A, 32)
+            for r in range(world):
+                ok = ok and bool((plan.keys[r * n:(r + 1) * n] == r + 1).all()) and bool((plan.querys[r * n:(r + 1) * n] == 10 * (r + 1)).all())
+            if not warp_flag:             # without the warp every agent's map is read: x_3 crosses the wire too
+                ok = ok and all(bool((plan.x3_all[:, r * n:(r + 1) * n].float() == r + 1).all()) for r in range(world))
+            else:
+                ok = ok and not hasattr(plan, "x3_all")
+            res["w2c%d" % warp_flag] = ok and tuple(out["loc"].shape) == (n, 256, 256, 6, 1, 6)
+        ret[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_plans_exchange_the_right_rows():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 30100 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_worker_plans, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    for r in range(2):
+        assert all(ret[r].values()), (r, dict(ret[r]))
