@@ -264,3 +264,33 @@ def test_child_runner_isolates_pass_fail_and_hang(tmp_path):
     t0 = time.time()
     rc, tail = run_in_child(str(f), "test_hang", str(tmp_path / "hang.log"), 8)
     assert rc == "time limit of 8 s" and time.time() - t0 < 60 and not ran_and_passed(rc, tail)
+
+
+def test_plan_cache_is_bounded_and_least_recently_used():
+    """The module keeps at most ``max_plans`` plans (each owns GBs of static workspace): a hit refreshes its key, the
+    least recently used one is dropped, the set of static output pointers follows the live plans."""
+    m = _v2v()
+    m.use_cuda_graph = False
+    m.max_plans = 2
+
+    class P:
+        def __init__(self, tag):
+            self.tag, self.loc = tag, torch.zeros(4)
+
+    built = []
+
+    def factory(tag):
+        def f():
+            built.append(tag)
+            return P(tag)
+        return f
+    a = m._get_plan("a", factory("a"))
+    b = m._get_plan("b", factory("b"))
+    assert m._get_plan("a", factory("a2")) is a and built == ["a", "b"]          # hit: nothing rebuilt, "a" is now freshest
+    c = m._get_plan("c", factory("c"))
+    assert list(m._plans) == ["a", "c"]                                          # "b" was the least recently used
+    assert m._static_ptrs == {a.loc.data_ptr(), c.loc.data_ptr()} and b.loc.data_ptr() not in m._static_ptrs
+    with torch.no_grad():
+        m.classification.conv2.bias.add_(1.0)                                    # weights changed: the key is rebuilt
+    a2 = m._get_plan("a", factory("a3"))
+    assert a2 is not a and built[-1] == "a3" and list(m._plans) == ["c", "a"]

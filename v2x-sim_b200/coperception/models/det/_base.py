@@ -57,6 +57,10 @@ class PlanCacheMixin:
         self.use_cuda_graph = os.environ.get("V2X_CUDA_GRAPH", "1") != "0"
         self.alias_outputs = False
         self.verify_weights = os.environ.get("V2X_VERIFY_WEIGHTS", "0") == "1"
+        # a plan owns a static workspace of a few GB (B = 8: ~3.5 GB); callers that vary the batch size or the inference
+        # mode would otherwise accumulate one per key for the life of the module: least-recently-used plans beyond this
+        # many are dropped (their memory returns to torch's allocator once the caller holds no aliased output)
+        self.max_plans = int(os.environ.get("V2X_MAX_PLANS", "8"))
         self._plans = {}
         self._static_ptrs = set()     # data_ptr of every plan's static output buffers
         self._warned_grad = False
@@ -105,17 +109,23 @@ class PlanCacheMixin:
 
     def _get_plan(self, key, factory):
         fp = self._fingerprint()
-        hit = self._plans.get(key)
+        hit = self._plans.pop(key, None)
         if hit is not None and hit[0] == fp:
+            self._plans[key] = hit          # re-inserted at the end: dicts keep insertion order, the front is the LRU
             return hit[1]
+        del hit                             # a stale plan (weights changed) is released before its successor is built
         plan = factory()
         if self.use_cuda_graph:
             plan.capture()
         self._plans[key] = (fp, plan)
-        for name in ("loc", "cls", "logits"):
-            t = getattr(plan, name, None)
-            if isinstance(t, torch.Tensor):
-                self._static_ptrs.add(t.data_ptr())
+        while len(self._plans) > max(1, self.max_plans):
+            self._plans.pop(next(iter(self._plans)))
+        self._static_ptrs = set()
+        for _, live in self._plans.values():
+            for name in ("loc", "cls", "logits"):
+                t = getattr(live, name, None)
+                if isinstance(t, torch.Tensor):
+                    self._static_ptrs.add(t.data_ptr())
         return plan
 
     def _plan_list(self):
