@@ -52,7 +52,7 @@ def test_fafnet_module_kd_outputs():
 
 def test_train_mode_is_refused_where_not_built():
     """Every det model class and every seg class but DiscoNet trains on the sm_100a path (tests/test_gpu_train.py); what is
-    not built refuses loudly instead of silently doing something else: training with compress_level > 0, seg DiscoNet, the
+    not built refuses loudly instead of silently doing something else: training with fewer than 32 compressed channels, seg DiscoNet, the
     seg models' kd_flag outputs, and a When2com in .train() asked for the gated inference pass (training=False)."""
     from coperception.models.det import MeanFusion, When2com
     from coperception.models.seg import DiscoNet as SegDiscoNet
@@ -60,7 +60,8 @@ def test_train_mode_is_refused_where_not_built():
     args = (torch.zeros((5, 1, 256, 256, 13), device="cuda"), torch.zeros((1, 5, 5, 4, 4), device="cuda"),
             torch.full((1, 5), 5, device="cuda"))
     with pytest.raises(NotImplementedError):
-        MeanFusion(default_det_config(), layer=3, kd_flag=0, num_agent=5, compress_level=2).cuda().train()(*args, batch_size=1)
+        # (compress_level 1..3 trains since the compresser pair went on the tape; 4 leaves 16 channels, below the 32 it takes)
+        MeanFusion(default_det_config(), layer=3, kd_flag=0, num_agent=5, compress_level=4).cuda().train()(*args, batch_size=1)
     with pytest.raises(NotImplementedError):
         When2com(default_det_config(), layer=3, warp_flag=1, num_agent=5).cuda().train()(*args, training=False, batch_size=1)
     for kd in (True, False):     # seg DiscoNet: the train step exists (Tape.disco_fuse) but measured a cosine of 0.9985 on the
