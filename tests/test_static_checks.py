@@ -107,3 +107,17 @@ def test_every_library_entry_point_named_in_python_is_declared():
             if m.group(1) not in table and not m.group(1).startswith(allowed_prefixes):
                 stray.add((m.group(1), os.path.relpath(f, ROOT)))
     assert not stray, sorted(stray)
+
+
+def test_gpu_suite_refusal_cases_pass_under_the_cpu_dry_run():
+    """tools/gpu_suite_dryrun.py runs GPU test files on the CPU with every kernel a no-op.  The cases that assert a REFUSAL
+    launch no kernel, so they must pass outright there -- a feature that starts to run what a GPU test expects to be
+    refused (compressed training did) shows up here instead of stopping the round-end GPU run."""
+    import subprocess
+    import sys
+    sel = ["tests/test_gpu_dropin.py::test_train_mode_is_refused_where_not_built",
+           "tests/test_gpu_zz_options.py::test_when2com_refuses_what_the_reference_cannot_run",
+           "tests/test_gpu_zz_options.py::test_training_refuses_fewer_than_32_compressed_channels"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_suite_dryrun.py")] + sel, cwd=ROOT,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "3 passed" in r.stdout and "NON-NUMERIC failures: 0" in r.stdout, r.stdout[-2000:]
