@@ -3,6 +3,9 @@ the failures that are NOT numeric: exceptions other than AssertionError, and "DI
 construction (outputs are uninitialised memory) and are only counted.
 
 Usage: python tools/gpu_suite_dryrun.py [pytest selection ...]      (default: every tests/test_gpu_*.py)
+Run it per file: the whole suite takes over an hour on 8 cores (every case computes its CPU oracle), and
+test_gpu_nets.py::test_v2vnet_map_parity_planted must be deselected (-k "not map_parity"): its CPU NMS over
+uninitialised scores does not terminate in useful time.
 Exit status 1 if a non-numeric failure was found."""
 import glob
 import os
@@ -28,6 +31,8 @@ def main():
         msg = msg or ""
         if any(k in node for k in KNOWN):
             continue
+        if "DID NOT RAISE" in msg and "V2XError" in msg:
+            continue      # refusals that come from the real library's own checks (shared-memory fit, ...): the fake has none
         (numeric if msg.startswith(("assert", "AssertionError")) or msg == "" else other).append((node, msg))
     tail = [l for l in out.splitlines() if l.strip()][-1]
     print(tail)
