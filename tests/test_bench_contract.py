@@ -69,3 +69,26 @@ def test_measured_arm_other_configs(config):
     assert (BASE_KEYS | {"roofline", "clocks", "gpu_launches"}) <= set(d)
     assert d["value"] > 0 and 0 < d["e2e"]["value"] < d["value"] and d["e2e"]["h2d_bytes_per_step"] > 0
     assert 0 < d["roofline"]["frac"] < 1 and d["gpu_launches"] == d["kernels_per_step"] * 2
+
+
+def test_our_arm_executes_end_to_end_under_the_cpu_dry_run():
+    """tools/bench_dryrun.py: bench.py's own arm with kernels as no-ops.  Every key of the bench contract must be on the
+    one JSON line it prints (values are meaningless here; the B200 lines are under profiles/)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bench_dryrun.py"), "--steps", "2", "--warmup", "1",
+                        "--scenes", "1", "--no-cpu-baseline"], cwd=root, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["warmup"] >= 3 and d["config"]["workload"] and "model" not in d["config"]
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["gpu_launches"] == 27 * 2
