@@ -92,3 +92,26 @@ def test_our_arm_executes_end_to_end_under_the_cpu_dry_run():
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["gpu_launches"] == 27 * 2
+
+
+@pytest.mark.parametrize("extra", [[], ["--config", "w2c_det"]], ids=["v2v_det", "w2c_det"])
+def test_two_rank_launch_of_our_arm_under_the_cpu_dry_run(extra):
+    """The driver's N > 1 launch (torch.distributed.run, one rank per GPU) with kernels as no-ops and gloo in place of
+    NCCL: unit-sharded plan, per-step exchange, graph capture, barrier + max-over-ranks timing, ONE line from rank 0."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tools", "bench_dryrun.py"), "--gpus", "2", "--steps", "2",
+           "--warmup", "1", "--scenes", "2", "--no-cpu-baseline"] + extra
+    r = subprocess.run(cmd, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and "e2e" in d and "roofline" in d
