@@ -27,7 +27,7 @@ first_hardware_run = in_child_only      # the numerics cases below carry this ma
 
 GROUPS = ["test_when2com_det_options", "test_seg_when2com_options", "test_v2vnet_compressed_train_step_matches_oracle",
           "test_seg_unet_compressed_train_step_matches_oracle", "test_v2vnet_layer4", "test_sum_fusion_layer4"]
-CHILD_TIME_LIMIT_S = 600
+CHILD_TIME_LIMIT_S = 300      # a group takes 0.5 - 2 min; six groups bound the worst case at 30 min
 
 
 @pytest.mark.skipif(CHILD, reason="the parent-side launcher")
