@@ -120,12 +120,13 @@ class PlanCacheMixin:
         self._plans[key] = (fp, plan)
         while len(self._plans) > max(1, self.max_plans):
             self._plans.pop(next(iter(self._plans)))
-        self._static_ptrs = set()
-        for _, live in self._plans.values():
+        ptrs = set()
+        for _, live in list(self._plans.values()):       # (a snapshot: DataParallel replicas share this dict)
             for name in ("loc", "cls", "logits"):
                 t = getattr(live, name, None)
                 if isinstance(t, torch.Tensor):
-                    self._static_ptrs.add(t.data_ptr())
+                    ptrs.add(t.data_ptr())
+        self._static_ptrs = ptrs
         return plan
 
     def _plan_list(self):
